@@ -1,0 +1,217 @@
+/* geneevolve_b200.h — C-ABI of the B200-native GeneEvolve reproduction hot path.
+ *
+ * One shared library (libgeneevolve_b200.so, hand-written sm_100a CUDA) replaces the *bodies* of the
+ * private per-generation methods of the reference's `class Simulation`.  The reference has
+ * no plugin/FFI seam; the seam is cut at `Simulation::sim_next_generation` (src/Simulation.cpp:1890-2082)
+ * and the tail of `ras_init_generation0` (:529-679).  Every entry point below cites the reference
+ * interface it replaces.  All pointers are HOST pointers unless a name ends in `_dev`; sizes are explicit;
+ * no C++/torch types cross the boundary.  All functions return GE_OK (0) or a negative error code and
+ * leave a message retrievable with ge_last_error() — the reference's convention is `bool` + message on
+ * stdout + `return false` up to main (src/Main.cpp:84-88); the host shim maps non-zero to `return false`.
+ *
+ * Threading: like the reference, one host thread drives one context.  One context owns one GPU.
+ */
+#ifndef GENEEVOLVE_B200_H
+#define GENEEVOLVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GE_OK 0
+#define GE_ERR_INVALID -1      /* bad argument / call order */
+#define GE_ERR_CUDA -2         /* CUDA runtime failure (message has the CUDA error string) */
+#define GE_ERR_CAPACITY -3     /* a generation outgrew the capacity given at ge_create */
+#define GE_ERR_NO_MATES -4     /* "No one can marry" (:2125-2129) / "couples=0" (:2226-2230) */
+#define GE_ERR_NAN -5          /* A or D is NaN (:2716-2720) */
+#define GE_ERR_MIGRATION -6    /* migration row does not sum to 1 (:891-895) */
+#define GE_ERR_UNSUPPORTED -7  /* input outside what the bit-packed representation can express */
+
+/* representations of a chromosome (SURVEY.md §7.2 hard part 1) */
+#define GE_REP_BITS 1          /* bit-packed haplotypes, the HBM-bound throughput path */
+#define GE_REP_SEGMENTS 2      /* founder segments, the reference's own `class part` lists (src/Population.h:20-51) */
+
+/* where per-generation random draws come from */
+#define GE_RNG_PHILOX 0        /* Philox4x32-10 counter-based streams on the device (replaces RasRandomNumber) */
+#define GE_RNG_REPLAY 1        /* every draw is supplied by the caller (fixed-draw parity mode) */
+
+/* selection functions, Simulation::ras_selection_func (:3386-3428) */
+#define GE_SEL_DEFAULT 0       /* "" -> logit(0,1) */
+#define GE_SEL_LOGIT 1
+#define GE_SEL_PROBIT 2
+#define GE_SEL_STAB 3
+#define GE_SEL_THR 4
+
+typedef struct ge_ctx ge_ctx;
+
+/* ge_create: replaces the allocation side of ras_init_parameters (:164-525). */
+typedef struct ge_config {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t n_pop;           /* Simulation::_n_pop */
+    int32_t n_chr;           /* Population::_nchr (equal in all populations) */
+    int32_t n_phen;          /* Population::_pheno_scheme.size() */
+    int32_t vt_type;         /* Parameters::_vt_type: 1 = parents' phenotype, 2 = parents' F (:3122-3131) */
+    int32_t representation;  /* GE_REP_BITS | GE_REP_SEGMENTS (bit-or) */
+    int32_t rng_mode;        /* GE_RNG_PHILOX or GE_RNG_REPLAY */
+    int32_t reserved0;
+    uint64_t seed;           /* Parameters::_seed; Philox key */
+    uint64_t capacity;       /* max individuals per population in any generation */
+    uint64_t seg_capacity;   /* max segments per population per generation (GE_REP_SEGMENTS), 0 = auto */
+    int32_t rank;            /* shard of the offspring axis this context owns */
+    int32_t world_size;
+} ge_config;
+
+/* one row of the generation-info file, Population::ras_read_generation_info_file (src/Population.cpp:13-96) */
+typedef struct ge_gen_params {
+    uint64_t pop_size;       /* _pop_size[gen-1] */
+    double mat_cor;          /* _mat_cor[gen-1] */
+    int32_t offspring_dist;  /* 'p' or 'f' (_offspring_dist[gen-1]) */
+    int32_t selection_func;  /* GE_SEL_* (_selection_func[gen-1]) */
+    double selection_par1;
+    double selection_par2;
+} ge_gen_params;
+
+/* Draws of one population for one generation (fixed-draw parity mode, or exported after a Philox
+ * generation).  Slot order is the reference's loop order in Simulation::reproduce (:2433-2488):
+ * offspring i, chromosome c, gamete g (0 = from the father, 1 = from the mother) -> (i*n_chr + c)*2 + g. */
+typedef struct ge_draws {
+    uint64_t n_offspring;
+    const uint64_t *father;     /* [n_offspring] position of the father in the parent generation (Couples_Info::pos_male) */
+    const uint64_t *mother;     /* [n_offspring] */
+    const uint8_t *sex;         /* [n_offspring] 1 = male, 2 = female (:2472) */
+    const uint64_t *xo_off;     /* [n_offspring*n_chr*2 + 1] CSR offsets into xo_bp */
+    const uint64_t *xo_bp;      /* crossover positions in bp, ras_sim_loc_rec's list WITHOUT its two sentinels (:2983,:2993) */
+    const uint8_t *start_hap;   /* [n_offspring*n_chr*2] starting haplotype (:2449,:2455) */
+    const uint64_t *mut_off;    /* [n_offspring*n_chr + 1] CSR offsets into mut_bp, or NULL (no mutation map) */
+    const uint64_t *mut_bp;     /* mutation positions in bp (:2519) */
+    const uint8_t *mut_gam;     /* 0 = paternal gamete, 1 = maternal (:2521) */
+    const double *e_raw;        /* [n_phen][n_offspring] N(0,1) environment draws (:3102), or NULL */
+    const double *common;       /* [n_phen][n_offspring] sibling-common effect per offspring (:2481-2484), or NULL */
+    const double *parental0;    /* [n_phen][n] generation-0 parental effect N(0,vf) (:3108-3114); read by ge_init_generation0 only */
+} ge_draws;
+
+/* per-individual arrays, the columns of the `.info` file (Population::ras_save_human_info,
+ * src/Population.cpp:510-568).  Caller allocates for ge_get_population_size() individuals. */
+typedef struct ge_indiv_soa {
+    uint64_t *ids;   /* [n][7] ID, ID_Father, ID_Mother, ID_Fathers_Father, ID_Fathers_Mother, ID_Mothers_Father, ID_Mothers_Mother */
+    uint8_t *sex;    /* [n] */
+    double *A, *D, *G, *C, *E, *F, *P; /* each [n_phen][n] */
+    double *mv, *sv, *svf;             /* each [n] mating_value, selection_value, selection_value_func */
+} ge_indiv_soa;
+
+/* the `.summary` row (Simulation::ras_save_res :782-834) */
+typedef struct ge_moments {
+    double var_A, var_D, var_G, var_C, var_E, var_F, var_P, h2;
+} ge_moments;
+
+const char *ge_last_error(void);
+int ge_version(void);
+
+int ge_create(const ge_config *cfg, ge_ctx **out);
+int ge_destroy(ge_ctx *ctx);
+
+/* ---- inputs: already-parsed flat arrays; the host keeps its text readers (SURVEY.md §5 "config") ---- */
+
+/* Population flags set in ras_init_parameters (:205-214): _avoid_inbreeding, _RM, _MM_percent. */
+int ge_set_population(ge_ctx *ctx, int pop, int avoid_inbreeding, int random_mating, double mm_percent);
+/* rMap + _recom_prob of one chromosome (src/Population.h:183-189, src/Population.cpp:349-414, 471-507). */
+int ge_set_genetic_map(ge_ctx *ctx, int pop, int chr, const uint64_t *bp, const double *recom_prob,
+                       uint64_t n_rows, uint64_t bp_dist_in_rmap);
+/* MutationMap of one chromosome (src/Population.h:192-197, src/Population.cpp:420-468). */
+int ge_set_mutation_map(ge_ctx *ctx, int pop, int chr, const uint64_t *bp, const double *rate, uint64_t n_rows);
+/* Legend::pos of one chromosome (src/format_hap.h:19-26); shared by all populations (:1186-1230 indexes
+ * every population's panel by the same SNP index).  Must be sorted ascending. */
+int ge_set_loci(ge_ctx *ctx, int chr, const uint64_t *pos, uint64_t n_loci);
+/* Hap_SNP of one population and chromosome (src/format_hap.h:28-32): alleles[h*n_loci + s] in {0,1},
+ * hap-major exactly like Hap_SNP::hap.  Packed to bits on the device. */
+int ge_set_founder_panel(ge_ctx *ctx, int pop, int chr, const uint8_t *alleles, uint64_t n_founder_haps);
+/* CV_INFO + CV of one phenotype and chromosome (src/Population.h:201-220, src/Population.cpp:197-343). */
+int ge_set_cv(ge_ctx *ctx, int pop, int phen, int chr, const uint64_t *bp, const double *a, const double *d,
+              uint64_t n_cv, const uint8_t *founder_cv, uint64_t n_founder_haps);
+/* Phenotype_scheme (src/Population.h:223-234). */
+int ge_set_pheno_scheme(ge_ctx *ctx, int pop, int phen, double va, double vd, double ve, double vc, double vf,
+                        double omega, double beta, double lambda);
+/* Simulation::_gamma (:503-508). */
+int ge_set_gamma(ge_ctx *ctx, const double *gamma /* [n_phen] */);
+
+/* ---- generation 0: Simulation::ras_init_generation0 (:529-679) + ras_initial_human_gen0 (:3000-3072) ----
+ * draws0[pop] (GE_RNG_REPLAY) carries sex, e_raw, common for the founders; NULL in GE_RNG_PHILOX mode. */
+int ge_init_generation0(ge_ctx *ctx, const ge_draws *draws0 /* [n_pop] or NULL */);
+
+/* ---- the per-generation seam, one entry point per private method of Simulation (src/Simulation.h:71-128) ---- */
+
+/* bool random_mate(int ipop,int gen_ind) :2090-2157 / bool assort_mate(int ipop,int gen_ind) :2167-2360.
+ * Chooses by the population's random_mating flag like sim_next_generation (:1907-1918). */
+int ge_mate(ge_ctx *ctx, int pop, int gen, const ge_gen_params *params);
+/* Population::_couples_info (src/Population.h:165-180): supply (replay) or read back the couples. */
+int ge_set_couples(ge_ctx *ctx, int pop, const uint64_t *pos_male, const uint64_t *pos_female,
+                   const uint8_t *inbreed, const int32_t *num_offspring, uint64_t n_couples);
+int ge_get_couples_count(ge_ctx *ctx, int pop, uint64_t *n_couples);
+int ge_get_couples(ge_ctx *ctx, int pop, uint64_t *pos_male, uint64_t *pos_female, uint8_t *inbreed,
+                   int32_t *num_offspring);
+/* std::vector<Human> reproduce(int ipop,int gen_num) :2394-2493 with ras_sim_loc_rec :2973-2995,
+ * recombine :2903-2958, ras_add_mutation :2497-2552.  draws == NULL -> Philox. */
+int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *draws);
+/* bool ras_compute_AD(int ipop,int gen_num) :2624-2749 with ras_find_cv :2752-2815. */
+int ge_compute_AD(ge_ctx *ctx, int pop, int gen);
+/* bool ras_scale_AD_compute_GEF(int gen_num,int ipop,int iphen,double,double) :3075-3206.
+ * e_raw: [n] N(0,1) draws for replay, NULL -> Philox (or the draws given to ge_reproduce). */
+int ge_scale_AD_compute_GEF(ge_ctx *ctx, int pop, int gen, int phen, const double *e_raw);
+/* bool sim_environmental_effects_specific_to_each_population(int iphen) :3345-3381 (all populations). */
+int ge_environmental_effects_specific_to_each_population(ge_ctx *ctx, int phen);
+/* bool ras_compute_mating_value_selection_value(int gen_num,int ipop) :3300-3342. */
+int ge_compute_mating_value_selection_value(ge_ctx *ctx, int pop, int gen, const ge_gen_params *params);
+/* bool ras_do_migration(int gen_ind) :877-989; row = migration_mat_gen[gen-1], n_pop*n_pop entries. */
+int ge_do_migration(ge_ctx *ctx, int gen, const double *migration_row);
+/* bool ras_save_human_info_to_Pop_info_prev_gen(int ipop) :3211-3236. */
+int ge_save_human_info_to_Pop_info_prev_gen(ge_ctx *ctx, int pop);
+
+/* bool sim_next_generation(int gen_num) :1890-2082 — all of the above in the reference's order for every
+ * population.  params: [n_pop]; migration_row: n_pop*n_pop or NULL; draws: [n_pop] or NULL. */
+int ge_step_generation(ge_ctx *ctx, int gen, const ge_gen_params *params, const double *migration_row,
+                       const ge_draws *draws);
+
+/* ---- results back to the host writers ---- */
+int ge_get_population_size(ge_ctx *ctx, int pop, uint64_t *n);
+int ge_download_individuals(ge_ctx *ctx, int pop, ge_indiv_soa *out);
+/* var() of each column like the per-generation report (:2014-2055, src/CommFunc.cpp:57-68) */
+int ge_get_moments(ge_ctx *ctx, int pop, int phen, ge_moments *out);
+int ge_get_mv_sv_var(ge_ctx *ctx, int pop, double *var_mv, double *var_sv);
+/* scaling constants: _var_a_gen0, _var_d_gen0, adjusted _beta, _gen0_SV_mean, _gen0_SV_var */
+int ge_get_gen0_constants(ge_ctx *ctx, int pop, int phen, double *var_a0, double *var_d0, double *beta,
+                          double *sv_mean0, double *sv_var0);
+/* Haplotypes of one chromosome as the reference's Hap_SNP matrix (ras_convert_interval_to_hap_matrix
+ * :1186-1230): alleles[(2*i+h)*n_loci + s] in {0,1}.  Works in both representations. */
+int ge_download_haplotypes(ge_ctx *ctx, int pop, int chr, uint8_t *alleles);
+/* Same, bit-packed: words_per_hap = ceil(n_loci/32) little-endian bit order (locus s -> word s/32, bit s%32). */
+int ge_download_haplotypes_packed(ge_ctx *ctx, int pop, int chr, uint32_t *words);
+/* Founder segments of one chromosome, the `.int` content (ras_write_hap_to_interval_format :1582-1639).
+ * seg_off: [2*n + 1] in (individual, haplotype) order; seg: [n_seg][4] = st, en, hap_index, root_population. */
+int ge_get_segment_count(ge_ctx *ctx, int pop, int chr, uint64_t *n_seg, uint64_t *n_mut);
+int ge_download_segments(ge_ctx *ctx, int pop, int chr, uint64_t *seg_off, uint64_t *seg,
+                         uint64_t *mut_off /* [2*n+1] per haplotype */, uint64_t *mut_bp);
+/* Causal-variant alleles, the `--debug` .cvval dump (:2665-2683): out[(i*2+h)*n_cv + k]. */
+int ge_download_cv_alleles(ge_ctx *ctx, int pop, int phen, int chr, uint8_t *out);
+/* Draws the device generated for the last ge_reproduce of this population (GE_RNG_PHILOX): sizes first,
+ * then the arrays (any pointer may be NULL to skip). */
+int ge_get_draw_counts(ge_ctx *ctx, int pop, uint64_t *n_offspring, uint64_t *n_xo, uint64_t *n_mut);
+int ge_download_draws(ge_ctx *ctx, int pop, uint64_t *father, uint64_t *mother, uint8_t *sex, uint64_t *xo_off,
+                      uint64_t *xo_bp, uint8_t *start_hap, uint64_t *mut_off, uint64_t *mut_bp, uint8_t *mut_gam);
+
+/* ---- measurement hooks (bench.py): CUDA-event time of the dominant kernel on the library's stream ---- */
+#define GE_KERNEL_PROPAGATE_BITS 0
+#define GE_KERNEL_RECOMBINE_SEGMENTS 1
+#define GE_KERNEL_COUNT 8
+int ge_set_profiling(ge_ctx *ctx, int enabled);
+int ge_get_kernel_time(ge_ctx *ctx, int kernel, double *total_ms, uint64_t *launches, uint64_t *algorithmic_bytes);
+int ge_reset_kernel_times(ge_ctx *ctx);
+int ge_get_launch_count(ge_ctx *ctx, uint64_t *launches);   /* every kernel this context launched */
+int ge_synchronize(ge_ctx *ctx);
+int ge_device_memory_bytes(ge_ctx *ctx, uint64_t *bytes);    /* device high-water mark (SURVEY.md §5 memory reporting) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

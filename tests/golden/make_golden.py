@@ -152,7 +152,8 @@ def main():
             ["--va", "0.5", "--vd", "0", "--ve", "0.4", "--vc", "0.1", "--vf", "0.05", "--avoid_inbreeding"], 31337)
 
         # D. two populations with migration (≤ 1 non-zero off-diagonal entry per row),
-        #    population-specific environmental shift (--gamma), vt_type 1
+        #    population-specific environmental shift (--gamma).  vf = 0: with migration the reference reads
+        #    _Pop_info_prev_gen out of bounds for the parental effect (parent ID vs. position, :3118-3133)
         rng = np.random.default_rng(404)
         d1 = write_inputs(d, rng, tag="D1", chrs=[1, 2], n_founders=30, n_snp=90, n_cv=6, n_phen=1,
                           map_rows=20, map_step=50, p_row=0.05)
@@ -160,7 +161,7 @@ def main():
         # its own founders and effect sizes: reuse the rng-independent layout by regenerating with same seed
         rng2 = np.random.default_rng(404)
         d2 = write_inputs(d, rng2, tag="D2", chrs=[1, 2], n_founders=30, n_snp=90, n_cv=6, n_phen=1,
-                          map_rows=20, map_step=50, p_row=0.05, cv_scale=1.0)
+                          map_rows=20, map_step=50, p_row=0.05, cv_scale=1.7)
         # different founder alleles for population 2: rewrite hap + cv hap files with flipped random bits
         rng3 = np.random.default_rng(405)
         for cc in [1, 2]:
@@ -180,8 +181,8 @@ def main():
         with open(f"{d}/D.mig", "w") as f:
             for _ in range(4):
                 f.write("0.9 0.1 0.2 0.8\n")
-        run("D_two_pops", ["--file_gen_info", f"{d}/D1.gen"] + d1 + ["--va", "0.5", "--vd", "0", "--ve", "0.5", "--vf", "0.1"] +
-            ["--next_population", "--file_gen_info", f"{d}/D2.gen"] + d2 + ["--va", "0.5", "--vd", "0", "--ve", "0.5", "--vf", "0.1"] +
+        run("D_two_pops", ["--file_gen_info", f"{d}/D1.gen"] + d1 + ["--va", "0.5", "--vd", "0", "--ve", "0.5"] +
+            ["--next_population", "--file_gen_info", f"{d}/D2.gen"] + d2 + ["--va", "0.5", "--vd", "0", "--ve", "0.5"] +
             ["--file_migration", f"{d}/D.mig", "--gamma", "0.2"], 99)
 
 
