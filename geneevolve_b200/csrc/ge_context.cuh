@@ -1,0 +1,254 @@
+// ge_context.cuh — device context of libgeneevolve_b200.so: growable device buffers, per-population
+// generation state (double-buffered), genome layout, scratch and the error plumbing shared by the
+// translation unit (ge_api.cu includes the kernel headers around this file).
+#pragma once
+#include "../../include/geneevolve_b200.h"
+#include "ge_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace gek;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &m) { g_err = m; return code; }
+
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) return fail(GE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define GE_TRY(expr) do { int rc_ = (expr); if (rc_ != GE_OK) return rc_; } while (0)
+
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+// ------------------------------------------------------------------------------------------------
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct SegState {   // founder segments of one generation (GE_REP_SEGMENTS): CSR over slots (i*n_chr + c)*2 + h
+    Buf off, seg;   // off: uint64 [n_slots+1]; seg: uint4 {st, en, hap_index, root_population}
+    uint64_t n_seg = 0;
+    bool valid = false;
+};
+struct MateScratch {  // scratch of the mating kernels (ge_mating.cuh)
+    Buf fam_off, keep, keys_a, keys_b, idx_a, idx_b, list_m, list_f, t1, t2, rank1, rank2, tmp_sort, counters, mv_m, mv_f;
+};
+
+struct Scheme { double va = 0, vd = 0, ve = 0, vc = 0, vf = 0, omega = 0, beta = 0, lambda = 0; };
+
+struct CvHost {  // one (phen, chr) block of one population
+    std::vector<uint64_t> bp;
+    std::vector<double> a, d;
+    std::vector<uint8_t> val;
+    uint64_t nhap = 0;
+};
+
+struct GenState {  // one generation of one population on the device
+    uint64_t n = 0;
+    Buf hap, cv_allele, cv_root, ids, sex, A, D, G, C, E, F, P, mv, sv, svf;
+    Buf hm_off, hm_bp;  // per-haplotype mutation lists (CSR over slots)
+    uint64_t n_hm = 0;
+    bool has_hm = false;
+    SegState seg;       // founder segments (GE_REP_SEGMENTS)
+};
+
+struct PopDev {
+    bool avoid_inbreeding = false, RM = false, has_mut = false;
+    double MM = 0;
+    std::vector<std::vector<uint64_t>> rmap_bp, mutmap_bp;
+    std::vector<std::vector<double>> recom_prob, mutmap_rate;
+    std::vector<uint64_t> bp_dist;
+    std::vector<std::vector<CvHost>> cv;  // [phen][chr]
+    std::vector<Scheme> scheme;
+    std::vector<std::vector<uint8_t>> panel;  // host copy until generation 0 is built
+    uint64_t n_founder_haps = 0;
+    // device maps
+    Buf d_row_off, d_bp, d_T, d_bp_dist, d_mrow_off, d_mbp, d_mT, d_cov_lo, d_cov_hi;
+    Buf d_omega, d_lambda, d_vd_zero;
+    GenState st[2];
+    int cur = 0;
+    Buf prev_P, prev_F;
+    uint64_t prev_n = 0;
+    // couples
+    Buf c_male, c_female, c_inbreed, c_noff;
+    uint64_t n_couples = 0;
+    // draws of the last reproduce
+    Buf father, mother, couple_of, xo_off, xo_bp, flips, start_hap, mut_off, mut_bp, mut_gam, e_raw, cnt32;
+    uint64_t n_off = 0, n_xo = 0, n_mut = 0;
+    bool have_couple_of = false, have_e_raw = false;
+    // constants
+    std::vector<double> var_a0, var_d0;
+    double sv_mean0 = 0, sv_var0 = 0;
+    Buf d_sv0;  // [2] mean, var on device
+    MateScratch mate;
+};
+
+struct KernelStat { double ms = 0; uint64_t launches = 0, bytes = 0; };
+
+struct ge_ctx {
+    ge_config cfg;
+    cudaStream_t stream = nullptr;
+    std::vector<PopDev> pop;
+    std::vector<std::vector<uint64_t>> loci;  // host positions per chromosome
+    std::vector<double> gamma;
+    Stream rng;
+    // genome layout
+    std::vector<uint32_t> chr_word_off, chr_nloci, locus_off;
+    uint32_t W = 0;
+    Buf d_chr_word_off, d_chr_nloci, d_locus_off, d_pos;
+    bool genome_ready = false;
+    // tile table
+    Buf d_tile_chr, d_tile_chunk0, d_tile_nchunk;
+    uint32_t n_tiles = 0;
+    // causal-variant set
+    std::vector<uint32_t> cv_block_off;  // [n_phen*n_chr+1]
+    uint32_t n_cv_tot = 0;
+    Buf d_cv_block_off, d_cv_bp, d_cv_chr, d_a_eff, d_d_eff, d_cv_count;
+    bool cv_ready = false;
+    // scratch
+    Buf scan_blocks, scan_total, partial, scalars, flags;
+    int n_sm = 148;
+    // stats
+    bool profiling = false;
+    KernelStat kstat[GE_KERNEL_COUNT];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    size_t mem_now = 0, mem_peak = 0;
+
+    bool bits() const { return cfg.representation & GE_REP_BITS; }
+    bool segs() const { return cfg.representation & GE_REP_SEGMENTS; }
+
+    int ensure(Buf &b, size_t bytes) {
+        if (bytes <= b.cap && b.p) return GE_OK;
+        if (bytes == 0) bytes = 16;
+        if (b.p) { cudaFree(b.p); mem_now -= b.cap; b.p = nullptr; b.cap = 0; }
+        size_t want = bytes + (bytes >> 3);  // a little slack so growing buffers do not reallocate every generation
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
+        if (e != cudaSuccess) return fail(GE_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        b.cap = want; mem_now += want; mem_peak = std::max(mem_peak, mem_now);
+        return GE_OK;
+    }
+    int ensure_exact(Buf &b, size_t bytes) {
+        if (bytes <= b.cap && b.p) return GE_OK;
+        if (b.p) { cudaFree(b.p); mem_now -= b.cap; b.p = nullptr; b.cap = 0; }
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMalloc(&b.p, bytes);
+        if (e != cudaSuccess) return fail(GE_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        b.cap = bytes; mem_now += bytes; mem_peak = std::max(mem_peak, mem_now);
+        return GE_OK;
+    }
+    void release(Buf &b) { if (b.p) { cudaFree(b.p); mem_now -= b.cap; } b.p = nullptr; b.cap = 0; }
+    template <class T> int upload(Buf &b, const std::vector<T> &v) {
+        GE_TRY(ensure(b, v.size() * sizeof(T)));
+        if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));  // v may be a temporary
+        return GE_OK;
+    }
+    Genome genome() const {
+        Genome g;
+        g.n_chr = cfg.n_chr; g.W = W;
+        g.chr_word_off = d_chr_word_off.as<uint32_t>(); g.chr_nloci = d_chr_nloci.as<uint32_t>();
+        g.locus_off = d_locus_off.as<uint32_t>(); g.pos = d_pos.as<uint32_t>();
+        return g;
+    }
+    CvSet cvset() const {
+        CvSet c;
+        c.n_chr = cfg.n_chr; c.n_phen = cfg.n_phen; c.n_cv_tot = n_cv_tot;
+        c.block_off = d_cv_block_off.as<uint32_t>(); c.bp = d_cv_bp.as<uint32_t>(); c.chr_of = d_cv_chr.as<uint32_t>();
+        return c;
+    }
+    TileTable tiles() const {
+        TileTable t;
+        t.n_items = n_tiles; t.chr = d_tile_chr.as<uint32_t>(); t.chunk0 = d_tile_chunk0.as<uint32_t>(); t.nchunk = d_tile_nchunk.as<uint32_t>();
+        return t;
+    }
+    MapDev rmap(const PopDev &P) const {
+        MapDev m; m.row_off = P.d_row_off.as<uint32_t>(); m.bp = P.d_bp.as<uint32_t>(); m.T = P.d_T.as<double>(); m.bp_dist = P.d_bp_dist.as<uint32_t>();
+        return m;
+    }
+    MapDev mmap(const PopDev &P) const {
+        MapDev m; m.row_off = P.d_mrow_off.as<uint32_t>(); m.bp = P.d_mbp.as<uint32_t>(); m.T = P.d_mT.as<double>(); m.bp_dist = nullptr;
+        return m;
+    }
+    int check_launch(const char *what) {
+        launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(GE_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+        return GE_OK;
+    }
+    // device exclusive scan: out[0..n] (n+1 entries), grand total also returned to the host when asked
+    int exclusive_scan(const uint32_t *in, uint64_t n, uint64_t *out, uint64_t *host_total) {
+        if (n == 0) {
+            CUDA_TRY(cudaMemsetAsync(out, 0, 8, stream));
+            if (host_total) *host_total = 0;
+            return GE_OK;
+        }
+        uint32_t nb = nblk(n, SCAN_THREADS * SCAN_ITEMS);
+        GE_TRY(ensure(scan_blocks, (size_t)nb * 8));
+        GE_TRY(ensure(scan_total, 8));
+        scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_blocks.as<uint64_t>());
+        GE_TRY(check_launch("scan_block_sums"));
+        scan_single_block_kernel<<<1, SCAN_THREADS, 0, stream>>>(scan_blocks.as<uint64_t>(), nb, scan_total.as<uint64_t>());
+        GE_TRY(check_launch("scan_single_block"));
+        scan_final_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_blocks.as<uint64_t>(), out);
+        GE_TRY(check_launch("scan_final"));
+        if (host_total) {
+            CUDA_TRY(cudaMemcpyAsync(host_total, scan_total.p, 8, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+        return GE_OK;
+    }
+    // mean (denominator n) or variance (two-pass, n-1) of a device column into a device scalar
+    int d_mean(const double *x, uint64_t n, double *out) {
+        int nb = (int)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n, 256)), 1024);
+        GE_TRY(ensure(partial, 1024 * 8));
+        moment_partial_kernel<<<nb, 256, 0, stream>>>(x, n, nullptr, 0, partial.as<double>());
+        GE_TRY(check_launch("moment_partial"));
+        moment_final_kernel<<<1, 32, 0, stream>>>(partial.as<double>(), nb, (double)n, out);
+        return check_launch("moment_final");
+    }
+    int d_var(const double *x, uint64_t n, double *out /* device */, double *mean_scratch /* device */) {
+        if (n <= 1) { CUDA_TRY(cudaMemsetAsync(out, 0, 8, stream)); return GE_OK; }
+        GE_TRY(d_mean(x, n, mean_scratch));
+        int nb = (int)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n, 256)), 1024);
+        moment_partial_kernel<<<nb, 256, 0, stream>>>(x, n, mean_scratch, 1, partial.as<double>());
+        GE_TRY(check_launch("moment_partial"));
+        moment_final_kernel<<<1, 32, 0, stream>>>(partial.as<double>(), nb, (double)(n - 1), out);
+        return check_launch("moment_final");
+    }
+    int h_var(const double *x, uint64_t n, double *host_out, double *host_mean = nullptr) {
+        GE_TRY(ensure(scalars, 64 * 8));
+        double *s = scalars.as<double>();
+        GE_TRY(d_var(x, n, s + 0, s + 1));
+        if (n <= 1) GE_TRY(d_mean(x, std::max<uint64_t>(n, 1), s + 1));
+        double h[2];
+        CUDA_TRY(cudaMemcpyAsync(h, s, 16, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        *host_out = h[0];
+        if (host_mean) *host_mean = h[1];
+        return GE_OK;
+    }
+    int check_flags(const char *where) {
+        int h[4];
+        CUDA_TRY(cudaMemcpyAsync(h, flags.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (h[0]) return fail(GE_ERR_NAN, std::string("Error: A or D is nan (") + where + ")");
+        if (h[1]) return fail(GE_ERR_INVALID, "parent ID outside the previous generation (the reference reads out of bounds here, :3118-3133)");
+        return GE_OK;
+    }
+};
+
+#define CHECK_CTX(ctx) if (!(ctx)) return fail(GE_ERR_INVALID, "null context")
+#define CHECK_POP(ctx, p) CHECK_CTX(ctx); if ((p) < 0 || (p) >= (ctx)->cfg.n_pop) return fail(GE_ERR_INVALID, "bad population index")
+#define CHECK_CHR(ctx, c) if ((c) < 0 || (c) >= (ctx)->cfg.n_chr) return fail(GE_ERR_INVALID, "bad chromosome index")
+#define CHECK_PHEN(ctx, f) if ((f) < 0 || (f) >= (ctx)->cfg.n_phen) return fail(GE_ERR_INVALID, "bad phenotype index")
+

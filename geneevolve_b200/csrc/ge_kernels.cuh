@@ -1,0 +1,709 @@
+// ge_kernels.cuh — hand-written sm_100a kernels of the GeneEvolve reproduction hot path.
+//
+// Everything here is HBM-bound integer/bit work or tiny fp64 reductions; there is no dense contraction, so
+// no tensor-core (tcgen05) path — see DESIGN.md §Kernels for the roofline that bounds each kernel.
+// Reference lines cited as :N are src/Simulation.cpp:N of MMesbahU/GeneEvolve.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gek {
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (replaces RasRandomNumber / std::minstd_rand0 / rand())
+// ------------------------------------------------------------------------------------------------
+enum Purpose : uint32_t {
+    P_THIN = 1, P_RM_PAIR = 2, P_TRIM = 3, P_TEMPLATE = 4, P_POISSON = 5, P_REMAINDER = 6, P_XO = 7, P_MUT = 8,
+    P_SEX = 9, P_ENOISE = 10, P_F0 = 11, P_COMMON = 12, P_MIGRATE = 13
+};
+
+struct Stream { uint32_t k0, k1; };
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                                       uint32_t c2, uint32_t c3, uint32_t w[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        uint32_t h0 = __umulhi(M0, c0), l0 = M0 * c0, h1 = __umulhi(M1, c2), l1 = M1 * c2;
+#else
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += W0; k1 += W1;
+    }
+    w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+
+__device__ __forceinline__ void draw(const Stream s, uint32_t purpose, int pop, int gen, uint64_t entity,
+                                     uint32_t sub, uint32_t block, uint32_t w[4]) {
+    uint32_t c3 = (purpose << 24) | ((uint32_t)pop << 20) | ((uint32_t)gen & 0xFFFFFu);
+    philox4x32_10(s.k0, s.k1, block, (uint32_t)entity, sub, c3, w);
+}
+
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {  // [0,1), 53 bits
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void normal2(const Stream s, uint32_t purpose, int pop, int gen, uint64_t entity,
+                                        uint32_t sub, double &z0, double &z1) {
+    uint32_t w[4];
+    draw(s, purpose, pop, gen, entity, sub, 0, w);
+    double u1 = 1.0 - u01(w[0], w[1]);
+    double u2 = u01(w[2], w[3]);
+    double r = sqrt(-2.0 * log(u1));
+    double th = 6.283185307179586476925286766559 * u2;
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// genome layout of one bit-packed haplotype row
+// ------------------------------------------------------------------------------------------------
+struct Genome {
+    int n_chr;
+    uint32_t W;                    // u32 words per haplotype row (multiple of 32 -> rows are 128 B aligned)
+    const uint32_t *chr_word_off;  // [n_chr] first word of each chromosome (multiple of 4 -> 16 B aligned)
+    const uint32_t *chr_nloci;     // [n_chr]
+    const uint32_t *locus_off;     // [n_chr+1] offsets into pos
+    const uint32_t *pos;           // concatenated locus positions (bp), ascending inside a chromosome
+};
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;  // first index with a[idx] >= key
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Crossover positions (bp) -> locus indices.  A locus s of chromosome c takes parental haplotype
+// start ^ (#{crossovers b <= pos[s]} & 1) (recombine :2903-2958 followed by materialisation :1186-1230), i.e.
+// the haplotype flips at locus index lower_bound(pos, b).  One thread per (offspring, chromosome, gamete) slot.
+__global__ void xo_to_flips_kernel(Genome g, uint64_t n_slots, const uint64_t *__restrict__ xo_off,
+                                   const uint32_t *__restrict__ xo_bp, uint32_t *__restrict__ flips) {
+    uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    int c = (int)((slot >> 1) % (uint64_t)g.n_chr);
+    const uint32_t *pos = g.pos + g.locus_off[c];
+    uint32_t nl = g.chr_nloci[c];
+    for (uint64_t e = xo_off[slot]; e < xo_off[slot + 1]; e++) flips[e] = lower_bound_u32(pos, nl, xo_bp[e]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE hot kernel: bit-packed haplotype propagation (G5 in SURVEY.md §8a)
+//   offspring row (i, g)  <-  alternating runs of the two haplotype rows of parent (father|mother)[i]
+// One CTA per offspring; its warps pull work items (gamete, chromosome tile) from a shared counter, so long
+// and short chromosomes balance.  Inside an item the control flow is warp-uniform: whole 16-byte chunks
+// between two crossovers are a pure LDG.128/STG.128 copy with 4 independent loads in flight per lane; the
+// (at most a few) chunks that contain a crossover are mask-merged from both parental rows.
+// Algorithmic HBM traffic: 2 bits read + 2 bits written per individual-locus = 0.5 byte.
+// ------------------------------------------------------------------------------------------------
+struct TileTable {
+    uint32_t n_items;          // items of ONE gamete; the CTA processes 2*n_items
+    const uint32_t *chr;       // [n_items]
+    const uint32_t *chunk0;    // [n_items] first 16 B chunk inside the chromosome
+    const uint32_t *nchunk;    // [n_items]
+};
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void warp_copy_chunks(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint32_t q, uint32_t qe, int lane) {
+    uint32_t c = q + lane;
+    for (; c + 96 < qe; c += 128) {
+        uint4 a = ld_stream(src + c), b = ld_stream(src + c + 32), d = ld_stream(src + c + 64), e = ld_stream(src + c + 96);
+        st_stream(dst + c, a); st_stream(dst + c + 32, b); st_stream(dst + c + 64, d); st_stream(dst + c + 96, e);
+    }
+    for (; c < qe; c += 32) st_stream(dst + c, ld_stream(src + c));
+}
+
+constexpr int PROP_THREADS = 256;
+constexpr int PROP_MAX_SMEM_FLIPS = 64;
+
+__global__ void __launch_bounds__(PROP_THREADS)
+propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, uint32_t *__restrict__ off_rows,
+                      const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+                      const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips,
+                      const uint8_t *__restrict__ start_hap, uint64_t off_first, uint32_t n_off) {
+    __shared__ uint32_t s_next;
+    __shared__ uint32_t s_flips[PROP_THREADS / 32][PROP_MAX_SMEM_FLIPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t oi = blockIdx.x; oi < n_off; oi += gridDim.x) {
+        const uint64_t i = off_first + oi;  // offspring index in the (possibly sharded) generation
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = 0;
+        __syncthreads();
+        const uint32_t pf = father[i], pm = mother[i];
+        for (;;) {
+            uint32_t item = 0;
+            if (lane == 0) item = atomicAdd(&s_next, 1u);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= 2 * tt.n_items) break;
+            const int gam = item >= tt.n_items;
+            const uint32_t it = gam ? item - tt.n_items : item;
+            const uint32_t c = tt.chr[it], q0 = tt.chunk0[it], q1 = q0 + tt.nchunk[it];
+            const uint64_t slot = (i * (uint64_t)g.n_chr + c) * 2 + gam;
+            const uint64_t e0 = xo_off[slot];
+            const uint32_t k = (uint32_t)(xo_off[slot + 1] - e0);
+            const uint32_t *fl;
+            if (k <= PROP_MAX_SMEM_FLIPS) {
+                __syncwarp();
+                for (uint32_t t = lane; t < k; t += 32) s_flips[warp][t] = flips[e0 + t];
+                __syncwarp();
+                fl = s_flips[warp];
+            } else fl = flips + e0;
+            const uint32_t woff = g.chr_word_off[c];
+            const uint32_t prow = gam ? pm : pf;
+            const uint4 *h0 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow) * g.W + woff);
+            const uint4 *h1 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow + 1) * g.W + woff);
+            uint4 *dst = reinterpret_cast<uint4 *>(off_rows + (uint64_t)(2 * i + gam) * g.W + woff);
+            // flips at or before the first locus of the tile only set the parity
+            uint32_t j = 0;
+            const uint32_t x0 = q0 << 7;
+            while (j < k && fl[j] <= x0) j++;
+            uint32_t cur = (start_hap[slot] ^ j) & 1u;
+            uint32_t q = q0;
+            while (q < q1) {
+                const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
+                const uint32_t qb = f >> 7;
+                if (j >= k || qb >= q1) { warp_copy_chunks(dst, cur ? h1 : h0, q, q1, lane); break; }
+                warp_copy_chunks(dst, cur ? h1 : h0, q, qb, lane);
+                // chunk qb holds one or more flips: merge both parental chunks under a 128-bit mask
+                // (mask bit = 1 -> haplotype 1).  A flip on the chunk's first locus gives bit offset 0.
+                if (lane == 0) {
+                    const uint4 a = ld_stream(h0 + qb), b = ld_stream(h1 + qb);
+                    const uint32_t fill = cur ? 0xFFFFFFFFu : 0u;
+                    uint32_t m0 = fill, m1 = fill, m2 = fill, m3 = fill;
+                    const uint32_t base = qb << 7;
+                    for (uint32_t jj = j; jj < k && fl[jj] < base + 128u; jj++) {
+                        const uint32_t r = fl[jj] - base;
+                        m0 ^= r < 32u ? 0xFFFFFFFFu << r : 0u;
+                        m1 ^= r <= 32u ? 0xFFFFFFFFu : (r < 64u ? 0xFFFFFFFFu << (r - 32u) : 0u);
+                        m2 ^= r <= 64u ? 0xFFFFFFFFu : (r < 96u ? 0xFFFFFFFFu << (r - 64u) : 0u);
+                        m3 ^= r <= 96u ? 0xFFFFFFFFu : 0xFFFFFFFFu << (r - 96u);
+                    }
+                    uint4 o;
+                    o.x = (a.x & ~m0) | (b.x & m0); o.y = (a.y & ~m1) | (b.y & m1);
+                    o.z = (a.z & ~m2) | (b.z & m2); o.w = (a.w & ~m3) | (b.w & m3);
+                    st_stream(dst + qb, o);
+                }
+                while (j < k && fl[j] < ((qb + 1) << 7)) { j++; cur ^= 1u; }
+                q = qb + 1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Founder panel (Hap_SNP bytes, hap-major) -> bit-packed generation-0 rows, masked to the covered range
+// [rmap.bp[0], rmap.bp[last]) (a locus outside it lies in no `part`, :3029-3034, and reads 0 at :1186-1230).
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_panel_kernel(const uint8_t *__restrict__ alleles, uint32_t n_rows, uint32_t n_loci,
+                                  const uint32_t *__restrict__ pos, uint32_t cov_lo, uint32_t cov_hi,
+                                  uint32_t *__restrict__ rows, uint32_t W, uint32_t woff) {
+    uint32_t nw = (n_loci + 31) >> 5;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n_rows * nw) return;
+    uint32_t r = (uint32_t)(t / nw), w = (uint32_t)(t % nw);
+    uint32_t v = 0;
+    for (uint32_t b = 0; b < 32; b++) {
+        uint32_t s = w * 32 + b;
+        if (s < n_loci) {
+            uint32_t p = pos[s];
+            if (p >= cov_lo && p < cov_hi && alleles[(uint64_t)r * n_loci + s]) v |= 1u << b;
+        }
+    }
+    rows[(uint64_t)r * W + woff + w] = v;
+}
+
+__global__ void unpack_rows_kernel(const uint32_t *__restrict__ rows, uint32_t W, uint32_t woff, uint32_t n_rows,
+                                   uint32_t n_loci, uint8_t *__restrict__ alleles) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n_rows * n_loci) return;
+    uint32_t r = (uint32_t)(t / n_loci), s = (uint32_t)(t % n_loci);
+    alleles[t] = (rows[(uint64_t)r * W + woff + (s >> 5)] >> (s & 31)) & 1u;
+}
+
+__global__ void gather_packed_chr_kernel(const uint32_t *__restrict__ rows, uint32_t W, uint32_t woff, uint32_t n_rows,
+                                         uint32_t nw, uint32_t *__restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n_rows * nw) return;
+    uint32_t r = (uint32_t)(t / nw), w = (uint32_t)(t % nw);
+    out[t] = rows[(uint64_t)r * W + woff + w];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Causal variants: a second, tiny locus set carried as byte planes (allele, root population) per haplotype.
+// Layout cv[(2*i+h) * n_cv_tot + k]; block (phen f, chromosome c) starts at cv_block_off[f*n_chr+c].
+// ------------------------------------------------------------------------------------------------
+struct CvSet {
+    int n_chr, n_phen;
+    uint32_t n_cv_tot;
+    const uint32_t *block_off;  // [n_phen*n_chr + 1]
+    const uint32_t *bp;         // [n_cv_tot] CV positions
+    const uint32_t *chr_of;     // [n_cv_tot]
+};
+
+// generation 0: allele = founder CV allele when covered, root = population (ras_find_cv :2752-2815)
+__global__ void cv_init_kernel(CvSet cs, const uint8_t *__restrict__ founder_cv /* [n_rows][n_cv_tot] */, uint32_t n_rows,
+                               const uint32_t *__restrict__ cov_lo, const uint32_t *__restrict__ cov_hi, uint8_t root,
+                               uint8_t *__restrict__ allele, uint8_t *__restrict__ rootp) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n_rows * cs.n_cv_tot) return;
+    uint32_t k = (uint32_t)(t % cs.n_cv_tot);
+    uint32_t c = cs.chr_of[k], p = cs.bp[k];
+    bool cov = p >= cov_lo[c] && p < cov_hi[c];
+    allele[t] = cov ? founder_cv[t] : 0;
+    if (rootp) rootp[t] = root;
+}
+
+// one thread per (offspring gamete row, CV): parity of the crossovers at or below the CV position
+__global__ void cv_propagate_kernel(CvSet cs, const uint8_t *__restrict__ par_allele, const uint8_t *__restrict__ par_root,
+                                    uint8_t *__restrict__ off_allele, uint8_t *__restrict__ off_root,
+                                    const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+                                    const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
+                                    const uint8_t *__restrict__ start_hap, uint64_t off_first, uint64_t n_off) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_off * 2 * cs.n_cv_tot) return;
+    uint32_t k = (uint32_t)(t % cs.n_cv_tot);
+    uint64_t row = t / cs.n_cv_tot;
+    uint64_t i = off_first + (row >> 1);
+    int gam = (int)(row & 1);
+    uint32_t c = cs.chr_of[k], p = cs.bp[k];
+    uint64_t slot = (i * (uint64_t)cs.n_chr + c) * 2 + gam;
+    int h = start_hap[slot];
+    for (uint64_t e = xo_off[slot]; e < xo_off[slot + 1]; e++) h ^= (xo_bp[e] <= p);
+    uint32_t parent = gam ? mother[i] : father[i];
+    uint64_t src = ((uint64_t)parent * 2 + (h & 1)) * cs.n_cv_tot + k;
+    uint64_t dst = (i * 2 + gam) * (uint64_t)cs.n_cv_tot + k;
+    off_allele[dst] = par_allele[src];
+    if (off_root) off_root[dst] = par_root[src];
+}
+
+// allele count per CV over the population (frq numerator, :2647-2663).  Tiles of 32 CVs x 512 rows: a warp
+// reads 32 consecutive bytes of one row (one sector), 8 warps stride the rows; one 64-bit atomic per CV and tile.
+__global__ void cv_count_tiled_kernel(const uint8_t *__restrict__ allele, uint64_t n_rows, uint32_t n_cv_tot, unsigned long long *__restrict__ count) {
+    __shared__ unsigned int sh[8][32];
+    uint32_t k = blockIdx.x * 32 + threadIdx.x;
+    uint64_t r0 = (uint64_t)blockIdx.y * 512, r1 = min(r0 + 512, n_rows);
+    unsigned int s = 0;
+    if (k < n_cv_tot)
+        for (uint64_t r = r0 + threadIdx.y; r < r1; r += 8) s += allele[r * n_cv_tot + k];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && k < n_cv_tot) {
+        unsigned int t = 0;
+        for (int y = 0; y < 8; y++) t += sh[y][threadIdx.x];
+        if (t) atomicAdd(&count[k], (unsigned long long)t);
+    }
+}
+
+// A and D per individual (ras_compute_AD :2686-2746): one warp per individual and phenotype; lanes stride
+// the CVs of a chromosome, warp-shuffle reduce, chromosomes added in ascending order like the reference.
+__global__ void genetic_value_kernel(CvSet cs, const uint8_t *__restrict__ allele, const uint8_t *__restrict__ rootp,
+                                     const unsigned long long *__restrict__ count, uint64_t n_count /* individuals in frq */,
+                                     const double *__restrict__ a_eff /* [n_pop][n_cv_tot] */, const double *__restrict__ d_eff,
+                                     const uint8_t *__restrict__ vd_zero /* [n_phen] */, uint64_t n, double *__restrict__ A,
+                                     double *__restrict__ D, double *__restrict__ Gv, int *__restrict__ nan_flag) {
+    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (wid >= n * cs.n_phen) return;
+    uint64_t i = wid % n;
+    int f = (int)(wid / n);
+    const uint8_t *al0 = allele + (i * 2) * (uint64_t)cs.n_cv_tot, *al1 = al0 + cs.n_cv_tot;
+    const uint8_t *r0 = rootp ? rootp + (i * 2) * (uint64_t)cs.n_cv_tot : nullptr, *r1 = rootp ? r0 + cs.n_cv_tot : nullptr;
+    double add = 0, dom = 0, bv = 0;
+    for (int c = 0; c < cs.n_chr; c++) {
+        uint32_t b0 = cs.block_off[f * cs.n_chr + c], b1 = cs.block_off[f * cs.n_chr + c + 1];
+        double Ac = 0, Dc = 0;
+        for (uint32_t k = b0 + lane; k < b1; k += 32) {
+            uint64_t o0 = r0 ? (uint64_t)r0[k] * cs.n_cv_tot + k : k, o1 = r1 ? (uint64_t)r1[k] * cs.n_cv_tot + k : k;
+            double a = (a_eff[o0] + a_eff[o1]) / 2;
+            double d = (d_eff[o0] + d_eff[o1]) / 2;
+            if (vd_zero[f]) d = 0;
+            unsigned t = al0[k] + al1[k];
+            double p = (double)count[k] / (double)(2 * n_count), q = 1 - p;
+            double alpha = a + d * (q - p);
+            Ac += ((double)t - 2 * p) * alpha;
+            double ct = t == 0 ? -2 * p * p : (t == 1 ? 2 * p * q : -2 * q * q);
+            Dc += ct * d;
+        }
+        for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
+        add += Ac; dom += Dc; bv += Ac + Dc;
+    }
+    if (lane == 0) {
+        A[(uint64_t)f * n + i] = add; D[(uint64_t)f * n + i] = dom; Gv[(uint64_t)f * n + i] = bv;
+        if (isnan(add) || isnan(dom)) *nan_flag = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp64 population moments: sum, then centred sum of squares (two-pass like CommFunc::var, src/CommFunc.cpp:57-68)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_reduce_sum(double v) {
+    __shared__ double sh[32];
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    if (threadIdx.x < 32) for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;  // valid in thread 0
+}
+// partial[blockIdx.x] = sum over this block's grid-stride slice of (x - *shift)^2 (pow2) or of x
+__global__ void moment_partial_kernel(const double *__restrict__ x, uint64_t n, const double *__restrict__ shift, int pow2, double *__restrict__ partial) {
+    double s = 0, mu = shift ? *shift : 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double v = x[i] - mu;
+        s += pow2 ? v * v : v;
+    }
+    s = block_reduce_sum(s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// out[0] = (sum of partials) / denom  — fixed order, one thread
+__global__ void moment_final_kernel(const double *__restrict__ partial, int n_partial, double denom, double *__restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < n_partial; i++) s += partial[i];
+        *out = denom > 0 ? s / denom : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phenotypes: ras_scale_AD_compute_GEF :3075-3206 (elementwise part) and MV/SV :3300-3342
+// ------------------------------------------------------------------------------------------------
+__global__ void enoise_kernel(Stream st, int pop, int gen, int f, uint64_t first, uint64_t n, double *__restrict__ e) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double z0, z1;
+    normal2(st, P_ENOISE, pop, gen, first + i, (uint32_t)f, z0, z1);
+    e[i] = z0;
+}
+__global__ void normal_scaled_kernel(Stream st, uint32_t purpose, int pop, int gen, int f, uint64_t first, uint64_t n, double sd, double *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double z0, z1;
+    normal2(st, purpose, pop, gen, first + i, (uint32_t)f, z0, z1);
+    out[i] = z0 * sd;
+}
+
+struct PhenoArgs {
+    double s_a, s_d, ve, vf, beta;
+    int gen, vt_type;
+    uint64_t n, prev_n;
+};
+__global__ void phenotype_kernel(PhenoArgs a, const double *__restrict__ e_raw, const double *__restrict__ var_e,
+                                 double *__restrict__ A, double *__restrict__ D, double *__restrict__ G, const double *__restrict__ Cc,
+                                 double *__restrict__ E, double *__restrict__ F, double *__restrict__ P,
+                                 const uint64_t *__restrict__ ids, const double *__restrict__ prev_P, const double *__restrict__ prev_F,
+                                 const double *__restrict__ f0, int *__restrict__ err_flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double s_ev = a.ve > 0 ? sqrt(*var_e / a.ve) : 0.0;
+    double e = s_ev > 0 ? e_raw[i] / s_ev : 0.0;
+    double av = A[i] / a.s_a;
+    double dv = a.s_d > 0 ? D[i] / a.s_d : 0.0;
+    double fv = 0.0;
+    if (a.vf > 0) {
+        if (a.gen == 0) fv = f0 ? f0[i] : 0.0;
+        else {
+            uint64_t idf = ids[i * 7 + 1], idm = ids[i * 7 + 2];
+            if (idf >= a.prev_n || idm >= a.prev_n) { *err_flag = 1; }
+            else {
+                const double *src = a.vt_type == 1 ? prev_P : prev_F;
+                fv = a.beta * (src[idf] + src[idm]);
+            }
+        }
+    }
+    E[i] = e; A[i] = av; D[i] = dv; G[i] = av + dv; F[i] = fv;
+    P[i] = av + dv + Cc[i] + e + fv;
+}
+
+__global__ void mv_sv_kernel(uint64_t n, int n_phen, const double *__restrict__ P, const double *__restrict__ omega,
+                             const double *__restrict__ lambda, double *__restrict__ mv, double *__restrict__ sv_raw) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double m = 0, s = 0;
+    for (int f = 0; f < n_phen; f++) { double p = P[(uint64_t)f * n + i]; m += omega[f] * p; s += lambda[f] * p; }
+    mv[i] = m; sv_raw[i] = s;
+}
+__global__ void selection_kernel(uint64_t n, int gen, int func, double par1, double par2, const double *__restrict__ mean0,
+                                 const double *__restrict__ var0, const double *__restrict__ sv_raw, double *__restrict__ sv, double *__restrict__ svf) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double z = sv_raw[i] - *mean0;
+    if (*var0 > 0) z = (sv_raw[i] - *mean0) / sqrt(*var0);
+    sv[i] = z;
+    double r = 1.0;
+    if (gen != 0) {  // ras_selection_func :3386-3428
+        if (func == 0) { double y = exp(0.0 + 1.0 * z); r = y / (1 + y); }
+        else if (func == 1) { double y = exp(par1 + par2 * z); r = y / (1 + y); }
+        else if (func == 2) r = .5 * (1 + erf((z - par1) / (sqrt(2.0) * par2)));
+        else if (func == 3) { const double pi = 3.1415926; double u = (z - par1) / par2; r = 1 / (sqrt(2.0 * pi) * par2) * exp(-0.5 * (u * u)); }
+        else if (func == 4) r = z <= par2 ? par1 : 1.0;
+    }
+    svf[i] = r;
+}
+__global__ void add_scalar_kernel(double *__restrict__ x, uint64_t n, double v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += v;
+}
+
+// pedigree of the offspring (:2471-2479)
+__global__ void pedigree_kernel(uint64_t first, uint64_t n_off, const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+                                const uint64_t *__restrict__ par_ids, uint64_t *__restrict__ ids) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_off) return;
+    uint64_t i = first + t;
+    const uint64_t *fa = par_ids + (uint64_t)father[i] * 7, *mo = par_ids + (uint64_t)mother[i] * 7;
+    uint64_t *d = ids + i * 7;
+    d[0] = i; d[1] = fa[0]; d[2] = mo[0]; d[3] = fa[1]; d[4] = fa[2]; d[5] = mo[1]; d[6] = mo[2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic exclusive scan of uint32 counts into uint64 offsets (block-level scans; three launches)
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;  // per thread -> 2048 per block
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t &total) {
+    __shared__ uint64_t wsum[SCAN_THREADS / 32];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t x = v;
+    for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        if (lane < SCAN_THREADS / 32) wsum[lane] = w;
+    }
+    __syncthreads();
+    uint64_t base = warp ? wsum[warp - 1] : 0;
+    total = wsum[SCAN_THREADS / 32 - 1];
+    return base + x - v;
+}
+__global__ void scan_block_sums_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ block_sums) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_THREADS * SCAN_ITEMS;
+    uint64_t s = 0;
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; if (i < n) s += in[i]; }
+    uint64_t total; block_exclusive_scan(s, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void scan_single_block_kernel(uint64_t *__restrict__ block_sums, uint32_t nb, uint64_t *__restrict__ grand_total) {
+    // serial over chunks of SCAN_THREADS entries; nb is small (n / 2048)
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b < nb; b += SCAN_THREADS) {
+        uint32_t i = b + threadIdx.x;
+        uint64_t v = i < nb ? block_sums[i] : 0, total;
+        uint64_t ex = block_exclusive_scan(v, total);
+        uint64_t c = carry;
+        if (i < nb) block_sums[i] = ex + c;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+__global__ void scan_final_kernel(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ block_sums, uint64_t *__restrict__ out) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_THREADS * SCAN_ITEMS;
+    uint64_t v[SCAN_ITEMS], s = 0;
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; v[k] = i < n ? in[i] : 0; s += v[k]; }
+    uint64_t total, ex = block_exclusive_scan(s, total);
+    uint64_t run = block_sums[blockIdx.x] + ex;
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; if (i < n) out[i] = run; run += v[k]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = run;  // total at out[n]
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox crossover / mutation sampling: exact skip-sampler over the survival table T[k] = prod_{i<k}(1-p_i)
+// (same law as one Bernoulli(p_j) per map row, ras_sim_loc_rec :2973-2995, one uniform per crossover)
+// ------------------------------------------------------------------------------------------------
+struct MapDev {
+    const uint32_t *row_off;  // [n_chr+1] offsets into bp (rows per chromosome)
+    const uint32_t *bp;       // concatenated map rows
+    const double *T;          // concatenated survival tables, chromosome c starts at row_off[c] + c (R_c + 1 entries)
+    const uint32_t *bp_dist;  // [n_chr]
+};
+__device__ __forceinline__ long long next_success(const double *T, uint32_t R, uint32_t j, double v) {
+    if (j >= R || !(T[R] < v)) return -1;
+    uint32_t lo = j, hi = R - 1;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (T[mid + 1] < v) hi = mid; else lo = mid + 1; }
+    return (long long)lo;
+}
+// one thread per slot; pass 0 counts (and writes start_hap), pass 1 writes positions
+template <bool FILL>
+__global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int gen, uint64_t slot_first, uint64_t n_slots,
+                                 uint32_t *__restrict__ count, const uint64_t *__restrict__ xo_off, uint32_t *__restrict__ xo_bp,
+                                 uint8_t *__restrict__ start_hap) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_slots) return;
+    uint64_t slot = slot_first + t;
+    uint64_t i = (slot >> 1) / (uint64_t)n_chr;
+    int c = (int)((slot >> 1) % (uint64_t)n_chr), gam = (int)(slot & 1);
+    uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
+    const double *T = m.T + r0 + c;
+    uint32_t j = 0, blk = 0, n = 0;
+    uint64_t o = FILL ? xo_off[slot] : 0;
+    for (;;) {
+        uint32_t w[4];
+        draw(st, P_XO, pop, gen, i, (uint32_t)(c * 2 + gam), blk, w);
+        if (blk == 0 && !FILL) start_hap[slot] = (uint8_t)(w[3] & 1u);
+        blk++;
+        if (j >= R) break;
+        double v = (1.0 - u01(w[0], w[1])) * T[j];
+        long long k = next_success(T, R, j, v);
+        if (k < 0) break;
+        if (FILL) xo_bp[o + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
+        n++;
+        j = (uint32_t)k + 1;
+    }
+    if (!FILL) count[slot] = n;
+}
+// mutations: one thread per (offspring, chromosome)
+template <bool FILL>
+__global__ void sample_mut_kernel(Stream st, MapDev m, int n_chr, int pop, int gen, uint64_t first, uint64_t n_items,
+                                  uint32_t *__restrict__ count, const uint64_t *__restrict__ mut_off, uint32_t *__restrict__ mut_bp,
+                                  uint8_t *__restrict__ mut_gam) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    uint64_t item = first + t;
+    uint64_t i = item / (uint64_t)n_chr;
+    int c = (int)(item % (uint64_t)n_chr);
+    uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
+    const double *T = m.T + r0 + c;
+    uint32_t j = 1, blk = 0, n = 0;
+    uint64_t o = FILL ? mut_off[item] : 0;
+    for (;;) {
+        if (j >= R) break;
+        uint32_t w[4];
+        draw(st, P_MUT, pop, gen, i, (uint32_t)c, blk++, w);
+        double v = (1.0 - u01(w[0], w[1])) * T[j];
+        long long k = next_success(T, R, j, v);
+        if (k < 0) break;
+        if (FILL) {
+            uint32_t s0 = m.bp[r0 + (uint32_t)k - 1], s1 = m.bp[r0 + (uint32_t)k];
+            mut_bp[o + n] = s0 + (uint32_t)(((uint64_t)w[2] * (uint64_t)(s1 - s0 + 1)) >> 32);
+            mut_gam[o + n] = (uint8_t)(w[3] & 1u);
+        }
+        n++;
+        j = (uint32_t)k + 1;
+    }
+    if (!FILL) count[item] = n;
+}
+__global__ void sex_kernel(Stream st, int pop, int gen, uint64_t first, uint64_t n, uint8_t *__restrict__ sex) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[4];
+    draw(st, P_SEX, pop, gen, first + i, 0, 0, w);
+    sex[first + i] = (uint8_t)((w[0] & 1u) + 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-haplotype mutation lists (the bit path's analogue of part::mutation_pos): inherit by crossover
+// parity, append this generation's hits, toggle a locus only on its first hit in the lineage (the reference
+// looks positions up with std::find, :1218-1222/:2770-2774, so repeated hits do not toggle back).
+// One thread per offspring slot; pass 0 counts, pass 1 fills + applies.
+// ------------------------------------------------------------------------------------------------
+struct MutArgs {
+    int n_chr;
+    uint64_t off_first, n_off;
+    const uint32_t *father, *mother;
+    const uint64_t *xo_off; const uint32_t *xo_bp; const uint8_t *start_hap;
+    const uint64_t *par_hm_off; const uint32_t *par_hm_bp;   // parent lists, slot (par*n_chr + c)*2 + h; may be null (empty)
+    const uint64_t *mut_off; const uint32_t *mut_bp; const uint8_t *mut_gam;  // this generation's hits per (i,c); may be null
+    const uint32_t *cov_lo, *cov_hi;                          // [n_chr]
+};
+__device__ __forceinline__ int parity_at(const MutArgs &a, uint64_t slot, uint32_t pos) {
+    int h = a.start_hap[slot];
+    for (uint64_t e = a.xo_off[slot]; e < a.xo_off[slot + 1]; e++) h ^= (a.xo_bp[e] <= pos);
+    return h & 1;
+}
+template <bool FILL>
+__global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *__restrict__ count, const uint64_t *__restrict__ hm_off,
+                                      uint32_t *__restrict__ hm_bp, uint32_t *__restrict__ off_rows, uint8_t *__restrict__ cv_allele) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_off * a.n_chr * 2) return;
+    uint64_t slot = a.off_first * a.n_chr * 2 + t;
+    uint64_t i = (slot >> 1) / (uint64_t)a.n_chr;
+    int c = (int)((slot >> 1) % (uint64_t)a.n_chr), gam = (int)(slot & 1);
+    uint32_t parent = gam ? a.mother[i] : a.father[i];
+    uint32_t n = 0;
+    uint64_t o = FILL ? hm_off[slot] : 0;
+    if (a.par_hm_off) {
+        for (int h = 0; h < 2; h++) {
+            uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2 + h;
+            for (uint64_t e = a.par_hm_off[ps]; e < a.par_hm_off[ps + 1]; e++) {
+                uint32_t m = a.par_hm_bp[e];
+                if (parity_at(a, slot, m) == h) { if (FILL) hm_bp[o + n] = m; n++; }
+            }
+        }
+    }
+    uint32_t n_inherited = n;
+    if (a.mut_off) {
+        uint64_t item = i * a.n_chr + c;
+        for (uint64_t e = a.mut_off[item]; e < a.mut_off[item + 1]; e++) {
+            if (a.mut_gam[e] != gam) continue;
+            uint32_t m = a.mut_bp[e];
+            if (m < a.cov_lo[c] || m >= a.cov_hi[c]) continue;
+            if (FILL) {
+                bool seen = false;
+                for (uint32_t q = 0; q < n; q++) if (hm_bp[o + q] == m) { seen = true; break; }
+                hm_bp[o + n] = m;
+                if (!seen) {
+                    if (off_rows) {
+                        const uint32_t *pos = g.pos + g.locus_off[c];
+                        uint32_t nl = g.chr_nloci[c];
+                        for (uint32_t s = lower_bound_u32(pos, nl, m); s < nl && pos[s] == m; s++)
+                            off_rows[(uint64_t)(2 * i + gam) * g.W + g.chr_word_off[c] + (s >> 5)] ^= 1u << (s & 31);
+                    }
+                    if (cv_allele) {
+                        for (int f = 0; f < cs.n_phen; f++)
+                            for (uint32_t k = cs.block_off[f * cs.n_chr + c]; k < cs.block_off[f * cs.n_chr + c + 1]; k++)
+                                if (cs.bp[k] == m) cv_allele[(i * 2 + gam) * (uint64_t)cs.n_cv_tot + k] ^= 1;
+                    }
+                }
+            }
+            n++;
+        }
+    }
+    (void)n_inherited;
+    if (!FILL) count[slot] = n;
+}
+
+// couples -> offspring (reproduce :2402-2406, :2432-2485): offsets by exclusive scan of the family sizes
+__global__ void family_size_kernel(uint64_t n_couples, const uint8_t *__restrict__ inbreed, const int32_t *__restrict__ noff, uint32_t *__restrict__ cnt) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_couples) cnt[k] = inbreed[k] ? 0u : (uint32_t)max(noff[k], 0);
+}
+__global__ void expand_couples_kernel(uint64_t n_couples, const uint64_t *__restrict__ off, const uint32_t *__restrict__ male,
+                                      const uint32_t *__restrict__ female, uint32_t *__restrict__ father, uint32_t *__restrict__ mother,
+                                      uint32_t *__restrict__ couple_of) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_couples) return;
+    for (uint64_t i = off[k]; i < off[k + 1]; i++) { father[i] = male[k]; mother[i] = female[k]; couple_of[i] = (uint32_t)k; }
+}
+__global__ void common_from_couples_kernel(Stream st, int pop, int gen, int f, double sd, uint64_t first, uint64_t n_off,
+                                           const uint32_t *__restrict__ couple_of, double *__restrict__ Cc) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_off) return;
+    double z0, z1;
+    normal2(st, P_COMMON, pop, gen, couple_of[first + t], (uint32_t)f, z0, z1);
+    Cc[first + t] = z0 * sd;
+}
+
+}  // namespace gek

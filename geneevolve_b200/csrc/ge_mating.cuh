@@ -1,0 +1,290 @@
+// ge_mating.cuh — parent-pair selection on the device: random_mate (:2090-2157) and assort_mate (:2167-2360)
+// under the Philox streams of DESIGN.md §RNG, and migration (:877-989).
+//
+// The reference has no fitness-weighted roulette wheel: selection is Bernoulli thinning of who may mate
+// (U_i < selection_value_func_i) followed by uniform index draws (random mating) or by pairing the males and
+// females, both sorted by mating value, through the ranks of a bivariate-normal template (assortative).
+// So the scans here are stream compaction and offspring-offset prefix sums.
+// Sorting (mating values, template values, trim keys; n <= N/2 elements, < 1 % of a generation) uses
+// cub::DeviceRadixSort, which is stable — that is what fixes the tie order the oracle also uses.
+#pragma once
+#include "ge_context.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace gek {
+
+__device__ __forceinline__ uint64_t key64(const uint32_t w[4]) { return ((uint64_t)w[0] << 32) | w[1]; }
+__device__ __forceinline__ uint64_t sortable(double x) {  // monotone map double -> uint64
+    if (x == 0.0) x = 0.0;  // -0.0 and +0.0 compare equal
+    uint64_t b = (uint64_t)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// thinning (:2105-2117 / :2186-2216): number of list entries individual i contributes, split by sex
+__global__ void thin_count_kernel(Stream st, int pop, int gen, uint64_t n, const uint8_t *__restrict__ sex, const double *__restrict__ svf,
+                                  int with_mm, double mm, uint32_t *__restrict__ cnt_m, uint32_t *__restrict__ cnt_f) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[4];
+    draw(st, P_THIN, pop, gen, i, 0, 0, w);
+    double r = u01(w[0], w[1]), r2 = u01(w[2], w[3]);
+    uint32_t c = 0;
+    if (r < svf[i]) c = (with_mm && r2 < mm) ? 2u : 1u;
+    cnt_m[i] = sex[i] == 1 ? c : 0u;
+    cnt_f[i] = sex[i] == 2 ? c : 0u;
+}
+__global__ void thin_fill_kernel(uint64_t n, const uint64_t *__restrict__ off, uint32_t *__restrict__ list) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (uint64_t k = off[i]; k < off[i + 1]; k++) list[k] = (uint32_t)i;
+}
+__global__ void rm_pair_kernel(Stream st, int pop, int gen, uint64_t n_couples, const uint32_t *__restrict__ list_m, uint64_t n_m,
+                               const uint32_t *__restrict__ list_f, uint64_t n_f, uint32_t *__restrict__ male, uint32_t *__restrict__ female,
+                               uint8_t *__restrict__ inbreed, int32_t *__restrict__ noff) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_couples) return;
+    uint32_t w[4];
+    draw(st, P_RM_PAIR, pop, gen, k, 0, 0, w);
+    male[k] = list_m[((uint64_t)w[0] * n_m) >> 32];
+    female[k] = list_f[((uint64_t)w[1] * n_f) >> 32];
+    inbreed[k] = 0; noff[k] = 1;
+}
+__global__ void philox_keys_kernel(Stream st, uint32_t purpose, int pop, int gen, uint32_t sub, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t w[4];
+    draw(st, purpose, pop, gen, k, sub, 0, w);
+    keys[k] = key64(w); idx[k] = (uint32_t)k;
+}
+__global__ void mark_kernel(uint64_t n_mark, const uint32_t *__restrict__ sorted_idx, uint32_t *__restrict__ keep /* preset to 1 */) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_mark) keep[sorted_idx[k]] = 0;
+}
+__global__ void fill_u32_kernel(uint32_t *__restrict__ x, uint64_t n, uint32_t v) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) x[k] = v;
+}
+__global__ void compact_kernel(uint64_t n, const uint32_t *__restrict__ keep, const uint64_t *__restrict__ off, const uint32_t *__restrict__ in, uint32_t *__restrict__ out) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && keep[k]) out[off[k]] = in[k];
+}
+__global__ void mv_keys_kernel(uint64_t n, const uint32_t *__restrict__ list, const double *__restrict__ mv, uint64_t *__restrict__ keys) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) keys[k] = sortable(mv[list[k]]);
+}
+// bivariate-normal template (ras_mvnorm, src/RasRandomNumber.cpp:15-53, with U = [[1,rho],[0,sqrt(1-rho^2)]])
+__global__ void template_kernel(Stream st, int pop, int gen, uint64_t n, double rho, double u11, uint64_t *__restrict__ k1, uint64_t *__restrict__ k2, uint32_t *__restrict__ idx) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double z0, z1;
+    normal2(st, P_TEMPLATE, pop, gen, i, 0, z0, z1);
+    k1[i] = sortable(z0);
+    k2[i] = sortable(z0 * rho + z1 * u11);
+    idx[i] = (uint32_t)i;
+}
+__global__ void rank_scatter_kernel(uint64_t n, const uint32_t *__restrict__ sorted_idx, uint32_t *__restrict__ rank) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) rank[sorted_idx[k]] = (uint32_t)k;
+}
+// couple i = (male at rank(t1_i), female at rank(t2_i)) and the sib/cousin exclusion (:2296-2320)
+__global__ void pair_kernel(uint64_t n, const uint32_t *__restrict__ males, const uint32_t *__restrict__ females, const uint32_t *__restrict__ r1,
+                            const uint32_t *__restrict__ r2, const uint64_t *__restrict__ ids, int avoid_inbreeding, uint32_t *__restrict__ male,
+                            uint32_t *__restrict__ female, uint8_t *__restrict__ inbreed, uint32_t *__restrict__ inbreed_cnt) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t pm = males[r1[i]], pf = females[r2[i]];
+    male[i] = pm; female[i] = pf;
+    uint8_t ib = 0;
+    if (avoid_inbreeding) {
+        const uint64_t *a = ids + (uint64_t)pm * 7, *b = ids + (uint64_t)pf * 7;
+        bool sib = a[1] == b[1];
+        bool cousin = (a[3] == b[3] || a[3] == b[5] || a[5] == b[3] || a[5] == b[5] || a[4] == b[4] || a[4] == b[6] || a[6] == b[4] || a[6] == b[6]);
+        ib = sib || cousin;
+    }
+    inbreed[i] = ib;
+    inbreed_cnt[i] = ib;
+}
+// exact Poisson(lam): sum of independent Poisson(<=32) chunks, each by sequential-search inversion (ras_rpois, src/RasRandomNumber.cpp:57-67)
+__global__ void poisson_kernel(Stream st, int pop, int gen, uint64_t n, double lam, int32_t *__restrict__ noff) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int total = 0; uint32_t blk = 0; double rem = lam;
+    while (rem > 0) {
+        double l = rem > 32.0 ? 32.0 : rem;
+        rem -= l;
+        uint32_t w[4];
+        draw(st, P_POISSON, pop, gen, i, 0, blk++, w);
+        double u = u01(w[0], w[1]);
+        double pk = exp(-l), F = pk; int k = 0;
+        while (u >= F && k < 400) { k++; pk *= l / (double)k; F += pk; }
+        total += k;
+    }
+    noff[i] = total;
+}
+__global__ void fixed_family_kernel(uint64_t n, int32_t nfix, int32_t *__restrict__ noff) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) noff[i] = nfix;
+}
+__global__ void remainder_keys_kernel(Stream st, int pop, int gen, uint64_t n, const uint8_t *__restrict__ inbreed, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[4];
+    draw(st, P_REMAINDER, pop, gen, i, 0, 0, w);
+    keys[i] = inbreed[i] ? 0xFFFFFFFFFFFFFFFFull : key64(w);
+    idx[i] = (uint32_t)i;
+}
+__global__ void remainder_add_kernel(uint64_t n_add, const uint32_t *__restrict__ sorted_idx, const uint8_t *__restrict__ inbreed, int32_t *__restrict__ noff) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_add && !inbreed[sorted_idx[k]]) noff[sorted_idx[k]]++;
+}
+
+}  // namespace gek
+
+static void mate_release(MateScratch &m) {
+    for (Buf *b : {&m.fam_off, &m.keep, &m.keys_a, &m.keys_b, &m.idx_a, &m.idx_b, &m.list_m, &m.list_f, &m.t1, &m.t2, &m.rank1, &m.rank2,
+                   &m.tmp_sort, &m.counters, &m.mv_m, &m.mv_f})
+        if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+}
+
+// stable sort of (uint64 key, uint32 value) pairs: keys_in/vals_in -> keys_out/vals_out
+static int sort_pairs(ge_ctx *ctx, MateScratch &M, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n) {
+    if (n == 0) return GE_OK;
+    size_t bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 64, ctx->stream));
+    GE_TRY(ctx->ensure(M.tmp_sort, bytes));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(M.tmp_sort.p, bytes, kin, kout, vin, vout, (int)n, 0, 64, ctx->stream));
+    ctx->launches += 8;  // radix passes of the library sort (approximate, only for the launch counter)
+    return GE_OK;
+}
+
+// thinning + compaction of one sex list; returns list length on the host
+static int thin_lists(ge_ctx *ctx, int pop, int gen, bool with_mm, uint64_t *n_m, uint64_t *n_f) {
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    MateScratch &M = P.mate;
+    uint64_t n = S.n;
+    cudaStream_t st = ctx->stream;
+    GE_TRY(ctx->ensure(M.keep, (n + 1) * 4)); GE_TRY(ctx->ensure(M.rank1, (n + 1) * 4));  // cnt_m, cnt_f
+    GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8));  // offsets
+    thin_count_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->rng, pop, gen, n, S.sex.as<uint8_t>(), S.svf.as<double>(), with_mm, P.MM, M.keep.as<uint32_t>(), M.rank1.as<uint32_t>());
+    GE_TRY(ctx->check_launch("thin_count"));
+    GE_TRY(ctx->exclusive_scan(M.keep.as<uint32_t>(), n, M.keys_a.as<uint64_t>(), n_m));
+    GE_TRY(ctx->exclusive_scan(M.rank1.as<uint32_t>(), n, M.keys_b.as<uint64_t>(), n_f));
+    GE_TRY(ctx->ensure(M.list_m, std::max<uint64_t>(*n_m, 1) * 4)); GE_TRY(ctx->ensure(M.list_f, std::max<uint64_t>(*n_f, 1) * 4));
+    thin_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, M.keys_a.as<uint64_t>(), M.list_m.as<uint32_t>());
+    GE_TRY(ctx->check_launch("thin_fill"));
+    thin_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, M.keys_b.as<uint64_t>(), M.list_f.as<uint32_t>());
+    return ctx->check_launch("thin_fill");
+}
+
+static int ensure_couples(ge_ctx *ctx, PopDev &P, uint64_t n) {
+    GE_TRY(ctx->ensure(P.c_male, std::max<uint64_t>(n, 1) * 4)); GE_TRY(ctx->ensure(P.c_female, std::max<uint64_t>(n, 1) * 4));
+    GE_TRY(ctx->ensure(P.c_inbreed, std::max<uint64_t>(n, 1))); GE_TRY(ctx->ensure(P.c_noff, std::max<uint64_t>(n, 1) * 4));
+    return GE_OK;
+}
+
+// remove the n_remove entries with the smallest (Philox key, position); survivors keep their order (:2233-2246)
+static int trim_list(ge_ctx *ctx, int pop, int gen, Buf &list, uint64_t n, uint64_t n_remove, uint32_t sub) {
+    PopDev &P = ctx->pop[pop];
+    MateScratch &M = P.mate;
+    cudaStream_t st = ctx->stream;
+    GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8));
+    GE_TRY(ctx->ensure(M.idx_a, n * 4)); GE_TRY(ctx->ensure(M.idx_b, n * 4)); GE_TRY(ctx->ensure(M.keep, (n + 1) * 4));
+    philox_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->rng, P_TRIM, pop, gen, sub, n, M.keys_a.as<uint64_t>(), M.idx_a.as<uint32_t>());
+    GE_TRY(ctx->check_launch("trim_keys"));
+    GE_TRY(sort_pairs(ctx, M, M.keys_a.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n));
+    fill_u32_kernel<<<nblk(n, 256), 256, 0, st>>>(M.keep.as<uint32_t>(), n, 1u);
+    GE_TRY(ctx->check_launch("fill"));
+    mark_kernel<<<nblk(n_remove, 256), 256, 0, st>>>(n_remove, M.idx_b.as<uint32_t>(), M.keep.as<uint32_t>());
+    GE_TRY(ctx->check_launch("mark"));
+    GE_TRY(ctx->exclusive_scan(M.keep.as<uint32_t>(), n, M.keys_a.as<uint64_t>(), nullptr));
+    compact_kernel<<<nblk(n, 256), 256, 0, st>>>(n, M.keep.as<uint32_t>(), M.keys_a.as<uint64_t>(), list.as<uint32_t>(), M.idx_a.as<uint32_t>());
+    GE_TRY(ctx->check_launch("compact"));
+    CUDA_TRY(cudaMemcpyAsync(list.p, M.idx_a.p, (n - n_remove) * 4, cudaMemcpyDeviceToDevice, st));
+    return GE_OK;
+}
+
+// sort a list of individuals by mating value, ascending, stable (:2251-2252)
+static int sort_by_mv(ge_ctx *ctx, int pop, Buf &list, uint64_t n) {
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    MateScratch &M = P.mate;
+    GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8)); GE_TRY(ctx->ensure(M.idx_a, n * 4));
+    mv_keys_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, list.as<uint32_t>(), S.mv.as<double>(), M.keys_a.as<uint64_t>());
+    GE_TRY(ctx->check_launch("mv_keys"));
+    GE_TRY(sort_pairs(ctx, M, M.keys_a.as<uint64_t>(), M.keys_b.as<uint64_t>(), list.as<uint32_t>(), M.idx_a.as<uint32_t>(), n));
+    CUDA_TRY(cudaMemcpyAsync(list.p, M.idx_a.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return GE_OK;
+}
+
+static int mate_philox(ge_ctx *ctx, int pop, int gen, const ge_gen_params &gp) {
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    MateScratch &M = P.mate;
+    cudaStream_t st = ctx->stream;
+    uint64_t n_m = 0, n_f = 0;
+    if (S.n == 0) return fail(GE_ERR_INVALID, "empty population");
+    GE_TRY(thin_lists(ctx, pop, gen, !P.RM, &n_m, &n_f));
+    if (P.RM) {  // random_mate :2090-2157
+        if (n_m == 0 || n_f == 0) return fail(GE_ERR_NO_MATES, "Error: No one can marry, num_males_mate=" + std::to_string(n_m) + ", num_females_mate=" + std::to_string(n_f));
+        uint64_t nc = gp.pop_size;
+        GE_TRY(ensure_couples(ctx, P, nc));
+        rm_pair_kernel<<<nblk(nc, 256), 256, 0, st>>>(ctx->rng, pop, gen, nc, M.list_m.as<uint32_t>(), n_m, M.list_f.as<uint32_t>(), n_f, P.c_male.as<uint32_t>(),
+                                                      P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
+        GE_TRY(ctx->check_launch("rm_pair"));
+        P.n_couples = nc;
+        return GE_OK;
+    }
+    // assort_mate :2167-2360
+    uint64_t n2 = std::min(n_m, n_f);
+    if (n2 == 0) return fail(GE_ERR_NO_MATES, "Error: couples=0, num_males_mate=" + std::to_string(n_m) + ", num_females_mate=" + std::to_string(n_f));
+    if (n_m > n_f) GE_TRY(trim_list(ctx, pop, gen, M.list_m, n_m, n_m - n_f, 0));
+    else if (n_f > n_m) GE_TRY(trim_list(ctx, pop, gen, M.list_f, n_f, n_f - n_m, 1));
+    GE_TRY(sort_by_mv(ctx, pop, M.list_m, n2));
+    GE_TRY(sort_by_mv(ctx, pop, M.list_f, n2));
+    // template ranks
+    GE_TRY(ctx->ensure(M.t1, n2 * 8)); GE_TRY(ctx->ensure(M.t2, n2 * 8)); GE_TRY(ctx->ensure(M.idx_a, n2 * 4)); GE_TRY(ctx->ensure(M.idx_b, n2 * 4));
+    GE_TRY(ctx->ensure(M.keys_b, (n2 + 1) * 8)); GE_TRY(ctx->ensure(M.rank1, (n2 + 1) * 4)); GE_TRY(ctx->ensure(M.rank2, (n2 + 1) * 4));
+    double rho = gp.mat_cor, u11 = std::sqrt(1.0 - rho * rho);
+    template_kernel<<<nblk(n2, 256), 256, 0, st>>>(ctx->rng, pop, gen, n2, rho, u11, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>());
+    GE_TRY(ctx->check_launch("template"));
+    GE_TRY(sort_pairs(ctx, M, M.t1.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2));
+    rank_scatter_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, M.idx_b.as<uint32_t>(), M.rank1.as<uint32_t>());
+    GE_TRY(ctx->check_launch("rank_scatter"));
+    GE_TRY(sort_pairs(ctx, M, M.t2.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2));
+    rank_scatter_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, M.idx_b.as<uint32_t>(), M.rank2.as<uint32_t>());
+    GE_TRY(ctx->check_launch("rank_scatter"));
+    GE_TRY(ensure_couples(ctx, P, n2));
+    GE_TRY(ctx->ensure(M.keep, (n2 + 1) * 4)); GE_TRY(ctx->ensure(M.keys_a, (n2 + 1) * 8));
+    pair_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>(), M.rank1.as<uint32_t>(), M.rank2.as<uint32_t>(), S.ids.as<uint64_t>(),
+                                               P.avoid_inbreeding, P.c_male.as<uint32_t>(), P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), M.keep.as<uint32_t>());
+    GE_TRY(ctx->check_launch("pair"));
+    uint64_t n_inbreed = 0;
+    if (P.avoid_inbreeding) GE_TRY(ctx->exclusive_scan(M.keep.as<uint32_t>(), n2, M.keys_a.as<uint64_t>(), &n_inbreed));
+    if (n2 == n_inbreed) return fail(GE_ERR_NO_MATES, "every couple is inbred");
+    if (gp.offspring_dist == 'p' || gp.offspring_dist == 'P') {  // :2329-2337
+        double lam = (double)gp.pop_size / (double)(n2 - n_inbreed);
+        poisson_kernel<<<nblk(n2, 256), 256, 0, st>>>(ctx->rng, pop, gen, n2, lam, P.c_noff.as<int32_t>());
+        GE_TRY(ctx->check_launch("poisson"));
+    } else {  // :2338-2355
+        int nfix = (int)std::floor((double)gp.pop_size / (double)(n2 - n_inbreed));
+        uint64_t remain = gp.pop_size - (uint64_t)nfix * (n2 - n_inbreed);
+        fixed_family_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, nfix, P.c_noff.as<int32_t>());
+        GE_TRY(ctx->check_launch("fixed_family"));
+        if (remain) {
+            // the remainder goes to distinct random couples that may marry (the reference indexes an empty
+            // list here when --avoid_inbreeding is on, :2314-2353; this is its evident intent)
+            remainder_keys_kernel<<<nblk(n2, 256), 256, 0, st>>>(ctx->rng, pop, gen, n2, P.c_inbreed.as<uint8_t>(), M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>());
+            GE_TRY(ctx->check_launch("remainder_keys"));
+            GE_TRY(sort_pairs(ctx, M, M.t1.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2));
+            uint64_t n_add = std::min(remain, n2 - n_inbreed);
+            remainder_add_kernel<<<nblk(n_add, 256), 256, 0, st>>>(n_add, M.idx_b.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
+            GE_TRY(ctx->check_launch("remainder_add"));
+        }
+    }
+    P.n_couples = n2;
+    return GE_OK;
+}
+
+static int migrate(ge_ctx *, int, const double *) { return fail(GE_ERR_UNSUPPORTED, "device migration is not built yet"); }

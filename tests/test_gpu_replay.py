@@ -1,0 +1,65 @@
+"""Fixed-draw parity of the CUDA path (-m gpu): given the REAL reference's exported parent pairs,
+crossovers, start haplotypes, mutation hits, sex and N(0,1) draws (tests/golden/*.npz), the library must give
+bit-exact haplotypes / causal-variant alleles / pedigree and genetic values + phenotypes within 1e-9
+relative (north star: bit-exact integers, 1e-6 relative on genetic values) — every generation, through the
+C-ABI.  The CPU oracle runs alongside as a second checker."""
+import numpy as np
+import pytest
+
+from geneevolve_b200 import capi
+from golden_util import SCENARIOS, Golden
+from oracle.oracle import OracleEngine
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-9, 1e-11
+FLOAT_KEYS = ["A", "D", "G", "C", "E", "F", "P", "mv", "sv", "svf"]
+
+
+def step_replay(G, eng, gen):
+    eng.step_generation(gen, G.all_params(gen), None, [G.draws(gen, p) for p in range(G.n_pop)])
+
+
+def compare_to_golden(G, eng, gen, pops=None):
+    for p in pops if pops is not None else range(G.n_pop):
+        ind = eng.individuals(p)
+        assert eng.population_size(p) == int(G.g(gen, p, "n"))
+        assert np.array_equal(ind["ids"], G.g(gen, p, "ids"))
+        assert np.array_equal(ind["sex"], G.g(gen, p, "sex"))
+        for k in FLOAT_KEYS:
+            np.testing.assert_allclose(ind[k], G.g(gen, p, k), rtol=RTOL, atol=ATOL, err_msg=f"{G.name} gen {gen} pop {p} {k}")
+        for c in range(G.n_chr):
+            assert np.array_equal(eng.haplotypes(p, c), G.g(gen, p, f"c{c}.hap")), f"{G.name} gen {gen} chr {c}: haplotypes"
+
+
+@pytest.mark.parametrize("name", [s for s in SCENARIOS if not s.startswith("D_")])
+@pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS])
+def test_replay_matches_reference(cuda_lib, name, rep):
+    G = Golden(name)
+    gpu = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_REPLAY, representation=rep))
+    cpu = OracleEngine(**G.engine_kwargs(rng_mode=capi.GE_RNG_REPLAY))
+    for e in (gpu, cpu):
+        G.configure(e)
+        e.init_generation0([G.draws0(p) for p in range(G.n_pop)])
+    compare_to_golden(G, gpu, 0)
+    for f in range(G.n_phen):
+        a, b = gpu.gen0_constants(0, f), cpu.gen0_constants(0, f)
+        for k in a:
+            assert a[k] == pytest.approx(b[k], rel=1e-12, abs=1e-14)
+    for gen in range(1, G.G + 1):
+        step_replay(G, gpu, gen)
+        step_replay(G, cpu, gen)
+        compare_to_golden(G, gpu, gen)
+        for c in range(G.n_chr):
+            for f in range(G.n_phen):
+                assert np.array_equal(gpu.cv_alleles(0, f, c), cpu.cv_alleles(0, f, c)), "causal-variant alleles"
+            if rep & capi.GE_REP_SEGMENTS:
+                s, r = gpu.segments(0, c), cpu.segments(0, c)
+                assert np.array_equal(s["seg_off"], r["seg_off"]) and np.array_equal(s["seg"], r["seg"]), "segments"
+                assert np.array_equal(s["seg"], G.g(gen, 0, f"c{c}.seg"))
+                assert np.array_equal(s["mut_off"], r["mut_off"])
+                for k in range(len(s["mut_off"]) - 1):
+                    assert np.array_equal(np.sort(s["mut_bp"][s["mut_off"][k]:s["mut_off"][k + 1]]), np.sort(r["mut_bp"][r["mut_off"][k]:r["mut_off"][k + 1]]))
+        for f in range(G.n_phen):
+            m, r = gpu.moments(0, f), cpu.moments(0, f)
+            for k in m:
+                assert m[k] == pytest.approx(r[k], rel=1e-9, abs=1e-12)
