@@ -163,6 +163,11 @@ class Engine:
         assert al.ndim == 2 and al.shape[1] == self.n_loci[chr_]
         self._call("set_founder_panel", self.ctx, pop, chr_, _ptr(al, _u8p), C.c_uint64(al.shape[0]))
 
+    def set_founder_panel_packed(self, pop, chr_, words):
+        w = _arr(words, np.uint32)
+        assert w.ndim == 2 and w.shape[1] == (self.n_loci[chr_] + 31) // 32
+        self._call("set_founder_panel_packed", self.ctx, pop, chr_, _ptr(w, _u32p), C.c_uint64(w.shape[0]))
+
     def set_cv(self, pop, phen, chr_, bp, a, d, founder_cv):
         bp, a, d, v = _arr(bp, np.uint64), _arr(a, np.float64), _arr(d, np.float64), _arr(founder_cv, np.uint8)
         assert v.ndim == 2 and v.shape[1] == len(bp)
@@ -243,13 +248,25 @@ class Engine:
         self._call("get_population_size", self.ctx, pop, C.byref(n))
         return n.value
 
-    def individuals(self, pop):
+    @staticmethod
+    def individual_bytes(n, n_phen):
+        """Bytes ge_download_individuals moves for n individuals (the `.info` columns)."""
+        return n * (7 * 8 + 1 + 7 * 8 * n_phen + 3 * 8)
+
+    def individuals(self, pop, out=None):
+        """`.info` columns of one population.  `out`: optional dict of preallocated (e.g. pinned) arrays
+        sized for at least the current population; views of the right length are returned."""
         n, nf = self.population_size(pop), self.n_phen
-        out = {"ids": np.zeros((n, 7), np.uint64), "sex": np.zeros(n, np.uint8)}
-        for k in "ADGCEFP":
-            out[k] = np.zeros((nf, n), np.float64)
-        for k in ("mv", "sv", "svf"):
-            out[k] = np.zeros(n, np.float64)
+        if out is None:
+            out = {"ids": np.zeros((n, 7), np.uint64), "sex": np.zeros(n, np.uint8)}
+            for k in "ADGCEFP":
+                out[k] = np.zeros((nf, n), np.float64)
+            for k in ("mv", "sv", "svf"):
+                out[k] = np.zeros(n, np.float64)
+        else:
+            out = {"ids": out["ids"].reshape(-1)[:n * 7].reshape(n, 7), "sex": out["sex"][:n],
+                   **{k: out[k].reshape(-1)[:nf * n].reshape(nf, n) for k in "ADGCEFP"},
+                   **{k: out[k][:n] for k in ("mv", "sv", "svf")}}
         s = ge_indiv_soa()
         s.ids, s.sex = _ptr(out["ids"], _u64p), _ptr(out["sex"], _u8p)
         for k in list("ADGCEFP") + ["mv", "sv", "svf"]:
@@ -329,6 +346,14 @@ class Engine:
         n = C.c_uint64()
         self._call("get_launch_count", self.ctx, C.byref(n))
         return n.value
+
+    def timer_start(self):
+        self._call("timer_start", self.ctx)
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._call("timer_stop", self.ctx, C.byref(ms))
+        return ms.value
 
     def synchronize(self):
         self._call("synchronize", self.ctx)

@@ -248,6 +248,15 @@ int ge_set_founder_panel(ge_ctx *ctx, int pop, int chr, const uint8_t *al, uint6
     P.n_founder_haps = nh;
     return GE_OK;
 }
+int ge_set_founder_panel_packed(ge_ctx *ctx, int pop, int chr, const uint32_t *words, uint64_t nh) {
+    CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr);
+    PopDev &P = ctx->pop[pop];
+    if (P.panel_packed.empty()) P.panel_packed.resize(ctx->cfg.n_chr);
+    uint64_t nw = (ctx->loci[chr].size() + 31) / 32;
+    P.panel_packed[chr].assign(words, words + nh * nw);
+    P.n_founder_haps = nh;
+    return GE_OK;
+}
 int ge_set_cv(ge_ctx *ctx, int pop, int phen, int chr, const uint64_t *bp, const double *a, const double *d, uint64_t ncv, const uint8_t *val, uint64_t nh) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr); CHECK_PHEN(ctx, phen);
     CvHost &h = ctx->pop[pop].cv[phen][chr];
@@ -438,11 +447,27 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
         for (int c = 0; c < C; c++) {
             uint32_t nl = ctx->chr_nloci[c];
             if (nl == 0) continue;
+            bool packed = !P.panel_packed.empty() && !P.panel_packed[c].empty();
+            uint32_t nwc = (nl + 31) / 32;
+            if (packed) {
+                if (P.panel_packed[c].size() != (size_t)2 * n * nwc) return fail(GE_ERR_INVALID, "packed founder panel of the wrong size");
+                Buf tmp;
+                GE_TRY(ctx->ensure_exact(tmp, P.panel_packed[c].size() * 4));
+                CUDA_TRY(cudaMemcpyAsync(tmp.p, P.panel_packed[c].data(), P.panel_packed[c].size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                uint64_t tot = (uint64_t)2 * n * nwc;
+                mask_packed_panel_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(tmp.as<uint32_t>(), (uint32_t)(2 * n), nl, ctx->d_pos.as<uint32_t>() + ctx->locus_off[c],
+                                                                                  (uint32_t)P.rmap_bp[c].front(), (uint32_t)P.rmap_bp[c].back(), S.hap.as<uint32_t>(), ctx->W, ctx->chr_word_off[c]);
+                GE_TRY(ctx->check_launch("mask_packed_panel"));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                ctx->release(tmp);
+                std::vector<uint32_t>().swap(P.panel_packed[c]);
+                continue;
+            }
             if (P.panel[c].size() != (size_t)2 * n * nl) return fail(GE_ERR_INVALID, "founder panel missing or of the wrong size (ge_set_founder_panel)");
             Buf tmp;
             GE_TRY(ctx->ensure_exact(tmp, P.panel[c].size()));
             CUDA_TRY(cudaMemcpyAsync(tmp.p, P.panel[c].data(), P.panel[c].size(), cudaMemcpyHostToDevice, ctx->stream));
-            uint64_t tot = (uint64_t)2 * n * ((nl + 31) / 32);
+            uint64_t tot = (uint64_t)2 * n * nwc;
             pack_panel_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(tmp.as<uint8_t>(), (uint32_t)(2 * n), nl, ctx->d_pos.as<uint32_t>() + ctx->locus_off[c],
                                                                        (uint32_t)P.rmap_bp[c].front(), (uint32_t)P.rmap_bp[c].back(), S.hap.as<uint32_t>(), ctx->W, ctx->chr_word_off[c]);
             GE_TRY(ctx->check_launch("pack_panel"));
@@ -683,20 +708,18 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         GE_TRY(ctx->ensure(P.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
         xo_to_flips_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->genome(), n_slots, P.xo_off.as<uint64_t>(), P.xo_bp.as<uint32_t>(), P.flips.as<uint32_t>());
         GE_TRY(ctx->check_launch("xo_to_flips"));
-        if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+        ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0};
+        if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, st)); }
         unsigned grid = (unsigned)std::min<uint64_t>(n_off, (uint64_t)ctx->n_sm * 64);
         propagate_bits_kernel<<<grid, PROP_THREADS, 0, st>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), P.father.as<uint32_t>(),
                                                              P.mother.as<uint32_t>(), P.xo_off.as<uint64_t>(), P.flips.as<uint32_t>(), P.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
         GE_TRY(ctx->check_launch("propagate_bits"));
         if (ctx->profiling) {
-            CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-            CUDA_TRY(cudaEventSynchronize(ctx->ev1));
-            float ms = 0;
-            CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-            KernelStat &k = ctx->kstat[GE_KERNEL_PROPAGATE_BITS];
+            CUDA_TRY(cudaEventRecord(evp.b, st));
             uint64_t M = 0;
             for (uint32_t v : ctx->chr_nloci) M += v;
-            k.ms += ms; k.launches++; k.bytes += n_off * M / 2;  // 0.5 byte per individual-locus
+            evp.bytes = n_off * M / 2;  // 0.5 byte per individual-locus
+            ctx->ev_pending.push_back(evp);
         }
     }
     // ---- causal-variant planes
@@ -912,12 +935,24 @@ int ge_set_profiling(ge_ctx *ctx, int enabled) { CHECK_CTX(ctx); ctx->profiling 
 int ge_get_kernel_time(ge_ctx *ctx, int k, double *ms, uint64_t *launches, uint64_t *bytes) {
     CHECK_CTX(ctx);
     if (k < 0 || k >= GE_KERNEL_COUNT) return fail(GE_ERR_INVALID, "bad kernel id");
+    ctx->resolve_events();
     *ms = ctx->kstat[k].ms; *launches = ctx->kstat[k].launches; *bytes = ctx->kstat[k].bytes;
     return GE_OK;
 }
-int ge_reset_kernel_times(ge_ctx *ctx) { CHECK_CTX(ctx); for (auto &k : ctx->kstat) k = KernelStat(); ctx->launches = 0; return GE_OK; }
+int ge_reset_kernel_times(ge_ctx *ctx) { CHECK_CTX(ctx); ctx->resolve_events(); for (auto &k : ctx->kstat) k = KernelStat(); ctx->launches = 0; return GE_OK; }
 int ge_get_launch_count(ge_ctx *ctx, uint64_t *n) { CHECK_CTX(ctx); *n = ctx->launches; return GE_OK; }
 int ge_synchronize(ge_ctx *ctx) { CHECK_CTX(ctx); CUDA_TRY(cudaSetDevice(ctx->cfg.device)); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return GE_OK; }
 int ge_device_memory_bytes(ge_ctx *ctx, uint64_t *b) { CHECK_CTX(ctx); *b = ctx->mem_peak; return GE_OK; }
+int ge_timer_start(ge_ctx *ctx) { CHECK_CTX(ctx); CUDA_TRY(cudaSetDevice(ctx->cfg.device)); CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream)); return GE_OK; }
+int ge_timer_stop(ge_ctx *ctx, double *ms) {
+    CHECK_CTX(ctx);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+    *ms = f;
+    return GE_OK;
+}
 
 }  // extern "C"

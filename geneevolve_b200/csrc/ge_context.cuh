@@ -69,6 +69,7 @@ struct PopDev {
     std::vector<std::vector<CvHost>> cv;  // [phen][chr]
     std::vector<Scheme> scheme;
     std::vector<std::vector<uint8_t>> panel;  // host copy until generation 0 is built
+    std::vector<std::vector<uint32_t>> panel_packed;  // alternative: bit-packed by the host
     uint64_t n_founder_haps = 0;
     // device maps
     Buf d_row_off, d_bp, d_T, d_bp_dist, d_mrow_off, d_mbp, d_mT, d_cov_lo, d_cov_hi;
@@ -119,7 +120,23 @@ struct ge_ctx {
     // stats
     bool profiling = false;
     KernelStat kstat[GE_KERNEL_COUNT];
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // ge_timer_start / ge_timer_stop
+    struct EvPair { cudaEvent_t a, b; int kernel; uint64_t bytes; };
+    std::vector<EvPair> ev_pending;            // per-launch events of profiled kernels, resolved lazily (no sync in the loop)
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t get_event() {
+        if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void resolve_events() {
+        for (auto &p : ev_pending) {
+            cudaEventSynchronize(p.b);
+            float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b);
+            kstat[p.kernel].ms += ms; kstat[p.kernel].launches++; kstat[p.kernel].bytes += p.bytes;
+            ev_pool.push_back(p.a); ev_pool.push_back(p.b);
+        }
+        ev_pending.clear();
+    }
     uint64_t launches = 0;
     size_t mem_now = 0, mem_peak = 0;
 

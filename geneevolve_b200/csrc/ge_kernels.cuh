@@ -228,6 +228,21 @@ __global__ void pack_panel_kernel(const uint8_t *__restrict__ alleles, uint32_t 
     rows[(uint64_t)r * W + woff + w] = v;
 }
 
+// host-packed panel words -> rows, masking loci outside the covered range
+__global__ void mask_packed_panel_kernel(const uint32_t *__restrict__ words, uint32_t n_rows, uint32_t n_loci, const uint32_t *__restrict__ pos,
+                                         uint32_t cov_lo, uint32_t cov_hi, uint32_t *__restrict__ rows, uint32_t W, uint32_t woff) {
+    uint32_t nw = (n_loci + 31) >> 5;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n_rows * nw) return;
+    uint32_t r = (uint32_t)(t / nw), w = (uint32_t)(t % nw);
+    uint32_t m = 0;
+    for (uint32_t b = 0; b < 32; b++) {
+        uint32_t s = w * 32 + b;
+        if (s < n_loci) { uint32_t p = pos[s]; if (p >= cov_lo && p < cov_hi) m |= 1u << b; }
+    }
+    rows[(uint64_t)r * W + woff + w] = words[t] & m;
+}
+
 __global__ void unpack_rows_kernel(const uint32_t *__restrict__ rows, uint32_t W, uint32_t woff, uint32_t n_rows,
                                    uint32_t n_loci, uint8_t *__restrict__ alleles) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -127,6 +127,9 @@ int ge_set_loci(ge_ctx *ctx, int chr, const uint64_t *pos, uint64_t n_loci);
 /* Hap_SNP of one population and chromosome (src/format_hap.h:28-32): alleles[h*n_loci + s] in {0,1},
  * hap-major exactly like Hap_SNP::hap.  Packed to bits on the device. */
 int ge_set_founder_panel(ge_ctx *ctx, int pop, int chr, const uint8_t *alleles, uint64_t n_founder_haps);
+/* Same panel, already bit-packed by the host: words[h*words_per_hap + w], words_per_hap = ceil(n_loci/32),
+ * locus s -> word s/32, bit s%32 (the layout ge_download_haplotypes_packed returns). */
+int ge_set_founder_panel_packed(ge_ctx *ctx, int pop, int chr, const uint32_t *words, uint64_t n_founder_haps);
 /* CV_INFO + CV of one phenotype and chromosome (src/Population.h:201-220, src/Population.cpp:197-343). */
 int ge_set_cv(ge_ctx *ctx, int pop, int phen, int chr, const uint64_t *bp, const double *a, const double *d,
               uint64_t n_cv, const uint8_t *founder_cv, uint64_t n_founder_haps);
@@ -209,6 +212,9 @@ int ge_get_kernel_time(ge_ctx *ctx, int kernel, double *total_ms, uint64_t *laun
 int ge_reset_kernel_times(ge_ctx *ctx);
 int ge_get_launch_count(ge_ctx *ctx, uint64_t *launches);   /* every kernel this context launched */
 int ge_synchronize(ge_ctx *ctx);
+/* CUDA events on the library's stream around a caller-defined region (everything queued in between) */
+int ge_timer_start(ge_ctx *ctx);
+int ge_timer_stop(ge_ctx *ctx, double *elapsed_ms);
 int ge_device_memory_bytes(ge_ctx *ctx, uint64_t *bytes);    /* device high-water mark (SURVEY.md §5 memory reporting) */
 
 #ifdef __cplusplus
