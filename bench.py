@@ -48,27 +48,27 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.samples, self.stop, self.index = [], False, index
-        self.t = threading.Thread(target=self.run, daemon=True)
-
-    def run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.05)
+        self.index, self.proc, self.samples = index, None, []
 
     def __enter__(self):
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)  # let the first samples arrive before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.t.join(timeout=10)
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            self.samples = [[x.strip() for x in line.split(",")] for line in out.strip().splitlines() if line.count(",") >= 5]
 
     def summary(self):
         if not self.samples:
@@ -264,7 +264,7 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3_100k_x_1M")
