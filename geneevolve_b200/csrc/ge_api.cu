@@ -193,7 +193,7 @@ int ge_destroy(ge_ctx *ctx) {
     for (PopDev &P : ctx->pop) {
         for (Buf *b : {&P.d_row_off, &P.d_bp, &P.d_T, &P.d_bp_dist, &P.d_mrow_off, &P.d_mbp, &P.d_mT, &P.d_cov_lo, &P.d_cov_hi, &P.d_omega,
                        &P.d_lambda, &P.d_vd_zero, &P.prev_P, &P.prev_F, &P.c_male, &P.c_female, &P.c_inbreed, &P.c_noff, &P.father, &P.mother,
-                       &P.couple_of, &P.xo_off, &P.xo_bp, &P.flips, &P.start_hap, &P.mut_off, &P.mut_bp, &P.mut_gam, &P.e_raw, &P.cnt32, &P.d_sv0})
+                       &P.couple_of, &P.xo_off, &P.xo_bp, &P.flips, &P.start_hap, &P.mut_off, &P.mut_bp, &P.mut_gam, &P.e_raw, &P.cnt32, &P.d_sv0, &P.founder_rows, &P.founder_cv})
             freeb(*b);
         for (GenState &s : P.st) {
             for (Buf *b : {&s.hap, &s.cv_allele, &s.cv_root, &s.ids, &s.sex, &s.A, &s.D, &s.G, &s.C, &s.E, &s.F, &s.P, &s.mv, &s.sv, &s.svf, &s.hm_off, &s.hm_bp}) freeb(*b);
@@ -442,8 +442,13 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
     for (int f = 0; f < nf; f++) { om[f] = P.scheme[f].omega; la[f] = P.scheme[f].lambda; vz[f] = P.scheme[f].vd == 0; }
     GE_TRY(ctx->upload(P.d_omega, om)); GE_TRY(ctx->upload(P.d_lambda, la)); GE_TRY(ctx->upload(P.d_vd_zero, vz));
     // bit-packed rows from the founder panel
-    if (ctx->bits()) {
-        CUDA_TRY(cudaMemsetAsync(S.hap.p, 0, (size_t)n * 2 * ctx->W * 4, ctx->stream));
+    bool have_panel = !P.panel_packed.empty();
+    for (int c = 0; c < C && !have_panel; c++) have_panel = !P.panel[c].empty();
+    if (ctx->bits() && !have_panel) return fail(GE_ERR_INVALID, "GE_REP_BITS needs the founder panel (ge_set_founder_panel)");
+    if (have_panel) {
+        uint32_t *rows0 = S.hap.as<uint32_t>();
+        if (ctx->segs()) { GE_TRY(ctx->ensure_exact(P.founder_rows, (size_t)n * 2 * ctx->W * 4)); rows0 = P.founder_rows.as<uint32_t>(); }
+        CUDA_TRY(cudaMemsetAsync(rows0, 0, (size_t)n * 2 * ctx->W * 4, ctx->stream));
         for (int c = 0; c < C; c++) {
             uint32_t nl = ctx->chr_nloci[c];
             if (nl == 0) continue;
@@ -456,7 +461,7 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
                 CUDA_TRY(cudaMemcpyAsync(tmp.p, P.panel_packed[c].data(), P.panel_packed[c].size() * 4, cudaMemcpyHostToDevice, ctx->stream));
                 uint64_t tot = (uint64_t)2 * n * nwc;
                 mask_packed_panel_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(tmp.as<uint32_t>(), (uint32_t)(2 * n), nl, ctx->d_pos.as<uint32_t>() + ctx->locus_off[c],
-                                                                                  (uint32_t)P.rmap_bp[c].front(), (uint32_t)P.rmap_bp[c].back(), S.hap.as<uint32_t>(), ctx->W, ctx->chr_word_off[c]);
+                                                                                  (uint32_t)P.rmap_bp[c].front(), (uint32_t)P.rmap_bp[c].back(), rows0, ctx->W, ctx->chr_word_off[c]);
                 GE_TRY(ctx->check_launch("mask_packed_panel"));
                 CUDA_TRY(cudaStreamSynchronize(ctx->stream));
                 ctx->release(tmp);
@@ -469,11 +474,13 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
             CUDA_TRY(cudaMemcpyAsync(tmp.p, P.panel[c].data(), P.panel[c].size(), cudaMemcpyHostToDevice, ctx->stream));
             uint64_t tot = (uint64_t)2 * n * nwc;
             pack_panel_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(tmp.as<uint8_t>(), (uint32_t)(2 * n), nl, ctx->d_pos.as<uint32_t>() + ctx->locus_off[c],
-                                                                       (uint32_t)P.rmap_bp[c].front(), (uint32_t)P.rmap_bp[c].back(), S.hap.as<uint32_t>(), ctx->W, ctx->chr_word_off[c]);
+                                                                       (uint32_t)P.rmap_bp[c].front(), (uint32_t)P.rmap_bp[c].back(), rows0, ctx->W, ctx->chr_word_off[c]);
             GE_TRY(ctx->check_launch("pack_panel"));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             ctx->release(tmp);
         }
+        if (ctx->segs() && ctx->bits())
+            CUDA_TRY(cudaMemcpyAsync(S.hap.p, P.founder_rows.p, (size_t)n * 2 * ctx->W * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     // causal-variant planes
     if (ctx->n_cv_tot) {
@@ -485,7 +492,8 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
                 uint32_t b0 = ctx->cv_block_off[(size_t)f * C + c], ncv = (uint32_t)h.bp.size();
                 for (uint64_t r = 0; r < 2 * n; r++) std::memcpy(&fcv[r * ctx->n_cv_tot + b0], &h.val[r * ncv], ncv);
             }
-        Buf tmp;
+        Buf tmp_local;
+        Buf &tmp = ctx->segs() ? P.founder_cv : tmp_local;
         GE_TRY(ctx->ensure_exact(tmp, fcv.size()));
         CUDA_TRY(cudaMemcpyAsync(tmp.p, fcv.data(), fcv.size(), cudaMemcpyHostToDevice, ctx->stream));
         uint64_t tot = (uint64_t)2 * n * ctx->n_cv_tot;
@@ -493,7 +501,7 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
                                                                 (uint8_t)p, S.cv_allele.as<uint8_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr);
         GE_TRY(ctx->check_launch("cv_init"));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        ctx->release(tmp);
+        ctx->release(tmp_local);
     }
     if (ctx->segs()) GE_TRY(seg_init_gen0(ctx, p, n));
     // pedigree, sex, sibling-common effect

@@ -71,6 +71,7 @@ struct PopDev {
     std::vector<std::vector<uint8_t>> panel;  // host copy until generation 0 is built
     std::vector<std::vector<uint32_t>> panel_packed;  // alternative: bit-packed by the host
     uint64_t n_founder_haps = 0;
+    Buf founder_rows, founder_cv;  // kept on the device for segment materialisation / ras_find_cv (GE_REP_SEGMENTS)
     // device maps
     Buf d_row_off, d_bp, d_T, d_bp_dist, d_mrow_off, d_mbp, d_mT, d_cov_lo, d_cov_hi;
     Buf d_omega, d_lambda, d_vd_zero;

@@ -1,11 +1,271 @@
-// ge_segments.cuh — founder-segment representation (the reference's `class part` lists, src/Population.h:20-51).
+// ge_segments.cuh — founder-segment representation (GE_REP_SEGMENTS): the reference's own chromosome model,
+// a sorted list of `class part {st,en,hap_index,root_population}` per haplotype (src/Population.h:20-51).
+// Needed where bit-packed rows cannot fit (BASELINE config 5: 1M individuals x 10M loci = 2.5 TB per
+// generation) and for the `.int` output; its cost is proportional to crossovers, not to loci.
+//
+// Device layout: one CSR over haplotype slots (i*n_chr + c)*2 + h; a segment is one uint4 (16 B, one
+// LDG.128/STG.128).  part::mutation_pos lives in the per-haplotype mutation lists shared with the bit path
+// (ge_kernels.cuh, mutation_lists_kernel): inside a haplotype the parts are disjoint, so "position is in the
+// part that covers it" and "position is in the haplotype's list" are the same predicate.
 #pragma once
 #include "ge_context.cuh"
 
-static void seg_release(SegState &s) { (void)s; }
-static int seg_init_gen0(ge_ctx *, int, uint64_t) { return fail(GE_ERR_UNSUPPORTED, "GE_REP_SEGMENTS is not built yet"); }
-static int seg_recombine(ge_ctx *, int, uint64_t) { return fail(GE_ERR_UNSUPPORTED, "GE_REP_SEGMENTS is not built yet"); }
-static int seg_find_cv(ge_ctx *, int) { return fail(GE_ERR_UNSUPPORTED, "GE_REP_SEGMENTS is not built yet"); }
-static int seg_materialise(ge_ctx *, int, int, uint8_t *) { return fail(GE_ERR_UNSUPPORTED, "GE_REP_SEGMENTS is not built yet"); }
-static int seg_count(ge_ctx *, int, int, uint64_t *, uint64_t *) { return fail(GE_ERR_UNSUPPORTED, "GE_REP_SEGMENTS is not built yet"); }
-static int seg_download(ge_ctx *, int, int, uint64_t *, uint64_t *, uint64_t *, uint64_t *) { return fail(GE_ERR_UNSUPPORTED, "GE_REP_SEGMENTS is not built yet"); }
+namespace gek {
+
+__global__ void seg_init_kernel(uint64_t n, int n_chr, int pop, const uint32_t *__restrict__ cov_lo, const uint32_t *__restrict__ cov_hi,
+                                uint64_t *__restrict__ off, uint4 *__restrict__ seg) {
+    uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t n_slots = n * n_chr * 2;
+    if (slot > n_slots) return;
+    off[slot] = slot;
+    if (slot == n_slots) return;
+    uint64_t i = (slot >> 1) / (uint64_t)n_chr;
+    int c = (int)((slot >> 1) % (uint64_t)n_chr), h = (int)(slot & 1);
+    seg[slot] = make_uint4(cov_lo[c], cov_hi[c], (uint32_t)(2 * i + h), (uint32_t)pop);  // :3029-3034
+}
+
+struct SegArgs {
+    int n_chr;
+    uint64_t off_first, n_off;
+    const uint32_t *father, *mother;
+    const uint64_t *xo_off; const uint32_t *xo_bp; const uint8_t *start_hap;
+    const uint64_t *par_off; const uint4 *par_seg;
+    const uint32_t *cov_lo, *cov_hi;
+};
+
+// Simulation::recombine (:2903-2958), branch for branch.  One thread per offspring haplotype slot; pass 0 counts
+// the pieces, pass 1 writes them at the scanned offsets.  No merging of adjacent same-founder pieces, zero-length
+// and clipped pieces exactly as the reference emits them.
+template <bool FILL>
+__global__ void seg_recombine_kernel(SegArgs a, uint32_t *__restrict__ count, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_off * a.n_chr * 2) return;
+    uint64_t slot = a.off_first * a.n_chr * 2 + t;
+    uint64_t i = (slot >> 1) / (uint64_t)a.n_chr;
+    int c = (int)((slot >> 1) % (uint64_t)a.n_chr), gam = (int)(slot & 1);
+    uint32_t parent = gam ? a.mother[i] : a.father[i];
+    uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2;
+    const uint4 *H0 = a.par_seg + a.par_off[ps], *H1 = a.par_seg + a.par_off[ps + 1];
+    uint32_t n0 = (uint32_t)(a.par_off[ps + 1] - a.par_off[ps]), n1 = (uint32_t)(a.par_off[ps + 2] - a.par_off[ps + 1]);
+    uint64_t e0 = a.xo_off[slot];
+    uint32_t k = (uint32_t)(a.xo_off[slot + 1] - e0);
+    int hi = a.start_hap[slot] & 1;
+    uint4 *out = FILL ? off_seg + off_off[slot] : nullptr;
+    uint32_t n = 0;
+    if (k == 0) {  // recombination_locs.size() < 3: the chosen parental haplotype unchanged (:2910)
+        const uint4 *H = hi ? H1 : H0;
+        uint32_t nH = hi ? n1 : n0;
+        if (FILL) for (uint32_t q = 0; q < nH; q++) out[q] = H[q];
+        n = nH;
+    } else {
+        for (uint32_t i1 = 1; i1 <= k + 1; i1++) {
+            uint32_t L = i1 == 1 ? a.cov_lo[c] : a.xo_bp[e0 + i1 - 2];
+            uint32_t R = i1 == k + 1 ? a.cov_hi[c] : a.xo_bp[e0 + i1 - 1];
+            const uint4 *H = hi ? H1 : H0;
+            uint32_t nH = hi ? n1 : n0, i2 = 0;
+            while (i2 < nH && H[i2].y <= L) i2++;
+            if (i2 < nH) {
+                uint4 q = H[i2];
+                if (q.x < L && L < q.y && R < q.y) { if (FILL) out[n] = make_uint4(L, R, q.z, q.w); n++; i2++; }
+            }
+            if (i2 < nH) {
+                uint4 q = H[i2];
+                if (q.x < L && L < q.y && R >= q.y) { if (FILL) out[n] = make_uint4(L, q.y, q.z, q.w); n++; i2++; }
+            }
+            while (i2 < nH) {
+                uint4 q = H[i2];
+                if (!(q.y <= R && L <= q.x)) break;
+                if (FILL) out[n] = q;
+                n++; i2++;
+            }
+            if (i2 < nH) {
+                uint4 q = H[i2];
+                if (q.x < R && R < q.y) { if (FILL) out[n] = make_uint4(q.x, R, q.z, q.w); n++; }
+            }
+            hi ^= 1;
+        }
+    }
+    if (!FILL) count[slot] = n;
+}
+
+// ras_find_cv (:2752-2815) on the segment lists: allele/root planes of every (haplotype row, CV)
+__global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__restrict__ off, const uint4 *__restrict__ seg,
+                                   const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp,
+                                   const uint8_t *const *__restrict__ founder_cv /* [n_pop] -> [nh][n_cv_tot] */,
+                                   uint8_t *__restrict__ allele, uint8_t *__restrict__ rootp) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * cs.n_cv_tot) return;
+    uint32_t k = (uint32_t)(t % cs.n_cv_tot);
+    uint64_t row = t / cs.n_cv_tot;  // 2*i + h
+    uint32_t c = cs.chr_of[k], bp = cs.bp[k];
+    uint64_t slot = ((row >> 1) * cs.n_chr + c) * 2 + (row & 1);
+    uint8_t v = 0, r = 0;
+    bool found = false;
+    for (uint64_t e = off[slot]; e < off[slot + 1]; e++) {
+        uint4 q = seg[e];
+        if (q.x <= bp && bp < q.y) { v = founder_cv[q.w][(uint64_t)q.z * cs.n_cv_tot + k]; r = (uint8_t)q.w; found = true; }
+    }
+    if (found && hm_off) {
+        for (uint64_t e = hm_off[slot]; e < hm_off[slot + 1]; e++) if (hm_bp[e] == bp) { v ^= 1; break; }
+    }
+    allele[t] = v;
+    if (rootp) rootp[t] = found ? r : 0;  // covered by no part: the effect tables hold a = d = 0 there (Human_CV ctor)
+}
+
+// ras_convert_interval_to_hap_matrix (:1186-1230): alleles of one chromosome from segments + founder panels
+__global__ void seg_materialise_kernel(Genome g, int c, uint64_t n_rows, const uint64_t *__restrict__ off, const uint4 *__restrict__ seg,
+                                       const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp,
+                                       const uint32_t *const *__restrict__ founder_rows /* [n_pop] packed rows */, uint8_t *__restrict__ alleles) {
+    uint32_t nl = g.chr_nloci[c];
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * nl) return;
+    uint32_t s = (uint32_t)(t % nl);
+    uint64_t row = t / nl;
+    uint32_t pos = g.pos[g.locus_off[c] + s];
+    uint64_t slot = ((row >> 1) * g.n_chr + c) * 2 + (row & 1);
+    uint8_t v = 0;
+    bool found = false;
+    for (uint64_t e = off[slot]; e < off[slot + 1]; e++) {
+        uint4 q = seg[e];
+        if (q.x <= pos && pos < q.y) { v = (founder_rows[q.w][(uint64_t)q.z * g.W + g.chr_word_off[c] + (s >> 5)] >> (s & 31)) & 1u; found = true; }
+    }
+    if (found && hm_off) {
+        for (uint64_t e = hm_off[slot]; e < hm_off[slot + 1]; e++) if (hm_bp[e] == pos) { v ^= 1; break; }
+    }
+    alleles[t] = v;
+}
+
+}  // namespace gek
+
+static void seg_release(SegState &s) {
+    for (Buf *b : {&s.off, &s.seg}) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
+    s.valid = false;
+}
+
+static int seg_init_gen0(ge_ctx *ctx, int p, uint64_t n) {
+    PopDev &P = ctx->pop[p];
+    SegState &S = P.st[P.cur].seg;
+    uint64_t n_slots = n * ctx->cfg.n_chr * 2;
+    GE_TRY(ctx->ensure(S.off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(S.seg, std::max<uint64_t>(n_slots, 1) * 16));
+    seg_init_kernel<<<nblk(n_slots + 1, 256), 256, 0, ctx->stream>>>(n, ctx->cfg.n_chr, p, P.d_cov_lo.as<uint32_t>(), P.d_cov_hi.as<uint32_t>(),
+                                                                     S.off.as<uint64_t>(), S.seg.as<uint4>());
+    GE_TRY(ctx->check_launch("seg_init"));
+    S.n_seg = n_slots; S.valid = true;
+    return GE_OK;
+}
+
+static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
+    PopDev &P = ctx->pop[pop];
+    GenState &par = P.st[P.cur], &off = P.st[P.cur ^ 1];
+    if (!par.seg.valid) return fail(GE_ERR_INVALID, "parent generation has no segment lists");
+    int C = ctx->cfg.n_chr;
+    uint64_t n_slots = n_off * C * 2;
+    SegArgs a;
+    a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = P.father.as<uint32_t>(); a.mother = P.mother.as<uint32_t>();
+    a.xo_off = P.xo_off.as<uint64_t>(); a.xo_bp = P.xo_bp.as<uint32_t>(); a.start_hap = P.start_hap.as<uint8_t>();
+    a.par_off = par.seg.off.as<uint64_t>(); a.par_seg = par.seg.seg.as<uint4>(); a.cov_lo = P.d_cov_lo.as<uint32_t>(); a.cov_hi = P.d_cov_hi.as<uint32_t>();
+    GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
+    GE_TRY(ctx->ensure(off.seg.off, (n_slots + 1) * 8));
+    ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_RECOMBINE_SEGMENTS, 0};
+    if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, ctx->stream)); }
+    seg_recombine_kernel<false><<<nblk(n_slots, 128), 128, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
+    GE_TRY(ctx->check_launch("seg_recombine<count>"));
+    GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, off.seg.off.as<uint64_t>(), &off.seg.n_seg));
+    if (ctx->cfg.seg_capacity && off.seg.n_seg > ctx->cfg.seg_capacity) return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity");
+    GE_TRY(ctx->ensure(off.seg.seg, std::max<uint64_t>(off.seg.n_seg, 1) * 16));
+    seg_recombine_kernel<true><<<nblk(n_slots, 128), 128, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+    GE_TRY(ctx->check_launch("seg_recombine<fill>"));
+    if (ctx->profiling) {
+        CUDA_TRY(cudaEventRecord(evp.b, ctx->stream));
+        evp.bytes = 16 * (par.seg.n_seg * 0 + 2 * off.seg.n_seg);  // 16 B per segment read (approx. one parental piece per emitted piece) + written
+        ctx->ev_pending.push_back(evp);
+    }
+    off.seg.valid = true;
+    return GE_OK;
+}
+
+static int seg_device_tables(ge_ctx *ctx, Buf &tbl, bool cv) {
+    std::vector<const void *> ptrs(ctx->cfg.n_pop);
+    for (int p = 0; p < ctx->cfg.n_pop; p++) ptrs[p] = cv ? ctx->pop[p].founder_cv.p : ctx->pop[p].founder_rows.p;
+    return ctx->upload(tbl, ptrs);
+}
+
+static int seg_find_cv(ge_ctx *ctx, int pop) {
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists");
+    if (ctx->n_cv_tot == 0) return GE_OK;
+    Buf tbl;
+    GE_TRY(seg_device_tables(ctx, tbl, true));
+    uint64_t tot = 2 * S.n * ctx->n_cv_tot;
+    seg_find_cv_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(),
+                                                                S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
+                                                                tbl.as<const uint8_t *>(), S.cv_allele.as<uint8_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr);
+    GE_TRY(ctx->check_launch("seg_find_cv"));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->release(tbl);
+    return GE_OK;
+}
+
+static int seg_materialise(ge_ctx *ctx, int pop, int c, uint8_t *d_alleles) {
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists");
+    Buf tbl;
+    GE_TRY(seg_device_tables(ctx, tbl, false));
+    uint64_t tot = 2 * S.n * ctx->chr_nloci[c];
+    seg_materialise_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->genome(), c, 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(),
+                                                                    S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
+                                                                    tbl.as<const uint32_t *>(), d_alleles);
+    GE_TRY(ctx->check_launch("seg_materialise"));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->release(tbl);
+    return GE_OK;
+}
+
+// host-side slicing of one chromosome out of the slot-major CSR (output path, `.int` writer)
+static int seg_host_copy(ge_ctx *ctx, int pop, std::vector<uint64_t> &off, std::vector<uint4> &seg, std::vector<uint64_t> &hoff, std::vector<uint32_t> &hbp) {
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists (GE_REP_SEGMENTS not enabled)");
+    uint64_t n_slots = S.n * ctx->cfg.n_chr * 2;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    off.resize(n_slots + 1); seg.resize(S.seg.n_seg);
+    CUDA_TRY(cudaMemcpy(off.data(), S.seg.off.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));
+    if (S.seg.n_seg) CUDA_TRY(cudaMemcpy(seg.data(), S.seg.seg.p, S.seg.n_seg * 16, cudaMemcpyDeviceToHost));
+    hoff.assign(n_slots + 1, 0); hbp.clear();
+    if (S.has_hm) {
+        CUDA_TRY(cudaMemcpy(hoff.data(), S.hm_off.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));
+        hbp.resize(S.n_hm);
+        if (S.n_hm) CUDA_TRY(cudaMemcpy(hbp.data(), S.hm_bp.p, S.n_hm * 4, cudaMemcpyDeviceToHost));
+    }
+    return GE_OK;
+}
+
+static int seg_count(ge_ctx *ctx, int pop, int c, uint64_t *ns, uint64_t *nm) {
+    std::vector<uint64_t> off, hoff; std::vector<uint4> seg; std::vector<uint32_t> hbp;
+    GE_TRY(seg_host_copy(ctx, pop, off, seg, hoff, hbp));
+    uint64_t n = ctx->pop[pop].st[ctx->pop[pop].cur].n; int C = ctx->cfg.n_chr;
+    uint64_t a = 0, b = 0;
+    for (uint64_t i = 0; i < n; i++) for (int h = 0; h < 2; h++) { uint64_t s = (i * C + c) * 2 + h; a += off[s + 1] - off[s]; b += hoff[s + 1] - hoff[s]; }
+    *ns = a; *nm = b;
+    return GE_OK;
+}
+
+static int seg_download(ge_ctx *ctx, int pop, int c, uint64_t *o_off, uint64_t *o_seg, uint64_t *o_moff, uint64_t *o_mbp) {
+    std::vector<uint64_t> off, hoff; std::vector<uint4> seg; std::vector<uint32_t> hbp;
+    GE_TRY(seg_host_copy(ctx, pop, off, seg, hoff, hbp));
+    uint64_t n = ctx->pop[pop].st[ctx->pop[pop].cur].n; int C = ctx->cfg.n_chr;
+    uint64_t a = 0, b = 0;
+    for (uint64_t i = 0; i < n; i++)
+        for (int h = 0; h < 2; h++) {
+            uint64_t s = (i * C + c) * 2 + h;
+            o_off[i * 2 + h] = a;
+            if (o_moff) o_moff[i * 2 + h] = b;
+            for (uint64_t e = off[s]; e < off[s + 1]; e++, a++) { o_seg[a * 4] = seg[e].x; o_seg[a * 4 + 1] = seg[e].y; o_seg[a * 4 + 2] = seg[e].z; o_seg[a * 4 + 3] = seg[e].w; }
+            for (uint64_t e = hoff[s]; e < hoff[s + 1]; e++, b++) if (o_mbp) o_mbp[b] = hbp[e];
+        }
+    o_off[2 * n] = a;
+    if (o_moff) o_moff[2 * n] = b;
+    return GE_OK;
+}
