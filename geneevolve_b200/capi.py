@@ -233,6 +233,10 @@ class Engine:
         r = _arr(row, np.float64)
         self._call("do_migration", self.ctx, gen, _ptr(r, _f64p))
 
+    def set_migration_sample(self, src_pop, positions):
+        a = _arr(positions, np.uint64)
+        self._call("set_migration_sample", self.ctx, src_pop, _ptr(a, _u64p), C.c_uint64(len(a)))
+
     def save_human_info_to_Pop_info_prev_gen(self, pop):
         self._call("save_human_info_to_Pop_info_prev_gen", self.ctx, pop)
 

@@ -769,6 +769,12 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
     return GE_OK;
 }
 
+int ge_set_migration_sample(ge_ctx *ctx, int src, const uint64_t *pos, uint64_t n) {
+    CHECK_POP(ctx, src);
+    ctx->mig_sample.resize(ctx->cfg.n_pop);
+    ctx->mig_sample[src].assign(pos, pos + n);
+    return GE_OK;
+}
 int ge_do_migration(ge_ctx *ctx, int gen, const double *row) {  // ras_do_migration :877-989
     CHECK_CTX(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));

@@ -101,6 +101,7 @@ struct ge_ctx {
     std::vector<PopDev> pop;
     std::vector<std::vector<uint64_t>> loci;  // host positions per chromosome
     std::vector<double> gamma;
+    std::vector<std::vector<uint64_t>> mig_sample;  // fixed-draw mode: migrants per source population
     Stream rng;
     // genome layout
     std::vector<uint32_t> chr_word_off, chr_nloci, locus_off;

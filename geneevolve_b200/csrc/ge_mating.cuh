@@ -287,4 +287,195 @@ static int mate_philox(ge_ctx *ctx, int pop, int gen, const ge_gen_params &gp) {
     return GE_OK;
 }
 
-static int migrate(ge_ctx *, int, const double *) { return fail(GE_ERR_UNSUPPORTED, "device migration is not built yet"); }
+
+// ------------------------------------------------------------------------------------------------
+// migration (ras_do_migration :877-989): whole individuals move between populations.  Each destination
+// population is rebuilt by gathering (source population, source position) pairs: its stayers in order, then
+// the camps of the other populations in (source, destination) order, each camp in descending source position
+// (the reference sorts the sample descending, :922).  Every per-individual column, the bit-packed rows, the CV
+// planes and the CSR lists (mutations, segments) are gathered on the device; only the small index lists are
+// built on the host.
+// ------------------------------------------------------------------------------------------------
+namespace gek {
+
+constexpr int MAX_POP = 16;
+struct PopPtrs { const void *p[MAX_POP]; uint64_t n[MAX_POP]; };
+
+__global__ void gather_rows_kernel(PopPtrs src, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst,
+                                   uint32_t rows_per_ind, uint32_t row_words, uint32_t *__restrict__ dst) {
+    // one CTA per destination row
+    uint64_t r = blockIdx.x;
+    if (r >= n_dst * rows_per_ind) return;
+    uint64_t k = r / rows_per_ind; uint32_t sub = (uint32_t)(r % rows_per_ind);
+    const uint32_t *s = static_cast<const uint32_t *>(src.p[gpop[k]]) + ((uint64_t)gidx[k] * rows_per_ind + sub) * row_words;
+    uint32_t *d = dst + r * row_words;
+    for (uint32_t w = threadIdx.x; w < row_words; w += blockDim.x) d[w] = s[w];
+}
+__global__ void gather_bytes_kernel(PopPtrs src, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst,
+                                    uint32_t bytes_per_ind, uint8_t *__restrict__ dst) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_dst * bytes_per_ind) return;
+    uint64_t k = t / bytes_per_ind; uint32_t b = (uint32_t)(t % bytes_per_ind);
+    dst[t] = static_cast<const uint8_t *>(src.p[gpop[k]])[(uint64_t)gidx[k] * bytes_per_ind + b];
+}
+// fp64 columns are stored [f*n + i] with n the population's own size
+__global__ void gather_f64_kernel(PopPtrs src, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst, int n_col,
+                                  double *__restrict__ dst) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_dst * n_col) return;
+    uint64_t k = t % n_dst; int f = (int)(t / n_dst);
+    int p = gpop[k];
+    dst[(uint64_t)f * n_dst + k] = static_cast<const double *>(src.p[p])[(uint64_t)f * src.n[p] + gidx[k]];
+}
+// CSR gather: slots_per_ind lists per individual; element = ELEM bytes
+__global__ void gather_csr_count_kernel(PopPtrs src_off, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst,
+                                        uint32_t slots_per_ind, uint32_t *__restrict__ cnt) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_dst * slots_per_ind) return;
+    uint64_t k = t / slots_per_ind; uint32_t sub = (uint32_t)(t % slots_per_ind);
+    const uint64_t *o = static_cast<const uint64_t *>(src_off.p[gpop[k]]);
+    uint64_t s = (uint64_t)gidx[k] * slots_per_ind + sub;
+    cnt[t] = o ? (uint32_t)(o[s + 1] - o[s]) : 0u;
+}
+template <class T>
+__global__ void gather_csr_fill_kernel(PopPtrs src_off, PopPtrs src_val, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx,
+                                       uint64_t n_dst, uint32_t slots_per_ind, const uint64_t *__restrict__ dst_off, T *__restrict__ dst) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_dst * slots_per_ind) return;
+    uint64_t k = t / slots_per_ind; uint32_t sub = (uint32_t)(t % slots_per_ind);
+    const uint64_t *o = static_cast<const uint64_t *>(src_off.p[gpop[k]]);
+    if (!o) return;
+    const T *v = static_cast<const T *>(src_val.p[gpop[k]]);
+    uint64_t s = (uint64_t)gidx[k] * slots_per_ind + sub;
+    uint64_t d = dst_off[t];
+    for (uint64_t e = o[s]; e < o[s + 1]; e++) dst[d++] = v[e];
+}
+__global__ void migrate_keys_kernel(Stream st, int pop, int gen, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t w[4];
+    draw(st, P_MIGRATE, pop, gen, k, 0, 0, w);
+    keys[k] = key64(w); idx[k] = (uint32_t)k;
+}
+
+}  // namespace gek
+
+static int migrate(ge_ctx *ctx, int gen, const double *row) {
+    int np = ctx->cfg.n_pop, C = ctx->cfg.n_chr, nf = ctx->cfg.n_phen;
+    if (np > MAX_POP) return fail(GE_ERR_UNSUPPORTED, "too many populations");
+    if (!row) return fail(GE_ERR_INVALID, "null migration row");
+    cudaStream_t st = ctx->stream;
+    std::vector<std::vector<uint64_t>> num_move(np, std::vector<uint64_t>(np, 0));
+    for (int i = 0; i < np; i++) {
+        double s = 0;
+        for (int j = 0; j < np; j++) s += row[i * np + j];
+        if (s < 0.99999 || s > 1.00001) return fail(GE_ERR_MIGRATION, "Error: The sum of columns in transition matrix in [--file_migration] must be 1.");
+    }
+    std::vector<uint64_t> n_old(np);
+    for (int i = 0; i < np; i++) n_old[i] = ctx->pop[i].st[ctx->pop[i].cur].n;
+    for (int i = 0; i < np; i++) for (int j = 0; j < np; j++) if (i != j) num_move[i][j] = (uint64_t)std::llround(row[i * np + j] * (double)n_old[i]);
+    // the migrants of every source population, sorted descending (:921-922)
+    std::vector<std::vector<uint64_t>> sample(np);
+    for (int i = 0; i < np; i++) {
+        uint64_t s = 0;
+        for (uint64_t v : num_move[i]) s += v;
+        if (s > n_old[i]) return fail(GE_ERR_MIGRATION, "more migrants than individuals");
+        if (ctx->cfg.rng_mode == GE_RNG_REPLAY) {
+            if ((int)ctx->mig_sample.size() <= i || ctx->mig_sample[i].size() != s) return fail(GE_ERR_INVALID, "replay mode: ge_set_migration_sample must supply the migrants");
+            sample[i] = ctx->mig_sample[i];
+        } else if (s) {
+            // uniform sample without replacement = the s smallest (Philox key, position) pairs
+            PopDev &P = ctx->pop[i];
+            MateScratch &M = P.mate;
+            uint64_t n = n_old[i];
+            GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8)); GE_TRY(ctx->ensure(M.idx_a, n * 4)); GE_TRY(ctx->ensure(M.idx_b, n * 4));
+            migrate_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->rng, i, gen, n, M.keys_a.as<uint64_t>(), M.idx_a.as<uint32_t>());
+            GE_TRY(ctx->check_launch("migrate_keys"));
+            GE_TRY(sort_pairs(ctx, M, M.keys_a.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n));
+            std::vector<uint32_t> h(s);
+            CUDA_TRY(cudaMemcpyAsync(h.data(), M.idx_b.p, s * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            sample[i].assign(h.begin(), h.end());
+        }
+        std::sort(sample[i].begin(), sample[i].end(), std::greater<uint64_t>());
+        for (uint64_t v : sample[i]) if (v >= n_old[i]) return fail(GE_ERR_INVALID, "migrant position out of range");
+    }
+    // gather lists per destination
+    std::vector<std::vector<uint8_t>> gp(np);
+    std::vector<std::vector<uint32_t>> gi(np);
+    for (int j = 0; j < np; j++) {
+        std::vector<uint8_t> gone(n_old[j], 0);
+        for (uint64_t v : sample[j]) gone[v] = 1;
+        for (uint64_t k = 0; k < n_old[j]; k++) if (!gone[k]) { gp[j].push_back((uint8_t)j); gi[j].push_back((uint32_t)k); }
+    }
+    for (int i = 0; i < np; i++) {
+        uint64_t k = 0;  // consecutive slices of the sample go to consecutive destinations (the reference does not
+        for (int j = 0; j < np; j++) {  // reset k, :924-936; identical whenever the reference itself survives)
+            if (i == j) continue;
+            for (uint64_t it = 0; it < num_move[i][j]; it++, k++) { gp[j].push_back((uint8_t)i); gi[j].push_back((uint32_t)sample[i][k]); }
+        }
+    }
+    for (int j = 0; j < np; j++) if (gp[j].size() > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "population outgrew capacity through migration");
+    // source tables
+    auto table = [&](auto getter) { PopPtrs t{}; for (int p = 0; p < np; p++) { GenState &S = ctx->pop[p].st[ctx->pop[p].cur]; t.p[p] = getter(S); t.n[p] = S.n; } return t; };
+    bool any_hm = false, any_seg = ctx->segs();
+    for (int p = 0; p < np; p++) any_hm |= ctx->pop[p].st[ctx->pop[p].cur].has_hm;
+    for (int j = 0; j < np; j++) {
+        PopDev &P = ctx->pop[j];
+        GenState &D = P.st[P.cur ^ 1];
+        uint64_t n = gp[j].size();
+        Buf d_gp, d_gi;
+        GE_TRY(ctx->upload(d_gp, gp[j])); GE_TRY(ctx->upload(d_gi, gi[j]));
+        const uint8_t *g8 = d_gp.as<uint8_t>(); const uint32_t *g32 = d_gi.as<uint32_t>();
+        if (n) {
+            if (ctx->bits()) {
+                gather_rows_kernel<<<(unsigned)(n * 2), 256, 0, st>>>(table([](GenState &S) { return S.hap.p; }), g8, g32, n, 2, ctx->W, D.hap.as<uint32_t>());
+                GE_TRY(ctx->check_launch("gather_rows"));
+            }
+            if (ctx->n_cv_tot) {
+                gather_bytes_kernel<<<nblk(n * 2 * ctx->n_cv_tot, 256), 256, 0, st>>>(table([](GenState &S) { return S.cv_allele.p; }), g8, g32, n, 2 * ctx->n_cv_tot, D.cv_allele.as<uint8_t>());
+                GE_TRY(ctx->check_launch("gather_cv"));
+                gather_bytes_kernel<<<nblk(n * 2 * ctx->n_cv_tot, 256), 256, 0, st>>>(table([](GenState &S) { return S.cv_root.p; }), g8, g32, n, 2 * ctx->n_cv_tot, D.cv_root.as<uint8_t>());
+                GE_TRY(ctx->check_launch("gather_cv_root"));
+            }
+            gather_bytes_kernel<<<nblk(n * 56, 256), 256, 0, st>>>(table([](GenState &S) { return S.ids.p; }), g8, g32, n, 56, D.ids.as<uint8_t>());
+            GE_TRY(ctx->check_launch("gather_ids"));
+            gather_bytes_kernel<<<nblk(n, 256), 256, 0, st>>>(table([](GenState &S) { return S.sex.p; }), g8, g32, n, 1, D.sex.as<uint8_t>());
+            GE_TRY(ctx->check_launch("gather_sex"));
+            struct Col { Buf GenState::*m; int cols; };
+            const Col cols[] = {{&GenState::A, nf}, {&GenState::D, nf}, {&GenState::G, nf}, {&GenState::C, nf}, {&GenState::E, nf}, {&GenState::F, nf},
+                                {&GenState::P, nf}, {&GenState::mv, 1}, {&GenState::sv, 1}, {&GenState::svf, 1}};
+            for (const Col &cc : cols) {
+                PopPtrs t{};
+                for (int p = 0; p < np; p++) { GenState &S = ctx->pop[p].st[ctx->pop[p].cur]; t.p[p] = (S.*(cc.m)).p; t.n[p] = S.n; }
+                gather_f64_kernel<<<nblk(n * cc.cols, 256), 256, 0, st>>>(t, g8, g32, n, cc.cols, (D.*(cc.m)).as<double>());
+                GE_TRY(ctx->check_launch("gather_f64"));
+            }
+        }
+        uint32_t spi = (uint32_t)(C * 2);
+        if (any_hm) {
+            PopPtrs to = table([](GenState &S) { return S.has_hm ? S.hm_off.p : nullptr; }), tv = table([](GenState &S) { return S.hm_bp.p; });
+            GE_TRY(ctx->ensure(P.cnt32, (n * spi + 1) * 4)); GE_TRY(ctx->ensure(D.hm_off, (n * spi + 1) * 8));
+            if (n) { gather_csr_count_kernel<<<nblk(n * spi, 256), 256, 0, st>>>(to, g8, g32, n, spi, P.cnt32.as<uint32_t>()); GE_TRY(ctx->check_launch("gather_csr_count")); }
+            GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n * spi, D.hm_off.as<uint64_t>(), &D.n_hm));
+            GE_TRY(ctx->ensure(D.hm_bp, std::max<uint64_t>(D.n_hm, 1) * 4));
+            if (n) { gather_csr_fill_kernel<uint32_t><<<nblk(n * spi, 256), 256, 0, st>>>(to, tv, g8, g32, n, spi, D.hm_off.as<uint64_t>(), D.hm_bp.as<uint32_t>()); GE_TRY(ctx->check_launch("gather_csr_fill")); }
+            D.has_hm = true;
+        } else D.has_hm = false;
+        if (any_seg) {
+            PopPtrs to = table([](GenState &S) { return S.seg.valid ? S.seg.off.p : nullptr; }), tv = table([](GenState &S) { return S.seg.seg.p; });
+            GE_TRY(ctx->ensure(P.cnt32, (n * spi + 1) * 4)); GE_TRY(ctx->ensure(D.seg.off, (n * spi + 1) * 8));
+            if (n) { gather_csr_count_kernel<<<nblk(n * spi, 256), 256, 0, st>>>(to, g8, g32, n, spi, P.cnt32.as<uint32_t>()); GE_TRY(ctx->check_launch("gather_csr_count")); }
+            GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n * spi, D.seg.off.as<uint64_t>(), &D.seg.n_seg));
+            GE_TRY(ctx->ensure(D.seg.seg, std::max<uint64_t>(D.seg.n_seg, 1) * 16));
+            if (n) { gather_csr_fill_kernel<uint4><<<nblk(n * spi, 256), 256, 0, st>>>(to, tv, g8, g32, n, spi, D.seg.off.as<uint64_t>(), D.seg.seg.as<uint4>()); GE_TRY(ctx->check_launch("gather_csr_fill")); }
+            D.seg.valid = true;
+        }
+        D.n = n;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->release(d_gp); ctx->release(d_gi);
+    }
+    for (int j = 0; j < np; j++) ctx->pop[j].cur ^= 1;
+    ctx->mig_sample.clear();
+    return GE_OK;
+}

@@ -168,6 +168,9 @@ int ge_environmental_effects_specific_to_each_population(ge_ctx *ctx, int phen);
 int ge_compute_mating_value_selection_value(ge_ctx *ctx, int pop, int gen, const ge_gen_params *params);
 /* bool ras_do_migration(int gen_ind) :877-989; row = migration_mat_gen[gen-1], n_pop*n_pop entries. */
 int ge_do_migration(ge_ctx *ctx, int gen, const double *migration_row);
+/* Fixed-draw mode only: the individuals ras_SampleWithoutReplacement (src/RasRandomNumber.cpp:90-120) picked in
+ * population src_pop for the next ge_do_migration (positions in that population, any order). */
+int ge_set_migration_sample(ge_ctx *ctx, int src_pop, const uint64_t *positions, uint64_t n);
 /* bool ras_save_human_info_to_Pop_info_prev_gen(int ipop) :3211-3236. */
 int ge_save_human_info_to_Pop_info_prev_gen(ge_ctx *ctx, int pop);
 

@@ -172,6 +172,7 @@ struct go_ctx {
     std::vector<double> gamma;
     std::default_random_engine glob_generator;  // src/Simulation.h:137
     Stream stream;
+    std::vector<std::vector<uint64_t>> mig_sample;  // replay: supplied migrant positions per source population
     std::default_random_engine mig_engine;  // the `static` engine of ras_SampleWithoutReplacement
     bool mig_engine_seeded = false;
 
@@ -1025,6 +1026,9 @@ struct go_ctx {
                     if ((N - t) * u >= n - m) t++;
                     else { sample[m] = t; t++; m++; }
                 }
+            } else if (rng_mode == GE_RNG_REPLAY) {
+                if ((int)mig_sample.size() <= i || mig_sample[i].size() != s) return fail(GE_ERR_INVALID, "replay mode: go_set_migration_sample must supply the migrants");
+                sample = mig_sample[i];
             } else {
                 // the s smallest (key, index) pairs: a uniform sample without replacement
                 uint64_t N = pop[i].n;
@@ -1203,6 +1207,12 @@ int go_scale_AD_compute_GEF(go_ctx *ctx, int pop, int gen, int phen, const doubl
 int go_environmental_effects_specific_to_each_population(go_ctx *ctx, int phen) { return ctx->env_effects(phen); }
 int go_compute_mating_value_selection_value(go_ctx *ctx, int pop, int gen, const ge_gen_params *gp) { CHECK_POP(ctx, pop); return ctx->compute_mv_sv(pop, gen, gp); }
 int go_do_migration(go_ctx *ctx, int gen, const double *row) { return ctx->do_migration(gen, row); }
+int go_set_migration_sample(go_ctx *ctx, int src, const uint64_t *pos, uint64_t n) {
+    CHECK_POP(ctx, src);
+    ctx->mig_sample.resize(ctx->cfg.n_pop);
+    ctx->mig_sample[src].assign(pos, pos + n);
+    return GE_OK;
+}
 int go_save_human_info_to_Pop_info_prev_gen(go_ctx *ctx, int pop) { CHECK_POP(ctx, pop); ctx->save_prev(pop); return GE_OK; }
 int go_step_generation(go_ctx *ctx, int gen, const ge_gen_params *gp, const double *mig, const ge_draws *dr) { return ctx->step_generation(gen, gp, mig, dr); }
 

@@ -47,6 +47,7 @@ int go_scale_AD_compute_GEF(go_ctx *ctx, int pop, int gen, int phen, const doubl
 int go_environmental_effects_specific_to_each_population(go_ctx *ctx, int phen);
 int go_compute_mating_value_selection_value(go_ctx *ctx, int pop, int gen, const ge_gen_params *params);
 int go_do_migration(go_ctx *ctx, int gen, const double *migration_row);
+int go_set_migration_sample(go_ctx *ctx, int src_pop, const uint64_t *positions, uint64_t n);
 int go_save_human_info_to_Pop_info_prev_gen(go_ctx *ctx, int pop);
 int go_step_generation(go_ctx *ctx, int gen, const ge_gen_params *params, const double *migration_row, const ge_draws *draws);
 int go_get_population_size(go_ctx *ctx, int pop, uint64_t *n);

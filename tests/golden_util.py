@@ -102,3 +102,19 @@ class Golden:
                     found[i] = True
         assert found.all()
         return out
+
+    def migration_sample(self, gen, pop):
+        """Positions (in the pre-migration population `pop`) of the individuals the reference moved out in
+        generation `gen`: the stayers head the post-migration population in their original order."""
+        n_pre = len(self.g(gen, pop, "premig_ids"))
+        row = self.migration_row(gen).reshape(self.n_pop, self.n_pop)
+        s = sum(int(round(row[pop, j] * n_pre)) for j in range(self.n_pop) if j != pop)
+        stay = self.g(gen, pop, "ids")[:n_pre - s, 0]
+        return np.array(sorted(set(range(n_pre)) - set(int(x) for x in stay), reverse=True), dtype=np.uint64)
+
+    def step_replay(self, eng, gen):
+        """One generation with the reference's draws through the composite entry point."""
+        if self.n_pop > 1:
+            for p in range(self.n_pop):
+                eng.set_migration_sample(p, self.migration_sample(gen, p))
+        eng.step_generation(gen, self.all_params(gen), self.migration_row(gen), [self.draws(gen, p) for p in range(self.n_pop)])

@@ -25,7 +25,7 @@ def covered_hits(G, d, pop):
     return out
 
 
-@pytest.mark.parametrize("name", [s for s in SCENARIOS if not s.startswith("D_")])
+@pytest.mark.parametrize("name", SCENARIOS)
 def test_philox_generation_matches_oracle(cuda_lib, name):
     G = Golden(name)
     gpu = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=400))
@@ -36,27 +36,29 @@ def test_philox_generation_matches_oracle(cuda_lib, name):
     for gen in range(0, G.G + 1):
         if gen:
             try:
-                gpu.step_generation(gen, G.all_params(gen))
+                gpu.step_generation(gen, G.all_params(gen), G.migration_row(gen))
             except capi.GeneEvolveError as e:
                 # tiny inbreeding-avoiding populations can run out of marriageable couples: the oracle must
                 # stop in the same generation with the same error
                 with pytest.raises(capi.GeneEvolveError) as e2:
-                    cpu.step_generation(gen, G.all_params(gen))
+                    cpu.step_generation(gen, G.all_params(gen), G.migration_row(gen))
                 assert e2.value.code == e.code
                 return
-            cpu.step_generation(gen, G.all_params(gen))
-            a, b = gpu.get_couples(0), cpu.get_couples(0)
-            for k in a:
-                assert np.array_equal(a[k], b[k]), f"{name} gen {gen}: couples {k}"
-            da, db = gpu.draws(0), cpu.draws(0)
-            for k in ("father", "mother", "sex", "xo_off", "xo_bp", "start_hap"):
-                assert np.array_equal(da[k], db[k]), f"{name} gen {gen}: draw {k}"
-            assert covered_hits(G, da, 0) == covered_hits(G, db, 0)
-        a, b = gpu.individuals(0), cpu.individuals(0)
-        assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["sex"], b["sex"])
-        for k in FLOAT_KEYS:
-            np.testing.assert_allclose(a[k], b[k], rtol=1e-9, atol=1e-11, err_msg=f"{name} gen {gen} {k}")
-        for c in range(G.n_chr):
-            assert np.array_equal(gpu.haplotypes(0, c), cpu.haplotypes(0, c)), f"{name} gen {gen} chr {c}"
-            for f in range(G.n_phen):
-                assert np.array_equal(gpu.cv_alleles(0, f, c), cpu.cv_alleles(0, f, c))
+            cpu.step_generation(gen, G.all_params(gen), G.migration_row(gen))
+            for p in range(G.n_pop):
+                a, b = gpu.get_couples(p), cpu.get_couples(p)
+                for k in a:
+                    assert np.array_equal(a[k], b[k]), f"{name} gen {gen}: couples {k}"
+                da, db = gpu.draws(p), cpu.draws(p)
+                for k in ("father", "mother", "xo_off", "xo_bp", "start_hap") + (("sex",) if G.n_pop == 1 else ()):
+                    assert np.array_equal(da[k], db[k]), f"{name} gen {gen}: draw {k}"
+                assert covered_hits(G, da, p) == covered_hits(G, db, p)
+        for p in range(G.n_pop):
+            a, b = gpu.individuals(p), cpu.individuals(p)
+            assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["sex"], b["sex"])
+            for k in FLOAT_KEYS:
+                np.testing.assert_allclose(a[k], b[k], rtol=1e-9, atol=1e-11, err_msg=f"{name} gen {gen} {k}")
+            for c in range(G.n_chr):
+                assert np.array_equal(gpu.haplotypes(p, c), cpu.haplotypes(p, c)), f"{name} gen {gen} chr {c}"
+                for f in range(G.n_phen):
+                    assert np.array_equal(gpu.cv_alleles(p, f, c), cpu.cv_alleles(p, f, c))

@@ -16,7 +16,7 @@ FLOAT_KEYS = ["A", "D", "G", "C", "E", "F", "P", "mv", "sv", "svf"]
 
 
 def step_replay(G, eng, gen):
-    eng.step_generation(gen, G.all_params(gen), None, [G.draws(gen, p) for p in range(G.n_pop)])
+    G.step_replay(eng, gen)
 
 
 def compare_to_golden(G, eng, gen, pops=None):
@@ -31,7 +31,7 @@ def compare_to_golden(G, eng, gen, pops=None):
             assert np.array_equal(eng.haplotypes(p, c), G.g(gen, p, f"c{c}.hap")), f"{G.name} gen {gen} chr {c}: haplotypes"
 
 
-@pytest.mark.parametrize("name", [s for s in SCENARIOS if not s.startswith("D_")])
+@pytest.mark.parametrize("name", SCENARIOS)
 @pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS])
 def test_replay_matches_reference(cuda_lib, name, rep):
     G = Golden(name)
@@ -41,25 +41,27 @@ def test_replay_matches_reference(cuda_lib, name, rep):
         G.configure(e)
         e.init_generation0([G.draws0(p) for p in range(G.n_pop)])
     compare_to_golden(G, gpu, 0)
-    for f in range(G.n_phen):
-        a, b = gpu.gen0_constants(0, f), cpu.gen0_constants(0, f)
-        for k in a:
-            assert a[k] == pytest.approx(b[k], rel=1e-12, abs=1e-14)
+    for p in range(G.n_pop):
+        for f in range(G.n_phen):
+            a, b = gpu.gen0_constants(p, f), cpu.gen0_constants(p, f)
+            for k in a:
+                assert a[k] == pytest.approx(b[k], rel=1e-12, abs=1e-14)
     for gen in range(1, G.G + 1):
         step_replay(G, gpu, gen)
         step_replay(G, cpu, gen)
         compare_to_golden(G, gpu, gen)
-        for c in range(G.n_chr):
+        for p in range(G.n_pop):
+            for c in range(G.n_chr):
+                for f in range(G.n_phen):
+                    assert np.array_equal(gpu.cv_alleles(p, f, c), cpu.cv_alleles(p, f, c)), "causal-variant alleles"
+                if rep & capi.GE_REP_SEGMENTS:
+                    s, r = gpu.segments(p, c), cpu.segments(p, c)
+                    assert np.array_equal(s["seg_off"], r["seg_off"]) and np.array_equal(s["seg"], r["seg"]), "segments"
+                    assert np.array_equal(s["seg"], G.g(gen, p, f"c{c}.seg"))
+                    assert np.array_equal(s["mut_off"], r["mut_off"])
+                    for k in range(len(s["mut_off"]) - 1):
+                        assert np.array_equal(np.sort(s["mut_bp"][s["mut_off"][k]:s["mut_off"][k + 1]]), np.sort(r["mut_bp"][r["mut_off"][k]:r["mut_off"][k + 1]]))
             for f in range(G.n_phen):
-                assert np.array_equal(gpu.cv_alleles(0, f, c), cpu.cv_alleles(0, f, c)), "causal-variant alleles"
-            if rep & capi.GE_REP_SEGMENTS:
-                s, r = gpu.segments(0, c), cpu.segments(0, c)
-                assert np.array_equal(s["seg_off"], r["seg_off"]) and np.array_equal(s["seg"], r["seg"]), "segments"
-                assert np.array_equal(s["seg"], G.g(gen, 0, f"c{c}.seg"))
-                assert np.array_equal(s["mut_off"], r["mut_off"])
-                for k in range(len(s["mut_off"]) - 1):
-                    assert np.array_equal(np.sort(s["mut_bp"][s["mut_off"][k]:s["mut_off"][k + 1]]), np.sort(r["mut_bp"][r["mut_off"][k]:r["mut_off"][k + 1]]))
-        for f in range(G.n_phen):
-            m, r = gpu.moments(0, f), cpu.moments(0, f)
-            for k in m:
-                assert m[k] == pytest.approx(r[k], rel=1e-9, abs=1e-12)
+                m, r = gpu.moments(p, f), cpu.moments(p, f)
+                for k in m:
+                    assert m[k] == pytest.approx(r[k], rel=1e-9, abs=1e-12)
