@@ -47,6 +47,9 @@ class ge_moments(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("var_A", "var_D", "var_G", "var_C", "var_E", "var_F", "var_P", "h2")]
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
+
+
 class GeneEvolveError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"[{code}] {msg}")
@@ -177,6 +180,24 @@ class Engine:
 
     def set_pheno_scheme(self, pop, phen, va, vd, ve, vc=0.0, vf=0.0, omega=1.0, beta=0.0, lam=1.0):
         self._call("set_pheno_scheme", self.ctx, pop, phen, *[C.c_double(x) for x in (va, vd, ve, vc, vf, omega, beta, lam)])
+
+    def set_chromosome_ids(self, global_ids):
+        a = _arr(global_ids, np.int32)
+        assert len(a) == self.n_chr
+        self._call("set_chromosome_ids", self.ctx, _ptr(a, _i32p))
+
+    def set_allreduce(self, fn):
+        """fn(ptr:int, count:int, stream:int) -> None must sum `count` doubles at `ptr` over all ranks."""
+        def thunk(user, buf, count, stream):
+            try:
+                fn(buf or 0, int(count), stream or 0)
+                return 0
+            except Exception as e:  # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._allreduce_cb = ALLREDUCE_FN(thunk)  # keep alive
+        self._call("set_allreduce", self.ctx, self._allreduce_cb, None)
 
     def set_gamma(self, gamma):
         g = _arr(gamma, np.float64)

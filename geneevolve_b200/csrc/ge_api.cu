@@ -51,6 +51,7 @@ static int build_genome(ge_ctx *ctx) {
     GE_TRY(ctx->upload(ctx->d_chr_nloci, ctx->chr_nloci));
     GE_TRY(ctx->upload(ctx->d_locus_off, ctx->locus_off));
     GE_TRY(ctx->upload(ctx->d_pos, pos));
+    GE_TRY(ctx->upload(ctx->d_chr_ids, ctx->chr_ids));
     // tile table: (chromosome, first chunk, chunk count), longest first so the warps of a CTA balance
     const uint32_t TILE = 512;  // 16-byte chunks per work item = 8 KB
     struct Item { uint32_t c, q0, nq; };
@@ -168,6 +169,8 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     c->rng.k0 = (uint32_t)cfg->seed; c->rng.k1 = (uint32_t)(cfg->seed >> 32);
     c->pop.resize(cfg->n_pop);
     c->loci.resize(cfg->n_chr);
+    c->chr_ids.resize(cfg->n_chr);
+    for (int k = 0; k < cfg->n_chr; k++) c->chr_ids[k] = (uint32_t)k;
     for (PopDev &P : c->pop) {
         P.rmap_bp.resize(cfg->n_chr); P.recom_prob.resize(cfg->n_chr); P.bp_dist.assign(cfg->n_chr, 1);
         P.mutmap_bp.resize(cfg->n_chr); P.mutmap_rate.resize(cfg->n_chr);
@@ -203,7 +206,7 @@ int ge_destroy(ge_ctx *ctx) {
     }
     for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
                    &ctx->d_cv_block_off, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks,
-                   &ctx->scan_total, &ctx->partial, &ctx->scalars, &ctx->flags})
+                   &ctx->scan_total, &ctx->partial, &ctx->scalars, &ctx->flags, &ctx->d_chr_ids, &ctx->ar_scratch})
         freeb(*b);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -269,6 +272,13 @@ int ge_set_pheno_scheme(ge_ctx *ctx, int pop, int phen, double va, double vd, do
     S.va = va; S.vd = vd; S.ve = ve; S.vc = vc; S.vf = vf; S.omega = omega; S.beta = beta; S.lambda = lambda;
     return GE_OK;
 }
+int ge_set_chromosome_ids(ge_ctx *ctx, const int32_t *ids) {
+    CHECK_CTX(ctx);
+    if (ctx->genome_ready) return fail(GE_ERR_INVALID, "ge_set_chromosome_ids after the genome layout was frozen");
+    for (int k = 0; k < ctx->cfg.n_chr; k++) { if (ids[k] < 0 || ids[k] > 32767) return fail(GE_ERR_INVALID, "bad chromosome id"); ctx->chr_ids[k] = (uint32_t)ids[k]; }
+    return GE_OK;
+}
+int ge_set_allreduce(ge_ctx *ctx, ge_allreduce_fn fn, void *user) { CHECK_CTX(ctx); ctx->allreduce = fn; ctx->allreduce_user = user; return GE_OK; }
 int ge_set_gamma(ge_ctx *ctx, const double *g) { CHECK_CTX(ctx); ctx->gamma.assign(g, g + ctx->cfg.n_phen); return GE_OK; }
 
 // ---------------- per-method entry points ----------------
@@ -293,7 +303,22 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
         ctx->cvset(), S.cv_allele.as<uint8_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.n,
         ctx->d_a_eff.as<double>(), ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), S.n, S.A.as<double>(), S.D.as<double>(), S.G.as<double>(),
         ctx->flags.as<int>());
-    return ctx->check_launch("genetic_value");
+    GE_TRY(ctx->check_launch("genetic_value"));
+    if (ctx->allreduce) {
+        // chromosome-sharded contexts hold partial sums over their own chromosomes: sum A, D, G over the ranks
+        size_t nb = (size_t)S.n * ctx->cfg.n_phen * 8;
+        GE_TRY(ctx->ensure(ctx->ar_scratch, 3 * nb));
+        char *sc = ctx->ar_scratch.as<char>();
+        CUDA_TRY(cudaMemcpyAsync(sc, S.A.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(sc + nb, S.D.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(sc + 2 * nb, S.G.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        int rc = ctx->allreduce(ctx->allreduce_user, reinterpret_cast<double *>(sc), 3 * nb / 8, (void *)ctx->stream);
+        if (rc != 0) return fail(GE_ERR_INVALID, "allreduce hook failed");
+        CUDA_TRY(cudaMemcpyAsync(S.A.p, sc, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(S.D.p, sc + nb, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(S.G.p, sc + 2 * nb, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return GE_OK;
 }
 
 static int scale_AD_compute_GEF_impl(ge_ctx *ctx, int pop, int gen, int f, const double *e_host, const double *f0_host) {  // :3075-3206

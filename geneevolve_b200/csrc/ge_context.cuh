@@ -102,6 +102,10 @@ struct ge_ctx {
     std::vector<std::vector<uint64_t>> loci;  // host positions per chromosome
     std::vector<double> gamma;
     std::vector<std::vector<uint64_t>> mig_sample;  // fixed-draw mode: migrants per source population
+    std::vector<uint32_t> chr_ids;                  // global chromosome index of each local chromosome
+    Buf d_chr_ids, ar_scratch;
+    ge_allreduce_fn allreduce = nullptr;
+    void *allreduce_user = nullptr;
     Stream rng;
     // genome layout
     std::vector<uint32_t> chr_word_off, chr_nloci, locus_off;
@@ -192,10 +196,12 @@ struct ge_ctx {
     }
     MapDev rmap(const PopDev &P) const {
         MapDev m; m.row_off = P.d_row_off.as<uint32_t>(); m.bp = P.d_bp.as<uint32_t>(); m.T = P.d_T.as<double>(); m.bp_dist = P.d_bp_dist.as<uint32_t>();
+        m.chr_id = d_chr_ids.as<uint32_t>();
         return m;
     }
     MapDev mmap(const PopDev &P) const {
         MapDev m; m.row_off = P.d_mrow_off.as<uint32_t>(); m.bp = P.d_mbp.as<uint32_t>(); m.T = P.d_mT.as<double>(); m.bp_dist = nullptr;
+        m.chr_id = d_chr_ids.as<uint32_t>();
         return m;
     }
     int check_launch(const char *what) {

@@ -553,6 +553,7 @@ struct MapDev {
     const uint32_t *bp;       // concatenated map rows
     const double *T;          // concatenated survival tables, chromosome c starts at row_off[c] + c (R_c + 1 entries)
     const uint32_t *bp_dist;  // [n_chr]
+    const uint32_t *chr_id;   // [n_chr] index in the full genome (Philox counter; differs from c on a sharded context)
 };
 __device__ __forceinline__ long long next_success(const double *T, uint32_t R, uint32_t j, double v) {
     if (j >= R || !(T[R] < v)) return -1;
@@ -576,7 +577,7 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int ge
     uint64_t o = FILL ? xo_off[slot] : 0;
     for (;;) {
         uint32_t w[4];
-        draw(st, P_XO, pop, gen, i, (uint32_t)(c * 2 + gam), blk, w);
+        draw(st, P_XO, pop, gen, i, m.chr_id[c] * 2u + (uint32_t)gam, blk, w);
         if (blk == 0 && !FILL) start_hap[slot] = (uint8_t)(w[3] & 1u);
         blk++;
         if (j >= R) break;
@@ -606,7 +607,7 @@ __global__ void sample_mut_kernel(Stream st, MapDev m, int n_chr, int pop, int g
     for (;;) {
         if (j >= R) break;
         uint32_t w[4];
-        draw(st, P_MUT, pop, gen, i, (uint32_t)c, blk++, w);
+        draw(st, P_MUT, pop, gen, i, m.chr_id[c], blk++, w);
         double v = (1.0 - u01(w[0], w[1])) * T[j];
         long long k = next_success(T, R, j, v);
         if (k < 0) break;

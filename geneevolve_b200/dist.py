@@ -1,0 +1,141 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed for the collective.
+
+Sharding axis: every rank holds ALL individuals but only ITS chromosomes.  A gamete's
+chromosomes are independent given the parents, so the HBM-bound propagation, the crossover/mutation sampling,
+the causal-variant planes and the allele counts are rank-local with no parent exchange at all; the one real
+exchange step is the sum over ranks of the per-individual partial genetic values (NCCL all-reduce of
+3 * n_phen * N doubles per population per generation), after which phenotypes, selection and mating are
+computed redundantly and identically on every rank (Philox draws are keyed by global indices).
+Sharding individuals instead would move 7/8 of every parental row over NVLink each generation (SURVEY.md §8e:
+~2.7 GB inbound per GPU per generation at 8 GPUs, ~3.5 ms at 770 GB/s, against ~1 ms of local HBM time).
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+
+def assign_chromosomes(weights, world_size):
+    """Longest-processing-time assignment of chromosomes (weights = loci per chromosome) to ranks."""
+    order = sorted(range(len(weights)), key=lambda c: -weights[c])
+    load = [0.0] * world_size
+    mine = [[] for _ in range(world_size)]
+    for c in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        mine[r].append(c)
+        load[r] += weights[c]
+    return [sorted(m) for m in mine]
+
+
+class _DevPtr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def cuda_allreduce_hook(device, group=None):
+    """Sum-allreduce of a raw device buffer on the library's stream through torch.distributed (NCCL)."""
+    import torch
+    import torch.distributed as dist
+
+    def hook(ptr, count, stream):
+        t = torch.as_tensor(_DevPtr(ptr, count), device=f"cuda:{device}")
+        ext = torch.cuda.ExternalStream(stream, device=device)
+        with torch.cuda.stream(ext):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return hook
+
+
+def host_allreduce_hook(group=None):
+    """Same for a host buffer (gloo) — used by the CPU tests of the sharding logic."""
+    import torch
+    import torch.distributed as dist
+
+    def hook(ptr, count, stream):
+        a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(count,))
+        t = torch.from_numpy(a)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return hook
+
+
+def bench_sharded(args, METRIC, UNIT):
+    """bench.py for WORLD_SIZE > 1: the same fixed workload, chromosomes spread over the ranks (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    from . import capi, workloads
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = workloads.make_workload(args.workload, n_override=args.n, loci_override=args.loci)
+    if len(cfg["chrs"]) < world:
+        raise SystemExit("workload has fewer chromosomes than ranks")
+    mine = assign_chromosomes(cfg["n_loci"], world)[rank]
+    M, N = sum(cfg["n_loci"]), cfg["n"]
+    cap = int(max(N, cfg["founders"]) * 1.03) + 1024
+    eng = capi.Engine(n_pop=1, n_chr=len(mine), n_phen=1, device=local, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX,
+                      seed=12345, capacity=cap, rank=rank, world_size=world)
+    workloads.configure_engine(eng, cfg, chrs_local=mine)
+    eng.set_allreduce(cuda_allreduce_hook(local))
+    eng.init_generation0()
+    gp = [capi.gen_params(N, cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
+    gen = 0
+    for _ in range(args.warmup):
+        gen += 1
+        eng.step_generation(gen, gp)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
+    out = {"ids": pin((cap, 7), torch.int64).view(np.uint64), "sex": pin((cap,), torch.uint8)}
+    for k in "ADGCEFP":
+        out[k] = pin((1, cap), torch.float64)
+    for k in ("mv", "sv", "svf"):
+        out[k] = pin((cap,), torch.float64)
+
+    def timed(e2e):
+        nonlocal gen
+        eng.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        work = 0
+        eng.timer_start()
+        for _ in range(args.steps):
+            gen += 1
+            eng.step_generation(gen, gp)
+            work += eng.population_size(0) * M
+            if e2e and rank == 0:
+                eng.individuals(0, out=out)  # every rank holds identical columns; rank 0 feeds the host writers
+        ms = eng.timer_stop()
+        eng.synchronize()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return work, float(t.item())
+
+    eng.set_profiling(True)
+    eng.reset_kernel_times()
+    from bench import ClockSampler
+    with ClockSampler(local) as clocks:
+        work, ms_dev = timed(False)
+    launches = eng.launch_count()
+    k_ms, k_n, k_bytes = eng.kernel_time(capi.GE_KERNEL_PROPAGATE_BITS)
+    eng.set_profiling(False)
+    work2, ms_e2e = timed(True)
+    kb = torch.tensor([k_bytes / max(k_ms, 1e-9) / 1e6], dtype=torch.float64, device="cuda")  # GB/s of this rank's kernel
+    dist.all_reduce(kb, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        pk = os.path.join(root, "MEASURED_PEAKS.json")
+        peak = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
+        achieved = float(kb.item()) / world  # mean per-GPU achieved GB/s
+        print(json.dumps({
+            "metric": METRIC, "value": work / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-packed + f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "individuals": N, "loci": M, "chromosomes": len(cfg["chrs"]), "parallelism": "chromosome-sharded x%d" % world,
+                       "chromosomes_rank0": mine, "collective": "all-reduce of 3*N doubles per generation (NCCL)",
+                       "l2": "inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (N * M / 4 / 1e9 / world)},
+            "e2e": {"value": work2 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,
+                    "d2h_bytes_per_step": capi.Engine.individual_bytes(N, 1), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "propagate_bits_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms_dev, "note": "per-GPU mean"},
+            "clocks": clocks.summary(), "cpu_baseline": None}))
+    dist.barrier()
+    dist.destroy_process_group()

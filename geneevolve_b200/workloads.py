@@ -88,16 +88,21 @@ def founder_words(cfg, c, rng):
     return w
 
 
-def configure_engine(eng, cfg, va=0.5, vd=0.0, ve=0.5, panel_seed=7):
-    rng = np.random.default_rng(panel_seed)
-    for c, pos in enumerate(cfg["loci"]):
-        eng.set_loci(c, pos)
+def configure_engine(eng, cfg, va=0.5, vd=0.0, ve=0.5, panel_seed=7, chrs_local=None):
+    """Feeds the workload to an engine.  chrs_local: indices (into cfg['chrs']) of the chromosomes this context
+    owns (multi-GPU chromosome sharding); the founder panel of a chromosome does not depend on the sharding."""
+    chrs_local = list(range(len(cfg["chrs"]))) if chrs_local is None else list(chrs_local)
+    if len(chrs_local) != len(cfg["chrs"]) or chrs_local != list(range(len(chrs_local))):
+        eng.set_chromosome_ids(chrs_local)
+    for k, c in enumerate(chrs_local):
+        eng.set_loci(k, cfg["loci"][c])
     eng.set_population(0, avoid_inbreeding=False, random_mating=cfg["rm"], mm_percent=0.0)
-    for c, (bp, cm, p) in enumerate(cfg["maps"]):
-        eng.set_genetic_map(0, c, bp, p, int(bp[1] - bp[0]))
-        eng.set_founder_panel_packed(0, c, founder_words(cfg, c, rng))
+    for k, c in enumerate(chrs_local):
+        bp, cm, p = cfg["maps"][c]
+        eng.set_genetic_map(0, k, bp, p, int(bp[1] - bp[0]))
+        eng.set_founder_panel_packed(0, k, founder_words(cfg, c, np.random.default_rng([panel_seed, c])))
         cv = cfg["cvs"][c]
-        eng.set_cv(0, 0, c, cv["bp"], cv["a"], cv["d"], cv["val"])
+        eng.set_cv(0, 0, k, cv["bp"], cv["a"], cv["d"], cv["val"])
     eng.set_pheno_scheme(0, 0, va=va, vd=vd, ve=ve, vc=0.0, vf=0.0, omega=1.0, beta=0.0, lam=1.0)
 
 

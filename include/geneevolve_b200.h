@@ -139,6 +139,18 @@ int ge_set_pheno_scheme(ge_ctx *ctx, int pop, int phen, double va, double vd, do
 /* Simulation::_gamma (:503-508). */
 int ge_set_gamma(ge_ctx *ctx, const double *gamma /* [n_phen] */);
 
+/* ---- multi-GPU: one context per GPU, each owning a subset of the chromosomes of EVERY individual (DESIGN.md
+ * §Multi-GPU).  Propagation, crossover sampling and allele counts are then rank-local; the only exchange is the
+ * sum over ranks of the per-individual partial genetic values inside ge_compute_AD. ----
+ * global_ids[c] = index of local chromosome c in the full genome; keys the Philox counters so that draws do
+ * not depend on the sharding.  Default: identity. */
+int ge_set_chromosome_ids(ge_ctx *ctx, const int32_t *global_ids /* [n_chr] */);
+/* Sum-allreduce hook: must leave the element-wise sum over all ranks in dev_buf (count doubles, device memory),
+ * ordered after the work already queued on cuda_stream and complete (or stream-ordered) on return.
+ * The Python host wires torch.distributed/NCCL (geneevolve_b200/dist.py); a C++ host can wire ncclAllReduce. */
+typedef int (*ge_allreduce_fn)(void *user, double *dev_buf, uint64_t count, void *cuda_stream);
+int ge_set_allreduce(ge_ctx *ctx, ge_allreduce_fn fn, void *user);
+
 /* ---- generation 0: Simulation::ras_init_generation0 (:529-679) + ras_initial_human_gen0 (:3000-3072) ----
  * draws0[pop] (GE_RNG_REPLAY) carries sex, e_raw, common for the founders; NULL in GE_RNG_PHILOX mode. */
 int ge_init_generation0(ge_ctx *ctx, const ge_draws *draws0 /* [n_pop] or NULL */);

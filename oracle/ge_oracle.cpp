@@ -172,6 +172,8 @@ struct go_ctx {
     std::vector<double> gamma;
     std::default_random_engine glob_generator;  // src/Simulation.h:137
     Stream stream;
+    std::vector<uint32_t> chr_ids;
+    ge_allreduce_fn allreduce = nullptr; void *allreduce_user = nullptr;
     std::vector<std::vector<uint64_t>> mig_sample;  // replay: supplied migrant positions per source population
     std::default_random_engine mig_engine;  // the `static` engine of ras_SampleWithoutReplacement
     bool mig_engine_seeded = false;
@@ -514,7 +516,7 @@ struct go_ctx {
         uint64_t R = P.recom_prob[c].size(), j = 0; uint32_t blk = 0;
         xo.clear();
         for (;;) {
-            uint32_t w[4]; stream.draw(P_XO, p, gen, i, (uint32_t)(c * 2 + g), blk, w);
+            uint32_t w[4]; stream.draw(P_XO, p, gen, i, chr_ids[c] * 2u + (uint32_t)g, blk, w);
             if (blk == 0) start = (int)(w[3] & 1u);
             blk++;
             if (j >= R) break;
@@ -530,7 +532,7 @@ struct go_ctx {
         uint64_t R = P.mut_rate[c].size(), j = 1; uint32_t blk = 0;
         for (;;) {
             if (j >= R) break;
-            uint32_t w[4]; stream.draw(P_MUT, p, gen, i, (uint32_t)c, blk++, w);
+            uint32_t w[4]; stream.draw(P_MUT, p, gen, i, chr_ids[c], blk++, w);
             double v = (1.0 - u01(w[0], w[1])) * T[j];
             int64_t k = next_success(T, j, v);
             if (k < 0) break;
@@ -824,6 +826,14 @@ struct go_ctx {
                 P.A[(uint64_t)f * n + i] = add; P.D[(uint64_t)f * n + i] = dom; P.G[(uint64_t)f * n + i] = bv;
                 P.A_raw[(uint64_t)f * n + i] = add; P.D_raw[(uint64_t)f * n + i] = dom;
             }
+        if (allreduce) {  // chromosome-sharded: sum the partial genetic values over the ranks
+            std::vector<double> buf;
+            buf.insert(buf.end(), P.A.begin(), P.A.end()); buf.insert(buf.end(), P.D.begin(), P.D.end()); buf.insert(buf.end(), P.G.begin(), P.G.end());
+            if (allreduce(allreduce_user, buf.data(), buf.size(), nullptr) != 0) return fail(GE_ERR_INVALID, "allreduce hook failed");
+            uint64_t m = P.A.size();
+            std::copy(buf.begin(), buf.begin() + m, P.A.begin()); std::copy(buf.begin() + m, buf.begin() + 2 * m, P.D.begin()); std::copy(buf.begin() + 2 * m, buf.end(), P.G.begin());
+            P.A_raw = P.A; P.D_raw = P.D;
+        }
         (void)gen;
         return GE_OK;
     }
@@ -1129,6 +1139,7 @@ int go_create(const ge_config *cfg, go_ctx **out) {
     c->cfg = *cfg; c->rng_mode = cfg->rng_mode;
     c->pop.resize(cfg->n_pop);
     c->loci.resize(cfg->n_chr);
+    for (int k = 0; k < cfg->n_chr; k++) c->chr_ids.push_back((uint32_t)k);
     c->stream.k0 = (uint32_t)cfg->seed; c->stream.k1 = (uint32_t)(cfg->seed >> 32);
     c->glob_generator.seed((unsigned)cfg->seed);  // Simulation::run :75-76
     for (Pop &P : c->pop) {
@@ -1179,6 +1190,8 @@ int go_set_pheno_scheme(go_ctx *ctx, int pop, int phen, double va, double vd, do
     S.va = va; S.vd = vd; S.ve = ve; S.vc = vc; S.vf = vf; S.omega = omega; S.beta = beta; S.lambda = lambda;
     return GE_OK;
 }
+int go_set_chromosome_ids(go_ctx *ctx, const int32_t *ids) { for (int k = 0; k < ctx->cfg.n_chr; k++) ctx->chr_ids[k] = (uint32_t)ids[k]; return GE_OK; }
+int go_set_allreduce(go_ctx *ctx, ge_allreduce_fn fn, void *user) { ctx->allreduce = fn; ctx->allreduce_user = user; return GE_OK; }
 int go_set_gamma(go_ctx *ctx, const double *g) { ctx->gamma.assign(g, g + ctx->cfg.n_phen); return GE_OK; }
 int go_init_generation0(go_ctx *ctx, const ge_draws *d0) { return ctx->init_generation0(d0); }
 int go_mate(go_ctx *ctx, int pop, int gen, const ge_gen_params *gp) { CHECK_POP(ctx, pop); return ctx->mate(pop, gen, *gp); }

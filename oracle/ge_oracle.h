@@ -36,6 +36,8 @@ int go_set_founder_panel(go_ctx *ctx, int pop, int chr, const uint8_t *alleles, 
 int go_set_cv(go_ctx *ctx, int pop, int phen, int chr, const uint64_t *bp, const double *a, const double *d, uint64_t n_cv, const uint8_t *founder_cv, uint64_t n_founder_haps);
 int go_set_pheno_scheme(go_ctx *ctx, int pop, int phen, double va, double vd, double ve, double vc, double vf, double omega, double beta, double lambda);
 int go_set_gamma(go_ctx *ctx, const double *gamma);
+int go_set_chromosome_ids(go_ctx *ctx, const int32_t *global_ids);
+int go_set_allreduce(go_ctx *ctx, ge_allreduce_fn fn, void *user); /* host buffer instead of a device buffer */
 int go_init_generation0(go_ctx *ctx, const ge_draws *draws0);
 int go_mate(go_ctx *ctx, int pop, int gen, const ge_gen_params *params);
 int go_set_couples(go_ctx *ctx, int pop, const uint64_t *pos_male, const uint64_t *pos_female, const uint8_t *inbreed, const int32_t *num_offspring, uint64_t n_couples);

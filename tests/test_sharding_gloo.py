@@ -1,0 +1,101 @@
+"""Multi-rank logic on CPU (world_size 2, gloo): chromosome-sharded engines + the sum-allreduce hook must
+reproduce the single-rank run — identical couples, draws and haplotypes (Philox counters carry global
+chromosome ids), fp64 columns to 1e-10 (the all-reduce changes the summation order of the chromosomes).
+The engines are CPU oracles standing in for the CUDA contexts: the host-side sharding logic (assignment,
+global ids, hook wiring, replicated mating) is the same code."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from geneevolve_b200 import capi, dist as gdist
+from golden_util import Golden
+from oracle.oracle import OracleEngine
+
+
+def configure_subset(G, eng, chrs):
+    z = G.z
+    eng.set_chromosome_ids(chrs)
+    for k, c in enumerate(chrs):
+        eng.set_loci(k, z[f"in.p0.c{c}.panel_pos"])
+    pre = "in.p0."
+    eng.set_population(0, bool(z[pre + "avoid_inbreeding"]), bool(z[pre + "RM"]), float(z[pre + "MM_percent"]))
+    for k, c in enumerate(chrs):
+        cp = pre + f"c{c}."
+        eng.set_genetic_map(0, k, z[cp + "rmap_bp"], z[cp + "recom_prob"], int(z[cp + "bp_dist"]))
+        if int(z[pre + "has_mutation_map"]):
+            eng.set_mutation_map(0, k, z[cp + "mut_bp"], z[cp + "mut_rate"])
+        eng.set_founder_panel(0, k, z[cp + "panel"])
+        for f in range(G.n_phen):
+            fp = cp + f"f{f}."
+            eng.set_cv(0, f, k, z[fp + "cv_bp"], z[fp + "cv_a"], z[fp + "cv_d"], z[fp + "cv_val"])
+    for f in range(G.n_phen):
+        s = z[pre + "scheme"][f]
+        eng.set_pheno_scheme(0, f, va=s[0], vd=s[1], ve=s[2], vc=s[3], vf=s[4], omega=s[5], beta=s[6], lam=s[7])
+
+
+def run_generations(G, eng, n_gen):
+    eng.init_generation0()
+    for gen in range(1, n_gen + 1):
+        eng.step_generation(gen, G.all_params(gen))
+    out = {"couples": eng.get_couples(0), "ind": eng.individuals(0)}
+    out["hap"] = [eng.haplotypes(0, k) for k in range(eng.n_chr)]
+    return out
+
+
+def worker(rank, world, port, name, n_gen, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    G = Golden(name)
+    weights = [len(G[f"in.p0.c{c}.panel_pos"]) for c in range(G.n_chr)]
+    mine = gdist.assign_chromosomes(weights, world)[rank]
+    kw = G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX)
+    kw.update(n_chr=len(mine), rank=rank, world_size=world)
+    eng = OracleEngine(**kw)
+    configure_subset(G, eng, mine)
+    eng.set_allreduce(gdist.host_allreduce_hook())
+    out = run_generations(G, eng, n_gen)
+    q.put((rank, mine, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_assign_chromosomes_balances():
+    w = [249, 243, 198, 191, 181, 171, 159, 146, 141, 135, 135, 133, 115, 107, 102, 90, 81, 78, 59, 63, 48, 51]
+    parts = gdist.assign_chromosomes(w, 8)
+    assert sorted(c for p in parts for c in p) == list(range(22))
+    loads = [sum(w[c] for c in p) for p in parts]
+    assert max(loads) <= 1.08 * sum(w) / 8
+
+
+@pytest.mark.parametrize("name", ["B_rm_mut", "A_am_pois"])
+def test_two_ranks_match_single_rank(name):
+    G = Golden(name)
+    n_gen = min(G.G, 3)
+    single = OracleEngine(**G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX))
+    G.configure(single)
+    ref = run_generations(G, single, n_gen)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, name, n_gen, q)) for r in range(2)]
+    [p.start() for p in procs]
+    results = [q.get(timeout=300) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    covered = []
+    for rank, mine, out in results:
+        for k in ("pos_male", "pos_female", "inbreed", "num_offspring"):
+            assert np.array_equal(out["couples"][k], ref["couples"][k]), f"rank {rank}: couples differ"
+        assert np.array_equal(out["ind"]["ids"], ref["ind"]["ids"]) and np.array_equal(out["ind"]["sex"], ref["ind"]["sex"])
+        for k in "ADGCEFP":
+            np.testing.assert_allclose(out["ind"][k], ref["ind"][k], rtol=1e-10, atol=1e-12)
+        for k, c in enumerate(mine):
+            assert np.array_equal(out["hap"][k], ref["hap"][c]), f"rank {rank}: chromosome {c} differs"
+            covered.append(c)
+    assert sorted(covered) == list(range(G.n_chr))
