@@ -16,7 +16,7 @@ static int alloc_gen_state(ge_ctx *ctx, GenState &s) {
     uint64_t cap = ctx->cfg.capacity;
     int nf = ctx->cfg.n_phen;
     if (ctx->bits()) GE_TRY(ctx->ensure_exact(s.hap, (size_t)cap * 2 * ctx->W * 4));
-    GE_TRY(ctx->ensure_exact(s.cv_allele, (size_t)cap * 2 * std::max<uint32_t>(ctx->n_cv_tot, 1)));
+    GE_TRY(ctx->ensure_exact(s.cv_allele, (size_t)cap * 2 * ctx->Wcv * 4));
     if (ctx->cfg.n_pop > 1) GE_TRY(ctx->ensure_exact(s.cv_root, (size_t)cap * 2 * std::max<uint32_t>(ctx->n_cv_tot, 1)));
     GE_TRY(ctx->ensure_exact(s.ids, (size_t)cap * 7 * 8));
     GE_TRY(ctx->ensure_exact(s.sex, (size_t)cap));
@@ -125,6 +125,17 @@ static int build_cvset(ge_ctx *ctx) {
             ctx->cv_block_off[(size_t)f * C + c + 1] = (uint32_t)bp.size();
         }
     ctx->n_cv_tot = (uint32_t)bp.size();
+    // bit-plane layout: every (phenotype, chromosome) block starts on a word boundary
+    ctx->cv_word_off.assign((size_t)nf * C + 1, 0);
+    std::vector<uint32_t> word_blk;
+    for (int b = 0; b < nf * C; b++) {
+        uint32_t nw = (ctx->cv_block_off[b + 1] - ctx->cv_block_off[b] + 31) / 32;
+        ctx->cv_word_off[b + 1] = ctx->cv_word_off[b] + nw;
+        word_blk.insert(word_blk.end(), nw, (uint32_t)b);
+    }
+    ctx->Wcv = std::max<uint32_t>((ctx->cv_word_off.back() + 3) & ~3u, 4);
+    word_blk.resize(ctx->Wcv, 0xFFFFFFFFu);
+    GE_TRY(ctx->upload(ctx->d_cv_word_off, ctx->cv_word_off)); GE_TRY(ctx->upload(ctx->d_cv_word_blk, word_blk));
     std::vector<double> a_eff((size_t)np * ctx->n_cv_tot), d_eff((size_t)np * ctx->n_cv_tot);
     for (int p = 0; p < np; p++)
         for (int f = 0; f < nf; f++)
@@ -179,8 +190,13 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
         P.panel.resize(cfg->n_chr);
         P.var_a0.assign(cfg->n_phen, 0); P.var_d0.assign(cfg->n_phen, 0);
     }
-    cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo);
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    for (PopDev &P : c->pop) for (DrawSet &D : P.ds) cudaEventCreateWithFlags(&D.bulk_done, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     if (c->ensure(c->flags, 64) != GE_OK) { delete c; return GE_ERR_CUDA; }
     cudaMemsetAsync(c->flags.p, 0, 64, c->stream);
@@ -191,13 +207,17 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
 int ge_destroy(ge_ctx *ctx) {
     if (!ctx) return GE_OK;
     cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->bulk);
     cudaStreamSynchronize(ctx->stream);
     auto freeb = [&](Buf &b) { ctx->release(b); };
     for (PopDev &P : ctx->pop) {
         for (Buf *b : {&P.d_row_off, &P.d_bp, &P.d_T, &P.d_bp_dist, &P.d_mrow_off, &P.d_mbp, &P.d_mT, &P.d_cov_lo, &P.d_cov_hi, &P.d_omega,
-                       &P.d_lambda, &P.d_vd_zero, &P.prev_P, &P.prev_F, &P.c_male, &P.c_female, &P.c_inbreed, &P.c_noff, &P.father, &P.mother,
-                       &P.couple_of, &P.xo_off, &P.xo_bp, &P.flips, &P.start_hap, &P.mut_off, &P.mut_bp, &P.mut_gam, &P.e_raw, &P.cnt32, &P.d_sv0, &P.founder_rows, &P.founder_cv})
+                       &P.d_lambda, &P.d_vd_zero, &P.prev_P, &P.prev_F, &P.c_male, &P.c_female, &P.c_inbreed, &P.c_noff, &P.mut_off, &P.mut_bp, &P.mut_gam, &P.e_raw, &P.cnt32, &P.d_sv0, &P.founder_rows, &P.founder_cv})
             freeb(*b);
+        for (DrawSet &D : P.ds) {
+            for (Buf *b : {&D.father, &D.mother, &D.couple_of, &D.xo_off, &D.xo_bp, &D.flips, &D.start_hap}) freeb(*b);
+            cudaEventDestroy(D.bulk_done);
+        }
         for (GenState &s : P.st) {
             for (Buf *b : {&s.hap, &s.cv_allele, &s.cv_root, &s.ids, &s.sex, &s.A, &s.D, &s.G, &s.C, &s.E, &s.F, &s.P, &s.mv, &s.sv, &s.svf, &s.hm_off, &s.hm_bp}) freeb(*b);
             seg_release(s.seg);
@@ -205,10 +225,13 @@ int ge_destroy(ge_ctx *ctx) {
         mate_release(P.mate);
     }
     for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
-                   &ctx->d_cv_block_off, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks,
+                   &ctx->d_cv_block_off, &ctx->d_cv_word_off, &ctx->d_cv_word_blk, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks,
                    &ctx->scan_total, &ctx->partial, &ctx->scalars, &ctx->flags, &ctx->d_chr_ids, &ctx->ar_scratch})
         freeb(*b);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_join);
+    for (auto &e : ctx->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->bulk);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GE_OK;
@@ -294,13 +317,13 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
     uint32_t ncv = ctx->n_cv_tot;
     if (ncv) {
         CUDA_TRY(cudaMemsetAsync(ctx->d_cv_count.p, 0, (size_t)ncv * 8, ctx->stream));
-        dim3 grid(nblk(ncv, 32), nblk(2 * S.n, 512));
-        cv_count_tiled_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(S.cv_allele.as<uint8_t>(), 2 * S.n, ncv, ctx->d_cv_count.as<unsigned long long>());
+        dim3 grid(nblk(ctx->Wcv, 32), nblk(2 * S.n, 512));
+        cv_count_bits_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), 2 * S.n, ctx->d_cv_count.as<unsigned long long>());
         GE_TRY(ctx->check_launch("cv_count"));
     }
     uint64_t nw = S.n * ctx->cfg.n_phen;
     genetic_value_kernel<<<nblk(nw * 32, 256), 256, 0, ctx->stream>>>(
-        ctx->cvset(), S.cv_allele.as<uint8_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.n,
+        ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.n,
         ctx->d_a_eff.as<double>(), ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), S.n, S.A.as<double>(), S.D.as<double>(), S.G.as<double>(),
         ctx->flags.as<int>());
     GE_TRY(ctx->check_launch("genetic_value"));
@@ -521,9 +544,9 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
         Buf &tmp = ctx->segs() ? P.founder_cv : tmp_local;
         GE_TRY(ctx->ensure_exact(tmp, fcv.size()));
         CUDA_TRY(cudaMemcpyAsync(tmp.p, fcv.data(), fcv.size(), cudaMemcpyHostToDevice, ctx->stream));
-        uint64_t tot = (uint64_t)2 * n * ctx->n_cv_tot;
+        uint64_t tot = (uint64_t)2 * n * ctx->Wcv;
         cv_init_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), tmp.as<uint8_t>(), (uint32_t)(2 * n), P.d_cov_lo.as<uint32_t>(), P.d_cov_hi.as<uint32_t>(),
-                                                                (uint8_t)p, S.cv_allele.as<uint8_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr);
+                                                                (uint8_t)p, S.cv_allele.as<uint32_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr);
         GE_TRY(ctx->check_launch("cv_init"));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ctx->release(tmp_local);
@@ -667,18 +690,22 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
     uint64_t n_off = 0;
     std::vector<uint32_t> tmp;
     cudaStream_t st = ctx->stream;
+    // the other draw set; the bulk stream may still read it for the generation before last
+    P.dcur ^= 1;
+    DrawSet &D = P.draws();
+    if (D.bulk_pending) { CUDA_TRY(cudaStreamWaitEvent(st, D.bulk_done, 0)); D.bulk_pending = false; }
     if (dr) {
         n_off = dr->n_offspring;
         if (n_off > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "offspring exceed capacity");
         if (!dr->father || !dr->mother || !dr->sex || !dr->xo_off || !dr->start_hap) return fail(GE_ERR_INVALID, "incomplete draws");
         for (uint64_t i = 0; i < n_off; i++) if (dr->father[i] >= par.n || dr->mother[i] >= par.n) return fail(GE_ERR_INVALID, "parent index out of range");
-        GE_TRY(upload_u64_as_u32(ctx, P.father, dr->father, n_off, tmp, "father"));
-        GE_TRY(upload_u64_as_u32(ctx, P.mother, dr->mother, n_off, tmp, "mother"));
+        GE_TRY(upload_u64_as_u32(ctx, D.father, dr->father, n_off, tmp, "father"));
+        GE_TRY(upload_u64_as_u32(ctx, D.mother, dr->mother, n_off, tmp, "mother"));
         uint64_t n_slots = n_off * C * 2;
         P.n_xo = dr->xo_off[n_slots];
-        GE_TRY(ctx->upload(P.xo_off, std::vector<uint64_t>(dr->xo_off, dr->xo_off + n_slots + 1)));
-        GE_TRY(upload_u64_as_u32(ctx, P.xo_bp, dr->xo_bp, P.n_xo, tmp, "crossover position"));
-        GE_TRY(ctx->upload(P.start_hap, std::vector<uint8_t>(dr->start_hap, dr->start_hap + n_slots)));
+        GE_TRY(ctx->upload(D.xo_off, std::vector<uint64_t>(dr->xo_off, dr->xo_off + n_slots + 1)));
+        GE_TRY(upload_u64_as_u32(ctx, D.xo_bp, dr->xo_bp, P.n_xo, tmp, "crossover position"));
+        GE_TRY(ctx->upload(D.start_hap, std::vector<uint8_t>(dr->start_hap, dr->start_hap + n_slots)));
         CUDA_TRY(cudaMemcpyAsync(off.sex.p, dr->sex, n_off, cudaMemcpyHostToDevice, st));
         if (dr->mut_off) {
             P.n_mut = dr->mut_off[n_off * C];
@@ -700,19 +727,19 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), P.n_couples, P.mate.fam_off.as<uint64_t>(), &n_off));
         if (n_off == 0) return fail(GE_ERR_NO_MATES, "no offspring");
         if (n_off > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "offspring (" + std::to_string(n_off) + ") exceed capacity");
-        GE_TRY(ctx->ensure(P.father, n_off * 4)); GE_TRY(ctx->ensure(P.mother, n_off * 4)); GE_TRY(ctx->ensure(P.couple_of, n_off * 4));
+        GE_TRY(ctx->ensure(D.father, n_off * 4)); GE_TRY(ctx->ensure(D.mother, n_off * 4)); GE_TRY(ctx->ensure(D.couple_of, n_off * 4));
         expand_couples_kernel<<<nblk(P.n_couples, 256), 256, 0, st>>>(P.n_couples, P.mate.fam_off.as<uint64_t>(), P.c_male.as<uint32_t>(), P.c_female.as<uint32_t>(),
-                                                                      P.father.as<uint32_t>(), P.mother.as<uint32_t>(), P.couple_of.as<uint32_t>());
+                                                                      D.father.as<uint32_t>(), D.mother.as<uint32_t>(), D.couple_of.as<uint32_t>());
         GE_TRY(ctx->check_launch("expand_couples"));
         P.have_couple_of = true;
         // crossovers: count, scan, fill
         uint64_t n_slots = n_off * C * 2;
-        GE_TRY(ctx->ensure(P.xo_off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(P.start_hap, n_slots));
-        sample_xo_kernel<false><<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, P.cnt32.as<uint32_t>(), nullptr, nullptr, P.start_hap.as<uint8_t>());
+        GE_TRY(ctx->ensure(D.xo_off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(D.start_hap, n_slots));
+        sample_xo_kernel<false><<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, P.cnt32.as<uint32_t>(), nullptr, nullptr, D.start_hap.as<uint8_t>());
         GE_TRY(ctx->check_launch("sample_xo<count>"));
-        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, P.xo_off.as<uint64_t>(), &P.n_xo));
-        GE_TRY(ctx->ensure(P.xo_bp, std::max<uint64_t>(P.n_xo, 1) * 4));
-        sample_xo_kernel<true><<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, nullptr, P.xo_off.as<uint64_t>(), P.xo_bp.as<uint32_t>(), nullptr);
+        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, D.xo_off.as<uint64_t>(), &P.n_xo));
+        GE_TRY(ctx->ensure(D.xo_bp, std::max<uint64_t>(P.n_xo, 1) * 4));
+        sample_xo_kernel<true><<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, nullptr, D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), nullptr);
         GE_TRY(ctx->check_launch("sample_xo<fill>"));
         if (P.has_mut) {
             uint64_t n_items = n_off * C;
@@ -729,47 +756,60 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         CUDA_TRY(cudaMemsetAsync(off.C.p, 0, (size_t)n_off * nf * 8, st));
         for (int f = 0; f < nf; f++)
             if (P.scheme[f].vc > 0) {
-                common_from_couples_kernel<<<nblk(n_off, 256), 256, 0, st>>>(ctx->rng, pop, gen, f, std::sqrt(P.scheme[f].vc), 0, n_off, P.couple_of.as<uint32_t>(),
+                common_from_couples_kernel<<<nblk(n_off, 256), 256, 0, st>>>(ctx->rng, pop, gen, f, std::sqrt(P.scheme[f].vc), 0, n_off, D.couple_of.as<uint32_t>(),
                                                                             off.C.as<double>() + (uint64_t)f * n_off);
                 GE_TRY(ctx->check_launch("common"));
             }
     }
     P.n_off = n_off;
     uint64_t n_slots = n_off * C * 2;
-    // ---- bit-packed propagation
+    // ---- bit-packed propagation: the HBM-bound bulk of the generation, on the bulk stream.  Nothing later on the
+    // control stream needs the rows (genetic values come from the causal-variant planes), so mating, sampling
+    // and phenotypes of the NEXT generation overlap with this copy.
+    bool bulk_launched = false;
     if (ctx->bits()) {
-        GE_TRY(ctx->ensure(P.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
-        xo_to_flips_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->genome(), n_slots, P.xo_off.as<uint64_t>(), P.xo_bp.as<uint32_t>(), P.flips.as<uint32_t>());
+        GE_TRY(ctx->ensure(D.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
+        xo_to_flips_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->genome(), n_slots, D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.flips.as<uint32_t>());
         GE_TRY(ctx->check_launch("xo_to_flips"));
+        CUDA_TRY(cudaEventRecord(ctx->ev_ready, st));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->bulk, ctx->ev_ready, 0));
         ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0};
-        if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, st)); }
-        unsigned grid = (unsigned)std::min<uint64_t>(n_off, (uint64_t)ctx->n_sm * 64);
-        propagate_bits_kernel<<<grid, PROP_THREADS, 0, st>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), P.father.as<uint32_t>(),
-                                                             P.mother.as<uint32_t>(), P.xo_off.as<uint64_t>(), P.flips.as<uint32_t>(), P.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
+        if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, ctx->bulk)); }
+        unsigned grid = (unsigned)std::min<uint64_t>(n_off, 1u << 20);  // one short-lived CTA per offspring: control-stream kernels get SM slots quickly
+        propagate_bits_kernel<<<grid, PROP_THREADS, 0, ctx->bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+                                                                    D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
         GE_TRY(ctx->check_launch("propagate_bits"));
         if (ctx->profiling) {
-            CUDA_TRY(cudaEventRecord(evp.b, st));
+            CUDA_TRY(cudaEventRecord(evp.b, ctx->bulk));
             uint64_t M = 0;
             for (uint32_t v : ctx->chr_nloci) M += v;
             evp.bytes = n_off * M / 2;  // 0.5 byte per individual-locus
             ctx->ev_pending.push_back(evp);
         }
+        CUDA_TRY(cudaEventRecord(D.bulk_done, ctx->bulk));
+        D.bulk_pending = true;
+        bulk_launched = true;
     }
     // ---- causal-variant planes
     if (ctx->n_cv_tot && (ctx->bits() || !ctx->segs())) {
-        uint64_t tot = n_off * 2 * ctx->n_cv_tot;
-        cv_propagate_kernel<<<nblk(tot, 256), 256, 0, st>>>(ctx->cvset(), par.cv_allele.as<uint8_t>(), ctx->cfg.n_pop > 1 ? par.cv_root.as<uint8_t>() : nullptr,
-                                                            off.cv_allele.as<uint8_t>(), ctx->cfg.n_pop > 1 ? off.cv_root.as<uint8_t>() : nullptr, P.father.as<uint32_t>(),
-                                                            P.mother.as<uint32_t>(), P.xo_off.as<uint64_t>(), P.xo_bp.as<uint32_t>(), P.start_hap.as<uint8_t>(), 0, n_off);
-        GE_TRY(ctx->check_launch("cv_propagate"));
+        uint64_t tot = n_off * 2 * ctx->Wcv;
+        cv_propagate_bits_kernel<<<nblk(tot, 256), 256, 0, st>>>(ctx->cvset(), par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
+                                                                 D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, n_off);
+        GE_TRY(ctx->check_launch("cv_propagate_bits"));
+        if (ctx->cfg.n_pop > 1) {
+            uint64_t tr = n_off * 2 * ctx->n_cv_tot;
+            cv_root_propagate_kernel<<<nblk(tr, 256), 256, 0, st>>>(ctx->cvset(), par.cv_root.as<uint8_t>(), off.cv_root.as<uint8_t>(), D.father.as<uint32_t>(), D.mother.as<uint32_t>(),
+                                                                    D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, n_off);
+            GE_TRY(ctx->check_launch("cv_root_propagate"));
+        }
     }
     // ---- founder segments
     if (ctx->segs()) GE_TRY(seg_recombine(ctx, pop, n_off));
     // ---- mutation lists (inherit + this generation's hits)
     if (P.has_mut || par.has_hm) {
         MutArgs a;
-        a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = P.father.as<uint32_t>(); a.mother = P.mother.as<uint32_t>();
-        a.xo_off = P.xo_off.as<uint64_t>(); a.xo_bp = P.xo_bp.as<uint32_t>(); a.start_hap = P.start_hap.as<uint8_t>();
+        a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = D.father.as<uint32_t>(); a.mother = D.mother.as<uint32_t>();
+        a.xo_off = D.xo_off.as<uint64_t>(); a.xo_bp = D.xo_bp.as<uint32_t>(); a.start_hap = D.start_hap.as<uint8_t>();
         a.par_hm_off = par.has_hm ? par.hm_off.as<uint64_t>() : nullptr; a.par_hm_bp = par.hm_bp.as<uint32_t>();
         bool hits = P.has_mut && (dr ? dr->mut_off != nullptr : true);
         a.mut_off = hits ? P.mut_off.as<uint64_t>() : nullptr; a.mut_bp = P.mut_bp.as<uint32_t>(); a.mut_gam = P.mut_gam.as<uint8_t>();
@@ -780,13 +820,14 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         GE_TRY(ctx->check_launch("mutation_lists<count>"));
         GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, off.hm_off.as<uint64_t>(), &off.n_hm));
         GE_TRY(ctx->ensure(off.hm_bp, std::max<uint64_t>(off.n_hm, 1) * 4));
+        if (bulk_launched) GE_TRY(ctx->join_bulk());  // the fill pass toggles bits of the freshly propagated rows
         mutation_lists_kernel<true><<<nblk(n_slots, 128), 128, 0, st>>>(a, ctx->genome(), ctx->cvset(), nullptr, off.hm_off.as<uint64_t>(), off.hm_bp.as<uint32_t>(),
-                                                                        ctx->bits() ? off.hap.as<uint32_t>() : nullptr, ctx->n_cv_tot ? off.cv_allele.as<uint8_t>() : nullptr);
+                                                                        ctx->bits() ? off.hap.as<uint32_t>() : nullptr, ctx->n_cv_tot ? off.cv_allele.as<uint32_t>() : nullptr);
         GE_TRY(ctx->check_launch("mutation_lists<fill>"));
         off.has_hm = true;
     } else off.has_hm = false;
     // ---- pedigree
-    pedigree_kernel<<<nblk(n_off, 256), 256, 0, st>>>(0, n_off, P.father.as<uint32_t>(), P.mother.as<uint32_t>(), par.ids.as<uint64_t>(), off.ids.as<uint64_t>());
+    pedigree_kernel<<<nblk(n_off, 256), 256, 0, st>>>(0, n_off, D.father.as<uint32_t>(), D.mother.as<uint32_t>(), par.ids.as<uint64_t>(), off.ids.as<uint64_t>());
     GE_TRY(ctx->check_launch("pedigree"));
     off.n = n_off;
     P.cur ^= 1;
@@ -884,6 +925,7 @@ int ge_download_haplotypes(ge_ctx *ctx, int pop, int c, uint8_t *al) {
     Buf tmp;
     GE_TRY(ctx->ensure_exact(tmp, tot));
     if (ctx->bits()) {
+        GE_TRY(ctx->join_bulk());
         unpack_rows_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), ctx->W, ctx->chr_word_off[c], (uint32_t)(2 * S.n), nl, tmp.as<uint8_t>());
         GE_TRY(ctx->check_launch("unpack_rows"));
     } else GE_TRY(seg_materialise(ctx, pop, c, tmp.as<uint8_t>()));
@@ -902,6 +944,7 @@ int ge_download_haplotypes_packed(ge_ctx *ctx, int pop, int c, uint32_t *words) 
     if (tot == 0) return GE_OK;
     Buf tmp;
     GE_TRY(ctx->ensure_exact(tmp, tot * 4));
+    GE_TRY(ctx->join_bulk());
     gather_packed_chr_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), ctx->W, ctx->chr_word_off[c], (uint32_t)(2 * S.n), nw, tmp.as<uint32_t>());
     GE_TRY(ctx->check_launch("gather_packed"));
     CUDA_TRY(cudaMemcpyAsync(words, tmp.p, tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -927,8 +970,14 @@ int ge_download_cv_alleles(ge_ctx *ctx, int pop, int f, int c, uint8_t *out) {
     GenState &S = ctx->pop[pop].st[ctx->pop[pop].cur];
     uint32_t b0 = ctx->cv_block_off[(size_t)f * ctx->cfg.n_chr + c], b1 = ctx->cv_block_off[(size_t)f * ctx->cfg.n_chr + c + 1];
     if (b1 == b0 || S.n == 0) return GE_OK;
+    uint64_t tot = 2 * S.n * (b1 - b0);
+    Buf tmp;
+    GE_TRY(ctx->ensure_exact(tmp, tot));
+    cv_unpack_block_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.cv_allele.as<uint32_t>(), ctx->Wcv, ctx->cv_word_off[(size_t)f * ctx->cfg.n_chr + c], b1 - b0, 2 * S.n, tmp.as<uint8_t>());
+    GE_TRY(ctx->check_launch("cv_unpack_block"));
+    CUDA_TRY(cudaMemcpyAsync(out, tmp.p, tot, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(cudaMemcpy2D(out, b1 - b0, S.cv_allele.as<uint8_t>() + b0, ctx->n_cv_tot, b1 - b0, 2 * S.n, cudaMemcpyDeviceToHost));
+    ctx->release(tmp);
     return GE_OK;
 }
 
@@ -944,6 +993,7 @@ int ge_download_draws(ge_ctx *ctx, int pop, uint64_t *fa, uint64_t *mo, uint8_t 
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
+    DrawSet &D = P.draws();
     int C = ctx->cfg.n_chr;
     uint64_t n = P.n_off, ns = n * C * 2;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -955,11 +1005,11 @@ int ge_download_draws(ge_ctx *ctx, int pop, uint64_t *fa, uint64_t *mo, uint8_t 
         for (uint64_t k = 0; k < cnt; k++) dst[k] = t[k];
         return GE_OK;
     };
-    GE_TRY(get32(P.father, n, fa)); GE_TRY(get32(P.mother, n, mo));
+    GE_TRY(get32(D.father, n, fa)); GE_TRY(get32(D.mother, n, mo));
     if (sex && n) CUDA_TRY(cudaMemcpy(sex, S.sex.p, n, cudaMemcpyDeviceToHost));
-    if (xo_off) CUDA_TRY(cudaMemcpy(xo_off, P.xo_off.p, (ns + 1) * 8, cudaMemcpyDeviceToHost));
-    GE_TRY(get32(P.xo_bp, P.n_xo, xo_bp));
-    if (start && ns) CUDA_TRY(cudaMemcpy(start, P.start_hap.p, ns, cudaMemcpyDeviceToHost));
+    if (xo_off) CUDA_TRY(cudaMemcpy(xo_off, D.xo_off.p, (ns + 1) * 8, cudaMemcpyDeviceToHost));
+    GE_TRY(get32(D.xo_bp, P.n_xo, xo_bp));
+    if (start && ns) CUDA_TRY(cudaMemcpy(start, D.start_hap.p, ns, cudaMemcpyDeviceToHost));
     if (mut_off) {
         if (P.has_mut && P.mut_off.p) CUDA_TRY(cudaMemcpy(mut_off, P.mut_off.p, (n * C + 1) * 8, cudaMemcpyDeviceToHost));
         else std::memset(mut_off, 0, (n * C + 1) * 8);
@@ -980,12 +1030,20 @@ int ge_get_kernel_time(ge_ctx *ctx, int k, double *ms, uint64_t *launches, uint6
 }
 int ge_reset_kernel_times(ge_ctx *ctx) { CHECK_CTX(ctx); ctx->resolve_events(); for (auto &k : ctx->kstat) k = KernelStat(); ctx->launches = 0; return GE_OK; }
 int ge_get_launch_count(ge_ctx *ctx, uint64_t *n) { CHECK_CTX(ctx); *n = ctx->launches; return GE_OK; }
-int ge_synchronize(ge_ctx *ctx) { CHECK_CTX(ctx); CUDA_TRY(cudaSetDevice(ctx->cfg.device)); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return GE_OK; }
+int ge_synchronize(ge_ctx *ctx) {
+    CHECK_CTX(ctx);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->bulk));
+    return GE_OK;
+}
 int ge_device_memory_bytes(ge_ctx *ctx, uint64_t *b) { CHECK_CTX(ctx); *b = ctx->mem_peak; return GE_OK; }
-int ge_timer_start(ge_ctx *ctx) { CHECK_CTX(ctx); CUDA_TRY(cudaSetDevice(ctx->cfg.device)); CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream)); return GE_OK; }
+// both streams are joined on either side, so the region covers the bulk propagation of every step queued in between
+int ge_timer_start(ge_ctx *ctx) { CHECK_CTX(ctx); CUDA_TRY(cudaSetDevice(ctx->cfg.device)); GE_TRY(ctx->join_bulk()); CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream)); return GE_OK; }
 int ge_timer_stop(ge_ctx *ctx, double *ms) {
     CHECK_CTX(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(ctx->join_bulk());
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaEventSynchronize(ctx->ev1));
     float f = 0;

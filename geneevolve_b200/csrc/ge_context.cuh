@@ -53,11 +53,19 @@ struct CvHost {  // one (phen, chr) block of one population
 
 struct GenState {  // one generation of one population on the device
     uint64_t n = 0;
-    Buf hap, cv_allele, cv_root, ids, sex, A, D, G, C, E, F, P, mv, sv, svf;
+    Buf hap, cv_allele /* bit plane [2n][Wcv] */, cv_root /* byte plane [2n][n_cv_tot], n_pop > 1 only */, ids, sex, A, D, G, C, E, F, P, mv, sv, svf;
     Buf hm_off, hm_bp;  // per-haplotype mutation lists (CSR over slots)
     uint64_t n_hm = 0;
     bool has_hm = false;
     SegState seg;       // founder segments (GE_REP_SEGMENTS)
+};
+
+// Draws of one reproduce call.  Double-buffered: the bulk stream may still be copying haplotype rows of
+// generation g from set g&1 while the control stream already samples generation g+1 into the other set.
+struct DrawSet {
+    Buf father, mother, couple_of, xo_off, xo_bp, flips, start_hap;
+    cudaEvent_t bulk_done = nullptr;   // recorded on the bulk stream after the propagation that reads this set
+    bool bulk_pending = false;
 };
 
 struct PopDev {
@@ -83,7 +91,10 @@ struct PopDev {
     Buf c_male, c_female, c_inbreed, c_noff;
     uint64_t n_couples = 0;
     // draws of the last reproduce
-    Buf father, mother, couple_of, xo_off, xo_bp, flips, start_hap, mut_off, mut_bp, mut_gam, e_raw, cnt32;
+    DrawSet ds[2];
+    int dcur = 0;
+    DrawSet &draws() { return ds[dcur]; }
+    Buf mut_off, mut_bp, mut_gam, e_raw, cnt32;
     uint64_t n_off = 0, n_xo = 0, n_mut = 0;
     bool have_couple_of = false, have_e_raw = false;
     // constants
@@ -97,7 +108,9 @@ struct KernelStat { double ms = 0; uint64_t launches = 0, bytes = 0; };
 
 struct ge_ctx {
     ge_config cfg;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;  // control stream (high priority): mating, sampling, CV planes, phenotypes
+    cudaStream_t bulk = nullptr;    // bulk stream (low priority): bit-packed haplotype propagation, one generation behind at most
+    cudaEvent_t ev_ready = nullptr, ev_join = nullptr;
     std::vector<PopDev> pop;
     std::vector<std::vector<uint64_t>> loci;  // host positions per chromosome
     std::vector<double> gamma;
@@ -117,8 +130,9 @@ struct ge_ctx {
     uint32_t n_tiles = 0;
     // causal-variant set
     std::vector<uint32_t> cv_block_off;  // [n_phen*n_chr+1]
-    uint32_t n_cv_tot = 0;
-    Buf d_cv_block_off, d_cv_bp, d_cv_chr, d_a_eff, d_d_eff, d_cv_count;
+    std::vector<uint32_t> cv_word_off;   // [n_phen*n_chr+1]
+    uint32_t n_cv_tot = 0, Wcv = 4;
+    Buf d_cv_word_off, d_cv_word_blk, d_cv_block_off, d_cv_bp, d_cv_chr, d_a_eff, d_d_eff, d_cv_count;
     bool cv_ready = false;
     // scratch
     Buf scan_blocks, scan_total, partial, scalars, flags;
@@ -185,7 +199,8 @@ struct ge_ctx {
     }
     CvSet cvset() const {
         CvSet c;
-        c.n_chr = cfg.n_chr; c.n_phen = cfg.n_phen; c.n_cv_tot = n_cv_tot;
+        c.n_chr = cfg.n_chr; c.n_phen = cfg.n_phen; c.n_cv_tot = n_cv_tot; c.Wcv = Wcv;
+        c.word_off = d_cv_word_off.as<uint32_t>(); c.word_blk = d_cv_word_blk.as<uint32_t>();
         c.block_off = d_cv_block_off.as<uint32_t>(); c.bp = d_cv_bp.as<uint32_t>(); c.chr_of = d_cv_chr.as<uint32_t>();
         return c;
     }
@@ -203,6 +218,12 @@ struct ge_ctx {
         MapDev m; m.row_off = P.d_mrow_off.as<uint32_t>(); m.bp = P.d_mbp.as<uint32_t>(); m.T = P.d_mT.as<double>(); m.bp_dist = nullptr;
         m.chr_id = d_chr_ids.as<uint32_t>();
         return m;
+    }
+    // the control stream waits for everything queued on the bulk stream (before it touches haplotype rows)
+    int join_bulk() {
+        CUDA_TRY(cudaEventRecord(ev_join, bulk));
+        CUDA_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
+        return GE_OK;
     }
     int check_launch(const char *what) {
         launches++;

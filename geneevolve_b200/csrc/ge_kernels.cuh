@@ -260,36 +260,86 @@ __global__ void gather_packed_chr_kernel(const uint32_t *__restrict__ rows, uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// Causal variants: a second, tiny locus set carried as byte planes (allele, root population) per haplotype.
-// Layout cv[(2*i+h) * n_cv_tot + k]; block (phen f, chromosome c) starts at cv_block_off[f*n_chr+c].
+// Causal variants: a second, tiny locus set carried as BIT planes, one row of Wcv u32 words per haplotype
+// (row 2*i+h).  Block (phenotype f, chromosome c) = CVs [block_off[b], block_off[b+1]) and starts on a word
+// boundary, word_off[b]; CV k of block b is bit (k - block_off[b]) of that block's words.  With 1 000 CVs on 22
+// chromosomes a row is 176 B, so the whole plane of a 100k population (35 MB) lives in L2.  With more than one
+// population the root population of every (haplotype, CV) is carried next to it as a byte plane
+// [row][n_cv_tot] because ras_find_cv takes the effect sizes a, d from the root population (:2776-2786).
 // ------------------------------------------------------------------------------------------------
 struct CvSet {
     int n_chr, n_phen;
     uint32_t n_cv_tot;
-    const uint32_t *block_off;  // [n_phen*n_chr + 1]
+    uint32_t Wcv;               // words per row (multiple of 4)
+    const uint32_t *block_off;  // [n_phen*n_chr + 1] first CV of each block
+    const uint32_t *word_off;   // [n_phen*n_chr + 1] first word of each block
+    const uint32_t *word_blk;   // [Wcv] block of each word, 0xFFFFFFFF for padding words
     const uint32_t *bp;         // [n_cv_tot] CV positions
     const uint32_t *chr_of;     // [n_cv_tot]
 };
 
-// generation 0: allele = founder CV allele when covered, root = population (ras_find_cv :2752-2815)
+// generation 0: allele = founder CV allele when covered, root = population (ras_find_cv :2752-2815).
+// One thread per (row, word).
 __global__ void cv_init_kernel(CvSet cs, const uint8_t *__restrict__ founder_cv /* [n_rows][n_cv_tot] */, uint32_t n_rows,
                                const uint32_t *__restrict__ cov_lo, const uint32_t *__restrict__ cov_hi, uint8_t root,
-                               uint8_t *__restrict__ allele, uint8_t *__restrict__ rootp) {
+                               uint32_t *__restrict__ bits, uint8_t *__restrict__ rootp) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint64_t)n_rows * cs.n_cv_tot) return;
-    uint32_t k = (uint32_t)(t % cs.n_cv_tot);
-    uint32_t c = cs.chr_of[k], p = cs.bp[k];
-    bool cov = p >= cov_lo[c] && p < cov_hi[c];
-    allele[t] = cov ? founder_cv[t] : 0;
-    if (rootp) rootp[t] = root;
+    if (t >= (uint64_t)n_rows * cs.Wcv) return;
+    uint32_t w = (uint32_t)(t % cs.Wcv);
+    uint64_t row = t / cs.Wcv;
+    uint32_t b = cs.word_blk[w], v = 0;
+    if (b != 0xFFFFFFFFu) {
+        uint32_t c = b % (uint32_t)cs.n_chr;
+        uint32_t k0 = cs.block_off[b] + (w - cs.word_off[b]) * 32u, k1 = min(k0 + 32u, cs.block_off[b + 1]);
+        uint32_t lo = cov_lo[c], hi = cov_hi[c];
+        for (uint32_t k = k0; k < k1; k++) {
+            uint32_t p = cs.bp[k];
+            if (p >= lo && p < hi && founder_cv[row * cs.n_cv_tot + k]) v |= 1u << (k - k0);
+            if (rootp) rootp[row * cs.n_cv_tot + k] = root;
+        }
+    }
+    bits[t] = v;
 }
 
-// one thread per (offspring gamete row, CV): parity of the crossovers at or below the CV position
-__global__ void cv_propagate_kernel(CvSet cs, const uint8_t *__restrict__ par_allele, const uint8_t *__restrict__ par_root,
-                                    uint8_t *__restrict__ off_allele, uint8_t *__restrict__ off_root,
-                                    const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
-                                    const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
-                                    const uint8_t *__restrict__ start_hap, uint64_t off_first, uint64_t n_off) {
+// One thread per (offspring gamete row, word): the haplotype of CV k is start ^ parity of the crossovers at or
+// below its position, so a crossover flips every CV of the word from index lower_bound(bp, crossover) upwards;
+// the word is then a mask-merge of the two parental words — the same operation as the boundary chunk of
+// propagate_bits_kernel.
+__global__ void cv_propagate_bits_kernel(CvSet cs, const uint32_t *__restrict__ par_bits, uint32_t *__restrict__ off_bits,
+                                         const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+                                         const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
+                                         const uint8_t *__restrict__ start_hap, uint64_t off_first, uint64_t n_off) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_off * 2 * cs.Wcv) return;
+    uint32_t w = (uint32_t)(t % cs.Wcv);
+    uint64_t row = t / cs.Wcv;
+    uint64_t i = off_first + (row >> 1);
+    int gam = (int)(row & 1);
+    uint32_t b = cs.word_blk[w], v = 0;
+    if (b != 0xFFFFFFFFu) {
+        uint32_t c = b % (uint32_t)cs.n_chr;
+        uint32_t k0 = cs.block_off[b] + (w - cs.word_off[b]) * 32u, nk = min(32u, cs.block_off[b + 1] - k0);
+        uint64_t slot = (i * (uint64_t)cs.n_chr + c) * 2 + gam;
+        uint32_t mask = start_hap[slot] ? 0xFFFFFFFFu : 0u;
+        const uint32_t *bp = cs.bp + k0;
+        for (uint64_t e = xo_off[slot]; e < xo_off[slot + 1]; e++) {
+            const uint32_t x = xo_bp[e];
+            uint32_t m = 0;  // CVs at or above the crossover flip (cv.info rows need not be sorted)
+            for (uint32_t j = 0; j < nk; j++) m |= (uint32_t)(x <= __ldg(bp + j)) << j;
+            mask ^= m;
+        }
+        uint32_t parent = gam ? mother[i] : father[i];
+        const uint32_t *pr = par_bits + (uint64_t)parent * 2 * cs.Wcv + w;
+        v = (pr[0] & ~mask) | (pr[cs.Wcv] & mask);
+    }
+    off_bits[(i * 2 + gam) * (uint64_t)cs.Wcv + w] = v;
+}
+
+// root-population plane (only with more than one population): one thread per (offspring gamete row, CV)
+__global__ void cv_root_propagate_kernel(CvSet cs, const uint8_t *__restrict__ par_root, uint8_t *__restrict__ off_root,
+                                         const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+                                         const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
+                                         const uint8_t *__restrict__ start_hap, uint64_t off_first, uint64_t n_off) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_off * 2 * cs.n_cv_tot) return;
     uint32_t k = (uint32_t)(t % cs.n_cv_tot);
@@ -301,33 +351,45 @@ __global__ void cv_propagate_kernel(CvSet cs, const uint8_t *__restrict__ par_al
     int h = start_hap[slot];
     for (uint64_t e = xo_off[slot]; e < xo_off[slot + 1]; e++) h ^= (xo_bp[e] <= p);
     uint32_t parent = gam ? mother[i] : father[i];
-    uint64_t src = ((uint64_t)parent * 2 + (h & 1)) * cs.n_cv_tot + k;
-    uint64_t dst = (i * 2 + gam) * (uint64_t)cs.n_cv_tot + k;
-    off_allele[dst] = par_allele[src];
-    if (off_root) off_root[dst] = par_root[src];
+    off_root[(i * 2 + gam) * (uint64_t)cs.n_cv_tot + k] = par_root[((uint64_t)parent * 2 + (h & 1)) * cs.n_cv_tot + k];
 }
 
-// allele count per CV over the population (frq numerator, :2647-2663).  Tiles of 32 CVs x 512 rows: a warp
-// reads 32 consecutive bytes of one row (one sector), 8 warps stride the rows; one 64-bit atomic per CV and tile.
-__global__ void cv_count_tiled_kernel(const uint8_t *__restrict__ allele, uint64_t n_rows, uint32_t n_cv_tot, unsigned long long *__restrict__ count) {
-    __shared__ unsigned int sh[8][32];
-    uint32_t k = blockIdx.x * 32 + threadIdx.x;
-    uint64_t r0 = (uint64_t)blockIdx.y * 512, r1 = min(r0 + 512, n_rows);
-    unsigned int s = 0;
-    if (k < n_cv_tot)
-        for (uint64_t r = r0 + threadIdx.y; r < r1; r += 8) s += allele[r * n_cv_tot + k];
-    sh[threadIdx.y][threadIdx.x] = s;
+// allele count per CV over the population (frq numerator, :2647-2663).  A CTA takes 32 word columns x 512 rows:
+// a warp reads 32 consecutive words of one row (128 B), 8 warps stride the rows, every thread keeps the 32 bit
+// counters of its word in registers; shared-memory atomics fold the 8 warps, one 64-bit atomic per CV and CTA.
+__global__ void cv_count_bits_kernel(CvSet cs, const uint32_t *__restrict__ bits, uint64_t n_rows, unsigned long long *__restrict__ count) {
+    __shared__ unsigned int sh[32][33];
+    const uint32_t w = blockIdx.x * 32 + threadIdx.x;
+    const uint64_t r0 = (uint64_t)blockIdx.y * 512, r1 = min(r0 + 512, n_rows);
+    for (int q = threadIdx.y; q < 32; q += 8) sh[q][threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.y == 0 && k < n_cv_tot) {
-        unsigned int t = 0;
-        for (int y = 0; y < 8; y++) t += sh[y][threadIdx.x];
-        if (t) atomicAdd(&count[k], (unsigned long long)t);
+    unsigned int cnt[32];
+#pragma unroll
+    for (int b = 0; b < 32; b++) cnt[b] = 0;
+    if (w < cs.Wcv)
+        for (uint64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+            uint32_t v = bits[r * cs.Wcv + w];
+#pragma unroll
+            for (int b = 0; b < 32; b++) cnt[b] += (v >> b) & 1u;
+        }
+#pragma unroll
+    for (int b = 0; b < 32; b++) if (cnt[b]) atomicAdd(&sh[threadIdx.x][b], cnt[b]);
+    __syncthreads();
+    if (w < cs.Wcv) {
+        uint32_t blk = cs.word_blk[w];
+        if (blk != 0xFFFFFFFFu) {
+            uint32_t k0 = cs.block_off[blk] + (w - cs.word_off[blk]) * 32u, k1 = cs.block_off[blk + 1];
+            for (uint32_t b = threadIdx.y; b < 32u; b += 8) {
+                unsigned int v = sh[threadIdx.x][b];
+                if (v && k0 + b < k1) atomicAdd(&count[k0 + b], (unsigned long long)v);
+            }
+        }
     }
 }
 
 // A and D per individual (ras_compute_AD :2686-2746): one warp per individual and phenotype; lanes stride
-// the CVs of a chromosome, warp-shuffle reduce, chromosomes added in ascending order like the reference.
-__global__ void genetic_value_kernel(CvSet cs, const uint8_t *__restrict__ allele, const uint8_t *__restrict__ rootp,
+// the CVs of each chromosome block and the warp reduces once at the end (fp64, fixed shuffle tree).
+__global__ void genetic_value_kernel(CvSet cs, const uint32_t *__restrict__ bits, const uint8_t *__restrict__ rootp,
                                      const unsigned long long *__restrict__ count, uint64_t n_count /* individuals in frq */,
                                      const double *__restrict__ a_eff /* [n_pop][n_cv_tot] */, const double *__restrict__ d_eff,
                                      const uint8_t *__restrict__ vd_zero /* [n_phen] */, uint64_t n, double *__restrict__ A,
@@ -337,31 +399,41 @@ __global__ void genetic_value_kernel(CvSet cs, const uint8_t *__restrict__ allel
     if (wid >= n * cs.n_phen) return;
     uint64_t i = wid % n;
     int f = (int)(wid / n);
-    const uint8_t *al0 = allele + (i * 2) * (uint64_t)cs.n_cv_tot, *al1 = al0 + cs.n_cv_tot;
+    const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
     const uint8_t *r0 = rootp ? rootp + (i * 2) * (uint64_t)cs.n_cv_tot : nullptr, *r1 = rootp ? r0 + cs.n_cv_tot : nullptr;
-    double add = 0, dom = 0, bv = 0;
+    const bool no_d = vd_zero[f] != 0;
+    const double two_n = (double)(2 * n_count);
+    double Ac = 0, Dc = 0;
     for (int c = 0; c < cs.n_chr; c++) {
-        uint32_t b0 = cs.block_off[f * cs.n_chr + c], b1 = cs.block_off[f * cs.n_chr + c + 1];
-        double Ac = 0, Dc = 0;
+        const int blk = f * cs.n_chr + c;
+        const uint32_t b0 = cs.block_off[blk], b1 = cs.block_off[blk + 1], wo = cs.word_off[blk];
         for (uint32_t k = b0 + lane; k < b1; k += 32) {
+            const uint32_t j = k - b0;
+            const unsigned t = ((al0[wo + (j >> 5)] >> (j & 31)) & 1u) + ((al1[wo + (j >> 5)] >> (j & 31)) & 1u);
             uint64_t o0 = r0 ? (uint64_t)r0[k] * cs.n_cv_tot + k : k, o1 = r1 ? (uint64_t)r1[k] * cs.n_cv_tot + k : k;
             double a = (a_eff[o0] + a_eff[o1]) / 2;
-            double d = (d_eff[o0] + d_eff[o1]) / 2;
-            if (vd_zero[f]) d = 0;
-            unsigned t = al0[k] + al1[k];
-            double p = (double)count[k] / (double)(2 * n_count), q = 1 - p;
+            double d = no_d ? 0.0 : (d_eff[o0] + d_eff[o1]) / 2;
+            double p = (double)count[k] / two_n, q = 1 - p;
             double alpha = a + d * (q - p);
             Ac += ((double)t - 2 * p) * alpha;
             double ct = t == 0 ? -2 * p * p : (t == 1 ? 2 * p * q : -2 * q * q);
             Dc += ct * d;
         }
-        for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
-        add += Ac; dom += Dc; bv += Ac + Dc;
     }
+    for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
     if (lane == 0) {
-        A[(uint64_t)f * n + i] = add; D[(uint64_t)f * n + i] = dom; Gv[(uint64_t)f * n + i] = bv;
-        if (isnan(add) || isnan(dom)) *nan_flag = 1;
+        A[(uint64_t)f * n + i] = Ac; D[(uint64_t)f * n + i] = Dc; Gv[(uint64_t)f * n + i] = Ac + Dc;
+        if (isnan(Ac) || isnan(Dc)) *nan_flag = 1;
     }
+}
+
+// bit plane -> bytes of one block (the `--debug` .cvval dump): out[row*ncv + j]
+__global__ void cv_unpack_block_kernel(const uint32_t *__restrict__ bits, uint32_t Wcv, uint32_t wo, uint32_t ncv, uint64_t n_rows, uint8_t *__restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * ncv) return;
+    uint32_t j = (uint32_t)(t % ncv);
+    uint64_t row = t / ncv;
+    out[t] = (bits[row * Wcv + wo + (j >> 5)] >> (j & 31)) & 1u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -651,7 +723,7 @@ __device__ __forceinline__ int parity_at(const MutArgs &a, uint64_t slot, uint32
 }
 template <bool FILL>
 __global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *__restrict__ count, const uint64_t *__restrict__ hm_off,
-                                      uint32_t *__restrict__ hm_bp, uint32_t *__restrict__ off_rows, uint8_t *__restrict__ cv_allele) {
+                                      uint32_t *__restrict__ hm_bp, uint32_t *__restrict__ off_rows, uint32_t *__restrict__ cv_bits) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_off * a.n_chr * 2) return;
     uint64_t slot = a.off_first * a.n_chr * 2 + t;
@@ -687,10 +759,13 @@ __global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *_
                         for (uint32_t s = lower_bound_u32(pos, nl, m); s < nl && pos[s] == m; s++)
                             off_rows[(uint64_t)(2 * i + gam) * g.W + g.chr_word_off[c] + (s >> 5)] ^= 1u << (s & 31);
                     }
-                    if (cv_allele) {
-                        for (int f = 0; f < cs.n_phen; f++)
-                            for (uint32_t k = cs.block_off[f * cs.n_chr + c]; k < cs.block_off[f * cs.n_chr + c + 1]; k++)
-                                if (cs.bp[k] == m) cv_allele[(i * 2 + gam) * (uint64_t)cs.n_cv_tot + k] ^= 1;
+                    if (cv_bits) {  // the words of block (f, c) of this row belong to this thread alone
+                        for (int f = 0; f < cs.n_phen; f++) {
+                            const int blk = f * cs.n_chr + c;
+                            const uint32_t b0 = cs.block_off[blk], b1 = cs.block_off[blk + 1];
+                            for (uint32_t k = b0; k < b1; k++)
+                                if (cs.bp[k] == m) cv_bits[(i * 2 + gam) * (uint64_t)cs.Wcv + cs.word_off[blk] + ((k - b0) >> 5)] ^= 1u << ((k - b0) & 31);
+                        }
                     }
                 }
             }

@@ -365,6 +365,7 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
     if (np > MAX_POP) return fail(GE_ERR_UNSUPPORTED, "too many populations");
     if (!row) return fail(GE_ERR_INVALID, "null migration row");
     cudaStream_t st = ctx->stream;
+    GE_TRY(ctx->join_bulk());  // whole individuals move, haplotype rows included
     std::vector<std::vector<uint64_t>> num_move(np, std::vector<uint64_t>(np, 0));
     for (int i = 0; i < np; i++) {
         double s = 0;
@@ -433,7 +434,7 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
                 GE_TRY(ctx->check_launch("gather_rows"));
             }
             if (ctx->n_cv_tot) {
-                gather_bytes_kernel<<<nblk(n * 2 * ctx->n_cv_tot, 256), 256, 0, st>>>(table([](GenState &S) { return S.cv_allele.p; }), g8, g32, n, 2 * ctx->n_cv_tot, D.cv_allele.as<uint8_t>());
+                gather_bytes_kernel<<<nblk(n * 8 * ctx->Wcv, 256), 256, 0, st>>>(table([](GenState &S) { return S.cv_allele.p; }), g8, g32, n, 8 * ctx->Wcv, D.cv_allele.as<uint8_t>());
                 GE_TRY(ctx->check_launch("gather_cv"));
                 gather_bytes_kernel<<<nblk(n * 2 * ctx->n_cv_tot, 256), 256, 0, st>>>(table([](GenState &S) { return S.cv_root.p; }), g8, g32, n, 2 * ctx->n_cv_tot, D.cv_root.as<uint8_t>());
                 GE_TRY(ctx->check_launch("gather_cv_root"));

@@ -88,28 +88,38 @@ __global__ void seg_recombine_kernel(SegArgs a, uint32_t *__restrict__ count, co
     if (!FILL) count[slot] = n;
 }
 
-// ras_find_cv (:2752-2815) on the segment lists: allele/root planes of every (haplotype row, CV)
+// ras_find_cv (:2752-2815) on the segment lists: allele bit plane / root byte plane.  One thread per (haplotype
+// row, word of the CV bit plane); every CV of the word scans the segment list of its chromosome (the LAST part that
+// covers the position wins, like the reference's loop over all parts).
 __global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__restrict__ off, const uint4 *__restrict__ seg,
                                    const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp,
                                    const uint8_t *const *__restrict__ founder_cv /* [n_pop] -> [nh][n_cv_tot] */,
-                                   uint8_t *__restrict__ allele, uint8_t *__restrict__ rootp) {
+                                   uint32_t *__restrict__ bits, uint8_t *__restrict__ rootp) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_rows * cs.n_cv_tot) return;
-    uint32_t k = (uint32_t)(t % cs.n_cv_tot);
-    uint64_t row = t / cs.n_cv_tot;  // 2*i + h
-    uint32_t c = cs.chr_of[k], bp = cs.bp[k];
-    uint64_t slot = ((row >> 1) * cs.n_chr + c) * 2 + (row & 1);
-    uint8_t v = 0, r = 0;
-    bool found = false;
-    for (uint64_t e = off[slot]; e < off[slot + 1]; e++) {
-        uint4 q = seg[e];
-        if (q.x <= bp && bp < q.y) { v = founder_cv[q.w][(uint64_t)q.z * cs.n_cv_tot + k]; r = (uint8_t)q.w; found = true; }
+    if (t >= n_rows * cs.Wcv) return;
+    uint32_t w = (uint32_t)(t % cs.Wcv);
+    uint64_t row = t / cs.Wcv;  // 2*i + h
+    uint32_t blk = cs.word_blk[w], out = 0;
+    if (blk != 0xFFFFFFFFu) {
+        uint32_t c = blk % (uint32_t)cs.n_chr;
+        uint32_t k0 = cs.block_off[blk] + (w - cs.word_off[blk]) * 32u, k1 = min(k0 + 32u, cs.block_off[blk + 1]);
+        uint64_t slot = ((row >> 1) * cs.n_chr + c) * 2 + (row & 1);
+        for (uint32_t k = k0; k < k1; k++) {
+            uint32_t bp = cs.bp[k];
+            uint8_t v = 0, r = 0;
+            bool found = false;
+            for (uint64_t e = off[slot]; e < off[slot + 1]; e++) {
+                uint4 q = seg[e];
+                if (q.x <= bp && bp < q.y) { v = founder_cv[q.w][(uint64_t)q.z * cs.n_cv_tot + k]; r = (uint8_t)q.w; found = true; }
+            }
+            if (found && hm_off) {
+                for (uint64_t e = hm_off[slot]; e < hm_off[slot + 1]; e++) if (hm_bp[e] == bp) { v ^= 1; break; }
+            }
+            out |= (uint32_t)(v & 1) << (k - k0);
+            if (rootp) rootp[row * cs.n_cv_tot + k] = found ? r : 0;  // covered by no part: the effect tables hold a = d = 0 there (Human_CV ctor)
+        }
     }
-    if (found && hm_off) {
-        for (uint64_t e = hm_off[slot]; e < hm_off[slot + 1]; e++) if (hm_bp[e] == bp) { v ^= 1; break; }
-    }
-    allele[t] = v;
-    if (rootp) rootp[t] = found ? r : 0;  // covered by no part: the effect tables hold a = d = 0 there (Human_CV ctor)
+    bits[t] = out;
 }
 
 // ras_convert_interval_to_hap_matrix (:1186-1230): alleles of one chromosome from segments + founder panels
@@ -161,8 +171,9 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     int C = ctx->cfg.n_chr;
     uint64_t n_slots = n_off * C * 2;
     SegArgs a;
-    a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = P.father.as<uint32_t>(); a.mother = P.mother.as<uint32_t>();
-    a.xo_off = P.xo_off.as<uint64_t>(); a.xo_bp = P.xo_bp.as<uint32_t>(); a.start_hap = P.start_hap.as<uint8_t>();
+    DrawSet &D = P.draws();
+    a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = D.father.as<uint32_t>(); a.mother = D.mother.as<uint32_t>();
+    a.xo_off = D.xo_off.as<uint64_t>(); a.xo_bp = D.xo_bp.as<uint32_t>(); a.start_hap = D.start_hap.as<uint8_t>();
     a.par_off = par.seg.off.as<uint64_t>(); a.par_seg = par.seg.seg.as<uint4>(); a.cov_lo = P.d_cov_lo.as<uint32_t>(); a.cov_hi = P.d_cov_hi.as<uint32_t>();
     GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
     GE_TRY(ctx->ensure(off.seg.off, (n_slots + 1) * 8));
@@ -197,10 +208,10 @@ static int seg_find_cv(ge_ctx *ctx, int pop) {
     if (ctx->n_cv_tot == 0) return GE_OK;
     Buf tbl;
     GE_TRY(seg_device_tables(ctx, tbl, true));
-    uint64_t tot = 2 * S.n * ctx->n_cv_tot;
+    uint64_t tot = 2 * S.n * ctx->Wcv;
     seg_find_cv_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(),
                                                                 S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
-                                                                tbl.as<const uint8_t *>(), S.cv_allele.as<uint8_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr);
+                                                                tbl.as<const uint8_t *>(), S.cv_allele.as<uint32_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr);
     GE_TRY(ctx->check_launch("seg_find_cv"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->release(tbl);
