@@ -52,6 +52,24 @@ static int build_genome(ge_ctx *ctx) {
     GE_TRY(ctx->upload(ctx->d_locus_off, ctx->locus_off));
     GE_TRY(ctx->upload(ctx->d_pos, pos));
     GE_TRY(ctx->upload(ctx->d_chr_ids, ctx->chr_ids));
+    // coarse position index (locus_lower_bound): about two buckets per locus, at least 1024 per chromosome
+    std::vector<uint32_t> bkt_off(C + 1, 0), bkt_shift(C, 0), bkt;
+    for (int c = 0; c < C; c++) {
+        const auto &L = ctx->loci[c];
+        uint64_t maxpos = L.empty() ? 0 : L.back();
+        uint32_t sh = 0;
+        while ((maxpos >> sh) + 1 > 2 * L.size() + 1024) sh++;
+        bkt_shift[c] = sh;
+        uint64_t nb = (maxpos >> sh) + 1;
+        size_t s0 = 0;
+        for (uint64_t b = 0; b < nb; b++) {
+            while (s0 < L.size() && L[s0] < (b << sh)) s0++;
+            bkt.push_back((uint32_t)s0);
+        }
+        bkt.push_back((uint32_t)L.size());
+        bkt_off[c + 1] = (uint32_t)bkt.size();
+    }
+    GE_TRY(ctx->upload(ctx->d_bkt_off, bkt_off)); GE_TRY(ctx->upload(ctx->d_bkt_shift, bkt_shift)); GE_TRY(ctx->upload(ctx->d_bkt, bkt));
     // tile table: (chromosome, first chunk, chunk count), longest first so the warps of a CTA balance
     const uint32_t TILE = 512;  // 16-byte chunks per work item = 8 KB
     struct Item { uint32_t c, q0, nq; };
@@ -135,6 +153,10 @@ static int build_cvset(ge_ctx *ctx) {
     }
     ctx->Wcv = std::max<uint32_t>((ctx->cv_word_off.back() + 3) & ~3u, 4);
     word_blk.resize(ctx->Wcv, 0xFFFFFFFFu);
+    ctx->cv_sorted = true;
+    for (int b = 0; b < nf * C; b++)
+        for (uint32_t k = ctx->cv_block_off[b] + 1; k < ctx->cv_block_off[b + 1]; k++) if (bp[k] < bp[k - 1]) ctx->cv_sorted = false;
+    GE_TRY(ctx->ensure(ctx->d_LA, (size_t)std::max<uint32_t>(ctx->n_cv_tot, 1) * 24)); GE_TRY(ctx->ensure(ctx->d_LD, (size_t)std::max<uint32_t>(ctx->n_cv_tot, 1) * 24));
     GE_TRY(ctx->upload(ctx->d_cv_word_off, ctx->cv_word_off)); GE_TRY(ctx->upload(ctx->d_cv_word_blk, word_blk));
     std::vector<double> a_eff((size_t)np * ctx->n_cv_tot), d_eff((size_t)np * ctx->n_cv_tot);
     for (int p = 0; p < np; p++)
@@ -224,7 +246,7 @@ int ge_destroy(ge_ctx *ctx) {
         }
         mate_release(P.mate);
     }
-    for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
+    for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_bkt_off, &ctx->d_bkt_shift, &ctx->d_bkt, &ctx->d_LA, &ctx->d_LD, &ctx->xo_stash, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
                    &ctx->d_cv_block_off, &ctx->d_cv_word_off, &ctx->d_cv_word_blk, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks,
                    &ctx->scan_total, &ctx->partial, &ctx->scalars, &ctx->flags, &ctx->d_chr_ids, &ctx->ar_scratch})
         freeb(*b);
@@ -322,11 +344,20 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
         GE_TRY(ctx->check_launch("cv_count"));
     }
     uint64_t nw = S.n * ctx->cfg.n_phen;
-    genetic_value_kernel<<<nblk(nw * 32, 256), 256, 0, ctx->stream>>>(
-        ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.n,
-        ctx->d_a_eff.as<double>(), ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), S.n, S.A.as<double>(), S.D.as<double>(), S.G.as<double>(),
-        ctx->flags.as<int>());
-    GE_TRY(ctx->check_launch("genetic_value"));
+    if (ctx->cfg.n_pop == 1 && ncv) {
+        cv_tables_kernel<<<nblk(ncv, 128), 128, 0, ctx->stream>>>(ctx->cvset(), ctx->d_cv_count.as<unsigned long long>(), S.n, ctx->d_a_eff.as<double>(),
+                                                                  ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), ctx->d_LA.as<double>(), ctx->d_LD.as<double>());
+        GE_TRY(ctx->check_launch("cv_tables"));
+        genetic_value_lut_kernel<<<nblk(nw * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_LA.as<double>(), ctx->d_LD.as<double>(), S.n,
+                                                                              S.A.as<double>(), S.D.as<double>(), S.G.as<double>(), ctx->flags.as<int>());
+        GE_TRY(ctx->check_launch("genetic_value_lut"));
+    } else {
+        genetic_value_kernel<<<nblk(nw * 32, 256), 256, 0, ctx->stream>>>(
+            ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.n,
+            ctx->d_a_eff.as<double>(), ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), S.n, S.A.as<double>(), S.D.as<double>(), S.G.as<double>(),
+            ctx->flags.as<int>());
+        GE_TRY(ctx->check_launch("genetic_value"));
+    }
     if (ctx->allreduce) {
         // chromosome-sharded contexts hold partial sums over their own chromosomes: sum A, D, G over the ranks
         size_t nb = (size_t)S.n * ctx->cfg.n_phen * 8;
@@ -735,12 +766,16 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         // crossovers: count, scan, fill
         uint64_t n_slots = n_off * C * 2;
         GE_TRY(ctx->ensure(D.xo_off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(D.start_hap, n_slots));
-        sample_xo_kernel<false><<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, P.cnt32.as<uint32_t>(), nullptr, nullptr, D.start_hap.as<uint8_t>());
+        GE_TRY(ctx->ensure(ctx->xo_stash, n_slots * XO_STASH * 4));
+        sample_xo_kernel<false><<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, P.cnt32.as<uint32_t>(), nullptr, nullptr, D.start_hap.as<uint8_t>(),
+                                                                    ctx->xo_stash.as<uint32_t>());
         GE_TRY(ctx->check_launch("sample_xo<count>"));
         GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, D.xo_off.as<uint64_t>(), &P.n_xo));
         GE_TRY(ctx->ensure(D.xo_bp, std::max<uint64_t>(P.n_xo, 1) * 4));
-        sample_xo_kernel<true><<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, nullptr, D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), nullptr);
-        GE_TRY(ctx->check_launch("sample_xo<fill>"));
+        if (ctx->bits()) GE_TRY(ctx->ensure(D.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
+        xo_place_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ctx->genome(), C, pop, gen, n_slots, D.xo_off.as<uint64_t>(), ctx->xo_stash.as<uint32_t>(),
+                                                            D.xo_bp.as<uint32_t>(), ctx->bits() ? D.flips.as<uint32_t>() : nullptr);
+        GE_TRY(ctx->check_launch("xo_place"));
         if (P.has_mut) {
             uint64_t n_items = n_off * C;
             GE_TRY(ctx->ensure(P.mut_off, (n_items + 1) * 8));
@@ -768,9 +803,11 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
     // and phenotypes of the NEXT generation overlap with this copy.
     bool bulk_launched = false;
     if (ctx->bits()) {
-        GE_TRY(ctx->ensure(D.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
-        xo_to_flips_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->genome(), n_slots, D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.flips.as<uint32_t>());
-        GE_TRY(ctx->check_launch("xo_to_flips"));
+        if (dr) {  // replayed crossovers: positions -> locus indices (the Philox path did it in xo_place_kernel)
+            GE_TRY(ctx->ensure(D.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
+            xo_to_flips_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->genome(), n_slots, D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.flips.as<uint32_t>());
+            GE_TRY(ctx->check_launch("xo_to_flips"));
+        }
         CUDA_TRY(cudaEventRecord(ctx->ev_ready, st));
         CUDA_TRY(cudaStreamWaitEvent(ctx->bulk, ctx->ev_ready, 0));
         ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0};

@@ -123,7 +123,7 @@ struct ge_ctx {
     // genome layout
     std::vector<uint32_t> chr_word_off, chr_nloci, locus_off;
     uint32_t W = 0;
-    Buf d_chr_word_off, d_chr_nloci, d_locus_off, d_pos;
+    Buf d_chr_word_off, d_chr_nloci, d_locus_off, d_pos, d_bkt_off, d_bkt_shift, d_bkt;
     bool genome_ready = false;
     // tile table
     Buf d_tile_chr, d_tile_chunk0, d_tile_nchunk;
@@ -132,6 +132,8 @@ struct ge_ctx {
     std::vector<uint32_t> cv_block_off;  // [n_phen*n_chr+1]
     std::vector<uint32_t> cv_word_off;   // [n_phen*n_chr+1]
     uint32_t n_cv_tot = 0, Wcv = 4;
+    bool cv_sorted = true;
+    Buf d_LA, d_LD, xo_stash;
     Buf d_cv_word_off, d_cv_word_blk, d_cv_block_off, d_cv_bp, d_cv_chr, d_a_eff, d_d_eff, d_cv_count;
     bool cv_ready = false;
     // scratch
@@ -195,11 +197,12 @@ struct ge_ctx {
         g.n_chr = cfg.n_chr; g.W = W;
         g.chr_word_off = d_chr_word_off.as<uint32_t>(); g.chr_nloci = d_chr_nloci.as<uint32_t>();
         g.locus_off = d_locus_off.as<uint32_t>(); g.pos = d_pos.as<uint32_t>();
+        g.bkt_off = d_bkt_off.as<uint32_t>(); g.bkt_shift = d_bkt_shift.as<uint32_t>(); g.bkt = d_bkt.as<uint32_t>();
         return g;
     }
     CvSet cvset() const {
         CvSet c;
-        c.n_chr = cfg.n_chr; c.n_phen = cfg.n_phen; c.n_cv_tot = n_cv_tot; c.Wcv = Wcv;
+        c.n_chr = cfg.n_chr; c.n_phen = cfg.n_phen; c.n_cv_tot = n_cv_tot; c.Wcv = Wcv; c.sorted = cv_sorted;
         c.word_off = d_cv_word_off.as<uint32_t>(); c.word_blk = d_cv_word_blk.as<uint32_t>();
         c.block_off = d_cv_block_off.as<uint32_t>(); c.bp = d_cv_bp.as<uint32_t>(); c.chr_of = d_cv_chr.as<uint32_t>();
         return c;

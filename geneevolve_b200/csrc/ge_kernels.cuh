@@ -71,6 +71,10 @@ struct Genome {
     const uint32_t *chr_nloci;     // [n_chr]
     const uint32_t *locus_off;     // [n_chr+1] offsets into pos
     const uint32_t *pos;           // concatenated locus positions (bp), ascending inside a chromosome
+    // coarse position index: bkt[bkt_off[c] + b] = first locus of chromosome c with pos >= b << bkt_shift[c]
+    const uint32_t *bkt_off;       // [n_chr+1]
+    const uint32_t *bkt_shift;     // [n_chr]
+    const uint32_t *bkt;
 };
 
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint32_t key) {
@@ -78,6 +82,22 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t 
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
         if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// first locus of chromosome c with position >= key: one bucket lookup, then a search over the few loci of the
+// bucket (about one on average) instead of ~20 dependent loads over the whole position table
+__device__ __forceinline__ uint32_t locus_lower_bound(const Genome &g, int c, uint32_t key) {
+    const uint32_t *pos = g.pos + g.locus_off[c];
+    const uint32_t nb = g.bkt_off[c + 1] - g.bkt_off[c] - 1;  // buckets 0..nb-1, entry nb = n_loci
+    const uint32_t b = key >> g.bkt_shift[c];
+    if (b >= nb) return g.chr_nloci[c];
+    const uint32_t *t = g.bkt + g.bkt_off[c] + b;
+    uint32_t lo = __ldg(t), hi = __ldg(t + 1);
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(pos + mid) < key) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -90,9 +110,7 @@ __global__ void xo_to_flips_kernel(Genome g, uint64_t n_slots, const uint64_t *_
     uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     int c = (int)((slot >> 1) % (uint64_t)g.n_chr);
-    const uint32_t *pos = g.pos + g.locus_off[c];
-    uint32_t nl = g.chr_nloci[c];
-    for (uint64_t e = xo_off[slot]; e < xo_off[slot + 1]; e++) flips[e] = lower_bound_u32(pos, nl, xo_bp[e]);
+    for (uint64_t e = xo_off[slot]; e < xo_off[slot + 1]; e++) flips[e] = locus_lower_bound(g, c, xo_bp[e]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,6 +289,7 @@ struct CvSet {
     int n_chr, n_phen;
     uint32_t n_cv_tot;
     uint32_t Wcv;               // words per row (multiple of 4)
+    int sorted;                 // every block lists its positions in ascending order (binary search allowed)
     const uint32_t *block_off;  // [n_phen*n_chr + 1] first CV of each block
     const uint32_t *word_off;   // [n_phen*n_chr + 1] first word of each block
     const uint32_t *word_blk;   // [Wcv] block of each word, 0xFFFFFFFF for padding words
@@ -323,10 +342,15 @@ __global__ void cv_propagate_bits_kernel(CvSet cs, const uint32_t *__restrict__ 
         uint32_t mask = start_hap[slot] ? 0xFFFFFFFFu : 0u;
         const uint32_t *bp = cs.bp + k0;
         for (uint64_t e = xo_off[slot]; e < xo_off[slot + 1]; e++) {
-            const uint32_t x = xo_bp[e];
-            uint32_t m = 0;  // CVs at or above the crossover flip (cv.info rows need not be sorted)
-            for (uint32_t j = 0; j < nk; j++) m |= (uint32_t)(x <= __ldg(bp + j)) << j;
-            mask ^= m;
+            const uint32_t x = xo_bp[e];  // CVs at or above the crossover flip
+            if (cs.sorted) {
+                const uint32_t idx = lower_bound_u32(bp, nk, x);
+                if (idx < 32u) mask ^= 0xFFFFFFFFu << idx;
+            } else {  // cv.info rows need not be sorted
+                uint32_t m = 0;
+                for (uint32_t j = 0; j < nk; j++) m |= (uint32_t)(x <= __ldg(bp + j)) << j;
+                mask ^= m;
+            }
         }
         uint32_t parent = gam ? mother[i] : father[i];
         const uint32_t *pr = par_bits + (uint64_t)parent * 2 * cs.Wcv + w;
@@ -418,6 +442,53 @@ __global__ void genetic_value_kernel(CvSet cs, const uint32_t *__restrict__ bits
             Ac += ((double)t - 2 * p) * alpha;
             double ct = t == 0 ? -2 * p * p : (t == 1 ? 2 * p * q : -2 * q * q);
             Dc += ct * d;
+        }
+    }
+    for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
+    if (lane == 0) {
+        A[(uint64_t)f * n + i] = Ac; D[(uint64_t)f * n + i] = Dc; Gv[(uint64_t)f * n + i] = Ac + Dc;
+        if (isnan(Ac) || isnan(Dc)) *nan_flag = 1;
+    }
+}
+
+// One population: the per-CV terms do not depend on the individual, so they are tabulated once per generation —
+// LA[k][t] = (t - 2p) * alpha, LD[k][t] = c_t * d for genotype t in {0,1,2} (the very products of :2691-2712) —
+// and the per-individual kernel only gathers and adds them in the same order as genetic_value_kernel.
+__global__ void cv_tables_kernel(CvSet cs, const unsigned long long *__restrict__ count, uint64_t n_count, const double *__restrict__ a_eff,
+                                 const double *__restrict__ d_eff, const uint8_t *__restrict__ vd_zero, double *__restrict__ LA, double *__restrict__ LD) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cs.n_cv_tot) return;
+    int blk = 0;
+    while (cs.block_off[blk + 1] <= k) blk++;
+    const int f = blk / cs.n_chr;
+    const double two_n = (double)(2 * n_count);
+    double a = (a_eff[k] + a_eff[k]) / 2;
+    double d = vd_zero[f] ? 0.0 : (d_eff[k] + d_eff[k]) / 2;
+    double p = (double)count[k] / two_n, q = 1 - p;
+    double alpha = a + d * (q - p);
+    for (int t = 0; t < 3; t++) {
+        LA[k * 3 + t] = ((double)t - 2 * p) * alpha;
+        double ct = t == 0 ? -2 * p * p : (t == 1 ? 2 * p * q : -2 * q * q);
+        LD[k * 3 + t] = ct * d;
+    }
+}
+__global__ void genetic_value_lut_kernel(CvSet cs, const uint32_t *__restrict__ bits, const double *__restrict__ LA, const double *__restrict__ LD,
+                                         uint64_t n, double *__restrict__ A, double *__restrict__ D, double *__restrict__ Gv, int *__restrict__ nan_flag) {
+    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (wid >= n * cs.n_phen) return;
+    uint64_t i = wid % n;
+    int f = (int)(wid / n);
+    const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
+    double Ac = 0, Dc = 0;
+    for (int c = 0; c < cs.n_chr; c++) {
+        const int blk = f * cs.n_chr + c;
+        const uint32_t b0 = cs.block_off[blk], b1 = cs.block_off[blk + 1], wo = cs.word_off[blk];
+        for (uint32_t k = b0 + lane; k < b1; k += 32) {
+            const uint32_t j = k - b0;
+            const unsigned t = ((al0[wo + (j >> 5)] >> (j & 31)) & 1u) + ((al1[wo + (j >> 5)] >> (j & 31)) & 1u);
+            Ac += LA[k * 3 + t];
+            Dc += LD[k * 3 + t];
         }
     }
     for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
@@ -633,11 +704,14 @@ __device__ __forceinline__ long long next_success(const double *T, uint32_t R, u
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (T[mid + 1] < v) hi = mid; else lo = mid + 1; }
     return (long long)lo;
 }
-// one thread per slot; pass 0 counts (and writes start_hap), pass 1 writes positions
+// One thread per slot.  Pass 0 counts, writes start_hap and stashes the first XO_STASH positions of the slot at a
+// fixed stride; after the scan, xo_place_kernel moves the stash into the CSR (re-drawing only the rare longer lists
+// with pass 1's code) and converts positions to locus indices in the same sweep.
+constexpr int XO_STASH = 4;
 template <bool FILL>
 __global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int gen, uint64_t slot_first, uint64_t n_slots,
                                  uint32_t *__restrict__ count, const uint64_t *__restrict__ xo_off, uint32_t *__restrict__ xo_bp,
-                                 uint8_t *__restrict__ start_hap) {
+                                 uint8_t *__restrict__ start_hap, uint32_t *__restrict__ stash = nullptr) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_slots) return;
     uint64_t slot = slot_first + t;
@@ -657,11 +731,49 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int ge
         long long k = next_success(T, R, j, v);
         if (k < 0) break;
         if (FILL) xo_bp[o + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
+        else if (stash && n < XO_STASH) stash[t * XO_STASH + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
         n++;
         j = (uint32_t)k + 1;
     }
     if (!FILL) count[slot] = n;
 }
+// stash -> CSR (+ locus indices of the flips when the bit-packed rows are kept); slots longer than the stash re-draw
+__global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int pop, int gen, uint64_t n_slots, const uint64_t *__restrict__ xo_off,
+                                const uint32_t *__restrict__ stash, uint32_t *__restrict__ xo_bp, uint32_t *__restrict__ flips) {
+    uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const uint64_t o = xo_off[slot];
+    const uint32_t cnt = (uint32_t)(xo_off[slot + 1] - o);
+    if (cnt == 0) return;
+    const int c = (int)((slot >> 1) % (uint64_t)n_chr);
+    if (cnt <= XO_STASH) {
+        for (uint32_t q = 0; q < cnt; q++) {
+            uint32_t x = stash[slot * XO_STASH + q];
+            xo_bp[o + q] = x;
+            if (flips) flips[o + q] = locus_lower_bound(g, c, x);
+        }
+        return;
+    }
+    const uint64_t i = (slot >> 1) / (uint64_t)n_chr;
+    const int gam = (int)(slot & 1);
+    const uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
+    const double *T = m.T + r0 + c;
+    uint32_t j = 0, blk = 0, n = 0;
+    for (;;) {
+        uint32_t w[4];
+        draw(st, P_XO, pop, gen, i, m.chr_id[c] * 2u + (uint32_t)gam, blk++, w);
+        if (j >= R) break;
+        double v = (1.0 - u01(w[0], w[1])) * T[j];
+        long long k = next_success(T, R, j, v);
+        if (k < 0) break;
+        uint32_t x = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
+        xo_bp[o + n] = x;
+        if (flips) flips[o + n] = locus_lower_bound(g, c, x);
+        n++;
+        j = (uint32_t)k + 1;
+    }
+}
+
 // mutations: one thread per (offspring, chromosome)
 template <bool FILL>
 __global__ void sample_mut_kernel(Stream st, MapDev m, int n_chr, int pop, int gen, uint64_t first, uint64_t n_items,
