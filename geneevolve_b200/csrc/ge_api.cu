@@ -6,6 +6,7 @@
 // flat arrays in and pulls `.info` / `.hap` / `.int` content out on demand.  There is no CPU compute path.
 // Reference lines cited as :N are src/Simulation.cpp:N.
 #include "ge_context.cuh"
+#include <cstdlib>
 #include "ge_segments.cuh"
 #include "ge_mating.cuh"
 
@@ -216,6 +217,7 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
     cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo);
+    c->serial = std::getenv("GE_SERIAL") != nullptr;  // measurement aid: queue the bulk kernel on the control stream (no overlap)
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     for (PopDev &P : c->pop) for (DrawSet &D : P.ds) cudaEventCreateWithFlags(&D.bulk_done, cudaEventDisableTiming);
@@ -808,22 +810,23 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
             xo_to_flips_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->genome(), n_slots, D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.flips.as<uint32_t>());
             GE_TRY(ctx->check_launch("xo_to_flips"));
         }
+        cudaStream_t bulk = ctx->serial ? st : ctx->bulk;
         CUDA_TRY(cudaEventRecord(ctx->ev_ready, st));
-        CUDA_TRY(cudaStreamWaitEvent(ctx->bulk, ctx->ev_ready, 0));
+        CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_ready, 0));
         ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0};
-        if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, ctx->bulk)); }
+        if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, bulk)); }
         unsigned grid = (unsigned)std::min<uint64_t>(n_off, 1u << 20);  // one short-lived CTA per offspring: control-stream kernels get SM slots quickly
-        propagate_bits_kernel<<<grid, PROP_THREADS, 0, ctx->bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+        propagate_bits_kernel<<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
                                                                     D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
         GE_TRY(ctx->check_launch("propagate_bits"));
         if (ctx->profiling) {
-            CUDA_TRY(cudaEventRecord(evp.b, ctx->bulk));
+            CUDA_TRY(cudaEventRecord(evp.b, bulk));
             uint64_t M = 0;
             for (uint32_t v : ctx->chr_nloci) M += v;
             evp.bytes = n_off * M / 2;  // 0.5 byte per individual-locus
             ctx->ev_pending.push_back(evp);
         }
-        CUDA_TRY(cudaEventRecord(D.bulk_done, ctx->bulk));
+        CUDA_TRY(cudaEventRecord(D.bulk_done, bulk));
         D.bulk_pending = true;
         bulk_launched = true;
     }

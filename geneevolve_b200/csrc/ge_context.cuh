@@ -111,6 +111,7 @@ struct ge_ctx {
     cudaStream_t stream = nullptr;  // control stream (high priority): mating, sampling, CV planes, phenotypes
     cudaStream_t bulk = nullptr;    // bulk stream (low priority): bit-packed haplotype propagation, one generation behind at most
     cudaEvent_t ev_ready = nullptr, ev_join = nullptr;
+    bool serial = false;
     std::vector<PopDev> pop;
     std::vector<std::vector<uint64_t>> loci;  // host positions per chromosome
     std::vector<double> gamma;

@@ -148,22 +148,39 @@ __device__ __forceinline__ void warp_copy_chunks(uint4 *__restrict__ dst, const 
 }
 
 constexpr int PROP_THREADS = 256;
-constexpr int PROP_MAX_SMEM_FLIPS = 64;
+constexpr int PROP_SMEM_FLIPS = 384;   // flips of one offspring staged in shared memory (mean 2 x 36 on the 22 autosomes)
 
-__global__ void __launch_bounds__(PROP_THREADS)
+// dynamic shared memory: uint64 xo_off[2*n_chr+1] | uint32 flips[PROP_SMEM_FLIPS] | uint8 start[2*n_chr]
+static inline size_t prop_smem_bytes(int n_chr) { return (size_t)(2 * n_chr + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((2 * n_chr + 15) & ~15); }
+
+__global__ void __launch_bounds__(PROP_THREADS, 6)
 propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, uint32_t *__restrict__ off_rows,
                       const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                       const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips,
                       const uint8_t *__restrict__ start_hap, uint64_t off_first, uint32_t n_off) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_next;
-    __shared__ uint32_t s_flips[PROP_THREADS / 32][PROP_MAX_SMEM_FLIPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_ls = 2 * g.n_chr;  // slots of one offspring: chromosome-major, gamete-minor — contiguous in every draw array
+    uint64_t *s_off = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_fl = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(n_ls + 1) * 8);
+    uint8_t *s_start = smem_raw + (size_t)(n_ls + 1) * 8 + PROP_SMEM_FLIPS * 4;
+    const int lane = threadIdx.x & 31;
     for (uint32_t oi = blockIdx.x; oi < n_off; oi += gridDim.x) {
         const uint64_t i = off_first + oi;  // offspring index in the (possibly sharded) generation
+        const uint64_t slot0 = i * (uint64_t)n_ls;
         __syncthreads();
+        // stage this offspring's crossover metadata once, coalesced: the work items below never wait on a
+        // dependent global load before their first copy
+        for (int t = threadIdx.x; t <= n_ls; t += PROP_THREADS) s_off[t] = xo_off[slot0 + t];
+        for (int t = threadIdx.x; t < n_ls; t += PROP_THREADS) s_start[t] = start_hap[slot0 + t];
         if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
+        const uint64_t e_base = s_off[0];
+        const uint32_t n_fl = (uint32_t)(s_off[n_ls] - e_base);
+        const bool staged = n_fl <= PROP_SMEM_FLIPS;
+        if (staged) for (uint32_t t = threadIdx.x; t < n_fl; t += PROP_THREADS) s_fl[t] = flips[e_base + t];
         const uint32_t pf = father[i], pm = mother[i];
+        __syncthreads();
         for (;;) {
             uint32_t item = 0;
             if (lane == 0) item = atomicAdd(&s_next, 1u);
@@ -172,16 +189,10 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
             const int gam = item >= tt.n_items;
             const uint32_t it = gam ? item - tt.n_items : item;
             const uint32_t c = tt.chr[it], q0 = tt.chunk0[it], q1 = q0 + tt.nchunk[it];
-            const uint64_t slot = (i * (uint64_t)g.n_chr + c) * 2 + gam;
-            const uint64_t e0 = xo_off[slot];
-            const uint32_t k = (uint32_t)(xo_off[slot + 1] - e0);
-            const uint32_t *fl;
-            if (k <= PROP_MAX_SMEM_FLIPS) {
-                __syncwarp();
-                for (uint32_t t = lane; t < k; t += 32) s_flips[warp][t] = flips[e0 + t];
-                __syncwarp();
-                fl = s_flips[warp];
-            } else fl = flips + e0;
+            const int ls = (int)c * 2 + gam;
+            const uint64_t e0 = s_off[ls];
+            const uint32_t k = (uint32_t)(s_off[ls + 1] - e0);
+            const uint32_t *fl = staged ? s_fl + (e0 - e_base) : flips + e0;
             const uint32_t woff = g.chr_word_off[c];
             const uint32_t prow = gam ? pm : pf;
             const uint4 *h0 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow) * g.W + woff);
@@ -191,7 +202,7 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
             uint32_t j = 0;
             const uint32_t x0 = q0 << 7;
             while (j < k && fl[j] <= x0) j++;
-            uint32_t cur = (start_hap[slot] ^ j) & 1u;
+            uint32_t cur = (s_start[ls] ^ j) & 1u;
             uint32_t q = q0;
             while (q < q1) {
                 const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
