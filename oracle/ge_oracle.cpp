@@ -1178,6 +1178,14 @@ int go_set_founder_panel(go_ctx *ctx, int pop, int chr, const uint8_t *al, uint6
     P.panel[chr].assign(al, al + nh * ctx->loci[chr].size()); P.n_founder_haps = nh;
     return GE_OK;
 }
+int go_set_founder_panel_packed(go_ctx *ctx, int pop, int chr, const uint32_t *words, uint64_t nh) {  // same panel, bit-packed
+    CHECK_POP(ctx, pop);
+    uint64_t nl = ctx->loci[chr].size(), nw = (nl + 31) / 32;
+    std::vector<uint8_t> al(nh * nl);
+    for (uint64_t h = 0; h < nh; h++)
+        for (uint64_t s = 0; s < nl; s++) al[h * nl + s] = (words[h * nw + (s >> 5)] >> (s & 31)) & 1u;
+    return go_set_founder_panel(ctx, pop, chr, al.data(), nh);
+}
 int go_set_cv(go_ctx *ctx, int pop, int phen, int chr, const uint64_t *bp, const double *a, const double *d, uint64_t ncv, const uint8_t *val, uint64_t nh) {
     CHECK_POP(ctx, pop);
     CvChr &cv = ctx->pop[pop].cv[phen][chr];

@@ -33,6 +33,7 @@ int go_set_genetic_map(go_ctx *ctx, int pop, int chr, const uint64_t *bp, const 
 int go_set_mutation_map(go_ctx *ctx, int pop, int chr, const uint64_t *bp, const double *rate, uint64_t n_rows);
 int go_set_loci(go_ctx *ctx, int chr, const uint64_t *pos, uint64_t n_loci);
 int go_set_founder_panel(go_ctx *ctx, int pop, int chr, const uint8_t *alleles, uint64_t n_founder_haps);
+int go_set_founder_panel_packed(go_ctx *ctx, int pop, int chr, const uint32_t *words, uint64_t n_founder_haps);
 int go_set_cv(go_ctx *ctx, int pop, int phen, int chr, const uint64_t *bp, const double *a, const double *d, uint64_t n_cv, const uint8_t *founder_cv, uint64_t n_founder_haps);
 int go_set_pheno_scheme(go_ctx *ctx, int pop, int phen, double va, double vd, double ve, double vc, double vf, double omega, double beta, double lambda);
 int go_set_gamma(go_ctx *ctx, const double *gamma);

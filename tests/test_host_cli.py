@@ -1,0 +1,151 @@
+"""The C++ host (host/): the reference's command line and file formats over the C-ABI.
+
+The same checks run twice: without a GPU on the host sources compiled against the CPU oracle (tests/host_oracle_shim.h,
+built into tests/_build/ by this test) and with -m gpu on the product binary host/geneevolve_b200_cli, which links
+libgeneevolve_b200.so.  Where the reference binary (oracle/_ref/GeneEvolve_ref) is present, it is run on the same
+input files: the set of output files, every header and every draw-independent column (generation-0 IDs, additive
+values, the generation-0 var_A/var_E of the summary) must be identical to what the reference writes.  The genotype
+outputs are checked against each other: every part of the `.int` file, materialised from the founder panel
+(ras_convert_interval_to_hap_matrix, src/Simulation.cpp:1186-1230), must reproduce the `.hap` file.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import stats_util as su
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "GeneEvolve_ref")
+INFO_HEADER = ("ID ID_Father ID_Mother ID_Fathers_Father ID_Fathers_Mother ID_Mothers_Father ID_Mothers_Mother sex "
+               "ph1_A ph1_D ph1_G ph1_C ph1_E ph1_F ph1_P MV SV SV_f")
+SUMMARY_HEADER = ("gen ph1_var_A ph1_var_D ph1_var_G ph1_var_C ph1_var_E ph1_var_F ph1_var_P ph1_h2 ph1_var_G_std "
+                  "var_mating_value var_selection_value")
+INT_HEADER = "h_ID chr hap st en hap_index gen0_indv root_pop"
+
+
+def oracle_cli():
+    """host/*.cpp compiled against the CPU oracle (test-only build)."""
+    from oracle import oracle
+    oracle.lib()
+    out = os.path.join(HERE, "_build", "host_oracle_cli")
+    srcs = [os.path.join(ROOT, "host", f) for f in ("main.cpp", "ge_host.cpp")]
+    deps = srcs + [os.path.join(ROOT, "host", "ge_host.hpp"), os.path.join(HERE, "host_oracle_shim.h"), oracle.LIB]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O1", "-std=c++14", "-I" + os.path.join(ROOT, "include"), "-include", os.path.join(HERE, "host_oracle_shim.h"),
+                        "-o", out] + srcs + ["-L" + os.path.dirname(oracle.LIB), "-l:libge_oracle.so", "-Wl,-rpath," + os.path.dirname(oracle.LIB)], check=True)
+    return out
+
+
+def product_cli():
+    out = os.path.join(ROOT, "host", "geneevolve_b200_cli")
+    assert os.path.exists(out), "host/geneevolve_b200_cli is missing: run __graft_entry__.build()"
+    return out
+
+
+def scenario(tmp_path, n_gen=3):
+    sc = dict(su.SCENARIOS["S_assort"])
+    sc["gens"] = sc["gens"][:n_gen]
+    return sc, su.write_reference_inputs(sc, str(tmp_path))
+
+
+def check_cli(cli, tmp_path):
+    sc, args = scenario(tmp_path)
+    G = len(sc["gens"])
+    pre = str(tmp_path / "ours")
+    r = subprocess.run([cli] + args + ["--seed", "5", "--prefix", pre, "--out_hap", "--out_interval", "--quiet"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    names = sorted(f[len("ours"):] for f in os.listdir(tmp_path) if f.startswith("ours"))
+    expect = sorted([f".info.pop1.gen{g}.txt" for g in range(G + 1)] + [".pop1.summary"] +
+                    [f".pop1.gen{G}.chr{c}.{e}" for c in sc["chrs"] for e in ("hap", "indv", "int")])
+    assert names == expect
+    # headers and shapes
+    for g in range(G + 1):
+        with open(f"{pre}.info.pop1.gen{g}.txt") as f:
+            assert f.readline().rstrip("\n") == INFO_HEADER
+    with open(f"{pre}.pop1.summary") as f:
+        assert f.readline().rstrip("\n") == SUMMARY_HEADER
+    summ = np.loadtxt(f"{pre}.pop1.summary", skiprows=1)
+    assert summ.shape == (G + 1, 12) and np.array_equal(summ[:, 0], np.arange(G + 1))
+    assert summ[0, 1] == pytest.approx(sc["va"], rel=1e-5) and np.allclose(summ[:, 5], sc["ve"], rtol=1e-5)   # var_A(0) = va, var_E = ve every generation
+    info_last = np.loadtxt(f"{pre}.info.pop1.gen{G}.txt", skiprows=1)
+    n_last = info_last.shape[0]
+    assert abs(n_last - sc["gens"][-1][0]) < 6 * np.sqrt(sc["gens"][-1][0])     # Poisson families
+    assert np.array_equal(info_last[:, 0], np.arange(1, n_last + 1)) and set(info_last[:, 7]) <= {1.0, 2.0}
+    assert np.allclose(info_last[:, 10], info_last[:, 8] + info_last[:, 9], atol=1e-5)                         # G = A + D
+    assert np.allclose(info_last[:, 14], info_last[:, 8:14].sum(axis=1) - info_last[:, 10], atol=2e-5)         # P = A + D + C + E + F
+    # genotype outputs: .hap (rows = SNPs, columns = haplotypes), .indv, .int; segments materialise to the .hap file
+    panel = su.make_panel(sc)
+    for P in panel:
+        c = P["chr"]
+        base = f"{pre}.pop1.gen{G}.chr{c}"
+        hap = np.loadtxt(base + ".hap", dtype=np.uint8)
+        assert hap.shape == (sc["n_snp"], 2 * n_last)
+        assert np.array_equal(np.loadtxt(base + ".indv", dtype=np.int64), np.arange(1, n_last + 1))
+        with open(base + ".int") as f:
+            assert f.readline().rstrip("\n") == INT_HEADER
+            rows = [line.split() for line in f]
+        lo, hi = 1000 * c, 1000 * c + (sc["map_rows"] - 1) * sc["map_step"]
+        rebuilt = np.zeros_like(hap)
+        cover = {}
+        for h_id, chr_, ih, st, en, hidx, who, root in rows:
+            assert int(chr_) == c and root == "1" and who == f"id{(int(hidx) - 1) // 2 + 1}.{(int(hidx) - 1) % 2 + 1}"
+            col = 2 * (int(h_id) - 1) + int(ih)
+            sel = (P["pos"] >= int(st)) & (P["pos"] < int(en))
+            rebuilt[sel, col] = P["hap"][sel, int(hidx) - 1]
+            cover.setdefault(col, []).append((int(st), int(en)))
+        assert np.array_equal(rebuilt, hap), "the .int parts do not materialise to the .hap file"
+        for col in range(2 * n_last):   # parts tile [first map row, last map row) in order, no gaps
+            seg = cover[col]
+            assert seg[0][0] == lo and seg[-1][1] == hi and all(a[1] == b[0] for a, b in zip(seg, seg[1:]))
+    # against the reference binary on the same files
+    if os.path.exists(REF_BIN):
+        rp = str(tmp_path / "ref")
+        rr = subprocess.run([REF_BIN] + args + ["--seed", "5", "--prefix", rp, "--out_hap", "--out_interval"], capture_output=True, text=True)
+        assert rr.returncode == 0
+        ref_names = sorted(f[len("ref"):] for f in os.listdir(tmp_path) if f.startswith("ref"))
+        assert ref_names == names
+        for suffix in [".info.pop1.gen0.txt", ".pop1.summary", f".pop1.gen{G}.chr{sc['chrs'][0]}.int"]:
+            with open(pre + suffix) as a, open(rp + suffix) as b:
+                assert a.readline() == b.readline(), suffix
+        a, b = np.loadtxt(pre + ".info.pop1.gen0.txt", skiprows=1), np.loadtxt(rp + ".info.pop1.gen0.txt", skiprows=1)
+        assert a.shape == b.shape and np.array_equal(a[:, :7], b[:, :7])
+        for col in (8, 9, 10, 11, 13):   # A, D, G, C, F at generation 0 do not depend on any draw
+            assert np.array_equal(a[:, col], b[:, col]), col
+        rs = np.loadtxt(rp + ".pop1.summary", skiprows=1)
+        assert rs.shape == summ.shape and np.array_equal(rs[0, [1, 2, 3, 4, 5, 6]], summ[0, [1, 2, 3, 4, 5, 6]])
+        with open(pre + f".pop1.gen{G}.chr{sc['chrs'][0]}.hap") as f1, open(rp + f".pop1.gen{G}.chr{sc['chrs'][0]}.hap") as f2:
+            l1, l2 = f1.readline(), f2.readline()
+            assert set(l1) == set(l2) == set("01 \n") and l1[1] == l2[1] == " " and l1.endswith(" \n") and l2.endswith(" \n")
+
+
+def check_errors(cli, tmp_path):
+    sc, args = scenario(tmp_path, 1)
+    bad = [a if a != str(tmp_path / "s.rmap") else str(tmp_path / "missing.rmap") for a in args]
+    r = subprocess.run([cli] + bad + ["--prefix", str(tmp_path / "e")], capture_output=True, text=True)
+    assert r.returncode == 255 and "Error: can not open the file [" in r.stdout          # exit code -1 like src/Main.cpp:84-88
+    r = subprocess.run([cli] + args[2:] + ["--prefix", str(tmp_path / "e")], capture_output=True, text=True)
+    assert r.returncode == 255 and "missing parameter [--file_gen_info]" in r.stdout
+    r = subprocess.run([cli] + args + ["--out_vcf"], capture_output=True, text=True)
+    assert r.returncode == 255 and "--out_vcf" in r.stdout
+
+
+def test_host_cli_on_oracle(tmp_path):
+    check_cli(oracle_cli(), tmp_path)
+
+
+def test_host_cli_errors_on_oracle(tmp_path):
+    check_errors(oracle_cli(), tmp_path)
+
+
+@pytest.mark.gpu
+def test_host_cli_on_gpu(tmp_path):
+    check_cli(product_cli(), tmp_path)
+
+
+@pytest.mark.gpu
+def test_host_cli_errors_on_gpu(tmp_path):
+    check_errors(product_cli(), tmp_path)
