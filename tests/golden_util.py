@@ -8,7 +8,8 @@ import numpy as np
 from geneevolve_b200 import capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SCENARIOS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")))
+SCENARIOS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
+                   if not os.path.basename(p).startswith("stats_inputs_"))  # those hold inputs only (tests/test_statistics.py)
 
 
 class Golden:

@@ -1,0 +1,288 @@
+"""Edge cases and size-independent properties of the CUDA path (-m gpu), through the C-ABI.
+
+Part 1 — adversarial small cases against the (pinned) CPU oracle under caller-supplied draws: chromosome lengths
+around the 32-bit word / 128-bit chunk / 8 KB tile boundaries (1, 31, 32, 33, 127, 128, 129, 4097 … loci), crossovers
+exactly on locus positions, on the first and last map rows, duplicated, hundreds per gamete (beyond the shared-memory
+staging of propagate_bits_kernel), empty crossover lists, a single offspring, couples without offspring.
+Part 2 — error behaviour of the boundary (capacity, empty mating lists, bad migration rows, bad indices).
+Part 3 — properties at the bench's full size (100 000 individuals x 1 000 000 loci), where no CPU oracle can follow:
+the causal-variant bit planes and the bit-packed haplotype rows are propagated by two independent kernels from the
+same draws, so the rows read at the CV loci must equal the CV planes; with recombination switched off every
+offspring row must be a verbatim copy of the drawn parental row.
+"""
+import numpy as np
+import pytest
+
+from geneevolve_b200 import capi, workloads
+from oracle.oracle import OracleEngine
+
+pytestmark = pytest.mark.gpu
+
+
+class Case:
+    """A random single-population input with chosen chromosome sizes, plus caller-supplied draws."""
+
+    def __init__(self, seed, n_loci, n_founders=12, map_rows=9, step=64, n_cv=5):
+        rng = np.random.default_rng(seed)
+        self.rng, self.n_chr, self.nf = rng, len(n_loci), n_founders
+        self.maps, self.loci, self.panel, self.cv = [], [], [], []
+        for c, nl in enumerate(n_loci):
+            bp = 1000 + step * np.arange(map_rows, dtype=np.uint64)
+            p = np.concatenate([[0.0], rng.uniform(0.0, 0.2, map_rows - 1)])
+            lo, hi = int(bp[0]) - 20, int(bp[-1]) + 20          # some loci outside the covered range
+            if nl <= hi - lo:
+                pos = np.sort(rng.choice(np.arange(lo, hi), size=nl, replace=False)).astype(np.uint64)
+            else:                                               # more loci than bp: duplicates are legal positions
+                pos = np.sort(rng.integers(lo, hi, size=nl)).astype(np.uint64)
+            hap = (rng.uniform(size=(2 * n_founders, nl)) < 0.5).astype(np.uint8)
+            k = min(n_cv, nl)
+            idx = np.sort(rng.choice(nl, size=k, replace=False))
+            self.maps.append((bp, p, step)); self.loci.append(pos); self.panel.append(hap)
+            self.cv.append(dict(bp=pos[idx], a=rng.normal(size=k), d=rng.normal(size=k) * 0.3, val=hap[:, idx]))
+
+    def kwargs(self, cap, **over):
+        kw = dict(n_pop=1, n_chr=self.n_chr, n_phen=1, seed=11, capacity=cap, rng_mode=capi.GE_RNG_REPLAY)
+        kw.update(over)
+        return kw
+
+    def configure(self, e):
+        for c in range(self.n_chr):
+            e.set_loci(c, self.loci[c])
+        e.set_population(0, False, False, 0.0)
+        for c in range(self.n_chr):
+            bp, p, step = self.maps[c]
+            e.set_genetic_map(0, c, bp, p, step)
+            e.set_founder_panel(0, c, self.panel[c])
+            e.set_cv(0, 0, c, self.cv[c]["bp"], self.cv[c]["a"], self.cv[c]["d"], self.cv[c]["val"])
+        e.set_pheno_scheme(0, 0, va=0.5, vd=0.1, ve=0.4)
+
+    def draws0(self):
+        n = self.nf
+        return capi.Draws(n, sex=(np.arange(n) % 2 + 1).astype(np.uint8), e_raw=self.rng.normal(size=(1, n)))
+
+    def draws(self, n_par, n_off, xo_lists):
+        """xo_lists(slot, chromosome) -> sorted crossover positions of that gamete."""
+        rng, C = self.rng, self.n_chr
+        off, bp = [0], []
+        for s in range(n_off * C * 2):
+            x = list(xo_lists(s, (s // 2) % C))
+            bp += x
+            off.append(len(bp))
+        return capi.Draws(n_off, father=rng.integers(0, n_par, n_off), mother=rng.integers(0, n_par, n_off),
+                          sex=rng.integers(1, 3, n_off).astype(np.uint8), xo_off=np.array(off, np.uint64), xo_bp=np.array(bp, np.uint64),
+                          start_hap=rng.integers(0, 2, n_off * C * 2).astype(np.uint8), e_raw=rng.normal(size=(1, n_off)))
+
+
+def run_pair(cuda_lib, case, gens, rep=capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, cap=64):
+    """gens: list of (n_off, xo_lists).  Runs the library and the oracle on identical draws, compares everything."""
+    gpu = capi.Engine(cuda_lib, **case.kwargs(cap, representation=rep))
+    cpu = OracleEngine(**case.kwargs(cap))
+    d0 = case.draws0()
+    for e in (gpu, cpu):
+        case.configure(e)
+        e.init_generation0([d0])
+    gp = [capi.gen_params(10)]
+    n_par = case.nf
+    for g, (n_off, xo) in enumerate(gens, 1):
+        d = case.draws(n_par, n_off, xo)
+        for e in (gpu, cpu):
+            e.step_generation(g, gp, None, [d])
+        for c in range(case.n_chr):
+            assert np.array_equal(gpu.haplotypes(0, c), cpu.haplotypes(0, c)), f"gen {g} chr {c}: haplotypes"
+            assert np.array_equal(gpu.haplotypes(0, c), cpu.haplotypes_from_segments(0, c)), f"gen {g} chr {c}: bits vs segments"
+            assert np.array_equal(gpu.cv_alleles(0, 0, c), cpu.cv_alleles(0, 0, c)), f"gen {g} chr {c}: CV alleles"
+            if rep & capi.GE_REP_SEGMENTS:
+                assert np.array_equal(gpu.segments(0, c)["seg"], cpu.segments(0, c)["seg"])
+        a, b = gpu.individuals(0), cpu.individuals(0)
+        assert np.array_equal(a["ids"], b["ids"])
+        for k in "ADGEP":
+            np.testing.assert_allclose(a[k], b[k], rtol=1e-9, atol=1e-11)
+        n_par = n_off
+
+
+@pytest.mark.parametrize("n_loci", [[1], [31, 32, 33], [127, 128, 129], [255, 257, 1], [4097, 5], [65536 + 1, 200]])
+def test_word_chunk_and_tile_boundaries(cuda_lib, n_loci):
+    case = Case(1000 + sum(n_loci), n_loci)
+
+    def xo(slot, c):
+        bp, _, step = case.maps[c]
+        r = case.rng
+        k = int(r.integers(0, 4))
+        return np.sort(r.integers(int(bp[0]), int(bp[-1]) + step, size=k))
+
+    run_pair(cuda_lib, case, [(9, xo), (1, xo), (17, xo)])
+
+
+def test_crossovers_on_loci_map_rows_and_duplicates(cuda_lib):
+    case = Case(7, [100, 40])
+
+    def xo(slot, c):
+        bp, _, step = case.maps[c]
+        pos = case.loci[c]
+        choice = slot % 6
+        if choice == 0:
+            return []                                            # the chosen parental haplotype unchanged (:2910)
+        if choice == 1:
+            return [int(bp[0])]                                  # on the first map row: flips everything
+        if choice == 2:
+            return [int(bp[-1]), int(bp[-1]) + step - 1]         # last-row quirk: positions at/after the covered end
+        if choice == 3:
+            p = int(pos[len(pos) // 2])
+            return [p, p]                                        # duplicate on a locus: two flips, no net change
+        if choice == 4:
+            return sorted(int(x) for x in pos[[3, 4, 5]])        # on three consecutive loci
+        return sorted(int(x) for x in case.rng.choice(pos, size=7))
+
+    run_pair(cuda_lib, case, [(24, xo), (24, xo)])
+
+
+def test_hundreds_of_crossovers_per_gamete(cuda_lib):
+    """More flips per offspring than propagate_bits_kernel stages in shared memory (global-memory fallback)."""
+    case = Case(9, [3000], map_rows=40, step=100)
+
+    def xo(slot, c):
+        bp, _, step = case.maps[c]
+        return np.sort(case.rng.integers(int(bp[0]), int(bp[-1]), size=260))
+
+    run_pair(cuda_lib, case, [(6, xo), (5, xo)], rep=capi.GE_REP_BITS)
+
+
+def test_philox_many_crossovers_matches_oracle(cuda_lib):
+    """Recombination rates high enough that most gametes exceed the per-slot stash of sample_xo_kernel."""
+    case = Case(21, [300, 90], map_rows=60, step=64)
+    case.maps = [(bp, np.concatenate([[0.0], np.full(len(bp) - 1, 0.35)]), step) for bp, _, step in case.maps]
+    kw = case.kwargs(80, rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS)
+    gpu, cpu = capi.Engine(cuda_lib, **kw), OracleEngine(**kw)
+    for e in (gpu, cpu):
+        case.configure(e)
+        e.set_population(0, False, True, 0.0)   # random mating
+        e.init_generation0()
+    for g in range(1, 4):
+        gp = [capi.gen_params(40, 0.0, "p", "thr", 1, 1)]
+        for e in (gpu, cpu):
+            e.step_generation(g, gp)
+        da, db = gpu.draws(0), cpu.draws(0)
+        assert len(da["xo_bp"]) / (40 * 2 * 2) > 8          # mean crossovers per gamete-chromosome
+        for k in ("father", "mother", "xo_off", "xo_bp", "start_hap", "sex"):
+            assert np.array_equal(da[k], db[k]), k
+        for c in range(2):
+            assert np.array_equal(gpu.haplotypes(0, c), cpu.haplotypes(0, c))
+
+
+def test_boundary_errors(cuda_lib):
+    case = Case(3, [50])
+    e = capi.Engine(cuda_lib, **case.kwargs(16, representation=capi.GE_REP_BITS))
+    case.configure(e)
+    e.init_generation0([case.draws0()])
+    gp = [capi.gen_params(10)]
+    none = lambda s, c: []  # noqa: E731
+    with pytest.raises(capi.GeneEvolveError) as ei:          # more offspring than the capacity given at ge_create
+        e.step_generation(1, gp, None, [case.draws(case.nf, 17, none)])
+    assert ei.value.code == -3
+    d = case.draws(case.nf, 4, none)
+    d.arrays["father"][2] = case.nf                            # parent index outside the parent generation
+    with pytest.raises(capi.GeneEvolveError) as ei:
+        e.step_generation(1, gp, None, [d])
+    assert ei.value.code == -1
+    with pytest.raises(capi.GeneEvolveError):                  # replay context cannot mate on its own
+        e.mate(0, 1, gp[0])
+    # Philox context: nobody may mate when the selection function is 0 for everyone (thr with p1 = 0)
+    kw = case.kwargs(64, rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS)
+    p = capi.Engine(cuda_lib, **kw)
+    case.configure(p)
+    p.init_generation0()
+    p.step_generation(1, [capi.gen_params(20, 0.0, "p", "thr", 0.0, 1e9)])   # evaluated at the END of generation 1
+    with pytest.raises(capi.GeneEvolveError) as ei:
+        p.step_generation(2, [capi.gen_params(20)])
+    assert ei.value.code == -4 and "couples=0" in str(ei.value)
+    with pytest.raises(capi.GeneEvolveError):
+        capi.Engine(cuda_lib, n_pop=1, n_chr=1, n_phen=1, capacity=0)
+
+
+def test_migration_row_must_sum_to_one(cuda_lib):
+    case = Case(5, [40])
+    kw = case.kwargs(64, rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, n_pop=2)
+    e = capi.Engine(cuda_lib, **kw)
+    for c in range(case.n_chr):
+        e.set_loci(c, case.loci[c])
+    for p in range(2):
+        e.set_population(p, False, True, 0.0)
+        bp, pr, step = case.maps[0]
+        e.set_genetic_map(p, 0, bp, pr, step)
+        e.set_founder_panel(p, 0, case.panel[0])
+        e.set_cv(p, 0, 0, case.cv[0]["bp"], case.cv[0]["a"], case.cv[0]["d"], case.cv[0]["val"])
+        e.set_pheno_scheme(p, 0, va=0.5, vd=0.0, ve=0.5)
+    e.init_generation0()
+    gp = [capi.gen_params(20, 0.0, "p", "thr", 1, 1)] * 2
+    with pytest.raises(capi.GeneEvolveError) as ei:
+        e.step_generation(1, gp, [0.9, 0.2, 0.1, 0.9])
+    assert ei.value.code == -6
+    e2 = capi.Engine(cuda_lib, **kw)  # a valid ring row moves round(0.1 * n) individuals each way
+    for c in range(case.n_chr):
+        e2.set_loci(c, case.loci[c])
+    for p in range(2):
+        e2.set_population(p, False, True, 0.0)
+        bp, pr, step = case.maps[0]
+        e2.set_genetic_map(p, 0, bp, pr, step)
+        e2.set_founder_panel(p, 0, case.panel[0])
+        e2.set_cv(p, 0, 0, case.cv[0]["bp"], case.cv[0]["a"], case.cv[0]["d"], case.cv[0]["val"])
+        e2.set_pheno_scheme(p, 0, va=0.5, vd=0.0, ve=0.5)
+    e2.init_generation0()
+    e2.step_generation(1, gp, [0.9, 0.1, 0.2, 0.8])
+    assert (e2.population_size(0), e2.population_size(1)) == (20 - 2 + 4, 20 - 4 + 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full size
+# ---------------------------------------------------------------------------------------------------------------
+def full_size_engine(cuda_lib, zero_recombination=False, n=100000):
+    cfg = workloads.make_workload("config3_100k_x_1M", n_override=n)
+    if zero_recombination:
+        cfg["maps"] = [(bp, cm, np.zeros_like(p)) for bp, cm, p in cfg["maps"]]
+    cap = int(max(cfg["n"], cfg["founders"]) * 1.03) + 1024
+    eng = capi.Engine(cuda_lib, n_pop=1, n_chr=len(cfg["chrs"]), n_phen=1, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX,
+                      seed=99, capacity=cap)
+    workloads.configure_engine(eng, cfg)
+    eng.init_generation0()
+    return eng, cfg
+
+
+def test_full_size_rows_agree_with_cv_planes(cuda_lib):
+    """100k x 1M, three generations with assortative mating and selection: at every causal variant the bit-packed row
+    (propagate_bits_kernel) and the CV plane (cv_propagate_bits_kernel) must hold the same allele."""
+    eng, cfg = full_size_engine(cuda_lib)
+    gp = [capi.gen_params(cfg["n"], cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
+    for g in range(1, 4):
+        eng.step_generation(g, gp)
+    n = eng.population_size(0)
+    assert abs(n - cfg["n"]) < 6 * np.sqrt(cfg["n"])
+    for c in (len(cfg["chrs"]) - 1, 0, 10):          # the shortest, the longest and a middle chromosome
+        words = eng.haplotypes_packed(0, c)
+        idx = cfg["cvs"][c]["idx"].astype(np.int64)
+        at_cv = ((words[:, idx // 32] >> (idx % 32).astype(np.uint32)) & 1).astype(np.uint8)
+        cv = eng.cv_alleles(0, 0, c)
+        assert at_cv.shape == cv.shape == (2 * n, len(idx))
+        assert np.array_equal(at_cv, cv), f"chromosome index {c}"
+        f = words.view(np.uint8).reshape(2 * n, -1)
+        assert 0.3 < np.unpackbits(f[:2000], axis=1).mean() < 0.7   # rows still look like random founder mosaics
+    ind = eng.individuals(0)
+    assert np.isfinite(ind["P"]).all() and 0.3 < np.var(ind["A"][0]) / np.var(ind["P"][0]) < 0.7
+
+
+def test_full_width_rows_are_verbatim_parental_copies_without_recombination(cuda_lib):
+    """20k x 1M with every recombination probability zero: each offspring row equals the drawn parental row."""
+    eng, cfg = full_size_engine(cuda_lib, zero_recombination=True, n=20000)
+    gp = [capi.gen_params(cfg["n"], cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
+    eng.step_generation(1, gp)
+    C = len(cfg["chrs"])
+    for c in (C - 1, 3):
+        parents = eng.haplotypes_packed(0, c)
+        eng.step_generation(2 if c == C - 1 else 3, gp)
+        d = eng.draws(0)
+        assert len(d["xo_bp"]) == 0
+        kids = eng.haplotypes_packed(0, c)
+        n_off = len(d["father"])
+        slot = (np.arange(n_off) * C + c) * 2
+        src_f = 2 * d["father"].astype(np.int64) + d["start_hap"][slot]
+        src_m = 2 * d["mother"].astype(np.int64) + d["start_hap"][slot + 1]
+        assert np.array_equal(kids[0::2], parents[src_f]) and np.array_equal(kids[1::2], parents[src_m])
