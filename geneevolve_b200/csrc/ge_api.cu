@@ -217,7 +217,11 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
     cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo);
-    c->serial = std::getenv("GE_SERIAL") != nullptr;  // measurement aid: queue the bulk kernel on the control stream (no overlap)
+    c->serial = std::getenv("GE_SERIAL") != nullptr;
+    if (const char *t = std::getenv("GE_THIN")) c->thin = std::atoi(t);
+    if (const char *t = std::getenv("GE_PROP_DEPTH")) c->prop_depth = std::atoi(t);
+    if (const char *t = std::getenv("GE_PROP")) c->use_tma = std::string(t) == "tma";
+    if (const char *t = std::getenv("GE_THIN_MIN_GB")) c->thin_min_bytes = std::atof(t) * 1e9;  // measurement aid: queue the bulk kernel on the control stream (no overlap)
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     for (PopDev &P : c->pop) for (DrawSet &D : P.ds) cudaEventCreateWithFlags(&D.bulk_done, cudaEventDisableTiming);
@@ -350,7 +354,7 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
         cv_tables_kernel<<<nblk(ncv, 128), 128, 0, ctx->stream>>>(ctx->cvset(), ctx->d_cv_count.as<unsigned long long>(), S.n, ctx->d_a_eff.as<double>(),
                                                                   ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), ctx->d_LA.as<double>(), ctx->d_LD.as<double>());
         GE_TRY(ctx->check_launch("cv_tables"));
-        genetic_value_lut_kernel<<<nblk(nw * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_LA.as<double>(), ctx->d_LD.as<double>(), S.n,
+        genetic_value_lut_kernel<<<ctx->ctrl_grid(nw * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_LA.as<double>(), ctx->d_LD.as<double>(), S.n,
                                                                               S.A.as<double>(), S.D.as<double>(), S.G.as<double>(), ctx->flags.as<int>());
         GE_TRY(ctx->check_launch("genetic_value_lut"));
     } else {
@@ -769,13 +773,13 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         uint64_t n_slots = n_off * C * 2;
         GE_TRY(ctx->ensure(D.xo_off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(D.start_hap, n_slots));
         GE_TRY(ctx->ensure(ctx->xo_stash, n_slots * XO_STASH * 4));
-        sample_xo_kernel<false><<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, P.cnt32.as<uint32_t>(), nullptr, nullptr, D.start_hap.as<uint8_t>(),
+        sample_xo_kernel<false><<<ctx->ctrl_grid(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, P.cnt32.as<uint32_t>(), nullptr, nullptr, D.start_hap.as<uint8_t>(),
                                                                     ctx->xo_stash.as<uint32_t>());
         GE_TRY(ctx->check_launch("sample_xo<count>"));
         GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, D.xo_off.as<uint64_t>(), &P.n_xo));
         GE_TRY(ctx->ensure(D.xo_bp, std::max<uint64_t>(P.n_xo, 1) * 4));
         if (ctx->bits()) GE_TRY(ctx->ensure(D.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
-        xo_place_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ctx->genome(), C, pop, gen, n_slots, D.xo_off.as<uint64_t>(), ctx->xo_stash.as<uint32_t>(),
+        xo_place_kernel<<<ctx->ctrl_grid(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ctx->genome(), C, pop, gen, n_slots, D.xo_off.as<uint64_t>(), ctx->xo_stash.as<uint32_t>(),
                                                             D.xo_bp.as<uint32_t>(), ctx->bits() ? D.flips.as<uint32_t>() : nullptr);
         GE_TRY(ctx->check_launch("xo_place"));
         if (P.has_mut) {
@@ -816,7 +820,16 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0};
         if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, bulk)); }
         unsigned grid = (unsigned)std::min<uint64_t>(n_off, 1u << 20);  // one short-lived CTA per offspring: control-stream kernels get SM slots quickly
-        propagate_bits_kernel<<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+        if (ctx->use_tma) {
+            size_t sm = prop_tma_smem_bytes(C);
+            if (!ctx->tma_attr_set) { CUDA_TRY(cudaFuncSetAttribute(propagate_bits_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); ctx->tma_attr_set = true; }
+            propagate_bits_tma_kernel<<<grid, TMA_WARPS * 32 + TMA_MERGE_THREADS, sm, bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+                                                                         D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
+        } else if (ctx->prop_depth == 8)
+        propagate_bits_kernel<8><<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+                                                                    D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
+        else
+        propagate_bits_kernel<4><<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
                                                                     D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
         GE_TRY(ctx->check_launch("propagate_bits"));
         if (ctx->profiling) {
@@ -828,12 +841,14 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         }
         CUDA_TRY(cudaEventRecord(D.bulk_done, bulk));
         D.bulk_pending = true;
+        // thin control kernels only pay off while the bulk copy is much longer than the control chain (~1.5 ms)
+        ctx->bulk_busy = !ctx->serial && (double)n_off * ctx->W * 16.0 > ctx->thin_min_bytes;
         bulk_launched = true;
     }
     // ---- causal-variant planes
     if (ctx->n_cv_tot && (ctx->bits() || !ctx->segs())) {
         uint64_t tot = n_off * 2 * ctx->Wcv;
-        cv_propagate_bits_kernel<<<nblk(tot, 256), 256, 0, st>>>(ctx->cvset(), par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
+        cv_propagate_bits_kernel<<<ctx->ctrl_grid(tot, 256), 256, 0, st>>>(ctx->cvset(), par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
                                                                  D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, n_off);
         GE_TRY(ctx->check_launch("cv_propagate_bits"));
         if (ctx->cfg.n_pop > 1) {

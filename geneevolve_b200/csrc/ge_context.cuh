@@ -112,6 +112,18 @@ struct ge_ctx {
     cudaStream_t bulk = nullptr;    // bulk stream (low priority): bit-packed haplotype propagation, one generation behind at most
     cudaEvent_t ev_ready = nullptr, ev_join = nullptr;
     bool serial = false;
+    int thin = 8;   // CTAs per SM the heavy control-stream kernels may take while a bulk copy is in flight (0 = no limit)
+    bool bulk_busy = false;
+    int prop_depth = 4;
+    bool use_tma = false, tma_attr_set = false;
+    double thin_min_bytes = 30e9;  // bytes moved by one bulk launch above which the control kernels go thin
+    // grid of a grid-stride control kernel: full width, or thin while it shares the GPU with propagate_bits_kernel,
+    // so that the high-priority control stream displaces only a fraction of the bulk kernel's resident CTAs
+    unsigned ctrl_grid(uint64_t n_threads, unsigned block) const {
+        uint64_t full = std::max<uint64_t>(1, (n_threads + block - 1) / block);
+        if (!bulk_busy || serial || thin <= 0) return (unsigned)std::min<uint64_t>(full, 1u << 30);
+        return (unsigned)std::min<uint64_t>(full, (uint64_t)n_sm * thin);
+    }
     std::vector<PopDev> pop;
     std::vector<std::vector<uint64_t>> loci;  // host positions per chromosome
     std::vector<double> gamma;

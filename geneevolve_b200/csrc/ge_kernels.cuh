@@ -138,8 +138,18 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+template <int DEPTH>
 __device__ __forceinline__ void warp_copy_chunks(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint32_t q, uint32_t qe, int lane) {
     uint32_t c = q + lane;
+    if (DEPTH == 8) {  // eight independent 16-byte loads in flight per lane: the same bytes in flight per SM with half the warps
+        for (; c + 224 < qe; c += 256) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = ld_stream(src + c + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) st_stream(dst + c + 32 * u, v[u]);
+        }
+    }
     for (; c + 96 < qe; c += 128) {
         uint4 a = ld_stream(src + c), b = ld_stream(src + c + 32), d = ld_stream(src + c + 64), e = ld_stream(src + c + 96);
         st_stream(dst + c, a); st_stream(dst + c + 32, b); st_stream(dst + c + 64, d); st_stream(dst + c + 96, e);
@@ -153,7 +163,8 @@ constexpr int PROP_SMEM_FLIPS = 384;   // flips of one offspring staged in share
 // dynamic shared memory: uint64 xo_off[2*n_chr+1] | uint32 flips[PROP_SMEM_FLIPS] | uint8 start[2*n_chr]
 static inline size_t prop_smem_bytes(int n_chr) { return (size_t)(2 * n_chr + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((2 * n_chr + 15) & ~15); }
 
-__global__ void __launch_bounds__(PROP_THREADS, 6)
+template <int DEPTH>
+__global__ void __launch_bounds__(PROP_THREADS, DEPTH == 8 ? 3 : 6)
 propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, uint32_t *__restrict__ off_rows,
                       const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                       const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips,
@@ -207,8 +218,8 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
             while (q < q1) {
                 const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
                 const uint32_t qb = f >> 7;
-                if (j >= k || qb >= q1) { warp_copy_chunks(dst, cur ? h1 : h0, q, q1, lane); break; }
-                warp_copy_chunks(dst, cur ? h1 : h0, q, qb, lane);
+                if (j >= k || qb >= q1) { warp_copy_chunks<DEPTH>(dst, cur ? h1 : h0, q, q1, lane); break; }
+                warp_copy_chunks<DEPTH>(dst, cur ? h1 : h0, q, qb, lane);
                 // chunk qb holds one or more flips: merge both parental chunks under a 128-bit mask
                 // (mask bit = 1 -> haplotype 1).  A flip on the chunk's first locus gives bit offset 0.
                 if (lane == 0) {
@@ -233,6 +244,206 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same propagation with TMA-staged copies (cp.async.bulk, 1-D): every run between two crossovers is a
+// contiguous 16-byte-aligned range of one parental row, so it moves global -> shared -> global as bulk copies of
+// up to PROP_PIECE bytes issued by ONE thread per warp, completion tracked by an mbarrier per ring slot (loads)
+// and by bulk async-groups (stores).  The data never passes through registers: a CTA needs 4 driver threads, almost
+// no registers and no issue slots, so the control-stream kernels of the next generation co-reside on the SMs
+// instead of displacing copy warps, and bytes in flight per SM are set by the shared-memory ring, not by occupancy.
+// The one chunk that holds a crossover is still mask-merged with plain vector loads/stores by the driver thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int TMA_WARPS = 4;                 // driver warps (rings) per CTA
+constexpr int TMA_SLOTS = 8;                 // ring slots per warp
+constexpr int TMA_LOOKAHEAD = 6;             // loads in flight ahead of the store cursor (<= TMA_SLOTS - 2)
+constexpr uint32_t PROP_PIECE = 2048;        // bytes per bulk copy (128 chunks; the mean run between crossovers is ~2 KB)
+constexpr int TMA_MERGE_THREADS = 128;       // threads that mask-merge the crossover chunks while the drivers copy
+
+static inline size_t prop_tma_smem_bytes(int n_chr) {
+    size_t meta = (size_t)(2 * n_chr + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((2 * n_chr + 15) & ~15);
+    meta = (meta + 127) & ~(size_t)127;
+    return meta + (size_t)TMA_WARPS * TMA_SLOTS * PROP_PIECE + 128;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+struct TmaRing {  // one per driver thread
+    unsigned char *buf;      // TMA_SLOTS * PROP_PIECE bytes of shared memory
+    uint64_t *bar;           // TMA_SLOTS mbarriers
+    unsigned char *dst[TMA_SLOTS];
+    uint32_t bytes[TMA_SLOTS];
+    uint32_t n_issued, n_stored;
+    uint64_t policy;
+    __device__ __forceinline__ void store_oldest() {
+        const uint32_t sl = n_stored % TMA_SLOTS;
+        mbar_wait(bar + sl, (n_stored / TMA_SLOTS) & 1u);
+        tma_store_1d(dst[sl], buf + (size_t)sl * PROP_PIECE, bytes[sl], policy);
+        n_stored++;
+    }
+    // queue the copy of nbytes (multiple of 16, <= PROP_PIECE) from gsrc to gdst
+    __device__ __forceinline__ void copy(const void *gsrc, void *gdst, uint32_t nbytes) {
+        const uint32_t sl = n_issued % TMA_SLOTS;
+        // slot sl was last used by piece n_issued - TMA_SLOTS, whose store is at least two groups back
+        if (n_issued >= TMA_SLOTS) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TMA_SLOTS - TMA_LOOKAHEAD - 1) : "memory");
+        dst[sl] = static_cast<unsigned char *>(gdst);
+        bytes[sl] = nbytes;
+        mbar_expect_tx(bar + sl, nbytes);
+        tma_load_1d(buf + (size_t)sl * PROP_PIECE, gsrc, nbytes, bar + sl);
+        n_issued++;
+        if (n_issued - n_stored > TMA_LOOKAHEAD) store_oldest();
+    }
+    __device__ __forceinline__ void drain() {
+        while (n_stored < n_issued) store_oldest();
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+};
+
+__device__ __forceinline__ void tma_copy_run(TmaRing &r, const uint4 *src, uint4 *dst, uint32_t q, uint32_t qe) {
+    while (q < qe) {
+        const uint32_t nq = min(qe - q, PROP_PIECE / 16u);
+        r.copy(src + q, dst + q, nq * 16u);
+        q += nq;
+    }
+}
+
+__global__ void __launch_bounds__(TMA_WARPS * 32 + TMA_MERGE_THREADS)
+propagate_bits_tma_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, uint32_t *__restrict__ off_rows,
+                          const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+                          const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips,
+                          const uint8_t *__restrict__ start_hap, uint64_t off_first, uint32_t n_off) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_next;
+    __shared__ __align__(8) uint64_t s_bar[TMA_WARPS][TMA_SLOTS];
+    const int n_ls = 2 * g.n_chr;
+    uint64_t *s_off = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_fl = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(n_ls + 1) * 8);
+    uint8_t *s_start = smem_raw + (size_t)(n_ls + 1) * 8 + PROP_SMEM_FLIPS * 4;
+    size_t meta = (size_t)(n_ls + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((n_ls + 15) & ~15);
+    meta = (meta + 127) & ~(size_t)127;
+    unsigned char *ring0 = smem_raw + meta;
+    ring0 += (128 - (smem_u32(ring0) & 127u)) & 127u;   // 128-byte aligned ring buffers
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TmaRing ring;
+    ring.buf = ring0 + (size_t)(warp % TMA_WARPS) * TMA_SLOTS * PROP_PIECE;
+    ring.bar = s_bar[warp % TMA_WARPS];
+    ring.n_issued = ring.n_stored = 0;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(ring.policy));
+    if (lane == 0 && warp < TMA_WARPS) {
+        for (int sl = 0; sl < TMA_SLOTS; sl++) mbar_init(ring.bar + sl, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (uint32_t oi = blockIdx.x; oi < n_off; oi += gridDim.x) {
+        const uint64_t i = off_first + oi;
+        const uint64_t slot0 = i * (uint64_t)n_ls;
+        __syncthreads();
+        for (int t = threadIdx.x; t <= n_ls; t += blockDim.x) s_off[t] = xo_off[slot0 + t];
+        for (int t = threadIdx.x; t < n_ls; t += blockDim.x) s_start[t] = start_hap[slot0 + t];
+        if (threadIdx.x == 0) s_next = 0;
+        __syncthreads();
+        const uint64_t e_base = s_off[0];
+        const uint32_t n_fl = (uint32_t)(s_off[n_ls] - e_base);
+        const bool staged = n_fl <= PROP_SMEM_FLIPS;
+        if (staged) for (uint32_t t = threadIdx.x; t < n_fl; t += blockDim.x) s_fl[t] = flips[e_base + t];
+        const uint32_t pf = father[i], pm = mother[i];
+        __syncthreads();
+        if (warp >= TMA_WARPS) {
+            // merge threads: every chunk that holds a crossover is a mask-merge of both parental chunks (mask bit = 1 ->
+            // haplotype 1); thread t takes flip t of the offspring when it is the first flip of its chunk
+            for (uint32_t t = threadIdx.x - TMA_WARPS * 32; t < n_fl; t += TMA_MERGE_THREADS) {
+                const uint64_t e = e_base + t;
+                int lo = 0, hi = n_ls - 1;  // slot with s_off[ls] <= e < s_off[ls+1]
+                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid - 1; }
+                const int ls = lo;
+                const uint32_t *fl = staged ? s_fl + (s_off[ls] - e_base) : flips + s_off[ls];
+                const uint32_t jj = (uint32_t)(e - s_off[ls]), k = (uint32_t)(s_off[ls + 1] - s_off[ls]);
+                const uint32_t qb = fl[jj] >> 7;
+                if (jj > 0 && (fl[jj - 1] >> 7) == qb) continue;
+                const uint32_t c = (uint32_t)ls >> 1;
+                const int gam = ls & 1;
+                const uint32_t nq = ((g.chr_nloci[c] + 31) / 32 + 3) / 4;
+                if (qb >= nq) continue;   // a crossover beyond the last locus only sets the parity of nothing
+                const uint32_t woff = g.chr_word_off[c];
+                const uint32_t prow = gam ? pm : pf;
+                const uint4 *h0 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow) * g.W + woff);
+                const uint4 *h1 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow + 1) * g.W + woff);
+                uint4 *dst = reinterpret_cast<uint4 *>(off_rows + (uint64_t)(2 * i + gam) * g.W + woff);
+                const uint4 a = ld_stream(h0 + qb), b = ld_stream(h1 + qb);
+                const uint32_t fill = ((s_start[ls] ^ jj) & 1u) ? 0xFFFFFFFFu : 0u;
+                uint32_t m0 = fill, m1 = fill, m2 = fill, m3 = fill;
+                const uint32_t base = qb << 7;
+                for (uint32_t j2 = jj; j2 < k && fl[j2] < base + 128u; j2++) {
+                    const uint32_t r = fl[j2] - base;
+                    m0 ^= r < 32u ? 0xFFFFFFFFu << r : 0u;
+                    m1 ^= r <= 32u ? 0xFFFFFFFFu : (r < 64u ? 0xFFFFFFFFu << (r - 32u) : 0u);
+                    m2 ^= r <= 64u ? 0xFFFFFFFFu : (r < 96u ? 0xFFFFFFFFu << (r - 64u) : 0u);
+                    m3 ^= r <= 96u ? 0xFFFFFFFFu : 0xFFFFFFFFu << (r - 96u);
+                }
+                uint4 o;
+                o.x = (a.x & ~m0) | (b.x & m0); o.y = (a.y & ~m1) | (b.y & m1);
+                o.z = (a.z & ~m2) | (b.z & m2); o.w = (a.w & ~m3) | (b.w & m3);
+                st_stream(dst + qb, o);
+            }
+            continue;
+        }
+        if (lane != 0) continue;  // one driver thread per copy warp
+        for (;;) {
+            const uint32_t item = atomicAdd(&s_next, 1u);
+            if (item >= 2 * tt.n_items) break;
+            const int gam = item >= tt.n_items;
+            const uint32_t it = gam ? item - tt.n_items : item;
+            const uint32_t c = tt.chr[it], q0 = tt.chunk0[it], q1 = q0 + tt.nchunk[it];
+            const int ls = (int)c * 2 + gam;
+            const uint64_t e0 = s_off[ls];
+            const uint32_t k = (uint32_t)(s_off[ls + 1] - e0);
+            const uint32_t *fl = staged ? s_fl + (e0 - e_base) : flips + e0;
+            const uint32_t woff = g.chr_word_off[c];
+            const uint32_t prow = gam ? pm : pf;
+            const uint4 *h0 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow) * g.W + woff);
+            const uint4 *h1 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow + 1) * g.W + woff);
+            uint4 *dst = reinterpret_cast<uint4 *>(off_rows + (uint64_t)(2 * i + gam) * g.W + woff);
+            uint32_t j = 0;
+            const uint32_t x0 = q0 << 7;
+            while (j < k && fl[j] <= x0) j++;
+            uint32_t cur = (s_start[ls] ^ j) & 1u;
+            uint32_t q = q0;
+            while (q < q1) {   // whole runs between crossover chunks go through the TMA ring
+                const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
+                const uint32_t qb = f >> 7;
+                if (j >= k || qb >= q1) { tma_copy_run(ring, cur ? h1 : h0, dst, q, q1); break; }
+                tma_copy_run(ring, cur ? h1 : h0, dst, q, qb);
+                while (j < k && fl[j] < ((qb + 1) << 7)) { j++; cur ^= 1u; }
+                q = qb + 1;
+            }
+        }
+    }
+    if (lane == 0 && warp < TMA_WARPS) ring.drain();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -339,8 +550,7 @@ __global__ void cv_propagate_bits_kernel(CvSet cs, const uint32_t *__restrict__ 
                                          const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                                          const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
                                          const uint8_t *__restrict__ start_hap, uint64_t off_first, uint64_t n_off) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_off * 2 * cs.Wcv) return;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_off * 2 * cs.Wcv; t += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t w = (uint32_t)(t % cs.Wcv);
     uint64_t row = t / cs.Wcv;
     uint64_t i = off_first + (row >> 1);
@@ -368,6 +578,7 @@ __global__ void cv_propagate_bits_kernel(CvSet cs, const uint32_t *__restrict__ 
         v = (pr[0] & ~mask) | (pr[cs.Wcv] & mask);
     }
     off_bits[(i * 2 + gam) * (uint64_t)cs.Wcv + w] = v;
+    }
 }
 
 // root-population plane (only with more than one population): one thread per (offspring gamete row, CV)
@@ -485,27 +696,28 @@ __global__ void cv_tables_kernel(CvSet cs, const unsigned long long *__restrict_
 }
 __global__ void genetic_value_lut_kernel(CvSet cs, const uint32_t *__restrict__ bits, const double *__restrict__ LA, const double *__restrict__ LD,
                                          uint64_t n, double *__restrict__ A, double *__restrict__ D, double *__restrict__ Gv, int *__restrict__ nan_flag) {
-    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (wid >= n * cs.n_phen) return;
-    uint64_t i = wid % n;
-    int f = (int)(wid / n);
-    const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
-    double Ac = 0, Dc = 0;
-    for (int c = 0; c < cs.n_chr; c++) {
-        const int blk = f * cs.n_chr + c;
-        const uint32_t b0 = cs.block_off[blk], b1 = cs.block_off[blk + 1], wo = cs.word_off[blk];
-        for (uint32_t k = b0 + lane; k < b1; k += 32) {
-            const uint32_t j = k - b0;
-            const unsigned t = ((al0[wo + (j >> 5)] >> (j & 31)) & 1u) + ((al1[wo + (j >> 5)] >> (j & 31)) & 1u);
-            Ac += LA[k * 3 + t];
-            Dc += LD[k * 3 + t];
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < n * cs.n_phen; wid += n_warps) {
+        uint64_t i = wid % n;
+        int f = (int)(wid / n);
+        const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
+        double Ac = 0, Dc = 0;
+        for (int c = 0; c < cs.n_chr; c++) {
+            const int blk = f * cs.n_chr + c;
+            const uint32_t b0 = cs.block_off[blk], b1 = cs.block_off[blk + 1], wo = cs.word_off[blk];
+            for (uint32_t k = b0 + lane; k < b1; k += 32) {
+                const uint32_t j = k - b0;
+                const unsigned t = ((al0[wo + (j >> 5)] >> (j & 31)) & 1u) + ((al1[wo + (j >> 5)] >> (j & 31)) & 1u);
+                Ac += LA[k * 3 + t];
+                Dc += LD[k * 3 + t];
+            }
         }
-    }
-    for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
-    if (lane == 0) {
-        A[(uint64_t)f * n + i] = Ac; D[(uint64_t)f * n + i] = Dc; Gv[(uint64_t)f * n + i] = Ac + Dc;
-        if (isnan(Ac) || isnan(Dc)) *nan_flag = 1;
+        for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
+        if (lane == 0) {
+            A[(uint64_t)f * n + i] = Ac; D[(uint64_t)f * n + i] = Dc; Gv[(uint64_t)f * n + i] = Ac + Dc;
+            if (isnan(Ac) || isnan(Dc)) *nan_flag = 1;
+        }
     }
 }
 
@@ -723,8 +935,7 @@ template <bool FILL>
 __global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int gen, uint64_t slot_first, uint64_t n_slots,
                                  uint32_t *__restrict__ count, const uint64_t *__restrict__ xo_off, uint32_t *__restrict__ xo_bp,
                                  uint8_t *__restrict__ start_hap, uint32_t *__restrict__ stash = nullptr) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_slots) return;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_slots; t += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t slot = slot_first + t;
     uint64_t i = (slot >> 1) / (uint64_t)n_chr;
     int c = (int)((slot >> 1) % (uint64_t)n_chr), gam = (int)(slot & 1);
@@ -747,15 +958,15 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int ge
         j = (uint32_t)k + 1;
     }
     if (!FILL) count[slot] = n;
+    }
 }
 // stash -> CSR (+ locus indices of the flips when the bit-packed rows are kept); slots longer than the stash re-draw
 __global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int pop, int gen, uint64_t n_slots, const uint64_t *__restrict__ xo_off,
                                 const uint32_t *__restrict__ stash, uint32_t *__restrict__ xo_bp, uint32_t *__restrict__ flips) {
-    uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_slots) return;
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t o = xo_off[slot];
     const uint32_t cnt = (uint32_t)(xo_off[slot + 1] - o);
-    if (cnt == 0) return;
+    if (cnt == 0) continue;
     const int c = (int)((slot >> 1) % (uint64_t)n_chr);
     if (cnt <= XO_STASH) {
         for (uint32_t q = 0; q < cnt; q++) {
@@ -763,7 +974,7 @@ __global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int po
             xo_bp[o + q] = x;
             if (flips) flips[o + q] = locus_lower_bound(g, c, x);
         }
-        return;
+        continue;
     }
     const uint64_t i = (slot >> 1) / (uint64_t)n_chr;
     const int gam = (int)(slot & 1);
@@ -782,6 +993,7 @@ __global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int po
         if (flips) flips[o + n] = locus_lower_bound(g, c, x);
         n++;
         j = (uint32_t)k + 1;
+    }
     }
 }
 
