@@ -225,6 +225,8 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     for (PopDev &P : c->pop) for (DrawSet &D : P.ds) cudaEventCreateWithFlags(&D.bulk_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    for (SortLane &l : c->lane) { cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, prio_hi); cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming); }
     cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     if (c->ensure(c->flags, 64) != GE_OK) { delete c; return GE_ERR_CUDA; }
     cudaMemsetAsync(c->flags.p, 0, 64, c->stream);
@@ -237,6 +239,7 @@ int ge_destroy(ge_ctx *ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->bulk);
     cudaStreamSynchronize(ctx->stream);
+    for (SortLane &l : ctx->lane) cudaStreamSynchronize(l.s);
     auto freeb = [&](Buf &b) { ctx->release(b); };
     for (PopDev &P : ctx->pop) {
         for (Buf *b : {&P.d_row_off, &P.d_bp, &P.d_T, &P.d_bp_dist, &P.d_mrow_off, &P.d_mbp, &P.d_mT, &P.d_cov_lo, &P.d_cov_hi, &P.d_omega,
@@ -259,6 +262,11 @@ int ge_destroy(ge_ctx *ctx) {
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_join);
     for (auto &e : ctx->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (SortLane &l : ctx->lane) {
+        for (Buf *b : {&l.keys_in, &l.keys_out, &l.vals_out, &l.tmp}) freeb(*b);
+        cudaEventDestroy(l.done); cudaStreamDestroy(l.s);
+    }
+    cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->bulk);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -38,6 +38,15 @@ struct SegState {   // founder segments of one generation (GE_REP_SEGMENTS): CSR
     uint64_t n_seg = 0;
     bool valid = false;
 };
+// The four sorts of assortative mating (males and females by mating value, the two template columns) are independent
+// and, at <= N/2 keys each, pure launch latency (8 radix passes of ~10 us): they run side by side on four lanes.
+struct SortLane {
+    cudaStream_t s = nullptr;
+    cudaEvent_t done = nullptr;
+    Buf keys_in, keys_out, vals_out, tmp;
+};
+constexpr int N_SORT_LANES = 4;
+
 struct MateScratch {  // scratch of the mating kernels (ge_mating.cuh)
     Buf fam_off, keep, keys_a, keys_b, idx_a, idx_b, list_m, list_f, t1, t2, rank1, rank2, tmp_sort, counters, mv_m, mv_f;
 };
@@ -110,7 +119,17 @@ struct ge_ctx {
     ge_config cfg;
     cudaStream_t stream = nullptr;  // control stream (high priority): mating, sampling, CV planes, phenotypes
     cudaStream_t bulk = nullptr;    // bulk stream (low priority): bit-packed haplotype propagation, one generation behind at most
-    cudaEvent_t ev_ready = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_join = nullptr, ev_fork = nullptr;
+    SortLane lane[N_SORT_LANES];
+    int fork_lanes() {  // the lanes start after everything queued on the control stream so far
+        CUDA_TRY(cudaEventRecord(ev_fork, stream));
+        for (SortLane &l : lane) CUDA_TRY(cudaStreamWaitEvent(l.s, ev_fork, 0));
+        return GE_OK;
+    }
+    int join_lanes() {  // the control stream continues after every lane
+        for (SortLane &l : lane) { CUDA_TRY(cudaEventRecord(l.done, l.s)); CUDA_TRY(cudaStreamWaitEvent(stream, l.done, 0)); }
+        return GE_OK;
+    }
     bool serial = false;
     int thin = 8;   // CTAs per SM the heavy control-stream kernels may take while a bulk copy is in flight (0 = no limit)
     bool bulk_busy = false;

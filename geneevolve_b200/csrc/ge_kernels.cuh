@@ -753,13 +753,12 @@ __global__ void moment_partial_kernel(const double *__restrict__ x, uint64_t n, 
     s = block_reduce_sum(s);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
-// out[0] = (sum of partials) / denom  — fixed order, one thread
+// out[0] = (sum of partials) / denom  — one warp, fixed order: lane l adds partials l, l+32, ..., then a shuffle tree
 __global__ void moment_final_kernel(const double *__restrict__ partial, int n_partial, double denom, double *__restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0;
-        for (int i = 0; i < n_partial; i++) s += partial[i];
-        *out = denom > 0 ? s / denom : 0.0;
-    }
+    double s = 0;
+    for (int i = threadIdx.x; i < n_partial; i += 32) s += partial[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = denom > 0 ? s / denom : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------

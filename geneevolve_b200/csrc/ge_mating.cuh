@@ -148,14 +148,17 @@ static void mate_release(MateScratch &m) {
 }
 
 // stable sort of (uint64 key, uint32 value) pairs: keys_in/vals_in -> keys_out/vals_out
-static int sort_pairs(ge_ctx *ctx, MateScratch &M, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n) {
+static int sort_pairs_on(ge_ctx *ctx, cudaStream_t st, Buf &tmp, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n) {
     if (n == 0) return GE_OK;
     size_t bytes = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 64, ctx->stream));
-    GE_TRY(ctx->ensure(M.tmp_sort, bytes));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(M.tmp_sort.p, bytes, kin, kout, vin, vout, (int)n, 0, 64, ctx->stream));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 64, st));
+    GE_TRY(ctx->ensure(tmp, bytes));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, 64, st));
     ctx->launches += 8;  // radix passes of the library sort (approximate, only for the launch counter)
     return GE_OK;
+}
+static int sort_pairs(ge_ctx *ctx, MateScratch &M, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n) {
+    return sort_pairs_on(ctx, ctx->stream, M.tmp_sort, kin, kout, vin, vout, n);
 }
 
 // thinning + compaction of one sex list; returns list length on the host
@@ -169,8 +172,12 @@ static int thin_lists(ge_ctx *ctx, int pop, int gen, bool with_mm, uint64_t *n_m
     GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8));  // offsets
     thin_count_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->rng, pop, gen, n, S.sex.as<uint8_t>(), S.svf.as<double>(), with_mm, P.MM, M.keep.as<uint32_t>(), M.rank1.as<uint32_t>());
     GE_TRY(ctx->check_launch("thin_count"));
-    GE_TRY(ctx->exclusive_scan(M.keep.as<uint32_t>(), n, M.keys_a.as<uint64_t>(), n_m));
-    GE_TRY(ctx->exclusive_scan(M.rank1.as<uint32_t>(), n, M.keys_b.as<uint64_t>(), n_f));
+    GE_TRY(ctx->exclusive_scan(M.keep.as<uint32_t>(), n, M.keys_a.as<uint64_t>(), nullptr));
+    GE_TRY(ctx->exclusive_scan(M.rank1.as<uint32_t>(), n, M.keys_b.as<uint64_t>(), nullptr));
+    // both list lengths (the totals sit at out[n]) in one host read-back
+    CUDA_TRY(cudaMemcpyAsync(n_m, M.keys_a.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(n_f, M.keys_b.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     GE_TRY(ctx->ensure(M.list_m, std::max<uint64_t>(*n_m, 1) * 4)); GE_TRY(ctx->ensure(M.list_f, std::max<uint64_t>(*n_f, 1) * 4));
     thin_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, M.keys_a.as<uint64_t>(), M.list_m.as<uint32_t>());
     GE_TRY(ctx->check_launch("thin_fill"));
@@ -205,17 +212,23 @@ static int trim_list(ge_ctx *ctx, int pop, int gen, Buf &list, uint64_t n, uint6
     return GE_OK;
 }
 
-// sort a list of individuals by mating value, ascending, stable (:2251-2252)
-static int sort_by_mv(ge_ctx *ctx, int pop, Buf &list, uint64_t n) {
+// sort a list of individuals by mating value, ascending, stable (:2251-2252), on one sort lane
+static int sort_by_mv(ge_ctx *ctx, int pop, Buf &list, uint64_t n, SortLane &L) {
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
-    MateScratch &M = P.mate;
-    GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8)); GE_TRY(ctx->ensure(M.idx_a, n * 4));
-    mv_keys_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, list.as<uint32_t>(), S.mv.as<double>(), M.keys_a.as<uint64_t>());
+    GE_TRY(ctx->ensure(L.keys_in, (n + 1) * 8)); GE_TRY(ctx->ensure(L.keys_out, (n + 1) * 8)); GE_TRY(ctx->ensure(L.vals_out, (n + 1) * 4));
+    mv_keys_kernel<<<nblk(n, 256), 256, 0, L.s>>>(n, list.as<uint32_t>(), S.mv.as<double>(), L.keys_in.as<uint64_t>());
     GE_TRY(ctx->check_launch("mv_keys"));
-    GE_TRY(sort_pairs(ctx, M, M.keys_a.as<uint64_t>(), M.keys_b.as<uint64_t>(), list.as<uint32_t>(), M.idx_a.as<uint32_t>(), n));
-    CUDA_TRY(cudaMemcpyAsync(list.p, M.idx_a.p, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    GE_TRY(sort_pairs_on(ctx, L.s, L.tmp, L.keys_in.as<uint64_t>(), L.keys_out.as<uint64_t>(), list.as<uint32_t>(), L.vals_out.as<uint32_t>(), n));
+    CUDA_TRY(cudaMemcpyAsync(list.p, L.vals_out.p, n * 4, cudaMemcpyDeviceToDevice, L.s));
     return GE_OK;
+}
+// rank of every template value of one column: sort (key, index) and scatter the positions
+static int rank_column(ge_ctx *ctx, const uint64_t *keys, const uint32_t *idx, uint32_t *rank, uint64_t n, SortLane &L) {
+    GE_TRY(ctx->ensure(L.keys_out, (n + 1) * 8)); GE_TRY(ctx->ensure(L.vals_out, (n + 1) * 4));
+    GE_TRY(sort_pairs_on(ctx, L.s, L.tmp, keys, L.keys_out.as<uint64_t>(), idx, L.vals_out.as<uint32_t>(), n));
+    rank_scatter_kernel<<<nblk(n, 256), 256, 0, L.s>>>(n, L.vals_out.as<uint32_t>(), rank);
+    return ctx->check_launch("rank_scatter");
 }
 
 static int mate_philox(ge_ctx *ctx, int pop, int gen, const ge_gen_params &gp) {
@@ -241,20 +254,18 @@ static int mate_philox(ge_ctx *ctx, int pop, int gen, const ge_gen_params &gp) {
     if (n2 == 0) return fail(GE_ERR_NO_MATES, "Error: couples=0, num_males_mate=" + std::to_string(n_m) + ", num_females_mate=" + std::to_string(n_f));
     if (n_m > n_f) GE_TRY(trim_list(ctx, pop, gen, M.list_m, n_m, n_m - n_f, 0));
     else if (n_f > n_m) GE_TRY(trim_list(ctx, pop, gen, M.list_f, n_f, n_f - n_m, 1));
-    GE_TRY(sort_by_mv(ctx, pop, M.list_m, n2));
-    GE_TRY(sort_by_mv(ctx, pop, M.list_f, n2));
-    // template ranks
+    // template values first, then the four independent sorts side by side on the sort lanes
     GE_TRY(ctx->ensure(M.t1, n2 * 8)); GE_TRY(ctx->ensure(M.t2, n2 * 8)); GE_TRY(ctx->ensure(M.idx_a, n2 * 4)); GE_TRY(ctx->ensure(M.idx_b, n2 * 4));
     GE_TRY(ctx->ensure(M.keys_b, (n2 + 1) * 8)); GE_TRY(ctx->ensure(M.rank1, (n2 + 1) * 4)); GE_TRY(ctx->ensure(M.rank2, (n2 + 1) * 4));
     double rho = gp.mat_cor, u11 = std::sqrt(1.0 - rho * rho);
     template_kernel<<<nblk(n2, 256), 256, 0, st>>>(ctx->rng, pop, gen, n2, rho, u11, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>());
     GE_TRY(ctx->check_launch("template"));
-    GE_TRY(sort_pairs(ctx, M, M.t1.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2));
-    rank_scatter_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, M.idx_b.as<uint32_t>(), M.rank1.as<uint32_t>());
-    GE_TRY(ctx->check_launch("rank_scatter"));
-    GE_TRY(sort_pairs(ctx, M, M.t2.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2));
-    rank_scatter_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, M.idx_b.as<uint32_t>(), M.rank2.as<uint32_t>());
-    GE_TRY(ctx->check_launch("rank_scatter"));
+    GE_TRY(ctx->fork_lanes());
+    GE_TRY(sort_by_mv(ctx, pop, M.list_m, n2, ctx->lane[0]));
+    GE_TRY(sort_by_mv(ctx, pop, M.list_f, n2, ctx->lane[1]));
+    GE_TRY(rank_column(ctx, M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.rank1.as<uint32_t>(), n2, ctx->lane[2]));
+    GE_TRY(rank_column(ctx, M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.rank2.as<uint32_t>(), n2, ctx->lane[3]));
+    GE_TRY(ctx->join_lanes());
     GE_TRY(ensure_couples(ctx, P, n2));
     GE_TRY(ctx->ensure(M.keep, (n2 + 1) * 4)); GE_TRY(ctx->ensure(M.keys_a, (n2 + 1) * 8));
     pair_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>(), M.rank1.as<uint32_t>(), M.rank2.as<uint32_t>(), S.ids.as<uint64_t>(),

@@ -38,9 +38,13 @@ def cuda_allreduce_hook(device, group=None):
     import torch
     import torch.distributed as dist
 
+    cache = {}
+
     def hook(ptr, count, stream):
-        t = torch.as_tensor(_DevPtr(ptr, count), device=f"cuda:{device}")
-        ext = torch.cuda.ExternalStream(stream, device=device)
+        key = (ptr, count, stream)
+        if key not in cache:  # the library reuses one scratch buffer and one stream: wrap them once
+            cache[key] = (torch.as_tensor(_DevPtr(ptr, count), device=f"cuda:{device}"), torch.cuda.ExternalStream(stream, device=device))
+        t, ext = cache[key]
         with torch.cuda.stream(ext):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return hook

@@ -1,0 +1,25 @@
+"""Timing aid: runs ONE rank's share of a chromosome-sharded config-3 job on a single GPU (the all-reduce hook is a
+no-op, so values are wrong but the kernel work, launches and host read-backs are those of that rank)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from geneevolve_b200 import capi, workloads, dist as gdist
+
+world, steps = int(sys.argv[1]), int(sys.argv[2])
+cfg = workloads.make_workload("config3_100k_x_1M")
+mine = gdist.assign_chromosomes(cfg["n_loci"], world)[0]
+N = cfg["n"]
+eng = capi.Engine(n_pop=1, n_chr=len(mine), n_phen=1, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX, seed=12345,
+                  capacity=int(N * 1.03) + 1024, rank=0, world_size=world)
+workloads.configure_engine(eng, cfg, chrs_local=mine)
+eng.set_allreduce(lambda ptr, count, stream: None)
+eng.init_generation0()
+gp = [capi.gen_params(N, cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
+for g in range(1, 4):
+    eng.step_generation(g, gp)
+eng.set_profiling(True); eng.reset_kernel_times(); eng.synchronize()
+t0 = time.perf_counter(); eng.timer_start()
+for g in range(4, 4 + steps):
+    eng.step_generation(g, gp)
+ms = eng.timer_stop(); wall = (time.perf_counter() - t0) * 1e3
+k_ms, k_n, _ = eng.kernel_time(capi.GE_KERNEL_PROPAGATE_BITS)
+print(f"world {world}: chromosomes {mine}: {ms / steps:.3f} ms/step (host wall {wall / steps:.3f}), propagate {k_ms / max(k_n, 1):.3f} ms, launches/step {eng.launch_count() / steps:.0f}")
