@@ -179,8 +179,15 @@ def ours(args):
     cfg = workloads.make_workload(args.workload, n_override=args.n, loci_override=args.loci)
     M, N = sum(cfg["n_loci"]), cfg["n"]
     cap = int(max(N, cfg["founders"]) * 1.03) + 1024
-    eng = capi.Engine(n_pop=1, n_chr=len(cfg["chrs"]), n_phen=1, device=local, representation=capi.GE_REP_BITS,
+    segs = bool(cfg.get("segments"))
+    seg_cap = 0
+    if segs:  # parts per haplotype-genome after g generations ~ n_chr + g * (map length in Morgans); both arms run back to back
+        morgans = sum(float(p.sum()) for _, _, p in cfg["maps"])
+        seg_cap = int(2 * cap * (len(cfg["chrs"]) + (args.warmup + 2 * args.steps + 1) * morgans) * 1.05)
+    eng = capi.Engine(seg_capacity=seg_cap, n_pop=1, n_chr=len(cfg["chrs"]), n_phen=1, device=local, representation=capi.GE_REP_SEGMENTS if segs else capi.GE_REP_BITS,
                       rng_mode=capi.GE_RNG_PHILOX, seed=12345, capacity=cap)
+    kid = capi.GE_KERNEL_RECOMBINE_SEGMENTS if segs else capi.GE_KERNEL_PROPAGATE_BITS
+    kname = "seg_recombine_kernel (count + fill)" if segs else "propagate_bits_kernel"
     workloads.configure_engine(eng, cfg)
     eng.init_generation0()
     gp = [capi.gen_params(N, cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
@@ -209,7 +216,7 @@ def ours(args):
             work += eng.population_size(0) * M
         ms_dev = eng.timer_stop()
     launches = eng.launch_count()
-    k_ms, k_n, k_bytes = eng.kernel_time(capi.GE_KERNEL_PROPAGATE_BITS)
+    k_ms, k_n, k_bytes = eng.kernel_time(kid)
     eng.set_profiling(False)
     value = work / (ms_dev * 1e-3)
 
@@ -235,7 +242,7 @@ def ours(args):
     achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not segs and args.workload == "config3_100k_x_1M" and not args.n and not args.loci:
         traffic = json.load(open(tpath)).get("propagate_bits_dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -244,14 +251,17 @@ def ours(args):
         "config": {"workload": args.workload, "individuals": N, "loci": M, "chromosomes": len(cfg["chrs"]), "founders": cfg["founders"],
                    "causal_variants": sum(len(c["bp"]) for c in cfg["cvs"]), "mating": "random" if cfg["rm"] else "assortative rho=%.1f" % cfg["mat_cor"],
                    "selection": "logit(0,1)", "h2": 0.5, "rng": "philox4x32-10 on device",
-                   "l2": "inputs larger than L2 (%.1f GB of parental rows per step vs 126 MB)" % (N * M / 4 / 1e9),
+                   "l2": ("inputs larger than L2 (%.1f GB of parental rows per step vs 126 MB)" % (N * M / 4 / 1e9)) if not segs else
+                         "inputs larger than L2 (founder-segment lists, %.1f GB written per step)" % (k_bytes / max(k_n, 1) / 2e9),
+                   "representation": "founder segments (loci nominal; cost grows with the generation: steps are generations %d..%d)" % (args.warmup + 1, args.warmup + args.steps)
+                   if segs else "bit-packed haplotypes",
                    "device_memory_gb": eng.device_memory_bytes() / 1e9},
         "e2e": {"value": work2 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40, "d2h_bytes_per_step": d2h // args.steps,
                 "ms_per_step": ms_e2e / args.steps, "checksum": checksum,
                 "note": "generation state stays in HBM between steps by design (as it stays in process memory in the reference); per step the host sends the "
                         "generation-table row and receives every individual's .info columns in pinned memory"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "propagate_bits_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms_dev,
                      "algorithmic_bytes_per_launch": k_bytes // max(k_n, 1)},

@@ -341,6 +341,9 @@ class Engine:
         self._call("download_cv_alleles", self.ctx, pop, phen, chr_, _ptr(out, _u8p))
         return out
 
+    def recompute_cv_from_segments(self, pop):
+        self._call("recompute_cv_from_segments", self.ctx, pop)
+
     def draws(self, pop):
         no, nx, nm = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._call("get_draw_counts", self.ctx, pop, C.byref(no), C.byref(nx), C.byref(nm))

@@ -219,6 +219,9 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo);
     c->serial = std::getenv("GE_SERIAL") != nullptr;
     if (const char *t = std::getenv("GE_THIN")) c->thin = std::atoi(t);
+    c->cv_from_segments = std::getenv("GE_CV_FROM_SEGMENTS") != nullptr;
+    c->seg_per_thread = std::getenv("GE_SEG_PER_THREAD") != nullptr;
+    if (const char *t = std::getenv("GE_SEG_GROUP")) c->seg_group = std::atoi(t);
     if (const char *t = std::getenv("GE_PROP_DEPTH")) c->prop_depth = std::atoi(t);
     if (const char *t = std::getenv("GE_PROP")) c->use_tma = std::string(t) == "tma";
     if (const char *t = std::getenv("GE_THIN_MIN_GB")) c->thin_min_bytes = std::atof(t) * 1e9;  // measurement aid: queue the bulk kernel on the control stream (no overlap)
@@ -285,8 +288,11 @@ int ge_set_genetic_map(ge_ctx *ctx, int pop, int chr, const uint64_t *bp, const 
     // the bit-packed representation needs monotone crossover lists: row j's crossover lies in
     // [bp[j], bp[j]+bp_dist) (:2989), so rows must be at least bp_dist apart (true for the uniform b37 maps)
     for (uint64_t j = 0; j + 2 < n; j++)
-        if (bp[j + 1] < bp[j] + bp_dist && rp[j] > 0 && (ctx->cfg.representation & GE_REP_BITS))
-            return fail(GE_ERR_UNSUPPORTED, "genetic map rows closer than bp_dist_in_rmap give non-monotone crossover lists (only GE_REP_SEGMENTS follows the reference there)");
+        if (bp[j + 1] < bp[j] + bp_dist && rp[j] > 0) {
+            if (ctx->cfg.representation & GE_REP_BITS)
+                return fail(GE_ERR_UNSUPPORTED, "genetic map rows closer than bp_dist_in_rmap give non-monotone crossover lists (only GE_REP_SEGMENTS follows the reference there)");
+            ctx->seg_per_thread = true;  // segment lists may become unsorted: keep the reference's scan verbatim
+        }
     PopDev &P = ctx->pop[pop];
     P.rmap_bp[chr].assign(bp, bp + n); P.recom_prob[chr].assign(rp, rp + n); P.bp_dist[chr] = bp_dist;
     return GE_OK;
@@ -349,7 +355,7 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
     GenState &S = P.st[P.cur];
     if (S.n == 0) return fail(GE_ERR_INVALID, "empty population");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    if (ctx->segs() && !ctx->bits()) GE_TRY(seg_find_cv(ctx, pop));  // ras_find_cv on the segment lists
+    if (ctx->segs() && !ctx->bits() && ctx->cv_from_segments) GE_TRY(seg_find_cv(ctx, pop));  // ras_find_cv on the segment lists (verification mode)
     uint32_t ncv = ctx->n_cv_tot;
     if (ncv) {
         CUDA_TRY(cudaMemsetAsync(ctx->d_cv_count.p, 0, (size_t)ncv * 8, ctx->stream));
@@ -854,7 +860,7 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         bulk_launched = true;
     }
     // ---- causal-variant planes
-    if (ctx->n_cv_tot && (ctx->bits() || !ctx->segs())) {
+    if (ctx->n_cv_tot) {  // in every representation: crossover parity at the CV positions, never a rescan of the segment lists
         uint64_t tot = n_off * 2 * ctx->Wcv;
         cv_propagate_bits_kernel<<<ctx->ctrl_grid(tot, 256), 256, 0, st>>>(ctx->cvset(), par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
                                                                  D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, n_off);
@@ -1042,6 +1048,13 @@ int ge_download_cv_alleles(ge_ctx *ctx, int pop, int f, int c, uint8_t *out) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->release(tmp);
     return GE_OK;
+}
+
+int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop) {  // ras_find_cv :2752-2815 literally: scan the parts of every haplotype
+    CHECK_POP(ctx, pop);
+    if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_recompute_cv_from_segments needs GE_REP_SEGMENTS");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return seg_find_cv(ctx, pop);
 }
 
 int ge_get_draw_counts(ge_ctx *ctx, int pop, uint64_t *no, uint64_t *nx, uint64_t *nm) {

@@ -134,6 +134,9 @@ struct ge_ctx {
     int thin = 8;   // CTAs per SM the heavy control-stream kernels may take while a bulk copy is in flight (0 = no limit)
     bool bulk_busy = false;
     int prop_depth = 4;
+    int seg_group = 0;              // GE_SEG_GROUP: force 1, 8 or 32 lanes per slot in the segment recombination (0 = by list length)
+    bool seg_per_thread = false;    // a genetic map with rows closer than bp_dist_in_rmap was given, or GE_SEG_PER_THREAD is set
+    bool cv_from_segments = false;  // GE_CV_FROM_SEGMENTS: ge_compute_AD rescans the segment lists every generation like the reference
     bool use_tma = false, tma_attr_set = false;
     double thin_min_bytes = 30e9;  // bytes moved by one bulk launch above which the control kernels go thin
     // grid of a grid-stride control kernel: full width, or thin while it shares the GPU with propagate_bits_kernel,

@@ -36,56 +36,145 @@ struct SegArgs {
 // Simulation::recombine (:2903-2958), branch for branch.  One thread per offspring haplotype slot; pass 0 counts
 // the pieces, pass 1 writes them at the scanned offsets.  No merging of adjacent same-founder pieces, zero-length
 // and clipped pieces exactly as the reference emits them.
+// The reference rescans the parental list from part 0 for every interval (O(parts x crossovers)); the interval starts
+// L ascend, so one cursor per parental haplotype gives the same first part in O(parts + crossovers) — at generation
+// 100 a list holds ~160 parts.  A descending L (only possible with maps whose rows are closer than bp_dist_in_rmap)
+// resets the cursors, which restores the reference's rescan.
 template <bool FILL>
 __global__ void seg_recombine_kernel(SegArgs a, uint32_t *__restrict__ count, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_off * a.n_chr * 2) return;
-    uint64_t slot = a.off_first * a.n_chr * 2 + t;
-    uint64_t i = (slot >> 1) / (uint64_t)a.n_chr;
-    int c = (int)((slot >> 1) % (uint64_t)a.n_chr), gam = (int)(slot & 1);
-    uint32_t parent = gam ? a.mother[i] : a.father[i];
-    uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2;
-    const uint4 *H0 = a.par_seg + a.par_off[ps], *H1 = a.par_seg + a.par_off[ps + 1];
-    uint32_t n0 = (uint32_t)(a.par_off[ps + 1] - a.par_off[ps]), n1 = (uint32_t)(a.par_off[ps + 2] - a.par_off[ps + 1]);
-    uint64_t e0 = a.xo_off[slot];
-    uint32_t k = (uint32_t)(a.xo_off[slot + 1] - e0);
-    int hi = a.start_hap[slot] & 1;
-    uint4 *out = FILL ? off_seg + off_off[slot] : nullptr;
-    uint32_t n = 0;
-    if (k == 0) {  // recombination_locs.size() < 3: the chosen parental haplotype unchanged (:2910)
-        const uint4 *H = hi ? H1 : H0;
-        uint32_t nH = hi ? n1 : n0;
-        if (FILL) for (uint32_t q = 0; q < nH; q++) out[q] = H[q];
-        n = nH;
-    } else {
-        for (uint32_t i1 = 1; i1 <= k + 1; i1++) {
-            uint32_t L = i1 == 1 ? a.cov_lo[c] : a.xo_bp[e0 + i1 - 2];
-            uint32_t R = i1 == k + 1 ? a.cov_hi[c] : a.xo_bp[e0 + i1 - 1];
+    const uint64_t n_total = a.n_off * a.n_chr * 2;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t slot = a.off_first * a.n_chr * 2 + t;
+        uint64_t i = (slot >> 1) / (uint64_t)a.n_chr;
+        int c = (int)((slot >> 1) % (uint64_t)a.n_chr), gam = (int)(slot & 1);
+        uint32_t parent = gam ? a.mother[i] : a.father[i];
+        uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2;
+        const uint64_t o0 = a.par_off[ps], o1 = a.par_off[ps + 1], o2 = a.par_off[ps + 2];
+        const uint4 *H0 = a.par_seg + o0, *H1 = a.par_seg + o1;
+        const uint32_t n0 = (uint32_t)(o1 - o0), n1 = (uint32_t)(o2 - o1);
+        uint64_t e0 = a.xo_off[slot];
+        uint32_t k = (uint32_t)(a.xo_off[slot + 1] - e0);
+        int hi = a.start_hap[slot] & 1;
+        uint4 *out = FILL ? off_seg + off_off[slot] : nullptr;
+        uint32_t n = 0;
+        if (k == 0) {  // recombination_locs.size() < 3: the chosen parental haplotype unchanged (:2910)
             const uint4 *H = hi ? H1 : H0;
-            uint32_t nH = hi ? n1 : n0, i2 = 0;
-            while (i2 < nH && H[i2].y <= L) i2++;
-            if (i2 < nH) {
-                uint4 q = H[i2];
-                if (q.x < L && L < q.y && R < q.y) { if (FILL) out[n] = make_uint4(L, R, q.z, q.w); n++; i2++; }
+            n = hi ? n1 : n0;
+            if (FILL) for (uint32_t q = 0; q < n; q++) out[q] = H[q];
+        } else {
+            uint32_t cur0 = 0, cur1 = 0;   // first part of each parental haplotype that can still end after L
+            uint32_t prevL = 0;
+            for (uint32_t i1 = 1; i1 <= k + 1; i1++) {
+                uint32_t L = i1 == 1 ? a.cov_lo[c] : a.xo_bp[e0 + i1 - 2];
+                uint32_t R = i1 == k + 1 ? a.cov_hi[c] : a.xo_bp[e0 + i1 - 1];
+                if (L < prevL) { cur0 = 0; cur1 = 0; }
+                prevL = L;
+                const uint4 *H = hi ? H1 : H0;
+                uint32_t nH = hi ? n1 : n0, i2 = hi ? cur1 : cur0;
+                while (i2 < nH && H[i2].y <= L) i2++;
+                if (hi) cur1 = i2; else cur0 = i2;
+                if (i2 < nH) {
+                    uint4 q = H[i2];
+                    if (q.x < L && L < q.y && R < q.y) { if (FILL) out[n] = make_uint4(L, R, q.z, q.w); n++; i2++; }
+                }
+                if (i2 < nH) {
+                    uint4 q = H[i2];
+                    if (q.x < L && L < q.y && R >= q.y) { if (FILL) out[n] = make_uint4(L, q.y, q.z, q.w); n++; i2++; }
+                }
+                while (i2 < nH) {
+                    uint4 q = H[i2];
+                    if (!(q.y <= R && L <= q.x)) break;
+                    if (FILL) out[n] = q;
+                    n++; i2++;
+                }
+                if (i2 < nH) {
+                    uint4 q = H[i2];
+                    if (q.x < R && R < q.y) { if (FILL) out[n] = make_uint4(q.x, R, q.z, q.w); n++; }
+                }
+                hi ^= 1;
             }
-            if (i2 < nH) {
-                uint4 q = H[i2];
-                if (q.x < L && L < q.y && R >= q.y) { if (FILL) out[n] = make_uint4(L, q.y, q.z, q.w); n++; i2++; }
-            }
-            while (i2 < nH) {
-                uint4 q = H[i2];
-                if (!(q.y <= R && L <= q.x)) break;
-                if (FILL) out[n] = q;
-                n++; i2++;
-            }
-            if (i2 < nH) {
-                uint4 q = H[i2];
-                if (q.x < R && R < q.y) { if (FILL) out[n] = make_uint4(q.x, R, q.z, q.w); n++; }
-            }
-            hi ^= 1;
         }
+        if (!FILL) count[slot] = n;
     }
-    if (!FILL) count[slot] = n;
+}
+
+// The same function, one WARP per offspring haplotype slot — the kernel the segment path runs by default.
+// Parental lists are sorted and tile the chromosome, so whether part (x, y) of the current haplotype contributes to
+// interval [L, R) — and with which clip — is a local predicate that reproduces the four branches of :2922-2954:
+//   y <= L                      not reached (the `while` skip)
+//   x <  L, R <  y              (L, R)    interval inside one part   [clip both]
+//   x <  L, R >= y              (L, y)                               [clip start]
+//   x >= L, y <= R              (x, y)    whole part (zero-length parts included, as in the reference)
+//   x >= L, x < R < y           (x, R)                               [clip end]
+// The warp walks the intervals in order; for each it reads the parts of the current haplotype from that haplotype's
+// cursor in coalesced chunks of 32 (512 B), ballots the predicate and writes the pieces compacted with coalesced
+// 16-byte stores.  Pieces come out in (interval, part) order exactly as the reference appends them.  Lists that are
+// not sorted can only arise from genetic maps with rows closer than bp_dist_in_rmap; contexts with such a map use the
+// thread-per-slot kernel above, which is the reference's loop verbatim.
+// G lanes cooperate on one slot (G = 32: a warp; G = 8: four slots per warp while the lists are still short).
+template <bool FILL, int G>
+__global__ void seg_recombine_warp_kernel(SegArgs a, uint32_t *__restrict__ count, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg) {
+    const int lane = threadIdx.x & (G - 1);
+    const int shift = (threadIdx.x & 31) - lane;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << shift;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint64_t n_total = a.n_off * a.n_chr * 2;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) / G;
+    for (uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; t < n_total; t += n_warps) {
+        const uint64_t slot = a.off_first * a.n_chr * 2 + t;
+        const uint64_t i = (slot >> 1) / (uint64_t)a.n_chr;
+        const int c = (int)((slot >> 1) % (uint64_t)a.n_chr), gam = (int)(slot & 1);
+        const uint32_t parent = gam ? a.mother[i] : a.father[i];
+        const uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2;
+        const uint64_t o0 = a.par_off[ps], o1 = a.par_off[ps + 1], o2 = a.par_off[ps + 2];
+        const uint4 *H0 = a.par_seg + o0, *H1 = a.par_seg + o1;
+        const uint32_t n0 = (uint32_t)(o1 - o0), n1 = (uint32_t)(o2 - o1);
+        const uint64_t e0 = a.xo_off[slot];
+        const uint32_t k = (uint32_t)(a.xo_off[slot + 1] - e0);
+        int hi = a.start_hap[slot] & 1;
+        uint4 *out = FILL ? off_seg + off_off[slot] : nullptr;
+        uint32_t n = 0;
+        if (k == 0) {  // the chosen parental haplotype unchanged (:2910)
+            const uint4 *H = hi ? H1 : H0;
+            n = hi ? n1 : n0;
+            if (FILL) for (uint32_t q = lane; q < n; q += G) out[q] = H[q];
+        } else {
+            uint32_t cur0 = 0, cur1 = 0, prevL = 0;
+            const uint32_t lo_c = a.cov_lo[c], hi_c = a.cov_hi[c];
+            for (uint32_t i1 = 0; i1 <= k; i1++) {
+                const uint32_t L = i1 == 0 ? lo_c : a.xo_bp[e0 + i1 - 1];
+                const uint32_t R = i1 == k ? hi_c : a.xo_bp[e0 + i1];
+                if (L < prevL) { cur0 = 0; cur1 = 0; }
+                prevL = L;
+                const uint4 *H = hi ? H1 : H0;
+                const uint32_t nH = hi ? n1 : n0, base = hi ? cur1 : cur0;
+                uint32_t adv = 0;
+                for (uint32_t b = base; b < nH; b += G) {
+                    const uint32_t p = b + lane;
+                    const bool valid = p < nH;
+                    uint4 q = make_uint4(0, 0, 0, 0);
+                    if (valid) q = H[p];
+                    const bool reached = valid && q.y > L;
+                    bool emit = false;
+                    uint4 o = q;
+                    if (reached) {
+                        if (q.x < L) { emit = true; o.x = L; if (R < q.y) o.y = R; }
+                        else if (q.y <= R) emit = true;
+                        else if (q.x < R) { emit = true; o.y = R; }
+                    }
+                    const unsigned em = __ballot_sync(gmask, emit) >> shift;
+                    const unsigned past = __ballot_sync(gmask, reached && q.y > R);
+                    adv += __popc(__ballot_sync(gmask, valid && q.y <= R));
+                    if (FILL && emit) out[n + __popc(em & lt)] = o;
+                    n += __popc(em);
+                    if (past) break;
+                }
+                if (hi) cur1 = base + adv; else cur0 = base + adv;
+                hi ^= 1;
+            }
+        }
+        if (!FILL && lane == 0) count[slot] = n;
+    }
 }
 
 // ras_find_cv (:2752-2815) on the segment lists: allele bit plane / root byte plane.  One thread per (haplotype
@@ -177,19 +266,36 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     a.par_off = par.seg.off.as<uint64_t>(); a.par_seg = par.seg.seg.as<uint4>(); a.cov_lo = P.d_cov_lo.as<uint32_t>(); a.cov_hi = P.d_cov_hi.as<uint32_t>();
     GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
     GE_TRY(ctx->ensure(off.seg.off, (n_slots + 1) * 8));
-    ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_RECOMBINE_SEGMENTS, 0};
-    if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, ctx->stream)); }
-    seg_recombine_kernel<false><<<nblk(n_slots, 128), 128, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
+    // both passes are timed separately (the scan's host read-back and a possible reallocation lie between them)
+    ge_ctx::EvPair ev1{nullptr, nullptr, GE_KERNEL_RECOMBINE_SEGMENTS, 0}, ev2 = ev1;
+    if (ctx->profiling) { ev1.a = ctx->get_event(); ev1.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev1.a, ctx->stream)); }
+    // lanes per slot: the reference's loop verbatim in one thread while the lists are short (or may be unsorted), a whole
+    // warp once a parental list averages 30 parts (8 lanes per slot, GE_SEG_GROUP=8, never won a measurement)
+    const double avg_parts = (double)par.seg.n_seg / (double)std::max<uint64_t>(1, par.n * C * 2);
+    int group = ctx->seg_per_thread ? 1 : (ctx->seg_group > 0 ? ctx->seg_group : (avg_parts < 30 ? 1 : 32));  // measured cross-over at ~30 parts per list (1M individuals)
+    const unsigned wgrid = (unsigned)std::min<uint64_t>(nblk(n_slots * (uint64_t)group, 256), (uint64_t)ctx->n_sm * 64);
+    if (group == 1) seg_recombine_kernel<false><<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
+    else if (group == 8) seg_recombine_warp_kernel<false, 8><<<wgrid, 256, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
+    else seg_recombine_warp_kernel<false, 32><<<wgrid, 256, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
     GE_TRY(ctx->check_launch("seg_recombine<count>"));
+    if (ctx->profiling) CUDA_TRY(cudaEventRecord(ev1.b, ctx->stream));
     GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, off.seg.off.as<uint64_t>(), &off.seg.n_seg));
     if (ctx->cfg.seg_capacity && off.seg.n_seg > ctx->cfg.seg_capacity) return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity");
-    GE_TRY(ctx->ensure(off.seg.seg, std::max<uint64_t>(off.seg.n_seg, 1) * 16));
-    seg_recombine_kernel<true><<<nblk(n_slots, 128), 128, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+    // lists grow by ~36 parts per individual-haplotype-genome per generation: size the buffer once when the caller
+    // gave seg_capacity, otherwise grow geometrically (a reallocation of tens of GB costs more than a generation)
+    uint64_t want = std::max<uint64_t>(off.seg.n_seg, 1);
+    if (ctx->cfg.seg_capacity) want = ctx->cfg.seg_capacity; else if (want * 16 > off.seg.seg.cap) want += want / 2;
+    GE_TRY(ctx->ensure_exact(off.seg.seg, want * 16));
+    if (ctx->profiling) { ev2.a = ctx->get_event(); ev2.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev2.a, ctx->stream)); }
+    if (group == 1) seg_recombine_kernel<true><<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+    else if (group == 8) seg_recombine_warp_kernel<true, 8><<<wgrid, 256, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+    else seg_recombine_warp_kernel<true, 32><<<wgrid, 256, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
     GE_TRY(ctx->check_launch("seg_recombine<fill>"));
     if (ctx->profiling) {
-        CUDA_TRY(cudaEventRecord(evp.b, ctx->stream));
-        evp.bytes = 16 * (par.seg.n_seg * 0 + 2 * off.seg.n_seg);  // 16 B per segment read (approx. one parental piece per emitted piece) + written
-        ctx->ev_pending.push_back(evp);
+        CUDA_TRY(cudaEventRecord(ev2.b, ctx->stream));
+        // 16 B per part: every emitted piece comes from one parental part, read by both passes and written once
+        ev1.bytes = 16 * off.seg.n_seg; ev2.bytes = 32 * off.seg.n_seg;
+        ctx->ev_pending.push_back(ev1); ctx->ev_pending.push_back(ev2);
     }
     off.seg.valid = true;
     return GE_OK;

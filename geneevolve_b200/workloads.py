@@ -21,6 +21,10 @@ CONFIGS = {
     "config1_bundled_1chr": dict(n=1000, loci=1000, chrs=[1], founders=2000, n_cv=100, rm=True, mat_cor=0.0),
     "config2_chr22_10k": dict(n=10000, loci=500000, chrs=[22], founders=2000, n_cv=1000, rm=False, mat_cor=0.0),
     "config3_100k_x_1M": dict(n=100000, loci=1000000, chrs=list(range(1, 23)), founders=4000, n_cv=1000, rm=False, mat_cor=0.4),
+    # config 5 (whole-genome sequence): 2.5 TB per generation bit-packed does not fit, so it runs on founder segments
+    # like the reference; the 10M loci are nominal (the segment path never touches non-causal loci)
+    "config5_1M_x_10M_segments": dict(n=1000000, loci=10000000, chrs=list(range(1, 23)), founders=4000, n_cv=1000, rm=False, mat_cor=0.4,
+                                      segments=True),
 }
 
 
@@ -56,6 +60,8 @@ def make_workload(name, seed=20261018, n_override=None, loci_override=None):
     loci = []
     for (bp, _, _), nl in zip(maps, n_loci):
         lo, hi = int(bp[0]), int(bp[-1])
+        if cfg.get("segments"):  # only the causal variants need positions
+            nl = max(1000, cfg["n_cv"])
         pos = np.sort(rng.choice(hi - lo, size=nl, replace=False).astype(np.uint64) + np.uint64(lo)) if nl < (hi - lo) // 4 else \
             np.unique(rng.integers(lo, hi, size=nl * 2, dtype=np.uint64))[:nl]
         loci.append(pos)
@@ -69,7 +75,7 @@ def make_workload(name, seed=20261018, n_override=None, loci_override=None):
         f = np.clip(rng.beta(0.5, 0.5, size=k), 0.01, 0.99)
         val = (rng.random((nh, k)) < f[None, :]).astype(np.uint8)
         cvs.append(dict(bp=pos[sel], a=rng.normal(size=k), d=np.zeros(k), val=val, idx=sel))
-    cfg.update(maps=maps, loci=loci, cvs=cvs, n_loci=[len(p) for p in loci], seed=seed)
+    cfg.update(maps=maps, loci=loci, cvs=cvs, n_loci=[int(x) for x in n_loci] if cfg.get("segments") else [len(p) for p in loci], seed=seed)
     return cfg
 
 
@@ -94,13 +100,16 @@ def configure_engine(eng, cfg, va=0.5, vd=0.0, ve=0.5, panel_seed=7, chrs_local=
     chrs_local = list(range(len(cfg["chrs"]))) if chrs_local is None else list(chrs_local)
     if len(chrs_local) != len(cfg["chrs"]) or chrs_local != list(range(len(chrs_local))):
         eng.set_chromosome_ids(chrs_local)
+    segments_only = bool(cfg.get("segments"))
     for k, c in enumerate(chrs_local):
-        eng.set_loci(k, cfg["loci"][c])
+        if not segments_only:
+            eng.set_loci(k, cfg["loci"][c])
     eng.set_population(0, avoid_inbreeding=False, random_mating=cfg["rm"], mm_percent=0.0)
     for k, c in enumerate(chrs_local):
         bp, cm, p = cfg["maps"][c]
         eng.set_genetic_map(0, k, bp, p, int(bp[1] - bp[0]))
-        eng.set_founder_panel_packed(0, k, founder_words(cfg, c, np.random.default_rng([panel_seed, c])))
+        if not segments_only:
+            eng.set_founder_panel_packed(0, k, founder_words(cfg, c, np.random.default_rng([panel_seed, c])))
         cv = cfg["cvs"][c]
         eng.set_cv(0, 0, k, cv["bp"], cv["a"], cv["d"], cv["val"])
     eng.set_pheno_scheme(0, 0, va=va, vd=vd, ve=ve, vc=0.0, vf=0.0, omega=1.0, beta=0.0, lam=1.0)

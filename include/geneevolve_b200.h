@@ -212,6 +212,10 @@ int ge_download_segments(ge_ctx *ctx, int pop, int chr, uint64_t *seg_off, uint6
                          uint64_t *mut_off /* [2*n+1] per haplotype */, uint64_t *mut_bp);
 /* Causal-variant alleles, the `--debug` .cvval dump (:2665-2683): out[(i*2+h)*n_cv + k]. */
 int ge_download_cv_alleles(ge_ctx *ctx, int pop, int phen, int chr, uint8_t *out);
+/* Verification aid (GE_REP_SEGMENTS): rebuild the causal-variant planes of the current generation by scanning every
+ * haplotype's parts exactly like ras_find_cv (:2752-2815).  The hot path never does this — it carries the planes
+ * forward by crossover parity — so the planes before and after this call must be identical. */
+int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop);
 /* Draws the device generated for the last ge_reproduce of this population (GE_RNG_PHILOX): sizes first,
  * then the arrays (any pointer may be NULL to skip). */
 int ge_get_draw_counts(ge_ctx *ctx, int pop, uint64_t *n_offspring, uint64_t *n_xo, uint64_t *n_mut);

@@ -61,6 +61,13 @@ def test_replay_matches_reference(cuda_lib, name, rep):
                     assert np.array_equal(s["mut_off"], r["mut_off"])
                     for k in range(len(s["mut_off"]) - 1):
                         assert np.array_equal(np.sort(s["mut_bp"][s["mut_off"][k]:s["mut_off"][k + 1]]), np.sort(r["mut_bp"][r["mut_off"][k]:r["mut_off"][k + 1]]))
+            if rep & capi.GE_REP_SEGMENTS:
+                # the planes the hot path carries forward by crossover parity == ras_find_cv (:2752-2815) on the parts
+                before = [[gpu.cv_alleles(p, f, c) for c in range(G.n_chr)] for f in range(G.n_phen)]
+                gpu.recompute_cv_from_segments(p)
+                for f in range(G.n_phen):
+                    for c in range(G.n_chr):
+                        assert np.array_equal(gpu.cv_alleles(p, f, c), before[f][c]), "propagated CV planes differ from ras_find_cv on the segments"
             for f in range(G.n_phen):
                 m, r = gpu.moments(p, f), cpu.moments(p, f)
                 for k in m:
