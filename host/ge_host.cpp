@@ -4,10 +4,17 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
+#include <deque>
 #include <fstream>
+#include <functional>
+#include <future>
 #include <iostream>
+#include <mutex>
 #include <sstream>
+#include <thread>
 
 namespace gehost {
 
@@ -352,7 +359,8 @@ bool read_output_generations(const std::string &path, std::vector<int> &out, std
 // ------------------------------------------------------------------------------------------------
 // the simulation driver
 // ------------------------------------------------------------------------------------------------
-HostSimulation::~HostSimulation() { if (ctx) ge_destroy(ctx); }
+HostSimulation::HostSimulation(const Options &o) : opt(o) {}
+HostSimulation::~HostSimulation() { info_writer.reset(); if (ctx) ge_destroy(ctx); }
 bool HostSimulation::gfail(const char *what) { err = std::string(what) + ": " + ge_last_error(); return false; }
 
 bool HostSimulation::load_inputs() {
@@ -429,32 +437,102 @@ bool HostSimulation::upload() {
     return true;
 }
 
-bool HostSimulation::write_info(int pop, int gen) {  // Population::ras_save_human_info, src/Population.cpp:510-568
+// The reference writes `<prefix>.info.popK.genG.txt` for every individual after every generation, single-threaded
+// inside the generation loop.  Here the loop only downloads the columns (one pinned-speed copy); formatting and
+// writing run on a background thread that splits the rows over the host's cores, so the text dump overlaps the next
+// generations on the GPU.  Numbers are printed with "%g", which is what `ostream << double` produces.
+class InfoWriter {
+public:
+    InfoWriter() : worker([this] { loop(); }) {}
+    ~InfoWriter() { finish(); }
+    void submit(std::function<void()> job) {
+        std::unique_lock<std::mutex> l(m);
+        cv_room.wait(l, [this] { return q.size() < 3; });   // bounded: at most three generations of columns in flight
+        q.push_back(std::move(job));
+        cv_job.notify_one();
+    }
+    void finish() {
+        {
+            std::unique_lock<std::mutex> l(m);
+            if (done) return;
+            done = true;
+            cv_job.notify_one();
+        }
+        worker.join();
+    }
+    std::string error;   // first failure, read after finish()
+
+private:
+    void loop() {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv_job.wait(l, [this] { return done || !q.empty(); });
+                if (q.empty()) return;
+                job = std::move(q.front());
+                q.pop_front();
+                cv_room.notify_one();
+            }
+            job();
+        }
+    }
+    std::mutex m;
+    std::condition_variable cv_job, cv_room;
+    std::deque<std::function<void()>> q;
+    bool done = false;
+    std::thread worker;
+};
+
+struct InfoColumns {  // one generation of one population, as downloaded
     uint64_t n = 0;
-    if (ge_get_population_size(ctx, pop, &n) != GE_OK) return gfail("ge_get_population_size");
-    std::vector<uint64_t> ids(n * 7);
-    std::vector<uint8_t> sex(n);
-    std::vector<double> col[7], mv(n), sv(n), svf(n);
-    for (auto &c : col) c.resize(n * n_phen);
-    ge_indiv_soa s = {ids.data(), sex.data(), col[0].data(), col[1].data(), col[2].data(), col[3].data(), col[4].data(), col[5].data(), col[6].data(),
-                      mv.data(), sv.data(), svf.data()};
+    int n_phen = 0;
+    std::vector<uint64_t> ids;
+    std::vector<uint8_t> sex;
+    std::vector<double> col[7], mv, sv, svf;
+};
+
+static void format_info_rows(const InfoColumns &c, uint64_t i0, uint64_t i1, std::string &out) {
+    char buf[64];
+    out.reserve((size_t)(i1 - i0) * (60 + 80 * c.n_phen));
+    auto put_u = [&](uint64_t v) { out.append(buf, (size_t)std::snprintf(buf, sizeof buf, "%llu ", (unsigned long long)v)); };
+    auto put_d = [&](double v, char end) { int k = std::snprintf(buf, sizeof buf, "%g", v); buf[k] = end; out.append(buf, (size_t)k + 1); };
+    for (uint64_t i = i0; i < i1; i++) {
+        for (int k = 0; k < 7; k++) put_u(c.ids[i * 7 + k] + 1);  // IDs start from 1 in the files
+        put_u(c.sex[i]);
+        for (int j = 0; j < c.n_phen; j++)
+            for (int k = 0; k < 7; k++) put_d(c.col[k][(uint64_t)j * c.n + i], ' ');
+        put_d(c.mv[i], ' '); put_d(c.sv[i], ' '); put_d(c.svf[i], '\n');
+    }
+}
+
+bool HostSimulation::write_info(int pop, int gen) {  // Population::ras_save_human_info, src/Population.cpp:510-568
+    auto cols = std::make_shared<InfoColumns>();
+    InfoColumns &c = *cols;
+    if (ge_get_population_size(ctx, pop, &c.n) != GE_OK) return gfail("ge_get_population_size");
+    c.n_phen = n_phen;
+    c.ids.resize(c.n * 7); c.sex.resize(c.n); c.mv.resize(c.n); c.sv.resize(c.n); c.svf.resize(c.n);
+    for (auto &v : c.col) v.resize(c.n * n_phen);
+    ge_indiv_soa s = {c.ids.data(), c.sex.data(), c.col[0].data(), c.col[1].data(), c.col[2].data(), c.col[3].data(), c.col[4].data(), c.col[5].data(),
+                      c.col[6].data(), c.mv.data(), c.sv.data(), c.svf.data()};
     if (ge_download_individuals(ctx, pop, &s) != GE_OK) return gfail("ge_download_individuals");
     std::string path = opt.prefix + ".info.pop" + std::to_string(pop + 1) + ".gen" + std::to_string(gen) + ".txt";
-    std::ofstream o(path.c_str());
-    if (!o) return fail("Error: can not open the file [" + path + "] to write.");
-    const char *sep = " ";
-    o << "ID" << sep << "ID_Father" << sep << "ID_Mother" << sep << "ID_Fathers_Father" << sep << "ID_Fathers_Mother" << sep << "ID_Mothers_Father" << sep
-      << "ID_Mothers_Mother" << sep << "sex" << sep;
-    for (int j = 0; j < n_phen; j++)
-        for (const char *k : {"_A", "_D", "_G", "_C", "_E", "_F", "_P"}) o << "ph" << j + 1 << k << sep;
-    o << "MV" << sep << "SV" << sep << "SV_f" << std::endl;
-    for (uint64_t i = 0; i < n; i++) {
-        for (int k = 0; k < 7; k++) o << ids[i * 7 + k] + 1 << sep;  // IDs start from 1 in the files
-        o << (int)sex[i] << sep;
-        for (int j = 0; j < n_phen; j++)
-            for (int k = 0; k < 7; k++) o << col[k][(uint64_t)j * n + i] << sep;
-        o << mv[i] << sep << sv[i] << sep << svf[i] << std::endl;
-    }
+    if (!info_writer) info_writer.reset(new InfoWriter());
+    InfoWriter *w = info_writer.get();
+    w->submit([cols, path, w] {
+        std::ofstream o(path.c_str(), std::ios::binary);
+        if (!o) { if (w->error.empty()) w->error = "Error: can not open the file [" + path + "] to write."; return; }
+        o << "ID ID_Father ID_Mother ID_Fathers_Father ID_Fathers_Mother ID_Mothers_Father ID_Mothers_Mother sex ";
+        for (int j = 0; j < cols->n_phen; j++)
+            for (const char *k : {"_A", "_D", "_G", "_C", "_E", "_F", "_P"}) o << "ph" << j + 1 << k << ' ';
+        o << "MV SV SV_f\n";
+        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)(cols->n / 4096 + 1)));
+        std::vector<std::string> part(nt);
+        std::vector<std::future<void>> fut;
+        for (unsigned t = 0; t < nt; t++)
+            fut.push_back(std::async(std::launch::async, [&, t] { format_info_rows(*cols, cols->n * t / nt, cols->n * (t + 1) / nt, part[t]); }));
+        for (unsigned t = 0; t < nt; t++) { fut[t].get(); o.write(part[t].data(), (std::streamsize)part[t].size()); }
+    });
     return true;
 }
 
@@ -565,6 +643,10 @@ bool HostSimulation::run() {
         }
         if (ge_step_generation(ctx, gen, gp.data(), n_pop > 1 ? migration[gen - 1].data() : nullptr, nullptr) != GE_OK) return gfail("ge_step_generation");
         if (!after_generation(gen)) return false;
+    }
+    if (info_writer) {
+        info_writer->finish();
+        if (!info_writer->error.empty()) return fail(info_writer->error);
     }
     return write_summary();
 }

@@ -11,6 +11,7 @@
 // Nothing is computed here: every number in the outputs comes out of the library.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -72,9 +73,11 @@ bool count_hap_columns(const std::string &path, uint64_t &n_hap, std::string &er
 bool read_migration(const std::string &path, int n_pop, size_t n_gen, std::vector<std::vector<double>> &out, std::string &err);
 bool read_output_generations(const std::string &path, std::vector<int> &out, std::string &err);
 
+class InfoWriter;  // background formatter/writer of the per-generation .info files (ge_host.cpp)
+
 class HostSimulation {
 public:
-    explicit HostSimulation(const Options &o) : opt(o) {}
+    explicit HostSimulation(const Options &o);
     ~HostSimulation();
     bool run();                       // Simulation::run
     const std::string &error() const { return err; }
@@ -85,6 +88,7 @@ private:
     std::vector<std::vector<double>> migration;   // [gen][n_pop*n_pop]
     std::vector<int> output_generations;
     ge_ctx *ctx = nullptr;
+    std::unique_ptr<InfoWriter> info_writer;
     int n_pop = 0, n_chr = 0, n_phen = 0, tot_gen = 0;
     bool need_panel = false;
     std::string err;

@@ -36,7 +36,7 @@ def oracle_cli():
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O1", "-std=c++14", "-I" + os.path.join(ROOT, "include"), "-include", os.path.join(HERE, "host_oracle_shim.h"),
-                        "-o", out] + srcs + ["-L" + os.path.dirname(oracle.LIB), "-l:libge_oracle.so", "-Wl,-rpath," + os.path.dirname(oracle.LIB)], check=True)
+                        "-o", out] + srcs + ["-L" + os.path.dirname(oracle.LIB), "-l:libge_oracle.so", "-pthread", "-Wl,-rpath," + os.path.dirname(oracle.LIB)], check=True)
     return out
 
 
@@ -131,6 +131,49 @@ def check_errors(cli, tmp_path):
     assert r.returncode == 255 and "missing parameter [--file_gen_info]" in r.stdout
     r = subprocess.run([cli] + args + ["--out_vcf"], capture_output=True, text=True)
     assert r.returncode == 255 and "--out_vcf" in r.stdout
+
+
+def check_two_populations(cli, tmp_path):
+    """--next_population and --file_migration: under random mating the sizes after migration are draw-independent, so
+    the row counts of every .info file must equal the reference's."""
+    sc = dict(su.SCENARIOS["S_drift_ld"])
+    sc["gens"] = [(120, 0.0, "p", "thr", 1, 1)] * 3
+    a1 = su.write_reference_inputs(sc, str(tmp_path), tag="p1")
+    sc2 = dict(sc)
+    sc2["gens"] = [(80, 0.0, "p", "thr", 1, 1)] * 3
+    a2 = su.write_reference_inputs(sc2, str(tmp_path), tag="p2")
+    mig = tmp_path / "mig.txt"
+    mig.write_text("0.9 0.1 0.25 0.75\n" * 3)
+    args = a1 + ["--next_population"] + a2 + ["--file_migration", str(mig)]
+    pre = str(tmp_path / "ours")
+    r = subprocess.run([cli] + args + ["--seed", "9", "--prefix", pre, "--out_interval", "--quiet"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = {(p, g): sum(1 for _ in open(f"{pre}.info.pop{p}.gen{g}.txt")) - 1 for p in (1, 2) for g in range(4)}
+    n1, n2 = 120, 80
+    m12, m21 = round(0.1 * n1), round(0.25 * n2)
+    for g in range(1, 4):
+        assert rows[(1, g)] == n1 - m12 + m21 and rows[(2, g)] == n2 - m21 + m12
+    ints = sorted(f for f in os.listdir(tmp_path) if f.startswith("ours") and f.endswith(".int"))
+    assert ints == ["ours.pop1.gen3.chr1.int", "ours.pop2.gen3.chr1.int"]
+    roots = {line.split()[-1] for line in list(open(tmp_path / "ours.pop1.gen3.chr1.int"))[1:]}
+    assert roots == {"1", "2"}      # after three generations of migration both founder panels contribute
+    if os.path.exists(REF_BIN):
+        rp = str(tmp_path / "ref")
+        rr = subprocess.run([REF_BIN] + args + ["--seed", "9", "--prefix", rp, "--out_interval"], capture_output=True, text=True)
+        assert rr.returncode == 0
+        for (p, g), n in rows.items():
+            assert sum(1 for _ in open(f"{rp}.info.pop{p}.gen{g}.txt")) - 1 == n, (p, g)
+        with open(f"{rp}.pop2.summary") as f1, open(f"{pre}.pop2.summary") as f2:
+            assert f1.readline() == f2.readline()
+
+
+def test_host_cli_two_populations_on_oracle(tmp_path):
+    check_two_populations(oracle_cli(), tmp_path)
+
+
+@pytest.mark.gpu
+def test_host_cli_two_populations_on_gpu(tmp_path):
+    check_two_populations(product_cli(), tmp_path)
 
 
 def test_host_cli_on_oracle(tmp_path):
