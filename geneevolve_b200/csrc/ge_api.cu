@@ -106,30 +106,51 @@ static std::vector<double> survival_table(const std::vector<double> &p, size_t f
     return T;
 }
 
+// value index of one survival table for next_success (ge_kernels.cuh): entry b = first row k with T[k+1] < 1 - b/scale
+static void value_index(const std::vector<double> &T, std::vector<uint32_t> &vb, double &scale) {
+    const size_t R = T.size() - 1;
+    const size_t B = std::max<size_t>(16, 2 * R);
+    const double span = 1.0 - T[R];
+    scale = span > 0 ? (double)B / span : 0.0;
+    size_t k = 0;
+    for (size_t b = 0; b <= B; b++) {
+        const double v_hi = scale > 0 ? 1.0 - (double)b / scale : 1.0;
+        while (k < R && !(T[k + 1] < v_hi)) k++;
+        vb.push_back((uint32_t)std::min(k, R > 0 ? R - 1 : 0));
+    }
+}
+
 static int build_maps(ge_ctx *ctx, PopDev &P) {
     int C = ctx->cfg.n_chr;
     std::vector<uint32_t> row_off(C + 1, 0), bp, dist, cov_lo(C), cov_hi(C);
-    std::vector<double> T;
+    std::vector<double> T, vscale(C, 0.0);
+    std::vector<uint32_t> vb, vb_off(C + 1, 0);
     for (int c = 0; c < C; c++) {
         if (P.rmap_bp[c].size() < 2) return fail(GE_ERR_INVALID, "genetic map of a chromosome is missing (ge_set_genetic_map)");
         for (uint64_t v : P.rmap_bp[c]) { if (v > 0xFFFFFFFFull) return fail(GE_ERR_UNSUPPORTED, "map position does not fit 32 bits"); bp.push_back((uint32_t)v); }
         row_off[c + 1] = (uint32_t)bp.size();
         std::vector<double> t = survival_table(P.recom_prob[c], 0);
         T.insert(T.end(), t.begin(), t.end());
+        value_index(t, vb, vscale[c]);
+        vb_off[c + 1] = (uint32_t)vb.size();
         dist.push_back((uint32_t)P.bp_dist[c]);
         cov_lo[c] = (uint32_t)P.rmap_bp[c].front(); cov_hi[c] = (uint32_t)P.rmap_bp[c].back();
     }
     GE_TRY(ctx->upload(P.d_row_off, row_off)); GE_TRY(ctx->upload(P.d_bp, bp)); GE_TRY(ctx->upload(P.d_T, T));
+    GE_TRY(ctx->upload(P.d_vb, vb)); GE_TRY(ctx->upload(P.d_vb_off, vb_off)); GE_TRY(ctx->upload(P.d_vb_scale, vscale));
     GE_TRY(ctx->upload(P.d_bp_dist, dist)); GE_TRY(ctx->upload(P.d_cov_lo, cov_lo)); GE_TRY(ctx->upload(P.d_cov_hi, cov_hi));
     if (P.has_mut) {
-        std::vector<uint32_t> mro(C + 1, 0), mbp; std::vector<double> mT;
+        std::vector<uint32_t> mro(C + 1, 0), mbp, mvb, mvb_off(C + 1, 0); std::vector<double> mT, mvscale(C, 0.0);
         for (int c = 0; c < C; c++) {
             for (uint64_t v : P.mutmap_bp[c]) mbp.push_back((uint32_t)v);
             mro[c + 1] = (uint32_t)mbp.size();
             std::vector<double> t = survival_table(P.mutmap_rate[c], 1);
             mT.insert(mT.end(), t.begin(), t.end());
+            value_index(t, mvb, mvscale[c]);
+            mvb_off[c + 1] = (uint32_t)mvb.size();
         }
         GE_TRY(ctx->upload(P.d_mrow_off, mro)); GE_TRY(ctx->upload(P.d_mbp, mbp)); GE_TRY(ctx->upload(P.d_mT, mT));
+        GE_TRY(ctx->upload(P.d_mvb, mvb)); GE_TRY(ctx->upload(P.d_mvb_off, mvb_off)); GE_TRY(ctx->upload(P.d_mvb_scale, mvscale));
     }
     return GE_OK;
 }
@@ -250,7 +271,7 @@ int ge_destroy(ge_ctx *ctx) {
     for (SortLane &l : ctx->lane) cudaStreamSynchronize(l.s);
     auto freeb = [&](Buf &b) { ctx->release(b); };
     for (PopDev &P : ctx->pop) {
-        for (Buf *b : {&P.d_row_off, &P.d_bp, &P.d_T, &P.d_bp_dist, &P.d_mrow_off, &P.d_mbp, &P.d_mT, &P.d_cov_lo, &P.d_cov_hi, &P.d_omega,
+        for (Buf *b : {&P.d_row_off, &P.d_bp, &P.d_T, &P.d_bp_dist, &P.d_mrow_off, &P.d_mbp, &P.d_mT, &P.d_vb, &P.d_vb_off, &P.d_vb_scale, &P.d_mvb, &P.d_mvb_off, &P.d_mvb_scale, &P.d_cov_lo, &P.d_cov_hi, &P.d_omega,
                        &P.d_lambda, &P.d_vd_zero, &P.prev_P, &P.prev_F, &P.c_male, &P.c_female, &P.c_inbreed, &P.c_noff, &P.mut_off, &P.mut_bp, &P.mut_gam, &P.e_raw, &P.cnt32, &P.d_sv0, &P.founder_rows, &P.founder_cv})
             freeb(*b);
         for (DrawSet &D : P.ds) {

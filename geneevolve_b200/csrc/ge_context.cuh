@@ -91,6 +91,7 @@ struct PopDev {
     Buf founder_rows, founder_cv;  // kept on the device for segment materialisation / ras_find_cv (GE_REP_SEGMENTS)
     // device maps
     Buf d_row_off, d_bp, d_T, d_bp_dist, d_mrow_off, d_mbp, d_mT, d_cov_lo, d_cov_hi;
+    Buf d_vb, d_vb_off, d_vb_scale, d_mvb, d_mvb_off, d_mvb_scale;   // value indexes of the survival tables
     Buf d_omega, d_lambda, d_vd_zero;
     GenState st[2];
     int cur = 0;
@@ -249,11 +250,13 @@ struct ge_ctx {
     }
     MapDev rmap(const PopDev &P) const {
         MapDev m; m.row_off = P.d_row_off.as<uint32_t>(); m.bp = P.d_bp.as<uint32_t>(); m.T = P.d_T.as<double>(); m.bp_dist = P.d_bp_dist.as<uint32_t>();
+        m.vb = P.d_vb.as<uint32_t>(); m.vb_off = P.d_vb_off.as<uint32_t>(); m.vb_scale = P.d_vb_scale.as<double>();
         m.chr_id = d_chr_ids.as<uint32_t>();
         return m;
     }
     MapDev mmap(const PopDev &P) const {
         MapDev m; m.row_off = P.d_mrow_off.as<uint32_t>(); m.bp = P.d_mbp.as<uint32_t>(); m.T = P.d_mT.as<double>(); m.bp_dist = nullptr;
+        m.vb = P.d_mvb.as<uint32_t>(); m.vb_off = P.d_mvb_off.as<uint32_t>(); m.vb_scale = P.d_mvb_scale.as<double>();
         m.chr_id = d_chr_ids.as<uint32_t>();
         return m;
     }

@@ -917,13 +917,25 @@ struct MapDev {
     const uint32_t *row_off;  // [n_chr+1] offsets into bp (rows per chromosome)
     const uint32_t *bp;       // concatenated map rows
     const double *T;          // concatenated survival tables, chromosome c starts at row_off[c] + c (R_c + 1 entries)
+    // value index of T (exact acceleration of the search below): vb[vb_off[c] + b] = first row k with
+    // T[k+1] < 1 - b / vb_scale[c], b = 0 .. B_c where B_c = vb_off[c+1] - vb_off[c] - 1
+    const uint32_t *vb_off;   // [n_chr+1]
+    const uint32_t *vb;
+    const double *vb_scale;   // [n_chr]
     const uint32_t *bp_dist;  // [n_chr]
     const uint32_t *chr_id;   // [n_chr] index in the full genome (Philox counter; differs from c on a sharded context)
 };
-__device__ __forceinline__ long long next_success(const double *T, uint32_t R, uint32_t j, double v) {
+// first row k >= j with T[k+1] < v, or -1.  T is non-increasing, so {k : T[k+1] < v} is an up-set with minimum k_g(v) and the
+// answer is max(j, k_g).  k_g lies between the index entries of v's bucket; one bucket of slack on either side absorbs
+// the rounding of the bucket number, and the binary search over that range returns exactly what a search over [0, R) would.
+__device__ __forceinline__ long long next_success(const MapDev &m, int c, const double *T, uint32_t R, uint32_t j, double v) {
     if (j >= R || !(T[R] < v)) return -1;
-    uint32_t lo = j, hi = R - 1;
+    const uint32_t *vb = m.vb + m.vb_off[c];
+    const uint32_t B = m.vb_off[c + 1] - m.vb_off[c] - 1;
+    uint32_t b = (uint32_t)fmin((1.0 - v) * m.vb_scale[c], (double)(B - 1));
+    uint32_t lo = __ldg(vb + (b > 0 ? b - 1 : 0)), hi = __ldg(vb + min(b + 2, B));
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (T[mid + 1] < v) hi = mid; else lo = mid + 1; }
+    if (lo < j) lo = j;
     return (long long)lo;
 }
 // One thread per slot.  Pass 0 counts, writes start_hap and stashes the first XO_STASH positions of the slot at a
@@ -949,7 +961,7 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int ge
         blk++;
         if (j >= R) break;
         double v = (1.0 - u01(w[0], w[1])) * T[j];
-        long long k = next_success(T, R, j, v);
+        long long k = next_success(m, c, T, R, j, v);
         if (k < 0) break;
         if (FILL) xo_bp[o + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
         else if (stash && n < XO_STASH) stash[t * XO_STASH + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
@@ -985,7 +997,7 @@ __global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int po
         draw(st, P_XO, pop, gen, i, m.chr_id[c] * 2u + (uint32_t)gam, blk++, w);
         if (j >= R) break;
         double v = (1.0 - u01(w[0], w[1])) * T[j];
-        long long k = next_success(T, R, j, v);
+        long long k = next_success(m, c, T, R, j, v);
         if (k < 0) break;
         uint32_t x = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
         xo_bp[o + n] = x;
@@ -1015,7 +1027,7 @@ __global__ void sample_mut_kernel(Stream st, MapDev m, int n_chr, int pop, int g
         uint32_t w[4];
         draw(st, P_MUT, pop, gen, i, m.chr_id[c], blk++, w);
         double v = (1.0 - u01(w[0], w[1])) * T[j];
-        long long k = next_success(T, R, j, v);
+        long long k = next_success(m, c, T, R, j, v);
         if (k < 0) break;
         if (FILL) {
             uint32_t s0 = m.bp[r0 + (uint32_t)k - 1], s1 = m.bp[r0 + (uint32_t)k];
