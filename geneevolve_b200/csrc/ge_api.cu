@@ -325,6 +325,8 @@ int ge_set_genetic_map(ge_ctx *ctx, int pop, int chr, const uint64_t *bp, const 
 }
 int ge_set_mutation_map(ge_ctx *ctx, int pop, int chr, const uint64_t *bp, const double *rate, uint64_t n) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr);
+    if (!bp || !rate || n < 2) return fail(GE_ERR_INVALID, "ge_set_mutation_map: need >= 2 rows");
+    for (uint64_t k = 0; k < n; k++) if (bp[k] > 0xFFFFFFFFull) return fail(GE_ERR_UNSUPPORTED, "mutation-map position does not fit 32 bits");
     PopDev &P = ctx->pop[pop];
     P.mutmap_bp[chr].assign(bp, bp + n); P.mutmap_rate[chr].assign(rate, rate + n); P.has_mut = true;
     return GE_OK;
@@ -337,6 +339,8 @@ int ge_set_loci(ge_ctx *ctx, int chr, const uint64_t *pos, uint64_t n) {
 }
 int ge_set_founder_panel(ge_ctx *ctx, int pop, int chr, const uint8_t *al, uint64_t nh) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr);
+    if (!al || nh == 0 || (nh & 1)) return fail(GE_ERR_INVALID, "ge_set_founder_panel: need an even, non-zero number of founder haplotypes");
+    if (ctx->loci[chr].empty()) return fail(GE_ERR_INVALID, "ge_set_founder_panel: call ge_set_loci for this chromosome first");
     PopDev &P = ctx->pop[pop];
     P.panel[chr].assign(al, al + nh * ctx->loci[chr].size());
     P.n_founder_haps = nh;
@@ -344,6 +348,8 @@ int ge_set_founder_panel(ge_ctx *ctx, int pop, int chr, const uint8_t *al, uint6
 }
 int ge_set_founder_panel_packed(ge_ctx *ctx, int pop, int chr, const uint32_t *words, uint64_t nh) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr);
+    if (!words || nh == 0 || (nh & 1)) return fail(GE_ERR_INVALID, "ge_set_founder_panel_packed: need an even, non-zero number of founder haplotypes");
+    if (ctx->loci[chr].empty()) return fail(GE_ERR_INVALID, "ge_set_founder_panel_packed: call ge_set_loci for this chromosome first");
     PopDev &P = ctx->pop[pop];
     if (P.panel_packed.empty()) P.panel_packed.resize(ctx->cfg.n_chr);
     uint64_t nw = (ctx->loci[chr].size() + 31) / 32;
@@ -353,6 +359,9 @@ int ge_set_founder_panel_packed(ge_ctx *ctx, int pop, int chr, const uint32_t *w
 }
 int ge_set_cv(ge_ctx *ctx, int pop, int phen, int chr, const uint64_t *bp, const double *a, const double *d, uint64_t ncv, const uint8_t *val, uint64_t nh) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr); CHECK_PHEN(ctx, phen);
+    if (ncv && (!bp || !a || !d || !val)) return fail(GE_ERR_INVALID, "ge_set_cv: null array");
+    if (nh == 0 || (nh & 1)) return fail(GE_ERR_INVALID, "ge_set_cv: need an even, non-zero number of founder haplotypes");
+    for (uint64_t k = 0; k < ncv; k++) if (bp[k] > 0xFFFFFFFFull) return fail(GE_ERR_UNSUPPORTED, "causal-variant position does not fit 32 bits");
     CvHost &h = ctx->pop[pop].cv[phen][chr];
     h.bp.assign(bp, bp + ncv); h.a.assign(a, a + ncv); h.d.assign(d, d + ncv); h.val.assign(val, val + nh * ncv); h.nhap = nh;
     return GE_OK;
@@ -767,15 +776,24 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
     uint64_t n_off = 0;
     std::vector<uint32_t> tmp;
     cudaStream_t st = ctx->stream;
+    if (dr) {  // validate the caller's draws before any state changes
+        n_off = dr->n_offspring;
+        if (n_off == 0) return fail(GE_ERR_NO_MATES, "no offspring");
+        if (n_off > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "offspring exceed capacity");
+        if (!dr->father || !dr->mother || !dr->sex || !dr->xo_off || !dr->start_hap) return fail(GE_ERR_INVALID, "incomplete draws");
+        for (uint64_t i = 0; i < n_off; i++) if (dr->father[i] >= par.n || dr->mother[i] >= par.n) return fail(GE_ERR_INVALID, "parent index out of range");
+        const uint64_t ns = n_off * C * 2;
+        for (uint64_t k = 0; k < ns; k++) if (dr->xo_off[k + 1] < dr->xo_off[k]) return fail(GE_ERR_INVALID, "xo_off must be non-decreasing");
+        if (dr->xo_off[ns] && !dr->xo_bp) return fail(GE_ERR_INVALID, "incomplete draws: xo_bp");
+    } else {
+        if (ctx->cfg.rng_mode != GE_RNG_PHILOX) return fail(GE_ERR_INVALID, "replay mode needs draws");
+        if (P.n_couples == 0) return fail(GE_ERR_INVALID, "no couples: call ge_mate or ge_set_couples first");
+    }
     // the other draw set; the bulk stream may still read it for the generation before last
     P.dcur ^= 1;
     DrawSet &D = P.draws();
     if (D.bulk_pending) { CUDA_TRY(cudaStreamWaitEvent(st, D.bulk_done, 0)); D.bulk_pending = false; }
     if (dr) {
-        n_off = dr->n_offspring;
-        if (n_off > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "offspring exceed capacity");
-        if (!dr->father || !dr->mother || !dr->sex || !dr->xo_off || !dr->start_hap) return fail(GE_ERR_INVALID, "incomplete draws");
-        for (uint64_t i = 0; i < n_off; i++) if (dr->father[i] >= par.n || dr->mother[i] >= par.n) return fail(GE_ERR_INVALID, "parent index out of range");
         GE_TRY(upload_u64_as_u32(ctx, D.father, dr->father, n_off, tmp, "father"));
         GE_TRY(upload_u64_as_u32(ctx, D.mother, dr->mother, n_off, tmp, "mother"));
         uint64_t n_slots = n_off * C * 2;
@@ -794,8 +812,6 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         if (dr->common) CUDA_TRY(cudaMemcpyAsync(off.C.p, dr->common, (size_t)n_off * nf * 8, cudaMemcpyHostToDevice, st));
         P.have_couple_of = false;
     } else {
-        if (ctx->cfg.rng_mode != GE_RNG_PHILOX) return fail(GE_ERR_INVALID, "replay mode needs draws");
-        if (P.n_couples == 0) return fail(GE_ERR_INVALID, "no couples: call ge_mate or ge_set_couples first");
         // offspring offsets = exclusive scan of the family sizes of the couples that may marry (:2402-2406)
         GE_TRY(ctx->ensure(P.cnt32, (size_t)std::max<uint64_t>(P.n_couples, ctx->cfg.capacity * C * 2 + 1) * 4));
         GE_TRY(ctx->ensure(P.mate.fam_off, (P.n_couples + 1) * 8));

@@ -15,7 +15,7 @@ from test_sharding_gloo import configure_subset, run_generations
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["B_rm_mut", "A_am_pois"])
+@pytest.mark.parametrize("name", ["B_rm_mut", "A_am_pois", "D_two_pops"])
 def test_two_sharded_contexts_match_one(cuda_lib, name):
     G = Golden(name)
     n_gen = min(G.G, 3)

@@ -20,28 +20,33 @@ def configure_subset(G, eng, chrs):
     eng.set_chromosome_ids(chrs)
     for k, c in enumerate(chrs):
         eng.set_loci(k, z[f"in.p0.c{c}.panel_pos"])
-    pre = "in.p0."
-    eng.set_population(0, bool(z[pre + "avoid_inbreeding"]), bool(z[pre + "RM"]), float(z[pre + "MM_percent"]))
-    for k, c in enumerate(chrs):
-        cp = pre + f"c{c}."
-        eng.set_genetic_map(0, k, z[cp + "rmap_bp"], z[cp + "recom_prob"], int(z[cp + "bp_dist"]))
-        if int(z[pre + "has_mutation_map"]):
-            eng.set_mutation_map(0, k, z[cp + "mut_bp"], z[cp + "mut_rate"])
-        eng.set_founder_panel(0, k, z[cp + "panel"])
+    for p in range(G.n_pop):
+        pre = f"in.p{p}."
+        eng.set_population(p, bool(z[pre + "avoid_inbreeding"]), bool(z[pre + "RM"]), float(z[pre + "MM_percent"]))
+        for k, c in enumerate(chrs):
+            cp = pre + f"c{c}."
+            eng.set_genetic_map(p, k, z[cp + "rmap_bp"], z[cp + "recom_prob"], int(z[cp + "bp_dist"]))
+            if int(z[pre + "has_mutation_map"]):
+                eng.set_mutation_map(p, k, z[cp + "mut_bp"], z[cp + "mut_rate"])
+            eng.set_founder_panel(p, k, z[cp + "panel"])
+            for f in range(G.n_phen):
+                fp = cp + f"f{f}."
+                eng.set_cv(p, f, k, z[fp + "cv_bp"], z[fp + "cv_a"], z[fp + "cv_d"], z[fp + "cv_val"])
         for f in range(G.n_phen):
-            fp = cp + f"f{f}."
-            eng.set_cv(0, f, k, z[fp + "cv_bp"], z[fp + "cv_a"], z[fp + "cv_d"], z[fp + "cv_val"])
-    for f in range(G.n_phen):
-        s = z[pre + "scheme"][f]
-        eng.set_pheno_scheme(0, f, va=s[0], vd=s[1], ve=s[2], vc=s[3], vf=s[4], omega=s[5], beta=s[6], lam=s[7])
+            s = z[pre + "scheme"][f]
+            eng.set_pheno_scheme(p, f, va=s[0], vd=s[1], ve=s[2], vc=s[3], vf=s[4], omega=s[5], beta=s[6], lam=s[7])
+    if len(z["in.gamma"]):
+        eng.set_gamma(z["in.gamma"])
 
 
 def run_generations(G, eng, n_gen):
+    """State of the LAST population after n_gen generations (with migration every population feeds into it)."""
     eng.init_generation0()
     for gen in range(1, n_gen + 1):
-        eng.step_generation(gen, G.all_params(gen))
-    out = {"couples": eng.get_couples(0), "ind": eng.individuals(0)}
-    out["hap"] = [eng.haplotypes(0, k) for k in range(eng.n_chr)]
+        eng.step_generation(gen, G.all_params(gen), G.migration_row(gen))
+    p = G.n_pop - 1
+    out = {"couples": eng.get_couples(p), "ind": eng.individuals(p)}
+    out["hap"] = [eng.haplotypes(p, k) for k in range(eng.n_chr)]
     return out
 
 
@@ -71,7 +76,7 @@ def test_assign_chromosomes_balances():
     assert max(loads) <= 1.08 * sum(w) / 8
 
 
-@pytest.mark.parametrize("name", ["B_rm_mut", "A_am_pois"])
+@pytest.mark.parametrize("name", ["B_rm_mut", "A_am_pois", "D_two_pops"])
 def test_two_ranks_match_single_rank(name):
     G = Golden(name)
     n_gen = min(G.G, 3)
