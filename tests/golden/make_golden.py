@@ -186,5 +186,46 @@ def main():
             ["--file_migration", f"{d}/D.mig", "--gamma", "0.2"], 99)
 
 
+def three_populations():
+    """F. BASELINE config 4 in miniature: three populations of different sizes, ring migration (the reference only
+    survives matrices with at most one non-zero off-diagonal entry per row), two phenotypes with
+    population-specific effect sizes, assortative mating in one population, random mating in another."""
+    with tempfile.TemporaryDirectory() as d:
+        frags = []
+        for k, (tag, scale) in enumerate([("F1", 1.0), ("F2", 1.4), ("F3", 0.7)]):
+            rng = np.random.default_rng(606)   # same SNP / CV positions in every population (required by :1186-1230, :2762)
+            frag = write_inputs(d, rng, tag=tag, chrs=[1, 2], n_founders=26, n_snp=80, n_cv=5, n_phen=2,
+                                map_rows=18, map_step=50, p_row=0.05, cv_scale=scale)
+            rngk = np.random.default_rng(607 + k)   # population-specific founder alleles
+            for cc in [1, 2]:
+                hap = np.loadtxt(f"{d}/{tag}.chr{cc}.hap", dtype=int)
+                hap2 = hap ^ (rngk.uniform(size=hap.shape) < 0.3).astype(int)
+                pos = [int(l.split()[1]) for l in open(f"{d}/{tag}.chr{cc}.legend").read().splitlines()[1:]]
+                with open(f"{d}/{tag}.chr{cc}.hap", "w") as f:
+                    for r in range(hap2.shape[0]):
+                        f.write(" ".join(map(str, hap2[r])) + " \n")
+                for ph in range(2):
+                    cvpos = [int(l.split()[1]) for l in open(f"{d}/{tag}.ph{ph}.cvinfo").read().splitlines()[1:] if int(l.split()[0]) == cc]
+                    with open(f"{d}/{tag}.ph{ph}.cv.chr{cc}.hap", "w") as f:
+                        for p in cvpos:
+                            f.write(" ".join(map(str, hap2[pos.index(p)])) + " \n")
+            frags.append(frag)
+        write_geninfo(f"{d}/F1.gen", [(50, 0.3, "p", "logit", 0, 1)] * 3)
+        write_geninfo(f"{d}/F2.gen", [(40, 0.0, "p", "probit", 0, 1)] * 3)
+        write_geninfo(f"{d}/F3.gen", [(30, 0.0, "f", "logit", 0.2, 1.5)] * 3)
+        with open(f"{d}/F.mig", "w") as f:
+            for _ in range(3):
+                f.write("0.9 0.1 0 0 0.85 0.15 0.2 0 0.8\n")
+        ph = ["--va", "0.5", "--vd", "0", "--ve", "0.5", "--omega", "1", "--lambda", "1", "--va", "0.4", "--vd", "0.1", "--ve", "0.5", "--omega", "0.5", "--lambda", "0"]
+        run("F_three_pops_ring", ["--file_gen_info", f"{d}/F1.gen"] + frags[0] + ph +
+            ["--next_population", "--file_gen_info", f"{d}/F2.gen"] + frags[1] + ph + ["--RM"] +
+            ["--next_population", "--file_gen_info", f"{d}/F3.gen"] + frags[2] + ph +
+            ["--file_migration", f"{d}/F.mig"], 2026)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "F":
+        three_populations()     # added later; the other fixtures are not regenerated
+    else:
+        main()
+        three_populations()
