@@ -3,6 +3,7 @@
 #include "ge_host.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -628,12 +629,22 @@ bool HostSimulation::write_genotypes(int gen) {
 }
 
 bool HostSimulation::run() {
+    // phase timers like the reference's "Time taken for ..." lines (src/Simulation.cpp:70-114), in milliseconds
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        auto t1 = std::chrono::steady_clock::now();
+        if (!opt.quiet) std::cout << "  Time taken for " << what << ": " << std::chrono::duration<double, std::milli>(t1 - t0).count() << " ms" << std::endl;
+        t0 = t1;
+    };
     if (!load_inputs()) return false;
     if (!opt.quiet) std::cout << "  populations: " << n_pop << ", chromosomes: " << n_chr << ", phenotypes: " << n_phen << ", generations: " << tot_gen << std::endl;
+    lap("reading the input files");
     if (!upload()) return false;
+    lap("creating the device context and uploading the inputs");
     summary.assign(n_pop, {});
     if (ge_init_generation0(ctx, nullptr) != GE_OK) return gfail("ge_init_generation0");
     if (!after_generation(0)) return false;
+    lap("initializing generation 0");
     std::vector<ge_gen_params> gp(n_pop);
     for (int gen = 1; gen <= tot_gen; gen++) {  // ras_main_sim :684-702
         for (int p = 0; p < n_pop; p++) {
@@ -644,11 +655,14 @@ bool HostSimulation::run() {
         if (ge_step_generation(ctx, gen, gp.data(), n_pop > 1 ? migration[gen - 1].data() : nullptr, nullptr) != GE_OK) return gfail("ge_step_generation");
         if (!after_generation(gen)) return false;
     }
+    lap("the main body of simulation");
     if (info_writer) {
         info_writer->finish();
         if (!info_writer->error.empty()) return fail(info_writer->error);
     }
-    return write_summary();
+    bool ok = write_summary();
+    lap("finishing the output files");
+    return ok;
 }
 
 }  // namespace gehost
