@@ -28,7 +28,7 @@ const char *Options::usage() {
            "    --file_gen_info F --file_hap_name F --file_recom_map F [--file_mutation_map F] [--RM] [--MM x]\n"
            "    per phenotype: --file_cv_info F --file_cvs F [--va x --vd x --vc x --ve x --vf x --omega x --beta x --lambda x]\n"
            "  global: [--gamma x]... [--file_migration F] [--vt_type 1|2] [--avoid_inbreeding] [--seed n] [--prefix P]\n"
-           "          [--out_hap] [--out_interval] [--file_output_generations F] [--device n] [--quiet]\n"
+           "          [--out_hap] [--out_interval] [--file_output_generations F] [--device n] [--gpus N] [--quiet]\n"
            "  not on this path (rejected): --file_ref_vcf --out_plink --out_plink01 --out_vcf\n";
 }
 
@@ -73,6 +73,7 @@ bool Options::parse(const std::vector<std::string> &a) {
         else if (f == "--out_interval") out_interval = true;
         else if (f == "--file_output_generations") file_output_generations = need(i);
         else if (f == "--device") device = (int)num(i);
+        else if (f == "--gpus") gpus = (int)num(i);
         else if (f == "--quiet") quiet = true;
         else if (f == "--debug") {}
         else if (f == "--help" || f == "-h" || f == "?") help = true;
@@ -109,6 +110,7 @@ bool Options::parse(const std::vector<std::string> &a) {
     if (gamma.size() != nphen) return (error = "Error: the number of [--gamma] must be equal to the number of phenotypes (" + std::to_string(nphen) + ").", false);
     if (npop > 1 && file_migration.empty())
         return (error = "Error: When you have more than one populations, you must specify the [--file_migration] option.", false);
+    if (gpus < 1) return (error = "Error: [--gpus] must be at least 1.", false);
     if (seed == 0) seed = 1;  // the reference seeds from the clock here (src/parameters.cpp:206-209); a fixed default keeps runs reproducible
     return true;
 }
@@ -360,7 +362,27 @@ bool read_output_generations(const std::string &path, std::vector<int> &out, std
 // ------------------------------------------------------------------------------------------------
 // the simulation driver
 // ------------------------------------------------------------------------------------------------
-HostSimulation::HostSimulation(const Options &o) : opt(o) {}
+HostSimulation::HostSimulation(const Options &o, int rank_, int world_, Collective *coll_) : opt(o), rank(rank_), world(world_), coll(coll_) {
+    if (rank != 0) opt.quiet = true;   // one narrator
+}
+int HostSimulation::allreduce_hook(void *user, double *buf, uint64_t count, void *stream) {
+    HostSimulation *self = static_cast<HostSimulation *>(user);
+    return self->coll->allreduce_sum(self->rank, buf, count, stream);
+}
+std::vector<std::vector<int>> HostSimulation::assign_chromosomes(const std::vector<double> &weight, int world) {
+    std::vector<int> order(weight.size());
+    for (size_t c = 0; c < order.size(); c++) order[c] = (int)c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+    std::vector<std::vector<int>> out(world);
+    std::vector<double> load(world, 0.0);
+    for (int c : order) {
+        int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        out[r].push_back(c);
+        load[r] += weight[c];
+    }
+    for (auto &v : out) std::sort(v.begin(), v.end());
+    return out;
+}
 HostSimulation::~HostSimulation() { info_writer.reset(); if (ctx) ge_destroy(ctx); }
 bool HostSimulation::gfail(const char *what) { err = std::string(what) + ": " + ge_last_error(); return false; }
 
@@ -402,26 +424,38 @@ bool HostSimulation::upload() {
         for (const GenRow &r : in[p].gens) cap = std::max(cap, r.pop_size);
     }
     cap = (uint64_t)((double)cap * (n_pop > 1 ? 1.6 : 1.0) + 8.0 * std::sqrt((double)cap)) + 256;  // Poisson family sizes and migration
+    // multi-GPU: every rank holds all individuals but only its chromosomes
+    if (world > n_chr) return fail("Error: [--gpus] exceeds the number of chromosomes.");
+    std::vector<double> weight(n_chr);
+    for (int c = 0; c < n_chr; c++) weight[c] = (double)(in[0].rmap[c].bp.back() - in[0].rmap[c].bp.front());
+    mine = assign_chromosomes(weight, world)[rank];
+    const int n_loc = (int)mine.size();
     ge_config cfg = {};
-    cfg.device = opt.device; cfg.n_pop = n_pop; cfg.n_chr = n_chr; cfg.n_phen = n_phen; cfg.vt_type = opt.vt_type;
+    cfg.device = opt.device + rank; cfg.n_pop = n_pop; cfg.n_chr = n_loc; cfg.n_phen = n_phen; cfg.vt_type = opt.vt_type;
     cfg.representation = (opt.out_hap ? GE_REP_BITS : 0) | ((opt.out_interval || !opt.out_hap) ? GE_REP_SEGMENTS : 0);
-    cfg.rng_mode = GE_RNG_PHILOX; cfg.seed = opt.seed; cfg.capacity = cap; cfg.rank = 0; cfg.world_size = 1;
+    cfg.rng_mode = GE_RNG_PHILOX; cfg.seed = opt.seed; cfg.capacity = cap; cfg.rank = rank; cfg.world_size = world;
     if (ge_create(&cfg, &ctx) != GE_OK) return gfail("ge_create");
+    if (world > 1) {
+        std::vector<int32_t> ids(mine.begin(), mine.end());
+        if (ge_set_chromosome_ids(ctx, ids.data()) != GE_OK) return gfail("ge_set_chromosome_ids");
+        if (ge_set_allreduce(ctx, &HostSimulation::allreduce_hook, this) != GE_OK) return gfail("ge_set_allreduce");
+    }
     if (ge_set_gamma(ctx, opt.gamma.data()) != GE_OK) return gfail("ge_set_gamma");
-    for (int c = 0; c < n_chr && need_panel; c++)
-        if (ge_set_loci(ctx, c, in[0].legend_pos[c].data(), in[0].legend_pos[c].size()) != GE_OK) return gfail("ge_set_loci");
+    for (int k = 0; k < n_loc && need_panel; k++)
+        if (ge_set_loci(ctx, k, in[0].legend_pos[mine[k]].data(), in[0].legend_pos[mine[k]].size()) != GE_OK) return gfail("ge_set_loci");
     for (int p = 0; p < n_pop; p++) {
         const PopOptions &O = opt.pop[p];
         PopInputs &I = in[p];
         if (ge_set_population(ctx, p, opt.avoid_inbreeding, O.RM, O.MM) != GE_OK) return gfail("ge_set_population");
-        for (int c = 0; c < n_chr; c++) {
+        for (int k = 0; k < n_loc; k++) {
+            const int c = mine[k];
             const GeneticMap &m = I.rmap[c];
-            if (ge_set_genetic_map(ctx, p, c, m.bp.data(), m.recom_prob.data(), m.bp.size(), m.bp_dist) != GE_OK) return gfail("ge_set_genetic_map");
+            if (ge_set_genetic_map(ctx, p, k, m.bp.data(), m.recom_prob.data(), m.bp.size(), m.bp_dist) != GE_OK) return gfail("ge_set_genetic_map");
             if (!I.mutmap.empty() && !I.mutmap[c].bp.empty() &&
-                ge_set_mutation_map(ctx, p, c, I.mutmap[c].bp.data(), I.mutmap[c].rate.data(), I.mutmap[c].bp.size()) != GE_OK) return gfail("ge_set_mutation_map");
+                ge_set_mutation_map(ctx, p, k, I.mutmap[c].bp.data(), I.mutmap[c].rate.data(), I.mutmap[c].bp.size()) != GE_OK) return gfail("ge_set_mutation_map");
             for (int f = 0; f < n_phen; f++) {
                 const CvBlock &b = I.cv[f][c];
-                if (ge_set_cv(ctx, p, f, c, b.bp.data(), b.a.data(), b.d.data(), b.bp.size(), b.val.data(), b.n_hap) != GE_OK) return gfail("ge_set_cv");
+                if (ge_set_cv(ctx, p, f, k, b.bp.data(), b.a.data(), b.d.data(), b.bp.size(), b.val.data(), b.n_hap) != GE_OK) return gfail("ge_set_cv");
             }
             if (need_panel) {
                 uint64_t nh = 0;
@@ -429,7 +463,7 @@ bool HostSimulation::upload() {
                 std::vector<uint32_t> words;
                 if (!opt.quiet) std::cout << "    reading founder panel [" << I.chrs[c].hap << "]" << std::endl;
                 if (!read_hap_packed(I.chrs[c].hap, nh, I.legend_pos[c].size(), words, err)) return false;
-                if (ge_set_founder_panel_packed(ctx, p, c, words.data(), nh) != GE_OK) return gfail("ge_set_founder_panel_packed");
+                if (ge_set_founder_panel_packed(ctx, p, k, words.data(), nh) != GE_OK) return gfail("ge_set_founder_panel_packed");
             }
         }
         for (int f = 0; f < n_phen; f++)
@@ -538,7 +572,7 @@ bool HostSimulation::write_info(int pop, int gen) {  // Population::ras_save_hum
 }
 
 bool HostSimulation::after_generation(int gen) {
-    for (int p = 0; p < n_pop; p++) {
+    for (int p = 0; p < n_pop && rank == 0; p++) {   // every rank holds identical per-individual columns: rank 0 reports
         if (!write_info(p, gen)) return false;
         SummaryRow r;
         r.m.resize(n_phen);
@@ -590,12 +624,13 @@ bool HostSimulation::write_genotypes(int gen) {
         ge_indiv_soa s = {};
         s.ids = ids.data();
         if (ge_download_individuals(ctx, p, &s) != GE_OK) return gfail("ge_download_individuals");
-        for (int c = 0; c < n_chr; c++) {
+        for (int k = 0; k < (int)mine.size(); k++) {   // each rank writes the files of its own chromosomes
+            const int c = mine[k];
             std::string base = opt.prefix + ".pop" + std::to_string(p + 1) + ".gen" + std::to_string(gen) + ".chr" + std::to_string(in[0].chrs[c].chr);
             if (opt.out_hap) {  // ras_write_hap_legend_sample :1142-1182 -> format_hap::write_hap / write_indv (src/format_hap.cpp:6-53)
                 uint64_t ns = in[0].legend_pos[c].size();
                 std::vector<uint8_t> m(2 * n * ns);
-                if (ge_download_haplotypes(ctx, p, c, m.data()) != GE_OK) return gfail("ge_download_haplotypes");
+                if (ge_download_haplotypes(ctx, p, k, m.data()) != GE_OK) return gfail("ge_download_haplotypes");
                 std::ofstream o((base + ".hap").c_str());
                 if (!o) return fail("Error: can not open the file [" + base + ".hap] to write.");
                 std::string line(2 * 2 * n, ' ');
@@ -608,9 +643,9 @@ bool HostSimulation::write_genotypes(int gen) {
             }
             if (opt.out_interval) {  // ras_write_hap_to_interval_format :1582-1639
                 uint64_t nseg = 0, nmut = 0;
-                if (ge_get_segment_count(ctx, p, c, &nseg, &nmut) != GE_OK) return gfail("ge_get_segment_count");
+                if (ge_get_segment_count(ctx, p, k, &nseg, &nmut) != GE_OK) return gfail("ge_get_segment_count");
                 std::vector<uint64_t> off(2 * n + 1), seg(4 * std::max<uint64_t>(nseg, 1));
-                if (ge_download_segments(ctx, p, c, off.data(), seg.data(), nullptr, nullptr) != GE_OK) return gfail("ge_download_segments");
+                if (ge_download_segments(ctx, p, k, off.data(), seg.data(), nullptr, nullptr) != GE_OK) return gfail("ge_download_segments");
                 std::ofstream o((base + ".int").c_str());
                 if (!o) return fail("Error: can not open the file [" + base + ".int] to write.");
                 o << "h_ID chr hap st en hap_index gen0_indv root_pop" << std::endl;
@@ -660,7 +695,7 @@ bool HostSimulation::run() {
         info_writer->finish();
         if (!info_writer->error.empty()) return fail(info_writer->error);
     }
-    bool ok = write_summary();
+    bool ok = rank != 0 || write_summary();
     lap("finishing the output files");
     return ok;
 }

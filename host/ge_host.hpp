@@ -39,7 +39,7 @@ struct Options {
     std::vector<PopOptions> pop;
     std::vector<double> gamma;
     std::string file_migration, file_output_generations, prefix = "out";
-    int vt_type = 1, device = 0;
+    int vt_type = 1, device = 0, gpus = 1;   // --gpus N: chromosomes are spread over devices device .. device+N-1
     bool avoid_inbreeding = false, out_hap = false, out_interval = false, quiet = false, help = false;
     uint64_t seed = 0;
     std::string error;
@@ -75,12 +75,26 @@ bool read_output_generations(const std::string &path, std::vector<int> &out, std
 
 class InfoWriter;  // background formatter/writer of the per-generation .info files (ge_host.cpp)
 
+// Sum-allreduce between the per-GPU contexts of one run (the library's only exchange step, ge_set_allreduce).  The
+// product binary links the NCCL implementation (ge_collective_nccl.cpp); the CPU tests of the host link a
+// thread-barrier implementation over host buffers.
+class Collective {
+public:
+    virtual ~Collective() {}
+    virtual bool init(int world, int first_device, std::string &err) = 0;   // once, before the rank threads start
+    virtual int allreduce_sum(int rank, double *buf, uint64_t count, void *stream) = 0;
+    virtual void abort() = 0;                                               // a rank failed: release the others
+};
+Collective *make_collective();
+
 class HostSimulation {
 public:
-    explicit HostSimulation(const Options &o);
+    explicit HostSimulation(const Options &o, int rank = 0, int world = 1, Collective *coll = nullptr);
     ~HostSimulation();
     bool run();                       // Simulation::run
     const std::string &error() const { return err; }
+    // longest-processing-time assignment of chromosomes (weights: map span in bp) to ranks
+    static std::vector<std::vector<int>> assign_chromosomes(const std::vector<double> &weight, int world);
 
 private:
     Options opt;
@@ -89,6 +103,10 @@ private:
     std::vector<int> output_generations;
     ge_ctx *ctx = nullptr;
     std::unique_ptr<InfoWriter> info_writer;
+    int rank = 0, world = 1;
+    Collective *coll = nullptr;
+    std::vector<int> mine;            // global indices of the chromosomes this rank owns (all of them when world == 1)
+    static int allreduce_hook(void *user, double *buf, uint64_t count, void *stream);
     int n_pop = 0, n_chr = 0, n_phen = 0, tot_gen = 0;
     bool need_panel = false;
     std::string err;

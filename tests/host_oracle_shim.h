@@ -7,6 +7,8 @@
 #define ge_create go_create
 #define ge_destroy go_destroy
 #define ge_set_gamma go_set_gamma
+#define ge_set_chromosome_ids go_set_chromosome_ids
+#define ge_set_allreduce go_set_allreduce
 #define ge_set_loci go_set_loci
 #define ge_set_population go_set_population
 #define ge_set_genetic_map go_set_genetic_map

@@ -31,7 +31,7 @@ def oracle_cli():
     from oracle import oracle
     oracle.lib()
     out = os.path.join(HERE, "_build", "host_oracle_cli")
-    srcs = [os.path.join(ROOT, "host", f) for f in ("main.cpp", "ge_host.cpp")]
+    srcs = [os.path.join(ROOT, "host", f) for f in ("main.cpp", "ge_host.cpp")] + [os.path.join(HERE, "host_thread_collective.cpp")]
     deps = srcs + [os.path.join(ROOT, "host", "ge_host.hpp"), os.path.join(HERE, "host_oracle_shim.h"), oracle.LIB]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -174,6 +174,41 @@ def test_host_cli_two_populations_on_oracle(tmp_path):
 @pytest.mark.gpu
 def test_host_cli_two_populations_on_gpu(tmp_path):
     check_two_populations(product_cli(), tmp_path)
+
+
+def check_multi_gpu(cli, tmp_path):
+    """--gpus 2 (chromosome shards, one context per device, sum-allreduce of the partial genetic values) must write
+    the same files as --gpus 1: genotype and segment files byte for byte, per-individual columns to 1e-9."""
+    sc, args = scenario(tmp_path, 3)
+    outs = {}
+    for g in (1, 2):
+        pre = str(tmp_path / f"g{g}")
+        r = subprocess.run([cli] + args + ["--seed", "11", "--prefix", pre, "--out_hap", "--out_interval", "--quiet", "--gpus", str(g)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[g] = sorted(f[len(f"g{g}"):] for f in os.listdir(tmp_path) if f.startswith(f"g{g}."))
+    assert outs[1] == outs[2] and len(outs[1]) == 4 + 1 + 3 * len(sc["chrs"])
+    for suffix in outs[1]:
+        a, b = str(tmp_path / ("g1" + suffix)), str(tmp_path / ("g2" + suffix))
+        if suffix.endswith((".hap", ".int", ".indv")):
+            assert open(a, "rb").read() == open(b, "rb").read(), suffix
+        else:
+            with open(a) as fa, open(b) as fb:
+                assert fa.readline() == fb.readline()
+            np.testing.assert_allclose(np.loadtxt(a, skiprows=1), np.loadtxt(b, skiprows=1), rtol=1e-5, atol=1e-6, err_msg=suffix)
+    r = subprocess.run([cli] + args + ["--gpus", "7", "--prefix", str(tmp_path / "e")], capture_output=True, text=True)
+    assert r.returncode == 255 and ("exceeds the number of chromosomes" in r.stdout or "cannot set up the collective" in r.stdout)
+
+
+def test_host_cli_multi_gpu_on_oracle(tmp_path):
+    check_multi_gpu(oracle_cli(), tmp_path)
+
+
+@pytest.mark.gpu
+def test_host_cli_multi_gpu_on_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    check_multi_gpu(product_cli(), tmp_path)
 
 
 def test_host_cli_on_oracle(tmp_path):
