@@ -269,6 +269,35 @@ def test_full_size_rows_agree_with_cv_planes(cuda_lib):
     assert np.isfinite(ind["P"]).all() and 0.3 < np.var(ind["A"][0]) / np.var(ind["P"][0]) < 0.7
 
 
+def test_north_star_target_hundred_generations(cuda_lib):
+    """The north-star run itself — 100 000 individuals x 1 000 000 loci x 100 generations, assortative mating rho = 0.4 with
+    logit selection — must finish in seconds and still satisfy the two-path invariant at generation 100: rows read at
+    the causal loci equal the causal-variant planes (any single wrong run boundary in any of the 100 copies of any
+    ancestor would break it for that lineage)."""
+    import time
+    eng, cfg = full_size_engine(cuda_lib)
+    gp = [capi.gen_params(cfg["n"], cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
+    eng.synchronize()
+    t0 = time.perf_counter()
+    for g in range(1, 101):
+        eng.step_generation(g, gp)
+    eng.synchronize()
+    wall = time.perf_counter() - t0
+    assert wall < 5.0, f"100 generations took {wall:.2f} s"
+    n = eng.population_size(0)
+    assert abs(n - cfg["n"]) < 6 * np.sqrt(cfg["n"])
+    for c in (len(cfg["chrs"]) - 1, 7):
+        words = eng.haplotypes_packed(0, c)
+        idx = cfg["cvs"][c]["idx"].astype(np.int64)
+        at_cv = ((words[:, idx // 32] >> (idx % 32).astype(np.uint32)) & 1).astype(np.uint8)
+        assert np.array_equal(at_cv, eng.cv_alleles(0, 0, c)), f"chromosome index {c} after 100 generations"
+    ind = eng.individuals(0)
+    assert np.isfinite(ind["P"]).all() and np.array_equal(ind["ids"][:, 0], np.arange(n, dtype=np.uint64))
+    h2 = np.var(ind["A"][0]) / np.var(ind["P"][0])
+    assert 0.2 < h2 < 0.8 and abs(np.var(ind["E"][0], ddof=1) - 0.5) < 1e-9     # var(E) is rescaled to ve exactly every generation (:3167-3180)
+    print(f"north-star target: 100 generations of {cfg['n']} x {sum(cfg['n_loci'])} in {wall:.2f} s ({wall * 10:.2f} ms per generation), h2 = {h2:.3f}")
+
+
 def test_full_width_rows_are_verbatim_parental_copies_without_recombination(cuda_lib):
     """20k x 1M with every recombination probability zero: each offspring row equals the drawn parental row."""
     eng, cfg = full_size_engine(cuda_lib, zero_recombination=True, n=20000)
