@@ -341,6 +341,12 @@ class Engine:
         self._call("download_cv_alleles", self.ctx, pop, phen, chr_, _ptr(out, _u8p))
         return out
 
+    def compact_segments(self, pop):
+        """Merges adjacent same-founder parts (extension, see the header); returns (parts before, parts after)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._call("compact_segments", self.ctx, pop, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def recompute_cv_from_segments(self, pop):
         self._call("recompute_cv_from_segments", self.ctx, pop)
 

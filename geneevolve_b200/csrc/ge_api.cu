@@ -1093,6 +1093,13 @@ int ge_download_cv_alleles(ge_ctx *ctx, int pop, int f, int c, uint8_t *out) {
     return GE_OK;
 }
 
+int ge_compact_segments(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_after) {
+    CHECK_POP(ctx, pop);
+    if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_compact_segments needs GE_REP_SEGMENTS");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return seg_compact(ctx, pop, n_before, n_after);
+}
+
 int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop) {  // ras_find_cv :2752-2815 literally: scan the parts of every haplotype
     CHECK_POP(ctx, pop);
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_recompute_cv_from_segments needs GE_REP_SEGMENTS");

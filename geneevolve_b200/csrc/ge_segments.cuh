@@ -236,6 +236,34 @@ __global__ void seg_materialise_kernel(Genome g, int c, uint64_t n_rows, const u
 
 }  // namespace gek
 
+namespace gek {
+// Segment compaction (the documentation's limitation #2: lists only ever grow because the reference never
+// merges): adjacent parts of one haplotype that continue the same founder haplotype (en == next st, same hap_index and
+// root population) become one part.  Zero-length parts disappear into their neighbour or are dropped when they carry
+// no length of their own.  The materialised haplotype is unchanged; the `.int` listing is no longer the reference's.
+// One thread per haplotype slot; pass 0 counts, pass 1 writes.
+template <bool FILL>
+__global__ void seg_compact_kernel(uint64_t n_slots, const uint64_t *__restrict__ off, const uint4 *__restrict__ seg, uint32_t *__restrict__ count,
+                                   const uint64_t *__restrict__ new_off, uint4 *__restrict__ out) {
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e0 = off[slot], e1 = off[slot + 1];
+        uint4 *o = FILL ? out + new_off[slot] : nullptr;
+        uint32_t n = 0;
+        bool open = false;
+        uint4 cur = make_uint4(0, 0, 0, 0);
+        for (uint64_t e = e0; e < e1; e++) {
+            const uint4 q = seg[e];
+            if (q.x == q.y && e1 - e0 > 1) continue;                       // zero-length part: covers no locus
+            if (open && q.x == cur.y && q.z == cur.z && q.w == cur.w) { cur.y = q.y; continue; }
+            if (open) { if (FILL) o[n] = cur; n++; }
+            cur = q; open = true;
+        }
+        if (open) { if (FILL) o[n] = cur; n++; }
+        if (!FILL) count[slot] = n;
+    }
+}
+}  // namespace gek
+
 static void seg_release(SegState &s) {
     for (Buf *b : {&s.off, &s.seg}) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     s.valid = false;
@@ -337,6 +365,29 @@ static int seg_materialise(ge_ctx *ctx, int pop, int c, uint8_t *d_alleles) {
     GE_TRY(ctx->check_launch("seg_materialise"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->release(tbl);
+    return GE_OK;
+}
+
+static int seg_compact(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_after) {
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur], &O = P.st[P.cur ^ 1];   // the other generation's buffers are free between generations
+    if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists (GE_REP_SEGMENTS not enabled)");
+    const uint64_t n_slots = S.n * ctx->cfg.n_chr * 2;
+    if (n_before) *n_before = S.seg.n_seg;
+    GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
+    GE_TRY(ctx->ensure(O.seg.off, (n_slots + 1) * 8));
+    const unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n_slots, 128)), (uint64_t)ctx->n_sm * 64);
+    seg_compact_kernel<false><<<grid, 128, 0, ctx->stream>>>(n_slots, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.cnt32.as<uint32_t>(), nullptr, nullptr);
+    GE_TRY(ctx->check_launch("seg_compact<count>"));
+    uint64_t n_new = 0;
+    GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, O.seg.off.as<uint64_t>(), &n_new));
+    GE_TRY(ctx->ensure(O.seg.seg, std::max<uint64_t>(n_new, 1) * 16));
+    seg_compact_kernel<true><<<grid, 128, 0, ctx->stream>>>(n_slots, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), nullptr, O.seg.off.as<uint64_t>(), O.seg.seg.as<uint4>());
+    GE_TRY(ctx->check_launch("seg_compact<fill>"));
+    std::swap(S.seg.off, O.seg.off); std::swap(S.seg.seg, O.seg.seg);
+    S.seg.n_seg = n_new;
+    O.seg.valid = false;
+    if (n_after) *n_after = n_new;
     return GE_OK;
 }
 

@@ -29,6 +29,7 @@ const char *Options::usage() {
            "    per phenotype: --file_cv_info F --file_cvs F [--va x --vd x --vc x --ve x --vf x --omega x --beta x --lambda x]\n"
            "  global: [--gamma x]... [--file_migration F] [--vt_type 1|2] [--avoid_inbreeding] [--seed n] [--prefix P]\n"
            "          [--out_hap] [--out_interval] [--file_output_generations F] [--device n] [--gpus N] [--quiet]\n"
+           "          [--compact_segments]  (extension: merge adjacent same-founder segments after every generation)\n"
            "  not on this path (rejected): --file_ref_vcf --out_plink --out_plink01 --out_vcf\n";
 }
 
@@ -74,6 +75,7 @@ bool Options::parse(const std::vector<std::string> &a) {
         else if (f == "--file_output_generations") file_output_generations = need(i);
         else if (f == "--device") device = (int)num(i);
         else if (f == "--gpus") gpus = (int)num(i);
+        else if (f == "--compact_segments") compact_segments = true;
         else if (f == "--quiet") quiet = true;
         else if (f == "--debug") {}
         else if (f == "--help" || f == "-h" || f == "?") help = true;
@@ -688,6 +690,10 @@ bool HostSimulation::run() {
             gp[p].selection_func = r.selection_func; gp[p].selection_par1 = r.par1; gp[p].selection_par2 = r.par2;
         }
         if (ge_step_generation(ctx, gen, gp.data(), n_pop > 1 ? migration[gen - 1].data() : nullptr, nullptr) != GE_OK) return gfail("ge_step_generation");
+#ifndef GE_HOST_NO_COMPACT
+        if (opt.compact_segments && (opt.out_interval || !opt.out_hap))
+            for (int p = 0; p < n_pop; p++) if (ge_compact_segments(ctx, p, nullptr, nullptr) != GE_OK) return gfail("ge_compact_segments");
+#endif
         if (!after_generation(gen)) return false;
     }
     lap("the main body of simulation");

@@ -41,6 +41,7 @@ struct Options {
     std::string file_migration, file_output_generations, prefix = "out";
     int vt_type = 1, device = 0, gpus = 1;   // --gpus N: chromosomes are spread over devices device .. device+N-1
     bool avoid_inbreeding = false, out_hap = false, out_interval = false, quiet = false, help = false;
+    bool compact_segments = false;           // extension (ge_compact_segments): the .int output is then not the reference's
     uint64_t seed = 0;
     std::string error;
     bool parse(const std::vector<std::string> &args);  // false + error on a bad command line

@@ -212,6 +212,11 @@ int ge_download_segments(ge_ctx *ctx, int pop, int chr, uint64_t *seg_off, uint6
                          uint64_t *mut_off /* [2*n+1] per haplotype */, uint64_t *mut_bp);
 /* Causal-variant alleles, the `--debug` .cvval dump (:2665-2683): out[(i*2+h)*n_cv + k]. */
 int ge_download_cv_alleles(ge_ctx *ctx, int pop, int phen, int chr, uint8_t *out);
+/* Extension beyond the reference (GeneEvolveDocumentation.pdf p.52, limitation #2: segment lists only
+ * grow): merge adjacent parts of a haplotype that continue the same founder haplotype and drop zero-length parts.
+ * The materialised haplotypes, causal-variant alleles and all values are unchanged; ge_download_segments then returns
+ * the merged lists, which are no longer the reference's `.int` content.  n_before / n_after may be NULL. */
+int ge_compact_segments(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_after);
 /* Verification aid (GE_REP_SEGMENTS): rebuild the causal-variant planes of the current generation by scanning every
  * haplotype's parts exactly like ras_find_cv (:2752-2815).  The hot path never does this — it carries the planes
  * forward by crossover parity — so the planes before and after this call must be identical. */

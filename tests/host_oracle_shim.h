@@ -2,6 +2,7 @@
  * against the CPU oracle instead of the CUDA library, so that the host's readers, writers and generation loop can be
  * exercised without a GPU.  The product binary (host/Makefile) never sees this file. */
 #include "../oracle/ge_oracle.h"
+#define GE_HOST_NO_COMPACT /* the oracle restates the reference, which never merges segments */
 #define ge_ctx go_ctx
 #define ge_last_error go_last_error
 #define ge_create go_create

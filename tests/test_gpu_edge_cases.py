@@ -315,3 +315,38 @@ def test_full_width_rows_are_verbatim_parental_copies_without_recombination(cuda
         src_f = 2 * d["father"].astype(np.int64) + d["start_hap"][slot]
         src_m = 2 * d["mother"].astype(np.int64) + d["start_hap"][slot + 1]
         assert np.array_equal(kids[0::2], parents[src_f]) and np.array_equal(kids[1::2], parents[src_m])
+
+
+def test_segment_compaction_preserves_haplotypes(cuda_lib):
+    """ge_compact_segments (extension): two segment-only contexts on the same Philox streams, one compacted
+    after every generation.  A small closed population drifts towards few founders, so adjacent same-founder parts and
+    zero-length parts do occur; materialised haplotypes, CV alleles and phenotypes must stay identical, the lists shrink,
+    and a second compaction changes nothing."""
+    case = Case(77, [400, 150], n_founders=8, map_rows=30, step=64)
+    case.maps = [(bp, np.concatenate([[0.0], np.full(len(bp) - 1, 0.08)]), step) for bp, _, step in case.maps]
+    kw = case.kwargs(80, rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_SEGMENTS)
+    plain, packed = capi.Engine(cuda_lib, **kw), capi.Engine(cuda_lib, **kw)
+    for e in (plain, packed):
+        case.configure(e)
+        e.set_population(0, False, True, 0.0)
+        e.init_generation0()
+    shrunk = 0
+    for g in range(1, 13):
+        gp = [capi.gen_params(30, 0.0, "p", "thr", 1, 1)]
+        plain.step_generation(g, gp)
+        packed.step_generation(g, gp)
+        before, after = packed.compact_segments(0)
+        assert after <= before and packed.compact_segments(0) == (after, after)
+        shrunk += before - after
+        for c in range(2):
+            assert np.array_equal(plain.haplotypes(0, c), packed.haplotypes(0, c)), f"gen {g} chr {c}"
+            assert np.array_equal(plain.cv_alleles(0, 0, c), packed.cv_alleles(0, 0, c))
+            s = packed.segments(0, c)
+            seg, off = s["seg"], s["seg_off"]
+            for r in range(len(off) - 1):     # still a contiguous tiling, no mergeable neighbours left
+                q = seg[off[r]:off[r + 1]]
+                assert np.all(q[1:, 0] == q[:-1, 1]) and not np.any((q[1:, 2] == q[:-1, 2]) & (q[1:, 3] == q[:-1, 3]))
+        a, b = plain.individuals(0), packed.individuals(0)
+        for k in "ADGEP":
+            assert np.array_equal(a[k], b[k])
+    assert shrunk > 0
