@@ -163,8 +163,10 @@ constexpr int PROP_SMEM_FLIPS = 384;   // flips of one offspring staged in share
 // dynamic shared memory: uint64 xo_off[2*n_chr+1] | uint32 flips[PROP_SMEM_FLIPS] | uint8 start[2*n_chr]
 static inline size_t prop_smem_bytes(int n_chr) { return (size_t)(2 * n_chr + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((2 * n_chr + 15) & ~15); }
 
-// 32 registers -> 8 CTAs (64 warps) per SM for DEPTH 4: measured 1.4 % faster than 40 registers / 6 CTAs on the same box
-template <int DEPTH, int MINB = (DEPTH == 8 ? 3 : 8)>
+// PREFETCH issues the two loads of a crossover chunk before the run copy that precedes it.  Same-box measurements on
+// config 3 (kernel alone / pipelined step): 40 registers, 6 CTAs/SM with prefetch 6.55 / 7.67 ms (default); 32 registers,
+// 8 CTAs/SM without prefetch 6.85 / 7.74 ms; 32 registers with prefetch spills and loses (6.95 / 8.02 ms).
+template <int DEPTH, int MINB = (DEPTH == 8 ? 3 : 6), bool PREFETCH = (DEPTH == 4)>
 __global__ void __launch_bounds__(PROP_THREADS, MINB)
 propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, uint32_t *__restrict__ off_rows,
                       const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
@@ -220,11 +222,14 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
                 const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
                 const uint32_t qb = f >> 7;
                 if (j >= k || qb >= q1) { warp_copy_chunks<DEPTH>(dst, cur ? h1 : h0, q, q1, lane); break; }
-                warp_copy_chunks<DEPTH>(dst, cur ? h1 : h0, q, qb, lane);
                 // chunk qb holds one or more flips: merge both parental chunks under a 128-bit mask
                 // (mask bit = 1 -> haplotype 1).  A flip on the chunk's first locus gives bit offset 0.
+                // Its two loads are issued before the run that precedes it, so their latency hides behind that copy.
+                uint4 a = make_uint4(0, 0, 0, 0), b = a;
+                if (PREFETCH && lane == 0) { a = ld_stream(h0 + qb); b = ld_stream(h1 + qb); }
+                warp_copy_chunks<DEPTH>(dst, cur ? h1 : h0, q, qb, lane);
                 if (lane == 0) {
-                    const uint4 a = ld_stream(h0 + qb), b = ld_stream(h1 + qb);
+                    if (!PREFETCH) { a = ld_stream(h0 + qb); b = ld_stream(h1 + qb); }
                     const uint32_t fill = cur ? 0xFFFFFFFFu : 0u;
                     uint32_t m0 = fill, m1 = fill, m2 = fill, m3 = fill;
                     const uint32_t base = qb << 7;
