@@ -138,7 +138,7 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int DEPTH>
+template <int DEPTH, bool TAIL_BATCHED = true>
 __device__ __forceinline__ void warp_copy_chunks(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint32_t q, uint32_t qe, int lane) {
     uint32_t c = q + lane;
     if (DEPTH == 8) {  // eight independent 16-byte loads in flight per lane: the same bytes in flight per SM with half the warps
@@ -154,7 +154,21 @@ __device__ __forceinline__ void warp_copy_chunks(uint4 *__restrict__ dst, const 
         uint4 a = ld_stream(src + c), b = ld_stream(src + c + 32), d = ld_stream(src + c + 64), e = ld_stream(src + c + 96);
         st_stream(dst + c, a); st_stream(dst + c + 32, b); st_stream(dst + c + 64, d); st_stream(dst + c + 96, e);
     }
-    for (; c < qe; c += 32) st_stream(dst + c, ld_stream(src + c));
+    if (TAIL_BATCHED) {
+        // the remainder (the mean run between crossovers is about one such iteration long): all of a lane's loads are issued
+        // before its first store, so the tail costs one memory latency instead of one per 512 bytes
+        if (c < qe) {
+            const bool p1 = c + 32 < qe, p2 = c + 64 < qe;
+            uint4 a = ld_stream(src + c), b = a, d = a;
+            if (p1) b = ld_stream(src + c + 32);
+            if (p2) d = ld_stream(src + c + 64);
+            st_stream(dst + c, a);
+            if (p1) st_stream(dst + c + 32, b);
+            if (p2) st_stream(dst + c + 64, d);
+        }
+    } else {
+        for (; c < qe; c += 32) st_stream(dst + c, ld_stream(src + c));
+    }
 }
 
 constexpr int PROP_THREADS = 256;
@@ -166,7 +180,7 @@ static inline size_t prop_smem_bytes(int n_chr) { return (size_t)(2 * n_chr + 1)
 // PREFETCH issues the two loads of a crossover chunk before the run copy that precedes it.  Same-box measurements on
 // config 3 (kernel alone / pipelined step): 40 registers, 6 CTAs/SM with prefetch 6.55 / 7.67 ms (default); 32 registers,
 // 8 CTAs/SM without prefetch 6.85 / 7.74 ms; 32 registers with prefetch spills and loses (6.95 / 8.02 ms).
-template <int DEPTH, int MINB = (DEPTH == 8 ? 3 : 6), bool PREFETCH = (DEPTH == 4)>
+template <int DEPTH, int MINB = (DEPTH == 8 ? 3 : 6), bool PREFETCH = (DEPTH == 4), bool TAIL_BATCHED = true>
 __global__ void __launch_bounds__(PROP_THREADS, MINB)
 propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, uint32_t *__restrict__ off_rows,
                       const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
@@ -221,13 +235,13 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
             while (q < q1) {
                 const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
                 const uint32_t qb = f >> 7;
-                if (j >= k || qb >= q1) { warp_copy_chunks<DEPTH>(dst, cur ? h1 : h0, q, q1, lane); break; }
+                if (j >= k || qb >= q1) { warp_copy_chunks<DEPTH, TAIL_BATCHED>(dst, cur ? h1 : h0, q, q1, lane); break; }
                 // chunk qb holds one or more flips: merge both parental chunks under a 128-bit mask
                 // (mask bit = 1 -> haplotype 1).  A flip on the chunk's first locus gives bit offset 0.
                 // Its two loads are issued before the run that precedes it, so their latency hides behind that copy.
                 uint4 a = make_uint4(0, 0, 0, 0), b = a;
                 if (PREFETCH && lane == 0) { a = ld_stream(h0 + qb); b = ld_stream(h1 + qb); }
-                warp_copy_chunks<DEPTH>(dst, cur ? h1 : h0, q, qb, lane);
+                warp_copy_chunks<DEPTH, TAIL_BATCHED>(dst, cur ? h1 : h0, q, qb, lane);
                 if (lane == 0) {
                     if (!PREFETCH) { a = ld_stream(h0 + qb); b = ld_stream(h1 + qb); }
                     const uint32_t fill = cur ? 0xFFFFFFFFu : 0u;
