@@ -122,3 +122,65 @@ def test_gpu_heterozygosity_decay_at_the_documented_scale(cuda_lib):
             # Wright-Fisher drift predicts Var(H_t) ~ (dH/dp)^2 Var(p_t) = 4 (1 - 2p)^2 p q * sum 1/(2 N_k)
             mse, expect = np.mean((h - theory * h0) ** 2), np.mean(4 * (1 - 2 * q0) ** 2 * q0 * (1 - q0)) * drift
             assert 0.7 * expect < mse < 1.3 * expect and mse < 3e-4, (gen, mse, expect)
+
+
+@pytest.mark.gpu
+def test_gpu_ld_decay_follows_the_genetic_map(cuda_lib):
+    """LD decay versus genetic distance against theory (doc §3.4 recipe, here with a closed form instead of PLINK): under
+    random mating D_t(x, y) = D_0(x, y) (1 - c_xy)^t (1 - 1/2N)^t, where c_xy is the recombination fraction between the two
+    SNPs under the law the sampler implements — row j of the map fires with probability p_j and its crossover lands
+    uniformly in [bp_j, bp_j + bp_dist) (the reference's position/probability offset).  The b37-shaped
+    chr22 map has hot and cold spots, so rates AND positions of the crossovers have to be right for the binned regression
+    slopes of D_t on D_0 to follow the prediction."""
+    from geneevolve_b200 import workloads
+    N, n_snp, n_founders = 20000, 1500, 2000
+    rng = np.random.default_rng(2204)
+    (bp, cm, p), = workloads.genetic_map([22])
+    dist = int(bp[1] - bp[0])
+    pos = np.sort(rng.choice(np.arange(int(bp[1]), int(bp[-2])), size=n_snp, replace=False)).astype(np.uint64)
+    anc = (rng.uniform(size=(8, n_snp)) < rng.uniform(0.25, 0.75, n_snp)[None, :]).astype(np.uint8)
+    panel = np.zeros((2 * n_founders, n_snp), np.uint8)
+    for h in range(2 * n_founders):                      # mosaics of 8 ancestral haplotypes in blocks of 100-200 SNPs: long-range LD
+        s = 0
+        while s < n_snp:
+            L = int(rng.integers(100, 200))
+            panel[h, s:s + L] = anc[rng.integers(0, 8), s:s + L]
+            s += L
+    cv_idx = np.sort(rng.choice(n_snp, size=40, replace=False))
+    eng = capi.Engine(cuda_lib, n_pop=1, n_chr=1, n_phen=1, seed=414, capacity=N + 64, rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS)
+    eng.set_loci(0, pos)
+    eng.set_population(0, False, True, 0.0)
+    eng.set_genetic_map(0, 0, bp, p, dist)
+    eng.set_founder_panel(0, 0, panel)
+    eng.set_cv(0, 0, 0, pos[cv_idx], rng.normal(size=40), np.zeros(40), panel[:, cv_idx])
+    eng.set_pheno_scheme(0, 0, va=0.5, vd=0.0, ve=0.5)
+    eng.init_generation0()
+
+    def ld():
+        w = eng.haplotypes_packed(0, 0)
+        x = np.unpackbits(w.view(np.uint8), axis=1, bitorder="little")[:, :n_snp].astype(np.float32)
+        x -= x.mean(axis=0, keepdims=True)
+        return (x.T @ x / x.shape[0]).astype(np.float64)
+
+    # expected crossovers between consecutive SNPs: row j contributes p_j * |[bp_j, bp_j + dist) ∩ (x, y]| / dist
+    edges = np.concatenate([[0.0], np.cumsum(p)])         # cumulative rate at the START of each row's landing interval, spread uniformly over it
+    def cum_rate(x):                                      # expected number of crossovers at positions <= x
+        j = np.clip((x.astype(np.int64) - int(bp[0])) // dist, 0, len(bp) - 1)
+        frac = np.clip((x.astype(np.float64) - bp[j].astype(np.float64)) / dist, 0.0, 1.0)
+        return edges[j] + p[j] * frac
+    lam = np.abs(cum_rate(pos)[:, None] - cum_rate(pos)[None, :])
+    c = 0.5 * (1.0 - np.exp(-2.0 * lam))                  # Haldane: odd number of (near-Poisson) crossovers
+    iu = np.triu_indices(n_snp, k=1)
+    D0 = ld()[iu]
+    gp = [capi.gen_params(N, 0.0, "p", "thr", 1, 1)]
+    bins = [0.0, 0.005, 0.02, 0.05, 0.1]
+    for gen in range(1, 21):
+        eng.step_generation(gen, gp)
+        if gen in (10, 20):
+            Dt = ld()[iu]
+            for lo, hi in zip(bins[:-1], bins[1:]):
+                m = (c[iu] >= lo) & (c[iu] < hi) & (np.abs(D0) > 0.02)
+                assert m.sum() > 500
+                slope = np.sum(Dt[m] * D0[m]) / np.sum(D0[m] ** 2)
+                expect = np.sum(D0[m] ** 2 * (1 - c[iu][m]) ** gen) / np.sum(D0[m] ** 2) * (1 - 1 / (2 * N)) ** gen
+                assert abs(slope - expect) < 0.02, (gen, lo, hi, slope, expect)
