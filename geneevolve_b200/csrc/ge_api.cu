@@ -184,7 +184,11 @@ static int build_cvset(ge_ctx *ctx) {
     ctx->cv_sorted = true;
     for (int b = 0; b < nf * C; b++)
         for (uint32_t k = ctx->cv_block_off[b] + 1; k < ctx->cv_block_off[b + 1]; k++) if (bp[k] < bp[k - 1]) ctx->cv_sorted = false;
-    GE_TRY(ctx->ensure(ctx->d_LA, (size_t)std::max<uint32_t>(ctx->n_cv_tot, 1) * 24)); GE_TRY(ctx->ensure(ctx->d_LD, (size_t)std::max<uint32_t>(ctx->n_cv_tot, 1) * 24));
+    GE_TRY(ctx->ensure(ctx->d_LA, (size_t)std::max<uint32_t>(ctx->n_cv_tot, 1) * 48));
+    std::vector<uint32_t> bitpos(ctx->n_cv_tot);
+    for (int b = 0; b < nf * C; b++)
+        for (uint32_t k = ctx->cv_block_off[b]; k < ctx->cv_block_off[b + 1]; k++) bitpos[k] = ctx->cv_word_off[b] * 32 + (k - ctx->cv_block_off[b]);
+    GE_TRY(ctx->upload(ctx->d_cv_bitpos, bitpos));
     GE_TRY(ctx->upload(ctx->d_cv_word_off, ctx->cv_word_off)); GE_TRY(ctx->upload(ctx->d_cv_word_blk, word_blk));
     std::vector<double> a_eff((size_t)np * ctx->n_cv_tot), d_eff((size_t)np * ctx->n_cv_tot);
     for (int p = 0; p < np; p++)
@@ -285,7 +289,7 @@ int ge_destroy(ge_ctx *ctx) {
         }
         mate_release(P.mate);
     }
-    for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_bkt_off, &ctx->d_bkt_shift, &ctx->d_bkt, &ctx->d_LA, &ctx->d_LD, &ctx->xo_stash, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
+    for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_bkt_off, &ctx->d_bkt_shift, &ctx->d_bkt, &ctx->d_LA, &ctx->d_cv_bitpos, &ctx->xo_stash, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
                    &ctx->d_cv_block_off, &ctx->d_cv_word_off, &ctx->d_cv_word_blk, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks,
                    &ctx->scan_total, &ctx->partial, &ctx->scalars, &ctx->flags, &ctx->d_chr_ids, &ctx->ar_scratch})
         freeb(*b);
@@ -402,9 +406,9 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
     uint64_t nw = S.n * ctx->cfg.n_phen;
     if (ctx->cfg.n_pop == 1 && ncv) {
         cv_tables_kernel<<<nblk(ncv, 128), 128, 0, ctx->stream>>>(ctx->cvset(), ctx->d_cv_count.as<unsigned long long>(), S.n, ctx->d_a_eff.as<double>(),
-                                                                  ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), ctx->d_LA.as<double>(), ctx->d_LD.as<double>());
+                                                                  ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), ctx->d_LA.as<double2>());
         GE_TRY(ctx->check_launch("cv_tables"));
-        genetic_value_lut_kernel<<<ctx->ctrl_grid(nw * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_LA.as<double>(), ctx->d_LD.as<double>(), S.n,
+        genetic_value_lut_kernel<<<ctx->ctrl_grid(nw * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_cv_bitpos.as<uint32_t>(), ctx->d_LA.as<double2>(), S.n,
                                                                               S.A.as<double>(), S.D.as<double>(), S.G.as<double>(), ctx->flags.as<int>());
         GE_TRY(ctx->check_launch("genetic_value_lut"));
     } else {

@@ -169,7 +169,7 @@ struct ge_ctx {
     std::vector<uint32_t> cv_word_off;   // [n_phen*n_chr+1]
     uint32_t n_cv_tot = 0, Wcv = 4;
     bool cv_sorted = true;
-    Buf d_LA, d_LD, xo_stash;
+    Buf d_LA /* double2 [n_cv][3] */, d_cv_bitpos, xo_stash;
     Buf d_cv_word_off, d_cv_word_blk, d_cv_block_off, d_cv_bp, d_cv_chr, d_a_eff, d_d_eff, d_cv_count;
     bool cv_ready = false;
     // scratch

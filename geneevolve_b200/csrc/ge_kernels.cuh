@@ -694,10 +694,10 @@ __global__ void genetic_value_kernel(CvSet cs, const uint32_t *__restrict__ bits
 }
 
 // One population: the per-CV terms do not depend on the individual, so they are tabulated once per generation —
-// LA[k][t] = (t - 2p) * alpha, LD[k][t] = c_t * d for genotype t in {0,1,2} (the very products of :2691-2712) —
-// and the per-individual kernel only gathers and adds them in the same order as genetic_value_kernel.
+// LAD[k][t] = {(t - 2p) * alpha, c_t * d} for genotype t in {0,1,2} (the very products of :2691-2712) —
+// and the per-individual kernel only gathers and adds them.
 __global__ void cv_tables_kernel(CvSet cs, const unsigned long long *__restrict__ count, uint64_t n_count, const double *__restrict__ a_eff,
-                                 const double *__restrict__ d_eff, const uint8_t *__restrict__ vd_zero, double *__restrict__ LA, double *__restrict__ LD) {
+                                 const double *__restrict__ d_eff, const uint8_t *__restrict__ vd_zero, double2 *__restrict__ LAD) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cs.n_cv_tot) return;
     int blk = 0;
@@ -709,29 +709,28 @@ __global__ void cv_tables_kernel(CvSet cs, const unsigned long long *__restrict_
     double p = (double)count[k] / two_n, q = 1 - p;
     double alpha = a + d * (q - p);
     for (int t = 0; t < 3; t++) {
-        LA[k * 3 + t] = ((double)t - 2 * p) * alpha;
         double ct = t == 0 ? -2 * p * p : (t == 1 ? 2 * p * q : -2 * q * q);
-        LD[k * 3 + t] = ct * d;
+        LAD[k * 3 + t] = make_double2(((double)t - 2 * p) * alpha, ct * d);
     }
 }
-__global__ void genetic_value_lut_kernel(CvSet cs, const uint32_t *__restrict__ bits, const double *__restrict__ LA, const double *__restrict__ LD,
+// Lanes stride the CVs of the phenotype as one flat list (bitpos[k] = position of CV k in the bit row, LAD[k][t] =
+// {LA, LD} in one 16-byte load), so there is no per-chromosome bookkeeping and every lane has the same trip count.
+__global__ void genetic_value_lut_kernel(CvSet cs, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ bitpos, const double2 *__restrict__ LAD,
                                          uint64_t n, double *__restrict__ A, double *__restrict__ D, double *__restrict__ Gv, int *__restrict__ nan_flag) {
     const int lane = threadIdx.x & 31;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < n * cs.n_phen; wid += n_warps) {
-        uint64_t i = wid % n;
-        int f = (int)(wid / n);
+        const uint64_t i = wid % n;
+        const int f = (int)(wid / n);
         const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
+        const uint32_t k1 = cs.block_off[(f + 1) * cs.n_chr];
         double Ac = 0, Dc = 0;
-        for (int c = 0; c < cs.n_chr; c++) {
-            const int blk = f * cs.n_chr + c;
-            const uint32_t b0 = cs.block_off[blk], b1 = cs.block_off[blk + 1], wo = cs.word_off[blk];
-            for (uint32_t k = b0 + lane; k < b1; k += 32) {
-                const uint32_t j = k - b0;
-                const unsigned t = ((al0[wo + (j >> 5)] >> (j & 31)) & 1u) + ((al1[wo + (j >> 5)] >> (j & 31)) & 1u);
-                Ac += LA[k * 3 + t];
-                Dc += LD[k * 3 + t];
-            }
+        for (uint32_t k = cs.block_off[f * cs.n_chr] + lane; k < k1; k += 32) {
+            const uint32_t bp = __ldg(bitpos + k), w = bp >> 5, b = bp & 31u;
+            const unsigned t = ((al0[w] >> b) & 1u) + ((al1[w] >> b) & 1u);
+            const double2 v = __ldg(LAD + k * 3 + t);
+            Ac += v.x;
+            Dc += v.y;
         }
         for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
         if (lane == 0) {
