@@ -96,7 +96,8 @@ class Draws:
 
 
 def default_library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgeneevolve_b200.so")
+    # GE_LIBRARY: measurement aid — another build of the same CUDA library (A/B runs on one box)
+    return os.environ.get("GE_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgeneevolve_b200.so")
 
 
 def load_library(path=None):

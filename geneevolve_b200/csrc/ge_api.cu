@@ -18,6 +18,7 @@ static int alloc_gen_state(ge_ctx *ctx, GenState &s) {
     int nf = ctx->cfg.n_phen;
     if (ctx->bits()) GE_TRY(ctx->ensure_exact(s.hap, (size_t)cap * 2 * ctx->W * 4));
     GE_TRY(ctx->ensure_exact(s.cv_allele, (size_t)cap * 2 * ctx->Wcv * 4));
+    CUDA_TRY(cudaMemsetAsync(s.cv_allele.p, 0, (size_t)cap * 2 * ctx->Wcv * 4, ctx->stream));   // padding words stay zero
     if (ctx->cfg.n_pop > 1) GE_TRY(ctx->ensure_exact(s.cv_root, (size_t)cap * 2 * std::max<uint32_t>(ctx->n_cv_tot, 1)));
     GE_TRY(ctx->ensure_exact(s.ids, (size_t)cap * 7 * 8));
     GE_TRY(ctx->ensure_exact(s.sex, (size_t)cap));
