@@ -180,6 +180,8 @@ def ours(args):
         return gdist.bench_sharded(args, METRIC, UNIT)
     torch.cuda.set_device(local)
     cfg = workloads.make_workload(args.workload, n_override=args.n, loci_override=args.loci)
+    if "pops" in cfg:
+        raise SystemExit("multi-population workloads run chromosome-sharded: launch with torchrun (config 4 needs >= 4 GPUs at full size)")
     M, N = sum(cfg["n_loci"]), cfg["n"]
     cap = int(max(N, cfg["founders"]) * 1.03) + 1024
     segs = bool(cfg.get("segments"))

@@ -19,7 +19,7 @@ static int alloc_gen_state(ge_ctx *ctx, GenState &s) {
     if (ctx->bits()) GE_TRY(ctx->ensure_exact(s.hap, (size_t)cap * 2 * ctx->W * 4));
     GE_TRY(ctx->ensure_exact(s.cv_allele, (size_t)cap * 2 * ctx->Wcv * 4));
     CUDA_TRY(cudaMemsetAsync(s.cv_allele.p, 0, (size_t)cap * 2 * ctx->Wcv * 4, ctx->stream));   // padding words stay zero
-    if (ctx->cfg.n_pop > 1) GE_TRY(ctx->ensure_exact(s.cv_root, (size_t)cap * 2 * std::max<uint32_t>(ctx->n_cv_tot, 1)));
+    if (ctx->use_root) GE_TRY(ctx->ensure_exact(s.cv_root, (size_t)cap * 2 * std::max<uint32_t>(ctx->n_cv_tot, 1)));
     GE_TRY(ctx->ensure_exact(s.ids, (size_t)cap * 7 * 8));
     GE_TRY(ctx->ensure_exact(s.sex, (size_t)cap));
     for (Buf *b : {&s.A, &s.D, &s.G, &s.C, &s.E, &s.F, &s.P}) {
@@ -207,6 +207,12 @@ static int build_cvset(ge_ctx *ctx) {
     GE_TRY(ctx->upload(ctx->d_cv_block_off, ctx->cv_block_off));
     GE_TRY(ctx->upload(ctx->d_cv_bp, bp)); GE_TRY(ctx->upload(ctx->d_cv_chr, chr_of));
     GE_TRY(ctx->upload(ctx->d_a_eff, a_eff)); GE_TRY(ctx->upload(ctx->d_d_eff, d_eff));
+    // ras_find_cv takes a, d from the ROOT population of each allele (:2776-2786); that only matters when the populations'
+    // effect tables differ — otherwise no root plane is carried and the tabulated single-population path applies
+    ctx->use_root = false;
+    for (int p = 1; p < np && !ctx->use_root; p++)
+        for (uint32_t k = 0; k < ctx->n_cv_tot; k++)
+            if (a_eff[(size_t)p * ctx->n_cv_tot + k] != a_eff[k] || d_eff[(size_t)p * ctx->n_cv_tot + k] != d_eff[k]) { ctx->use_root = true; break; }
     GE_TRY(ctx->ensure(ctx->d_cv_count, (size_t)std::max<uint32_t>(ctx->n_cv_tot, 1) * 8));
     ctx->cv_ready = true;
     return GE_OK;
@@ -280,6 +286,7 @@ int ge_destroy(ge_ctx *ctx) {
         for (Buf *b : {&P.d_row_off, &P.d_bp, &P.d_T, &P.d_bp_dist, &P.d_mrow_off, &P.d_mbp, &P.d_mT, &P.d_vb, &P.d_vb_off, &P.d_vb_scale, &P.d_mvb, &P.d_mvb_off, &P.d_mvb_scale, &P.d_cov_lo, &P.d_cov_hi, &P.d_omega,
                        &P.d_lambda, &P.d_vd_zero, &P.prev_P, &P.prev_F, &P.c_male, &P.c_female, &P.c_inbreed, &P.c_noff, &P.mut_off, &P.mut_bp, &P.mut_gam, &P.e_raw, &P.cnt32, &P.d_sv0, &P.founder_rows, &P.founder_cv})
             freeb(*b);
+        freeb(P.mig_pop[0]); freeb(P.mig_idx[0]); freeb(P.rowmap_buf[0]); freeb(P.rowmap_buf[1]);
         for (DrawSet &D : P.ds) {
             for (Buf *b : {&D.father, &D.mother, &D.couple_of, &D.xo_off, &D.xo_bp, &D.flips, &D.start_hap}) freeb(*b);
             cudaEventDestroy(D.bulk_done);
@@ -302,6 +309,8 @@ int ge_destroy(ge_ctx *ctx) {
         cudaEventDestroy(l.done); cudaStreamDestroy(l.s);
     }
     cudaEventDestroy(ctx->ev_fork);
+    for (int q = 0; q < 2; q++) { for (Buf &b : ctx->mig_lists[q]) freeb(b); if (ctx->mig_done[q]) cudaEventDestroy(ctx->mig_done[q]); }
+    freeb(ctx->mig_stage);
     cudaStreamDestroy(ctx->bulk);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -405,7 +414,7 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
         GE_TRY(ctx->check_launch("cv_count"));
     }
     uint64_t nw = S.n * ctx->cfg.n_phen;
-    if (ctx->cfg.n_pop == 1 && ncv) {
+    if (!ctx->use_root && ncv) {
         cv_tables_kernel<<<nblk(ncv, 128), 128, 0, ctx->stream>>>(ctx->cvset(), ctx->d_cv_count.as<unsigned long long>(), S.n, ctx->d_a_eff.as<double>(),
                                                                   ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), ctx->d_LA.as<double2>());
         GE_TRY(ctx->check_launch("cv_tables"));
@@ -414,7 +423,7 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
         GE_TRY(ctx->check_launch("genetic_value_lut"));
     } else {
         genetic_value_kernel<<<nblk(nw * 32, 256), 256, 0, ctx->stream>>>(
-            ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.n,
+            ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.n,
             ctx->d_a_eff.as<double>(), ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), S.n, S.A.as<double>(), S.D.as<double>(), S.G.as<double>(),
             ctx->flags.as<int>());
         GE_TRY(ctx->check_launch("genetic_value"));
@@ -638,7 +647,7 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
         CUDA_TRY(cudaMemcpyAsync(tmp.p, fcv.data(), fcv.size(), cudaMemcpyHostToDevice, ctx->stream));
         uint64_t tot = (uint64_t)2 * n * ctx->Wcv;
         cv_init_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), tmp.as<uint8_t>(), (uint32_t)(2 * n), P.d_cov_lo.as<uint32_t>(), P.d_cov_hi.as<uint32_t>(),
-                                                                (uint8_t)p, S.cv_allele.as<uint32_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr);
+                                                                (uint8_t)p, S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr);
         GE_TRY(ctx->check_launch("cv_init"));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ctx->release(tmp_local);
@@ -885,13 +894,13 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         if (ctx->use_tma) {
             size_t sm = prop_tma_smem_bytes(C);
             if (!ctx->tma_attr_set) { CUDA_TRY(cudaFuncSetAttribute(propagate_bits_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); ctx->tma_attr_set = true; }
-            propagate_bits_tma_kernel<<<grid, TMA_WARPS * 32 + TMA_MERGE_THREADS, sm, bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+            propagate_bits_tma_kernel<<<grid, TMA_WARPS * 32 + TMA_MERGE_THREADS, sm, bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), par.rowmap, off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
                                                                          D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
         } else if (ctx->prop_depth == 8)
-        propagate_bits_kernel<8><<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+        propagate_bits_kernel<8><<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), par.rowmap, off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
                                                                     D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
         else
-        propagate_bits_kernel<4><<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+        propagate_bits_kernel<4><<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), par.rowmap, off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
                                                                     D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
         GE_TRY(ctx->check_launch("propagate_bits"));
         if (ctx->profiling) {
@@ -913,7 +922,7 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         cv_propagate_bits_kernel<<<ctx->ctrl_grid(tot, 256), 256, 0, st>>>(ctx->cvset(), par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
                                                                  D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, n_off);
         GE_TRY(ctx->check_launch("cv_propagate_bits"));
-        if (ctx->cfg.n_pop > 1) {
+        if (ctx->use_root) {
             uint64_t tr = n_off * 2 * ctx->n_cv_tot;
             cv_root_propagate_kernel<<<nblk(tr, 256), 256, 0, st>>>(ctx->cvset(), par.cv_root.as<uint8_t>(), off.cv_root.as<uint8_t>(), D.father.as<uint32_t>(), D.mother.as<uint32_t>(),
                                                                     D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, n_off);
@@ -947,6 +956,7 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
     pedigree_kernel<<<nblk(n_off, 256), 256, 0, st>>>(0, n_off, D.father.as<uint32_t>(), D.mother.as<uint32_t>(), par.ids.as<uint64_t>(), off.ids.as<uint64_t>());
     GE_TRY(ctx->check_launch("pedigree"));
     off.n = n_off;
+    off.rowmap = nullptr;   // a fresh generation is written in identity order
     P.cur ^= 1;
     if (dr) CUDA_TRY(cudaStreamSynchronize(st));  // caller buffers were read asynchronously
     return GE_OK;
@@ -1043,7 +1053,8 @@ int ge_download_haplotypes(ge_ctx *ctx, int pop, int c, uint8_t *al) {
     GE_TRY(ctx->ensure_exact(tmp, tot));
     if (ctx->bits()) {
         GE_TRY(ctx->join_bulk());
-        unpack_rows_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), ctx->W, ctx->chr_word_off[c], (uint32_t)(2 * S.n), nl, tmp.as<uint8_t>());
+        unpack_rows_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), S.rowmap, ctx->W, ctx->chr_word_off[c], (uint32_t)(2 * S.n), nl,
+                                                                    tmp.as<uint8_t>());
         GE_TRY(ctx->check_launch("unpack_rows"));
     } else GE_TRY(seg_materialise(ctx, pop, c, tmp.as<uint8_t>()));
     CUDA_TRY(cudaMemcpyAsync(al, tmp.p, tot, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1062,7 +1073,8 @@ int ge_download_haplotypes_packed(ge_ctx *ctx, int pop, int c, uint32_t *words) 
     Buf tmp;
     GE_TRY(ctx->ensure_exact(tmp, tot * 4));
     GE_TRY(ctx->join_bulk());
-    gather_packed_chr_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), ctx->W, ctx->chr_word_off[c], (uint32_t)(2 * S.n), nw, tmp.as<uint32_t>());
+    gather_packed_chr_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), S.rowmap, ctx->W, ctx->chr_word_off[c], (uint32_t)(2 * S.n), nw,
+                                                                      tmp.as<uint32_t>());
     GE_TRY(ctx->check_launch("gather_packed"));
     CUDA_TRY(cudaMemcpyAsync(words, tmp.p, tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -63,6 +63,7 @@ struct CvHost {  // one (phen, chr) block of one population
 struct GenState {  // one generation of one population on the device
     uint64_t n = 0;
     Buf hap, cv_allele /* bit plane [2n][Wcv] */, cv_root /* byte plane [2n][n_cv_tot], n_pop > 1 only */, ids, sex, A, D, G, C, E, F, P, mv, sv, svf;
+    const uint32_t *rowmap = nullptr;   // after a migration: physical row pair of every individual (PopDev::rowmap_buf); identity otherwise
     Buf hm_off, hm_bp;  // per-haplotype mutation lists (CSR over slots)
     uint64_t n_hm = 0;
     bool has_hm = false;
@@ -96,6 +97,8 @@ struct PopDev {
     GenState st[2];
     int cur = 0;
     Buf prev_P, prev_F;
+    Buf mig_pop[1], mig_idx[1];                 // gather lists of a migration (control stream only)
+    Buf rowmap_buf[2];                          // row maps of the last two migrations (by generation parity; the bulk stream reads them late)
     uint64_t prev_n = 0;
     // couples
     Buf c_male, c_female, c_inbreed, c_noff;
@@ -153,6 +156,9 @@ struct ge_ctx {
     std::vector<std::vector<uint64_t>> mig_sample;  // fixed-draw mode: migrants per source population
     std::vector<uint32_t> chr_ids;                  // global chromosome index of each local chromosome
     Buf d_chr_ids, ar_scratch;
+    Buf mig_lists[2][5], mig_stage;             // row moves of the last two migrations (the bulk stream reads them late) + staging rows
+    cudaEvent_t mig_done[2] = {nullptr, nullptr};
+    bool mig_pending[2] = {false, false};
     ge_allreduce_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
     Stream rng;
@@ -169,6 +175,7 @@ struct ge_ctx {
     std::vector<uint32_t> cv_word_off;   // [n_phen*n_chr+1]
     uint32_t n_cv_tot = 0, Wcv = 4;
     bool cv_sorted = true;
+    bool use_root = false;   // populations with different effect tables: carry the root population of every CV allele
     Buf d_LA /* double2 [n_cv][3] */, d_cv_bitpos, xo_stash;
     Buf d_cv_word_off, d_cv_word_blk, d_cv_block_off, d_cv_bp, d_cv_chr, d_a_eff, d_d_eff, d_cv_count;
     bool cv_ready = false;

@@ -182,7 +182,7 @@ static inline size_t prop_smem_bytes(int n_chr) { return (size_t)(2 * n_chr + 1)
 // 8 CTAs/SM without prefetch 6.85 / 7.74 ms; 32 registers with prefetch spills and loses (6.95 / 8.02 ms).
 template <int DEPTH, int MINB = (DEPTH == 8 ? 3 : 6), bool PREFETCH = (DEPTH == 4), bool TAIL_BATCHED = true>
 __global__ void __launch_bounds__(PROP_THREADS, MINB)
-propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, uint32_t *__restrict__ off_rows,
+propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, const uint32_t *__restrict__ par_rowmap, uint32_t *__restrict__ off_rows,
                       const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                       const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips,
                       const uint8_t *__restrict__ start_hap, uint64_t off_first, uint32_t n_off) {
@@ -207,7 +207,8 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
         const uint32_t n_fl = (uint32_t)(s_off[n_ls] - e_base);
         const bool staged = n_fl <= PROP_SMEM_FLIPS;
         if (staged) for (uint32_t t = threadIdx.x; t < n_fl; t += PROP_THREADS) s_fl[t] = flips[e_base + t];
-        const uint32_t pf = father[i], pm = mother[i];
+        // after a migration the parents' rows are not in logical order: par_rowmap gives the physical row pair
+        const uint32_t pf = par_rowmap ? par_rowmap[father[i]] : father[i], pm = par_rowmap ? par_rowmap[mother[i]] : mother[i];
         __syncthreads();
         for (;;) {
             uint32_t item = 0;
@@ -353,7 +354,7 @@ __device__ __forceinline__ void tma_copy_run(TmaRing &r, const uint4 *src, uint4
 }
 
 __global__ void __launch_bounds__(TMA_WARPS * 32 + TMA_MERGE_THREADS)
-propagate_bits_tma_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, uint32_t *__restrict__ off_rows,
+propagate_bits_tma_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, const uint32_t *__restrict__ par_rowmap, uint32_t *__restrict__ off_rows,
                           const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                           const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips,
                           const uint8_t *__restrict__ start_hap, uint64_t off_first, uint32_t n_off) {
@@ -391,7 +392,8 @@ propagate_bits_tma_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ p
         const uint32_t n_fl = (uint32_t)(s_off[n_ls] - e_base);
         const bool staged = n_fl <= PROP_SMEM_FLIPS;
         if (staged) for (uint32_t t = threadIdx.x; t < n_fl; t += blockDim.x) s_fl[t] = flips[e_base + t];
-        const uint32_t pf = father[i], pm = mother[i];
+        // after a migration the parents' rows are not in logical order: par_rowmap gives the physical row pair
+        const uint32_t pf = par_rowmap ? par_rowmap[father[i]] : father[i], pm = par_rowmap ? par_rowmap[mother[i]] : mother[i];
         __syncthreads();
         if (warp >= TMA_WARPS) {
             // merge threads: every chunk that holds a crossover is a mask-merge of both parental chunks (mask bit = 1 ->
@@ -503,19 +505,21 @@ __global__ void mask_packed_panel_kernel(const uint32_t *__restrict__ words, uin
     rows[(uint64_t)r * W + woff + w] = words[t] & m;
 }
 
-__global__ void unpack_rows_kernel(const uint32_t *__restrict__ rows, uint32_t W, uint32_t woff, uint32_t n_rows,
+__global__ void unpack_rows_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ rowmap, uint32_t W, uint32_t woff, uint32_t n_rows,
                                    uint32_t n_loci, uint8_t *__restrict__ alleles) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint64_t)n_rows * n_loci) return;
     uint32_t r = (uint32_t)(t / n_loci), s = (uint32_t)(t % n_loci);
+    if (rowmap) r = rowmap[r >> 1] * 2 + (r & 1);   // logical haplotype row -> physical row (after a migration)
     alleles[t] = (rows[(uint64_t)r * W + woff + (s >> 5)] >> (s & 31)) & 1u;
 }
 
-__global__ void gather_packed_chr_kernel(const uint32_t *__restrict__ rows, uint32_t W, uint32_t woff, uint32_t n_rows,
+__global__ void gather_packed_chr_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ rowmap, uint32_t W, uint32_t woff, uint32_t n_rows,
                                          uint32_t nw, uint32_t *__restrict__ out) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (uint64_t)n_rows * nw) return;
     uint32_t r = (uint32_t)(t / nw), w = (uint32_t)(t % nw);
+    if (rowmap) r = rowmap[r >> 1] * 2 + (r & 1);
     out[t] = rows[(uint64_t)r * W + woff + w];
 }
 

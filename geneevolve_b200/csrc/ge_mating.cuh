@@ -312,15 +312,23 @@ namespace gek {
 constexpr int MAX_POP = 16;
 struct PopPtrs { const void *p[MAX_POP]; uint64_t n[MAX_POP]; };
 
-__global__ void gather_rows_kernel(PopPtrs src, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst,
-                                   uint32_t rows_per_ind, uint32_t row_words, uint32_t *__restrict__ dst) {
-    // one CTA per destination row
-    uint64_t r = blockIdx.x;
-    if (r >= n_dst * rows_per_ind) return;
-    uint64_t k = r / rows_per_ind; uint32_t sub = (uint32_t)(r % rows_per_ind);
-    const uint32_t *s = static_cast<const uint32_t *>(src.p[gpop[k]]) + ((uint64_t)gidx[k] * rows_per_ind + sub) * row_words;
-    uint32_t *d = dst + r * row_words;
-    for (uint32_t w = threadIdx.x; w < row_words; w += blockDim.x) d[w] = s[w];
+// Moves the two bit-packed rows of migrant m from (spop[m], row pair sidx[m]) to (dpop[m], row pair didx[m]); one CTA per
+// row (rows are multiples of 128 bytes): streaming 16-byte copies, four in flight per thread.
+__global__ void move_rows_kernel(PopPtrs src, const uint8_t *__restrict__ spop, const uint32_t *__restrict__ sidx, PopPtrs dst,
+                                 const uint8_t *__restrict__ dpop, const uint32_t *__restrict__ didx, uint64_t n_moves, uint32_t row_words) {
+    for (uint64_t r = blockIdx.x; r < n_moves * 2; r += gridDim.x) {
+        const uint64_t m = r >> 1;
+        const uint32_t h = (uint32_t)(r & 1);
+        const uint4 *s = reinterpret_cast<const uint4 *>(static_cast<const uint32_t *>(src.p[spop ? spop[m] : 0]) + ((uint64_t)sidx[m] * 2 + h) * row_words);
+        uint4 *d = reinterpret_cast<uint4 *>(static_cast<uint32_t *>(const_cast<void *>(dst.p[dpop ? dpop[m] : 0])) + ((uint64_t)didx[m] * 2 + h) * row_words);
+        const uint32_t nq = row_words / 4;
+        uint32_t c = threadIdx.x;
+        for (; c + 3 * blockDim.x < nq; c += 4 * blockDim.x) {
+            uint4 a = ld_stream(s + c), b = ld_stream(s + c + blockDim.x), e = ld_stream(s + c + 2 * blockDim.x), f = ld_stream(s + c + 3 * blockDim.x);
+            st_stream(d + c, a); st_stream(d + c + blockDim.x, b); st_stream(d + c + 2 * blockDim.x, e); st_stream(d + c + 3 * blockDim.x, f);
+        }
+        for (; c < nq; c += blockDim.x) st_stream(d + c, ld_stream(s + c));
+    }
 }
 __global__ void gather_bytes_kernel(PopPtrs src, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst,
                                     uint32_t bytes_per_ind, uint8_t *__restrict__ dst) {
@@ -376,7 +384,13 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
     if (np > MAX_POP) return fail(GE_ERR_UNSUPPORTED, "too many populations");
     if (!row) return fail(GE_ERR_INVALID, "null migration row");
     cudaStream_t st = ctx->stream;
-    GE_TRY(ctx->join_bulk());  // whole individuals move, haplotype rows included
+    // Whole individuals move.  Everything the control chain needs (per-individual columns, causal-variant planes, lists)
+    // is gathered into the other generation buffer on the control stream.  The bit-packed rows are NOT re-packed (that
+    // would be a second full pass over the generation): stayers keep their physical rows, each incoming migrant's two
+    // rows are copied — through a staging buffer, on the bulk stream, behind the copy that still produces them — into a
+    // row pair vacated by an emigrant (or appended), and a per-individual row map (logical position -> physical row
+    // pair) is handed to the next propagation, whose offspring are written in identity order again.
+    const int par = gen & 1;
     std::vector<std::vector<uint64_t>> num_move(np, std::vector<uint64_t>(np, 0));
     for (int i = 0; i < np; i++) {
         double s = 0;
@@ -436,19 +450,17 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
         PopDev &P = ctx->pop[j];
         GenState &D = P.st[P.cur ^ 1];
         uint64_t n = gp[j].size();
-        Buf d_gp, d_gi;
+        Buf &d_gp = P.mig_pop[0], &d_gi = P.mig_idx[0];   // read on the control stream only
         GE_TRY(ctx->upload(d_gp, gp[j])); GE_TRY(ctx->upload(d_gi, gi[j]));
         const uint8_t *g8 = d_gp.as<uint8_t>(); const uint32_t *g32 = d_gi.as<uint32_t>();
         if (n) {
-            if (ctx->bits()) {
-                gather_rows_kernel<<<(unsigned)(n * 2), 256, 0, st>>>(table([](GenState &S) { return S.hap.p; }), g8, g32, n, 2, ctx->W, D.hap.as<uint32_t>());
-                GE_TRY(ctx->check_launch("gather_rows"));
-            }
             if (ctx->n_cv_tot) {
                 gather_bytes_kernel<<<nblk(n * 8 * ctx->Wcv, 256), 256, 0, st>>>(table([](GenState &S) { return S.cv_allele.p; }), g8, g32, n, 8 * ctx->Wcv, D.cv_allele.as<uint8_t>());
                 GE_TRY(ctx->check_launch("gather_cv"));
-                gather_bytes_kernel<<<nblk(n * 2 * ctx->n_cv_tot, 256), 256, 0, st>>>(table([](GenState &S) { return S.cv_root.p; }), g8, g32, n, 2 * ctx->n_cv_tot, D.cv_root.as<uint8_t>());
-                GE_TRY(ctx->check_launch("gather_cv_root"));
+                if (ctx->use_root) {
+                    gather_bytes_kernel<<<nblk(n * 2 * ctx->n_cv_tot, 256), 256, 0, st>>>(table([](GenState &S) { return S.cv_root.p; }), g8, g32, n, 2 * ctx->n_cv_tot, D.cv_root.as<uint8_t>());
+                    GE_TRY(ctx->check_launch("gather_cv_root"));
+                }
             }
             gather_bytes_kernel<<<nblk(n * 56, 256), 256, 0, st>>>(table([](GenState &S) { return S.ids.p; }), g8, g32, n, 56, D.ids.as<uint8_t>());
             GE_TRY(ctx->check_launch("gather_ids"));
@@ -484,8 +496,56 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
             D.seg.valid = true;
         }
         D.n = n;
-        CUDA_TRY(cudaStreamSynchronize(st));
-        ctx->release(d_gp); ctx->release(d_gi);
+    }
+    if (ctx->bits()) {
+        for (int j = 0; j < np; j++)
+            if (ctx->pop[j].st[ctx->pop[j].cur].rowmap) return fail(GE_ERR_INVALID, "two migrations without a generation in between");
+        // physical placement of the rows: row map per destination, move list over all populations
+        std::vector<uint8_t> m_spop, m_dpop;
+        std::vector<uint32_t> m_sidx, m_didx, m_stage;
+        for (int j = 0; j < np; j++) {
+            PopDev &P = ctx->pop[j];
+            GenState &D = P.st[P.cur ^ 1];
+            std::vector<uint64_t> vacated(sample[j].rbegin(), sample[j].rend());   // ascending positions of the emigrants
+            size_t next_free = 0;
+            uint64_t next_new = n_old[j];
+            std::vector<uint32_t> rowmap(gp[j].size());
+            for (size_t k = 0; k < gp[j].size(); k++) {
+                if (gp[j][k] == j) { rowmap[k] = gi[j][k]; continue; }
+                uint32_t slot = next_free < vacated.size() ? (uint32_t)vacated[next_free++] : (uint32_t)next_new++;
+                rowmap[k] = slot;
+                m_stage.push_back((uint32_t)m_spop.size());
+                m_spop.push_back(gp[j][k]); m_sidx.push_back(gi[j][k]); m_dpop.push_back((uint8_t)j); m_didx.push_back(slot);
+            }
+            if (next_new > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "population outgrew capacity through migration");
+            // the map of generation g-2 in this slot was read by the propagation of generation g-1 (the previous draw set)
+            DrawSet &prev = P.ds[P.dcur ^ 1];
+            if (prev.bulk_pending) CUDA_TRY(cudaStreamWaitEvent(st, prev.bulk_done, 0));
+            GE_TRY(ctx->upload(P.rowmap_buf[par], rowmap));
+            D.rowmap = P.rowmap_buf[par].as<uint32_t>();
+        }
+        const uint64_t n_moves = m_spop.size();
+        if (n_moves) {
+            cudaStream_t bulk = ctx->serial ? st : ctx->bulk;
+            if (ctx->mig_pending[par]) { CUDA_TRY(cudaStreamWaitEvent(st, ctx->mig_done[par], 0)); ctx->mig_pending[par] = false; }
+            if (!ctx->mig_done[par]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->mig_done[par], cudaEventDisableTiming));
+            Buf *mb = ctx->mig_lists[par];
+            GE_TRY(ctx->upload(mb[0], m_spop)); GE_TRY(ctx->upload(mb[1], m_sidx)); GE_TRY(ctx->upload(mb[2], m_dpop)); GE_TRY(ctx->upload(mb[3], m_didx));
+            GE_TRY(ctx->upload(mb[4], m_stage));
+            GE_TRY(ctx->ensure(ctx->mig_stage, n_moves * 2 * (size_t)ctx->W * 4));
+            CUDA_TRY(cudaEventRecord(ctx->ev_ready, st));           // the lists are on the device
+            CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_ready, 0));
+            PopPtrs rows = table([](GenState &S) { return S.hap.p; }), stage{};
+            stage.p[0] = ctx->mig_stage.p;
+            const unsigned grid = (unsigned)std::min<uint64_t>(n_moves * 2, 1u << 20);
+            move_rows_kernel<<<grid, 256, 0, bulk>>>(rows, mb[0].as<uint8_t>(), mb[1].as<uint32_t>(), stage, nullptr, mb[4].as<uint32_t>(), n_moves, ctx->W);
+            GE_TRY(ctx->check_launch("move_rows<stage>"));
+            move_rows_kernel<<<grid, 256, 0, bulk>>>(stage, nullptr, mb[4].as<uint32_t>(), rows, mb[2].as<uint8_t>(), mb[3].as<uint32_t>(), n_moves, ctx->W);
+            GE_TRY(ctx->check_launch("move_rows<place>"));
+            CUDA_TRY(cudaEventRecord(ctx->mig_done[par], bulk));
+            ctx->mig_pending[par] = true;
+        }
+        for (int j = 0; j < np; j++) { PopDev &P = ctx->pop[j]; std::swap(P.st[P.cur].hap, P.st[P.cur ^ 1].hap); }   // the rows stay where they are
     }
     for (int j = 0; j < np; j++) ctx->pop[j].cur ^= 1;
     ctx->mig_sample.clear();

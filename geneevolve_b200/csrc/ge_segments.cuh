@@ -345,7 +345,7 @@ static int seg_find_cv(ge_ctx *ctx, int pop) {
     uint64_t tot = 2 * S.n * ctx->Wcv;
     seg_find_cv_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(),
                                                                 S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
-                                                                tbl.as<const uint8_t *>(), S.cv_allele.as<uint32_t>(), ctx->cfg.n_pop > 1 ? S.cv_root.as<uint8_t>() : nullptr);
+                                                                tbl.as<const uint8_t *>(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr);
     GE_TRY(ctx->check_launch("seg_find_cv"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->release(tbl);

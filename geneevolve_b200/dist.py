@@ -75,21 +75,27 @@ def bench_sharded(args, METRIC, UNIT):
         raise SystemExit("workload has fewer chromosomes than ranks")
     mine = assign_chromosomes(cfg["n_loci"], world)[rank]
     M, N = sum(cfg["n_loci"]), cfg["n"]
-    cap = int(max(N, cfg["founders"]) * 1.03) + 1024
-    eng = capi.Engine(n_pop=1, n_chr=len(mine), n_phen=1, device=local, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX,
+    pops = cfg.get("pops", [N])
+    n_phen = cfg.get("n_phen", 1)
+    cap = int(max(max(pops), cfg["founders"]) * (1.03 if len(pops) == 1 else 1.10)) + 1024   # migration moves ~2 % either way
+    eng = capi.Engine(n_pop=len(pops), n_chr=len(mine), n_phen=n_phen, device=local, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX,
                       seed=12345, capacity=cap, rank=rank, world_size=world)
-    workloads.configure_engine(eng, cfg, chrs_local=mine)
+    if len(pops) > 1:
+        workloads.configure_engine_multipop(eng, cfg, chrs_local=mine)
+    else:
+        workloads.configure_engine(eng, cfg, chrs_local=mine)
     eng.set_allreduce(cuda_allreduce_hook(local))
     eng.init_generation0()
-    gp = [capi.gen_params(N, cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
+    gp = [capi.gen_params(n, cfg["mat_cor"], "p", "logit", 0.0, 1.0) for n in pops]
+    mig = cfg.get("migration")
     gen = 0
     for _ in range(args.warmup):
         gen += 1
-        eng.step_generation(gen, gp)
+        eng.step_generation(gen, gp, mig)
     pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
     out = {"ids": pin((cap, 7), torch.int64).view(np.uint64), "sex": pin((cap,), torch.uint8)}
     for k in "ADGCEFP":
-        out[k] = pin((1, cap), torch.float64)
+        out[k] = pin((n_phen, cap), torch.float64)
     for k in ("mv", "sv", "svf"):
         out[k] = pin((cap,), torch.float64)
 
@@ -102,10 +108,11 @@ def bench_sharded(args, METRIC, UNIT):
         eng.timer_start()
         for _ in range(args.steps):
             gen += 1
-            eng.step_generation(gen, gp)
-            work += eng.population_size(0) * M
-            if e2e and rank == 0:
-                eng.individuals(0, out=out)  # every rank holds identical columns; rank 0 feeds the host writers
+            eng.step_generation(gen, gp, mig)
+            for q in range(len(pops)):
+                work += eng.population_size(q) * M
+                if e2e and rank == 0:
+                    eng.individuals(q, out=out)  # every rank holds identical columns; rank 0 feeds the host writers
         ms = eng.timer_stop()
         eng.synchronize()
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -132,11 +139,12 @@ def bench_sharded(args, METRIC, UNIT):
             "metric": METRIC, "value": work / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-packed + f64",
             "data": "synthetic",
-            "config": {"workload": args.workload, "individuals": N, "loci": M, "chromosomes": len(cfg["chrs"]), "parallelism": "chromosome-sharded x%d" % world,
+            "config": {"workload": args.workload, "individuals": sum(pops), "populations": pops, "phenotypes": n_phen, "loci": M, "chromosomes": len(cfg["chrs"]),
+                       "parallelism": "chromosome-sharded x%d" % world, "device_memory_gb_rank0": eng.device_memory_bytes() / 1e9,
                        "chromosomes_rank0": mine, "collective": "all-reduce of 3*N doubles per generation (NCCL)",
-                       "l2": "inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (N * M / 4 / 1e9 / world)},
+                       "l2": "inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (sum(pops) * M / 4 / 1e9 / world)},
             "e2e": {"value": work2 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,
-                    "d2h_bytes_per_step": capi.Engine.individual_bytes(N, 1), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": sum(capi.Engine.individual_bytes(n, n_phen) for n in pops), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "propagate_bits_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms_dev, "note": "per-GPU mean"},

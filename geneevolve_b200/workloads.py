@@ -21,6 +21,10 @@ CONFIGS = {
     "config1_bundled_1chr": dict(n=1000, loci=1000, chrs=[1], founders=2000, n_cv=100, rm=True, mat_cor=0.0),
     "config2_chr22_10k": dict(n=10000, loci=500000, chrs=[22], founders=2000, n_cv=1000, rm=False, mat_cor=0.0),
     "config3_100k_x_1M": dict(n=100000, loci=1000000, chrs=list(range(1, 23)), founders=4000, n_cv=1000, rm=False, mat_cor=0.4),
+    # config 4: three populations of different sizes, ring migration (a full matrix crashes the reference),
+    # two phenotypes; 150 GB of bit-packed rows per generation -> needs >= 4 GPUs (chromosome shards)
+    "config4_3pop_300k_x_2M": dict(n=150000, pops=[150000, 100000, 50000], loci=2000000, chrs=list(range(1, 23)), founders=4000, n_cv=1000, n_phen=2,
+                                   rm=False, mat_cor=0.4, migration=[0.98, 0.02, 0.0, 0.0, 0.98, 0.02, 0.02, 0.0, 0.98]),
     # config 5 (whole-genome sequence): 2.5 TB per generation bit-packed does not fit, so it runs on founder segments
     # like the reference; the 10M loci are nominal (the segment path never touches non-causal loci)
     "config5_1M_x_10M_segments": dict(n=1000000, loci=10000000, chrs=list(range(1, 23)), founders=4000, n_cv=1000, rm=False, mat_cor=0.4,
@@ -76,6 +80,20 @@ def make_workload(name, seed=20261018, n_override=None, loci_override=None):
         val = (rng.random((nh, k)) < f[None, :]).astype(np.uint8)
         cvs.append(dict(bp=pos[sel], a=rng.normal(size=k), d=np.zeros(k), val=val, idx=sel))
     cfg.update(maps=maps, loci=loci, cvs=cvs, n_loci=[int(x) for x in n_loci] if cfg.get("segments") else [len(p) for p in loci], seed=seed)
+    if "pops" in cfg:
+        # further phenotypes: their own CV sets (positions shared by all populations, as ras_find_cv requires); every
+        # population has its own founders, hence its own CV alleles (index [phenotype][chromosome]['val'][population])
+        all_cvs = []
+        for f in range(cfg["n_phen"]):
+            per_chr = []
+            for c, (pos, k) in enumerate(zip(loci, n_cv)):
+                r = np.random.default_rng([seed, 1000 + f, c])
+                sel = np.sort(r.choice(len(pos), size=k, replace=False))
+                fr = np.clip(r.beta(0.5, 0.5, size=k), 0.01, 0.99)
+                val = [(np.random.default_rng([seed, 2000 + f, c, q]).random((nh, k)) < fr[None, :]).astype(np.uint8) for q in range(len(cfg["pops"]))]
+                per_chr.append(dict(bp=pos[sel], a=r.normal(size=k), d=np.zeros(k), val=val, idx=sel))
+            all_cvs.append(per_chr)
+        cfg["cvs_multi"] = all_cvs
     return cfg
 
 
@@ -92,6 +110,43 @@ def founder_words(cfg, c, rng):
         word, bit = int(s) // 32, np.uint32(1 << (int(s) % 32))
         w[:, word] = (w[:, word] & ~bit) | (cv["val"][:, k].astype(np.uint32) * bit)
     return w
+
+
+def founder_words_multi(cfg, c, pop, rng):
+    """Like founder_words for population `pop` of a multi-population workload: the CV columns of every phenotype agree with
+    that population's CV panels."""
+    nh, nl = 2 * cfg["founders"], cfg["n_loci"][c]
+    nw = (nl + 31) // 32
+    w = rng.integers(0, 2 ** 32, size=(nh, nw), dtype=np.uint32)
+    if nl % 32:
+        w[:, -1] &= np.uint32((1 << (nl % 32)) - 1)
+    for f in range(cfg["n_phen"]):
+        cv = cfg["cvs_multi"][f][c]
+        for k, s in enumerate(cv["idx"]):
+            word, bit = int(s) // 32, np.uint32(1 << (int(s) % 32))
+            w[:, word] = (w[:, word] & ~bit) | (cv["val"][pop][:, k].astype(np.uint32) * bit)
+    return w
+
+
+def configure_engine_multipop(eng, cfg, chrs_local=None, panel_seed=7):
+    """Multi-population workloads (config 4): every population its own founders, sizes and (here identical) effect sizes;
+    phenotype f has omega = 1 / (1 + f), lambda = 1 for the first phenotype only."""
+    chrs_local = list(range(len(cfg["chrs"]))) if chrs_local is None else list(chrs_local)
+    if chrs_local != list(range(len(cfg["chrs"]))):
+        eng.set_chromosome_ids(chrs_local)
+    for k, c in enumerate(chrs_local):
+        eng.set_loci(k, cfg["loci"][c])
+    for p in range(len(cfg["pops"])):
+        eng.set_population(p, avoid_inbreeding=False, random_mating=cfg["rm"], mm_percent=0.0)
+        for k, c in enumerate(chrs_local):
+            bp, cm, pr = cfg["maps"][c]
+            eng.set_genetic_map(p, k, bp, pr, int(bp[1] - bp[0]))
+            eng.set_founder_panel_packed(p, k, founder_words_multi(cfg, c, p, np.random.default_rng([panel_seed, c, p])))
+            for f in range(cfg["n_phen"]):
+                cv = cfg["cvs_multi"][f][c]
+                eng.set_cv(p, f, k, cv["bp"], cv["a"], cv["d"], cv["val"][p])
+        for f in range(cfg["n_phen"]):
+            eng.set_pheno_scheme(p, f, va=0.5, vd=0.0, ve=0.5, vc=0.0, vf=0.0, omega=1.0 / (1 + f), beta=0.0, lam=1.0 if f == 0 else 0.0)
 
 
 def configure_engine(eng, cfg, va=0.5, vd=0.0, ve=0.5, panel_seed=7, chrs_local=None):

@@ -230,6 +230,29 @@ def test_migration_row_must_sum_to_one(cuda_lib):
     e2.init_generation0()
     e2.step_generation(1, gp, [0.9, 0.1, 0.2, 0.8])
     assert (e2.population_size(0), e2.population_size(1)) == (20 - 2 + 4, 20 - 4 + 2)
+    # both populations share one effect table here, so the library carries no root-population plane and uses the
+    # tabulated genetic values; the oracle always looks a, d up through the root population (:2776-2786): same numbers
+    cpu = OracleEngine(**kw)
+    for c in range(case.n_chr):
+        cpu.set_loci(c, case.loci[c])
+    for p in range(2):
+        cpu.set_population(p, False, True, 0.0)
+        bp, pr, step = case.maps[0]
+        cpu.set_genetic_map(p, 0, bp, pr, step)
+        cpu.set_founder_panel(p, 0, case.panel[0])
+        cpu.set_cv(p, 0, 0, case.cv[0]["bp"], case.cv[0]["a"], case.cv[0]["d"], case.cv[0]["val"])
+        cpu.set_pheno_scheme(p, 0, va=0.5, vd=0.0, ve=0.5)
+    cpu.init_generation0()
+    cpu.step_generation(1, gp, [0.9, 0.1, 0.2, 0.8])
+    for g in range(2, 5):
+        e2.step_generation(g, gp, [0.9, 0.1, 0.2, 0.8])
+        cpu.step_generation(g, gp, [0.9, 0.1, 0.2, 0.8])
+    for p in range(2):
+        a, b = e2.individuals(p), cpu.individuals(p)
+        assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["sex"], b["sex"])
+        for k in "ADGEP":
+            np.testing.assert_allclose(a[k], b[k], rtol=1e-9, atol=1e-11)
+        assert np.array_equal(e2.haplotypes(p, 0), cpu.haplotypes(p, 0))
 
 
 # ---------------------------------------------------------------------------------------------------------------
