@@ -78,8 +78,14 @@ def bench_sharded(args, METRIC, UNIT):
     pops = cfg.get("pops", [N])
     n_phen = cfg.get("n_phen", 1)
     cap = int(max(max(pops), cfg["founders"]) * (1.03 if len(pops) == 1 else 1.10)) + 1024   # migration moves ~2 % either way
-    eng = capi.Engine(n_pop=len(pops), n_chr=len(mine), n_phen=n_phen, device=local, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX,
-                      seed=12345, capacity=cap, rank=rank, world_size=world)
+    segs = bool(cfg.get("segments"))
+    seg_cap = 0
+    if segs:  # parts per haplotype after g generations ~ chromosomes + g * Morgans of this rank's chromosomes (both arms run back to back)
+        morgans = sum(float(cfg["maps"][c][2].sum()) for c in mine)
+        seg_cap = int(2 * cap * (len(mine) + (args.warmup + 2 * args.steps + 1) * morgans) * 1.05)
+    kid = capi.GE_KERNEL_RECOMBINE_SEGMENTS if segs else capi.GE_KERNEL_PROPAGATE_BITS
+    eng = capi.Engine(n_pop=len(pops), n_chr=len(mine), n_phen=n_phen, device=local, representation=capi.GE_REP_SEGMENTS if segs else capi.GE_REP_BITS,
+                      rng_mode=capi.GE_RNG_PHILOX, seed=12345, capacity=cap, seg_capacity=seg_cap, rank=rank, world_size=world)
     if len(pops) > 1:
         workloads.configure_engine_multipop(eng, cfg, chrs_local=mine)
     else:
@@ -125,7 +131,7 @@ def bench_sharded(args, METRIC, UNIT):
     with ClockSampler(local) as clocks:
         work, ms_dev = timed(False)
     launches = eng.launch_count()
-    k_ms, k_n, k_bytes = eng.kernel_time(capi.GE_KERNEL_PROPAGATE_BITS)
+    k_ms, k_n, k_bytes = eng.kernel_time(kid)
     eng.set_profiling(False)
     work2, ms_e2e = timed(True)
     kb = torch.tensor([k_bytes / max(k_ms, 1e-9) / 1e6], dtype=torch.float64, device="cuda")  # GB/s of this rank's kernel
@@ -141,12 +147,14 @@ def bench_sharded(args, METRIC, UNIT):
             "data": "synthetic",
             "config": {"workload": args.workload, "individuals": sum(pops), "populations": pops, "phenotypes": n_phen, "loci": M, "chromosomes": len(cfg["chrs"]),
                        "parallelism": "chromosome-sharded x%d" % world, "device_memory_gb_rank0": eng.device_memory_bytes() / 1e9,
+                       "representation": "founder segments (loci nominal; steps are generations %d..%d)" % (args.warmup + 1, args.warmup + args.steps) if segs else "bit-packed haplotypes",
                        "chromosomes_rank0": mine, "collective": "all-reduce of 3*N doubles per generation (NCCL)",
-                       "l2": "inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (sum(pops) * M / 4 / 1e9 / world)},
+                       "l2": ("inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (sum(pops) * M / 4 / 1e9 / world)) if not segs else
+                             "inputs larger than L2 (founder-segment lists, %.1f GB moved per step per GPU)" % (k_bytes / max(k_n, 1) * 2 / 1e9)},
             "e2e": {"value": work2 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,
                     "d2h_bytes_per_step": sum(capi.Engine.individual_bytes(n, n_phen) for n in pops), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "propagate_bits_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "seg_recombine_kernel (count + fill)" if segs else "propagate_bits_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms_dev, "note": "per-GPU mean"},
             "clocks": clocks.summary(), "cpu_baseline": None}))
     dist.barrier()
