@@ -223,9 +223,33 @@ def three_populations():
             ["--file_migration", f"{d}/F.mig"], 2026)
 
 
+def bundled_example():
+    """G. BASELINE config 1: the reference's own bundled example (Examples.zip: 2 000 founders, b37 50 kb map, 100 CVs per
+    chromosome) filtered to chromosome 1, random mating, 1 000 individuals per generation, three generations,
+    `--seed 12345` — the reference's real inputs and real genetic map (4 971 rows on chr1) rather than synthetic ones."""
+    import zipfile
+    with tempfile.TemporaryDirectory() as d:
+        zipfile.ZipFile("/root/reference/Examples.zip").extractall(d)
+        e = os.path.join(d, "Examples")
+        with open(f"{e}/g.hapaddr", "w") as f:
+            f.write(f"chr hap legend sample\n1 {e}/ref.chr1.hap {e}/ref.chr1.legend {e}/ref.chr1.indv\n")
+        with open(f"{e}/g.cvinfo", "w") as f:   # the loader rejects CV rows of inactive chromosomes (src/Population.cpp:250-254)
+            lines = open(f"{e}/cv.info").read().splitlines()
+            f.write(lines[0] + "\n" + "".join(l + "\n" for l in lines[1:] if l.split()[0] == "1"))
+        with open(f"{e}/g.cvs", "w") as f:
+            f.write(f"1 {e}/cv.chr1.hap\n")
+        write_geninfo(f"{e}/g.gen", [(1000, 0, "p", "thr", 1, 1)] * 3)
+        run("G_bundled_example_chr1", ["--file_gen_info", f"{e}/g.gen", "--file_hap_name", f"{e}/g.hapaddr", "--file_recom_map", f"{e}/Recom.Map.b37.50KbDiff",
+                                       "--file_cv_info", f"{e}/g.cvinfo", "--file_cvs", f"{e}/g.cvs", "--RM"], 12345)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "F":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "F":
         three_populations()     # added later; the other fixtures are not regenerated
+    elif which == "G":
+        bundled_example()
     else:
         main()
         three_populations()
+        bundled_example()

@@ -41,6 +41,10 @@ class Golden:
     def migration_row(self, gen):
         return self.z["in.migration"][gen - 1] if "in.migration" in self.z else None
 
+    def philox_capacity(self):
+        """Room for Poisson family sizes and migration under the library's own draws."""
+        return int(1.5 * max(int(self.z[f"g{g}.p{p}.n"]) for g in range(self.G + 1) for p in range(self.n_pop))) + 300
+
     def engine_kwargs(self, **over):
         cap = max(int(self.z[f"g{g}.p{p}.n"]) for g in range(self.G + 1) for p in range(self.n_pop)) + 64
         kw = dict(n_pop=self.n_pop, n_chr=self.n_chr, n_phen=self.n_phen, vt_type=self.vt_type, seed=self.seed, capacity=cap)

@@ -28,7 +28,7 @@ def covered_hits(G, d, pop):
 @pytest.mark.parametrize("name", SCENARIOS)
 def test_philox_generation_matches_oracle(cuda_lib, name):
     G = Golden(name)
-    gpu = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=400))
+    gpu = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=G.philox_capacity()))
     cpu = OracleEngine(**G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX))
     for e in (gpu, cpu):
         G.configure(e)

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 def test_two_sharded_contexts_match_one(cuda_lib, name):
     G = Golden(name)
     n_gen = min(G.G, 3)
-    single = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=400))
+    single = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=G.philox_capacity()))
     G.configure(single)
     ref = run_generations(G, single, n_gen)
 
@@ -44,7 +44,7 @@ def test_two_sharded_contexts_match_one(cuda_lib, name):
 
     def run(rank):
         try:
-            kw = G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=400)
+            kw = G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=G.philox_capacity())
             kw.update(n_chr=len(parts[rank]), rank=rank, world_size=world)
             eng = capi.Engine(cuda_lib, **kw)
             configure_subset(G, eng, parts[rank])
