@@ -222,6 +222,7 @@ def ours(args):
         ms_dev = eng.timer_stop()
     launches = eng.launch_count()
     k_ms, k_n, k_bytes = eng.kernel_time(kid)
+    phases = {name: eng.kernel_time(pid)[0] / args.steps for name, pid in capi.GE_PHASES.items()}   # ms per step, control stream, overlapped by the copy
     eng.set_profiling(False)
     value = work / (ms_dev * 1e-3)
 
@@ -270,6 +271,7 @@ def ours(args):
                      "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms_dev,
                      "algorithmic_bytes_per_launch": k_bytes // max(k_n, 1)},
+        "control_chain_ms_per_step": phases,
         "clocks": clocks.summary(),
     }
     line["cpu_baseline"] = cpu_baseline_single(args, M) if not args.no_cpu_baseline else None

@@ -15,6 +15,7 @@ GE_REP_BITS, GE_REP_SEGMENTS = 1, 2
 GE_RNG_PHILOX, GE_RNG_REPLAY = 0, 1
 GE_SEL = {"": 0, "logit": 1, "probit": 2, "stab": 3, "thr": 4}
 GE_KERNEL_PROPAGATE_BITS, GE_KERNEL_RECOMBINE_SEGMENTS = 0, 1
+GE_PHASES = {"mate": 2, "sample": 3, "cv_and_genetic_values": 4, "phenotype": 5}
 
 _u64p, _u8p, _f64p, _i32p, _u32p = (C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_double),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_uint32))

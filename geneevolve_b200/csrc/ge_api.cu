@@ -405,6 +405,7 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
     GenState &S = P.st[P.cur];
     if (S.n == 0) return fail(GE_ERR_INVALID, "empty population");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    ge_ctx::PhaseTimer timer(ctx, GE_PHASE_CV_AD);
     if (ctx->segs() && !ctx->bits() && ctx->cv_from_segments) GE_TRY(seg_find_cv(ctx, pop));  // ras_find_cv on the segment lists (verification mode)
     uint32_t ncv = ctx->n_cv_tot;
     if (ncv) {
@@ -767,6 +768,7 @@ int ge_mate(ge_ctx *ctx, int pop, int gen, const ge_gen_params *gp) {  // random
     if (!gp) return fail(GE_ERR_INVALID, "null params");
     if (ctx->cfg.rng_mode != GE_RNG_PHILOX) return fail(GE_ERR_INVALID, "replay mode: supply couples with ge_set_couples or offspring draws");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    ge_ctx::PhaseTimer timer(ctx, GE_PHASE_MATE);
     return mate_philox(ctx, pop, gen, *gp);
 }
 
@@ -827,6 +829,7 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         if (dr->common) CUDA_TRY(cudaMemcpyAsync(off.C.p, dr->common, (size_t)n_off * nf * 8, cudaMemcpyHostToDevice, st));
         P.have_couple_of = false;
     } else {
+        ge_ctx::PhaseTimer timer(ctx, GE_PHASE_SAMPLE);
         // offspring offsets = exclusive scan of the family sizes of the couples that may marry (:2402-2406)
         GE_TRY(ctx->ensure(P.cnt32, (size_t)std::max<uint64_t>(P.n_couples, ctx->cfg.capacity * C * 2 + 1) * 4));
         GE_TRY(ctx->ensure(P.mate.fam_off, (P.n_couples + 1) * 8));
@@ -984,8 +987,11 @@ int ge_step_generation(ge_ctx *ctx, int gen, const ge_gen_params *gp, const doub
         GE_TRY(ge_reproduce(ctx, p, gen, dr ? &dr[p] : nullptr));
         GE_TRY(ge_compute_AD(ctx, p, gen));
         uint64_t n = ctx->pop[p].st[ctx->pop[p].cur].n;
-        for (int f = 0; f < nf; f++)
-            GE_TRY(scale_AD_compute_GEF_impl(ctx, p, gen, f, (dr && dr[p].e_raw) ? dr[p].e_raw + (uint64_t)f * n : nullptr, nullptr));
+        {
+            ge_ctx::PhaseTimer timer(ctx, GE_PHASE_PHENOTYPE);
+            for (int f = 0; f < nf; f++)
+                GE_TRY(scale_AD_compute_GEF_impl(ctx, p, gen, f, (dr && dr[p].e_raw) ? dr[p].e_raw + (uint64_t)f * n : nullptr, nullptr));
+        }
     }
     for (int f = 0; f < nf; f++) GE_TRY(ge_environmental_effects_specific_to_each_population(ctx, f));
     for (int p = 0; p < np; p++) GE_TRY(ge_compute_mating_value_selection_value(ctx, p, gen, &gp[p]));

@@ -202,6 +202,14 @@ struct ge_ctx {
         }
         ev_pending.clear();
     }
+    // CUDA events around a phase of the control chain (only while profiling)
+    struct PhaseTimer {
+        ge_ctx *c; EvPair p;
+        PhaseTimer(ge_ctx *ctx, int id) : c(ctx), p{nullptr, nullptr, id, 0} {
+            if (c->profiling) { p.a = c->get_event(); p.b = c->get_event(); cudaEventRecord(p.a, c->stream); }
+        }
+        ~PhaseTimer() { if (p.a) { cudaEventRecord(p.b, c->stream); c->ev_pending.push_back(p); } }
+    };
     uint64_t launches = 0;
     size_t mem_now = 0, mem_peak = 0;
 

@@ -228,8 +228,13 @@ int ge_download_draws(ge_ctx *ctx, int pop, uint64_t *father, uint64_t *mother, 
                       uint64_t *xo_bp, uint8_t *start_hap, uint64_t *mut_off, uint64_t *mut_bp, uint8_t *mut_gam);
 
 /* ---- measurement hooks (bench.py): CUDA-event time of the dominant kernel on the library's stream ---- */
-#define GE_KERNEL_PROPAGATE_BITS 0
-#define GE_KERNEL_RECOMBINE_SEGMENTS 1
+#define GE_KERNEL_PROPAGATE_BITS 0      /* propagate_bits_kernel (bulk stream) */
+#define GE_KERNEL_RECOMBINE_SEGMENTS 1  /* seg_recombine count + fill passes */
+/* phases of the control chain (control stream, CUDA events around the whole phase: kernels, gaps and read-backs) */
+#define GE_PHASE_MATE 2                 /* random_mate / assort_mate */
+#define GE_PHASE_SAMPLE 3               /* family sizes, crossover (and mutation) sampling, placement */
+#define GE_PHASE_CV_AD 4                /* causal-variant planes, allele counts, genetic values */
+#define GE_PHASE_PHENOTYPE 5            /* noise, scaling, phenotypes, mating and selection values */
 #define GE_KERNEL_COUNT 8
 int ge_set_profiling(ge_ctx *ctx, int enabled);
 int ge_get_kernel_time(ge_ctx *ctx, int kernel, double *total_ms, uint64_t *launches, uint64_t *algorithmic_bytes);
