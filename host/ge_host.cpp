@@ -28,9 +28,10 @@ const char *Options::usage() {
            "    --file_gen_info F --file_hap_name F --file_recom_map F [--file_mutation_map F] [--RM] [--MM x]\n"
            "    per phenotype: --file_cv_info F --file_cvs F [--va x --vd x --vc x --ve x --vf x --omega x --beta x --lambda x]\n"
            "  global: [--gamma x]... [--file_migration F] [--vt_type 1|2] [--avoid_inbreeding] [--seed n] [--prefix P]\n"
-           "          [--out_hap] [--out_interval] [--file_output_generations F] [--device n] [--gpus N] [--quiet]\n"
+           "          [--out_hap] [--out_plink] [--out_plink01] [--out_interval] [--file_output_generations F]\n"
+           "          [--device n] [--gpus N] [--quiet]\n"
            "          [--compact_segments]  (extension: merge adjacent same-founder segments after every generation)\n"
-           "  not on this path (rejected): --file_ref_vcf --out_plink --out_plink01 --out_vcf\n";
+           "  rejected: --file_ref_vcf (libStatGen VCF reader), --out_vcf (the reference refuses it for hap-format founders too)\n";
 }
 
 bool Options::parse(const std::vector<std::string> &a) {
@@ -72,6 +73,8 @@ bool Options::parse(const std::vector<std::string> &a) {
         else if (f == "--prefix") prefix = need(i);
         else if (f == "--out_hap") out_hap = true;
         else if (f == "--out_interval") out_interval = true;
+        else if (f == "--out_plink") out_plink = true;
+        else if (f == "--out_plink01") out_plink01 = true;
         else if (f == "--file_output_generations") file_output_generations = need(i);
         else if (f == "--device") device = (int)num(i);
         else if (f == "--gpus") gpus = (int)num(i);
@@ -79,8 +82,10 @@ bool Options::parse(const std::vector<std::string> &a) {
         else if (f == "--quiet") quiet = true;
         else if (f == "--debug") {}
         else if (f == "--help" || f == "-h" || f == "?") help = true;
-        else if (f == "--file_ref_vcf" || f == "--out_plink" || f == "--out_plink01" || f == "--out_vcf")
-            error = "Error: [" + f + "] is host file I/O outside the GPU reproduction path; use the hap formats.";
+        else if (f == "--out_vcf")   // with hap-format founders the reference refuses too (src/Simulation.cpp:1071-1075)
+            error = "Error: current version can't convert to VCF output format! [--out_vcf]";
+        else if (f == "--file_ref_vcf")
+            error = "Error: [" + f + "] needs libStatGen's VCF reader, which is outside the GPU reproduction path; use the hap formats.";
         else error = "Error: unknown option [" + f + "].";
     }
     if (!error.empty() || help) return error.empty();
@@ -316,13 +321,18 @@ bool read_cvs(const std::string &path, const std::vector<ChrFiles> &chrs, std::v
     return true;
 }
 
-bool read_legend(const std::string &path, std::vector<std::string> &id, std::vector<uint64_t> &pos, std::string &err) {
+bool read_legend(const std::string &path, std::vector<std::string> &id, std::vector<uint64_t> &pos, std::vector<std::string> *al0,
+                 std::vector<std::string> *al1, std::string &err) {
     std::ifstream f;  // src/format_hap.cpp:125-156, header then id pos allele0 allele1
     if (!open_in(path, f, err)) return false;
     std::string a, b, c, d;
     f >> a >> b >> c >> d;
     uint64_t p;
-    while (f >> a >> p >> c >> d) { id.push_back(a); pos.push_back(p); }
+    while (f >> a >> p >> c >> d) {
+        id.push_back(a); pos.push_back(p);
+        if (al0) al0->push_back(c);
+        if (al1) al1->push_back(d);
+    }
     return true;
 }
 bool read_indv(const std::string &path, std::vector<std::string> &out, std::string &err) {
@@ -391,7 +401,7 @@ bool HostSimulation::gfail(const char *what) { err = std::string(what) + ": " + 
 bool HostSimulation::load_inputs() {
     n_pop = (int)opt.pop.size();
     n_phen = (int)opt.pop[0].file_cv_info.size();
-    need_panel = opt.out_hap;
+    need_panel = opt.out_hap || opt.out_plink || opt.out_plink01;
     in.assign(n_pop, PopInputs());
     for (int p = 0; p < n_pop; p++) {
         const PopOptions &O = opt.pop[p];
@@ -410,8 +420,9 @@ bool HostSimulation::load_inputs() {
         if ((int)I.chrs.size() != n_chr) return fail("Error: every population must list the same chromosomes.");
         if ((int)I.gens.size() != tot_gen) return fail("Error: every population needs the same number of generations.");
         if (need_panel) {
-            I.legend_pos.resize(n_chr); I.legend_id.resize(n_chr);
-            for (int c = 0; c < n_chr; c++) if (!read_legend(I.chrs[c].legend, I.legend_id[c], I.legend_pos[c], err)) return false;
+            I.legend_pos.resize(n_chr); I.legend_id.resize(n_chr); I.legend_al0.resize(n_chr); I.legend_al1.resize(n_chr);
+            for (int c = 0; c < n_chr; c++)
+                if (!read_legend(I.chrs[c].legend, I.legend_id[c], I.legend_pos[c], &I.legend_al0[c], &I.legend_al1[c], err)) return false;
         }
     }
     if (n_pop > 1 && !read_migration(opt.file_migration, n_pop, (size_t)tot_gen, migration, err)) return false;
@@ -434,7 +445,7 @@ bool HostSimulation::upload() {
     const int n_loc = (int)mine.size();
     ge_config cfg = {};
     cfg.device = opt.device + rank; cfg.n_pop = n_pop; cfg.n_chr = n_loc; cfg.n_phen = n_phen; cfg.vt_type = opt.vt_type;
-    cfg.representation = (opt.out_hap ? GE_REP_BITS : 0) | ((opt.out_interval || !opt.out_hap) ? GE_REP_SEGMENTS : 0);
+    cfg.representation = (need_panel ? GE_REP_BITS : 0) | ((opt.out_interval || !need_panel) ? GE_REP_SEGMENTS : 0);
     cfg.rng_mode = GE_RNG_PHILOX; cfg.seed = opt.seed; cfg.capacity = cap; cfg.rank = rank; cfg.world_size = world;
     if (ge_create(&cfg, &ctx) != GE_OK) return gfail("ge_create");
     if (world > 1) {
@@ -590,7 +601,7 @@ bool HostSimulation::after_generation(int gen) {
     }
     bool out = gen == tot_gen && gen > 0;  // the last generation is always written (:144), others on request (:2059-2063)
     for (int g : output_generations) out |= g == gen;
-    if (out && (opt.out_hap || opt.out_interval)) return write_genotypes(gen);
+    if (out && (need_panel || opt.out_interval)) return write_genotypes(gen);
     return true;
 }
 
@@ -623,16 +634,20 @@ bool HostSimulation::write_genotypes(int gen) {
         uint64_t n = 0;
         if (ge_get_population_size(ctx, p, &n) != GE_OK) return gfail("ge_get_population_size");
         std::vector<uint64_t> ids(n * 7);
+        std::vector<uint8_t> sex(n);
         ge_indiv_soa s = {};
-        s.ids = ids.data();
+        s.ids = ids.data(); s.sex = sex.data();
         if (ge_download_individuals(ctx, p, &s) != GE_OK) return gfail("ge_download_individuals");
         for (int k = 0; k < (int)mine.size(); k++) {   // each rank writes the files of its own chromosomes
             const int c = mine[k];
             std::string base = opt.prefix + ".pop" + std::to_string(p + 1) + ".gen" + std::to_string(gen) + ".chr" + std::to_string(in[0].chrs[c].chr);
-            if (opt.out_hap) {  // ras_write_hap_legend_sample :1142-1182 -> format_hap::write_hap / write_indv (src/format_hap.cpp:6-53)
-                uint64_t ns = in[0].legend_pos[c].size();
-                std::vector<uint8_t> m(2 * n * ns);
+            std::vector<uint8_t> m;   // alleles of this chromosome, [2n haplotypes][ns loci], materialised on the device
+            const uint64_t ns = need_panel ? in[0].legend_pos[c].size() : 0;
+            if (need_panel) {
+                m.resize(2 * n * ns);
                 if (ge_download_haplotypes(ctx, p, k, m.data()) != GE_OK) return gfail("ge_download_haplotypes");
+            }
+            if (opt.out_hap) {  // ras_write_hap_legend_sample :1142-1182 -> format_hap::write_hap / write_indv (src/format_hap.cpp:6-53)
                 std::ofstream o((base + ".hap").c_str());
                 if (!o) return fail("Error: can not open the file [" + base + ".hap] to write.");
                 std::string line(2 * 2 * n, ' ');
@@ -642,6 +657,32 @@ bool HostSimulation::write_genotypes(int gen) {
                 }
                 std::ofstream oi((base + ".indv").c_str());
                 for (uint64_t i = 0; i < n; i++) oi << ids[i * 7] + 1 << '\n';
+            }
+            // ras_write_hap_to_plink_format :1254-1303 -> format_plink::write_ped_map / write_ped01_map (src/format_plink.cpp:5-135).
+            // Both flags name the same two files in the reference, the 0/1 coding is written last and wins; same here.
+            for (int pass = 0; pass < 2; pass++) {
+                const bool hap01 = pass == 1;
+                if (!(hap01 ? opt.out_plink01 : opt.out_plink)) continue;
+                const PopInputs &I = in[p];
+                std::ofstream o((base + ".ped").c_str());
+                if (!o) return fail("Error: can not open the file [" + base + ".ped] to write.");
+                std::string line;
+                for (uint64_t i = 0; i < n; i++) {   // FID IID PID MID sex phen, IDs + 1 because 0 is PLINK's missing value (:1393-1404)
+                    const uint64_t *q = &ids[i * 7];
+                    line = std::to_string(q[1] + 1) + ' ' + std::to_string(q[0] + 1) + ' ' + std::to_string(q[1] + 1) + ' ' + std::to_string(q[2] + 1) + ' ' +
+                           std::to_string((int)sex[i]) + " -9";
+                    const uint8_t *h0 = &m[(2 * i) * ns], *h1 = &m[(2 * i + 1) * ns];
+                    for (uint64_t j = 0; j < ns; j++) {
+                        line += ' ';
+                        if (hap01) line += h0[j] ? '1' : '0'; else line += h0[j] ? I.legend_al1[c][j] : I.legend_al0[c][j];
+                        line += ' ';
+                        if (hap01) line += h1[j] ? '1' : '0'; else line += h1[j] ? I.legend_al1[c][j] : I.legend_al0[c][j];
+                    }
+                    o << line << '\n';
+                }
+                std::ofstream om((base + ".map").c_str());
+                if (!om) return fail("Error: can not open the file [" + base + ".map] to write.");
+                for (uint64_t j = 0; j < ns; j++) om << in[0].chrs[c].chr << ' ' << I.legend_id[c][j] << " 0 " << I.legend_pos[c][j] << '\n';
             }
             if (opt.out_interval) {  // ras_write_hap_to_interval_format :1582-1639
                 uint64_t nseg = 0, nmut = 0;
@@ -691,7 +732,7 @@ bool HostSimulation::run() {
         }
         if (ge_step_generation(ctx, gen, gp.data(), n_pop > 1 ? migration[gen - 1].data() : nullptr, nullptr) != GE_OK) return gfail("ge_step_generation");
 #ifndef GE_HOST_NO_COMPACT
-        if (opt.compact_segments && (opt.out_interval || !opt.out_hap))
+        if (opt.compact_segments && (opt.out_interval || !need_panel))
             for (int p = 0; p < n_pop; p++) if (ge_compact_segments(ctx, p, nullptr, nullptr) != GE_OK) return gfail("ge_compact_segments");
 #endif
         if (!after_generation(gen)) return false;

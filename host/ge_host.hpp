@@ -8,6 +8,7 @@
 //   HostSimulation::run     <- Simulation::run / ras_main_sim      (src/Simulation.cpp:68-161, 684-702)
 //   write_info / summary    <- Population::ras_save_human_info     (src/Population.cpp:510-568), ras_save_res (:782-834)
 //   write_hap / write_int   <- ras_write_hap_legend_sample (:1142-1182), ras_write_hap_to_interval_format (:1582-1639)
+//   write_ped / write_map   <- ras_write_hap_to_plink_format (:1254-1303), format_plink::write_ped_map / write_ped01_map
 // Nothing is computed here: every number in the outputs comes out of the library.
 #pragma once
 #include <cstdint>
@@ -40,7 +41,7 @@ struct Options {
     std::vector<double> gamma;
     std::string file_migration, file_output_generations, prefix = "out";
     int vt_type = 1, device = 0, gpus = 1;   // --gpus N: chromosomes are spread over devices device .. device+N-1
-    bool avoid_inbreeding = false, out_hap = false, out_interval = false, quiet = false, help = false;
+    bool avoid_inbreeding = false, out_hap = false, out_interval = false, out_plink = false, out_plink01 = false, quiet = false, help = false;
     bool compact_segments = false;           // extension (ge_compact_segments): the .int output is then not the reference's
     uint64_t seed = 0;
     std::string error;
@@ -56,7 +57,7 @@ struct PopInputs {
     std::vector<MutationMap> mutmap;                  // [chr] or empty
     std::vector<std::vector<CvBlock>> cv;             // [phen][chr]
     std::vector<std::vector<uint64_t>> legend_pos;    // [chr] (only when genotypes are needed)
-    std::vector<std::vector<std::string>> legend_id;
+    std::vector<std::vector<std::string>> legend_id, legend_al0, legend_al1;
 };
 
 // text readers; each returns false and fills err on failure
@@ -66,7 +67,8 @@ bool read_recombination_map(const std::string &path, const std::vector<ChrFiles>
 bool read_mutation_map(const std::string &path, const std::vector<ChrFiles> &chrs, std::vector<MutationMap> &out, std::string &err);
 bool read_cv_info(const std::string &path, const std::vector<ChrFiles> &chrs, std::vector<CvBlock> &out, std::string &err);
 bool read_cvs(const std::string &path, const std::vector<ChrFiles> &chrs, std::vector<CvBlock> &io, std::string &err);
-bool read_legend(const std::string &path, std::vector<std::string> &id, std::vector<uint64_t> &pos, std::string &err);
+bool read_legend(const std::string &path, std::vector<std::string> &id, std::vector<uint64_t> &pos, std::vector<std::string> *al0,
+                 std::vector<std::string> *al1, std::string &err);
 bool read_indv(const std::string &path, std::vector<std::string> &out, std::string &err);
 // IMPUTE2 .hap (rows = SNPs, columns = haplotypes) -> bit-packed hap-major words (ge_set_founder_panel_packed layout)
 bool read_hap_packed(const std::string &path, uint64_t n_hap, uint64_t n_snp, std::vector<uint32_t> &words, std::string &err);

@@ -130,7 +130,61 @@ def check_errors(cli, tmp_path):
     r = subprocess.run([cli] + args[2:] + ["--prefix", str(tmp_path / "e")], capture_output=True, text=True)
     assert r.returncode == 255 and "missing parameter [--file_gen_info]" in r.stdout
     r = subprocess.run([cli] + args + ["--out_vcf"], capture_output=True, text=True)
-    assert r.returncode == 255 and "--out_vcf" in r.stdout
+    assert r.returncode == 255 and "--out_vcf" in r.stdout and "can't convert to VCF output format" in r.stdout   # src/Simulation.cpp:1071-1075
+
+
+def check_plink(cli, tmp_path):
+    """--out_plink / --out_plink01 (ras_write_hap_to_plink_format, src/Simulation.cpp:1254-1303; format_plink::write_ped_map and
+    write_ped01_map, src/format_plink.cpp:5-135): the .map file is draw-independent and must equal the reference's byte for
+    byte; every .ped row is `father+1 ID+1 father+1 mother+1 sex -9` followed by the two alleles of every SNP, and must spell
+    out exactly the haplotypes the same run writes with --out_hap."""
+    sc, args = scenario(tmp_path, 2)
+    G = len(sc["gens"])
+    outs = {}
+    for flag in ("--out_plink", "--out_plink01"):
+        pre = str(tmp_path / ("o" + flag[6:]))
+        r = subprocess.run([cli] + args + ["--seed", "5", "--prefix", pre, "--out_hap", flag, "--quiet"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[flag] = pre
+    info = np.loadtxt(outs["--out_plink"] + f".info.pop1.gen{G}.txt", skiprows=1)
+    n = info.shape[0]
+    for c in sc["chrs"]:
+        hap = np.loadtxt(outs["--out_plink"] + f".pop1.gen{G}.chr{c}.hap", dtype=np.uint8)          # [snp][2n]
+        for flag, code in (("--out_plink", "AC"), ("--out_plink01", "01")):
+            base = outs[flag] + f".pop1.gen{G}.chr{c}"
+            rows = [line.rstrip("\n").split(" ") for line in open(base + ".ped")]
+            assert len(rows) == n and all(len(r) == 6 + 2 * sc["n_snp"] for r in rows)
+            ped = np.array([r[:6] for r in rows])
+            assert np.array_equal(ped[:, 1].astype(np.int64), info[:, 0].astype(np.int64))            # IID = ID (already + 1 in .info)
+            assert np.array_equal(ped[:, 0], ped[:, 2]) and np.array_equal(ped[:, 2].astype(np.int64), info[:, 1].astype(np.int64))
+            assert np.array_equal(ped[:, 3].astype(np.int64), info[:, 2].astype(np.int64))
+            assert np.array_equal(ped[:, 4].astype(np.int64), info[:, 7].astype(np.int64)) and set(ped[:, 5]) == {"-9"}
+            al = np.array([r[6:] for r in rows]).reshape(n, sc["n_snp"], 2)                            # [ind][snp][hap]
+            want = np.array(list(code))[hap.T.reshape(n, 2, sc["n_snp"]).transpose(0, 2, 1)]
+            assert np.array_equal(al, want), (flag, c)
+            lines = open(base + ".map").read().splitlines()
+            assert len(lines) == sc["n_snp"] and lines[0].split(" ")[0] == str(c) and lines[0].split(" ")[2] == "0"
+    if os.path.exists(REF_BIN):
+        for flag in ("--out_plink", "--out_plink01"):
+            rp = str(tmp_path / ("r" + flag[6:]))
+            rr = subprocess.run([REF_BIN] + args + ["--seed", "5", "--prefix", rp, flag], capture_output=True, text=True)
+            assert rr.returncode == 0
+            for c in sc["chrs"]:
+                a, b = outs[flag] + f".pop1.gen{G}.chr{c}", rp + f".pop1.gen{G}.chr{c}"
+                assert open(a + ".map", "rb").read() == open(b + ".map", "rb").read()
+                ra = open(a + ".ped").readline().rstrip("\n").split(" ")
+                rb = open(b + ".ped").readline().rstrip("\n").split(" ")
+                assert len(ra) == len(rb) and ra[5] == rb[5] == "-9" and set(ra[6:]) <= set(rb[6:]) | set("AC01")
+                assert rb[0] == rb[2] and rb[1] == "1" and ra[1] == "1"                                  # same ID conventions
+
+
+def test_host_cli_plink_on_oracle(tmp_path):
+    check_plink(oracle_cli(), tmp_path)
+
+
+@pytest.mark.gpu
+def test_host_cli_plink_on_gpu(tmp_path):
+    check_plink(product_cli(), tmp_path)
 
 
 def check_two_populations(cli, tmp_path):
