@@ -192,7 +192,7 @@ def ours(args):
     eng = capi.Engine(seg_capacity=seg_cap, n_pop=1, n_chr=len(cfg["chrs"]), n_phen=1, device=local, representation=capi.GE_REP_SEGMENTS if segs else capi.GE_REP_BITS,
                       rng_mode=capi.GE_RNG_PHILOX, seed=12345, capacity=cap)
     kid = capi.GE_KERNEL_RECOMBINE_SEGMENTS if segs else capi.GE_KERNEL_PROPAGATE_BITS
-    kname = "seg_recombine_kernel (count + fill)" if segs else "propagate_bits_kernel"
+    kname = "seg_plan_kernel + seg_gather_kernel" if segs else "propagate_bits_kernel"
     workloads.configure_engine(eng, cfg)
     eng.init_generation0()
     gp = [capi.gen_params(N, cfg["mat_cor"], "p", "logit", 0.0, 1.0)]

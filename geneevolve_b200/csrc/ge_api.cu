@@ -260,6 +260,7 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     c->cv_from_segments = std::getenv("GE_CV_FROM_SEGMENTS") != nullptr;
     c->seg_per_thread = std::getenv("GE_SEG_PER_THREAD") != nullptr;
     if (const char *t = std::getenv("GE_SEG_GROUP")) c->seg_group = std::atoi(t);
+    c->seg_walk = std::getenv("GE_SEG_WALK") != nullptr;
     if (const char *t = std::getenv("GE_PROP_DEPTH")) c->prop_depth = std::atoi(t);
     if (const char *t = std::getenv("GE_PROP")) c->use_tma = std::string(t) == "tma";
     if (const char *t = std::getenv("GE_THIN_MIN_GB")) c->thin_min_bytes = std::atof(t) * 1e9;  // measurement aid: queue the bulk kernel on the control stream (no overlap)

@@ -139,6 +139,8 @@ struct ge_ctx {
     bool bulk_busy = false;
     int prop_depth = 4;
     int seg_group = 0;              // GE_SEG_GROUP: force 1, 8 or 32 lanes per slot in the segment recombination (0 = by list length)
+    bool seg_walk = false;          // GE_SEG_WALK: the two walk passes (seg_recombine_warp_kernel) instead of plan + gather
+    Buf seg_desc, seg_iv_off;       // copy descriptor and output offset of every interval (seg_plan_kernel -> seg_gather_kernel)
     bool seg_per_thread = false;    // a genetic map with rows closer than bp_dist_in_rmap was given, or GE_SEG_PER_THREAD is set
     bool cv_from_segments = false;  // GE_CV_FROM_SEGMENTS: ge_compute_AD rescans the segment lists every generation like the reference
     bool use_tma = false, tma_attr_set = false;

@@ -177,6 +177,197 @@ __global__ void seg_recombine_warp_kernel(SegArgs a, uint32_t *__restrict__ coun
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Plan + gather: the form the segment path runs at scale (lists of >= 30 parts).  ncu on the walk kernels above
+// (1M individuals, generation 41) showed both passes ISSUE-bound (81 % / 65 % issue-active at 1.6 / 2.9 TB/s of DRAM
+// traffic): the walk evaluates the clip predicate twice per part (count, fill) and reads the other haplotype's parts
+// just to skip them.  Here the first pass only COUNTS prefixes and the second is a clipped copy:
+//
+//  positions   P_0 = cov_lo, P_j = j-th crossover (j = 1..k), P_{k+1} = cov_hi; interval j = [P_j, P_{j+1}) on
+//              haplotype start_hap ^ (j & 1).
+//  predicate   part (x, y) is emitted for [L, R) iff  y > L  and  (y <= R  or  x < R)  — the union of the four branches of
+//              :2922-2954 for L <= R — and what is emitted is (max(x, L), min(y, R)).
+//  sorted      parental lists are sorted tilings (x and y non-decreasing), so the emitted parts of an interval are the index
+//              range [i0, i1) with i0 = #(y <= L), i1 = max(#(y <= R), #(x < R)).
+//
+//  seg_plan_kernel    one thread per slot: for every interval two binary searches over the .y column of its haplotype (from
+//                     that haplotype's previous end); writes a 16-byte copy descriptor and the part count of every interval.
+//  (scan of the interval counts -> absolute output offset of every interval; seg_slot_offsets_kernel -> the new CSR offsets)
+//  seg_gather_kernel  flat clipped copy over all intervals, load-balanced by output part, fully coalesced stores.
+// Two warp-per-slot forms were built and measured first (bit-identical, GPU tests green): balloting the prefix counts chunk by
+// chunk (450 warp instructions per slot, slower than the walk) and a per-slot gather (52 % of stalls on one DRAM round trip per
+// interval, then 314 instructions per slot once flattened inside the warp).  The per-slot prologue — a division, six dependent
+// loads — is what both paid; here only the thread-per-slot plan pays it.
+// Slots whose positions do not ascend are done by one thread with the reference's loop verbatim (descriptor y = 0xFFFFFFFF).
+// ------------------------------------------------------------------------------------------------
+template <bool FILL>
+__device__ __forceinline__ uint32_t seg_recombine_verbatim(const uint4 *H0, uint32_t n0, const uint4 *H1, uint32_t n1, const uint32_t *__restrict__ xo, uint32_t k,
+                                                           uint32_t lo_c, uint32_t hi_c, int hi, uint4 *out) {
+    uint32_t n = 0, cur0 = 0, cur1 = 0, prevL = 0;
+    for (uint32_t i1 = 1; i1 <= k + 1; i1++) {
+        uint32_t L = i1 == 1 ? lo_c : xo[i1 - 2];
+        uint32_t R = i1 == k + 1 ? hi_c : xo[i1 - 1];
+        if (L < prevL) { cur0 = 0; cur1 = 0; }
+        prevL = L;
+        const uint4 *H = hi ? H1 : H0;
+        uint32_t nH = hi ? n1 : n0, i2 = hi ? cur1 : cur0;
+        while (i2 < nH && H[i2].y <= L) i2++;
+        if (hi) cur1 = i2; else cur0 = i2;
+        if (i2 < nH) { uint4 q = H[i2]; if (q.x < L && L < q.y && R < q.y) { if (FILL) out[n] = make_uint4(L, R, q.z, q.w); n++; i2++; } }
+        if (i2 < nH) { uint4 q = H[i2]; if (q.x < L && L < q.y && R >= q.y) { if (FILL) out[n] = make_uint4(L, q.y, q.z, q.w); n++; i2++; } }
+        while (i2 < nH) { uint4 q = H[i2]; if (!(q.y <= R && L <= q.x)) break; if (FILL) out[n] = q; n++; i2++; }
+        if (i2 < nH) { uint4 q = H[i2]; if (q.x < R && R < q.y) { if (FILL) out[n] = make_uint4(q.x, R, q.z, q.w); n++; } }
+        hi ^= 1;
+    }
+    return n;
+}
+
+struct SegSlot {   // what both passes need to know about one offspring haplotype slot
+    const uint4 *H0, *H1;
+    uint32_t n0, n1, k, c;
+    uint64_t e0, slot;
+    int hi;
+};
+__device__ __forceinline__ SegSlot seg_slot(const SegArgs &a, uint64_t t) {
+    SegSlot s;
+    const uint32_t per = (uint32_t)a.n_chr * 2u;
+    uint64_t i; uint32_t r;
+    if (t <= 0xFFFFFFFFull) { const uint32_t t32 = (uint32_t)t, q = t32 / per; i = q; r = t32 - q * per; }   // 32-bit division: the 64-bit one is ~100 instructions
+    else { i = t / per; r = (uint32_t)(t - i * per); }
+    i += a.off_first;
+    s.slot = a.off_first * per + t;
+    s.c = r >> 1;
+    const uint32_t parent = (r & 1u) ? a.mother[i] : a.father[i];
+    const uint64_t ps = ((uint64_t)parent * a.n_chr + s.c) * 2;
+    const uint64_t o0 = a.par_off[ps], o1 = a.par_off[ps + 1], o2 = a.par_off[ps + 2];
+    s.H0 = a.par_seg + o0; s.H1 = a.par_seg + o1;
+    s.n0 = (uint32_t)(o1 - o0); s.n1 = (uint32_t)(o2 - o1);
+    s.e0 = a.xo_off[s.slot];
+    s.k = (uint32_t)(a.xo_off[s.slot + 1] - s.e0);
+    s.hi = a.start_hap[s.slot] & 1;
+    return s;
+}
+
+constexpr uint32_t SEG_PLAN_VERBATIM = 0xFFFFFFFFu;
+
+// #(y <= X) among parts [lo, n) of a list with non-decreasing y, plus lo
+__device__ __forceinline__ uint32_t seg_count_y_le(const uint4 *__restrict__ H, uint32_t lo, uint32_t n, uint32_t X) {
+    uint32_t hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&H[mid].y) <= X) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// One THREAD per slot: two binary searches per interval over the .y column (about 1 KB of sectors per slot instead of the
+// 2.7 KB of both lists, and ~10 warp instructions per slot instead of ~400 for a warp that ballots its way through them).
+// Interval g = xo_off[slot] + slot + j gets a copy descriptor {absolute index of its first parental part (64 bit), L, R} and its
+// part count; the scan of the counts gives every interval its absolute output offset, so the copy itself knows nothing of slots.
+__global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__restrict__ iv_count, uint4 *__restrict__ desc, int *__restrict__ n_verbatim) {
+    const uint64_t n_total = a.n_off * a.n_chr * 2;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const SegSlot s = seg_slot(a, t);
+        const uint64_t g = s.e0 + s.slot;
+        const uint64_t b0 = (uint64_t)(s.H0 - a.par_seg), b1 = (uint64_t)(s.H1 - a.par_seg);
+        if (s.k == 0) {   // the chosen parental haplotype unchanged (:2910): one unclipped interval
+            const uint64_t src = s.hi ? b1 : b0;
+            desc[g] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), 0u, 0xFFFFFFFFu);
+            iv_count[g] = s.hi ? s.n1 : s.n0;
+            continue;
+        }
+        const uint32_t lo_c = a.cov_lo[s.c], hi_c = a.cov_hi[s.c];
+        const uint32_t *xo = a.xo_bp + s.e0;
+        bool fast = true;   // positions must ascend: cov_lo <= X_1 <= ... <= X_k <= cov_hi
+        {
+            uint32_t prev = lo_c;
+            for (uint32_t j = 0; j < s.k; j++) { const uint32_t x = __ldg(xo + j); fast &= x >= prev; prev = x; }
+            fast &= hi_c >= prev;
+        }
+        if (!fast) {   // the reference's loop verbatim (seg_verbatim_fill_kernel writes the parts)
+            const uint32_t n = seg_recombine_verbatim<false>(s.H0, s.n0, s.H1, s.n1, xo, s.k, lo_c, hi_c, s.hi, nullptr);
+            desc[g] = make_uint4(0u, SEG_PLAN_VERBATIM, 0u, 0u);
+            iv_count[g] = n;
+            for (uint32_t j = 1; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
+            atomicAdd(n_verbatim, 1);
+            continue;
+        }
+        uint32_t cur0 = 0, cur1 = 0, L = lo_c;
+        int h = s.hi;
+        for (uint32_t j = 0; j <= s.k; j++) {
+            const uint32_t R = j == s.k ? hi_c : __ldg(xo + j);
+            const uint4 *H = h ? s.H1 : s.H0;
+            const uint32_t nH = h ? s.n1 : s.n0;
+            const uint32_t i0 = seg_count_y_le(H, h ? cur1 : cur0, nH, L);   // first part with y > L
+            const uint32_t c = seg_count_y_le(H, i0, nH, R);                 // #(y <= R)
+            uint32_t i1 = c;                                                  // max(#(y <= R), #(x < R)), x non-decreasing
+            while (i1 < nH && __ldg(&H[i1].x) < R) i1++;
+            if (h) cur1 = c; else cur0 = c;
+            const uint64_t src = (h ? b1 : b0) + i0;
+            desc[g + j] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), L, R);
+            iv_count[g + j] = i1 - i0;
+            L = R; h ^= 1;
+        }
+    }
+}
+
+// CSR offsets of the new generation: slot -> output offset of its first interval
+__global__ void seg_slot_offsets_kernel(uint64_t n_slots, uint64_t slot0, const uint64_t *__restrict__ xo_off, const uint64_t *__restrict__ iv_off, uint64_t *__restrict__ off) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= n_slots) off[t] = iv_off[xo_off[slot0 + t] + slot0 + t];
+}
+
+// The copy: a CTA takes SEG_GATHER_IV consecutive intervals (descriptors and offsets staged in shared memory with coalesced
+// loads) and its threads walk the flat run of output parts those intervals own — every thread finds the interval of its output
+// index by a branch-free binary search of the staged offsets, four independent 16-byte loads per thread are in flight before the
+// first clip, and the stores of a warp are 512 contiguous bytes.  No per-slot prologue, no idle lanes on short intervals.
+constexpr int SEG_GATHER_IV = 128;
+__global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict__ desc, const uint64_t *__restrict__ iv_off, uint64_t n_iv,
+                                                         const uint4 *__restrict__ par_seg, uint4 *__restrict__ off_seg) {
+    __shared__ uint32_t s_rel[SEG_GATHER_IV + 1];
+    __shared__ uint4 s_desc[SEG_GATHER_IV];
+    const uint32_t tid = threadIdx.x;
+    for (uint64_t g0 = (uint64_t)blockIdx.x * SEG_GATHER_IV; g0 < n_iv; g0 += (uint64_t)gridDim.x * SEG_GATHER_IV) {
+        const uint32_t m = (uint32_t)min((uint64_t)SEG_GATHER_IV, n_iv - g0);
+        const uint64_t o0 = iv_off[g0];
+        if (tid < m) s_desc[tid] = desc[g0 + tid];
+        if (tid <= SEG_GATHER_IV) s_rel[tid] = (uint32_t)(iv_off[g0 + min(tid, m)] - o0);   // entries beyond m repeat the end: the search never lands there
+        __syncthreads();
+        const uint32_t n = s_rel[m];
+        uint4 *out = off_seg + o0;
+        for (uint32_t base = 0; base < n; base += 256 * 4) {
+            uint4 q[4];
+            uint32_t L[4], R[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t idx = base + u * 256 + tid;
+                uint32_t lo = 0;   // last interval whose first output is <= idx (empty intervals share an offset: the last one owns it)
+#pragma unroll
+                for (int w = SEG_GATHER_IV / 2; w > 0; w >>= 1) if (s_rel[lo + w] <= idx) lo += w;
+                const uint4 d = s_desc[lo];
+                ok[u] = idx < n && d.y != SEG_PLAN_VERBATIM;
+                L[u] = d.z; R[u] = d.w;
+                if (ok[u]) q[u] = ld_stream(par_seg + ((((uint64_t)d.y) << 32 | d.x) + (idx - s_rel[lo])));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (ok[u]) { q[u].x = max(q[u].x, L[u]); q[u].y = min(q[u].y, R[u]); st_stream(out + (base + u * 256 + tid), q[u]); }
+        }
+        __syncthreads();
+    }
+}
+
+// slots the plan could not turn into index ranges (rare: positions that do not ascend): the reference's loop writes them
+__global__ void seg_verbatim_fill_kernel(SegArgs a, const uint4 *__restrict__ desc, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg) {
+    const uint64_t n_total = a.n_off * a.n_chr * 2;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const SegSlot s = seg_slot(a, t);
+        if (s.k == 0 || desc[s.e0 + s.slot].y != SEG_PLAN_VERBATIM) continue;
+        seg_recombine_verbatim<true>(s.H0, s.n0, s.H1, s.n1, a.xo_bp + s.e0, s.k, a.cov_lo[s.c], a.cov_hi[s.c], s.hi, off_seg + off_off[s.slot]);
+    }
+}
+
 // ras_find_cv (:2752-2815) on the segment lists: allele bit plane / root byte plane.  One thread per (haplotype
 // row, word of the CV bit plane); every CV of the word scans the segment list of its chromosome (the LAST part that
 // covers the position wins, like the reference's loop over all parts).
@@ -302,11 +493,28 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     const double avg_parts = (double)par.seg.n_seg / (double)std::max<uint64_t>(1, par.n * C * 2);
     int group = ctx->seg_per_thread ? 1 : (ctx->seg_group > 0 ? ctx->seg_group : (avg_parts < 30 ? 1 : 32));  // measured cross-over at ~30 parts per list (1M individuals)
     const unsigned wgrid = (unsigned)std::min<uint64_t>(nblk(n_slots * (uint64_t)group, 256), (uint64_t)ctx->n_sm * 64);
-    if (group == 1) seg_recombine_kernel<false><<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
+    const bool plan = group == 32 && !ctx->seg_walk;   // plan + gather (default at scale); GE_SEG_WALK=1 keeps the two walk passes for A/B runs
+    const uint64_t n_iv = P.n_xo + n_slots;            // intervals: one more than crossovers in every slot
+    if (plan) {
+        GE_TRY(ctx->ensure(P.cnt32, (n_iv + 1) * 4));
+        GE_TRY(ctx->ensure(ctx->seg_desc, (size_t)(n_iv + 1) * 16));
+        GE_TRY(ctx->ensure(ctx->seg_iv_off, (size_t)(n_iv + 1) * 8));
+        CUDA_TRY(cudaMemsetAsync(ctx->flags.as<int>() + 2, 0, 4, ctx->stream));
+        seg_plan_kernel<<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->flags.as<int>() + 2);
+    } else if (group == 1) seg_recombine_kernel<false><<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
     else if (group == 8) seg_recombine_warp_kernel<false, 8><<<wgrid, 256, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
     else seg_recombine_warp_kernel<false, 32><<<wgrid, 256, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
     GE_TRY(ctx->check_launch("seg_recombine<count>"));
     if (ctx->profiling) CUDA_TRY(cudaEventRecord(ev1.b, ctx->stream));
+    int n_verbatim = 0;
+    if (plan) {
+        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_iv, ctx->seg_iv_off.as<uint64_t>(), nullptr));
+        seg_slot_offsets_kernel<<<nblk(n_slots + 1, 256), 256, 0, ctx->stream>>>(n_slots, 0, a.xo_off, ctx->seg_iv_off.as<uint64_t>(), off.seg.off.as<uint64_t>());
+        GE_TRY(ctx->check_launch("seg_slot_offsets"));
+        CUDA_TRY(cudaMemcpyAsync(&off.seg.n_seg, ctx->scan_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&n_verbatim, ctx->flags.as<int>() + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    } else
     GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, off.seg.off.as<uint64_t>(), &off.seg.n_seg));
     if (ctx->cfg.seg_capacity && off.seg.n_seg > ctx->cfg.seg_capacity) return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity");
     // lists grow by ~36 parts per individual-haplotype-genome per generation: size the buffer once when the caller
@@ -315,7 +523,14 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     if (ctx->cfg.seg_capacity) want = ctx->cfg.seg_capacity; else if (want * 16 > off.seg.seg.cap) want += want / 2;
     GE_TRY(ctx->ensure_exact(off.seg.seg, want * 16));
     if (ctx->profiling) { ev2.a = ctx->get_event(); ev2.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev2.a, ctx->stream)); }
-    if (group == 1) seg_recombine_kernel<true><<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+    if (plan) {
+        const unsigned ggrid = (unsigned)std::min<uint64_t>(nblk(n_iv, SEG_GATHER_IV), 1u << 30);
+        seg_gather_kernel<<<ggrid, 256, 0, ctx->stream>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, a.par_seg, off.seg.seg.as<uint4>());
+        if (n_verbatim) {
+            GE_TRY(ctx->check_launch("seg_gather"));
+            seg_verbatim_fill_kernel<<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, ctx->seg_desc.as<uint4>(), off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+        }
+    } else if (group == 1) seg_recombine_kernel<true><<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
     else if (group == 8) seg_recombine_warp_kernel<true, 8><<<wgrid, 256, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
     else seg_recombine_warp_kernel<true, 32><<<wgrid, 256, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
     GE_TRY(ctx->check_launch("seg_recombine<fill>"));

@@ -147,6 +147,34 @@ def test_hundreds_of_crossovers_per_gamete(cuda_lib):
     run_pair(cuda_lib, case, [(6, xo), (5, xo)], rep=capi.GE_REP_BITS)
 
 
+@pytest.mark.parametrize("walk", [False, True])
+def test_segment_warp_kernels_long_lists_and_many_crossovers(cuda_lib, monkeypatch, walk):
+    """The kernels the segment path runs at scale (GE_SEG_GROUP=32: seg_plan_kernel + seg_gather_kernel, or the two walk
+    passes with GE_SEG_WALK) against the oracle's verbatim `recombine`: lists that grow past several 32-part chunks, slots
+    without crossovers, crossovers on map rows / loci / duplicated, and slots with more than 30 crossovers (lane-0 fallback)."""
+    monkeypatch.setenv("GE_SEG_GROUP", "32")
+    if walk:
+        monkeypatch.setenv("GE_SEG_WALK", "1")
+    case = Case(31, [900, 60, 7], map_rows=50, step=128)
+
+    def xo(slot, c):
+        bp, _, step = case.maps[c]
+        r = case.rng
+        choice = slot % 7
+        if choice == 0:
+            return []
+        if choice == 1:
+            return [int(bp[0])]
+        if choice == 2:
+            p = int(case.loci[c][len(case.loci[c]) // 2])
+            return [p, p, int(bp[-1])]
+        if choice == 3:
+            return np.sort(r.integers(int(bp[0]), int(bp[-1]) + step, size=45))      # > 30 crossovers: verbatim fallback
+        return np.sort(r.integers(int(bp[0]), int(bp[-1]) + step, size=int(r.integers(1, 14))))
+
+    run_pair(cuda_lib, case, [(20, xo)] * 9, cap=64)
+
+
 def test_philox_many_crossovers_matches_oracle(cuda_lib):
     """Recombination rates high enough that most gametes exceed the per-slot stash of sample_xo_kernel."""
     case = Case(21, [300, 90], map_rows=60, step=64)

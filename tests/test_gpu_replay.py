@@ -32,8 +32,11 @@ def compare_to_golden(G, eng, gen, pops=None):
 
 
 @pytest.mark.parametrize("name", SCENARIOS)
-@pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS])
-def test_replay_matches_reference(cuda_lib, name, rep):
+@pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS, "segments-at-scale"])
+def test_replay_matches_reference(cuda_lib, name, rep, monkeypatch):
+    if rep == "segments-at-scale":   # the plan + gather kernels the segment path switches to once lists average 30 parts
+        monkeypatch.setenv("GE_SEG_GROUP", "32")
+        rep = capi.GE_REP_SEGMENTS
     G = Golden(name)
     gpu = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_REPLAY, representation=rep))
     cpu = OracleEngine(**G.engine_kwargs(rng_mode=capi.GE_RNG_REPLAY))
