@@ -261,6 +261,8 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     c->seg_per_thread = std::getenv("GE_SEG_PER_THREAD") != nullptr;
     if (const char *t = std::getenv("GE_SEG_GROUP")) c->seg_group = std::atoi(t);
     c->seg_walk = std::getenv("GE_SEG_WALK") != nullptr;
+    c->seg_sync_mode = std::getenv("GE_SEG_SYNC") != nullptr;
+    if (const char *t = std::getenv("GE_SEG_PLAN_MIN")) c->seg_plan_min_parts = std::atof(t);
     if (const char *t = std::getenv("GE_PROP_DEPTH")) c->prop_depth = std::atoi(t);
     if (const char *t = std::getenv("GE_PROP")) c->use_tma = std::string(t) == "tma";
     if (const char *t = std::getenv("GE_THIN_MIN_GB")) c->thin_min_bytes = std::atof(t) * 1e9;  // measurement aid: queue the bulk kernel on the control stream (no overlap)
@@ -294,13 +296,15 @@ int ge_destroy(ge_ctx *ctx) {
         }
         for (GenState &s : P.st) {
             for (Buf *b : {&s.hap, &s.cv_allele, &s.cv_root, &s.ids, &s.sex, &s.A, &s.D, &s.G, &s.C, &s.E, &s.F, &s.P, &s.mv, &s.sv, &s.svf, &s.hm_off, &s.hm_bp}) freeb(*b);
+            for (cudaEvent_t e : s.seg.ev) if (e) cudaEventDestroy(e);
             seg_release(s.seg);
         }
         mate_release(P.mate);
     }
     for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_bkt_off, &ctx->d_bkt_shift, &ctx->d_bkt, &ctx->d_LA, &ctx->d_cv_bitpos, &ctx->xo_stash, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
                    &ctx->d_cv_block_off, &ctx->d_cv_word_off, &ctx->d_cv_word_blk, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks,
-                   &ctx->scan_total, &ctx->partial, &ctx->scalars, &ctx->flags, &ctx->d_chr_ids, &ctx->ar_scratch})
+                   &ctx->scan_total, &ctx->partial, &ctx->scalars, &ctx->flags, &ctx->d_chr_ids, &ctx->ar_scratch, &ctx->seg_desc, &ctx->seg_iv_off, &ctx->seg_cnt,
+                   &ctx->seg_scan_blocks, &ctx->seg_scan_total, &ctx->seg_flags, &ctx->seg_verb})
         freeb(*b);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_join);
     for (auto &e : ctx->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -975,6 +979,7 @@ int ge_set_migration_sample(ge_ctx *ctx, int src, const uint64_t *pos, uint64_t 
 int ge_do_migration(ge_ctx *ctx, int gen, const double *row) {  // ras_do_migration :877-989
     CHECK_CTX(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(seg_finish_all(ctx));
     return migrate(ctx, gen, row);
 }
 
@@ -1174,25 +1179,28 @@ int ge_set_profiling(ge_ctx *ctx, int enabled) { CHECK_CTX(ctx); ctx->profiling 
 int ge_get_kernel_time(ge_ctx *ctx, int k, double *ms, uint64_t *launches, uint64_t *bytes) {
     CHECK_CTX(ctx);
     if (k < 0 || k >= GE_KERNEL_COUNT) return fail(GE_ERR_INVALID, "bad kernel id");
+    GE_TRY(seg_finish_all(ctx));
     ctx->resolve_events();
     *ms = ctx->kstat[k].ms; *launches = ctx->kstat[k].launches; *bytes = ctx->kstat[k].bytes;
     return GE_OK;
 }
-int ge_reset_kernel_times(ge_ctx *ctx) { CHECK_CTX(ctx); ctx->resolve_events(); for (auto &k : ctx->kstat) k = KernelStat(); ctx->launches = 0; return GE_OK; }
+int ge_reset_kernel_times(ge_ctx *ctx) { CHECK_CTX(ctx); GE_TRY(seg_finish_all(ctx)); ctx->resolve_events(); for (auto &k : ctx->kstat) k = KernelStat(); ctx->launches = 0; return GE_OK; }
 int ge_get_launch_count(ge_ctx *ctx, uint64_t *n) { CHECK_CTX(ctx); *n = ctx->launches; return GE_OK; }
 int ge_synchronize(ge_ctx *ctx) {
     CHECK_CTX(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(seg_finish_all(ctx));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->bulk));
     return GE_OK;
 }
 int ge_device_memory_bytes(ge_ctx *ctx, uint64_t *b) { CHECK_CTX(ctx); *b = ctx->mem_peak; return GE_OK; }
 // both streams are joined on either side, so the region covers the bulk propagation of every step queued in between
-int ge_timer_start(ge_ctx *ctx) { CHECK_CTX(ctx); CUDA_TRY(cudaSetDevice(ctx->cfg.device)); GE_TRY(ctx->join_bulk()); CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream)); return GE_OK; }
+int ge_timer_start(ge_ctx *ctx) { CHECK_CTX(ctx); CUDA_TRY(cudaSetDevice(ctx->cfg.device)); GE_TRY(seg_finish_all(ctx)); GE_TRY(ctx->join_bulk()); CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream)); return GE_OK; }
 int ge_timer_stop(ge_ctx *ctx, double *ms) {
     CHECK_CTX(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(seg_finish_all(ctx));
     GE_TRY(ctx->join_bulk());
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(cudaEventSynchronize(ctx->ev1));

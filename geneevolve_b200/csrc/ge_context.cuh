@@ -37,6 +37,11 @@ struct SegState {   // founder segments of one generation (GE_REP_SEGMENTS): CSR
     Buf off, seg;   // off: uint64 [n_slots+1]; seg: uint4 {st, en, hap_index, root_population}
     uint64_t n_seg = 0;
     bool valid = false;
+    // asynchronous form (bulk stream, seg_capacity given): n_seg arrives in pinned host memory behind `ready`
+    bool pending = false;
+    cudaEvent_t ready = nullptr;
+    uint64_t *h_total = nullptr;              // pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // profiling events of the two passes, accounted when n_seg is known
 };
 // The four sorts of assortative mating (males and females by mating value, the two template columns) are independent
 // and, at <= N/2 keys each, pure launch latency (8 radix passes of ~10 us): they run side by side on four lanes.
@@ -141,6 +146,9 @@ struct ge_ctx {
     int seg_group = 0;              // GE_SEG_GROUP: force 1, 8 or 32 lanes per slot in the segment recombination (0 = by list length)
     bool seg_walk = false;          // GE_SEG_WALK: the two walk passes (seg_recombine_warp_kernel) instead of plan + gather
     Buf seg_desc, seg_iv_off;       // copy descriptor and output offset of every interval (seg_plan_kernel -> seg_gather_kernel)
+    Buf seg_cnt, seg_scan_blocks, seg_scan_total, seg_flags, seg_verb;   // scratch of the segment path (its own: it may run on the bulk stream)
+    double seg_plan_min_parts = 0;  // GE_SEG_PLAN_MIN: parts per parental list below which the thread-per-slot walk is used (measured: plan + gather wins from generation 1)
+    bool seg_sync_mode = false;     // GE_SEG_SYNC: never queue the segment path on the bulk stream
     bool seg_per_thread = false;    // a genetic map with rows closer than bp_dist_in_rmap was given, or GE_SEG_PER_THREAD is set
     bool cv_from_segments = false;  // GE_CV_FROM_SEGMENTS: ge_compute_AD rescans the segment lists every generation like the reference
     bool use_tma = false, tma_attr_set = false;
@@ -291,24 +299,30 @@ struct ge_ctx {
     }
     // device exclusive scan: out[0..n] (n+1 entries), grand total also returned to the host when asked
     int exclusive_scan(const uint32_t *in, uint64_t n, uint64_t *out, uint64_t *host_total) {
-        if (n == 0) {
-            CUDA_TRY(cudaMemsetAsync(out, 0, 8, stream));
-            if (host_total) *host_total = 0;
-            return GE_OK;
-        }
-        uint32_t nb = nblk(n, SCAN_THREADS * SCAN_ITEMS);
-        GE_TRY(ensure(scan_blocks, (size_t)nb * 8));
-        GE_TRY(ensure(scan_total, 8));
-        scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_blocks.as<uint64_t>());
-        GE_TRY(check_launch("scan_block_sums"));
-        scan_single_block_kernel<<<1, SCAN_THREADS, 0, stream>>>(scan_blocks.as<uint64_t>(), nb, scan_total.as<uint64_t>());
-        GE_TRY(check_launch("scan_single_block"));
-        scan_final_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_blocks.as<uint64_t>(), out);
-        GE_TRY(check_launch("scan_final"));
+        GE_TRY(exclusive_scan_on(stream, scan_blocks, scan_total, in, n, out));
         if (host_total) {
+            if (n == 0) { *host_total = 0; return GE_OK; }
             CUDA_TRY(cudaMemcpyAsync(host_total, scan_total.p, 8, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
         }
+        return GE_OK;
+    }
+    // the same on any stream with its own scratch (the segment path scans on the bulk stream); the total stays in total.p
+    int exclusive_scan_on(cudaStream_t st, Buf &blocks, Buf &total, const uint32_t *in, uint64_t n, uint64_t *out) {
+        GE_TRY(ensure(total, 8));
+        if (n == 0) {
+            CUDA_TRY(cudaMemsetAsync(out, 0, 8, st));
+            CUDA_TRY(cudaMemsetAsync(total.p, 0, 8, st));
+            return GE_OK;
+        }
+        uint32_t nb = nblk(n, SCAN_THREADS * SCAN_ITEMS);
+        GE_TRY(ensure(blocks, (size_t)nb * 8));
+        scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>());
+        GE_TRY(check_launch("scan_block_sums"));
+        scan_single_block_kernel<<<1, SCAN_THREADS, 0, st>>>(blocks.as<uint64_t>(), nb, total.as<uint64_t>());
+        GE_TRY(check_launch("scan_single_block"));
+        scan_final_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>(), out);
+        GE_TRY(check_launch("scan_final"));
         return GE_OK;
     }
     // mean (denominator n) or variance (two-pass, n-1) of a device column into a device scalar

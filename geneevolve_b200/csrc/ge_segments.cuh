@@ -260,11 +260,27 @@ __device__ __forceinline__ uint32_t seg_count_y_le(const uint4 *__restrict__ H, 
     return lo;
 }
 
+// two such searches with independent loads in flight (XA <= XB in every caller that matters, not required)
+__device__ __forceinline__ void seg_count_y_le2(const uint4 *__restrict__ H, uint32_t lo, uint32_t n, uint32_t XA, uint32_t XB, uint32_t &rA, uint32_t &rB) {
+    uint32_t loA = lo, hiA = n, loB = lo, hiB = n;
+    while (loA < hiA || loB < hiB) {
+        const bool actA = loA < hiA, actB = loB < hiB;
+        const uint32_t mA = (loA + hiA) >> 1, mB = (loB + hiB) >> 1;
+        uint32_t yA = 0, yB = 0;
+        if (actA) yA = __ldg(&H[mA].y);
+        if (actB) yB = __ldg(&H[mB].y);
+        if (actA) { if (yA <= XA) loA = mA + 1; else hiA = mA; }
+        if (actB) { if (yB <= XB) loB = mB + 1; else hiB = mB; }
+    }
+    rA = loA; rB = loB;
+}
+
 // One THREAD per slot: two binary searches per interval over the .y column (about 1 KB of sectors per slot instead of the
 // 2.7 KB of both lists, and ~10 warp instructions per slot instead of ~400 for a warp that ballots its way through them).
 // Interval g = xo_off[slot] + slot + j gets a copy descriptor {absolute index of its first parental part (64 bit), L, R} and its
 // part count; the scan of the counts gives every interval its absolute output offset, so the copy itself knows nothing of slots.
-__global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__restrict__ iv_count, uint4 *__restrict__ desc, int *__restrict__ n_verbatim) {
+__global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__restrict__ iv_count, uint4 *__restrict__ desc, unsigned int *__restrict__ n_verbatim,
+                                                       uint64_t *__restrict__ verb_list, uint32_t verb_cap) {
     const uint64_t n_total = a.n_off * a.n_chr * 2;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
         const SegSlot s = seg_slot(a, t);
@@ -278,18 +294,26 @@ __global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__re
         }
         const uint32_t lo_c = a.cov_lo[s.c], hi_c = a.cov_hi[s.c];
         const uint32_t *xo = a.xo_bp + s.e0;
-        bool fast = true;   // positions must ascend: cov_lo <= X_1 <= ... <= X_k <= cov_hi
+        bool fast = true;   // positions must ascend: cov_lo <= X_1 <= ... <= X_k
         {
             uint32_t prev = lo_c;
             for (uint32_t j = 0; j < s.k; j++) { const uint32_t x = __ldg(xo + j); fast &= x >= prev; prev = x; }
-            fast &= hi_c >= prev;
+            if (fast && prev > hi_c) {
+                // a crossover in the last map row lies beyond cov_hi, so the last interval has L > R.  The reference's loop first skips
+                // every part with y <= L: if that is the whole list (the normal case, lists end at cov_hi) the interval emits nothing,
+                // which is what the index range gives (i0 = n).  Anything else goes to the verbatim loop.
+                const int hl = s.hi ^ (int)(s.k & 1u);
+                const uint32_t nl = hl ? s.n1 : s.n0;
+                fast = nl == 0 || __ldg(&(hl ? s.H1 : s.H0)[nl - 1].y) <= prev;
+            }
         }
         if (!fast) {   // the reference's loop verbatim (seg_verbatim_fill_kernel writes the parts)
             const uint32_t n = seg_recombine_verbatim<false>(s.H0, s.n0, s.H1, s.n1, xo, s.k, lo_c, hi_c, s.hi, nullptr);
             desc[g] = make_uint4(0u, SEG_PLAN_VERBATIM, 0u, 0u);
             iv_count[g] = n;
             for (uint32_t j = 1; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
-            atomicAdd(n_verbatim, 1);
+            const unsigned int w = atomicAdd(n_verbatim, 1u);
+            if (w < verb_cap) verb_list[w] = t;
             continue;
         }
         uint32_t cur0 = 0, cur1 = 0, L = lo_c;
@@ -298,8 +322,9 @@ __global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__re
             const uint32_t R = j == s.k ? hi_c : __ldg(xo + j);
             const uint4 *H = h ? s.H1 : s.H0;
             const uint32_t nH = h ? s.n1 : s.n0;
-            const uint32_t i0 = seg_count_y_le(H, h ? cur1 : cur0, nH, L);   // first part with y > L
-            const uint32_t c = seg_count_y_le(H, i0, nH, R);                 // #(y <= R)
+            uint32_t i0, c;                                                   // first part with y > L; #(y <= R) — searched side by side
+            seg_count_y_le2(H, h ? cur1 : cur0, nH, L, R, i0, c);
+            c = max(c, i0);                                                   // (L > R only in the checked last-row case, where both are n)
             uint32_t i1 = c;                                                  // max(#(y <= R), #(x < R)), x non-decreasing
             while (i1 < nH && __ldg(&H[i1].x) < R) i1++;
             if (h) cur1 = c; else cur0 = c;
@@ -323,7 +348,7 @@ __global__ void seg_slot_offsets_kernel(uint64_t n_slots, uint64_t slot0, const 
 // first clip, and the stores of a warp are 512 contiguous bytes.  No per-slot prologue, no idle lanes on short intervals.
 constexpr int SEG_GATHER_IV = 128;
 __global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict__ desc, const uint64_t *__restrict__ iv_off, uint64_t n_iv,
-                                                         const uint4 *__restrict__ par_seg, uint4 *__restrict__ off_seg) {
+                                                         const uint4 *__restrict__ par_seg, uint4 *__restrict__ off_seg, uint64_t cap) {
     __shared__ uint32_t s_rel[SEG_GATHER_IV + 1];
     __shared__ uint4 s_desc[SEG_GATHER_IV];
     const uint32_t tid = threadIdx.x;
@@ -333,7 +358,9 @@ __global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict
         if (tid < m) s_desc[tid] = desc[g0 + tid];
         if (tid <= SEG_GATHER_IV) s_rel[tid] = (uint32_t)(iv_off[g0 + min(tid, m)] - o0);   // entries beyond m repeat the end: the search never lands there
         __syncthreads();
-        const uint32_t n = s_rel[m];
+        // parts beyond the buffer are not written (asynchronous form: the host learns the total only afterwards and reports GE_ERR_CAPACITY)
+        const uint64_t room = cap > o0 ? cap - o0 : 0;
+        const uint32_t n = room < (uint64_t)s_rel[m] ? (uint32_t)room : s_rel[m];
         uint4 *out = off_seg + o0;
         for (uint32_t base = 0; base < n; base += 256 * 4) {
             uint4 q[4];
@@ -358,12 +385,18 @@ __global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict
     }
 }
 
-// slots the plan could not turn into index ranges (rare: positions that do not ascend): the reference's loop writes them
-__global__ void seg_verbatim_fill_kernel(SegArgs a, const uint4 *__restrict__ desc, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg) {
-    const uint64_t n_total = a.n_off * a.n_chr * 2;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const SegSlot s = seg_slot(a, t);
+// slots the plan could not turn into index ranges (rare: positions that do not ascend): the reference's loop writes them.
+// Always launched with a small grid: it walks the list the plan appended to (or, if the list overflowed, every slot).
+__global__ void seg_verbatim_fill_kernel(SegArgs a, const uint4 *__restrict__ desc, const unsigned int *__restrict__ n_verbatim, const uint64_t *__restrict__ verb_list,
+                                         uint32_t verb_cap, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg, uint64_t cap) {
+    const unsigned int nv = *n_verbatim;
+    if (nv == 0) return;
+    const bool listed = nv <= verb_cap;
+    const uint64_t n_total = listed ? nv : a.n_off * a.n_chr * 2;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_total; w += (uint64_t)gridDim.x * blockDim.x) {
+        const SegSlot s = seg_slot(a, listed ? verb_list[w] : w);
         if (s.k == 0 || desc[s.e0 + s.slot].y != SEG_PLAN_VERBATIM) continue;
+        if (off_off[s.slot + 1] > cap) continue;
         seg_recombine_verbatim<true>(s.H0, s.n0, s.H1, s.n1, a.xo_bp + s.e0, s.k, a.cov_lo[s.c], a.cov_hi[s.c], s.hi, off_seg + off_off[s.slot]);
     }
 }
@@ -457,7 +490,9 @@ __global__ void seg_compact_kernel(uint64_t n_slots, const uint64_t *__restrict_
 
 static void seg_release(SegState &s) {
     for (Buf *b : {&s.off, &s.seg}) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
-    s.valid = false;
+    if (s.ready) { cudaEventDestroy(s.ready); s.ready = nullptr; }
+    if (s.h_total) { cudaFreeHost(s.h_total); s.h_total = nullptr; }
+    s.valid = false; s.pending = false;
 }
 
 static int seg_init_gen0(ge_ctx *ctx, int p, uint64_t n) {
@@ -472,10 +507,39 @@ static int seg_init_gen0(ge_ctx *ctx, int p, uint64_t n) {
     return GE_OK;
 }
 
+// n_seg of a generation whose plan + gather was queued on the bulk stream: wait for the scan's total (not for the gather)
+static int seg_finish(ge_ctx *ctx, GenState &S) {
+    SegState &g = S.seg;
+    if (!g.pending) return GE_OK;
+    g.pending = false;
+    CUDA_TRY(cudaEventSynchronize(g.ready));
+    g.n_seg = g.h_total[0];
+    if (g.ev[0]) {   // 16 B per part: every emitted piece comes from one parental part, read by both passes and written once
+        ctx->ev_pending.push_back(ge_ctx::EvPair{g.ev[0], g.ev[1], GE_KERNEL_RECOMBINE_SEGMENTS, 16 * g.n_seg});
+        ctx->ev_pending.push_back(ge_ctx::EvPair{g.ev[2], g.ev[3], GE_KERNEL_RECOMBINE_SEGMENTS, 32 * g.n_seg});
+        g.ev[0] = g.ev[1] = g.ev[2] = g.ev[3] = nullptr;
+    }
+    if (ctx->cfg.seg_capacity && g.n_seg > ctx->cfg.seg_capacity) {
+        g.valid = false;
+        return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity (" + std::to_string(g.n_seg) + " parts; reported by the first call after the generation that overflowed)");
+    }
+    return GE_OK;
+}
+// before anything on the control stream (or the host) reads segment lists
+static int seg_finish_all(ge_ctx *ctx) {
+    if (!ctx->segs()) return GE_OK;
+    int rc = GE_OK;
+    for (PopDev &P : ctx->pop) for (GenState &S : P.st) { int r = seg_finish(ctx, S); if (r != GE_OK) rc = r; }
+    GE_TRY(ctx->join_bulk());
+    return rc;
+}
+
 static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     PopDev &P = ctx->pop[pop];
     GenState &par = P.st[P.cur], &off = P.st[P.cur ^ 1];
     if (!par.seg.valid) return fail(GE_ERR_INVALID, "parent generation has no segment lists");
+    GE_TRY(seg_finish(ctx, par));
+    GE_TRY(seg_finish(ctx, off));   // (a generation nobody looked at: its events and capacity check)
     int C = ctx->cfg.n_chr;
     uint64_t n_slots = n_off * C * 2;
     SegArgs a;
@@ -483,64 +547,103 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = D.father.as<uint32_t>(); a.mother = D.mother.as<uint32_t>();
     a.xo_off = D.xo_off.as<uint64_t>(); a.xo_bp = D.xo_bp.as<uint32_t>(); a.start_hap = D.start_hap.as<uint8_t>();
     a.par_off = par.seg.off.as<uint64_t>(); a.par_seg = par.seg.seg.as<uint4>(); a.cov_lo = P.d_cov_lo.as<uint32_t>(); a.cov_hi = P.d_cov_hi.as<uint32_t>();
-    GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
-    GE_TRY(ctx->ensure(off.seg.off, (n_slots + 1) * 8));
-    // both passes are timed separately (the scan's host read-back and a possible reallocation lie between them)
-    ge_ctx::EvPair ev1{nullptr, nullptr, GE_KERNEL_RECOMBINE_SEGMENTS, 0}, ev2 = ev1;
-    if (ctx->profiling) { ev1.a = ctx->get_event(); ev1.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev1.a, ctx->stream)); }
-    // lanes per slot: the reference's loop verbatim in one thread while the lists are short (or may be unsorted), a whole
-    // warp once a parental list averages 30 parts (8 lanes per slot, GE_SEG_GROUP=8, never won a measurement)
+    GE_TRY(ctx->ensure(off.seg.off, ((size_t)ctx->cfg.capacity * C * 2 + 1) * 8));
+    // the reference's loop verbatim in one thread per slot while the lists are short (or may be unsorted), plan + gather once a
+    // parental list averages 30 parts (GE_SEG_GROUP forces either; GE_SEG_WALK=1 selects the older warp-per-slot walk passes)
     const double avg_parts = (double)par.seg.n_seg / (double)std::max<uint64_t>(1, par.n * C * 2);
-    int group = ctx->seg_per_thread ? 1 : (ctx->seg_group > 0 ? ctx->seg_group : (avg_parts < 30 ? 1 : 32));  // measured cross-over at ~30 parts per list (1M individuals)
-    const unsigned wgrid = (unsigned)std::min<uint64_t>(nblk(n_slots * (uint64_t)group, 256), (uint64_t)ctx->n_sm * 64);
-    const bool plan = group == 32 && !ctx->seg_walk;   // plan + gather (default at scale); GE_SEG_WALK=1 keeps the two walk passes for A/B runs
-    const uint64_t n_iv = P.n_xo + n_slots;            // intervals: one more than crossovers in every slot
-    if (plan) {
-        GE_TRY(ctx->ensure(P.cnt32, (n_iv + 1) * 4));
-        GE_TRY(ctx->ensure(ctx->seg_desc, (size_t)(n_iv + 1) * 16));
-        GE_TRY(ctx->ensure(ctx->seg_iv_off, (size_t)(n_iv + 1) * 8));
-        CUDA_TRY(cudaMemsetAsync(ctx->flags.as<int>() + 2, 0, 4, ctx->stream));
-        seg_plan_kernel<<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->flags.as<int>() + 2);
-    } else if (group == 1) seg_recombine_kernel<false><<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
-    else if (group == 8) seg_recombine_warp_kernel<false, 8><<<wgrid, 256, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
-    else seg_recombine_warp_kernel<false, 32><<<wgrid, 256, 0, ctx->stream>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
-    GE_TRY(ctx->check_launch("seg_recombine<count>"));
-    if (ctx->profiling) CUDA_TRY(cudaEventRecord(ev1.b, ctx->stream));
-    int n_verbatim = 0;
-    if (plan) {
-        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_iv, ctx->seg_iv_off.as<uint64_t>(), nullptr));
-        seg_slot_offsets_kernel<<<nblk(n_slots + 1, 256), 256, 0, ctx->stream>>>(n_slots, 0, a.xo_off, ctx->seg_iv_off.as<uint64_t>(), off.seg.off.as<uint64_t>());
-        GE_TRY(ctx->check_launch("seg_slot_offsets"));
-        CUDA_TRY(cudaMemcpyAsync(&off.seg.n_seg, ctx->scan_total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(&n_verbatim, ctx->flags.as<int>() + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    } else
-    GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, off.seg.off.as<uint64_t>(), &off.seg.n_seg));
-    if (ctx->cfg.seg_capacity && off.seg.n_seg > ctx->cfg.seg_capacity) return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity");
-    // lists grow by ~36 parts per individual-haplotype-genome per generation: size the buffer once when the caller
-    // gave seg_capacity, otherwise grow geometrically (a reallocation of tens of GB costs more than a generation)
-    uint64_t want = std::max<uint64_t>(off.seg.n_seg, 1);
-    if (ctx->cfg.seg_capacity) want = ctx->cfg.seg_capacity; else if (want * 16 > off.seg.seg.cap) want += want / 2;
-    GE_TRY(ctx->ensure_exact(off.seg.seg, want * 16));
-    if (ctx->profiling) { ev2.a = ctx->get_event(); ev2.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev2.a, ctx->stream)); }
-    if (plan) {
-        const unsigned ggrid = (unsigned)std::min<uint64_t>(nblk(n_iv, SEG_GATHER_IV), 1u << 30);
-        seg_gather_kernel<<<ggrid, 256, 0, ctx->stream>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, a.par_seg, off.seg.seg.as<uint4>());
-        if (n_verbatim) {
-            GE_TRY(ctx->check_launch("seg_gather"));
-            seg_verbatim_fill_kernel<<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, ctx->seg_desc.as<uint4>(), off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+    int group = ctx->seg_per_thread ? 1 : (ctx->seg_group > 0 ? ctx->seg_group : (avg_parts < ctx->seg_plan_min_parts ? 1 : 32));
+    const bool plan = group == 32 && !ctx->seg_walk;
+    if (!plan) {   // ---- two walk passes on the control stream, host read-back of the total in between
+        cudaStream_t st = ctx->stream;
+        GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
+        ge_ctx::EvPair ev1{nullptr, nullptr, GE_KERNEL_RECOMBINE_SEGMENTS, 0}, ev2 = ev1;
+        if (ctx->profiling) { ev1.a = ctx->get_event(); ev1.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev1.a, st)); }
+        const unsigned wgrid = (unsigned)std::min<uint64_t>(nblk(n_slots * (uint64_t)group, 256), (uint64_t)ctx->n_sm * 64);
+        if (group == 1) seg_recombine_kernel<false><<<ctx->ctrl_grid(n_slots, 128), 128, 0, st>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
+        else if (group == 8) seg_recombine_warp_kernel<false, 8><<<wgrid, 256, 0, st>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
+        else seg_recombine_warp_kernel<false, 32><<<wgrid, 256, 0, st>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
+        GE_TRY(ctx->check_launch("seg_recombine<count>"));
+        if (ctx->profiling) CUDA_TRY(cudaEventRecord(ev1.b, st));
+        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, off.seg.off.as<uint64_t>(), &off.seg.n_seg));
+        if (ctx->cfg.seg_capacity && off.seg.n_seg > ctx->cfg.seg_capacity) return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity");
+        // lists grow by ~36 parts per individual-haplotype-genome per generation: size the buffer once when the caller
+        // gave seg_capacity, otherwise grow geometrically (a reallocation of tens of GB costs more than a generation)
+        uint64_t want = std::max<uint64_t>(off.seg.n_seg, 1);
+        if (ctx->cfg.seg_capacity) want = ctx->cfg.seg_capacity; else if (want * 16 > off.seg.seg.cap) want += want / 2;
+        GE_TRY(ctx->ensure_exact(off.seg.seg, want * 16));
+        if (ctx->profiling) { ev2.a = ctx->get_event(); ev2.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev2.a, st)); }
+        if (group == 1) seg_recombine_kernel<true><<<ctx->ctrl_grid(n_slots, 128), 128, 0, st>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+        else if (group == 8) seg_recombine_warp_kernel<true, 8><<<wgrid, 256, 0, st>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+        else seg_recombine_warp_kernel<true, 32><<<wgrid, 256, 0, st>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
+        GE_TRY(ctx->check_launch("seg_recombine<fill>"));
+        if (ctx->profiling) {
+            CUDA_TRY(cudaEventRecord(ev2.b, st));
+            ev1.bytes = 16 * off.seg.n_seg; ev2.bytes = 32 * off.seg.n_seg;
+            ctx->ev_pending.push_back(ev1); ctx->ev_pending.push_back(ev2);
         }
-    } else if (group == 1) seg_recombine_kernel<true><<<ctx->ctrl_grid(n_slots, 128), 128, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
-    else if (group == 8) seg_recombine_warp_kernel<true, 8><<<wgrid, 256, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
-    else seg_recombine_warp_kernel<true, 32><<<wgrid, 256, 0, ctx->stream>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
-    GE_TRY(ctx->check_launch("seg_recombine<fill>"));
-    if (ctx->profiling) {
-        CUDA_TRY(cudaEventRecord(ev2.b, ctx->stream));
-        // 16 B per part: every emitted piece comes from one parental part, read by both passes and written once
-        ev1.bytes = 16 * off.seg.n_seg; ev2.bytes = 32 * off.seg.n_seg;
-        ctx->ev_pending.push_back(ev1); ctx->ev_pending.push_back(ev2);
+        off.seg.valid = true;
+        return GE_OK;
     }
+    // ---- plan + gather.  With seg_capacity the output buffer is sized once, so nothing between the passes needs the host:
+    // the whole chain is queued on the bulk stream behind the draws (like the bit-packed copy) and the control chain of the
+    // next generation overlaps it; n_seg arrives in pinned memory and is looked at by the next call that needs it.
+    const bool async = ctx->cfg.seg_capacity != 0 && !ctx->serial && !ctx->seg_sync_mode;
+    cudaStream_t st = async ? ctx->bulk : ctx->stream;
+    const uint64_t n_iv = P.n_xo + n_slots;            // intervals: one more than crossovers in every slot
+    constexpr uint32_t VERB_CAP = 1u << 18;
+    GE_TRY(ctx->ensure(ctx->seg_cnt, (n_iv + 1) * 4));
+    GE_TRY(ctx->ensure(ctx->seg_desc, (size_t)(n_iv + 1) * 16));
+    GE_TRY(ctx->ensure(ctx->seg_iv_off, (size_t)(n_iv + 1) * 8));
+    GE_TRY(ctx->ensure(ctx->seg_flags, 16));
+    GE_TRY(ctx->ensure(ctx->seg_verb, (size_t)VERB_CAP * 8));
+    if (!off.seg.ready) CUDA_TRY(cudaEventCreateWithFlags(&off.seg.ready, cudaEventDisableTiming));
+    if (!off.seg.h_total) CUDA_TRY(cudaMallocHost(&off.seg.h_total, 16));
+    uint64_t cap = 0;
+    if (ctx->cfg.seg_capacity) { GE_TRY(ctx->ensure_exact(off.seg.seg, ctx->cfg.seg_capacity * 16)); cap = off.seg.seg.cap / 16; }
+    if (async) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_ready, ctx->stream));   // the draws (and whatever the control stream did to the parental lists) are complete
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
+    }
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (ctx->profiling) for (cudaEvent_t &e : ev) e = ctx->get_event();
+    if (ev[0]) CUDA_TRY(cudaEventRecord(ev[0], st));
+    CUDA_TRY(cudaMemsetAsync(ctx->seg_flags.p, 0, 16, st));
+    const unsigned pgrid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n_slots, 128)), 1u << 30);
+    seg_plan_kernel<<<pgrid, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP);
+    GE_TRY(ctx->check_launch("seg_plan"));
+    if (ev[1]) CUDA_TRY(cudaEventRecord(ev[1], st));
+    GE_TRY(ctx->exclusive_scan_on(st, ctx->seg_scan_blocks, ctx->seg_scan_total, ctx->seg_cnt.as<uint32_t>(), n_iv, ctx->seg_iv_off.as<uint64_t>()));
+    CUDA_TRY(cudaMemcpyAsync(off.seg.h_total, ctx->seg_scan_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(off.seg.ready, st));
+    seg_slot_offsets_kernel<<<nblk(n_slots + 1, 256), 256, 0, st>>>(n_slots, 0, a.xo_off, ctx->seg_iv_off.as<uint64_t>(), off.seg.off.as<uint64_t>());
+    GE_TRY(ctx->check_launch("seg_slot_offsets"));
+    off.seg.pending = true;
     off.seg.valid = true;
+    for (int k = 0; k < 4; k++) off.seg.ev[k] = ev[k];
+    if (!async) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const uint64_t n_seg = off.seg.h_total[0];
+        if (!ctx->cfg.seg_capacity) {   // grow geometrically (a reallocation of tens of GB costs more than a generation)
+            uint64_t want = std::max<uint64_t>(n_seg, 1);
+            if (want * 16 > off.seg.seg.cap) want += want / 2;
+            GE_TRY(ctx->ensure_exact(off.seg.seg, want * 16));
+            cap = off.seg.seg.cap / 16;
+        } else if (n_seg > ctx->cfg.seg_capacity) { off.seg.pending = false; off.seg.valid = false; return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity"); }
+    }
+    if (ev[2]) CUDA_TRY(cudaEventRecord(ev[2], st));
+    const unsigned ggrid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n_iv, SEG_GATHER_IV)), 1u << 30);
+    seg_gather_kernel<<<ggrid, 256, 0, st>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, a.par_seg, off.seg.seg.as<uint4>(), cap);
+    GE_TRY(ctx->check_launch("seg_gather"));
+    seg_verbatim_fill_kernel<<<ctx->n_sm * 8, 128, 0, st>>>(a, ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP,
+                                                       off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>(), cap);
+    GE_TRY(ctx->check_launch("seg_verbatim_fill"));
+    if (ev[3]) CUDA_TRY(cudaEventRecord(ev[3], st));
+    if (async) {
+        CUDA_TRY(cudaEventRecord(D.bulk_done, st));   // the draw set is read until here
+        D.bulk_pending = true;
+        // a long copy is in flight: the heavy control kernels of the next generation run on thin grids beside it (as for the bit-packed copy)
+        if (!ctx->bits()) ctx->bulk_busy = (double)par.seg.n_seg * 32.0 > ctx->thin_min_bytes;
+    } else GE_TRY(seg_finish(ctx, off));
     return GE_OK;
 }
 
@@ -551,6 +654,7 @@ static int seg_device_tables(ge_ctx *ctx, Buf &tbl, bool cv) {
 }
 
 static int seg_find_cv(ge_ctx *ctx, int pop) {
+    GE_TRY(seg_finish_all(ctx));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists");
@@ -568,6 +672,7 @@ static int seg_find_cv(ge_ctx *ctx, int pop) {
 }
 
 static int seg_materialise(ge_ctx *ctx, int pop, int c, uint8_t *d_alleles) {
+    GE_TRY(seg_finish_all(ctx));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists");
@@ -584,6 +689,7 @@ static int seg_materialise(ge_ctx *ctx, int pop, int c, uint8_t *d_alleles) {
 }
 
 static int seg_compact(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_after) {
+    GE_TRY(seg_finish_all(ctx));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur], &O = P.st[P.cur ^ 1];   // the other generation's buffers are free between generations
     if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists (GE_REP_SEGMENTS not enabled)");
@@ -608,6 +714,7 @@ static int seg_compact(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_aft
 
 // host-side slicing of one chromosome out of the slot-major CSR (output path, `.int` writer)
 static int seg_host_copy(ge_ctx *ctx, int pop, std::vector<uint64_t> &off, std::vector<uint4> &seg, std::vector<uint64_t> &hoff, std::vector<uint32_t> &hbp) {
+    GE_TRY(seg_finish_all(ctx));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists (GE_REP_SEGMENTS not enabled)");

@@ -175,6 +175,26 @@ def test_segment_warp_kernels_long_lists_and_many_crossovers(cuda_lib, monkeypat
     run_pair(cuda_lib, case, [(20, xo)] * 9, cap=64)
 
 
+def test_segment_capacity_is_enforced_on_both_paths(cuda_lib, monkeypatch):
+    """seg_capacity smaller than the lists: GE_ERR_CAPACITY from the generation itself (host read-back between the passes) or,
+    when the chain is queued on the bulk stream, from the first call after it — never a write beyond the buffer."""
+    for group, cap_parts in (("1", 40), ("32", 40)):
+        monkeypatch.setenv("GE_SEG_GROUP", group)
+        case = Case(5, [200, 50])
+        gpu = capi.Engine(cuda_lib, **case.kwargs(64, representation=capi.GE_REP_SEGMENTS, seg_capacity=cap_parts))
+        case.configure(gpu)
+        gpu.init_generation0([case.draws0()])
+
+        def xo(slot, c):
+            bp, _, step = case.maps[c]
+            return np.sort(case.rng.integers(int(bp[0]), int(bp[-1]), size=3))
+
+        with pytest.raises(capi.GeneEvolveError) as e:
+            gpu.step_generation(1, [capi.gen_params(10)], None, [case.draws(case.nf, 20, xo)])
+            gpu.segments(0, 0)
+        assert "seg_capacity" in str(e.value)
+
+
 def test_philox_many_crossovers_matches_oracle(cuda_lib):
     """Recombination rates high enough that most gametes exceed the per-slot stash of sample_xo_kernel."""
     case = Case(21, [300, 90], map_rows=60, step=64)

@@ -32,13 +32,22 @@ def compare_to_golden(G, eng, gen, pops=None):
 
 
 @pytest.mark.parametrize("name", SCENARIOS)
-@pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS, "segments-at-scale"])
+@pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS, "segments-thread-walk",
+                                 "segments-warp-walk", "segments-bulk-stream", "both-bulk-stream"])
 def test_replay_matches_reference(cuda_lib, name, rep, monkeypatch):
-    if rep == "segments-at-scale":   # the plan + gather kernels the segment path switches to once lists average 30 parts
-        monkeypatch.setenv("GE_SEG_GROUP", "32")
-        rep = capi.GE_REP_SEGMENTS
+    extra = {}
+    if isinstance(rep, str):
+        # the segment path's default is plan + gather (seg_plan_kernel, seg_gather_kernel); the walk kernels stay selectable
+        if rep == "segments-thread-walk":
+            monkeypatch.setenv("GE_SEG_GROUP", "1")
+        if rep == "segments-warp-walk":
+            monkeypatch.setenv("GE_SEG_GROUP", "32")
+            monkeypatch.setenv("GE_SEG_WALK", "1")
+        if rep.endswith("bulk-stream"):   # with seg_capacity the whole chain is queued on the bulk stream, n_seg is read back later
+            extra["seg_capacity"] = 400000
+        rep = capi.GE_REP_SEGMENTS | (capi.GE_REP_BITS if rep.startswith("both") else 0)
     G = Golden(name)
-    gpu = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_REPLAY, representation=rep))
+    gpu = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_REPLAY, representation=rep, **extra))
     cpu = OracleEngine(**G.engine_kwargs(rng_mode=capi.GE_RNG_REPLAY))
     for e in (gpu, cpu):
         G.configure(e)
