@@ -154,7 +154,7 @@ def bench_sharded(args, METRIC, UNIT):
             "e2e": {"value": work2 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,
                     "d2h_bytes_per_step": sum(capi.Engine.individual_bytes(n, n_phen) for n in pops), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "seg_recombine_kernel (count + fill)" if segs else "propagate_bits_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "seg_plan_kernel + seg_gather_kernel" if segs else "propagate_bits_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms_dev, "note": "per-GPU mean"},
             "clocks": clocks.summary(), "cpu_baseline": None}))
     dist.barrier()

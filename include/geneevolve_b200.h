@@ -58,7 +58,9 @@ typedef struct ge_config {
     int32_t reserved0;
     uint64_t seed;           /* Parameters::_seed; Philox key */
     uint64_t capacity;       /* max individuals per population in any generation */
-    uint64_t seg_capacity;   /* max segments per population per generation (GE_REP_SEGMENTS), 0 = auto */
+    uint64_t seg_capacity;   /* max segments per population per generation (GE_REP_SEGMENTS), 0 = auto (buffers grow, one host read-back
+                              * per generation).  When given, the segment path is queued on the bulk stream without a host read-back: a
+                              * generation that outgrows it is reported (GE_ERR_CAPACITY) by the first call after that generation. */
     int32_t rank;            /* shard of the offspring axis this context owns */
     int32_t world_size;
 } ge_config;
