@@ -349,6 +349,12 @@ class Engine:
         self._call("compact_segments", self.ctx, pop, C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def segment_format(self):
+        """Bytes per part in device memory: 16 (the reference's part) or 8 (packed, end implied)."""
+        b = C.c_int()
+        self._call("get_segment_format", self.ctx, C.byref(b))
+        return b.value
+
     def recompute_cv_from_segments(self, pop):
         self._call("recompute_cv_from_segments", self.ctx, pop)
 

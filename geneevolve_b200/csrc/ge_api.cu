@@ -262,6 +262,8 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     if (const char *t = std::getenv("GE_SEG_GROUP")) c->seg_group = std::atoi(t);
     c->seg_walk = std::getenv("GE_SEG_WALK") != nullptr;
     c->seg_sync_mode = std::getenv("GE_SEG_SYNC") != nullptr;
+    if (const char *t = std::getenv("GE_SEG_FORMAT")) c->seg_wide = std::atoi(t) == 16;
+    if (const char *t = std::getenv("GE_SEG_DEPTH")) c->seg_depth = std::atoi(t);
     if (const char *t = std::getenv("GE_SEG_PLAN_MIN")) c->seg_plan_min_parts = std::atof(t);
     if (const char *t = std::getenv("GE_PROP_DEPTH")) c->prop_depth = std::atoi(t);
     if (const char *t = std::getenv("GE_PROP")) c->use_tma = std::string(t) == "tma";
@@ -1134,6 +1136,13 @@ int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop) {  // ras_find_cv :2752-
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_recompute_cv_from_segments needs GE_REP_SEGMENTS");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     return seg_find_cv(ctx, pop);
+}
+
+int ge_get_segment_format(ge_ctx *ctx, int *bytes) {
+    CHECK_CTX(ctx);
+    if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_get_segment_format needs GE_REP_SEGMENTS");
+    *bytes = (int)ctx->seg_esz();
+    return GE_OK;
 }
 
 int ge_get_draw_counts(ge_ctx *ctx, int pop, uint64_t *no, uint64_t *nx, uint64_t *nm) {

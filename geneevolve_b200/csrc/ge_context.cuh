@@ -148,6 +148,10 @@ struct ge_ctx {
     Buf seg_desc, seg_iv_off;       // copy descriptor and output offset of every interval (seg_plan_kernel -> seg_gather_kernel)
     Buf seg_cnt, seg_scan_blocks, seg_scan_total, seg_flags, seg_verb;   // scratch of the segment path (its own: it may run on the bulk stream)
     double seg_plan_min_parts = 0;  // GE_SEG_PLAN_MIN: parts per parental list below which the thread-per-slot walk is used (measured: plan + gather wins from generation 1)
+    bool seg_packed = false;        // 8-byte parts {st, hap_index | root_population << 27} (decided in seg_init_gen0); else the reference's 16-byte parts
+    int seg_depth = 4;              // GE_SEG_DEPTH: independent loads per thread in the packed gather (4 or 8; 8 measured slower: 53 registers)
+    bool seg_wide = false;          // GE_SEG_FORMAT=16: never pack
+    size_t seg_esz() const { return seg_packed ? 8 : 16; }
     bool seg_sync_mode = false;     // GE_SEG_SYNC: never queue the segment path on the bulk stream
     bool seg_per_thread = false;    // a genetic map with rows closer than bp_dist_in_rmap was given, or GE_SEG_PER_THREAD is set
     bool cv_from_segments = false;  // GE_CV_FROM_SEGMENTS: ge_compute_AD rescans the segment lists every generation like the reference

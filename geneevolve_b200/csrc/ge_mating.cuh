@@ -491,8 +491,9 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
             GE_TRY(ctx->ensure(P.cnt32, (n * spi + 1) * 4)); GE_TRY(ctx->ensure(D.seg.off, (n * spi + 1) * 8));
             if (n) { gather_csr_count_kernel<<<nblk(n * spi, 256), 256, 0, st>>>(to, g8, g32, n, spi, P.cnt32.as<uint32_t>()); GE_TRY(ctx->check_launch("gather_csr_count")); }
             GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n * spi, D.seg.off.as<uint64_t>(), &D.seg.n_seg));
-            GE_TRY(ctx->ensure(D.seg.seg, std::max<uint64_t>(D.seg.n_seg, 1) * 16));
-            if (n) { gather_csr_fill_kernel<uint4><<<nblk(n * spi, 256), 256, 0, st>>>(to, tv, g8, g32, n, spi, D.seg.off.as<uint64_t>(), D.seg.seg.as<uint4>()); GE_TRY(ctx->check_launch("gather_csr_fill")); }
+            GE_TRY(ctx->ensure(D.seg.seg, std::max<uint64_t>(D.seg.n_seg, 1) * ctx->seg_esz()));
+            if (n && ctx->seg_packed) { gather_csr_fill_kernel<uint2><<<nblk(n * spi, 256), 256, 0, st>>>(to, tv, g8, g32, n, spi, D.seg.off.as<uint64_t>(), D.seg.seg.as<uint2>()); GE_TRY(ctx->check_launch("gather_csr_fill")); }
+            else if (n) { gather_csr_fill_kernel<uint4><<<nblk(n * spi, 256), 256, 0, st>>>(to, tv, g8, g32, n, spi, D.seg.off.as<uint64_t>(), D.seg.seg.as<uint4>()); GE_TRY(ctx->check_launch("gather_csr_fill")); }
             D.seg.valid = true;
         }
         D.n = n;

@@ -12,8 +12,19 @@
 
 namespace gek {
 
+// part e of a list that ends at e_end, in either format, as {st, en, hap_index, root_population}
+constexpr uint32_t SEG_ID_BITS_ = 27;
+__device__ __forceinline__ uint4 part_get(const uint4 *__restrict__ seg, uint64_t e, uint64_t, uint32_t) { return seg[e]; }
+__device__ __forceinline__ uint4 part_get(const uint2 *__restrict__ seg, uint64_t e, uint64_t e_end, uint32_t hi_c) {
+    const uint2 q = seg[e];
+    return make_uint4(q.x, e + 1 < e_end ? seg[e + 1].x : hi_c, q.y & ((1u << SEG_ID_BITS_) - 1u), q.y >> SEG_ID_BITS_);
+}
+__device__ __forceinline__ void part_put(uint4 *__restrict__ seg, uint64_t e, const uint4 v) { seg[e] = v; }
+__device__ __forceinline__ void part_put(uint2 *__restrict__ seg, uint64_t e, const uint4 v) { seg[e] = make_uint2(v.x, v.z | (v.w << SEG_ID_BITS_)); }
+
+template <class T>
 __global__ void seg_init_kernel(uint64_t n, int n_chr, int pop, const uint32_t *__restrict__ cov_lo, const uint32_t *__restrict__ cov_hi,
-                                uint64_t *__restrict__ off, uint4 *__restrict__ seg) {
+                                uint64_t *__restrict__ off, T *__restrict__ seg) {
     uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t n_slots = n * n_chr * 2;
     if (slot > n_slots) return;
@@ -21,7 +32,7 @@ __global__ void seg_init_kernel(uint64_t n, int n_chr, int pop, const uint32_t *
     if (slot == n_slots) return;
     uint64_t i = (slot >> 1) / (uint64_t)n_chr;
     int c = (int)((slot >> 1) % (uint64_t)n_chr), h = (int)(slot & 1);
-    seg[slot] = make_uint4(cov_lo[c], cov_hi[c], (uint32_t)(2 * i + h), (uint32_t)pop);  // :3029-3034
+    part_put(seg, slot, make_uint4(cov_lo[c], cov_hi[c], (uint32_t)(2 * i + h), (uint32_t)pop));  // :3029-3034
 }
 
 struct SegArgs {
@@ -29,7 +40,7 @@ struct SegArgs {
     uint64_t off_first, n_off;
     const uint32_t *father, *mother;
     const uint64_t *xo_off; const uint32_t *xo_bp; const uint8_t *start_hap;
-    const uint64_t *par_off; const uint4 *par_seg;
+    const uint64_t *par_off; const void *par_seg;   // uint4 parts, or uint2 packed parts (plan + gather only)
     const uint32_t *cov_lo, *cov_hi;
 };
 
@@ -50,7 +61,7 @@ __global__ void seg_recombine_kernel(SegArgs a, uint32_t *__restrict__ count, co
         uint32_t parent = gam ? a.mother[i] : a.father[i];
         uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2;
         const uint64_t o0 = a.par_off[ps], o1 = a.par_off[ps + 1], o2 = a.par_off[ps + 2];
-        const uint4 *H0 = a.par_seg + o0, *H1 = a.par_seg + o1;
+        const uint4 *H0 = static_cast<const uint4 *>(a.par_seg) + o0, *H1 = static_cast<const uint4 *>(a.par_seg) + o1;
         const uint32_t n0 = (uint32_t)(o1 - o0), n1 = (uint32_t)(o2 - o1);
         uint64_t e0 = a.xo_off[slot];
         uint32_t k = (uint32_t)(a.xo_off[slot + 1] - e0);
@@ -127,7 +138,7 @@ __global__ void seg_recombine_warp_kernel(SegArgs a, uint32_t *__restrict__ coun
         const uint32_t parent = gam ? a.mother[i] : a.father[i];
         const uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2;
         const uint64_t o0 = a.par_off[ps], o1 = a.par_off[ps + 1], o2 = a.par_off[ps + 2];
-        const uint4 *H0 = a.par_seg + o0, *H1 = a.par_seg + o1;
+        const uint4 *H0 = static_cast<const uint4 *>(a.par_seg) + o0, *H1 = static_cast<const uint4 *>(a.par_seg) + o1;
         const uint32_t n0 = (uint32_t)(o1 - o0), n1 = (uint32_t)(o2 - o1);
         const uint64_t e0 = a.xo_off[slot];
         const uint32_t k = (uint32_t)(a.xo_off[slot + 1] - e0);
@@ -223,7 +234,7 @@ __device__ __forceinline__ uint32_t seg_recombine_verbatim(const uint4 *H0, uint
 }
 
 struct SegSlot {   // what both passes need to know about one offspring haplotype slot
-    const uint4 *H0, *H1;
+    uint64_t b0, b1;   // absolute index of the first part of the two parental lists
     uint32_t n0, n1, k, c;
     uint64_t e0, slot;
     int hi;
@@ -240,7 +251,7 @@ __device__ __forceinline__ SegSlot seg_slot(const SegArgs &a, uint64_t t) {
     const uint32_t parent = (r & 1u) ? a.mother[i] : a.father[i];
     const uint64_t ps = ((uint64_t)parent * a.n_chr + s.c) * 2;
     const uint64_t o0 = a.par_off[ps], o1 = a.par_off[ps + 1], o2 = a.par_off[ps + 2];
-    s.H0 = a.par_seg + o0; s.H1 = a.par_seg + o1;
+    s.b0 = o0; s.b1 = o1;
     s.n0 = (uint32_t)(o1 - o0); s.n1 = (uint32_t)(o2 - o1);
     s.e0 = a.xo_off[s.slot];
     s.k = (uint32_t)(a.xo_off[s.slot + 1] - s.e0);
@@ -250,25 +261,26 @@ __device__ __forceinline__ SegSlot seg_slot(const SegArgs &a, uint64_t t) {
 
 constexpr uint32_t SEG_PLAN_VERBATIM = 0xFFFFFFFFu;
 
-// #(y <= X) among parts [lo, n) of a list with non-decreasing y, plus lo
-__device__ __forceinline__ uint32_t seg_count_y_le(const uint4 *__restrict__ H, uint32_t lo, uint32_t n, uint32_t X) {
-    uint32_t hi = n;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(&H[mid].y) <= X) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
+// Two part formats.  uint4 {st, en, hap_index, root_population} is the reference's `class part`.  uint2 {st, id} is the packed
+// form the segment path uses whenever lists are sorted tilings (every context except maps with rows closer than bp_dist_in_rmap
+// and the forced walk kernels): consecutive parts of a haplotype are contiguous (en_i = st_{i+1}, the last one ends at cov_hi
+// — recombine emits them that way, clip by clip), so en is implied and id = hap_index | root_population << 27.  Half the bytes
+// of the one HBM-bound kernel of the path, and half the footprint.
+static_assert(SEG_ID_BITS_ == 27, "id = hap_index | root_population << 27");
+__device__ __forceinline__ uint32_t part_y(const uint4 *__restrict__ H, uint32_t i, uint32_t, uint32_t) { return __ldg(&H[i].y); }
+__device__ __forceinline__ uint32_t part_y(const uint2 *__restrict__ H, uint32_t i, uint32_t n, uint32_t hi_c) { return i + 1 < n ? __ldg(&H[i + 1].x) : hi_c; }
 
-// two such searches with independent loads in flight (XA <= XB in every caller that matters, not required)
-__device__ __forceinline__ void seg_count_y_le2(const uint4 *__restrict__ H, uint32_t lo, uint32_t n, uint32_t XA, uint32_t XB, uint32_t &rA, uint32_t &rB) {
+// #(y <= X) among parts [lo, n) of a list with non-decreasing y, plus lo — two searches with independent loads in flight
+// (XA <= XB in every caller that matters, not required)
+template <class T>
+__device__ __forceinline__ void seg_count_y_le2(const T *__restrict__ H, uint32_t lo, uint32_t n, uint32_t hi_c, uint32_t XA, uint32_t XB, uint32_t &rA, uint32_t &rB) {
     uint32_t loA = lo, hiA = n, loB = lo, hiB = n;
     while (loA < hiA || loB < hiB) {
         const bool actA = loA < hiA, actB = loB < hiB;
         const uint32_t mA = (loA + hiA) >> 1, mB = (loB + hiB) >> 1;
         uint32_t yA = 0, yB = 0;
-        if (actA) yA = __ldg(&H[mA].y);
-        if (actB) yB = __ldg(&H[mB].y);
+        if (actA) yA = part_y(H, mA, n, hi_c);
+        if (actB) yB = part_y(H, mB, n, hi_c);
         if (actA) { if (yA <= XA) loA = mA + 1; else hiA = mA; }
         if (actB) { if (yB <= XB) loB = mB + 1; else hiB = mB; }
     }
@@ -279,24 +291,27 @@ __device__ __forceinline__ void seg_count_y_le2(const uint4 *__restrict__ H, uin
 // 2.7 KB of both lists, and ~10 warp instructions per slot instead of ~400 for a warp that ballots its way through them).
 // Interval g = xo_off[slot] + slot + j gets a copy descriptor {absolute index of its first parental part (64 bit), L, R} and its
 // part count; the scan of the counts gives every interval its absolute output offset, so the copy itself knows nothing of slots.
+template <class T>
 __global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__restrict__ iv_count, uint4 *__restrict__ desc, unsigned int *__restrict__ n_verbatim,
                                                        uint64_t *__restrict__ verb_list, uint32_t verb_cap) {
+    constexpr bool PACKED = sizeof(T) == 8;
+    const T *par = static_cast<const T *>(a.par_seg);
     const uint64_t n_total = a.n_off * a.n_chr * 2;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
         const SegSlot s = seg_slot(a, t);
         const uint64_t g = s.e0 + s.slot;
-        const uint64_t b0 = (uint64_t)(s.H0 - a.par_seg), b1 = (uint64_t)(s.H1 - a.par_seg);
         if (s.k == 0) {   // the chosen parental haplotype unchanged (:2910): one unclipped interval
-            const uint64_t src = s.hi ? b1 : b0;
+            const uint64_t src = s.hi ? s.b1 : s.b0;
             desc[g] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), 0u, 0xFFFFFFFFu);
             iv_count[g] = s.hi ? s.n1 : s.n0;
             continue;
         }
+        const T *H0 = par + s.b0, *H1 = par + s.b1;
         const uint32_t lo_c = a.cov_lo[s.c], hi_c = a.cov_hi[s.c];
         const uint32_t *xo = a.xo_bp + s.e0;
-        bool fast = true;   // positions must ascend: cov_lo <= X_1 <= ... <= X_k
+        bool fast = true;   // positions must ascend: X_1 <= ... <= X_k (positions below cov_lo only make the first interval empty)
         {
-            uint32_t prev = lo_c;
+            uint32_t prev = 0;
             for (uint32_t j = 0; j < s.k; j++) { const uint32_t x = __ldg(xo + j); fast &= x >= prev; prev = x; }
             if (fast && prev > hi_c) {
                 // a crossover in the last map row lies beyond cov_hi, so the last interval has L > R.  The reference's loop first skips
@@ -304,31 +319,35 @@ __global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__re
                 // which is what the index range gives (i0 = n).  Anything else goes to the verbatim loop.
                 const int hl = s.hi ^ (int)(s.k & 1u);
                 const uint32_t nl = hl ? s.n1 : s.n0;
-                fast = nl == 0 || __ldg(&(hl ? s.H1 : s.H0)[nl - 1].y) <= prev;
+                fast = nl == 0 || part_y(hl ? H1 : H0, nl - 1, nl, hi_c) <= prev;
             }
         }
-        if (!fast) {   // the reference's loop verbatim (seg_verbatim_fill_kernel writes the parts)
-            const uint32_t n = seg_recombine_verbatim<false>(s.H0, s.n0, s.H1, s.n1, xo, s.k, lo_c, hi_c, s.hi, nullptr);
-            desc[g] = make_uint4(0u, SEG_PLAN_VERBATIM, 0u, 0u);
-            iv_count[g] = n;
-            for (uint32_t j = 1; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
-            const unsigned int w = atomicAdd(n_verbatim, 1u);
-            if (w < verb_cap) verb_list[w] = t;
+        if (!fast) {
+            if constexpr (PACKED) {   // pieces that do not tile cannot be stored with an implied end: refuse (ge_last_error names the 16-byte format)
+                atomicAdd(n_verbatim + 1, 1u);
+                for (uint32_t j = 0; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
+            } else {   // the reference's loop verbatim (seg_verbatim_fill_kernel writes the parts)
+                const uint32_t n = seg_recombine_verbatim<false>(H0, s.n0, H1, s.n1, xo, s.k, lo_c, hi_c, s.hi, nullptr);
+                desc[g] = make_uint4(0u, SEG_PLAN_VERBATIM, 0u, 0u);
+                iv_count[g] = n;
+                for (uint32_t j = 1; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
+                const unsigned int w = atomicAdd(n_verbatim, 1u);
+                if (w < verb_cap) verb_list[w] = t;
+            }
             continue;
         }
         uint32_t cur0 = 0, cur1 = 0, L = lo_c;
         int h = s.hi;
         for (uint32_t j = 0; j <= s.k; j++) {
             const uint32_t R = j == s.k ? hi_c : __ldg(xo + j);
-            const uint4 *H = h ? s.H1 : s.H0;
+            const T *H = h ? H1 : H0;
             const uint32_t nH = h ? s.n1 : s.n0;
             uint32_t i0, c;                                                   // first part with y > L; #(y <= R) — searched side by side
-            seg_count_y_le2(H, h ? cur1 : cur0, nH, L, R, i0, c);
-            c = max(c, i0);                                                   // (L > R only in the checked last-row case, where both are n)
-            uint32_t i1 = c;                                                  // max(#(y <= R), #(x < R)), x non-decreasing
-            while (i1 < nH && __ldg(&H[i1].x) < R) i1++;
-            if (h) cur1 = c; else cur0 = c;
-            const uint64_t src = (h ? b1 : b0) + i0;
+            seg_count_y_le2(H, h ? cur1 : cur0, nH, hi_c, L, R, i0, c);
+            if (h) cur1 = c; else cur0 = c;                                   // #(y <= R): the next interval on this haplotype starts at or after R
+            uint32_t i1 = max(c, i0);                                         // max(#(y <= R), #(x < R)), x non-decreasing; L > R (first interval with a
+            while (i1 < nH && __ldg(&H[i1].x) < R) i1++;                      // position below cov_lo, last one beyond cov_hi) gives an empty range
+            const uint64_t src = (h ? s.b1 : s.b0) + i0;
             desc[g + j] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), L, R);
             iv_count[g + j] = i1 - i0;
             L = R; h ^= 1;
@@ -347,8 +366,18 @@ __global__ void seg_slot_offsets_kernel(uint64_t n_slots, uint64_t slot0, const 
 // index by a branch-free binary search of the staged offsets, four independent 16-byte loads per thread are in flight before the
 // first clip, and the stores of a warp are 512 contiguous bytes.  No per-slot prologue, no idle lanes on short intervals.
 constexpr int SEG_GATHER_IV = 128;
+__device__ __forceinline__ uint2 ld_stream(const uint2 *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(uint2 *p, const uint2 v) { asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ void part_clip(uint4 &q, uint32_t L, uint32_t R) { q.x = max(q.x, L); q.y = min(q.y, R); }
+__device__ __forceinline__ void part_clip(uint2 &q, uint32_t L, uint32_t) { q.x = max(q.x, L); }   // the end is the next part's start
+
+template <class T, int DEPTH>
 __global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict__ desc, const uint64_t *__restrict__ iv_off, uint64_t n_iv,
-                                                         const uint4 *__restrict__ par_seg, uint4 *__restrict__ off_seg, uint64_t cap) {
+                                                         const T *__restrict__ par_seg, T *__restrict__ off_seg, uint64_t cap) {
     __shared__ uint32_t s_rel[SEG_GATHER_IV + 1];
     __shared__ uint4 s_desc[SEG_GATHER_IV];
     const uint32_t tid = threadIdx.x;
@@ -361,13 +390,13 @@ __global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict
         // parts beyond the buffer are not written (asynchronous form: the host learns the total only afterwards and reports GE_ERR_CAPACITY)
         const uint64_t room = cap > o0 ? cap - o0 : 0;
         const uint32_t n = room < (uint64_t)s_rel[m] ? (uint32_t)room : s_rel[m];
-        uint4 *out = off_seg + o0;
-        for (uint32_t base = 0; base < n; base += 256 * 4) {
-            uint4 q[4];
-            uint32_t L[4], R[4];
-            bool ok[4];
+        T *out = off_seg + o0;
+        for (uint32_t base = 0; base < n; base += 256 * DEPTH) {
+            T q[DEPTH];
+            uint32_t L[DEPTH], R[DEPTH];
+            bool ok[DEPTH];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < DEPTH; u++) {
                 const uint32_t idx = base + u * 256 + tid;
                 uint32_t lo = 0;   // last interval whose first output is <= idx (empty intervals share an offset: the last one owns it)
 #pragma unroll
@@ -378,8 +407,8 @@ __global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict
                 if (ok[u]) q[u] = ld_stream(par_seg + ((((uint64_t)d.y) << 32 | d.x) + (idx - s_rel[lo])));
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (ok[u]) { q[u].x = max(q[u].x, L[u]); q[u].y = min(q[u].y, R[u]); st_stream(out + (base + u * 256 + tid), q[u]); }
+            for (int u = 0; u < DEPTH; u++)
+                if (ok[u]) { part_clip(q[u], L[u], R[u]); st_stream(out + (base + u * 256 + tid), q[u]); }
         }
         __syncthreads();
     }
@@ -397,14 +426,16 @@ __global__ void seg_verbatim_fill_kernel(SegArgs a, const uint4 *__restrict__ de
         const SegSlot s = seg_slot(a, listed ? verb_list[w] : w);
         if (s.k == 0 || desc[s.e0 + s.slot].y != SEG_PLAN_VERBATIM) continue;
         if (off_off[s.slot + 1] > cap) continue;
-        seg_recombine_verbatim<true>(s.H0, s.n0, s.H1, s.n1, a.xo_bp + s.e0, s.k, a.cov_lo[s.c], a.cov_hi[s.c], s.hi, off_seg + off_off[s.slot]);
+        const uint4 *par = static_cast<const uint4 *>(a.par_seg);
+        seg_recombine_verbatim<true>(par + s.b0, s.n0, par + s.b1, s.n1, a.xo_bp + s.e0, s.k, a.cov_lo[s.c], a.cov_hi[s.c], s.hi, off_seg + off_off[s.slot]);
     }
 }
 
 // ras_find_cv (:2752-2815) on the segment lists: allele bit plane / root byte plane.  One thread per (haplotype
 // row, word of the CV bit plane); every CV of the word scans the segment list of its chromosome (the LAST part that
 // covers the position wins, like the reference's loop over all parts).
-__global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__restrict__ off, const uint4 *__restrict__ seg,
+template <class T>
+__global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__restrict__ off, const T *__restrict__ seg, const uint32_t *__restrict__ cov_hi,
                                    const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp,
                                    const uint8_t *const *__restrict__ founder_cv /* [n_pop] -> [nh][n_cv_tot] */,
                                    uint32_t *__restrict__ bits, uint8_t *__restrict__ rootp) {
@@ -417,12 +448,14 @@ __global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__
         uint32_t c = blk % (uint32_t)cs.n_chr;
         uint32_t k0 = cs.block_off[blk] + (w - cs.word_off[blk]) * 32u, k1 = min(k0 + 32u, cs.block_off[blk + 1]);
         uint64_t slot = ((row >> 1) * cs.n_chr + c) * 2 + (row & 1);
+        const uint64_t e_end = off[slot + 1];
+        const uint32_t hi_c = cov_hi[c];
         for (uint32_t k = k0; k < k1; k++) {
             uint32_t bp = cs.bp[k];
             uint8_t v = 0, r = 0;
             bool found = false;
-            for (uint64_t e = off[slot]; e < off[slot + 1]; e++) {
-                uint4 q = seg[e];
+            for (uint64_t e = off[slot]; e < e_end; e++) {
+                uint4 q = part_get(seg, e, e_end, hi_c);
                 if (q.x <= bp && bp < q.y) { v = founder_cv[q.w][(uint64_t)q.z * cs.n_cv_tot + k]; r = (uint8_t)q.w; found = true; }
             }
             if (found && hm_off) {
@@ -436,7 +469,8 @@ __global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__
 }
 
 // ras_convert_interval_to_hap_matrix (:1186-1230): alleles of one chromosome from segments + founder panels
-__global__ void seg_materialise_kernel(Genome g, int c, uint64_t n_rows, const uint64_t *__restrict__ off, const uint4 *__restrict__ seg,
+template <class T>
+__global__ void seg_materialise_kernel(Genome g, int c, uint64_t n_rows, const uint64_t *__restrict__ off, const T *__restrict__ seg, const uint32_t *__restrict__ cov_hi,
                                        const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp,
                                        const uint32_t *const *__restrict__ founder_rows /* [n_pop] packed rows */, uint8_t *__restrict__ alleles) {
     uint32_t nl = g.chr_nloci[c];
@@ -446,10 +480,12 @@ __global__ void seg_materialise_kernel(Genome g, int c, uint64_t n_rows, const u
     uint64_t row = t / nl;
     uint32_t pos = g.pos[g.locus_off[c] + s];
     uint64_t slot = ((row >> 1) * g.n_chr + c) * 2 + (row & 1);
+    const uint64_t e_end = off[slot + 1];
+    const uint32_t hi_c = cov_hi[c];
     uint8_t v = 0;
     bool found = false;
-    for (uint64_t e = off[slot]; e < off[slot + 1]; e++) {
-        uint4 q = seg[e];
+    for (uint64_t e = off[slot]; e < e_end; e++) {
+        uint4 q = part_get(seg, e, e_end, hi_c);
         if (q.x <= pos && pos < q.y) { v = (founder_rows[q.w][(uint64_t)q.z * g.W + g.chr_word_off[c] + (s >> 5)] >> (s & 31)) & 1u; found = true; }
     }
     if (found && hm_off) {
@@ -466,23 +502,24 @@ namespace gek {
 // root population) become one part.  Zero-length parts disappear into their neighbour or are dropped when they carry
 // no length of their own.  The materialised haplotype is unchanged; the `.int` listing is no longer the reference's.
 // One thread per haplotype slot; pass 0 counts, pass 1 writes.
-template <bool FILL>
-__global__ void seg_compact_kernel(uint64_t n_slots, const uint64_t *__restrict__ off, const uint4 *__restrict__ seg, uint32_t *__restrict__ count,
-                                   const uint64_t *__restrict__ new_off, uint4 *__restrict__ out) {
+template <bool FILL, class T>
+__global__ void seg_compact_kernel(uint64_t n_slots, int n_chr, const uint32_t *__restrict__ cov_hi, const uint64_t *__restrict__ off, const T *__restrict__ seg,
+                                   uint32_t *__restrict__ count, const uint64_t *__restrict__ new_off, T *__restrict__ out) {
     for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t e0 = off[slot], e1 = off[slot + 1];
-        uint4 *o = FILL ? out + new_off[slot] : nullptr;
+        const uint32_t hi_c = cov_hi[(slot >> 1) % (uint64_t)n_chr];
+        const uint64_t o = FILL ? new_off[slot] : 0;
         uint32_t n = 0;
         bool open = false;
         uint4 cur = make_uint4(0, 0, 0, 0);
         for (uint64_t e = e0; e < e1; e++) {
-            const uint4 q = seg[e];
+            const uint4 q = part_get(seg, e, e1, hi_c);
             if (q.x == q.y && e1 - e0 > 1) continue;                       // zero-length part: covers no locus
             if (open && q.x == cur.y && q.z == cur.z && q.w == cur.w) { cur.y = q.y; continue; }
-            if (open) { if (FILL) o[n] = cur; n++; }
+            if (open) { if (FILL) part_put(out, o + n, cur); n++; }
             cur = q; open = true;
         }
-        if (open) { if (FILL) o[n] = cur; n++; }
+        if (open) { if (FILL) part_put(out, o + n, cur); n++; }
         if (!FILL) count[slot] = n;
     }
 }
@@ -499,9 +536,24 @@ static int seg_init_gen0(ge_ctx *ctx, int p, uint64_t n) {
     PopDev &P = ctx->pop[p];
     SegState &S = P.st[P.cur].seg;
     uint64_t n_slots = n * ctx->cfg.n_chr * 2;
-    GE_TRY(ctx->ensure(S.off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(S.seg, std::max<uint64_t>(n_slots, 1) * 16));
-    seg_init_kernel<<<nblk(n_slots + 1, 256), 256, 0, ctx->stream>>>(n, ctx->cfg.n_chr, p, P.d_cov_lo.as<uint32_t>(), P.d_cov_hi.as<uint32_t>(),
-                                                                     S.off.as<uint64_t>(), S.seg.as<uint4>());
+    // the part format is fixed here, once the maps are known: packed 8-byte parts wherever lists are sorted tilings and the walk
+    // kernels (which need en in memory) are not asked for
+    if (p == 0) {
+        bool same_range = true;
+        for (int q = 1; q < ctx->cfg.n_pop; q++)
+            for (int c = 0; c < ctx->cfg.n_chr; c++)
+                same_range &= ctx->pop[q].rmap_bp[c].front() == ctx->pop[0].rmap_bp[c].front() && ctx->pop[q].rmap_bp[c].back() == ctx->pop[0].rmap_bp[c].back();
+        uint64_t max_haps = 0;
+        for (PopDev &Q : ctx->pop) max_haps = std::max<uint64_t>(max_haps, Q.cv[0][0].nhap);
+        ctx->seg_packed = !ctx->seg_per_thread && ctx->seg_group == 0 && !ctx->seg_walk && !ctx->seg_wide && same_range && max_haps < (1ull << SEG_ID_BITS_) &&
+                          ctx->cfg.n_pop <= (1 << (32 - SEG_ID_BITS_));
+    }
+    const size_t esz = ctx->seg_esz();
+    GE_TRY(ctx->ensure(S.off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(S.seg, std::max<uint64_t>(n_slots, 1) * esz));
+    if (ctx->seg_packed) seg_init_kernel<uint2><<<nblk(n_slots + 1, 256), 256, 0, ctx->stream>>>(n, ctx->cfg.n_chr, p, P.d_cov_lo.as<uint32_t>(), P.d_cov_hi.as<uint32_t>(),
+                                                                                              S.off.as<uint64_t>(), S.seg.as<uint2>());
+    else seg_init_kernel<uint4><<<nblk(n_slots + 1, 256), 256, 0, ctx->stream>>>(n, ctx->cfg.n_chr, p, P.d_cov_lo.as<uint32_t>(), P.d_cov_hi.as<uint32_t>(),
+                                                                                S.off.as<uint64_t>(), S.seg.as<uint4>());
     GE_TRY(ctx->check_launch("seg_init"));
     S.n_seg = n_slots; S.valid = true;
     return GE_OK;
@@ -514,9 +566,14 @@ static int seg_finish(ge_ctx *ctx, GenState &S) {
     g.pending = false;
     CUDA_TRY(cudaEventSynchronize(g.ready));
     g.n_seg = g.h_total[0];
-    if (g.ev[0]) {   // 16 B per part: every emitted piece comes from one parental part, read by both passes and written once
-        ctx->ev_pending.push_back(ge_ctx::EvPair{g.ev[0], g.ev[1], GE_KERNEL_RECOMBINE_SEGMENTS, 16 * g.n_seg});
-        ctx->ev_pending.push_back(ge_ctx::EvPair{g.ev[2], g.ev[3], GE_KERNEL_RECOMBINE_SEGMENTS, 32 * g.n_seg});
+    if ((uint32_t)g.h_total[1]) {
+        g.valid = false;
+        return fail(GE_ERR_UNSUPPORTED, std::to_string((uint32_t)g.h_total[1]) + " gametes had crossover positions that do not ascend: the packed segment format cannot hold "
+                    "the pieces the reference emits for them (set GE_SEG_FORMAT=16 to keep its 16-byte parts)");
+    }
+    if (g.ev[0]) {   // 16 (8 packed) B per part: every emitted piece comes from one parental part, read by both passes and written once
+        ctx->ev_pending.push_back(ge_ctx::EvPair{g.ev[0], g.ev[1], GE_KERNEL_RECOMBINE_SEGMENTS, ctx->seg_esz() * g.n_seg});
+        ctx->ev_pending.push_back(ge_ctx::EvPair{g.ev[2], g.ev[3], GE_KERNEL_RECOMBINE_SEGMENTS, 2 * ctx->seg_esz() * g.n_seg});
         g.ev[0] = g.ev[1] = g.ev[2] = g.ev[3] = nullptr;
     }
     if (ctx->cfg.seg_capacity && g.n_seg > ctx->cfg.seg_capacity) {
@@ -546,13 +603,14 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     DrawSet &D = P.draws();
     a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = D.father.as<uint32_t>(); a.mother = D.mother.as<uint32_t>();
     a.xo_off = D.xo_off.as<uint64_t>(); a.xo_bp = D.xo_bp.as<uint32_t>(); a.start_hap = D.start_hap.as<uint8_t>();
-    a.par_off = par.seg.off.as<uint64_t>(); a.par_seg = par.seg.seg.as<uint4>(); a.cov_lo = P.d_cov_lo.as<uint32_t>(); a.cov_hi = P.d_cov_hi.as<uint32_t>();
+    a.par_off = par.seg.off.as<uint64_t>(); a.par_seg = par.seg.seg.p; a.cov_lo = P.d_cov_lo.as<uint32_t>(); a.cov_hi = P.d_cov_hi.as<uint32_t>();
     GE_TRY(ctx->ensure(off.seg.off, ((size_t)ctx->cfg.capacity * C * 2 + 1) * 8));
     // the reference's loop verbatim in one thread per slot while the lists are short (or may be unsorted), plan + gather once a
     // parental list averages 30 parts (GE_SEG_GROUP forces either; GE_SEG_WALK=1 selects the older warp-per-slot walk passes)
     const double avg_parts = (double)par.seg.n_seg / (double)std::max<uint64_t>(1, par.n * C * 2);
     int group = ctx->seg_per_thread ? 1 : (ctx->seg_group > 0 ? ctx->seg_group : (avg_parts < ctx->seg_plan_min_parts ? 1 : 32));
-    const bool plan = group == 32 && !ctx->seg_walk;
+    const bool plan = ctx->seg_packed || (group == 32 && !ctx->seg_walk);
+    const size_t esz = ctx->seg_esz();
     if (!plan) {   // ---- two walk passes on the control stream, host read-back of the total in between
         cudaStream_t st = ctx->stream;
         GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
@@ -599,7 +657,7 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     if (!off.seg.ready) CUDA_TRY(cudaEventCreateWithFlags(&off.seg.ready, cudaEventDisableTiming));
     if (!off.seg.h_total) CUDA_TRY(cudaMallocHost(&off.seg.h_total, 16));
     uint64_t cap = 0;
-    if (ctx->cfg.seg_capacity) { GE_TRY(ctx->ensure_exact(off.seg.seg, ctx->cfg.seg_capacity * 16)); cap = off.seg.seg.cap / 16; }
+    if (ctx->cfg.seg_capacity) { GE_TRY(ctx->ensure_exact(off.seg.seg, ctx->cfg.seg_capacity * esz)); cap = off.seg.seg.cap / esz; }
     if (async) {
         CUDA_TRY(cudaEventRecord(ctx->ev_ready, ctx->stream));   // the draws (and whatever the control stream did to the parental lists) are complete
         CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
@@ -609,11 +667,13 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
     if (ev[0]) CUDA_TRY(cudaEventRecord(ev[0], st));
     CUDA_TRY(cudaMemsetAsync(ctx->seg_flags.p, 0, 16, st));
     const unsigned pgrid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n_slots, 128)), 1u << 30);
-    seg_plan_kernel<<<pgrid, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP);
+    if (ctx->seg_packed) seg_plan_kernel<uint2><<<pgrid, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP);
+    else seg_plan_kernel<uint4><<<pgrid, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP);
     GE_TRY(ctx->check_launch("seg_plan"));
     if (ev[1]) CUDA_TRY(cudaEventRecord(ev[1], st));
     GE_TRY(ctx->exclusive_scan_on(st, ctx->seg_scan_blocks, ctx->seg_scan_total, ctx->seg_cnt.as<uint32_t>(), n_iv, ctx->seg_iv_off.as<uint64_t>()));
     CUDA_TRY(cudaMemcpyAsync(off.seg.h_total, ctx->seg_scan_total.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(off.seg.h_total + 1, ctx->seg_flags.as<unsigned int>() + 1, 4, cudaMemcpyDeviceToHost, st));   // slots whose crossovers do not ascend (packed format)
     CUDA_TRY(cudaEventRecord(off.seg.ready, st));
     seg_slot_offsets_kernel<<<nblk(n_slots + 1, 256), 256, 0, st>>>(n_slots, 0, a.xo_off, ctx->seg_iv_off.as<uint64_t>(), off.seg.off.as<uint64_t>());
     GE_TRY(ctx->check_launch("seg_slot_offsets"));
@@ -625,18 +685,24 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
         const uint64_t n_seg = off.seg.h_total[0];
         if (!ctx->cfg.seg_capacity) {   // grow geometrically (a reallocation of tens of GB costs more than a generation)
             uint64_t want = std::max<uint64_t>(n_seg, 1);
-            if (want * 16 > off.seg.seg.cap) want += want / 2;
-            GE_TRY(ctx->ensure_exact(off.seg.seg, want * 16));
-            cap = off.seg.seg.cap / 16;
+            if (want * esz > off.seg.seg.cap) want += want / 2;
+            GE_TRY(ctx->ensure_exact(off.seg.seg, want * esz));
+            cap = off.seg.seg.cap / esz;
         } else if (n_seg > ctx->cfg.seg_capacity) { off.seg.pending = false; off.seg.valid = false; return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity"); }
     }
     if (ev[2]) CUDA_TRY(cudaEventRecord(ev[2], st));
     const unsigned ggrid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n_iv, SEG_GATHER_IV)), 1u << 30);
-    seg_gather_kernel<<<ggrid, 256, 0, st>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, a.par_seg, off.seg.seg.as<uint4>(), cap);
-    GE_TRY(ctx->check_launch("seg_gather"));
-    seg_verbatim_fill_kernel<<<ctx->n_sm * 8, 128, 0, st>>>(a, ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP,
-                                                       off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>(), cap);
-    GE_TRY(ctx->check_launch("seg_verbatim_fill"));
+    if (ctx->seg_packed) {
+        if (ctx->seg_depth == 4) seg_gather_kernel<uint2, 4><<<ggrid, 256, 0, st>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, par.seg.seg.as<uint2>(), off.seg.seg.as<uint2>(), cap);
+        else seg_gather_kernel<uint2, 8><<<ggrid, 256, 0, st>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, par.seg.seg.as<uint2>(), off.seg.seg.as<uint2>(), cap);
+        GE_TRY(ctx->check_launch("seg_gather"));
+    } else {
+        seg_gather_kernel<uint4, 4><<<ggrid, 256, 0, st>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, par.seg.seg.as<uint4>(), off.seg.seg.as<uint4>(), cap);
+        GE_TRY(ctx->check_launch("seg_gather"));
+        seg_verbatim_fill_kernel<<<ctx->n_sm * 8, 128, 0, st>>>(a, ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP,
+                                                           off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>(), cap);
+        GE_TRY(ctx->check_launch("seg_verbatim_fill"));
+    }
     if (ev[3]) CUDA_TRY(cudaEventRecord(ev[3], st));
     if (async) {
         CUDA_TRY(cudaEventRecord(D.bulk_done, st));   // the draw set is read until here
@@ -662,9 +728,14 @@ static int seg_find_cv(ge_ctx *ctx, int pop) {
     Buf tbl;
     GE_TRY(seg_device_tables(ctx, tbl, true));
     uint64_t tot = 2 * S.n * ctx->Wcv;
-    seg_find_cv_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(),
-                                                                S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
-                                                                tbl.as<const uint8_t *>(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr);
+    if (ctx->seg_packed)
+        seg_find_cv_kernel<uint2><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), P.d_cov_hi.as<uint32_t>(),
+                                                                       S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
+                                                                       tbl.as<const uint8_t *>(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr);
+    else
+        seg_find_cv_kernel<uint4><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.d_cov_hi.as<uint32_t>(),
+                                                                       S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
+                                                                       tbl.as<const uint8_t *>(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr);
     GE_TRY(ctx->check_launch("seg_find_cv"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->release(tbl);
@@ -679,9 +750,12 @@ static int seg_materialise(ge_ctx *ctx, int pop, int c, uint8_t *d_alleles) {
     Buf tbl;
     GE_TRY(seg_device_tables(ctx, tbl, false));
     uint64_t tot = 2 * S.n * ctx->chr_nloci[c];
-    seg_materialise_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->genome(), c, 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(),
-                                                                    S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
-                                                                    tbl.as<const uint32_t *>(), d_alleles);
+    if (ctx->seg_packed)
+        seg_materialise_kernel<uint2><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->genome(), c, 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), P.d_cov_hi.as<uint32_t>(),
+                                                                           S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(), tbl.as<const uint32_t *>(), d_alleles);
+    else
+        seg_materialise_kernel<uint4><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->genome(), c, 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.d_cov_hi.as<uint32_t>(),
+                                                                           S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(), tbl.as<const uint32_t *>(), d_alleles);
     GE_TRY(ctx->check_launch("seg_materialise"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->release(tbl);
@@ -698,12 +772,16 @@ static int seg_compact(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_aft
     GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
     GE_TRY(ctx->ensure(O.seg.off, (n_slots + 1) * 8));
     const unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n_slots, 128)), (uint64_t)ctx->n_sm * 64);
-    seg_compact_kernel<false><<<grid, 128, 0, ctx->stream>>>(n_slots, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.cnt32.as<uint32_t>(), nullptr, nullptr);
+    const int C = ctx->cfg.n_chr;
+    const uint32_t *chi = P.d_cov_hi.as<uint32_t>();
+    if (ctx->seg_packed) seg_compact_kernel<false, uint2><<<grid, 128, 0, ctx->stream>>>(n_slots, C, chi, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), P.cnt32.as<uint32_t>(), nullptr, nullptr);
+    else seg_compact_kernel<false, uint4><<<grid, 128, 0, ctx->stream>>>(n_slots, C, chi, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.cnt32.as<uint32_t>(), nullptr, nullptr);
     GE_TRY(ctx->check_launch("seg_compact<count>"));
     uint64_t n_new = 0;
     GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, O.seg.off.as<uint64_t>(), &n_new));
-    GE_TRY(ctx->ensure(O.seg.seg, std::max<uint64_t>(n_new, 1) * 16));
-    seg_compact_kernel<true><<<grid, 128, 0, ctx->stream>>>(n_slots, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), nullptr, O.seg.off.as<uint64_t>(), O.seg.seg.as<uint4>());
+    GE_TRY(ctx->ensure(O.seg.seg, std::max<uint64_t>(n_new, 1) * ctx->seg_esz()));
+    if (ctx->seg_packed) seg_compact_kernel<true, uint2><<<grid, 128, 0, ctx->stream>>>(n_slots, C, chi, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), nullptr, O.seg.off.as<uint64_t>(), O.seg.seg.as<uint2>());
+    else seg_compact_kernel<true, uint4><<<grid, 128, 0, ctx->stream>>>(n_slots, C, chi, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), nullptr, O.seg.off.as<uint64_t>(), O.seg.seg.as<uint4>());
     GE_TRY(ctx->check_launch("seg_compact<fill>"));
     std::swap(S.seg.off, O.seg.off); std::swap(S.seg.seg, O.seg.seg);
     S.seg.n_seg = n_new;
@@ -722,7 +800,17 @@ static int seg_host_copy(ge_ctx *ctx, int pop, std::vector<uint64_t> &off, std::
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     off.resize(n_slots + 1); seg.resize(S.seg.n_seg);
     CUDA_TRY(cudaMemcpy(off.data(), S.seg.off.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));
-    if (S.seg.n_seg) CUDA_TRY(cudaMemcpy(seg.data(), S.seg.seg.p, S.seg.n_seg * 16, cudaMemcpyDeviceToHost));
+    if (S.seg.n_seg && !ctx->seg_packed) CUDA_TRY(cudaMemcpy(seg.data(), S.seg.seg.p, S.seg.n_seg * 16, cudaMemcpyDeviceToHost));
+    if (S.seg.n_seg && ctx->seg_packed) {   // {st, id} -> {st, en, hap_index, root_population}: en is the next part's st, cov_hi at the end of a list
+        std::vector<uint2> pk(S.seg.n_seg);
+        CUDA_TRY(cudaMemcpy(pk.data(), S.seg.seg.p, S.seg.n_seg * 8, cudaMemcpyDeviceToHost));
+        const int C = ctx->cfg.n_chr;
+        for (uint64_t sl = 0; sl < n_slots; sl++) {
+            const uint32_t hi_c = (uint32_t)P.rmap_bp[(sl >> 1) % C].back();
+            for (uint64_t e = off[sl]; e < off[sl + 1]; e++)
+                seg[e] = make_uint4(pk[e].x, e + 1 < off[sl + 1] ? pk[e + 1].x : hi_c, pk[e].y & ((1u << SEG_ID_BITS_) - 1u), pk[e].y >> SEG_ID_BITS_);
+        }
+    }
     hoff.assign(n_slots + 1, 0); hbp.clear();
     if (S.has_hm) {
         CUDA_TRY(cudaMemcpy(hoff.data(), S.hm_off.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));

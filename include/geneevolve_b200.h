@@ -223,6 +223,11 @@ int ge_compact_segments(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_af
  * haplotype's parts exactly like ras_find_cv (:2752-2815).  The hot path never does this — it carries the planes
  * forward by crossover parity — so the planes before and after this call must be identical. */
 int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop);
+/* Bytes per part in device memory (introspection for the tests and the bench): 16 = the reference's `class part` {st, en, hap_index,
+ * root_population}; 8 = packed {st, hap_index | root_population << 27} with the end implied by the next part, which the library
+ * uses whenever the lists are sorted tilings (every genetic map whose rows are at least bp_dist_in_rmap apart).  Downloads always
+ * return the four fields.  Valid after ge_init_generation0. */
+int ge_get_segment_format(ge_ctx *ctx, int *bytes_per_part);
 /* Draws the device generated for the last ge_reproduce of this population (GE_RNG_PHILOX): sizes first,
  * then the arrays (any pointer may be NULL to skip). */
 int ge_get_draw_counts(ge_ctx *ctx, int pop, uint64_t *n_offspring, uint64_t *n_xo, uint64_t *n_mut);

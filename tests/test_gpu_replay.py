@@ -35,14 +35,16 @@ def compare_to_golden(G, eng, gen, pops=None):
 @pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS, "segments-thread-walk",
                                  "segments-warp-walk", "segments-bulk-stream", "both-bulk-stream"])
 def test_replay_matches_reference(cuda_lib, name, rep, monkeypatch):
-    extra = {}
+    extra, fmt = {}, 8   # sorted genetic maps: packed 8-byte parts, unless a walk kernel (which needs `en` in memory) is forced
     if isinstance(rep, str):
         # the segment path's default is plan + gather (seg_plan_kernel, seg_gather_kernel); the walk kernels stay selectable
         if rep == "segments-thread-walk":
             monkeypatch.setenv("GE_SEG_GROUP", "1")
+            fmt = 16
         if rep == "segments-warp-walk":
             monkeypatch.setenv("GE_SEG_GROUP", "32")
             monkeypatch.setenv("GE_SEG_WALK", "1")
+            fmt = 16
         if rep.endswith("bulk-stream"):   # with seg_capacity the whole chain is queued on the bulk stream, n_seg is read back later
             extra["seg_capacity"] = 400000
         rep = capi.GE_REP_SEGMENTS | (capi.GE_REP_BITS if rep.startswith("both") else 0)
@@ -53,6 +55,8 @@ def test_replay_matches_reference(cuda_lib, name, rep, monkeypatch):
         G.configure(e)
         e.init_generation0([G.draws0(p) for p in range(G.n_pop)])
     compare_to_golden(G, gpu, 0)
+    if rep & capi.GE_REP_SEGMENTS:
+        assert gpu.segment_format() == fmt
     for p in range(G.n_pop):
         for f in range(G.n_phen):
             a, b = gpu.gen0_constants(p, f), cpu.gen0_constants(p, f)
