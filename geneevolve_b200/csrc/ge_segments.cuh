@@ -13,14 +13,14 @@
 namespace gek {
 
 // part e of a list that ends at e_end, in either format, as {st, en, hap_index, root_population}
-constexpr uint32_t SEG_ID_BITS_ = 27;
+constexpr uint32_t SEG_ID_BITS = 27;   // packed id = hap_index | root_population << 27
 __device__ __forceinline__ uint4 part_get(const uint4 *__restrict__ seg, uint64_t e, uint64_t, uint32_t) { return seg[e]; }
 __device__ __forceinline__ uint4 part_get(const uint2 *__restrict__ seg, uint64_t e, uint64_t e_end, uint32_t hi_c) {
     const uint2 q = seg[e];
-    return make_uint4(q.x, e + 1 < e_end ? seg[e + 1].x : hi_c, q.y & ((1u << SEG_ID_BITS_) - 1u), q.y >> SEG_ID_BITS_);
+    return make_uint4(q.x, e + 1 < e_end ? seg[e + 1].x : hi_c, q.y & ((1u << SEG_ID_BITS) - 1u), q.y >> SEG_ID_BITS);
 }
 __device__ __forceinline__ void part_put(uint4 *__restrict__ seg, uint64_t e, const uint4 v) { seg[e] = v; }
-__device__ __forceinline__ void part_put(uint2 *__restrict__ seg, uint64_t e, const uint4 v) { seg[e] = make_uint2(v.x, v.z | (v.w << SEG_ID_BITS_)); }
+__device__ __forceinline__ void part_put(uint2 *__restrict__ seg, uint64_t e, const uint4 v) { seg[e] = make_uint2(v.x, v.z | (v.w << SEG_ID_BITS)); }
 
 template <class T>
 __global__ void seg_init_kernel(uint64_t n, int n_chr, int pop, const uint32_t *__restrict__ cov_lo, const uint32_t *__restrict__ cov_hi,
@@ -266,7 +266,6 @@ constexpr uint32_t SEG_PLAN_VERBATIM = 0xFFFFFFFFu;
 // and the forced walk kernels): consecutive parts of a haplotype are contiguous (en_i = st_{i+1}, the last one ends at cov_hi
 // — recombine emits them that way, clip by clip), so en is implied and id = hap_index | root_population << 27.  Half the bytes
 // of the one HBM-bound kernel of the path, and half the footprint.
-static_assert(SEG_ID_BITS_ == 27, "id = hap_index | root_population << 27");
 __device__ __forceinline__ uint32_t part_y(const uint4 *__restrict__ H, uint32_t i, uint32_t, uint32_t) { return __ldg(&H[i].y); }
 __device__ __forceinline__ uint32_t part_y(const uint2 *__restrict__ H, uint32_t i, uint32_t n, uint32_t hi_c) { return i + 1 < n ? __ldg(&H[i + 1].x) : hi_c; }
 
@@ -545,8 +544,8 @@ static int seg_init_gen0(ge_ctx *ctx, int p, uint64_t n) {
                 same_range &= ctx->pop[q].rmap_bp[c].front() == ctx->pop[0].rmap_bp[c].front() && ctx->pop[q].rmap_bp[c].back() == ctx->pop[0].rmap_bp[c].back();
         uint64_t max_haps = 0;
         for (PopDev &Q : ctx->pop) max_haps = std::max<uint64_t>(max_haps, Q.cv[0][0].nhap);
-        ctx->seg_packed = !ctx->seg_per_thread && ctx->seg_group == 0 && !ctx->seg_walk && !ctx->seg_wide && same_range && max_haps < (1ull << SEG_ID_BITS_) &&
-                          ctx->cfg.n_pop <= (1 << (32 - SEG_ID_BITS_));
+        ctx->seg_packed = !ctx->seg_per_thread && ctx->seg_group == 0 && !ctx->seg_walk && !ctx->seg_wide && same_range && max_haps < (1ull << SEG_ID_BITS) &&
+                          ctx->cfg.n_pop <= (1 << (32 - SEG_ID_BITS));
     }
     const size_t esz = ctx->seg_esz();
     GE_TRY(ctx->ensure(S.off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(S.seg, std::max<uint64_t>(n_slots, 1) * esz));
@@ -808,7 +807,7 @@ static int seg_host_copy(ge_ctx *ctx, int pop, std::vector<uint64_t> &off, std::
         for (uint64_t sl = 0; sl < n_slots; sl++) {
             const uint32_t hi_c = (uint32_t)P.rmap_bp[(sl >> 1) % C].back();
             for (uint64_t e = off[sl]; e < off[sl + 1]; e++)
-                seg[e] = make_uint4(pk[e].x, e + 1 < off[sl + 1] ? pk[e + 1].x : hi_c, pk[e].y & ((1u << SEG_ID_BITS_) - 1u), pk[e].y >> SEG_ID_BITS_);
+                seg[e] = make_uint4(pk[e].x, e + 1 < off[sl + 1] ? pk[e + 1].x : hi_c, pk[e].y & ((1u << SEG_ID_BITS) - 1u), pk[e].y >> SEG_ID_BITS);
         }
     }
     hoff.assign(n_slots + 1, 0); hbp.clear();
