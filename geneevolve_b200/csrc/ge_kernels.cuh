@@ -129,6 +129,12 @@ struct TileTable {
     const uint32_t *nchunk;    // [n_items]
 };
 
+// a / b and a % b for 64-bit a that almost always fits 32 bits (thread and slot indices): the 64-bit division is ~100 instructions
+__device__ __forceinline__ void divmod_idx(uint64_t a, uint32_t b, uint64_t &q, uint32_t &r) {
+    if (a <= 0xFFFFFFFFull) { const uint32_t a32 = (uint32_t)a, q32 = a32 / b; q = q32; r = a32 - q32 * b; }
+    else { q = a / b; r = (uint32_t)(a - q * b); }
+}
+
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -575,8 +581,9 @@ __global__ void cv_propagate_bits_kernel(CvSet cs, const uint32_t *__restrict__ 
                                          const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
                                          const uint8_t *__restrict__ start_hap, uint64_t off_first, uint64_t n_off) {
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_off * 2 * cs.Wcv; t += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t w = (uint32_t)(t % cs.Wcv);
-    uint64_t row = t / cs.Wcv;
+    uint32_t w;
+    uint64_t row;
+    divmod_idx(t, cs.Wcv, row, w);
     uint64_t i = off_first + (row >> 1);
     int gam = (int)(row & 1);
     uint32_t b = cs.word_blk[w], v = 0;
@@ -724,8 +731,11 @@ __global__ void genetic_value_lut_kernel(CvSet cs, const uint32_t *__restrict__ 
     const int lane = threadIdx.x & 31;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < n * cs.n_phen; wid += n_warps) {
-        const uint64_t i = wid % n;
-        const int f = (int)(wid / n);
+        uint64_t fq;
+        uint32_t ir;
+        divmod_idx(wid, (uint32_t)n, fq, ir);   // individuals are indexed with 32 bits throughout (parent indices are uint32)
+        const uint64_t i = ir;
+        const int f = (int)fq;
         const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
         const uint32_t k1 = cs.block_off[(f + 1) * cs.n_chr];
         double Ac = 0, Dc = 0;
@@ -971,8 +981,10 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int ge
                                  uint8_t *__restrict__ start_hap, uint32_t *__restrict__ stash = nullptr) {
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_slots; t += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t slot = slot_first + t;
-    uint64_t i = (slot >> 1) / (uint64_t)n_chr;
-    int c = (int)((slot >> 1) % (uint64_t)n_chr), gam = (int)(slot & 1);
+    uint64_t i;
+    uint32_t cc;
+    divmod_idx(slot >> 1, (uint32_t)n_chr, i, cc);
+    const int c = (int)cc, gam = (int)(slot & 1);
     uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
     const double *T = m.T + r0 + c;
     uint32_t j = 0, blk = 0, n = 0;
@@ -1001,7 +1013,10 @@ __global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int po
     const uint64_t o = xo_off[slot];
     const uint32_t cnt = (uint32_t)(xo_off[slot + 1] - o);
     if (cnt == 0) continue;
-    const int c = (int)((slot >> 1) % (uint64_t)n_chr);
+    uint64_t i;
+    uint32_t cc;
+    divmod_idx(slot >> 1, (uint32_t)n_chr, i, cc);
+    const int c = (int)cc;
     if (cnt <= XO_STASH) {
         for (uint32_t q = 0; q < cnt; q++) {
             uint32_t x = stash[slot * XO_STASH + q];
@@ -1010,7 +1025,6 @@ __global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int po
         }
         continue;
     }
-    const uint64_t i = (slot >> 1) / (uint64_t)n_chr;
     const int gam = (int)(slot & 1);
     const uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
     const double *T = m.T + r0 + c;
