@@ -22,4 +22,5 @@ for g in range(4, 4 + steps):
     eng.step_generation(g, gp)
 ms = eng.timer_stop(); wall = (time.perf_counter() - t0) * 1e3
 k_ms, k_n, _ = eng.kernel_time(capi.GE_KERNEL_PROPAGATE_BITS)
-print(f"world {world}: chromosomes {mine}: {ms / steps:.3f} ms/step (host wall {wall / steps:.3f}), propagate {k_ms / max(k_n, 1):.3f} ms, launches/step {eng.launch_count() / steps:.0f}")
+phases = {name: round(eng.kernel_time(pid)[0] / steps, 3) for name, pid in capi.GE_PHASES.items()}
+print(f"world {world}: chromosomes {mine}: {ms / steps:.3f} ms/step (host wall {wall / steps:.3f}), propagate {k_ms / max(k_n, 1):.3f} ms, launches/step {eng.launch_count() / steps:.0f}, control chain {phases}")
