@@ -3,10 +3,16 @@
 // Needed where bit-packed rows cannot fit (BASELINE config 5: 1M individuals x 10M loci = 2.5 TB per
 // generation) and for the `.int` output; its cost is proportional to crossovers, not to loci.
 //
-// Device layout: one CSR over haplotype slots (i*n_chr + c)*2 + h; a segment is one uint4 (16 B, one
-// LDG.128/STG.128).  part::mutation_pos lives in the per-haplotype mutation lists shared with the bit path
+// Device layout: one CSR over haplotype slots (i*n_chr + c)*2 + h.  A part is either the reference's four fields
+// (uint4, 16 B) or, wherever lists are sorted tilings, the packed form {st, hap_index | root_population << 27} (uint2, 8 B)
+// whose end is the next part's start (see part_get below; the format is fixed in seg_init_gen0).
+// part::mutation_pos lives in the per-haplotype mutation lists shared with the bit path
 // (ge_kernels.cuh, mutation_lists_kernel): inside a haplotype the parts are disjoint, so "position is in the
 // part that covers it" and "position is in the haplotype's list" are the same predicate.
+//
+// Kernels: seg_recombine_kernel (one thread per slot, the reference's loop verbatim: maps that can give unsorted lists,
+// and the cross-check of the GPU tests), seg_recombine_warp_kernel (one warp per slot, the older at-scale form, kept
+// for A/B runs), and the default seg_plan_kernel + seg_gather_kernel.
 #pragma once
 #include "ge_context.cuh"
 
@@ -189,7 +195,7 @@ __global__ void seg_recombine_warp_kernel(SegArgs a, uint32_t *__restrict__ coun
 }
 
 // ------------------------------------------------------------------------------------------------
-// Plan + gather: the form the segment path runs at scale (lists of >= 30 parts).  ncu on the walk kernels above
+// Plan + gather: the form the segment path runs by default (every list length).  ncu on the walk kernels above
 // (1M individuals, generation 41) showed both passes ISSUE-bound (81 % / 65 % issue-active at 1.6 / 2.9 TB/s of DRAM
 // traffic): the walk evaluates the clip predicate twice per part (count, fill) and reads the other haplotype's parts
 // just to skip them.  Here the first pass only COUNTS prefixes and the second is a clipped copy:
