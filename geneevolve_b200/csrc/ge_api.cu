@@ -256,6 +256,7 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
     cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo);
     c->serial = std::getenv("GE_SERIAL") != nullptr;
+    c->cub_sorts = std::getenv("GE_CUB_SORTS") != nullptr;
     if (const char *t = std::getenv("GE_THIN")) c->thin = std::atoi(t);
     c->cv_from_segments = std::getenv("GE_CV_FROM_SEGMENTS") != nullptr;
     c->seg_per_thread = std::getenv("GE_SEG_PER_THREAD") != nullptr;

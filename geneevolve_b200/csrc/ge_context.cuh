@@ -140,6 +140,7 @@ struct ge_ctx {
         return GE_OK;
     }
     bool serial = false;
+    bool cub_sorts = false;         // GE_CUB_SORTS: cub::DeviceRadixSort for every sort of the mating chain (A/B against the small sorts)
     int thin = 8;   // CTAs per SM the heavy control-stream kernels may take while a bulk copy is in flight (0 = no limit)
     bool bulk_busy = false;
     int prop_depth = 4;

@@ -10,6 +10,7 @@
 #pragma once
 #include "ge_context.cuh"
 
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace gek {
@@ -147,9 +148,76 @@ static void mate_release(MateScratch &m) {
         if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small stable sorts.  The mating chain sorts <= N/2 (key, value) pairs five times per generation and sits on the dependency
+// cycle mating -> draws -> CV planes -> genetic values -> phenotypes -> selection -> mating: at these sizes
+// cub::DeviceRadixSort is ten dependent launches (histogram, scan, eight onesweep passes) of a few microseconds each, i.e. pure
+// launch latency.  Up to SMALL_SORT_MAX pairs are sorted in ONE launch (a tile of 4096 fits one CTA: cub::BlockRadixSort in
+// shared memory) or TWO (tiles sorted by one CTA each, then every element finds its final rank by binary searches of the other
+// tiles: rank = position in its tile + #(<= key) in earlier tiles + #(< key) in later tiles, which keeps the sort stable).
+// ------------------------------------------------------------------------------------------------
+namespace gek {
+constexpr int SS_THREADS = 512, SS_ITEMS = 8, SS_TILE = SS_THREADS * SS_ITEMS;
+constexpr uint64_t SMALL_SORT_MAX = 32ull * SS_TILE;   // 131 072 pairs: 31 searches of 12 steps per element at most
+
+__global__ void __launch_bounds__(SS_THREADS) small_sort_tile_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                                     uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t n) {
+    using Sort = cub::BlockRadixSort<uint64_t, SS_THREADS, SS_ITEMS, uint32_t>;
+    __shared__ typename Sort::TempStorage tmp;
+    const uint32_t base = blockIdx.x * SS_TILE;
+    uint64_t k[SS_ITEMS];
+    uint32_t v[SS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SS_ITEMS; j++) {   // blocked arrangement; padding sorts last (and, the sort being stable, after real all-ones keys)
+        const uint32_t idx = base + threadIdx.x * SS_ITEMS + j;
+        k[j] = idx < n ? kin[idx] : ~0ull;
+        v[j] = idx < n ? vin[idx] : 0xFFFFFFFFu;
+    }
+    Sort(tmp).Sort(k, v);
+#pragma unroll
+    for (int j = 0; j < SS_ITEMS; j++) {
+        const uint32_t idx = base + threadIdx.x * SS_ITEMS + j;
+        if (idx < n) { kout[idx] = k[j]; vout[idx] = v[j]; }
+    }
+}
+
+__global__ void small_sort_merge_kernel(const uint64_t *__restrict__ tk, const uint32_t *__restrict__ tv, uint64_t *__restrict__ kout,
+                                        uint32_t *__restrict__ vout, uint32_t n) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint64_t key = tk[e];
+    const uint32_t mine = e / SS_TILE, n_tiles = (n + SS_TILE - 1) / SS_TILE;
+    uint32_t rank = e - mine * SS_TILE;
+    for (uint32_t b = 0; b < n_tiles; b++) {
+        if (b == mine) continue;
+        const uint64_t *t = tk + (uint64_t)b * SS_TILE;
+        uint32_t lo = 0, hi = min((uint32_t)SS_TILE, n - b * SS_TILE);
+        if (b < mine) { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(t + mid) <= key) lo = mid + 1; else hi = mid; } }
+        else { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(t + mid) < key) lo = mid + 1; else hi = mid; } }
+        rank += lo;
+    }
+    kout[rank] = key;
+    vout[rank] = tv[e];
+}
+}  // namespace gek
+
 // stable sort of (uint64 key, uint32 value) pairs: keys_in/vals_in -> keys_out/vals_out
 static int sort_pairs_on(ge_ctx *ctx, cudaStream_t st, Buf &tmp, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n) {
     if (n == 0) return GE_OK;
+    if (n <= SMALL_SORT_MAX && !ctx->cub_sorts) {
+        const unsigned tiles = nblk(n, SS_TILE);
+        if (tiles == 1) {
+            small_sort_tile_kernel<<<1, SS_THREADS, 0, st>>>(kin, vin, kout, vout, (uint32_t)n);
+            return ctx->check_launch("small_sort_tile");
+        }
+        GE_TRY(ctx->ensure(tmp, n * 12 + 16));
+        uint64_t *tk = tmp.as<uint64_t>();
+        uint32_t *tv = reinterpret_cast<uint32_t *>(tk + n);
+        small_sort_tile_kernel<<<tiles, SS_THREADS, 0, st>>>(kin, vin, tk, tv, (uint32_t)n);
+        GE_TRY(ctx->check_launch("small_sort_tile"));
+        small_sort_merge_kernel<<<nblk(n, 256), 256, 0, st>>>(tk, tv, kout, vout, (uint32_t)n);
+        return ctx->check_launch("small_sort_merge");
+    }
     size_t bytes = 0;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 64, st));
     GE_TRY(ctx->ensure(tmp, bytes));
