@@ -923,8 +923,8 @@ int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reprod
         }
         CUDA_TRY(cudaEventRecord(D.bulk_done, bulk));
         D.bulk_pending = true;
-        // thin control kernels only pay off while the bulk copy is much longer than the control chain (~1.5 ms)
-        ctx->bulk_busy = !ctx->serial && (double)n_off * ctx->W * 16.0 > ctx->thin_min_bytes;
+        // thin control kernels only pay off while the bulk copy is longer than the control chain (~0.75 ms at 100k individuals)
+        ctx->note_bulk((double)n_off * ctx->W * 16.0);
         bulk_launched = true;
     }
     // ---- causal-variant planes

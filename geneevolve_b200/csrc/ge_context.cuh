@@ -157,13 +157,20 @@ struct ge_ctx {
     bool seg_per_thread = false;    // a genetic map with rows closer than bp_dist_in_rmap was given, or GE_SEG_PER_THREAD is set
     bool cv_from_segments = false;  // GE_CV_FROM_SEGMENTS: ge_compute_AD rescans the segment lists every generation like the reference
     bool use_tma = false, tma_attr_set = false;
-    double thin_min_bytes = 30e9;  // bytes moved by one bulk launch above which the control kernels go thin
-    // grid of a grid-stride control kernel: full width, or thin while it shares the GPU with propagate_bits_kernel,
+    double thin_min_bytes = 4e9;   // bytes moved by one bulk launch above which the control kernels go thin (below, the control chain is the critical path)
+    int thin_now = 0;              // CTAs per SM in force for the copy in flight
+    // Measured (scripts/emulate_rank.py, one rank of a 1/2/4/8-way shard of config 3): copies of >= 30 GB want 8 CTAs per SM for the
+    // control kernels, the 6-25 GB copies of a shard 4 (2-3 % faster than 8 or no limit), copies of ~1 GB (config 2) no limit.
+    void note_bulk(double bytes) {
+        bulk_busy = !serial && bytes > thin_min_bytes;
+        thin_now = bytes >= 30e9 ? thin : std::max(1, thin / 2);
+    }
+    // grid of a grid-stride control kernel: full width, or thin while it shares the GPU with the bulk copy,
     // so that the high-priority control stream displaces only a fraction of the bulk kernel's resident CTAs
     unsigned ctrl_grid(uint64_t n_threads, unsigned block) const {
         uint64_t full = std::max<uint64_t>(1, (n_threads + block - 1) / block);
         if (!bulk_busy || serial || thin <= 0) return (unsigned)std::min<uint64_t>(full, 1u << 30);
-        return (unsigned)std::min<uint64_t>(full, (uint64_t)n_sm * thin);
+        return (unsigned)std::min<uint64_t>(full, (uint64_t)n_sm * thin_now);
     }
     std::vector<PopDev> pop;
     std::vector<std::vector<uint64_t>> loci;  // host positions per chromosome

@@ -756,7 +756,7 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
         CUDA_TRY(cudaEventRecord(D.bulk_done, st));   // the draw set is read until here
         D.bulk_pending = true;
         // a long copy is in flight: the heavy control kernels of the next generation run on thin grids beside it (as for the bit-packed copy)
-        if (!ctx->bits()) ctx->bulk_busy = (double)par.seg.n_seg * 32.0 > ctx->thin_min_bytes;
+        if (!ctx->bits()) ctx->note_bulk((double)par.seg.n_seg * 2.0 * (double)esz);
     } else GE_TRY(seg_finish(ctx, off));
     return GE_OK;
 }
