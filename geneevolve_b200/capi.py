@@ -355,6 +355,13 @@ class Engine:
         self._call("get_segment_format", self.ctx, C.byref(b))
         return b.value
 
+    def ibd_sharing(self, pop, chrom, ind_a, ind_b, min_bp=0):
+        """(shared_bp, n_runs) per pair over the four haplotype combinations (ge_ibd_sharing)."""
+        a, b = np.ascontiguousarray(ind_a, np.uint64), np.ascontiguousarray(ind_b, np.uint64)
+        tot, runs = np.zeros(len(a), np.uint64), np.zeros(len(a), np.uint32)
+        self._call("ibd_sharing", self.ctx, pop, chrom, _ptr(a, _u64p), _ptr(b, _u64p), C.c_uint64(len(a)), C.c_uint64(int(min_bp)), _ptr(tot, _u64p), _ptr(runs, _u32p))
+        return tot, runs
+
     def recompute_cv_from_segments(self, pop):
         self._call("recompute_cv_from_segments", self.ctx, pop)
 

@@ -1139,6 +1139,13 @@ int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop) {  // ras_find_cv :2752-
     return seg_find_cv(ctx, pop);
 }
 
+int ge_ibd_sharing(ge_ctx *ctx, int pop, int chr, const uint64_t *ind_a, const uint64_t *ind_b, uint64_t n_pairs, uint64_t min_bp, uint64_t *shared_bp, uint32_t *n_runs) {
+    CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr);
+    if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_ibd_sharing needs GE_REP_SEGMENTS");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return seg_ibd(ctx, pop, chr, ind_a, ind_b, n_pairs, min_bp, shared_bp, n_runs);
+}
+
 int ge_get_segment_format(ge_ctx *ctx, int *bytes) {
     CHECK_CTX(ctx);
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_get_segment_format needs GE_REP_SEGMENTS");

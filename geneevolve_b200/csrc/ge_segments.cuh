@@ -573,6 +573,79 @@ __global__ void seg_compact_kernel(uint64_t n_slots, int n_chr, const uint32_t *
 }
 }  // namespace gek
 
+namespace gek {
+// Identity-by-descent sharing between pairs of individuals on one chromosome (the documentation's Example 10
+// derives it from the `.int` files with an external tool): two haplotypes are IBD where their parts name the same founder
+// haplotype.  One thread per (pair, haplotype of a, haplotype of b): a two-pointer walk over the two sorted lists; overlapping
+// pieces with equal (hap_index, root_population) that touch are one run; runs of at least min_bp count.
+template <class T>
+__global__ void seg_ibd_kernel(int n_chr, int c, const uint64_t *__restrict__ off, const T *__restrict__ seg, const uint32_t *__restrict__ cov_hi,
+                               const uint32_t *__restrict__ ind_a, const uint32_t *__restrict__ ind_b, uint64_t n_pairs, uint32_t min_bp,
+                               unsigned long long *__restrict__ shared_bp, uint32_t *__restrict__ n_runs) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs * 4) return;
+    const uint64_t pair = t >> 2;
+    const uint32_t ha = (uint32_t)(t >> 1) & 1u, hb = (uint32_t)t & 1u;
+    const uint32_t hi_c = cov_hi[c];
+    const uint64_t sa = ((uint64_t)ind_a[pair] * n_chr + c) * 2 + ha, sb = ((uint64_t)ind_b[pair] * n_chr + c) * 2 + hb;
+    uint64_t ea = off[sa], eb = off[sb];
+    const uint64_t ea_end = off[sa + 1], eb_end = off[sb + 1];
+    if (ea >= ea_end || eb >= eb_end) return;
+    uint4 qa = part_get(seg, ea, ea_end, hi_c), qb = part_get(seg, eb, eb_end, hi_c);
+    unsigned long long total = 0;
+    uint32_t runs = 0, run_lo = 0, run_hi = 0;
+    bool open = false;
+    auto close = [&]() { if (open && run_hi - run_lo >= min_bp) { total += run_hi - run_lo; runs++; } open = false; };
+    for (;;) {
+        const uint32_t lo = max(qa.x, qb.x), hi = min(qa.y, qb.y);
+        if (lo < hi) {
+            if (qa.z == qb.z && qa.w == qb.w) {
+                if (open && lo == run_hi) run_hi = hi;
+                else { close(); open = true; run_lo = lo; run_hi = hi; }
+            } else close();
+        }
+        const bool adv_a = qa.y <= qb.y, adv_b = qb.y <= qa.y;
+        if (adv_a) { if (++ea >= ea_end) break; qa = part_get(seg, ea, ea_end, hi_c); }
+        if (adv_b) { if (++eb >= eb_end) break; qb = part_get(seg, eb, eb_end, hi_c); }
+    }
+    close();
+    if (total) atomicAdd(&shared_bp[pair], total);
+    if (runs) atomicAdd(&n_runs[pair], runs);
+}
+}  // namespace gek
+
+static int seg_finish_all(ge_ctx *ctx);
+static int seg_ibd(ge_ctx *ctx, int pop, int c, const uint64_t *ind_a, const uint64_t *ind_b, uint64_t n_pairs, uint64_t min_bp, uint64_t *shared_bp, uint32_t *n_runs) {
+    GE_TRY(seg_finish_all(ctx));
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists (GE_REP_SEGMENTS not enabled)");
+    if (n_pairs == 0) return GE_OK;
+    if (!ind_a || !ind_b || !shared_bp || !n_runs) return fail(GE_ERR_INVALID, "ge_ibd_sharing: null argument");
+    std::vector<uint32_t> a(n_pairs), b(n_pairs);
+    for (uint64_t k = 0; k < n_pairs; k++) {
+        if (ind_a[k] >= S.n || ind_b[k] >= S.n) return fail(GE_ERR_INVALID, "ge_ibd_sharing: individual index out of range");
+        a[k] = (uint32_t)ind_a[k]; b[k] = (uint32_t)ind_b[k];
+    }
+    Buf da, db, dt, dr;
+    GE_TRY(ctx->upload(da, a)); GE_TRY(ctx->upload(db, b));
+    GE_TRY(ctx->ensure_exact(dt, n_pairs * 8)); GE_TRY(ctx->ensure_exact(dr, n_pairs * 4));
+    CUDA_TRY(cudaMemsetAsync(dt.p, 0, n_pairs * 8, ctx->stream)); CUDA_TRY(cudaMemsetAsync(dr.p, 0, n_pairs * 4, ctx->stream));
+    const uint32_t mb = (uint32_t)std::min<uint64_t>(min_bp, 0xFFFFFFFFull);
+    if (ctx->seg_packed)
+        seg_ibd_kernel<uint2><<<nblk(n_pairs * 4, 128), 128, 0, ctx->stream>>>(ctx->cfg.n_chr, c, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), P.d_cov_hi.as<uint32_t>(), da.as<uint32_t>(),
+                                                                             db.as<uint32_t>(), n_pairs, mb, dt.as<unsigned long long>(), dr.as<uint32_t>());
+    else
+        seg_ibd_kernel<uint4><<<nblk(n_pairs * 4, 128), 128, 0, ctx->stream>>>(ctx->cfg.n_chr, c, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.d_cov_hi.as<uint32_t>(), da.as<uint32_t>(),
+                                                                             db.as<uint32_t>(), n_pairs, mb, dt.as<unsigned long long>(), dr.as<uint32_t>());
+    GE_TRY(ctx->check_launch("seg_ibd"));
+    CUDA_TRY(cudaMemcpyAsync(shared_bp, dt.p, n_pairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(n_runs, dr.p, n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (Buf *x : {&da, &db, &dt, &dr}) ctx->release(*x);
+    return GE_OK;
+}
+
 static void seg_release(SegState &s) {
     for (Buf *b : {&s.off, &s.seg}) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     if (s.ready) { cudaEventDestroy(s.ready); s.ready = nullptr; }

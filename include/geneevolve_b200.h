@@ -228,6 +228,14 @@ int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop);
  * uses whenever the lists are sorted tilings (every genetic map whose rows are at least bp_dist_in_rmap apart).  Downloads always
  * return the four fields.  Valid after ge_init_generation0. */
 int ge_get_segment_format(ge_ctx *ctx, int *bytes_per_part);
+/* Extension (GeneEvolveDocumentation.pdf Example 10 derives the same from the `.int` files with an external
+ * tool): identity-by-descent sharing of n_pairs pairs of individuals of the current generation on one chromosome.  Two
+ * haplotypes are IBD where their parts name the same founder haplotype (hap_index, root_population); touching pieces are one
+ * run.  Over the four haplotype combinations of a pair: shared_bp[k] = total length of the runs of at least min_bp base pairs,
+ * n_runs[k] = their number.  ind_a[k] == ind_b[k] is allowed (the two combinations of different haplotypes then measure
+ * autozygosity; the two of a haplotype with itself give the covered length each). */
+int ge_ibd_sharing(ge_ctx *ctx, int pop, int chr, const uint64_t *ind_a, const uint64_t *ind_b, uint64_t n_pairs, uint64_t min_bp,
+                   uint64_t *shared_bp, uint32_t *n_runs);
 /* Draws the device generated for the last ge_reproduce of this population (GE_RNG_PHILOX): sizes first,
  * then the arrays (any pointer may be NULL to skip). */
 int ge_get_draw_counts(ge_ctx *ctx, int pop, uint64_t *n_offspring, uint64_t *n_xo, uint64_t *n_mut);

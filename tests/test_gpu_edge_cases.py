@@ -175,6 +175,57 @@ def test_segment_warp_kernels_long_lists_and_many_crossovers(cuda_lib, monkeypat
     run_pair(cuda_lib, case, [(20, xo)] * 9, cap=64)
 
 
+def ibd_numpy(seg, off, i, j, min_bp):
+    """Restatement of ge_ibd_sharing on the downloaded lists: per haplotype the covered positions are labelled with their
+    founder (hap_index, root), then runs of equal labels are measured position by position (small genomes only)."""
+    tot = runs = 0
+    for ha in range(2):
+        for hb in range(2):
+            A, B = seg[off[2 * i + ha]:off[2 * i + ha + 1]], seg[off[2 * j + hb]:off[2 * j + hb + 1]]
+            lo, hi = int(min(A[0, 0], B[0, 0])), int(max(A[-1, 1], B[-1, 1]))
+            la, lb = np.full(hi - lo, -1, np.int64), np.full(hi - lo, -2, np.int64)
+            for L, q in ((la, A), (lb, B)):
+                for st, en, z, w in q:
+                    L[int(st) - lo:int(en) - lo] = int(z) * 64 + int(w)
+            same = np.concatenate([[0], (la == lb).astype(np.int8), [0]])
+            d = np.diff(same)
+            for s0, s1 in zip(np.flatnonzero(d == 1), np.flatnonzero(d == -1)):   # maximal stretches on which the two agree
+                if s1 - s0 >= min_bp:
+                    tot += int(s1 - s0)
+                    runs += 1
+    return tot, runs
+
+
+@pytest.mark.parametrize("fmt", ["packed", "16"])
+def test_ibd_sharing_matches_a_position_by_position_count(cuda_lib, monkeypatch, fmt):
+    if fmt == "16":
+        monkeypatch.setenv("GE_SEG_FORMAT", "16")
+    case = Case(77, [120, 30], n_founders=10, map_rows=12, step=40)
+    gpu = capi.Engine(cuda_lib, **case.kwargs(64, representation=capi.GE_REP_SEGMENTS))
+    case.configure(gpu)
+    gpu.init_generation0([case.draws0()])
+    assert gpu.segment_format() == (8 if fmt == "packed" else 16)
+
+    def xo(slot, c):
+        bp, _, step = case.maps[c]
+        return np.sort(case.rng.integers(int(bp[0]), int(bp[-1]), size=int(case.rng.integers(0, 4))))
+
+    n_par = case.nf
+    for g in range(1, 5):      # small populations: plenty of shared ancestry after four generations
+        gpu.step_generation(g, [capi.gen_params(10)], None, [case.draws(n_par, 14, xo)])
+        n_par = 14
+    rng = np.random.default_rng(3)
+    a = np.concatenate([rng.integers(0, 14, 40), np.arange(14)])
+    b = np.concatenate([rng.integers(0, 14, 40), np.arange(14)])      # the last 14 pairs are individuals with themselves
+    for c in range(2):
+        s = gpu.segments(0, c)
+        for min_bp in (0, 25):
+            tot, runs = gpu.ibd_sharing(0, c, a, b, min_bp)
+            want = [ibd_numpy(s["seg"].astype(np.int64), s["seg_off"].astype(np.int64), int(i), int(j), min_bp) for i, j in zip(a, b)]
+            assert [int(t) for t in tot] == [w[0] for w in want] and [int(r) for r in runs] == [w[1] for w in want], (c, min_bp)
+        assert tot[:40].max() > 0   # unrelated pairs share something, too, after four generations of ten founders
+
+
 def test_segment_capacity_is_enforced_on_both_paths(cuda_lib, monkeypatch):
     """seg_capacity smaller than the lists: GE_ERR_CAPACITY from the generation itself (host read-back between the passes) or,
     when the chain is queued on the bulk stream, from the first call after it — never a write beyond the buffer."""
