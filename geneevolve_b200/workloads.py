@@ -49,8 +49,10 @@ def genetic_map(chrs, step=50000, seed=20261018):
     return out
 
 
-def make_workload(name, seed=20261018, n_override=None, loci_override=None):
+def make_workload(name, seed=20261018, n_override=None, loci_override=None, founders_override=None):
     cfg = dict(CONFIGS[name])
+    if founders_override:
+        cfg["founders"] = founders_override
     if n_override:
         cfg["n"] = n_override
     if loci_override:

@@ -15,13 +15,20 @@ from test_sharding_gloo import configure_subset, run_generations
 pytestmark = pytest.mark.gpu
 
 
+REPS = {"bits": (capi.GE_REP_BITS, 0), "segments": (capi.GE_REP_SEGMENTS, 0), "segments-bulk-stream": (capi.GE_REP_SEGMENTS, 400_000),
+        "bits+segments": (capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, 0)}
+
+
+@pytest.mark.parametrize("rep", sorted(REPS))
 @pytest.mark.parametrize("name", ["B_rm_mut", "A_am_pois", "D_two_pops"])
-def test_two_sharded_contexts_match_one(cuda_lib, name):
+def test_two_sharded_contexts_match_one(cuda_lib, name, rep):
     G = Golden(name)
     n_gen = min(G.G, 3)
-    single = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=G.philox_capacity()))
+    representation, seg_capacity = REPS[rep]
+    segs = bool(representation & capi.GE_REP_SEGMENTS)
+    single = capi.Engine(cuda_lib, **G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=representation, seg_capacity=seg_capacity, capacity=G.philox_capacity()))
     G.configure(single)
-    ref = run_generations(G, single, n_gen)
+    ref = run_generations(G, single, n_gen, segments=segs)
 
     world = 2
     weights = [len(G[f"in.p0.c{c}.panel_pos"]) for c in range(G.n_chr)]
@@ -44,12 +51,12 @@ def test_two_sharded_contexts_match_one(cuda_lib, name):
 
     def run(rank):
         try:
-            kw = G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=capi.GE_REP_BITS, capacity=G.philox_capacity())
+            kw = G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=representation, seg_capacity=seg_capacity, capacity=G.philox_capacity())
             kw.update(n_chr=len(parts[rank]), rank=rank, world_size=world)
             eng = capi.Engine(cuda_lib, **kw)
             configure_subset(G, eng, parts[rank])
             eng.set_allreduce(make_hook(rank))
-            results[rank] = run_generations(G, eng, n_gen)
+            results[rank] = run_generations(G, eng, n_gen, segments=segs)
         except Exception as e:  # pragma: no cover
             errors.append(e)
             barrier.abort()
@@ -67,3 +74,6 @@ def test_two_sharded_contexts_match_one(cuda_lib, name):
             np.testing.assert_allclose(out["ind"][k], ref["ind"][k], rtol=1e-10, atol=1e-12)
         for k, c in enumerate(parts[rank]):
             assert np.array_equal(out["hap"][k], ref["hap"][c])
+            if segs:
+                for key in ("seg_off", "seg", "mut_off", "mut_bp"):
+                    assert np.array_equal(out["seg"][k][key], ref["seg"][c][key]), f"rank {rank} chromosome {c}: {key}"

@@ -39,7 +39,7 @@ def configure_subset(G, eng, chrs):
         eng.set_gamma(z["in.gamma"])
 
 
-def run_generations(G, eng, n_gen):
+def run_generations(G, eng, n_gen, segments=False):
     """State of the LAST population after n_gen generations (with migration every population feeds into it)."""
     eng.init_generation0()
     for gen in range(1, n_gen + 1):
@@ -47,6 +47,8 @@ def run_generations(G, eng, n_gen):
     p = G.n_pop - 1
     out = {"couples": eng.get_couples(p), "ind": eng.individuals(p)}
     out["hap"] = [eng.haplotypes(p, k) for k in range(eng.n_chr)]
+    if segments:
+        out["seg"] = [eng.segments(p, k) for k in range(eng.n_chr)]
     return out
 
 
