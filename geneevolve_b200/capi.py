@@ -13,6 +13,7 @@ import numpy as np
 
 GE_REP_BITS, GE_REP_SEGMENTS = 1, 2
 GE_RNG_PHILOX, GE_RNG_REPLAY = 0, 1
+GE_FLAG_SERIAL, GE_FLAG_SEG_WIDE_PARTS, GE_FLAG_SEG_VERBATIM, GE_FLAG_CV_FROM_SEGMENTS, GE_FLAG_NO_GRAPH = 1, 2, 4, 8, 16
 GE_SEL = {"": 0, "logit": 1, "probit": 2, "stab": 3, "thr": 4}
 GE_KERNEL_PROPAGATE_BITS, GE_KERNEL_RECOMBINE_SEGMENTS = 0, 1
 GE_PHASES = {"mate": 2, "sample": 3, "cv_and_genetic_values": 4, "phenotype": 5}
@@ -24,7 +25,7 @@ _u64p, _u8p, _f64p, _i32p, _u32p = (C.POINTER(C.c_uint64), C.POINTER(C.c_uint8),
 class ge_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_pop", C.c_int32), ("n_chr", C.c_int32), ("n_phen", C.c_int32),
                 ("vt_type", C.c_int32), ("representation", C.c_int32), ("rng_mode", C.c_int32),
-                ("reserved0", C.c_int32), ("seed", C.c_uint64), ("capacity", C.c_uint64),
+                ("flags", C.c_int32), ("seed", C.c_uint64), ("capacity", C.c_uint64),
                 ("seg_capacity", C.c_uint64), ("rank", C.c_int32), ("world_size", C.c_int32)]
 
 
@@ -114,14 +115,14 @@ class Engine:
 
     def __init__(self, lib=None, prefix="ge_", *, n_pop=1, n_chr=1, n_phen=1, vt_type=1, device=0,
                  representation=GE_REP_BITS | GE_REP_SEGMENTS, rng_mode=GE_RNG_PHILOX, seed=1, capacity=0,
-                 seg_capacity=0, rank=0, world_size=1):
+                 seg_capacity=0, rank=0, world_size=1, flags=0):
         self.lib = lib if lib is not None else load_library()
         self.prefix = prefix
         self.n_pop, self.n_chr, self.n_phen = n_pop, n_chr, n_phen
         self.n_loci = [0] * n_chr
         self.n_cv = {}
         self._fn("last_error").restype = C.c_char_p
-        self.cfg = ge_config(device, n_pop, n_chr, n_phen, vt_type, representation, rng_mode, 0, seed,
+        self.cfg = ge_config(device, n_pop, n_chr, n_phen, vt_type, representation, rng_mode, flags, seed,
                              capacity, seg_capacity, rank, world_size)
         self.ctx = C.c_void_p()
         self._call("create", C.byref(self.cfg), C.byref(self.ctx))

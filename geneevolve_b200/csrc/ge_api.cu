@@ -30,6 +30,50 @@ static int alloc_gen_state(ge_ctx *ctx, GenState &s) {
     return GE_OK;
 }
 
+// expected draws of one generation at full capacity (+ ten standard deviations): what the draw buffers are sized for once
+static uint64_t draw_bound(double mean) { return (uint64_t)(mean + 10.0 * std::sqrt(mean + 1.0)) + 4096; }
+
+void ge_ctx::drop_graphs() {}
+
+// ge_ctx::pull_state — see ge_context.cuh
+int ge_ctx::pull_state(const char *where) {
+    const int np = cfg.n_pop;
+    CUDA_TRY(cudaMemcpyAsync(h_ss_all, d_ss_all.p, sizeof(StepState) * np, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    int rc = GE_OK;
+    for (int p = 0; p < np; p++) {
+        PopDev &P = pop[p];
+        P.hs = h_ss_all[p];
+        const StepState &h = P.hs;
+        for (int k = 0; k < 2; k++) { P.st[k].n = h.n[k]; P.st[k].n_hm = h.n_hm[k]; P.st[k].seg.n_seg = h.n_seg[k]; }
+        P.n_couples = h.n_couples; P.n_off = h.n_off; P.n_xo = h.n_xo; P.n_mut = h.n_mut; P.prev_n = h.prev_n;
+        for (EvPair &ev : ev_pending) if (ev.bytes_per_offspring && ev.pop == p) { ev.bytes = ev.bytes_per_offspring * h.n_off; ev.bytes_per_offspring = 0; }
+        if (!h.err || rc != GE_OK) continue;
+        const uint32_t e = h.err;
+        const std::string lists = "num_males_mate=" + std::to_string(h.n_m) + ", num_females_mate=" + std::to_string(h.n_f);
+        if (e & SE_NO_MATES_RM) rc = fail(GE_ERR_NO_MATES, "Error: No one can marry, " + lists);
+        else if (e & SE_NO_COUPLES) rc = fail(GE_ERR_NO_MATES, "Error: couples=0, " + lists);
+        else if (e & SE_ALL_INBRED) rc = fail(GE_ERR_NO_MATES, "every couple is inbred");
+        else if (e & SE_CAP_COUPLES) rc = fail(GE_ERR_CAPACITY, "couples exceed the couple buffers");
+        else if (e & SE_NO_OFFSPRING) rc = fail(GE_ERR_NO_MATES, "no offspring");
+        else if (e & SE_CAP_OFFSPRING) rc = fail(GE_ERR_CAPACITY, "offspring (" + std::to_string(h.n_off) + ") exceed capacity");
+        else if (e & SE_CAP_XO) rc = fail(GE_ERR_CAPACITY, "crossovers (" + std::to_string(h.n_xo) + ") exceed the draw buffers (" + std::to_string(h.xo_cap) + ", sized from the genetic map)");
+        else if (e & SE_CAP_MUT) rc = fail(GE_ERR_CAPACITY, "mutation hits (" + std::to_string(h.n_mut) + ") exceed the draw buffers");
+        else if (e & SE_CAP_HM) rc = fail(GE_ERR_CAPACITY, "per-haplotype mutation lists exceed their buffer");
+        else if (e & SE_CAP_SEG) rc = fail(GE_ERR_CAPACITY, "segments exceed seg_capacity (" + std::to_string(std::max(h.n_seg[0], h.n_seg[1])) + " parts; reported by the first read-back after the generation that overflowed)");
+        else if (e & SE_SEG_UNSORTED) rc = fail(GE_ERR_UNSUPPORTED, "gametes had crossover positions that do not ascend: the packed segment format cannot hold the pieces the reference emits for them "
+                                                                    "(create the context with GE_FLAG_SEG_WIDE_PARTS to keep its 16-byte parts)");
+        else if (e & SE_NAN) rc = fail(GE_ERR_NAN, std::string("Error: A or D is nan (") + where + ")");
+        else if (e & SE_PARENT_ID) rc = fail(GE_ERR_INVALID, "parent ID outside the previous generation (the reference reads out of bounds here, :3118-3133)");
+    }
+    if (rc != GE_OK) {
+        const std::string keep = g_err;
+        for (int p = 0; p < np; p++) if (pop[p].hs.err) { pop[p].hs.err = 0; push_state(pop[p], offsetof(StepState, err), 4); }
+        g_err = keep;
+    }
+    return rc;
+}
+
 // genome layout + tile table, once all loci are known
 static int build_genome(ge_ctx *ctx) {
     if (ctx->genome_ready) return GE_OK;
@@ -79,7 +123,6 @@ static int build_genome(ge_ctx *ctx) {
     for (int c = 0; c < C; c++) chunks_per_gamete += ((ctx->chr_nloci[c] + 31) / 32 + 3) / 4;
     uint32_t TILE = 1024;  // 16 KB; measured 0.7 % better than 8 KB on the whole genome, 4 KB and 2 KB are 2 % worse
     while (TILE > 64 && chunks_per_gamete / TILE < 6) TILE >>= 1;
-    if (const char *t = std::getenv("GE_TILE")) TILE = (uint32_t)std::max(16, std::atoi(t));  // measurement aid
     struct Item { uint32_t c, q0, nq; };
     std::vector<Item> items;
     for (int c = 0; c < C; c++) {
@@ -90,6 +133,7 @@ static int build_genome(ge_ctx *ctx) {
     std::vector<uint32_t> tc, t0, tn;
     for (auto &it : items) { tc.push_back(it.c); t0.push_back(it.q0); tn.push_back(it.nq); }
     ctx->n_tiles = (uint32_t)items.size();
+    ctx->n_loci_total = pos.size();
     GE_TRY(ctx->upload(ctx->d_tile_chr, tc));
     GE_TRY(ctx->upload(ctx->d_tile_chunk0, t0));
     GE_TRY(ctx->upload(ctx->d_tile_nchunk, tn));
@@ -228,8 +272,9 @@ int ge_version(void) { return 100; }
 
 int ge_create(const ge_config *cfg, ge_ctx **out) {
     if (!cfg || !out) return fail(GE_ERR_INVALID, "null argument");
-    if (cfg->n_pop < 1 || cfg->n_pop > 15 || cfg->n_chr < 1 || cfg->n_phen < 1) return fail(GE_ERR_INVALID, "bad n_pop/n_chr/n_phen");
+    if (cfg->n_pop < 1 || cfg->n_pop > 15 || cfg->n_chr < 1 || cfg->n_phen < 1 || cfg->n_phen > 8) return fail(GE_ERR_INVALID, "bad n_pop/n_chr/n_phen (at most 15 populations, 8 phenotypes)");
     if (cfg->capacity == 0) return fail(GE_ERR_INVALID, "capacity must be > 0");
+    if (cfg->capacity > 0x7FFFFFFFull) return fail(GE_ERR_UNSUPPORTED, "capacity above 2^31 individuals (positions in a generation are 32-bit)");
     if (cfg->rng_mode != GE_RNG_PHILOX && cfg->rng_mode != GE_RNG_REPLAY) return fail(GE_ERR_INVALID, "rng_mode must be GE_RNG_PHILOX or GE_RNG_REPLAY");
     if (!(cfg->representation & (GE_REP_BITS | GE_REP_SEGMENTS))) return fail(GE_ERR_INVALID, "representation must include GE_REP_BITS and/or GE_REP_SEGMENTS");
     int ndev = 0;
@@ -251,32 +296,39 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
         P.panel.resize(cfg->n_chr);
         P.var_a0.assign(cfg->n_phen, 0); P.var_d0.assign(cfg->n_phen, 0);
     }
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
-    cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo);
-    c->serial = std::getenv("GE_SERIAL") != nullptr;
-    c->cub_sorts = std::getenv("GE_CUB_SORTS") != nullptr;
-    if (const char *t = std::getenv("GE_THIN")) c->thin = std::atoi(t);
-    c->cv_from_segments = std::getenv("GE_CV_FROM_SEGMENTS") != nullptr;
-    c->seg_per_thread = std::getenv("GE_SEG_PER_THREAD") != nullptr;
-    if (const char *t = std::getenv("GE_SEG_GROUP")) c->seg_group = std::atoi(t);
-    c->seg_walk = std::getenv("GE_SEG_WALK") != nullptr;
-    c->seg_sync_mode = std::getenv("GE_SEG_SYNC") != nullptr;
-    if (const char *t = std::getenv("GE_SEG_FORMAT")) c->seg_wide = std::atoi(t) == 16;
-    if (const char *t = std::getenv("GE_SEG_DEPTH")) c->seg_depth = std::atoi(t);
-    if (const char *t = std::getenv("GE_SEG_PLAN_MIN")) c->seg_plan_min_parts = std::atof(t);
-    if (const char *t = std::getenv("GE_PROP_DEPTH")) c->prop_depth = std::atoi(t);
-    if (const char *t = std::getenv("GE_PROP")) c->use_tma = std::string(t) == "tma";
-    if (const char *t = std::getenv("GE_THIN_MIN_GB")) c->thin_min_bytes = std::atof(t) * 1e9;  // measurement aid: queue the bulk kernel on the control stream (no overlap)
-    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
-    cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
-    for (PopDev &P : c->pop) for (DrawSet &D : P.ds) cudaEventCreateWithFlags(&D.bulk_done, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-    for (SortLane &l : c->lane) { cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, prio_hi); cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming); }
-    cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
-    if (c->ensure(c->flags, 64) != GE_OK) { delete c; return GE_ERR_CUDA; }
-    cudaMemsetAsync(c->flags.p, 0, 64, c->stream);
+    c->serial = (cfg->flags & GE_FLAG_SERIAL) != 0;
+    c->seg_wide = (cfg->flags & GE_FLAG_SEG_WIDE_PARTS) != 0;
+    c->seg_per_thread = (cfg->flags & GE_FLAG_SEG_VERBATIM) != 0;
+    c->cv_from_segments = (cfg->flags & GE_FLAG_CV_FROM_SEGMENTS) != 0;
+    c->use_graph = (cfg->flags & GE_FLAG_NO_GRAPH) == 0;
+    // every CUDA object is created through one failure path: ge_destroy copes with whatever exists by then
+    auto setup = [&]() -> int {
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo));
+        CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        for (PopDev &P : c->pop) for (DrawSet &D : P.ds) CUDA_TRY(cudaEventCreateWithFlags(&D.bulk_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        for (SortLane &l : c->lane) { CUDA_TRY(cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, prio_hi)); CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming)); }
+        CUDA_TRY(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+        // the device-resident step state of every population, and its pinned read-back buffer
+        GE_TRY(c->ensure(c->d_ss_all, sizeof(StepState) * cfg->n_pop));
+        CUDA_TRY(cudaMemsetAsync(c->d_ss_all.p, 0, sizeof(StepState) * cfg->n_pop, c->stream));
+        CUDA_TRY(cudaMallocHost(&c->h_ss_all, sizeof(StepState) * cfg->n_pop));
+        for (int p = 0; p < cfg->n_pop; p++) {
+            PopDev &P = c->pop[p];
+            P.d_ss = c->d_ss_all.as<StepState>() + p;
+            P.hs = StepState{};
+            P.hs.cap = cfg->capacity;
+            for (int k = 0; k < 2; k++) { P.st[k].d_n = &P.d_ss->n[k]; P.st[k].d_n_hm = &P.d_ss->n_hm[k]; }
+            GE_TRY(c->push_state(P));
+        }
+        GE_TRY(c->ensure_partial());
+        return GE_OK;
+    };
+    if (int rc = setup()) { const std::string keep = g_err; ge_destroy(c); g_err = keep; return rc; }
     *out = c;
     return GE_OK;
 }
@@ -284,9 +336,10 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
 int ge_destroy(ge_ctx *ctx) {
     if (!ctx) return GE_OK;
     cudaSetDevice(ctx->cfg.device);
-    cudaStreamSynchronize(ctx->bulk);
-    cudaStreamSynchronize(ctx->stream);
-    for (SortLane &l : ctx->lane) cudaStreamSynchronize(l.s);
+    if (ctx->bulk) cudaStreamSynchronize(ctx->bulk);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (SortLane &l : ctx->lane) if (l.s) cudaStreamSynchronize(l.s);
+    ctx->drop_graphs();
     auto freeb = [&](Buf &b) { ctx->release(b); };
     for (PopDev &P : ctx->pop) {
         for (Buf *b : {&P.d_row_off, &P.d_bp, &P.d_T, &P.d_bp_dist, &P.d_mrow_off, &P.d_mbp, &P.d_mT, &P.d_vb, &P.d_vb_off, &P.d_vb_scale, &P.d_mvb, &P.d_mvb_off, &P.d_mvb_scale, &P.d_cov_lo, &P.d_cov_hi, &P.d_omega,
@@ -295,32 +348,32 @@ int ge_destroy(ge_ctx *ctx) {
         freeb(P.mig_pop[0]); freeb(P.mig_idx[0]); freeb(P.rowmap_buf[0]); freeb(P.rowmap_buf[1]);
         for (DrawSet &D : P.ds) {
             for (Buf *b : {&D.father, &D.mother, &D.couple_of, &D.xo_off, &D.xo_bp, &D.flips, &D.start_hap}) freeb(*b);
-            cudaEventDestroy(D.bulk_done);
+            if (D.bulk_done) cudaEventDestroy(D.bulk_done);
         }
         for (GenState &s : P.st) {
             for (Buf *b : {&s.hap, &s.cv_allele, &s.cv_root, &s.ids, &s.sex, &s.A, &s.D, &s.G, &s.C, &s.E, &s.F, &s.P, &s.mv, &s.sv, &s.svf, &s.hm_off, &s.hm_bp}) freeb(*b);
-            for (cudaEvent_t e : s.seg.ev) if (e) cudaEventDestroy(e);
-            seg_release(s.seg);
+            seg_release(ctx, s.seg);
         }
-        mate_release(P.mate);
+        mate_release(ctx, P.mate);
     }
     for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_bkt_off, &ctx->d_bkt_shift, &ctx->d_bkt, &ctx->d_LA, &ctx->d_cv_bitpos, &ctx->xo_stash, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
-                   &ctx->d_cv_block_off, &ctx->d_cv_word_off, &ctx->d_cv_word_blk, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks,
-                   &ctx->scan_total, &ctx->partial, &ctx->scalars, &ctx->flags, &ctx->d_chr_ids, &ctx->ar_scratch, &ctx->seg_desc, &ctx->seg_iv_off, &ctx->seg_cnt,
-                   &ctx->seg_scan_blocks, &ctx->seg_scan_total, &ctx->seg_flags, &ctx->seg_verb})
+                   &ctx->d_cv_block_off, &ctx->d_cv_word_off, &ctx->d_cv_word_blk, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks, &ctx->bulk_scan_blocks,
+                   &ctx->partial, &ctx->scalars, &ctx->d_ss_all, &ctx->d_chr_ids, &ctx->ar_scratch, &ctx->seg_desc, &ctx->seg_iv_off, &ctx->seg_cnt, &ctx->seg_flags, &ctx->seg_verb})
         freeb(*b);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_join);
+    if (ctx->h_ss_all) cudaFreeHost(ctx->h_ss_all);
+    for (uint64_t *c : ctx->pinned_chunks) cudaFreeHost(c);
+    for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_ready, ctx->ev_join, ctx->ev_fork}) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (SortLane &l : ctx->lane) {
-        for (Buf *b : {&l.keys_in, &l.keys_out, &l.vals_out, &l.tmp}) freeb(*b);
-        cudaEventDestroy(l.done); cudaStreamDestroy(l.s);
+        for (Buf *b : {&l.keys_in, &l.vals_in, &l.keys_out, &l.vals_out, &l.tmp}) freeb(*b);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.s) cudaStreamDestroy(l.s);
     }
-    cudaEventDestroy(ctx->ev_fork);
     for (int q = 0; q < 2; q++) { for (Buf &b : ctx->mig_lists[q]) freeb(b); if (ctx->mig_done[q]) cudaEventDestroy(ctx->mig_done[q]); }
     freeb(ctx->mig_stage);
-    cudaStreamDestroy(ctx->bulk);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->bulk) cudaStreamDestroy(ctx->bulk);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GE_OK;
 }
@@ -334,14 +387,20 @@ int ge_set_population(ge_ctx *ctx, int pop, int avoid_inbreeding, int random_mat
 int ge_set_genetic_map(ge_ctx *ctx, int pop, int chr, const uint64_t *bp, const double *rp, uint64_t n, uint64_t bp_dist) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr);
     if (!bp || !rp || n < 2 || bp_dist == 0 || bp_dist > 0xFFFFFFFFull) return fail(GE_ERR_INVALID, "ge_set_genetic_map: need >= 2 rows and 0 < bp_dist < 2^32");
+    if (ctx->gen0_done) return fail(GE_ERR_INVALID, "ge_set_genetic_map after ge_init_generation0 (the segment format and the draw buffers are fixed there)");
+    // A row with probability >= 1 would end the survival product the skip sampler searches (T = 0 from there on): the reference
+    // draws an independent Bernoulli per row (:2985-2990) and would go on.  Such maps (a 100 cM jump between two rows) are refused.
+    for (uint64_t j = 0; j < n; j++) if (rp[j] >= 1.0) return fail(GE_ERR_UNSUPPORTED, "genetic map row with recombination probability >= 1 (a jump of 100 cM or more between two rows)");
     // the bit-packed representation needs monotone crossover lists: row j's crossover lies in
-    // [bp[j], bp[j]+bp_dist) (:2989), so rows must be at least bp_dist apart (true for the uniform b37 maps)
-    for (uint64_t j = 0; j + 2 < n; j++)
-        if (bp[j + 1] < bp[j] + bp_dist && rp[j] > 0) {
-            if (ctx->cfg.representation & GE_REP_BITS)
-                return fail(GE_ERR_UNSUPPORTED, "genetic map rows closer than bp_dist_in_rmap give non-monotone crossover lists (only GE_REP_SEGMENTS follows the reference there)");
-            ctx->seg_per_thread = true;  // segment lists may become unsorted: keep the reference's scan verbatim
-        }
+    // [bp[j], bp[j]+bp_dist) (:2989), so two rows that can both recombine must be at least bp_dist apart (true for the uniform b37 maps)
+    bool close_rows = false;
+    for (uint64_t j = 0; j + 1 < n; j++)
+        if (bp[j + 1] < bp[j] + bp_dist && rp[j] > 0 && rp[j + 1] > 0) close_rows = true;
+    if (close_rows) {
+        if (ctx->cfg.representation & GE_REP_BITS)
+            return fail(GE_ERR_UNSUPPORTED, "genetic map rows closer than bp_dist_in_rmap give non-monotone crossover lists (only GE_REP_SEGMENTS follows the reference there)");
+        ctx->seg_per_thread = true;  // segment lists may become unsorted: keep the reference's scan verbatim (and its 16-byte parts)
+    }
     PopDev &P = ctx->pop[pop];
     P.rmap_bp[chr].assign(bp, bp + n); P.recom_prob[chr].assign(rp, rp + n); P.bp_dist[chr] = bp_dist;
     return GE_OK;
@@ -349,7 +408,11 @@ int ge_set_genetic_map(ge_ctx *ctx, int pop, int chr, const uint64_t *bp, const 
 int ge_set_mutation_map(ge_ctx *ctx, int pop, int chr, const uint64_t *bp, const double *rate, uint64_t n) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr);
     if (!bp || !rate || n < 2) return fail(GE_ERR_INVALID, "ge_set_mutation_map: need >= 2 rows");
-    for (uint64_t k = 0; k < n; k++) if (bp[k] > 0xFFFFFFFFull) return fail(GE_ERR_UNSUPPORTED, "mutation-map position does not fit 32 bits");
+    if (ctx->gen0_done) return fail(GE_ERR_INVALID, "ge_set_mutation_map after ge_init_generation0");
+    for (uint64_t k = 0; k < n; k++) {
+        if (bp[k] > 0x7FFFFFFFull) return fail(GE_ERR_UNSUPPORTED, "mutation-map position does not fit 31 bits");
+        if (rate[k] >= 1.0 && k >= 1) return fail(GE_ERR_UNSUPPORTED, "mutation rate >= 1 in a map row (the skip sampler's survival product would end there)");
+    }
     PopDev &P = ctx->pop[pop];
     P.mutmap_bp[chr].assign(bp, bp + n); P.mutmap_rate[chr].assign(rate, rate + n); P.has_mut = true;
     return GE_OK;
@@ -405,41 +468,41 @@ int ge_set_allreduce(ge_ctx *ctx, ge_allreduce_fn fn, void *user) { CHECK_CTX(ct
 int ge_set_gamma(ge_ctx *ctx, const double *g) { CHECK_CTX(ctx); ctx->gamma.assign(g, g + ctx->cfg.n_phen); return GE_OK; }
 
 // ---------------- per-method entry points ----------------
+// Every method has an enqueue_* form that only queues work (sizes are read from StepState on the device) and a public
+// form that adds the host synchronisation (pull_state) the reference's `bool` return needs.  ge_step_generation chains the
+// enqueue_* forms and synchronises once.
 
-int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
-    CHECK_POP(ctx, pop);
-    (void)gen;
+static int enqueue_AD(ge_ctx *ctx, int pop) {  // ras_compute_AD :2624-2749
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
-    if (S.n == 0) return fail(GE_ERR_INVALID, "empty population");
-    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    const uint64_t cap = ctx->cfg.capacity;
     ge_ctx::PhaseTimer timer(ctx, GE_PHASE_CV_AD);
     if (ctx->segs() && !ctx->bits() && ctx->cv_from_segments) GE_TRY(seg_find_cv(ctx, pop));  // ras_find_cv on the segment lists (verification mode)
     uint32_t ncv = ctx->n_cv_tot;
     if (ncv) {
         CUDA_TRY(cudaMemsetAsync(ctx->d_cv_count.p, 0, (size_t)ncv * 8, ctx->stream));
-        dim3 grid(nblk(ctx->Wcv, 32), nblk(2 * S.n, 512));
-        cv_count_bits_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), 2 * S.n, ctx->d_cv_count.as<unsigned long long>());
+        dim3 grid(nblk(ctx->Wcv, 32), nblk(2 * cap, 512));
+        cv_count_bits_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), S.d_n, ctx->d_cv_count.as<unsigned long long>());
         GE_TRY(ctx->check_launch("cv_count"));
     }
-    uint64_t nw = S.n * ctx->cfg.n_phen;
+    const uint64_t nw = cap * ctx->cfg.n_phen;
     if (!ctx->use_root && ncv) {
-        cv_tables_kernel<<<nblk(ncv, 128), 128, 0, ctx->stream>>>(ctx->cvset(), ctx->d_cv_count.as<unsigned long long>(), S.n, ctx->d_a_eff.as<double>(),
+        cv_tables_kernel<<<nblk(ncv, 128), 128, 0, ctx->stream>>>(ctx->cvset(), ctx->d_cv_count.as<unsigned long long>(), S.d_n, ctx->d_a_eff.as<double>(),
                                                                   ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), ctx->d_LA.as<double2>());
         GE_TRY(ctx->check_launch("cv_tables"));
-        genetic_value_lut_kernel<<<ctx->ctrl_grid(nw * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_cv_bitpos.as<uint32_t>(), ctx->d_LA.as<double2>(), S.n,
-                                                                              S.A.as<double>(), S.D.as<double>(), S.G.as<double>(), ctx->flags.as<int>());
+        genetic_value_lut_kernel<<<ctx->ctrl_grid(nw * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_cv_bitpos.as<uint32_t>(), ctx->d_LA.as<double2>(), S.d_n, cap,
+                                                                              S.A.as<double>(), S.D.as<double>(), S.G.as<double>(), &P.d_ss->err);
         GE_TRY(ctx->check_launch("genetic_value_lut"));
     } else {
-        genetic_value_kernel<<<nblk(nw * 32, 256), 256, 0, ctx->stream>>>(
-            ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.n,
-            ctx->d_a_eff.as<double>(), ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), S.n, S.A.as<double>(), S.D.as<double>(), S.G.as<double>(),
-            ctx->flags.as<int>());
+        genetic_value_kernel<<<ctx->ctrl_grid(nw * 32, 256), 256, 0, ctx->stream>>>(
+            ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.d_n,
+            ctx->d_a_eff.as<double>(), ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), cap, S.A.as<double>(), S.D.as<double>(), S.G.as<double>(), &P.d_ss->err);
         GE_TRY(ctx->check_launch("genetic_value"));
     }
     if (ctx->allreduce) {
-        // chromosome-sharded contexts hold partial sums over their own chromosomes: sum A, D, G over the ranks
-        size_t nb = (size_t)S.n * ctx->cfg.n_phen * 8;
+        // sharded contexts hold partial sums over their own loci: sum A, D, G over the ranks.  The columns go whole (stride =
+        // capacity; rows beyond the population hold stale finite values nobody reads), so the count does not depend on a device-side size.
+        size_t nb = (size_t)cap * ctx->cfg.n_phen * 8;
         GE_TRY(ctx->ensure(ctx->ar_scratch, 3 * nb));
         char *sc = ctx->ar_scratch.as<char>();
         CUDA_TRY(cudaMemcpyAsync(sc, S.A.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -453,89 +516,116 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {  // ras_compute_AD :2624-2749
     }
     return GE_OK;
 }
+int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {
+    CHECK_POP(ctx, pop);
+    (void)gen;
+    if (ctx->pop[pop].st[ctx->pop[pop].cur].n == 0) return fail(GE_ERR_INVALID, "empty population");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(enqueue_AD(ctx, pop));
+    return ctx->pull_state("ge_compute_AD");
+}
 
-static int scale_AD_compute_GEF_impl(ge_ctx *ctx, int pop, int gen, int f, const double *e_host, const double *f0_host) {  // :3075-3206
+// e_host / f0_host: replayed draws (host arrays of the population's current size), else Philox
+static int enqueue_GEF(ge_ctx *ctx, int pop, int f, bool gen0, const double *e_host, const double *f0_host) {  // :3075-3206
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
-    uint64_t n = S.n;
+    const uint64_t cap = ctx->cfg.capacity;
     Scheme &sc = P.scheme[f];
-    GE_TRY(ctx->ensure(P.e_raw, (size_t)ctx->cfg.capacity * ctx->cfg.n_phen * 8));
+    GE_TRY(ctx->ensure(P.e_raw, (size_t)cap * ctx->cfg.n_phen * 8));
     GE_TRY(ctx->ensure(ctx->scalars, 64 * 8));
-    double *e = P.e_raw.as<double>() + (uint64_t)f * n;
-    if (e_host) CUDA_TRY(cudaMemcpyAsync(e, e_host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    else if (ctx->cfg.rng_mode == GE_RNG_PHILOX) {
-        enoise_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->rng, pop, gen, f, 0, n, e);
-        GE_TRY(ctx->check_launch("enoise"));
+    GE_TRY(ctx->ensure_partial());
+    double *e = P.e_raw.as<double>() + (uint64_t)f * cap;
+    double *var_e = ctx->scalars.as<double>() + 8, *mean_e = ctx->scalars.as<double>() + 9;
+    const unsigned mg = ctx->moment_grid(cap);
+    if (e_host) {
+        CUDA_TRY(cudaMemcpyAsync(e, e_host, S.n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        GE_TRY(ctx->d_mean(e, devn(S.d_n), cap, mean_e));
+    } else if (ctx->cfg.rng_mode == GE_RNG_PHILOX) {
+        enoise_mean_kernel<<<mg, 256, 0, ctx->stream>>>(ctx->rng, P.d_ss, pop, f, S.d_n, e, ctx->partial.as<double>(), mean_e);
+        GE_TRY(ctx->check_launch("enoise_mean"));
     } else return fail(GE_ERR_INVALID, "replay mode needs e_raw");
     P.have_e_raw = true;
-    double *var_e = ctx->scalars.as<double>() + 8, *tmp = ctx->scalars.as<double>() + 9;
-    GE_TRY(ctx->d_var(e, n, var_e, tmp));
+    moment_kernel<<<mg, 256, 0, ctx->stream>>>(e, devn(S.d_n), mean_e, 1, 1, ctx->partial.as<double>(), var_e);
+    GE_TRY(ctx->check_launch("moment<var>"));
     double *f0 = nullptr;
-    if (gen == 0 && sc.vf > 0) {
-        f0 = S.F.as<double>() + (uint64_t)f * n;  // staged in place, the kernel reads f0[i] before writing F[i]
-        if (f0_host) CUDA_TRY(cudaMemcpyAsync(f0, f0_host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (gen0 && sc.vf > 0) {
+        f0 = S.F.as<double>() + (uint64_t)f * cap;  // staged in place, the kernel reads f0[i] before writing F[i]
+        if (f0_host) CUDA_TRY(cudaMemcpyAsync(f0, f0_host, S.n * 8, cudaMemcpyHostToDevice, ctx->stream));
         else if (ctx->cfg.rng_mode == GE_RNG_PHILOX) {
-            normal_scaled_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->rng, P_F0, pop, 0, f, 0, n, std::sqrt(sc.vf), f0);
+            normal_scaled_kernel<<<nblk(S.n, 256), 256, 0, ctx->stream>>>(ctx->rng, P_F0, pop, 0, f, S.n, std::sqrt(sc.vf), f0);
             GE_TRY(ctx->check_launch("f0"));
         } else return fail(GE_ERR_INVALID, "replay mode needs parental0 for vf > 0");
     }
     PhenoArgs a;
     a.s_a = 1; if (sc.va > 0) a.s_a = std::sqrt(P.var_a0[f] / sc.va);
     a.s_d = 0; if (sc.vd > 0) a.s_d = std::sqrt(P.var_d0[f] / sc.vd); else if (sc.vd == -1) a.s_d = 1;
-    a.ve = sc.ve; a.vf = sc.vf; a.beta = sc.beta; a.gen = gen; a.vt_type = ctx->cfg.vt_type; a.n = n; a.prev_n = P.prev_n;
-    uint64_t o = (uint64_t)f * n;
-    phenotype_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(
-        a, e, var_e, S.A.as<double>() + o, S.D.as<double>() + o, S.G.as<double>() + o, S.C.as<double>() + o, S.E.as<double>() + o,
-        S.F.as<double>() + o, S.P.as<double>() + o, S.ids.as<uint64_t>(), P.prev_P.as<double>() ? P.prev_P.as<double>() + (uint64_t)f * P.prev_n : nullptr,
-        P.prev_F.as<double>() ? P.prev_F.as<double>() + (uint64_t)f * P.prev_n : nullptr, f0, ctx->flags.as<int>() + 1);
+    a.ve = sc.ve; a.vf = sc.vf; a.beta = sc.beta; a.vt_type = ctx->cfg.vt_type;
+    uint64_t o = (uint64_t)f * cap;
+    phenotype_kernel<<<ctx->grid_for(cap, 256), 256, 0, ctx->stream>>>(
+        a, P.d_ss, S.d_n, &P.d_ss->prev_n, e, var_e, S.A.as<double>() + o, S.D.as<double>() + o, S.G.as<double>() + o, S.C.as<double>() + o, S.E.as<double>() + o,
+        S.F.as<double>() + o, S.P.as<double>() + o, S.ids.as<uint64_t>(), P.prev_P.as<double>() ? P.prev_P.as<double>() + o : nullptr,
+        P.prev_F.as<double>() ? P.prev_F.as<double>() + o : nullptr, f0, &P.d_ss->err);
     return ctx->check_launch("phenotype");
 }
 
 int ge_scale_AD_compute_GEF(ge_ctx *ctx, int pop, int gen, int phen, const double *e_raw) {
     CHECK_POP(ctx, pop); CHECK_PHEN(ctx, phen);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    GE_TRY(scale_AD_compute_GEF_impl(ctx, pop, gen, phen, e_raw, nullptr));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // e_raw is a caller buffer
-    return GE_OK;
+    PopDev &P = ctx->pop[pop];
+    if (P.hs.gen != gen) { P.hs.gen = gen; GE_TRY(ctx->push_state(P, offsetof(StepState, gen), 4)); }
+    GE_TRY(enqueue_GEF(ctx, pop, phen, gen == 0, e_raw, nullptr));
+    return ctx->pull_state("ge_scale_AD_compute_GEF");   // (also: e_raw is a caller buffer)
 }
 
-int ge_compute_mating_value_selection_value(ge_ctx *ctx, int pop, int gen, const ge_gen_params *gp) {  // :3300-3342
+static int enqueue_mv_sv(ge_ctx *ctx, int pop) {  // :3300-3342, generations >= 1 (generation 0 also takes the moments, below)
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    const uint64_t cap = ctx->cfg.capacity;
+    mv_sv_selection_kernel<<<ctx->grid_for(cap, 256), 256, 0, ctx->stream>>>(P.d_ss, S.d_n, ctx->cfg.n_phen, cap, S.P.as<double>(), P.d_omega.as<double>(), P.d_lambda.as<double>(),
+                                                                             P.d_sv0.as<double>(), S.mv.as<double>(), S.sv.as<double>(), S.svf.as<double>());
+    return ctx->check_launch("mv_sv_selection");
+}
+int ge_compute_mating_value_selection_value(ge_ctx *ctx, int pop, int gen, const ge_gen_params *gp) {
     CHECK_POP(ctx, pop);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
-    uint64_t n = S.n;
+    const uint64_t cap = ctx->cfg.capacity;
     GE_TRY(ctx->ensure(P.d_sv0, 16));
-    // sv_raw staged in S.sv, standardised in place by selection_kernel
-    mv_sv_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, ctx->cfg.n_phen, S.P.as<double>(), P.d_omega.as<double>(), P.d_lambda.as<double>(),
-                                                        S.mv.as<double>(), S.sv.as<double>());
-    GE_TRY(ctx->check_launch("mv_sv"));
-    double *sv0 = P.d_sv0.as<double>();
-    if (gen == 0) {
-        GE_TRY(ctx->d_var(S.sv.as<double>(), n, sv0 + 1, sv0 + 0));
-        if (n <= 1) GE_TRY(ctx->d_mean(S.sv.as<double>(), n, sv0));
+    ge_gen_params dummy{};
+    if (!gp) gp = &dummy;
+    P.hs.gen = gen; P.hs.sel_func = gp->selection_func; P.hs.sel_par1 = gp->selection_par1; P.hs.sel_par2 = gp->selection_par2;
+    GE_TRY(ctx->push_state(P, 0, offsetof(StepState, n)));
+    if (gen == 0) {   // the generation-0 mean and variance of the raw selection value standardise every later generation (:3325-3337)
+        mv_sv_selection_kernel<<<ctx->grid_for(cap, 256), 256, 0, ctx->stream>>>(P.d_ss, S.d_n, ctx->cfg.n_phen, cap, S.P.as<double>(), P.d_omega.as<double>(), P.d_lambda.as<double>(),
+                                                                                 nullptr, S.mv.as<double>(), S.sv.as<double>(), S.svf.as<double>());
+        GE_TRY(ctx->check_launch("mv_sv_raw"));
+        double *sv0 = P.d_sv0.as<double>();
+        GE_TRY(ctx->d_var(S.sv.as<double>(), devn(S.d_n), cap, sv0 + 1, sv0 + 0));
         double h[2];
         CUDA_TRY(cudaMemcpyAsync(h, sv0, 16, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         P.sv_mean0 = h[0]; P.sv_var0 = h[1];
     }
-    ge_gen_params dummy{};
-    if (!gp) gp = &dummy;
-    selection_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, gen, gp->selection_func, gp->selection_par1, gp->selection_par2, sv0, sv0 + 1,
-                                                            S.sv.as<double>(), S.sv.as<double>(), S.svf.as<double>());
-    return ctx->check_launch("selection");
+    GE_TRY(enqueue_mv_sv(ctx, pop));
+    return ctx->pull_state("ge_compute_mating_value_selection_value");
 }
 
-int ge_save_human_info_to_Pop_info_prev_gen(ge_ctx *ctx, int pop) {  // :3211-3236
-    CHECK_POP(ctx, pop);
+static int enqueue_save_prev(ge_ctx *ctx, int pop) {  // :3211-3236
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
-    size_t bytes = (size_t)ctx->cfg.capacity * ctx->cfg.n_phen * 8;
+    const uint64_t cap = ctx->cfg.capacity;
+    size_t bytes = (size_t)cap * ctx->cfg.n_phen * 8;
     GE_TRY(ctx->ensure(P.prev_P, bytes)); GE_TRY(ctx->ensure(P.prev_F, bytes));
-    size_t nb = (size_t)S.n * ctx->cfg.n_phen * 8;
-    CUDA_TRY(cudaMemcpyAsync(P.prev_P.p, S.P.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(P.prev_F.p, S.F.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-    P.prev_n = S.n;
+    save_prev_kernel<<<ctx->grid_for(cap * ctx->cfg.n_phen, 256), 256, 0, ctx->stream>>>(S.d_n, ctx->cfg.n_phen, cap, S.P.as<double>(), S.F.as<double>(), P.prev_P.as<double>(),
+                                                                                       P.prev_F.as<double>(), &P.d_ss->prev_n);
+    return ctx->check_launch("save_prev");
+}
+int ge_save_human_info_to_Pop_info_prev_gen(ge_ctx *ctx, int pop) {
+    CHECK_POP(ctx, pop);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(enqueue_save_prev(ctx, pop));
+    ctx->pop[pop].prev_n = ctx->pop[pop].st[ctx->pop[pop].cur].n;
     return GE_OK;
 }
 
@@ -544,6 +634,8 @@ int ge_environmental_effects_specific_to_each_population(ge_ctx *ctx, int f) {  
     if (ctx->gamma.empty() || ctx->gamma[f] == 0) return GE_OK;
     int np = ctx->cfg.n_pop;
     if (np < 2) return fail(GE_ERR_UNSUPPORTED, "--gamma with one population divides by zero in the reference (:3269)");
+    GE_TRY(ctx->pull_state("environmental effects"));   // population sizes (the moments below go through the host anyway)
+    const uint64_t cap = ctx->cfg.capacity;
     // pooled variance of P + a*s_i is quadratic in a; the moments come from the device, the scalar Newton
     // iteration (NewtonRaphson :44-63, central difference :35-39) runs on the host with the same start/tolerance
     std::vector<double> ni(np), mu(np), m2(np), s(np);
@@ -551,7 +643,7 @@ int ge_environmental_effects_specific_to_each_population(ge_ctx *ctx, int f) {  
     for (int p = 0; p < np; p++) {
         GenState &S = ctx->pop[p].st[ctx->pop[p].cur];
         double v, m;
-        GE_TRY(ctx->h_var(S.P.as<double>() + (uint64_t)f * S.n, S.n, &v, &m));
+        GE_TRY(ctx->h_var(S.P.as<double>() + (uint64_t)f * cap, S.n, &v, &m));
         ni[p] = (double)S.n; mu[p] = m; m2[p] = v * (double)(S.n > 1 ? S.n - 1 : 0);
         s[p] = (double)(2 * p / (np - 1) - 1);  // integer arithmetic as in the reference (:3269, :3289)
         N += ni[p];
@@ -577,7 +669,7 @@ int ge_environmental_effects_specific_to_each_population(ge_ctx *ctx, int f) {  
     }
     for (int p = 0; p < np; p++) {
         GenState &S = ctx->pop[p].st[ctx->pop[p].cur];
-        add_scalar_kernel<<<nblk(S.n, 256), 256, 0, ctx->stream>>>(S.P.as<double>() + (uint64_t)f * S.n, S.n, x1 * s[p]);
+        add_scalar_kernel<<<nblk(S.n, 256), 256, 0, ctx->stream>>>(S.P.as<double>() + (uint64_t)f * cap, S.n, x1 * s[p]);
         GE_TRY(ctx->check_launch("add_scalar"));
     }
     return GE_OK;
@@ -595,6 +687,33 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
     P.cur = 0;
     GenState &S = P.st[0];
     S.n = n;
+    // sizes the host decides go to the device-resident step state; the draw buffers are sized ONCE, from the maps: expected
+    // crossovers / mutation hits of a generation at full capacity plus ten standard deviations
+    {
+        const uint64_t cap = ctx->cfg.capacity;
+        double e_xo = 0, e_mut = 0;
+        for (int c = 0; c < C; c++) {
+            for (double q : P.recom_prob[c]) e_xo += std::min(std::max(q, 0.0), 1.0);
+            for (size_t k = 1; k < P.mutmap_rate[c].size(); k++) e_mut += std::min(std::max(P.mutmap_rate[c][k], 0.0), 1.0);
+        }
+        P.hs.n[0] = n; P.hs.n[1] = 0; P.hs.n_hm[0] = P.hs.n_hm[1] = 0; P.hs.gen = 0; P.hs.prev_n = n;
+        P.hs.xo_cap = draw_bound(2.0 * (double)cap * e_xo);
+        P.hs.mut_cap = P.has_mut ? draw_bound((double)cap * e_mut) : 0;
+        P.hs.hm_cap = 0;
+        GE_TRY(ctx->push_state(P));
+        const uint64_t slots = cap * C * 2;
+        for (DrawSet &D : P.ds) {
+            GE_TRY(ctx->ensure(D.father, cap * 4)); GE_TRY(ctx->ensure(D.mother, cap * 4)); GE_TRY(ctx->ensure(D.couple_of, cap * 4));
+            GE_TRY(ctx->ensure(D.xo_off, (slots + 1) * 8)); GE_TRY(ctx->ensure(D.start_hap, slots));
+            GE_TRY(ctx->ensure(D.xo_bp, P.hs.xo_cap * 4));
+            if (ctx->bits()) GE_TRY(ctx->ensure(D.flips, P.hs.xo_cap * 4));
+        }
+        if (ctx->cfg.rng_mode == GE_RNG_PHILOX) GE_TRY(ctx->ensure(ctx->xo_stash, slots * XO_STASH * 4));
+        GE_TRY(ctx->ensure(P.cnt32, (slots + 1) * 4));
+        if (P.has_mut) {
+            GE_TRY(ctx->ensure(P.mut_off, (cap * C + 1) * 8)); GE_TRY(ctx->ensure(P.mut_bp, P.hs.mut_cap * 4)); GE_TRY(ctx->ensure(P.mut_gam, P.hs.mut_cap));
+        }
+    }
     // scheme constants on the device
     std::vector<double> om(nf), la(nf); std::vector<uint8_t> vz(nf);
     for (int f = 0; f < nf; f++) { om[f] = P.scheme[f].omega; la[f] = P.scheme[f].lambda; vz[f] = P.scheme[f].vd == 0; }
@@ -667,18 +786,18 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
     for (uint64_t i = 0; i < n; i++) for (int k = 0; k < 7; k++) ids[i * 7 + k] = i;  // :3037-3043
     CUDA_TRY(cudaMemcpyAsync(S.ids.p, ids.data(), ids.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->cfg.rng_mode == GE_RNG_PHILOX) {
-        sex_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->rng, p, 0, 0, n, S.sex.as<uint8_t>());
+        sex_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->rng, p, 0, n, S.sex.as<uint8_t>());
         GE_TRY(ctx->check_launch("sex"));
     } else {
         if (!d0 || !d0[p].sex) return fail(GE_ERR_INVALID, "replay mode needs draws0[pop].sex");
         CUDA_TRY(cudaMemcpyAsync(S.sex.p, d0[p].sex, n, cudaMemcpyHostToDevice, ctx->stream));
     }
-    CUDA_TRY(cudaMemsetAsync(S.C.p, 0, (size_t)n * nf * 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(S.C.p, 0, (size_t)ctx->cfg.capacity * nf * 8, ctx->stream));
     for (int f = 0; f < nf; f++) {
         if (P.scheme[f].vc > 0) {
-            double *dst = S.C.as<double>() + (uint64_t)f * n;
+            double *dst = S.C.as<double>() + (uint64_t)f * ctx->cfg.capacity;
             if (ctx->cfg.rng_mode == GE_RNG_PHILOX) {
-                normal_scaled_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->rng, P_COMMON, p, 0, f, 0, n, std::sqrt(P.scheme[f].vc), dst);
+                normal_scaled_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->rng, P_COMMON, p, 0, f, n, std::sqrt(P.scheme[f].vc), dst);
                 GE_TRY(ctx->check_launch("common0"));
             } else if (d0 && d0[p].common) CUDA_TRY(cudaMemcpyAsync(dst, d0[p].common + (uint64_t)f * n, n * 8, cudaMemcpyHostToDevice, ctx->stream));
         }
@@ -690,7 +809,9 @@ static int init_pop_gen0(ge_ctx *ctx, int p, const ge_draws *d0) {  // ras_initi
 int ge_init_generation0(ge_ctx *ctx, const ge_draws *d0) {  // ras_init_generation0 :529-679
     CHECK_CTX(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    if (ctx->gen0_done) return fail(GE_ERR_INVALID, "ge_init_generation0 called twice");
     int nf = ctx->cfg.n_phen, np = ctx->cfg.n_pop;
+    const uint64_t cap = ctx->cfg.capacity;
     GE_TRY(build_genome(ctx));
     for (int p = 0; p < np; p++) GE_TRY(build_maps(ctx, ctx->pop[p]));
     if (ctx->bits()) {
@@ -703,19 +824,19 @@ int ge_init_generation0(ge_ctx *ctx, const ge_draws *d0) {  // ras_init_generati
     for (int p = 0; p < np; p++) {
         PopDev &P = ctx->pop[p];
         GE_TRY(init_pop_gen0(ctx, p, d0));
-        GE_TRY(ge_compute_AD(ctx, p, 0));
+        GE_TRY(enqueue_AD(ctx, p));
         GenState &S = P.st[P.cur];
         // ras_fill_Pop_info_prev_gen_for_gen0_prev :3240-3251
-        size_t bytes = (size_t)ctx->cfg.capacity * nf * 8;
+        size_t bytes = (size_t)cap * nf * 8;
         GE_TRY(ctx->ensure(P.prev_P, bytes)); GE_TRY(ctx->ensure(P.prev_F, bytes));
         CUDA_TRY(cudaMemsetAsync(P.prev_P.p, 0, bytes, ctx->stream)); CUDA_TRY(cudaMemsetAsync(P.prev_F.p, 0, bytes, ctx->stream));
         P.prev_n = S.n;
         for (int f = 0; f < nf; f++) {  // :555-566
-            GE_TRY(ctx->h_var(S.A.as<double>() + (uint64_t)f * S.n, S.n, &P.var_a0[f]));
-            GE_TRY(ctx->h_var(S.D.as<double>() + (uint64_t)f * S.n, S.n, &P.var_d0[f]));
+            GE_TRY(ctx->h_var(S.A.as<double>() + (uint64_t)f * cap, S.n, &P.var_a0[f]));
+            GE_TRY(ctx->h_var(S.D.as<double>() + (uint64_t)f * cap, S.n, &P.var_d0[f]));
             bool rp = ctx->cfg.rng_mode == GE_RNG_REPLAY && d0;
-            GE_TRY(scale_AD_compute_GEF_impl(ctx, p, 0, f, (rp && d0[p].e_raw) ? d0[p].e_raw + (uint64_t)f * S.n : nullptr,
-                                             (rp && d0[p].parental0) ? d0[p].parental0 + (uint64_t)f * S.n : nullptr));
+            GE_TRY(enqueue_GEF(ctx, p, f, true, (rp && d0[p].e_raw) ? d0[p].e_raw + (uint64_t)f * S.n : nullptr,
+                               (rp && d0[p].parental0) ? d0[p].parental0 + (uint64_t)f * S.n : nullptr));
         }
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
@@ -727,16 +848,17 @@ int ge_init_generation0(ge_ctx *ctx, const ge_draws *d0) {  // ras_init_generati
         GenState &S = P.st[P.cur];
         for (int f = 0; f < nf; f++) {
             double vP, vF;
-            GE_TRY(ctx->h_var(S.P.as<double>() + (uint64_t)f * S.n, S.n, &vP));
-            GE_TRY(ctx->h_var(S.F.as<double>() + (uint64_t)f * S.n, S.n, &vF));
+            GE_TRY(ctx->h_var(S.P.as<double>() + (uint64_t)f * cap, S.n, &vP));
+            GE_TRY(ctx->h_var(S.F.as<double>() + (uint64_t)f * cap, S.n, &vF));
             if (ctx->cfg.vt_type == 1) P.scheme[f].beta = std::sqrt(P.scheme[f].vf / (2 * vP));
             else if (ctx->cfg.vt_type == 2) { if (vF > 0) P.scheme[f].beta = std::sqrt(P.scheme[f].vf / (2 * vF)); }
         }
         std::vector<std::vector<uint8_t>>().swap(P.panel);  // the host copy of the panel is no longer needed
         P.panel.resize(ctx->cfg.n_chr);
     }
-    GE_TRY(ctx->check_flags("generation 0"));
-    return GE_OK;
+    for (PopDev &P : ctx->pop) for (const Scheme &sc : P.scheme) if (sc.vf > 0) ctx->needs_prev = true;
+    ctx->gen0_done = true;
+    return ctx->pull_state("generation 0");
 }
 
 // ---------------- mating ----------------
@@ -745,13 +867,23 @@ int ge_set_couples(ge_ctx *ctx, int pop, const uint64_t *m, const uint64_t *f, c
     CHECK_POP(ctx, pop);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     PopDev &P = ctx->pop[pop];
+    if (!ctx->gen0_done) return fail(GE_ERR_INVALID, "ge_set_couples before ge_init_generation0");
+    if (n == 0 || !m || !f || !inb || !no) return fail(GE_ERR_INVALID, "ge_set_couples: null array or no couples");
+    const uint64_t n_par = P.st[P.cur].n;
     std::vector<uint32_t> mm(n), ff(n);
-    for (uint64_t k = 0; k < n; k++) { mm[k] = (uint32_t)m[k]; ff[k] = (uint32_t)f[k]; }
-    GE_TRY(ctx->upload(P.c_male, mm)); GE_TRY(ctx->upload(P.c_female, ff));
-    GE_TRY(ctx->upload(P.c_inbreed, std::vector<uint8_t>(inb, inb + n)));
-    GE_TRY(ctx->upload(P.c_noff, std::vector<int32_t>(no, no + n)));
+    for (uint64_t k = 0; k < n; k++) {   // positions index the parent generation: validated before any kernel reads parental rows through them
+        if (m[k] >= n_par || f[k] >= n_par) return fail(GE_ERR_INVALID, "ge_set_couples: couple " + std::to_string(k) + " names a position outside the current generation (" + std::to_string(n_par) + " individuals)");
+        if (no[k] < 0) return fail(GE_ERR_INVALID, "ge_set_couples: negative num_offspring");
+        mm[k] = (uint32_t)m[k]; ff[k] = (uint32_t)f[k];
+    }
+    GE_TRY(ensure_couples(ctx, P, n));
+    CUDA_TRY(cudaMemcpyAsync(P.c_male.p, mm.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(P.c_female.p, ff.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(P.c_inbreed.p, inb, n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(P.c_noff.p, no, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     P.n_couples = n;
-    return GE_OK;
+    P.hs.n_couples = n;
+    return ctx->push_state(P, offsetof(StepState, n_couples), 8);   // (synchronises: the caller's arrays and mm/ff are free again)
 }
 int ge_get_couples_count(ge_ctx *ctx, int pop, uint64_t *n) { CHECK_POP(ctx, pop); *n = ctx->pop[pop].n_couples; return GE_OK; }
 int ge_get_couples(ge_ctx *ctx, int pop, uint64_t *m, uint64_t *f, uint8_t *inb, int32_t *no) {
@@ -771,13 +903,30 @@ int ge_get_couples(ge_ctx *ctx, int pop, uint64_t *m, uint64_t *f, uint8_t *inb,
     return GE_OK;
 }
 
+static StepRow step_row(int gen, const ge_gen_params &gp) {
+    StepRow r;
+    r.gen = gen; r.sel_func = gp.selection_func; r.offspring_dist = gp.offspring_dist; r.pad = 0; r.pop_size = gp.pop_size;
+    r.mat_cor = gp.mat_cor; r.sel_par1 = gp.selection_par1; r.sel_par2 = gp.selection_par2;
+    return r;
+}
+static int enqueue_step_begin(ge_ctx *ctx, int pop, int gen, const ge_gen_params &gp) {
+    PopDev &P = ctx->pop[pop];
+    step_begin_kernel<<<1, 1, 0, ctx->stream>>>(P.d_ss, step_row(gen, gp));
+    return ctx->check_launch("step_begin");
+}
+
 int ge_mate(ge_ctx *ctx, int pop, int gen, const ge_gen_params *gp) {  // random_mate :2090-2157 / assort_mate :2167-2360
     CHECK_POP(ctx, pop);
     if (!gp) return fail(GE_ERR_INVALID, "null params");
     if (ctx->cfg.rng_mode != GE_RNG_PHILOX) return fail(GE_ERR_INVALID, "replay mode: supply couples with ge_set_couples or offspring draws");
+    if (ctx->pop[pop].st[ctx->pop[pop].cur].n == 0) return fail(GE_ERR_INVALID, "empty population");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    ge_ctx::PhaseTimer timer(ctx, GE_PHASE_MATE);
-    return mate_philox(ctx, pop, gen, *gp);
+    GE_TRY(enqueue_step_begin(ctx, pop, gen, *gp));
+    {
+        ge_ctx::PhaseTimer timer(ctx, GE_PHASE_MATE);
+        GE_TRY(enqueue_mate(ctx, pop, *gp));
+    }
+    return ctx->pull_state("ge_mate");
 }
 
 // ---------------- reproduce ----------------
@@ -791,186 +940,204 @@ static int upload_u64_as_u32(ge_ctx *ctx, Buf &b, const uint64_t *src, uint64_t 
     return ctx->upload(b, tmp);
 }
 
-int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {  // reproduce :2394-2493
-    CHECK_POP(ctx, pop);
-    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+// everything wrong with a caller's draws is found BEFORE any state changes (buffers are flipped only afterwards)
+static int validate_draws(ge_ctx *ctx, PopDev &P, const ge_draws *dr, uint64_t n_par) {
+    const int C = ctx->cfg.n_chr;
+    const uint64_t n_off = dr->n_offspring;
+    if (n_off == 0) return fail(GE_ERR_NO_MATES, "no offspring");
+    if (n_off > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "offspring exceed capacity");
+    if (!dr->father || !dr->mother || !dr->sex || !dr->xo_off || !dr->start_hap) return fail(GE_ERR_INVALID, "incomplete draws");
+    for (uint64_t i = 0; i < n_off; i++) if (dr->father[i] >= n_par || dr->mother[i] >= n_par) return fail(GE_ERR_INVALID, "parent index out of range");
+    const uint64_t ns = n_off * C * 2;
+    if (dr->xo_off[0] != 0) return fail(GE_ERR_INVALID, "xo_off[0] must be 0");
+    for (uint64_t k = 0; k < ns; k++) if (dr->xo_off[k + 1] < dr->xo_off[k]) return fail(GE_ERR_INVALID, "xo_off must be non-decreasing");
+    if (dr->xo_off[ns] && !dr->xo_bp) return fail(GE_ERR_INVALID, "incomplete draws: xo_bp");
+    // the bit-packed rows (and packed 8-byte parts) need every slot's crossover positions in ascending order; the reference's own
+    // lists are (:2983-2993) whenever the map's rows are at least bp_dist_in_rmap apart
+    if (ctx->bits())
+        for (uint64_t k = 0; k < ns; k++)
+            for (uint64_t e = dr->xo_off[k] + 1; e < dr->xo_off[k + 1]; e++)
+                if (dr->xo_bp[e] < dr->xo_bp[e - 1]) return fail(GE_ERR_INVALID, "crossover positions of a gamete must ascend (GE_REP_BITS)");
+    if (dr->mut_off) {
+        if (!P.has_mut) return fail(GE_ERR_INVALID, "draws carry mutation hits but the population has no mutation map (ge_set_mutation_map)");
+        const uint64_t ni = n_off * C;
+        if (dr->mut_off[0] != 0) return fail(GE_ERR_INVALID, "mut_off[0] must be 0");
+        for (uint64_t k = 0; k < ni; k++) if (dr->mut_off[k + 1] < dr->mut_off[k]) return fail(GE_ERR_INVALID, "mut_off must be non-decreasing");
+        if (dr->mut_off[ni] && (!dr->mut_bp || !dr->mut_gam)) return fail(GE_ERR_INVALID, "incomplete draws: mut_bp / mut_gam");
+        for (uint64_t e = 0; e < dr->mut_off[ni]; e++) if (dr->mut_bp[e] > 0x7FFFFFFFull) return fail(GE_ERR_UNSUPPORTED, "mutation position does not fit 31 bits");
+    }
+    return GE_OK;
+}
+
+static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // reproduce :2394-2493
     PopDev &P = ctx->pop[pop];
-    int C = ctx->cfg.n_chr, nf = ctx->cfg.n_phen;
+    const int C = ctx->cfg.n_chr, nf = ctx->cfg.n_phen;
+    const uint64_t cap = ctx->cfg.capacity, slots = cap * C * 2;
     GenState &par = P.st[P.cur], &off = P.st[P.cur ^ 1];
-    if (par.n == 0) return fail(GE_ERR_INVALID, "ge_reproduce before ge_init_generation0");
-    uint64_t n_off = 0;
     std::vector<uint32_t> tmp;
     cudaStream_t st = ctx->stream;
-    if (dr) {  // validate the caller's draws before any state changes
-        n_off = dr->n_offspring;
-        if (n_off == 0) return fail(GE_ERR_NO_MATES, "no offspring");
-        if (n_off > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "offspring exceed capacity");
-        if (!dr->father || !dr->mother || !dr->sex || !dr->xo_off || !dr->start_hap) return fail(GE_ERR_INVALID, "incomplete draws");
-        for (uint64_t i = 0; i < n_off; i++) if (dr->father[i] >= par.n || dr->mother[i] >= par.n) return fail(GE_ERR_INVALID, "parent index out of range");
-        const uint64_t ns = n_off * C * 2;
-        for (uint64_t k = 0; k < ns; k++) if (dr->xo_off[k + 1] < dr->xo_off[k]) return fail(GE_ERR_INVALID, "xo_off must be non-decreasing");
-        if (dr->xo_off[ns] && !dr->xo_bp) return fail(GE_ERR_INVALID, "incomplete draws: xo_bp");
-    } else {
-        if (ctx->cfg.rng_mode != GE_RNG_PHILOX) return fail(GE_ERR_INVALID, "replay mode needs draws");
-        if (P.n_couples == 0) return fail(GE_ERR_INVALID, "no couples: call ge_mate or ge_set_couples first");
-    }
+    StepState *ss = P.d_ss;
     // the other draw set; the bulk stream may still read it for the generation before last
     P.dcur ^= 1;
     DrawSet &D = P.draws();
     if (D.bulk_pending) { CUDA_TRY(cudaStreamWaitEvent(st, D.bulk_done, 0)); D.bulk_pending = false; }
     if (dr) {
+        const uint64_t n_off = dr->n_offspring, n_slots = n_off * C * 2;
         GE_TRY(upload_u64_as_u32(ctx, D.father, dr->father, n_off, tmp, "father"));
         GE_TRY(upload_u64_as_u32(ctx, D.mother, dr->mother, n_off, tmp, "mother"));
-        uint64_t n_slots = n_off * C * 2;
         P.n_xo = dr->xo_off[n_slots];
+        if (P.n_xo > P.hs.xo_cap) {   // replayed lists may be longer than anything the map would draw
+            P.hs.xo_cap = P.n_xo + P.n_xo / 4;
+            for (DrawSet &Q : P.ds) { GE_TRY(ctx->ensure(Q.xo_bp, P.hs.xo_cap * 4)); if (ctx->bits()) GE_TRY(ctx->ensure(Q.flips, P.hs.xo_cap * 4)); }
+        }
         GE_TRY(ctx->upload(D.xo_off, std::vector<uint64_t>(dr->xo_off, dr->xo_off + n_slots + 1)));
         GE_TRY(upload_u64_as_u32(ctx, D.xo_bp, dr->xo_bp, P.n_xo, tmp, "crossover position"));
         GE_TRY(ctx->upload(D.start_hap, std::vector<uint8_t>(dr->start_hap, dr->start_hap + n_slots)));
         CUDA_TRY(cudaMemcpyAsync(off.sex.p, dr->sex, n_off, cudaMemcpyHostToDevice, st));
         if (dr->mut_off) {
             P.n_mut = dr->mut_off[n_off * C];
+            if (P.n_mut > P.hs.mut_cap) { P.hs.mut_cap = P.n_mut + P.n_mut / 4; GE_TRY(ctx->ensure(P.mut_bp, P.hs.mut_cap * 4)); GE_TRY(ctx->ensure(P.mut_gam, P.hs.mut_cap)); }
             GE_TRY(ctx->upload(P.mut_off, std::vector<uint64_t>(dr->mut_off, dr->mut_off + n_off * C + 1)));
             GE_TRY(upload_u64_as_u32(ctx, P.mut_bp, dr->mut_bp, P.n_mut, tmp, "mutation position"));
             GE_TRY(ctx->upload(P.mut_gam, std::vector<uint8_t>(dr->mut_gam, dr->mut_gam + P.n_mut)));
         } else P.n_mut = 0;
-        CUDA_TRY(cudaMemsetAsync(off.C.p, 0, (size_t)n_off * nf * 8, st));
-        if (dr->common) CUDA_TRY(cudaMemcpyAsync(off.C.p, dr->common, (size_t)n_off * nf * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(off.C.p, 0, (size_t)cap * nf * 8, st));
+        if (dr->common)
+            for (int f = 0; f < nf; f++) CUDA_TRY(cudaMemcpyAsync(off.C.as<double>() + (uint64_t)f * cap, dr->common + (uint64_t)f * n_off, n_off * 8, cudaMemcpyHostToDevice, st));
         P.have_couple_of = false;
+        // the host decided every size of this step
+        P.hs.n_off = n_off; P.hs.n_xo = P.n_xo; P.hs.n_mut = P.n_mut; P.hs.n_iv = P.n_xo + n_slots; P.hs.n[P.cur ^ 1] = n_off;
+        P.hs.dc[P.dcur] = DrawCounts{n_off, P.n_xo, P.n_xo + n_slots, 0u, 0u};
+        GE_TRY(ctx->push_state(P));
+        pedigree_kernel<<<nblk(n_off, 256), 256, 0, st>>>(n_off, D.father.as<uint32_t>(), D.mother.as<uint32_t>(), par.ids.as<uint64_t>(), off.ids.as<uint64_t>());
+        GE_TRY(ctx->check_launch("pedigree"));
     } else {
         ge_ctx::PhaseTimer timer(ctx, GE_PHASE_SAMPLE);
-        // offspring offsets = exclusive scan of the family sizes of the couples that may marry (:2402-2406)
-        GE_TRY(ctx->ensure(P.cnt32, (size_t)std::max<uint64_t>(P.n_couples, ctx->cfg.capacity * C * 2 + 1) * 4));
-        GE_TRY(ctx->ensure(P.mate.fam_off, (P.n_couples + 1) * 8));
-        family_size_kernel<<<nblk(P.n_couples, 256), 256, 0, st>>>(P.n_couples, P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>(), P.cnt32.as<uint32_t>());
+        // offspring offsets = exclusive scan of the family sizes of the couples that may marry (:2402-2406); the couple threads then
+        // write parents, sex, pedigree and the sibling-common effect of their children
+        const uint64_t cb = P.couples_cap;
+        family_size_kernel<<<ctx->grid_for(cb, 256), 256, 0, st>>>(ss, P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>(), P.cnt32.as<uint32_t>());
         GE_TRY(ctx->check_launch("family_size"));
-        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), P.n_couples, P.mate.fam_off.as<uint64_t>(), &n_off));
-        if (n_off == 0) return fail(GE_ERR_NO_MATES, "no offspring");
-        if (n_off > ctx->cfg.capacity) return fail(GE_ERR_CAPACITY, "offspring (" + std::to_string(n_off) + ") exceed capacity");
-        GE_TRY(ctx->ensure(D.father, n_off * 4)); GE_TRY(ctx->ensure(D.mother, n_off * 4)); GE_TRY(ctx->ensure(D.couple_of, n_off * 4));
-        expand_couples_kernel<<<nblk(P.n_couples, 256), 256, 0, st>>>(P.n_couples, P.mate.fam_off.as<uint64_t>(), P.c_male.as<uint32_t>(), P.c_female.as<uint32_t>(),
-                                                                      D.father.as<uint32_t>(), D.mother.as<uint32_t>(), D.couple_of.as<uint32_t>());
-        GE_TRY(ctx->check_launch("expand_couples"));
+        GE_TRY(ctx->scan(st, P.cnt32.as<uint32_t>(), devn(&ss->n_couples), cb, P.mate.fam_off.as<uint64_t>(), OffspringTotal{ss}));
+        CommonArgs ca;
+        ca.n_phen = nf; ca.stride = cap;
+        for (int f = 0; f < 8; f++) ca.sd[f] = (f < nf && P.scheme[f].vc > 0) ? std::sqrt(P.scheme[f].vc) : 0.0;
+        offspring_kernel<<<ctx->grid_for(cb, 128), 128, 0, st>>>(ctx->rng, ss, pop, P.mate.fam_off.as<uint64_t>(), P.c_male.as<uint32_t>(), P.c_female.as<uint32_t>(), par.ids.as<uint64_t>(), ca,
+                                                                 D.father.as<uint32_t>(), D.mother.as<uint32_t>(), D.couple_of.as<uint32_t>(), off.sex.as<uint8_t>(), off.ids.as<uint64_t>(),
+                                                                 off.C.as<double>(), off.d_n);
+        GE_TRY(ctx->check_launch("offspring"));
         P.have_couple_of = true;
-        // crossovers: count, scan, fill
-        uint64_t n_slots = n_off * C * 2;
-        GE_TRY(ctx->ensure(D.xo_off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(D.start_hap, n_slots));
-        GE_TRY(ctx->ensure(ctx->xo_stash, n_slots * XO_STASH * 4));
-        sample_xo_kernel<false><<<ctx->ctrl_grid(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), C, pop, gen, 0, n_slots, P.cnt32.as<uint32_t>(), nullptr, nullptr, D.start_hap.as<uint8_t>(),
-                                                                    ctx->xo_stash.as<uint32_t>());
-        GE_TRY(ctx->check_launch("sample_xo<count>"));
-        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, D.xo_off.as<uint64_t>(), &P.n_xo));
-        GE_TRY(ctx->ensure(D.xo_bp, std::max<uint64_t>(P.n_xo, 1) * 4));
-        if (ctx->bits()) GE_TRY(ctx->ensure(D.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
-        xo_place_kernel<<<ctx->ctrl_grid(n_slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ctx->genome(), C, pop, gen, n_slots, D.xo_off.as<uint64_t>(), ctx->xo_stash.as<uint32_t>(),
-                                                            D.xo_bp.as<uint32_t>(), ctx->bits() ? D.flips.as<uint32_t>() : nullptr);
+        // crossovers: count + stash, scan, place
+        sample_xo_kernel<<<ctx->ctrl_grid(slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ss, C, pop, P.cnt32.as<uint32_t>(), D.start_hap.as<uint8_t>(), ctx->xo_stash.as<uint32_t>());
+        GE_TRY(ctx->check_launch("sample_xo"));
+        GE_TRY(ctx->scan(st, P.cnt32.as<uint32_t>(), devn(&ss->n_off, (uint64_t)C * 2), slots, D.xo_off.as<uint64_t>(), XoTotal{ss, (uint64_t)C * 2, P.dcur}));
+        xo_place_kernel<<<ctx->ctrl_grid(slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ctx->genome(), ss, C, pop, D.xo_off.as<uint64_t>(), ctx->xo_stash.as<uint32_t>(),
+                                                                    D.xo_bp.as<uint32_t>(), ctx->bits() ? D.flips.as<uint32_t>() : nullptr);
         GE_TRY(ctx->check_launch("xo_place"));
         if (P.has_mut) {
-            uint64_t n_items = n_off * C;
-            GE_TRY(ctx->ensure(P.mut_off, (n_items + 1) * 8));
-            sample_mut_kernel<false><<<nblk(n_items, 128), 128, 0, st>>>(ctx->rng, ctx->mmap(P), C, pop, gen, 0, n_items, P.cnt32.as<uint32_t>(), nullptr, nullptr, nullptr);
+            const uint64_t items = cap * C;
+            sample_mut_kernel<false><<<ctx->grid_for(items, 128), 128, 0, st>>>(ctx->rng, ctx->mmap(P), ss, C, pop, P.cnt32.as<uint32_t>(), nullptr, nullptr, nullptr);
             GE_TRY(ctx->check_launch("sample_mut<count>"));
-            GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_items, P.mut_off.as<uint64_t>(), &P.n_mut));
-            GE_TRY(ctx->ensure(P.mut_bp, std::max<uint64_t>(P.n_mut, 1) * 4)); GE_TRY(ctx->ensure(P.mut_gam, std::max<uint64_t>(P.n_mut, 1)));
-            sample_mut_kernel<true><<<nblk(n_items, 128), 128, 0, st>>>(ctx->rng, ctx->mmap(P), C, pop, gen, 0, n_items, nullptr, P.mut_off.as<uint64_t>(), P.mut_bp.as<uint32_t>(), P.mut_gam.as<uint8_t>());
+            GE_TRY(ctx->scan(st, P.cnt32.as<uint32_t>(), devn(&ss->n_off, (uint64_t)C), items, P.mut_off.as<uint64_t>(), StoreTotal{&ss->n_mut, &ss->err, &ss->mut_cap, SE_CAP_MUT}));
+            sample_mut_kernel<true><<<ctx->grid_for(items, 128), 128, 0, st>>>(ctx->rng, ctx->mmap(P), ss, C, pop, nullptr, P.mut_off.as<uint64_t>(), P.mut_bp.as<uint32_t>(), P.mut_gam.as<uint8_t>());
             GE_TRY(ctx->check_launch("sample_mut<fill>"));
-        } else P.n_mut = 0;
-        sex_kernel<<<nblk(n_off, 256), 256, 0, st>>>(ctx->rng, pop, gen, 0, n_off, off.sex.as<uint8_t>());
-        GE_TRY(ctx->check_launch("sex"));
-        CUDA_TRY(cudaMemsetAsync(off.C.p, 0, (size_t)n_off * nf * 8, st));
-        for (int f = 0; f < nf; f++)
-            if (P.scheme[f].vc > 0) {
-                common_from_couples_kernel<<<nblk(n_off, 256), 256, 0, st>>>(ctx->rng, pop, gen, f, std::sqrt(P.scheme[f].vc), 0, n_off, D.couple_of.as<uint32_t>(),
-                                                                            off.C.as<double>() + (uint64_t)f * n_off);
-                GE_TRY(ctx->check_launch("common"));
-            }
+        }
     }
-    P.n_off = n_off;
-    uint64_t n_slots = n_off * C * 2;
     // ---- bit-packed propagation: the HBM-bound bulk of the generation, on the bulk stream.  Nothing later on the
     // control stream needs the rows (genetic values come from the causal-variant planes), so mating, sampling
     // and phenotypes of the NEXT generation overlap with this copy.
     bool bulk_launched = false;
     if (ctx->bits()) {
         if (dr) {  // replayed crossovers: positions -> locus indices (the Philox path did it in xo_place_kernel)
-            GE_TRY(ctx->ensure(D.flips, std::max<uint64_t>(P.n_xo, 1) * 4));
+            const uint64_t n_slots = dr->n_offspring * C * 2;
             xo_to_flips_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->genome(), n_slots, D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.flips.as<uint32_t>());
             GE_TRY(ctx->check_launch("xo_to_flips"));
         }
         cudaStream_t bulk = ctx->serial ? st : ctx->bulk;
         CUDA_TRY(cudaEventRecord(ctx->ev_ready, st));
         CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_ready, 0));
-        ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0};
+        ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0, 0, 0};
         if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, bulk)); }
-        unsigned grid = (unsigned)std::min<uint64_t>(n_off, 1u << 20);  // one short-lived CTA per offspring: control-stream kernels get SM slots quickly
-        if (ctx->use_tma) {
-            size_t sm = prop_tma_smem_bytes(C);
-            if (!ctx->tma_attr_set) { CUDA_TRY(cudaFuncSetAttribute(propagate_bits_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); ctx->tma_attr_set = true; }
-            propagate_bits_tma_kernel<<<grid, TMA_WARPS * 32 + TMA_MERGE_THREADS, sm, bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), par.rowmap, off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
-                                                                         D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
-        } else if (ctx->prop_depth == 8)
-        propagate_bits_kernel<8><<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), par.rowmap, off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
-                                                                    D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
-        else
-        propagate_bits_kernel<4><<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), par.hap.as<uint32_t>(), par.rowmap, off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
-                                                                    D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, (uint32_t)n_off);
+        // one short-lived CTA per offspring (control-stream kernels get SM slots quickly); CTAs beyond the device-side count exit at once
+        unsigned grid = (unsigned)std::min<uint64_t>(dr ? dr->n_offspring : cap, 1u << 20);
+        propagate_bits_kernel<<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), &ss->dc[P.dcur], par.hap.as<uint32_t>(), par.rowmap, off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
+                                                                                D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>());
         GE_TRY(ctx->check_launch("propagate_bits"));
         if (ctx->profiling) {
             CUDA_TRY(cudaEventRecord(evp.b, bulk));
-            uint64_t M = 0;
-            for (uint32_t v : ctx->chr_nloci) M += v;
-            evp.bytes = n_off * M / 2;  // 0.5 byte per individual-locus
+            evp.bytes_per_offspring = ctx->n_loci_total / 2;  // 0.5 byte per individual-locus; the offspring count is taken from the step's read-back
+            evp.pop = pop;
             ctx->ev_pending.push_back(evp);
         }
         CUDA_TRY(cudaEventRecord(D.bulk_done, bulk));
         D.bulk_pending = true;
         // thin control kernels only pay off while the bulk copy is longer than the control chain (~0.75 ms at 100k individuals)
-        ctx->note_bulk((double)n_off * ctx->W * 16.0);
+        ctx->note_bulk((double)cap * ctx->W * 16.0);
         bulk_launched = true;
     }
     // ---- causal-variant planes
     if (ctx->n_cv_tot) {  // in every representation: crossover parity at the CV positions, never a rescan of the segment lists
-        uint64_t tot = n_off * 2 * ctx->Wcv;
-        cv_propagate_bits_kernel<<<ctx->ctrl_grid(tot, 256), 256, 0, st>>>(ctx->cvset(), par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
-                                                                 D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, n_off);
+        uint64_t tot = cap * 2 * ctx->Wcv;
+        cv_propagate_bits_kernel<<<ctx->ctrl_grid(tot, 256), 256, 0, st>>>(ctx->cvset(), ss, par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
+                                                                 D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>());
         GE_TRY(ctx->check_launch("cv_propagate_bits"));
         if (ctx->use_root) {
-            uint64_t tr = n_off * 2 * ctx->n_cv_tot;
-            cv_root_propagate_kernel<<<nblk(tr, 256), 256, 0, st>>>(ctx->cvset(), par.cv_root.as<uint8_t>(), off.cv_root.as<uint8_t>(), D.father.as<uint32_t>(), D.mother.as<uint32_t>(),
-                                                                    D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>(), 0, n_off);
+            uint64_t tr = cap * 2 * ctx->n_cv_tot;
+            cv_root_propagate_kernel<<<ctx->grid_for(tr, 256), 256, 0, st>>>(ctx->cvset(), ss, par.cv_root.as<uint8_t>(), off.cv_root.as<uint8_t>(), D.father.as<uint32_t>(), D.mother.as<uint32_t>(),
+                                                                    D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>());
             GE_TRY(ctx->check_launch("cv_root_propagate"));
         }
     }
     // ---- founder segments
-    if (ctx->segs()) GE_TRY(seg_recombine(ctx, pop, n_off));
+    if (ctx->segs()) GE_TRY(seg_recombine(ctx, pop, dr ? dr->n_offspring : 0));
     // ---- mutation lists (inherit + this generation's hits)
     if (P.has_mut || par.has_hm) {
         MutArgs a;
-        a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = D.father.as<uint32_t>(); a.mother = D.mother.as<uint32_t>();
+        a.n_chr = C; a.ss = ss; a.father = D.father.as<uint32_t>(); a.mother = D.mother.as<uint32_t>();
         a.xo_off = D.xo_off.as<uint64_t>(); a.xo_bp = D.xo_bp.as<uint32_t>(); a.start_hap = D.start_hap.as<uint8_t>();
         a.par_hm_off = par.has_hm ? par.hm_off.as<uint64_t>() : nullptr; a.par_hm_bp = par.hm_bp.as<uint32_t>();
         bool hits = P.has_mut && (dr ? dr->mut_off != nullptr : true);
         a.mut_off = hits ? P.mut_off.as<uint64_t>() : nullptr; a.mut_bp = P.mut_bp.as<uint32_t>(); a.mut_gam = P.mut_gam.as<uint8_t>();
         a.cov_lo = P.d_cov_lo.as<uint32_t>(); a.cov_hi = P.d_cov_hi.as<uint32_t>();
-        GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
-        GE_TRY(ctx->ensure(off.hm_off, (n_slots + 1) * 8));
-        mutation_lists_kernel<false><<<nblk(n_slots, 128), 128, 0, st>>>(a, ctx->genome(), ctx->cvset(), P.cnt32.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr);
+        // room for the offspring lists: what the parents carry can at most double on the way down (both parental haplotypes inherited
+        // by every child of a growing population), plus this generation's hits.  par.n_hm is exact: it came with the last read-back.
+        const double growth = std::max(1.0, (double)cap / (double)std::max<uint64_t>(par.n, 1));
+        const uint64_t need = (uint64_t)(2.5 * growth * (double)par.n_hm) + P.hs.mut_cap + 1024;
+        GE_TRY(ctx->ensure(off.hm_off, (slots + 1) * 8));
+        if (need * 4 > off.hm_bp.cap) GE_TRY(ctx->ensure(off.hm_bp, need * 4 + need));
+        if (P.hs.hm_cap != off.hm_bp.cap / 4) { P.hs.hm_cap = off.hm_bp.cap / 4; GE_TRY(ctx->push_state(P, offsetof(StepState, hm_cap), 8)); }
+        const unsigned g = ctx->grid_for(slots, 128);
+        mutation_lists_kernel<false><<<g, 128, 0, st>>>(a, ctx->genome(), ctx->cvset(), P.cnt32.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr);
         GE_TRY(ctx->check_launch("mutation_lists<count>"));
-        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, off.hm_off.as<uint64_t>(), &off.n_hm));
-        GE_TRY(ctx->ensure(off.hm_bp, std::max<uint64_t>(off.n_hm, 1) * 4));
+        GE_TRY(ctx->scan(st, P.cnt32.as<uint32_t>(), devn(&ss->n_off, (uint64_t)C * 2), slots, off.hm_off.as<uint64_t>(), StoreTotal{off.d_n_hm, &ss->err, &ss->hm_cap, SE_CAP_HM}));
         if (bulk_launched) GE_TRY(ctx->join_bulk());  // the fill pass toggles bits of the freshly propagated rows
-        mutation_lists_kernel<true><<<nblk(n_slots, 128), 128, 0, st>>>(a, ctx->genome(), ctx->cvset(), nullptr, off.hm_off.as<uint64_t>(), off.hm_bp.as<uint32_t>(),
-                                                                        ctx->bits() ? off.hap.as<uint32_t>() : nullptr, ctx->n_cv_tot ? off.cv_allele.as<uint32_t>() : nullptr);
+        mutation_lists_kernel<true><<<g, 128, 0, st>>>(a, ctx->genome(), ctx->cvset(), nullptr, off.hm_off.as<uint64_t>(), off.hm_bp.as<uint32_t>(),
+                                                       ctx->bits() ? off.hap.as<uint32_t>() : nullptr, ctx->n_cv_tot ? off.cv_allele.as<uint32_t>() : nullptr);
         GE_TRY(ctx->check_launch("mutation_lists<fill>"));
         off.has_hm = true;
     } else off.has_hm = false;
-    // ---- pedigree
-    pedigree_kernel<<<nblk(n_off, 256), 256, 0, st>>>(0, n_off, D.father.as<uint32_t>(), D.mother.as<uint32_t>(), par.ids.as<uint64_t>(), off.ids.as<uint64_t>());
-    GE_TRY(ctx->check_launch("pedigree"));
-    off.n = n_off;
     off.rowmap = nullptr;   // a fresh generation is written in identity order
     P.cur ^= 1;
-    if (dr) CUDA_TRY(cudaStreamSynchronize(st));  // caller buffers were read asynchronously
     return GE_OK;
+}
+// a failed step leaves the population where it was: the parents' buffers are untouched (offspring go to the other set)
+static void rollback_reproduce(ge_ctx *ctx, int pop) { PopDev &P = ctx->pop[pop]; P.cur ^= 1; P.dcur ^= 1; P.st[P.cur ^ 1].seg.valid = false; }
+
+int ge_reproduce(ge_ctx *ctx, int pop, int gen, const ge_draws *dr) {
+    CHECK_POP(ctx, pop);
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    PopDev &P = ctx->pop[pop];
+    if (!ctx->gen0_done || P.st[P.cur].n == 0) return fail(GE_ERR_INVALID, "ge_reproduce before ge_init_generation0");
+    if (dr) GE_TRY(validate_draws(ctx, P, dr, P.st[P.cur].n));
+    else {
+        if (ctx->cfg.rng_mode != GE_RNG_PHILOX) return fail(GE_ERR_INVALID, "replay mode needs draws");
+        if (P.n_couples == 0) return fail(GE_ERR_INVALID, "no couples: call ge_mate or ge_set_couples first");
+    }
+    if (P.hs.gen != gen) { P.hs.gen = gen; GE_TRY(ctx->push_state(P, offsetof(StepState, gen), 4)); }
+    GE_TRY(enqueue_reproduce(ctx, pop, dr));
+    int rc = ctx->pull_state("ge_reproduce");   // (also: caller buffers were read asynchronously)
+    if (rc != GE_OK) rollback_reproduce(ctx, pop);
+    return rc;
 }
 
 int ge_set_migration_sample(ge_ctx *ctx, int src, const uint64_t *pos, uint64_t n) {
@@ -982,6 +1149,7 @@ int ge_set_migration_sample(ge_ctx *ctx, int src, const uint64_t *pos, uint64_t 
 int ge_do_migration(ge_ctx *ctx, int gen, const double *row) {  // ras_do_migration :877-989
     CHECK_CTX(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(ctx->pull_state("ge_do_migration"));   // the gather lists are built on the host from the population sizes
     GE_TRY(seg_finish_all(ctx));
     return migrate(ctx, gen, row);
 }
@@ -989,25 +1157,40 @@ int ge_do_migration(ge_ctx *ctx, int gen, const double *row) {  // ras_do_migrat
 int ge_step_generation(ge_ctx *ctx, int gen, const ge_gen_params *gp, const double *mig, const ge_draws *dr) {  // sim_next_generation :1890-2082
     CHECK_CTX(ctx);
     if (!gp) return fail(GE_ERR_INVALID, "null params");
+    if (!ctx->gen0_done) return fail(GE_ERR_INVALID, "ge_step_generation before ge_init_generation0");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     int nf = ctx->cfg.n_phen, np = ctx->cfg.n_pop;
-    for (int p = 0; p < np; p++) {
-        if (!dr) GE_TRY(ge_mate(ctx, p, gen, &gp[p]));
-        GE_TRY(ge_reproduce(ctx, p, gen, dr ? &dr[p] : nullptr));
-        GE_TRY(ge_compute_AD(ctx, p, gen));
-        uint64_t n = ctx->pop[p].st[ctx->pop[p].cur].n;
-        {
-            ge_ctx::PhaseTimer timer(ctx, GE_PHASE_PHENOTYPE);
-            for (int f = 0; f < nf; f++)
-                GE_TRY(scale_AD_compute_GEF_impl(ctx, p, gen, f, (dr && dr[p].e_raw) ? dr[p].e_raw + (uint64_t)f * n : nullptr, nullptr));
+    if (dr) for (int p = 0; p < np; p++) GE_TRY(validate_draws(ctx, ctx->pop[p], &dr[p], ctx->pop[p].st[ctx->pop[p].cur].n));
+    else if (ctx->cfg.rng_mode != GE_RNG_PHILOX) return fail(GE_ERR_INVALID, "replay mode needs draws");
+    int reproduced = 0;
+    bool migrated = false;
+    auto body = [&]() -> int {
+        for (int p = 0; p < np; p++) {
+            GE_TRY(enqueue_step_begin(ctx, p, gen, gp[p]));
+            if (!dr) { ge_ctx::PhaseTimer timer(ctx, GE_PHASE_MATE); GE_TRY(enqueue_mate(ctx, p, gp[p])); }
+            GE_TRY(enqueue_reproduce(ctx, p, dr ? &dr[p] : nullptr));
+            reproduced = p + 1;
+            GE_TRY(enqueue_AD(ctx, p));
+            {
+                ge_ctx::PhaseTimer timer(ctx, GE_PHASE_PHENOTYPE);
+                const uint64_t n = dr ? dr[p].n_offspring : 0;
+                for (int f = 0; f < nf; f++) GE_TRY(enqueue_GEF(ctx, p, f, false, (dr && dr[p].e_raw) ? dr[p].e_raw + (uint64_t)f * n : nullptr, nullptr));
+            }
         }
-    }
-    for (int f = 0; f < nf; f++) GE_TRY(ge_environmental_effects_specific_to_each_population(ctx, f));
-    for (int p = 0; p < np; p++) GE_TRY(ge_compute_mating_value_selection_value(ctx, p, gen, &gp[p]));
-    if (np > 1 && mig) GE_TRY(ge_do_migration(ctx, gen, mig));
-    for (int p = 0; p < np; p++) GE_TRY(ge_save_human_info_to_Pop_info_prev_gen(ctx, p));
-    GE_TRY(ctx->check_flags("generation"));  // also the one host sync of the generation
-    return GE_OK;
+        for (int f = 0; f < nf; f++) GE_TRY(ge_environmental_effects_specific_to_each_population(ctx, f));
+        for (int p = 0; p < np; p++) GE_TRY(enqueue_mv_sv(ctx, p));
+        if (np > 1 && mig) {
+            GE_TRY(ctx->pull_state("generation"));   // migration builds its gather lists on the host
+            GE_TRY(seg_finish_all(ctx));
+            GE_TRY(migrate(ctx, gen, mig));
+            migrated = true;
+        }
+        for (int p = 0; p < np; p++) if (ctx->needs_prev) GE_TRY(enqueue_save_prev(ctx, p));
+        return ctx->pull_state("generation");   // THE host synchronisation of the generation: sizes for the host's bookkeeping, errors
+    };
+    int rc = body();
+    if (rc != GE_OK && !migrated) for (int p = 0; p < reproduced; p++) rollback_reproduce(ctx, p);
+    return rc;
 }
 
 // ---------------- results ----------------
@@ -1020,11 +1203,16 @@ int ge_download_individuals(ge_ctx *ctx, int pop, ge_indiv_soa *o) {
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     uint64_t n = S.n; int nf = ctx->cfg.n_phen;
+    const uint64_t cap = ctx->cfg.capacity;
     cudaStream_t st = ctx->stream;
     auto cp = [&](void *dst, const Buf &src, size_t bytes) -> cudaError_t { return dst ? cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
+    // per-phenotype columns: [n_phen][n] for the caller, rows `capacity` apart on the device
+    auto cols = [&](double *dst, const Buf &src) -> cudaError_t {
+        return (dst && n) ? cudaMemcpy2DAsync(dst, n * 8, src.p, cap * 8, n * 8, (size_t)nf, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    };
     CUDA_TRY(cp(o->ids, S.ids, n * 56)); CUDA_TRY(cp(o->sex, S.sex, n));
-    CUDA_TRY(cp(o->A, S.A, n * nf * 8)); CUDA_TRY(cp(o->D, S.D, n * nf * 8)); CUDA_TRY(cp(o->G, S.G, n * nf * 8)); CUDA_TRY(cp(o->C, S.C, n * nf * 8));
-    CUDA_TRY(cp(o->E, S.E, n * nf * 8)); CUDA_TRY(cp(o->F, S.F, n * nf * 8)); CUDA_TRY(cp(o->P, S.P, n * nf * 8));
+    CUDA_TRY(cols(o->A, S.A)); CUDA_TRY(cols(o->D, S.D)); CUDA_TRY(cols(o->G, S.G)); CUDA_TRY(cols(o->C, S.C));
+    CUDA_TRY(cols(o->E, S.E)); CUDA_TRY(cols(o->F, S.F)); CUDA_TRY(cols(o->P, S.P));
     CUDA_TRY(cp(o->mv, S.mv, n * 8)); CUDA_TRY(cp(o->sv, S.sv, n * 8)); CUDA_TRY(cp(o->svf, S.svf, n * 8));
     CUDA_TRY(cudaStreamSynchronize(st));
     return GE_OK;
@@ -1034,7 +1222,7 @@ int ge_get_moments(ge_ctx *ctx, int pop, int f, ge_moments *m) {
     CHECK_POP(ctx, pop); CHECK_PHEN(ctx, f);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     GenState &S = ctx->pop[pop].st[ctx->pop[pop].cur];
-    uint64_t o = (uint64_t)f * S.n;
+    uint64_t o = (uint64_t)f * ctx->cfg.capacity;
     GE_TRY(ctx->h_var(S.A.as<double>() + o, S.n, &m->var_A)); GE_TRY(ctx->h_var(S.D.as<double>() + o, S.n, &m->var_D));
     GE_TRY(ctx->h_var(S.G.as<double>() + o, S.n, &m->var_G)); GE_TRY(ctx->h_var(S.C.as<double>() + o, S.n, &m->var_C));
     GE_TRY(ctx->h_var(S.E.as<double>() + o, S.n, &m->var_E)); GE_TRY(ctx->h_var(S.F.as<double>() + o, S.n, &m->var_F));

@@ -35,25 +35,20 @@ struct Buf {
 
 struct SegState {   // founder segments of one generation (GE_REP_SEGMENTS): CSR over slots (i*n_chr + c)*2 + h
     Buf off, seg;   // off: uint64 [n_slots+1]; seg: uint4 {st, en, hap_index, root_population}
-    uint64_t n_seg = 0;
+    uint64_t n_seg = 0;             // host mirror of StepState::n_seg[k] (exact after seg_finish_all)
     bool valid = false;
-    // asynchronous form (bulk stream, seg_capacity given): n_seg arrives in pinned host memory behind `ready`
-    bool pending = false;
-    cudaEvent_t ready = nullptr;
-    uint64_t *h_total = nullptr;              // pinned
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // profiling events of the two passes, accounted when n_seg is known
 };
 // The four sorts of assortative mating (males and females by mating value, the two template columns) are independent
 // and, at <= N/2 keys each, pure launch latency (8 radix passes of ~10 us): they run side by side on four lanes.
 struct SortLane {
     cudaStream_t s = nullptr;
     cudaEvent_t done = nullptr;
-    Buf keys_in, keys_out, vals_out, tmp;
+    Buf keys_in, vals_in, keys_out, vals_out, tmp;
 };
 constexpr int N_SORT_LANES = 4;
 
 struct MateScratch {  // scratch of the mating kernels (ge_mating.cuh)
-    Buf fam_off, keep, keys_a, keys_b, idx_a, idx_b, list_m, list_f, t1, t2, rank1, rank2, tmp_sort, counters, mv_m, mv_f;
+    Buf fam_off, keep, keep_off, keys_a, keys_b, idx_a, idx_b, list_m, list_f, t1, t2, rank1, rank2, tmp_sort;
 };
 
 struct Scheme { double va = 0, vd = 0, ve = 0, vc = 0, vf = 0, omega = 0, beta = 0, lambda = 0; };
@@ -66,7 +61,9 @@ struct CvHost {  // one (phen, chr) block of one population
 };
 
 struct GenState {  // one generation of one population on the device
-    uint64_t n = 0;
+    uint64_t n = 0;                     // host mirror of *d_n (exact after ge_ctx::pull_state)
+    uint64_t *d_n = nullptr;            // this buffer's size on the device: &StepState::n[k]
+    uint64_t *d_n_hm = nullptr;         // &StepState::n_hm[k]
     Buf hap, cv_allele /* bit plane [2n][Wcv] */, cv_root /* byte plane [2n][n_cv_tot], n_pop > 1 only */, ids, sex, A, D, G, C, E, F, P, mv, sv, svf;
     const uint32_t *rowmap = nullptr;   // after a migration: physical row pair of every individual (PopDev::rowmap_buf); identity otherwise
     Buf hm_off, hm_bp;  // per-haplotype mutation lists (CSR over slots)
@@ -105,9 +102,12 @@ struct PopDev {
     Buf mig_pop[1], mig_idx[1];                 // gather lists of a migration (control stream only)
     Buf rowmap_buf[2];                          // row maps of the last two migrations (by generation parity; the bulk stream reads them late)
     uint64_t prev_n = 0;
+    // device-resident sizes of the generation step (ge_kernels.cuh) and the host's copy of them
+    StepState *d_ss = nullptr;
+    StepState hs{};
     // couples
     Buf c_male, c_female, c_inbreed, c_noff;
-    uint64_t n_couples = 0;
+    uint64_t n_couples = 0, couples_cap = 0;
     // draws of the last reproduce
     DrawSet ds[2];
     int dcur = 0;
@@ -139,24 +139,20 @@ struct ge_ctx {
         for (SortLane &l : lane) { CUDA_TRY(cudaEventRecord(l.done, l.s)); CUDA_TRY(cudaStreamWaitEvent(stream, l.done, 0)); }
         return GE_OK;
     }
-    bool serial = false;
-    bool cub_sorts = false;         // GE_CUB_SORTS: cub::DeviceRadixSort for every sort of the mating chain (A/B against the small sorts)
+    bool serial = false;            // GE_FLAG_SERIAL: the bulk copy is queued on the control stream (no overlap; measurements)
+    bool gen0_done = false;         // ge_init_generation0 has run: maps, the segment format and the draw buffers are fixed
+    bool needs_prev = false;        // some phenotype has vertical transmission (vf > 0): keep the previous generation's P and F
+    bool use_graph = true;          // replay the control chain of a generation as a CUDA graph where possible (GE_FLAG_NO_GRAPH)
+    uint64_t n_loci_total = 0;      // loci of this context over all its chromosomes
     int thin = 8;   // CTAs per SM the heavy control-stream kernels may take while a bulk copy is in flight (0 = no limit)
     bool bulk_busy = false;
-    int prop_depth = 4;
-    int seg_group = 0;              // GE_SEG_GROUP: force 1, 8 or 32 lanes per slot in the segment recombination (0 = by list length)
-    bool seg_walk = false;          // GE_SEG_WALK: the two walk passes (seg_recombine_warp_kernel) instead of plan + gather
     Buf seg_desc, seg_iv_off;       // copy descriptor and output offset of every interval (seg_plan_kernel -> seg_gather_kernel)
-    Buf seg_cnt, seg_scan_blocks, seg_scan_total, seg_flags, seg_verb;   // scratch of the segment path (its own: it may run on the bulk stream)
-    double seg_plan_min_parts = 0;  // GE_SEG_PLAN_MIN: parts per parental list below which the thread-per-slot walk is used (measured: plan + gather wins from generation 1)
+    Buf seg_cnt, seg_flags, seg_verb;   // scratch of the segment path (its own: it may run on the bulk stream)
     bool seg_packed = false;        // 8-byte parts {st, hap_index | root_population << 27} (decided in seg_init_gen0); else the reference's 16-byte parts
-    int seg_depth = 4;              // GE_SEG_DEPTH: independent loads per thread in the packed gather (4 or 8; 8 measured slower: 53 registers)
-    bool seg_wide = false;          // GE_SEG_FORMAT=16: never pack
+    bool seg_wide = false;          // GE_FLAG_SEG_WIDE_PARTS: never pack
     size_t seg_esz() const { return seg_packed ? 8 : 16; }
-    bool seg_sync_mode = false;     // GE_SEG_SYNC: never queue the segment path on the bulk stream
-    bool seg_per_thread = false;    // a genetic map with rows closer than bp_dist_in_rmap was given, or GE_SEG_PER_THREAD is set
-    bool cv_from_segments = false;  // GE_CV_FROM_SEGMENTS: ge_compute_AD rescans the segment lists every generation like the reference
-    bool use_tma = false, tma_attr_set = false;
+    bool seg_per_thread = false;    // a genetic map with rows closer than bp_dist_in_rmap was given, or GE_FLAG_SEG_VERBATIM: the reference's loop, one thread per slot
+    bool cv_from_segments = false;  // GE_FLAG_CV_FROM_SEGMENTS: ge_compute_AD rescans the segment lists every generation like the reference
     double thin_min_bytes = 4e9;   // bytes moved by one bulk launch above which the control kernels go thin (below, the control chain is the critical path)
     int thin_now = 0;              // CTAs per SM in force for the copy in flight
     // Measured (scripts/emulate_rank.py, one rank of a 1/2/4/8-way shard of config 3): copies of >= 30 GB want 8 CTAs per SM for the
@@ -202,13 +198,25 @@ struct ge_ctx {
     Buf d_cv_word_off, d_cv_word_blk, d_cv_block_off, d_cv_bp, d_cv_chr, d_a_eff, d_d_eff, d_cv_count;
     bool cv_ready = false;
     // scratch
-    Buf scan_blocks, scan_total, partial, scalars, flags;
+    Buf scan_blocks, bulk_scan_blocks, partial, scalars;
+    Buf d_ss_all;                               // StepState [n_pop]
+    StepState *h_ss_all = nullptr;              // pinned read-back buffer of the same
+    uint64_t graph_epoch = 0;                   // bumped whenever a device buffer is (re)allocated: captured graphs hold raw pointers
     int n_sm = 148;
     // stats
     bool profiling = false;
     KernelStat kstat[GE_KERNEL_COUNT];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // ge_timer_start / ge_timer_stop
-    struct EvPair { cudaEvent_t a, b; int kernel; uint64_t bytes; };
+    // bytes_per_offspring != 0: the launch's size was only known on the device; pull_state multiplies by the offspring count it reads back
+    // count_src != nullptr: bytes = *count_src * count_scale, a pinned word the launch's stream fills behind the kernels (resolved lazily)
+    struct EvPair { cudaEvent_t a, b; int kernel; uint64_t bytes; uint64_t bytes_per_offspring = 0; int pop = 0; const uint64_t *count_src = nullptr; uint64_t count_scale = 0; };
+    std::vector<uint64_t *> pinned_chunks;   // 512 words each
+    size_t pinned_used = 0;
+    uint64_t *pinned_slot() {
+        if (pinned_chunks.empty() || pinned_used == 512) { uint64_t *c = nullptr; if (cudaMallocHost(&c, 512 * 8) != cudaSuccess) return nullptr; pinned_chunks.push_back(c); pinned_used = 0; }
+        return pinned_chunks.back() + pinned_used++;
+    }
+    void drop_graphs();
     std::vector<EvPair> ev_pending;            // per-launch events of profiled kernels, resolved lazily (no sync in the loop)
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t get_event() {
@@ -219,6 +227,7 @@ struct ge_ctx {
         for (auto &p : ev_pending) {
             cudaEventSynchronize(p.b);
             float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b);
+            if (p.count_src) p.bytes = *p.count_src * p.count_scale;
             kstat[p.kernel].ms += ms; kstat[p.kernel].launches++; kstat[p.kernel].bytes += p.bytes;
             ev_pool.push_back(p.a); ev_pool.push_back(p.b);
         }
@@ -227,7 +236,7 @@ struct ge_ctx {
     // CUDA events around a phase of the control chain (only while profiling)
     struct PhaseTimer {
         ge_ctx *c; EvPair p;
-        PhaseTimer(ge_ctx *ctx, int id) : c(ctx), p{nullptr, nullptr, id, 0} {
+        PhaseTimer(ge_ctx *ctx, int id) : c(ctx), p{nullptr, nullptr, id, 0, 0, 0} {
             if (c->profiling) { p.a = c->get_event(); p.b = c->get_event(); cudaEventRecord(p.a, c->stream); }
         }
         ~PhaseTimer() { if (p.a) { cudaEventRecord(p.b, c->stream); c->ev_pending.push_back(p); } }
@@ -247,6 +256,7 @@ struct ge_ctx {
         if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
         if (e != cudaSuccess) return fail(GE_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
         b.cap = want; mem_now += want; mem_peak = std::max(mem_peak, mem_now);
+        graph_epoch++;
         return GE_OK;
     }
     int ensure_exact(Buf &b, size_t bytes) {
@@ -256,9 +266,10 @@ struct ge_ctx {
         cudaError_t e = cudaMalloc(&b.p, bytes);
         if (e != cudaSuccess) return fail(GE_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
         b.cap = bytes; mem_now += bytes; mem_peak = std::max(mem_peak, mem_now);
+        graph_epoch++;
         return GE_OK;
     }
-    void release(Buf &b) { if (b.p) { cudaFree(b.p); mem_now -= b.cap; } b.p = nullptr; b.cap = 0; }
+    void release(Buf &b) { if (b.p) { cudaFree(b.p); mem_now -= b.cap; graph_epoch++; } b.p = nullptr; b.cap = 0; }
     template <class T> int upload(Buf &b, const std::vector<T> &v) {
         GE_TRY(ensure(b, v.size() * sizeof(T)));
         if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
@@ -309,57 +320,60 @@ struct ge_ctx {
         if (e != cudaSuccess) return fail(GE_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
         return GE_OK;
     }
-    // device exclusive scan: out[0..n] (n+1 entries), grand total also returned to the host when asked
+    // grid of a grid-stride kernel over at most `bound` elements
+    unsigned grid_for(uint64_t bound, unsigned block) const { return (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (bound + block - 1) / block), 1u << 20); }
+    // device exclusive scan: out[0..n] (n + 1 entries, out[n] = grand total); n lives on the device, n_bound (host) sizes the
+    // grid; on_total runs in the thread that stores out[n].  One launch for small arrays, three otherwise.
+    template <class TIn, class OnTotal>
+    int scan_with(cudaStream_t st, Buf &blocks, const TIn *in, DevN n, uint64_t n_bound, uint64_t *out, OnTotal on_total) {
+        if (n_bound <= 2 * SCAN1_CHUNK) {
+            scan_one_cta_kernel<TIn, OnTotal><<<1, SCAN1_THREADS, 0, st>>>(in, n, out, on_total);
+            return check_launch("scan_one_cta");
+        }
+        uint32_t nb = (uint32_t)(n_bound / SCAN_TILE) + 1;
+        GE_TRY(ensure(blocks, (size_t)nb * 8));
+        scan_block_sums_kernel<TIn><<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>());
+        GE_TRY(check_launch("scan_block_sums"));
+        scan_single_block_kernel<<<1, SCAN_THREADS, 0, st>>>(blocks.as<uint64_t>(), n);
+        GE_TRY(check_launch("scan_single_block"));
+        scan_final_kernel<TIn, OnTotal><<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>(), out, on_total);
+        return check_launch("scan_final");
+    }
+    template <class TIn, class OnTotal>
+    int scan(cudaStream_t st, const TIn *in, DevN n, uint64_t n_bound, uint64_t *out, OnTotal on_total) {
+        return scan_with(st, st == bulk ? bulk_scan_blocks : scan_blocks, in, n, n_bound, out, on_total);
+    }
+    // host-known n (setup, migration, downloads); the total is also returned to the host when asked (one sync)
     int exclusive_scan(const uint32_t *in, uint64_t n, uint64_t *out, uint64_t *host_total) {
-        GE_TRY(exclusive_scan_on(stream, scan_blocks, scan_total, in, n, out));
+        GE_TRY(scan(stream, in, hostn(n), n, out, NoTotal{}));
         if (host_total) {
-            if (n == 0) { *host_total = 0; return GE_OK; }
-            CUDA_TRY(cudaMemcpyAsync(host_total, scan_total.p, 8, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(host_total, out + n, 8, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
         }
         return GE_OK;
     }
-    // the same on any stream with its own scratch (the segment path scans on the bulk stream); the total stays in total.p
-    int exclusive_scan_on(cudaStream_t st, Buf &blocks, Buf &total, const uint32_t *in, uint64_t n, uint64_t *out) {
-        GE_TRY(ensure(total, 8));
-        if (n == 0) {
-            CUDA_TRY(cudaMemsetAsync(out, 0, 8, st));
-            CUDA_TRY(cudaMemsetAsync(total.p, 0, 8, st));
-            return GE_OK;
-        }
-        uint32_t nb = nblk(n, SCAN_THREADS * SCAN_ITEMS);
-        GE_TRY(ensure(blocks, (size_t)nb * 8));
-        scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>());
-        GE_TRY(check_launch("scan_block_sums"));
-        scan_single_block_kernel<<<1, SCAN_THREADS, 0, st>>>(blocks.as<uint64_t>(), nb, total.as<uint64_t>());
-        GE_TRY(check_launch("scan_single_block"));
-        scan_final_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>(), out);
-        GE_TRY(check_launch("scan_final"));
+    // mean (denominator n) or variance (two-pass, n-1) of a device column into a device scalar
+    unsigned moment_grid(uint64_t n_bound) const { return (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (n_bound + 255) / 256), MOMENT_MAX_BLOCKS); }
+    int ensure_partial() {
+        if (partial.p) return GE_OK;
+        GE_TRY(ensure(partial, MOMENT_MAX_BLOCKS * 8 + 16));
+        CUDA_TRY(cudaMemsetAsync(partial.p, 0, MOMENT_MAX_BLOCKS * 8 + 16, stream));
         return GE_OK;
     }
-    // mean (denominator n) or variance (two-pass, n-1) of a device column into a device scalar
-    int d_mean(const double *x, uint64_t n, double *out) {
-        int nb = (int)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n, 256)), 1024);
-        GE_TRY(ensure(partial, 1024 * 8));
-        moment_partial_kernel<<<nb, 256, 0, stream>>>(x, n, nullptr, 0, partial.as<double>());
-        GE_TRY(check_launch("moment_partial"));
-        moment_final_kernel<<<1, 32, 0, stream>>>(partial.as<double>(), nb, (double)n, out);
-        return check_launch("moment_final");
+    int d_mean(const double *x, DevN n, uint64_t n_bound, double *out) {
+        GE_TRY(ensure_partial());
+        moment_kernel<<<moment_grid(n_bound), 256, 0, stream>>>(x, n, nullptr, 0, 0, partial.as<double>(), out);
+        return check_launch("moment<mean>");
     }
-    int d_var(const double *x, uint64_t n, double *out /* device */, double *mean_scratch /* device */) {
-        if (n <= 1) { CUDA_TRY(cudaMemsetAsync(out, 0, 8, stream)); return GE_OK; }
-        GE_TRY(d_mean(x, n, mean_scratch));
-        int nb = (int)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n, 256)), 1024);
-        moment_partial_kernel<<<nb, 256, 0, stream>>>(x, n, mean_scratch, 1, partial.as<double>());
-        GE_TRY(check_launch("moment_partial"));
-        moment_final_kernel<<<1, 32, 0, stream>>>(partial.as<double>(), nb, (double)(n - 1), out);
-        return check_launch("moment_final");
+    int d_var(const double *x, DevN n, uint64_t n_bound, double *out /* device */, double *mean_scratch /* device */) {
+        GE_TRY(d_mean(x, n, n_bound, mean_scratch));
+        moment_kernel<<<moment_grid(n_bound), 256, 0, stream>>>(x, n, mean_scratch, 1, 1, partial.as<double>(), out);
+        return check_launch("moment<var>");
     }
     int h_var(const double *x, uint64_t n, double *host_out, double *host_mean = nullptr) {
         GE_TRY(ensure(scalars, 64 * 8));
         double *s = scalars.as<double>();
-        GE_TRY(d_var(x, n, s + 0, s + 1));
-        if (n <= 1) GE_TRY(d_mean(x, std::max<uint64_t>(n, 1), s + 1));
+        GE_TRY(d_var(x, hostn(n), n, s + 0, s + 1));
         double h[2];
         CUDA_TRY(cudaMemcpyAsync(h, s, 16, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
@@ -367,14 +381,16 @@ struct ge_ctx {
         if (host_mean) *host_mean = h[1];
         return GE_OK;
     }
-    int check_flags(const char *where) {
-        int h[4];
-        CUDA_TRY(cudaMemcpyAsync(h, flags.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        if (h[0]) return fail(GE_ERR_NAN, std::string("Error: A or D is nan (") + where + ")");
-        if (h[1]) return fail(GE_ERR_INVALID, "parent ID outside the previous generation (the reference reads out of bounds here, :3118-3133)");
+    // ---- device-resident step state <-> host ----
+    // host copy -> device (setup, replayed draws, migration: whenever the host decides a size)
+    int push_state(PopDev &P, size_t offset = 0, size_t bytes = sizeof(StepState)) {
+        CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(P.d_ss) + offset, reinterpret_cast<const char *>(&P.hs) + offset, bytes, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));   // P.hs is pageable and changes under the caller
         return GE_OK;
     }
+    // device -> host: THE host synchronisation of a generation.  Refreshes every host mirror of a device-side size and turns
+    // the error bits the kernels left into the reference's errors (message, code); the bits are cleared on the device.
+    int pull_state(const char *where);
 };
 
 #define CHECK_CTX(ctx) if (!(ctx)) return fail(GE_ERR_INVALID, "null context")

@@ -62,6 +62,64 @@ __device__ __forceinline__ void normal2(const Stream s, uint32_t purpose, int po
 }
 
 // ------------------------------------------------------------------------------------------------
+// Device-resident state of one population's generation step.  Every size that is only known once a kernel of the
+// step has run (list lengths after thinning, couples, offspring, crossovers, mutation hits) lives HERE and is read
+// by the kernels that follow, so nothing between mating and the phenotypes of a generation needs the host: grids
+// are sized from host-known bounds (capacity, the generation table's pop_size) and loop grid-stride up to the
+// device-side count.  The host reads the struct back once, at the end of the step (sizes for its own
+// bookkeeping, err for the reference's "No one can marry" class of errors).  Being plain device memory it is
+// also what lets a whole generation be replayed as a CUDA graph: no kernel argument depends on a count.
+// ------------------------------------------------------------------------------------------------
+enum StepErr : uint32_t {
+    SE_NAN = 1u << 0,            // A or D is NaN (:2716-2720)
+    SE_PARENT_ID = 1u << 1,      // parent ID outside the previous generation (:3118-3133 reads out of bounds there)
+    SE_NO_MATES_RM = 1u << 2,    // random_mate: an empty sex list (:2125-2129)
+    SE_NO_COUPLES = 1u << 3,     // assort_mate: couples = 0 (:2226-2230)
+    SE_ALL_INBRED = 1u << 4,     // every couple is inbred
+    SE_NO_OFFSPRING = 1u << 5,
+    SE_CAP_OFFSPRING = 1u << 6,  // offspring exceed ge_config.capacity
+    SE_CAP_XO = 1u << 7,         // crossovers exceed the draw buffers (sized from the genetic map at generation 0)
+    SE_CAP_MUT = 1u << 8,        // mutation hits exceed the draw buffers
+    SE_CAP_HM = 1u << 9,         // per-haplotype mutation lists exceed their buffer
+    SE_CAP_COUPLES = 1u << 10,
+    SE_CAP_SEG = 1u << 11,       // founder-segment lists exceed ge_config.seg_capacity
+    SE_SEG_UNSORTED = 1u << 12,  // packed 8-byte parts cannot hold the pieces of a gamete whose crossover positions do not ascend
+};
+// Sizes of one draw set (double-buffered like the draws themselves).  The bulk stream reads THESE, not the step's live counters: its
+// kernels run a generation behind the control stream, which by then is already overwriting n_off and n_xo for the next generation.
+struct DrawCounts { uint64_t n_off, n_xo, n_iv; uint32_t fatal, pad; };
+struct StepState {
+    // the generation-table row, written by step_begin_kernel
+    int32_t gen, sel_func, offspring_dist, pad0;
+    uint64_t pop_size;
+    double mat_cor, u11, sel_par1, sel_par2;
+    // sizes
+    uint64_t n[2];                        // individuals in generation buffers st[0], st[1]
+    uint64_t n_m, n_f, n2, n_trim;        // thinned sex lists; n2 = min(n_m, n_f); n_trim entries leave the longer one
+    uint64_t n_trim_list;                 // length of the list being trimmed (0: nothing to trim)
+    uint64_t n_couples, n_inbreed;
+    uint64_t n_off, n_xo, n_mut;          // offspring and draws of this generation
+    uint64_t n_hm[2];                     // entries of the per-haplotype mutation lists of st[0], st[1]
+    uint64_t n_iv;                        // intervals of the segment plan: n_xo + offspring slots
+    uint64_t n_seg[2];                    // parts in the founder-segment lists of st[0], st[1]
+    DrawCounts dc[2];                     // per draw set, frozen when its crossovers have been placed
+    uint64_t prev_n;                      // size of the snapshot read by vertical transmission (ras_save_human_info_to_Pop_info_prev_gen)
+    uint32_t trim_which;                  // 0: males are trimmed, 1: females
+    uint32_t err;                         // StepErr bits (sticky until the host clears them)
+    // capacities the kernels clamp to (host constants, set once)
+    uint64_t cap, xo_cap, mut_cap, hm_cap, couples_cap;
+};
+constexpr uint32_t SE_FATAL = SE_NO_MATES_RM | SE_NO_COUPLES | SE_ALL_INBRED | SE_NO_OFFSPRING | SE_CAP_OFFSPRING | SE_CAP_XO | SE_CAP_MUT | SE_CAP_HM | SE_CAP_COUPLES | SE_CAP_SEG | SE_SEG_UNSORTED;
+struct StepRow { int32_t gen, sel_func, offspring_dist, pad; uint64_t pop_size; double mat_cor, sel_par1, sel_par2; };
+// first kernel of a step: the host's generation-table row -> device (a kernel argument, so a captured graph replays
+// with one node-parameter update) and the per-step counters back to zero
+__global__ void step_begin_kernel(StepState *ss, StepRow r) {
+    ss->gen = r.gen; ss->sel_func = r.sel_func; ss->offspring_dist = r.offspring_dist; ss->pop_size = r.pop_size;
+    ss->mat_cor = r.mat_cor; ss->u11 = sqrt(1.0 - r.mat_cor * r.mat_cor); ss->sel_par1 = r.sel_par1; ss->sel_par2 = r.sel_par2;
+    ss->n_inbreed = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // genome layout of one bit-packed haplotype row
 // ------------------------------------------------------------------------------------------------
 struct Genome {
@@ -144,36 +202,23 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int DEPTH, bool TAIL_BATCHED = true>
+// whole chunks [q, qe) of one run: four independent 16-byte loads in flight per lane
 __device__ __forceinline__ void warp_copy_chunks(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint32_t q, uint32_t qe, int lane) {
     uint32_t c = q + lane;
-    if (DEPTH == 8) {  // eight independent 16-byte loads in flight per lane: the same bytes in flight per SM with half the warps
-        for (; c + 224 < qe; c += 256) {
-            uint4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = ld_stream(src + c + 32 * u);
-#pragma unroll
-            for (int u = 0; u < 8; u++) st_stream(dst + c + 32 * u, v[u]);
-        }
-    }
     for (; c + 96 < qe; c += 128) {
         uint4 a = ld_stream(src + c), b = ld_stream(src + c + 32), d = ld_stream(src + c + 64), e = ld_stream(src + c + 96);
         st_stream(dst + c, a); st_stream(dst + c + 32, b); st_stream(dst + c + 64, d); st_stream(dst + c + 96, e);
     }
-    if (TAIL_BATCHED) {
-        // the remainder (the mean run between crossovers is about one such iteration long): all of a lane's loads are issued
-        // before its first store, so the tail costs one memory latency instead of one per 512 bytes
-        if (c < qe) {
-            const bool p1 = c + 32 < qe, p2 = c + 64 < qe;
-            uint4 a = ld_stream(src + c), b = a, d = a;
-            if (p1) b = ld_stream(src + c + 32);
-            if (p2) d = ld_stream(src + c + 64);
-            st_stream(dst + c, a);
-            if (p1) st_stream(dst + c + 32, b);
-            if (p2) st_stream(dst + c + 64, d);
-        }
-    } else {
-        for (; c < qe; c += 32) st_stream(dst + c, ld_stream(src + c));
+    // the remainder (the mean run between crossovers is about one such iteration long): all of a lane's loads are issued
+    // before its first store, so the tail costs one memory latency instead of one per 512 bytes
+    if (c < qe) {
+        const bool p1 = c + 32 < qe, p2 = c + 64 < qe;
+        uint4 a = ld_stream(src + c), b = a, d = a;
+        if (p1) b = ld_stream(src + c + 32);
+        if (p2) d = ld_stream(src + c + 64);
+        st_stream(dst + c, a);
+        if (p1) st_stream(dst + c + 32, b);
+        if (p2) st_stream(dst + c + 64, d);
     }
 }
 
@@ -183,15 +228,17 @@ constexpr int PROP_SMEM_FLIPS = 384;   // flips of one offspring staged in share
 // dynamic shared memory: uint64 xo_off[2*n_chr+1] | uint32 flips[PROP_SMEM_FLIPS] | uint8 start[2*n_chr]
 static inline size_t prop_smem_bytes(int n_chr) { return (size_t)(2 * n_chr + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((2 * n_chr + 15) & ~15); }
 
-// PREFETCH issues the two loads of a crossover chunk before the run copy that precedes it.  Same-box measurements on
-// config 3 (kernel alone / pipelined step): 40 registers, 6 CTAs/SM with prefetch 6.55 / 7.67 ms (default); 32 registers,
-// 8 CTAs/SM without prefetch 6.85 / 7.74 ms; 32 registers with prefetch spills and loses (6.95 / 8.02 ms).
-template <int DEPTH, int MINB = (DEPTH == 8 ? 3 : 6), bool PREFETCH = (DEPTH == 4), bool TAIL_BATCHED = true>
-__global__ void __launch_bounds__(PROP_THREADS, MINB)
-propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, const uint32_t *__restrict__ par_rowmap, uint32_t *__restrict__ off_rows,
-                      const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
-                      const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips,
-                      const uint8_t *__restrict__ start_hap, uint64_t off_first, uint32_t n_off) {
+// The two loads of a crossover chunk are issued before the run copy that precedes it.  Same-box measurements on config 3
+// (kernel alone / pipelined step): 40 registers, 6 CTAs/SM with this prefetch 6.55 / 7.67 ms; 32 registers, 8 CTAs/SM
+// without it 6.85 / 7.74 ms; 32 registers with it spills (6.95 / 8.02 ms).  Rejected variants (eight loads per lane, a
+// persistent grid, TMA-staged bulk copies: profiles/r2a_tma_variant.md) are in DESIGN.md §3.
+// The grid is sized from the capacity; CTAs beyond the device-side offspring count exit at once.
+__global__ void __launch_bounds__(PROP_THREADS, 6)
+propagate_bits_kernel(Genome g, TileTable tt, const DrawCounts *__restrict__ dc, const uint32_t *__restrict__ par_rows, const uint32_t *__restrict__ par_rowmap,
+                      uint32_t *__restrict__ off_rows, const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+                      const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips, const uint8_t *__restrict__ start_hap) {
+    if (dc->fatal) return;
+    const uint32_t n_off = (uint32_t)dc->n_off;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_next;
     const int n_ls = 2 * g.n_chr;  // slots of one offspring: chromosome-major, gamete-minor — contiguous in every draw array
@@ -200,7 +247,7 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
     uint8_t *s_start = smem_raw + (size_t)(n_ls + 1) * 8 + PROP_SMEM_FLIPS * 4;
     const int lane = threadIdx.x & 31;
     for (uint32_t oi = blockIdx.x; oi < n_off; oi += gridDim.x) {
-        const uint64_t i = off_first + oi;  // offspring index in the (possibly sharded) generation
+        const uint64_t i = oi;
         const uint64_t slot0 = i * (uint64_t)n_ls;
         __syncthreads();
         // stage this offspring's crossover metadata once, coalesced: the work items below never wait on a
@@ -242,15 +289,14 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
             while (q < q1) {
                 const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
                 const uint32_t qb = f >> 7;
-                if (j >= k || qb >= q1) { warp_copy_chunks<DEPTH, TAIL_BATCHED>(dst, cur ? h1 : h0, q, q1, lane); break; }
+                if (j >= k || qb >= q1) { warp_copy_chunks(dst, cur ? h1 : h0, q, q1, lane); break; }
                 // chunk qb holds one or more flips: merge both parental chunks under a 128-bit mask
                 // (mask bit = 1 -> haplotype 1).  A flip on the chunk's first locus gives bit offset 0.
                 // Its two loads are issued before the run that precedes it, so their latency hides behind that copy.
                 uint4 a = make_uint4(0, 0, 0, 0), b = a;
-                if (PREFETCH && lane == 0) { a = ld_stream(h0 + qb); b = ld_stream(h1 + qb); }
-                warp_copy_chunks<DEPTH, TAIL_BATCHED>(dst, cur ? h1 : h0, q, qb, lane);
+                if (lane == 0) { a = ld_stream(h0 + qb); b = ld_stream(h1 + qb); }
+                warp_copy_chunks(dst, cur ? h1 : h0, q, qb, lane);
                 if (lane == 0) {
-                    if (!PREFETCH) { a = ld_stream(h0 + qb); b = ld_stream(h1 + qb); }
                     const uint32_t fill = cur ? 0xFFFFFFFFu : 0u;
                     uint32_t m0 = fill, m1 = fill, m2 = fill, m3 = fill;
                     const uint32_t base = qb << 7;
@@ -271,207 +317,6 @@ propagate_bits_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_r
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same propagation with TMA-staged copies (cp.async.bulk, 1-D): every run between two crossovers is a
-// contiguous 16-byte-aligned range of one parental row, so it moves global -> shared -> global as bulk copies of
-// up to PROP_PIECE bytes issued by ONE thread per warp, completion tracked by an mbarrier per ring slot (loads)
-// and by bulk async-groups (stores).  The data never passes through registers: a CTA needs 4 driver threads, almost
-// no registers and no issue slots, so the control-stream kernels of the next generation co-reside on the SMs
-// instead of displacing copy warps, and bytes in flight per SM are set by the shared-memory ring, not by occupancy.
-// The one chunk that holds a crossover is still mask-merged with plain vector loads/stores by the driver thread.
-// ------------------------------------------------------------------------------------------------
-constexpr int TMA_WARPS = 4;                 // driver warps (rings) per CTA
-constexpr int TMA_SLOTS = 8;                 // ring slots per warp
-constexpr int TMA_LOOKAHEAD = 6;             // loads in flight ahead of the store cursor (<= TMA_SLOTS - 2)
-constexpr uint32_t PROP_PIECE = 2048;        // bytes per bulk copy (128 chunks; the mean run between crossovers is ~2 KB)
-constexpr int TMA_MERGE_THREADS = 128;       // threads that mask-merge the crossover chunks while the drivers copy
-
-static inline size_t prop_tma_smem_bytes(int n_chr) {
-    size_t meta = (size_t)(2 * n_chr + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((2 * n_chr + 15) & ~15);
-    meta = (meta + 127) & ~(size_t)127;
-    return meta + (size_t)TMA_WARPS * TMA_SLOTS * PROP_PIECE + 128;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes, uint64_t policy) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
-struct TmaRing {  // one per driver thread
-    unsigned char *buf;      // TMA_SLOTS * PROP_PIECE bytes of shared memory
-    uint64_t *bar;           // TMA_SLOTS mbarriers
-    unsigned char *dst[TMA_SLOTS];
-    uint32_t bytes[TMA_SLOTS];
-    uint32_t n_issued, n_stored;
-    uint64_t policy;
-    __device__ __forceinline__ void store_oldest() {
-        const uint32_t sl = n_stored % TMA_SLOTS;
-        mbar_wait(bar + sl, (n_stored / TMA_SLOTS) & 1u);
-        tma_store_1d(dst[sl], buf + (size_t)sl * PROP_PIECE, bytes[sl], policy);
-        n_stored++;
-    }
-    // queue the copy of nbytes (multiple of 16, <= PROP_PIECE) from gsrc to gdst
-    __device__ __forceinline__ void copy(const void *gsrc, void *gdst, uint32_t nbytes) {
-        const uint32_t sl = n_issued % TMA_SLOTS;
-        // slot sl was last used by piece n_issued - TMA_SLOTS, whose store is at least two groups back
-        if (n_issued >= TMA_SLOTS) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TMA_SLOTS - TMA_LOOKAHEAD - 1) : "memory");
-        dst[sl] = static_cast<unsigned char *>(gdst);
-        bytes[sl] = nbytes;
-        mbar_expect_tx(bar + sl, nbytes);
-        tma_load_1d(buf + (size_t)sl * PROP_PIECE, gsrc, nbytes, bar + sl);
-        n_issued++;
-        if (n_issued - n_stored > TMA_LOOKAHEAD) store_oldest();
-    }
-    __device__ __forceinline__ void drain() {
-        while (n_stored < n_issued) store_oldest();
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-};
-
-__device__ __forceinline__ void tma_copy_run(TmaRing &r, const uint4 *src, uint4 *dst, uint32_t q, uint32_t qe) {
-    while (q < qe) {
-        const uint32_t nq = min(qe - q, PROP_PIECE / 16u);
-        r.copy(src + q, dst + q, nq * 16u);
-        q += nq;
-    }
-}
-
-__global__ void __launch_bounds__(TMA_WARPS * 32 + TMA_MERGE_THREADS)
-propagate_bits_tma_kernel(Genome g, TileTable tt, const uint32_t *__restrict__ par_rows, const uint32_t *__restrict__ par_rowmap, uint32_t *__restrict__ off_rows,
-                          const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
-                          const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips,
-                          const uint8_t *__restrict__ start_hap, uint64_t off_first, uint32_t n_off) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_next;
-    __shared__ __align__(8) uint64_t s_bar[TMA_WARPS][TMA_SLOTS];
-    const int n_ls = 2 * g.n_chr;
-    uint64_t *s_off = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *s_fl = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(n_ls + 1) * 8);
-    uint8_t *s_start = smem_raw + (size_t)(n_ls + 1) * 8 + PROP_SMEM_FLIPS * 4;
-    size_t meta = (size_t)(n_ls + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((n_ls + 15) & ~15);
-    meta = (meta + 127) & ~(size_t)127;
-    unsigned char *ring0 = smem_raw + meta;
-    ring0 += (128 - (smem_u32(ring0) & 127u)) & 127u;   // 128-byte aligned ring buffers
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    TmaRing ring;
-    ring.buf = ring0 + (size_t)(warp % TMA_WARPS) * TMA_SLOTS * PROP_PIECE;
-    ring.bar = s_bar[warp % TMA_WARPS];
-    ring.n_issued = ring.n_stored = 0;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(ring.policy));
-    if (lane == 0 && warp < TMA_WARPS) {
-        for (int sl = 0; sl < TMA_SLOTS; sl++) mbar_init(ring.bar + sl, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    for (uint32_t oi = blockIdx.x; oi < n_off; oi += gridDim.x) {
-        const uint64_t i = off_first + oi;
-        const uint64_t slot0 = i * (uint64_t)n_ls;
-        __syncthreads();
-        for (int t = threadIdx.x; t <= n_ls; t += blockDim.x) s_off[t] = xo_off[slot0 + t];
-        for (int t = threadIdx.x; t < n_ls; t += blockDim.x) s_start[t] = start_hap[slot0 + t];
-        if (threadIdx.x == 0) s_next = 0;
-        __syncthreads();
-        const uint64_t e_base = s_off[0];
-        const uint32_t n_fl = (uint32_t)(s_off[n_ls] - e_base);
-        const bool staged = n_fl <= PROP_SMEM_FLIPS;
-        if (staged) for (uint32_t t = threadIdx.x; t < n_fl; t += blockDim.x) s_fl[t] = flips[e_base + t];
-        // after a migration the parents' rows are not in logical order: par_rowmap gives the physical row pair
-        const uint32_t pf = par_rowmap ? par_rowmap[father[i]] : father[i], pm = par_rowmap ? par_rowmap[mother[i]] : mother[i];
-        __syncthreads();
-        if (warp >= TMA_WARPS) {
-            // merge threads: every chunk that holds a crossover is a mask-merge of both parental chunks (mask bit = 1 ->
-            // haplotype 1); thread t takes flip t of the offspring when it is the first flip of its chunk
-            for (uint32_t t = threadIdx.x - TMA_WARPS * 32; t < n_fl; t += TMA_MERGE_THREADS) {
-                const uint64_t e = e_base + t;
-                int lo = 0, hi = n_ls - 1;  // slot with s_off[ls] <= e < s_off[ls+1]
-                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= e) lo = mid; else hi = mid - 1; }
-                const int ls = lo;
-                const uint32_t *fl = staged ? s_fl + (s_off[ls] - e_base) : flips + s_off[ls];
-                const uint32_t jj = (uint32_t)(e - s_off[ls]), k = (uint32_t)(s_off[ls + 1] - s_off[ls]);
-                const uint32_t qb = fl[jj] >> 7;
-                if (jj > 0 && (fl[jj - 1] >> 7) == qb) continue;
-                const uint32_t c = (uint32_t)ls >> 1;
-                const int gam = ls & 1;
-                const uint32_t nq = ((g.chr_nloci[c] + 31) / 32 + 3) / 4;
-                if (qb >= nq) continue;   // a crossover beyond the last locus only sets the parity of nothing
-                const uint32_t woff = g.chr_word_off[c];
-                const uint32_t prow = gam ? pm : pf;
-                const uint4 *h0 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow) * g.W + woff);
-                const uint4 *h1 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow + 1) * g.W + woff);
-                uint4 *dst = reinterpret_cast<uint4 *>(off_rows + (uint64_t)(2 * i + gam) * g.W + woff);
-                const uint4 a = ld_stream(h0 + qb), b = ld_stream(h1 + qb);
-                const uint32_t fill = ((s_start[ls] ^ jj) & 1u) ? 0xFFFFFFFFu : 0u;
-                uint32_t m0 = fill, m1 = fill, m2 = fill, m3 = fill;
-                const uint32_t base = qb << 7;
-                for (uint32_t j2 = jj; j2 < k && fl[j2] < base + 128u; j2++) {
-                    const uint32_t r = fl[j2] - base;
-                    m0 ^= r < 32u ? 0xFFFFFFFFu << r : 0u;
-                    m1 ^= r <= 32u ? 0xFFFFFFFFu : (r < 64u ? 0xFFFFFFFFu << (r - 32u) : 0u);
-                    m2 ^= r <= 64u ? 0xFFFFFFFFu : (r < 96u ? 0xFFFFFFFFu << (r - 64u) : 0u);
-                    m3 ^= r <= 96u ? 0xFFFFFFFFu : 0xFFFFFFFFu << (r - 96u);
-                }
-                uint4 o;
-                o.x = (a.x & ~m0) | (b.x & m0); o.y = (a.y & ~m1) | (b.y & m1);
-                o.z = (a.z & ~m2) | (b.z & m2); o.w = (a.w & ~m3) | (b.w & m3);
-                st_stream(dst + qb, o);
-            }
-            continue;
-        }
-        if (lane != 0) continue;  // one driver thread per copy warp
-        for (;;) {
-            const uint32_t item = atomicAdd(&s_next, 1u);
-            if (item >= 2 * tt.n_items) break;
-            const int gam = item >= tt.n_items;
-            const uint32_t it = gam ? item - tt.n_items : item;
-            const uint32_t c = tt.chr[it], q0 = tt.chunk0[it], q1 = q0 + tt.nchunk[it];
-            const int ls = (int)c * 2 + gam;
-            const uint64_t e0 = s_off[ls];
-            const uint32_t k = (uint32_t)(s_off[ls + 1] - e0);
-            const uint32_t *fl = staged ? s_fl + (e0 - e_base) : flips + e0;
-            const uint32_t woff = g.chr_word_off[c];
-            const uint32_t prow = gam ? pm : pf;
-            const uint4 *h0 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow) * g.W + woff);
-            const uint4 *h1 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow + 1) * g.W + woff);
-            uint4 *dst = reinterpret_cast<uint4 *>(off_rows + (uint64_t)(2 * i + gam) * g.W + woff);
-            uint32_t j = 0;
-            const uint32_t x0 = q0 << 7;
-            while (j < k && fl[j] <= x0) j++;
-            uint32_t cur = (s_start[ls] ^ j) & 1u;
-            uint32_t q = q0;
-            while (q < q1) {   // whole runs between crossover chunks go through the TMA ring
-                const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
-                const uint32_t qb = f >> 7;
-                if (j >= k || qb >= q1) { tma_copy_run(ring, cur ? h1 : h0, dst, q, q1); break; }
-                tma_copy_run(ring, cur ? h1 : h0, dst, q, qb);
-                while (j < k && fl[j] < ((qb + 1) << 7)) { j++; cur ^= 1u; }
-                q = qb + 1;
-            }
-        }
-    }
-    if (lane == 0 && warp < TMA_WARPS) ring.drain();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -576,15 +421,17 @@ __global__ void cv_init_kernel(CvSet cs, const uint8_t *__restrict__ founder_cv 
 // below its position, so a crossover flips every CV of the word from index lower_bound(bp, crossover) upwards;
 // the word is then a mask-merge of the two parental words — the same operation as the boundary chunk of
 // propagate_bits_kernel.
-__global__ void cv_propagate_bits_kernel(CvSet cs, const uint32_t *__restrict__ par_bits, uint32_t *__restrict__ off_bits,
+__global__ void cv_propagate_bits_kernel(CvSet cs, const StepState *__restrict__ ss, const uint32_t *__restrict__ par_bits, uint32_t *__restrict__ off_bits,
                                          const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                                          const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
-                                         const uint8_t *__restrict__ start_hap, uint64_t off_first, uint64_t n_off) {
+                                         const uint8_t *__restrict__ start_hap) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n_off = ss->n_off;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_off * 2 * cs.Wcv; t += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t w;
     uint64_t row;
     divmod_idx(t, cs.Wcv, row, w);
-    uint64_t i = off_first + (row >> 1);
+    uint64_t i = row >> 1;
     int gam = (int)(row & 1);
     uint32_t b = cs.word_blk[w], v = 0;
     if (b != 0xFFFFFFFFu) {
@@ -613,15 +460,16 @@ __global__ void cv_propagate_bits_kernel(CvSet cs, const uint32_t *__restrict__ 
 }
 
 // root-population plane (only with more than one population): one thread per (offspring gamete row, CV)
-__global__ void cv_root_propagate_kernel(CvSet cs, const uint8_t *__restrict__ par_root, uint8_t *__restrict__ off_root,
+__global__ void cv_root_propagate_kernel(CvSet cs, const StepState *__restrict__ ss, const uint8_t *__restrict__ par_root, uint8_t *__restrict__ off_root,
                                          const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                                          const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
-                                         const uint8_t *__restrict__ start_hap, uint64_t off_first, uint64_t n_off) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_off * 2 * cs.n_cv_tot) return;
+                                         const uint8_t *__restrict__ start_hap) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n_off = ss->n_off;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_off * 2 * cs.n_cv_tot; t += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t k = (uint32_t)(t % cs.n_cv_tot);
     uint64_t row = t / cs.n_cv_tot;
-    uint64_t i = off_first + (row >> 1);
+    uint64_t i = row >> 1;
     int gam = (int)(row & 1);
     uint32_t c = cs.chr_of[k], p = cs.bp[k];
     uint64_t slot = (i * (uint64_t)cs.n_chr + c) * 2 + gam;
@@ -629,15 +477,18 @@ __global__ void cv_root_propagate_kernel(CvSet cs, const uint8_t *__restrict__ p
     for (uint64_t e = xo_off[slot]; e < xo_off[slot + 1]; e++) h ^= (xo_bp[e] <= p);
     uint32_t parent = gam ? mother[i] : father[i];
     off_root[(i * 2 + gam) * (uint64_t)cs.n_cv_tot + k] = par_root[((uint64_t)parent * 2 + (h & 1)) * cs.n_cv_tot + k];
+    }
 }
 
 // allele count per CV over the population (frq numerator, :2647-2663).  A CTA takes 32 word columns x 512 rows:
 // a warp reads 32 consecutive words of one row (128 B), 8 warps stride the rows, every thread keeps the 32 bit
 // counters of its word in registers; shared-memory atomics fold the 8 warps, one 64-bit atomic per CV and CTA.
-__global__ void cv_count_bits_kernel(CvSet cs, const uint32_t *__restrict__ bits, uint64_t n_rows, unsigned long long *__restrict__ count) {
+__global__ void cv_count_bits_kernel(CvSet cs, const uint32_t *__restrict__ bits, const uint64_t *__restrict__ n_ind, unsigned long long *__restrict__ count) {
     __shared__ unsigned int sh[32][33];
     const uint32_t w = blockIdx.x * 32 + threadIdx.x;
+    const uint64_t n_rows = 2 * *n_ind;
     const uint64_t r0 = (uint64_t)blockIdx.y * 512, r1 = min(r0 + 512, n_rows);
+    if (r0 >= n_rows) return;
     for (int q = threadIdx.y; q < 32; q += 8) sh[q][threadIdx.x] = 0;
     __syncthreads();
     unsigned int cnt[32];
@@ -667,13 +518,14 @@ __global__ void cv_count_bits_kernel(CvSet cs, const uint32_t *__restrict__ bits
 // A and D per individual (ras_compute_AD :2686-2746): one warp per individual and phenotype; lanes stride
 // the CVs of each chromosome block and the warp reduces once at the end (fp64, fixed shuffle tree).
 __global__ void genetic_value_kernel(CvSet cs, const uint32_t *__restrict__ bits, const uint8_t *__restrict__ rootp,
-                                     const unsigned long long *__restrict__ count, uint64_t n_count /* individuals in frq */,
+                                     const unsigned long long *__restrict__ count, const uint64_t *__restrict__ n_ind /* individuals (also in frq) */,
                                      const double *__restrict__ a_eff /* [n_pop][n_cv_tot] */, const double *__restrict__ d_eff,
-                                     const uint8_t *__restrict__ vd_zero /* [n_phen] */, uint64_t n, double *__restrict__ A,
-                                     double *__restrict__ D, double *__restrict__ Gv, int *__restrict__ nan_flag) {
-    uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                     const uint8_t *__restrict__ vd_zero /* [n_phen] */, uint64_t stride /* column stride = capacity */, double *__restrict__ A,
+                                     double *__restrict__ D, double *__restrict__ Gv, uint32_t *__restrict__ err) {
+    const uint64_t n = *n_ind, n_count = n;
     int lane = threadIdx.x & 31;
-    if (wid >= n * cs.n_phen) return;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < n * cs.n_phen; wid += n_warps) {
     uint64_t i = wid % n;
     int f = (int)(wid / n);
     const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
@@ -699,22 +551,23 @@ __global__ void genetic_value_kernel(CvSet cs, const uint32_t *__restrict__ bits
     }
     for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
     if (lane == 0) {
-        A[(uint64_t)f * n + i] = Ac; D[(uint64_t)f * n + i] = Dc; Gv[(uint64_t)f * n + i] = Ac + Dc;
-        if (isnan(Ac) || isnan(Dc)) *nan_flag = 1;
+        A[(uint64_t)f * stride + i] = Ac; D[(uint64_t)f * stride + i] = Dc; Gv[(uint64_t)f * stride + i] = Ac + Dc;
+        if (isnan(Ac) || isnan(Dc)) atomicOr(err, (uint32_t)SE_NAN);
+    }
     }
 }
 
 // One population: the per-CV terms do not depend on the individual, so they are tabulated once per generation —
 // LAD[k][t] = {(t - 2p) * alpha, c_t * d} for genotype t in {0,1,2} (the very products of :2691-2712) —
 // and the per-individual kernel only gathers and adds them.
-__global__ void cv_tables_kernel(CvSet cs, const unsigned long long *__restrict__ count, uint64_t n_count, const double *__restrict__ a_eff,
+__global__ void cv_tables_kernel(CvSet cs, const unsigned long long *__restrict__ count, const uint64_t *__restrict__ n_ind, const double *__restrict__ a_eff,
                                  const double *__restrict__ d_eff, const uint8_t *__restrict__ vd_zero, double2 *__restrict__ LAD) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cs.n_cv_tot) return;
     int blk = 0;
     while (cs.block_off[blk + 1] <= k) blk++;
     const int f = blk / cs.n_chr;
-    const double two_n = (double)(2 * n_count);
+    const double two_n = (double)(2 * *n_ind);
     double a = (a_eff[k] + a_eff[k]) / 2;
     double d = vd_zero[f] ? 0.0 : (d_eff[k] + d_eff[k]) / 2;
     double p = (double)count[k] / two_n, q = 1 - p;
@@ -727,7 +580,10 @@ __global__ void cv_tables_kernel(CvSet cs, const unsigned long long *__restrict_
 // Lanes stride the CVs of the phenotype as one flat list (bitpos[k] = position of CV k in the bit row, LAD[k][t] =
 // {LA, LD} in one 16-byte load), so there is no per-chromosome bookkeeping and every lane has the same trip count.
 __global__ void genetic_value_lut_kernel(CvSet cs, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ bitpos, const double2 *__restrict__ LAD,
-                                         uint64_t n, double *__restrict__ A, double *__restrict__ D, double *__restrict__ Gv, int *__restrict__ nan_flag) {
+                                         const uint64_t *__restrict__ n_ind, uint64_t stride /* column stride = capacity */, double *__restrict__ A, double *__restrict__ D,
+                                         double *__restrict__ Gv, uint32_t *__restrict__ err) {
+    const uint64_t n = *n_ind;
+    if (n == 0) return;
     const int lane = threadIdx.x & 31;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < n * cs.n_phen; wid += n_warps) {
@@ -748,8 +604,8 @@ __global__ void genetic_value_lut_kernel(CvSet cs, const uint32_t *__restrict__ 
         }
         for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
         if (lane == 0) {
-            A[(uint64_t)f * n + i] = Ac; D[(uint64_t)f * n + i] = Dc; Gv[(uint64_t)f * n + i] = Ac + Dc;
-            if (isnan(Ac) || isnan(Dc)) *nan_flag = 1;
+            A[(uint64_t)f * stride + i] = Ac; D[(uint64_t)f * stride + i] = Dc; Gv[(uint64_t)f * stride + i] = Ac + Dc;
+            if (isnan(Ac) || isnan(Dc)) atomicOr(err, (uint32_t)SE_NAN);
         }
     }
 }
@@ -763,9 +619,20 @@ __global__ void cv_unpack_block_kernel(const uint32_t *__restrict__ bits, uint32
     out[t] = (bits[row * Wcv + wo + (j >> 5)] >> (j & 31)) & 1u;
 }
 
+// a count that lives on the device: (*p) * mul + add (p == nullptr: add alone, a host-known count)
+struct DevN {
+    const uint64_t *p; uint64_t mul, add;
+    __device__ __forceinline__ uint64_t get() const { return (p ? *p : 0ull) * mul + add; }
+};
+static inline DevN devn(const uint64_t *p, uint64_t mul = 1, uint64_t add = 0) { return DevN{p, mul, add}; }
+static inline DevN hostn(uint64_t n) { return DevN{nullptr, 0, n}; }
+
 // ------------------------------------------------------------------------------------------------
-// fp64 population moments: sum, then centred sum of squares (two-pass like CommFunc::var, src/CommFunc.cpp:57-68)
+// fp64 population moments: sum, then centred sum of squares (two-pass like CommFunc::var, src/CommFunc.cpp:57-68).
+// One launch per pass: every CTA leaves its partial sum in a fixed slot, the last CTA to arrive (ticket) adds the
+// slots in a fixed order — so the result does not depend on the arrival order — and divides.
 // ------------------------------------------------------------------------------------------------
+constexpr int MOMENT_MAX_BLOCKS = 1024;
 __device__ __forceinline__ double block_reduce_sum(double v) {
     __shared__ double sh[32];
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -776,122 +643,172 @@ __device__ __forceinline__ double block_reduce_sum(double v) {
     if (threadIdx.x < 32) for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;  // valid in thread 0
 }
-// partial[blockIdx.x] = sum over this block's grid-stride slice of (x - *shift)^2 (pow2) or of x
-__global__ void moment_partial_kernel(const double *__restrict__ x, uint64_t n, const double *__restrict__ shift, int pow2, double *__restrict__ partial) {
+// scratch: double partial[MOMENT_MAX_BLOCKS] followed by one unsigned ticket (zero between launches)
+__device__ __forceinline__ void moment_finish(double s, double *__restrict__ partial, uint64_t n, int minus, double *__restrict__ out) {
+    __shared__ bool last;
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(partial + MOMENT_MAX_BLOCKS);
+    s = block_reduce_sum(s);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = s;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {   // lane l adds slots l, l+32, ..., then a shuffle tree: a fixed order
+        double t = 0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) t += *((volatile double *)(partial + i));
+        for (int o = 16; o; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) {
+            const double denom = (double)n - (double)minus;
+            *out = (denom > 0 && (minus == 0 || n > 1)) ? t / denom : 0.0;
+            *ticket = 0;
+        }
+    }
+}
+// *out = sum over i < n of x[i] (pow2 = 0, minus = 0: the mean) or of (x[i] - *shift)^2 (pow2 = 1, minus = 1: the variance), / (n - minus)
+__global__ void __launch_bounds__(256) moment_kernel(const double *__restrict__ x, DevN dn, const double *__restrict__ shift, int pow2, int minus, double *__restrict__ partial,
+                                                      double *__restrict__ out) {
+    const uint64_t n = dn.get();
     double s = 0, mu = shift ? *shift : 0.0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         double v = x[i] - mu;
         s += pow2 ? v * v : v;
     }
-    s = block_reduce_sum(s);
-    if (threadIdx.x == 0) partial[blockIdx.x] = s;
-}
-// out[0] = (sum of partials) / denom  — one warp, fixed order: lane l adds partials l, l+32, ..., then a shuffle tree
-__global__ void moment_final_kernel(const double *__restrict__ partial, int n_partial, double denom, double *__restrict__ out) {
-    double s = 0;
-    for (int i = threadIdx.x; i < n_partial; i += 32) s += partial[i];
-    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) *out = denom > 0 ? s / denom : 0.0;
+    moment_finish(s, partial, n, minus, out);
 }
 
 // ------------------------------------------------------------------------------------------------
 // phenotypes: ras_scale_AD_compute_GEF :3075-3206 (elementwise part) and MV/SV :3300-3342
 // ------------------------------------------------------------------------------------------------
-__global__ void enoise_kernel(Stream st, int pop, int gen, int f, uint64_t first, uint64_t n, double *__restrict__ e) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double z0, z1;
-    normal2(st, P_ENOISE, pop, gen, first + i, (uint32_t)f, z0, z1);
-    e[i] = z0;
+// environment draws e_i ~ N(0,1) (:3102) and their mean in the same pass
+__global__ void __launch_bounds__(256) enoise_mean_kernel(Stream st, const StepState *__restrict__ ss, int pop, int f, const uint64_t *__restrict__ n_ind, double *__restrict__ e,
+                                                           double *__restrict__ partial, double *__restrict__ out_mean) {
+    const uint64_t n = *n_ind;
+    const int gen = ss->gen;
+    double s = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double z0, z1;
+        normal2(st, P_ENOISE, pop, gen, i, (uint32_t)f, z0, z1);
+        e[i] = z0;
+        s += z0;
+    }
+    moment_finish(s, partial, n, 0, out_mean);
 }
-__global__ void normal_scaled_kernel(Stream st, uint32_t purpose, int pop, int gen, int f, uint64_t first, uint64_t n, double sd, double *__restrict__ out) {
+__global__ void normal_scaled_kernel(Stream st, uint32_t purpose, int pop, int gen, int f, uint64_t n, double sd, double *__restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double z0, z1;
-    normal2(st, purpose, pop, gen, first + i, (uint32_t)f, z0, z1);
+    normal2(st, purpose, pop, gen, i, (uint32_t)f, z0, z1);
     out[i] = z0 * sd;
 }
 
 struct PhenoArgs {
     double s_a, s_d, ve, vf, beta;
-    int gen, vt_type;
-    uint64_t n, prev_n;
+    int vt_type;
 };
-__global__ void phenotype_kernel(PhenoArgs a, const double *__restrict__ e_raw, const double *__restrict__ var_e,
+__global__ void phenotype_kernel(PhenoArgs a, const StepState *__restrict__ ss, const uint64_t *__restrict__ n_ind, const uint64_t *__restrict__ prev_n_ptr,
+                                 const double *__restrict__ e_raw, const double *__restrict__ var_e,
                                  double *__restrict__ A, double *__restrict__ D, double *__restrict__ G, const double *__restrict__ Cc,
                                  double *__restrict__ E, double *__restrict__ F, double *__restrict__ P,
                                  const uint64_t *__restrict__ ids, const double *__restrict__ prev_P, const double *__restrict__ prev_F,
-                                 const double *__restrict__ f0, int *__restrict__ err_flag) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    double s_ev = a.ve > 0 ? sqrt(*var_e / a.ve) : 0.0;
-    double e = s_ev > 0 ? e_raw[i] / s_ev : 0.0;
-    double av = A[i] / a.s_a;
-    double dv = a.s_d > 0 ? D[i] / a.s_d : 0.0;
-    double fv = 0.0;
-    if (a.vf > 0) {
-        if (a.gen == 0) fv = f0 ? f0[i] : 0.0;
-        else {
-            uint64_t idf = ids[i * 7 + 1], idm = ids[i * 7 + 2];
-            if (idf >= a.prev_n || idm >= a.prev_n) { *err_flag = 1; }
+                                 const double *__restrict__ f0, uint32_t *__restrict__ err) {
+    const uint64_t n = *n_ind;
+    const int gen = ss->gen;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double s_ev = a.ve > 0 ? sqrt(*var_e / a.ve) : 0.0;
+        double e = s_ev > 0 ? e_raw[i] / s_ev : 0.0;
+        double av = A[i] / a.s_a;
+        double dv = a.s_d > 0 ? D[i] / a.s_d : 0.0;
+        double fv = 0.0;
+        if (a.vf > 0) {
+            if (gen == 0) fv = f0 ? f0[i] : 0.0;
             else {
-                const double *src = a.vt_type == 1 ? prev_P : prev_F;
-                fv = a.beta * (src[idf] + src[idm]);
+                const uint64_t prev_n = *prev_n_ptr;
+                uint64_t idf = ids[i * 7 + 1], idm = ids[i * 7 + 2];
+                if (idf >= prev_n || idm >= prev_n) atomicOr(err, (uint32_t)SE_PARENT_ID);
+                else {
+                    const double *src = a.vt_type == 1 ? prev_P : prev_F;
+                    fv = a.beta * (src[idf] + src[idm]);
+                }
             }
         }
+        E[i] = e; A[i] = av; D[i] = dv; G[i] = av + dv; F[i] = fv;
+        P[i] = av + dv + Cc[i] + e + fv;
     }
-    E[i] = e; A[i] = av; D[i] = dv; G[i] = av + dv; F[i] = fv;
-    P[i] = av + dv + Cc[i] + e + fv;
 }
 
-__global__ void mv_sv_kernel(uint64_t n, int n_phen, const double *__restrict__ P, const double *__restrict__ omega,
-                             const double *__restrict__ lambda, double *__restrict__ mv, double *__restrict__ sv_raw) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double m = 0, s = 0;
-    for (int f = 0; f < n_phen; f++) { double p = P[(uint64_t)f * n + i]; m += omega[f] * p; s += lambda[f] * p; }
-    mv[i] = m; sv_raw[i] = s;
-}
-__global__ void selection_kernel(uint64_t n, int gen, int func, double par1, double par2, const double *__restrict__ mean0,
-                                 const double *__restrict__ var0, const double *__restrict__ sv_raw, double *__restrict__ sv, double *__restrict__ svf) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double z = sv_raw[i] - *mean0;
-    if (*var0 > 0) z = (sv_raw[i] - *mean0) / sqrt(*var0);
-    sv[i] = z;
-    double r = 1.0;
-    if (gen != 0) {  // ras_selection_func :3386-3428
-        if (func == 0) { double y = exp(0.0 + 1.0 * z); r = y / (1 + y); }
-        else if (func == 1) { double y = exp(par1 + par2 * z); r = y / (1 + y); }
-        else if (func == 2) r = .5 * (1 + erf((z - par1) / (sqrt(2.0) * par2)));
-        else if (func == 3) { const double pi = 3.1415926; double u = (z - par1) / par2; r = 1 / (sqrt(2.0 * pi) * par2) * exp(-0.5 * (u * u)); }
-        else if (func == 4) r = z <= par2 ? par1 : 1.0;
+// mating value and raw selection value (:3300-3322); with sv0 = {mean, var} of generation 0 also the standardised selection value
+// and its map to a mating probability (ras_selection_func :3386-3428).  Generation 0 runs it twice: raw values, moments, then all.
+__global__ void mv_sv_selection_kernel(const StepState *__restrict__ ss, const uint64_t *__restrict__ n_ind, int n_phen, uint64_t stride, const double *__restrict__ P,
+                                       const double *__restrict__ omega, const double *__restrict__ lambda, const double *__restrict__ sv0 /* null: raw only */,
+                                       double *__restrict__ mv, double *__restrict__ sv, double *__restrict__ svf) {
+    const uint64_t n = *n_ind;
+    const int gen = ss->gen, func = ss->sel_func;
+    const double par1 = ss->sel_par1, par2 = ss->sel_par2;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double m = 0, s = 0;
+        for (int f = 0; f < n_phen; f++) { double p = P[(uint64_t)f * stride + i]; m += omega[f] * p; s += lambda[f] * p; }
+        mv[i] = m;
+        if (!sv0) { sv[i] = s; continue; }
+        const double mean0 = sv0[0], var0 = sv0[1];
+        double z = s - mean0;
+        if (var0 > 0) z = (s - mean0) / sqrt(var0);
+        sv[i] = z;
+        double r = 1.0;
+        if (gen != 0) {  // ras_selection_func :3386-3428
+            if (func == 0) { double y = exp(0.0 + 1.0 * z); r = y / (1 + y); }
+            else if (func == 1) { double y = exp(par1 + par2 * z); r = y / (1 + y); }
+            else if (func == 2) r = .5 * (1 + erf((z - par1) / (sqrt(2.0) * par2)));
+            else if (func == 3) { const double pi = 3.1415926; double u = (z - par1) / par2; r = 1 / (sqrt(2.0 * pi) * par2) * exp(-0.5 * (u * u)); }
+            else if (func == 4) r = z <= par2 ? par1 : 1.0;
+        }
+        svf[i] = r;
     }
-    svf[i] = r;
 }
 __global__ void add_scalar_kernel(double *__restrict__ x, uint64_t n, double v) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] += v;
 }
+// ras_save_human_info_to_Pop_info_prev_gen (:3211-3236): phenotype and parental effect of the generation, by position
+__global__ void save_prev_kernel(const uint64_t *__restrict__ n_ind, int n_phen, uint64_t stride, const double *__restrict__ P, const double *__restrict__ F,
+                                 double *__restrict__ prev_P, double *__restrict__ prev_F, uint64_t *__restrict__ prev_n) {
+    const uint64_t n = *n_ind;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * n_phen; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t f = t / n, i = t - f * n;
+        prev_P[f * stride + i] = P[f * stride + i];
+        prev_F[f * stride + i] = F[f * stride + i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *prev_n = n;
+}
 
-// pedigree of the offspring (:2471-2479)
-__global__ void pedigree_kernel(uint64_t first, uint64_t n_off, const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+// pedigree of the offspring (:2471-2479) — replayed draws; the Philox path writes it in offspring_kernel
+__global__ void pedigree_kernel(uint64_t n_off, const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                                 const uint64_t *__restrict__ par_ids, uint64_t *__restrict__ ids) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_off) return;
-    uint64_t i = first + t;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_off) return;
     const uint64_t *fa = par_ids + (uint64_t)father[i] * 7, *mo = par_ids + (uint64_t)mother[i] * 7;
     uint64_t *d = ids + i * 7;
     d[0] = i; d[1] = fa[0]; d[2] = mo[0]; d[3] = fa[1]; d[4] = fa[2]; d[5] = mo[1]; d[6] = mo[2];
 }
 
 // ------------------------------------------------------------------------------------------------
-// generic exclusive scan of uint32 counts into uint64 offsets (block-level scans; three launches)
+// generic exclusive scan of counts into uint64 offsets, with the element count read from device memory
 // ------------------------------------------------------------------------------------------------
+// what the thread that owns out[n] does with the grand total (besides storing it)
+struct NoTotal { __device__ __forceinline__ void operator()(uint64_t) const {} };
+struct StoreTotal {   // *dst = total; err |= bit when it exceeds cap
+    uint64_t *dst; uint32_t *err; const uint64_t *cap; uint32_t bit;
+    __device__ __forceinline__ void operator()(uint64_t t) const { *dst = t; if (cap && t > *cap) atomicOr(err, bit); }
+};
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;  // per thread -> 2048 per block
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+template <int THREADS>
 __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t &total) {
-    __shared__ uint64_t wsum[SCAN_THREADS / 32];
+    __shared__ uint64_t wsum[THREADS / 32];
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t x = v;
     for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -899,47 +816,84 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t &t
     if (lane == 31) wsum[warp] = x;
     __syncthreads();
     if (warp == 0) {
-        uint64_t w = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
+        uint64_t w = lane < THREADS / 32 ? wsum[lane] : 0;
         for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-        if (lane < SCAN_THREADS / 32) wsum[lane] = w;
+        if (lane < THREADS / 32) wsum[lane] = w;
     }
     __syncthreads();
     uint64_t base = warp ? wsum[warp - 1] : 0;
-    total = wsum[SCAN_THREADS / 32 - 1];
+    total = wsum[THREADS / 32 - 1];
     return base + x - v;
 }
-__global__ void scan_block_sums_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ block_sums) {
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_THREADS * SCAN_ITEMS;
+// three launches, any size: block sums, scan of the block sums (one CTA), final pass.  Blocks beyond the device-side n idle.
+template <class TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const TIn *__restrict__ in, DevN dn, uint64_t *__restrict__ block_sums) {
+    const uint64_t n = dn.get();
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    if (base > n) return;
     uint64_t s = 0;
     for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; if (i < n) s += in[i]; }
-    uint64_t total; block_exclusive_scan(s, total);
+    uint64_t total; block_exclusive_scan<SCAN_THREADS>(s, total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
-__global__ void scan_single_block_kernel(uint64_t *__restrict__ block_sums, uint32_t nb, uint64_t *__restrict__ grand_total) {
-    // serial over chunks of SCAN_THREADS entries; nb is small (n / 2048)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_single_block_kernel(uint64_t *__restrict__ block_sums, DevN dn) {
+    // serial over chunks of SCAN_THREADS entries; nb is small (n / 2048 + 1)
+    const uint32_t nb = (uint32_t)(dn.get() / SCAN_TILE) + 1;
     __shared__ uint64_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (uint32_t b = 0; b < nb; b += SCAN_THREADS) {
         uint32_t i = b + threadIdx.x;
         uint64_t v = i < nb ? block_sums[i] : 0, total;
-        uint64_t ex = block_exclusive_scan(v, total);
+        uint64_t ex = block_exclusive_scan<SCAN_THREADS>(v, total);
         uint64_t c = carry;
         if (i < nb) block_sums[i] = ex + c;
         __syncthreads();
         if (threadIdx.x == 0) carry = c + total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *grand_total = carry;
 }
-__global__ void scan_final_kernel(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ block_sums, uint64_t *__restrict__ out) {
-    uint64_t base = (uint64_t)blockIdx.x * SCAN_THREADS * SCAN_ITEMS;
+template <class TIn, class OnTotal>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const TIn *__restrict__ in, DevN dn, const uint64_t *__restrict__ block_sums, uint64_t *__restrict__ out, OnTotal on_total) {
+    const uint64_t n = dn.get();
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    if (base > n) return;
     uint64_t v[SCAN_ITEMS], s = 0;
     for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; v[k] = i < n ? in[i] : 0; s += v[k]; }
-    uint64_t total, ex = block_exclusive_scan(s, total);
+    uint64_t total, ex = block_exclusive_scan<SCAN_THREADS>(s, total);
     uint64_t run = block_sums[blockIdx.x] + ex;
-    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; if (i < n) out[i] = run; run += v[k]; }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = run;  // total at out[n]
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k;
+        if (i <= n) out[i] = run;                    // out[n] = grand total (everything at or beyond n counts zero)
+        if (i == n) on_total(run);
+        run += v[k];
+    }
+}
+// one launch, small arrays (the launch-bound configurations): ONE CTA walks the array in chunks with a running carry
+constexpr int SCAN1_THREADS = 1024;
+constexpr int SCAN1_CHUNK = SCAN1_THREADS * SCAN_ITEMS;
+template <class TIn, class OnTotal>
+__global__ void __launch_bounds__(SCAN1_THREADS) scan_one_cta_kernel(const TIn *__restrict__ in, DevN dn, uint64_t *__restrict__ out, OnTotal on_total) {
+    const uint64_t n = dn.get();
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base <= n; base += SCAN1_CHUNK) {
+        uint64_t v[SCAN_ITEMS], s = 0;
+        for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; v[k] = i < n ? in[i] : 0; s += v[k]; }
+        uint64_t total, ex = block_exclusive_scan<SCAN1_THREADS>(s, total);
+        const uint64_t c = carry;
+        uint64_t run = c + ex;
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k;
+            if (i <= n) out[i] = run;
+            if (i == n) on_total(run);
+            run += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -971,16 +925,16 @@ __device__ __forceinline__ long long next_success(const MapDev &m, int c, const 
     if (lo < j) lo = j;
     return (long long)lo;
 }
-// One thread per slot.  Pass 0 counts, writes start_hap and stashes the first XO_STASH positions of the slot at a
-// fixed stride; after the scan, xo_place_kernel moves the stash into the CSR (re-drawing only the rare longer lists
-// with pass 1's code) and converts positions to locus indices in the same sweep.
+// One thread per slot: counts the crossovers of the slot, writes start_hap and stashes the first XO_STASH positions at a
+// fixed stride; after the scan, xo_place_kernel moves the stash into the CSR (re-drawing only the rare longer lists)
+// and converts positions to locus indices in the same sweep.
 constexpr int XO_STASH = 4;
-template <bool FILL>
-__global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int gen, uint64_t slot_first, uint64_t n_slots,
-                                 uint32_t *__restrict__ count, const uint64_t *__restrict__ xo_off, uint32_t *__restrict__ xo_bp,
-                                 uint8_t *__restrict__ start_hap, uint32_t *__restrict__ stash = nullptr) {
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_slots; t += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t slot = slot_first + t;
+__global__ void sample_xo_kernel(Stream st, MapDev m, const StepState *__restrict__ ss, int n_chr, int pop, uint32_t *__restrict__ count,
+                                 uint8_t *__restrict__ start_hap, uint32_t *__restrict__ stash) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n_slots = ss->n_off * (uint64_t)n_chr * 2;
+    const int gen = ss->gen;
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t i;
     uint32_t cc;
     divmod_idx(slot >> 1, (uint32_t)n_chr, i, cc);
@@ -988,27 +942,28 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, int n_chr, int pop, int ge
     uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
     const double *T = m.T + r0 + c;
     uint32_t j = 0, blk = 0, n = 0;
-    uint64_t o = FILL ? xo_off[slot] : 0;
     for (;;) {
         uint32_t w[4];
         draw(st, P_XO, pop, gen, i, m.chr_id[c] * 2u + (uint32_t)gam, blk, w);
-        if (blk == 0 && !FILL) start_hap[slot] = (uint8_t)(w[3] & 1u);
+        if (blk == 0) start_hap[slot] = (uint8_t)(w[3] & 1u);
         blk++;
         if (j >= R) break;
         double v = (1.0 - u01(w[0], w[1])) * T[j];
         long long k = next_success(m, c, T, R, j, v);
         if (k < 0) break;
-        if (FILL) xo_bp[o + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
-        else if (stash && n < XO_STASH) stash[t * XO_STASH + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
+        if (n < XO_STASH) stash[slot * XO_STASH + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
         n++;
         j = (uint32_t)k + 1;
     }
-    if (!FILL) count[slot] = n;
+    count[slot] = n;
     }
 }
 // stash -> CSR (+ locus indices of the flips when the bit-packed rows are kept); slots longer than the stash re-draw
-__global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int pop, int gen, uint64_t n_slots, const uint64_t *__restrict__ xo_off,
+__global__ void xo_place_kernel(Stream st, MapDev m, Genome g, const StepState *__restrict__ ss, int n_chr, int pop, const uint64_t *__restrict__ xo_off,
                                 const uint32_t *__restrict__ stash, uint32_t *__restrict__ xo_bp, uint32_t *__restrict__ flips) {
+    if (ss->err & SE_FATAL) return;   // (also: more crossovers than the draw buffers hold — nothing is written)
+    const uint64_t n_slots = ss->n_off * (uint64_t)n_chr * 2;
+    const int gen = ss->gen;
     for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t o = xo_off[slot];
     const uint32_t cnt = (uint32_t)(xo_off[slot + 1] - o);
@@ -1044,15 +999,25 @@ __global__ void xo_place_kernel(Stream st, MapDev m, Genome g, int n_chr, int po
     }
     }
 }
+// the grand total of the crossover scan: n_xo, the interval count of the segment plan, and the capacity check
+struct XoTotal {
+    StepState *ss; uint64_t slots_per_ind; int dset;
+    __device__ __forceinline__ void operator()(uint64_t t) const {
+        ss->n_xo = t; ss->n_iv = t + ss->n_off * slots_per_ind;
+        if (t > ss->xo_cap) atomicOr(&ss->err, (uint32_t)SE_CAP_XO);
+        DrawCounts &d = ss->dc[dset];   // what the bulk stream will read, a generation behind
+        d.n_off = ss->n_off; d.n_xo = t; d.n_iv = ss->n_iv; d.fatal = ((ss->err & SE_FATAL) != 0) || t > ss->xo_cap;
+    }
+};
 
 // mutations: one thread per (offspring, chromosome)
 template <bool FILL>
-__global__ void sample_mut_kernel(Stream st, MapDev m, int n_chr, int pop, int gen, uint64_t first, uint64_t n_items,
-                                  uint32_t *__restrict__ count, const uint64_t *__restrict__ mut_off, uint32_t *__restrict__ mut_bp,
-                                  uint8_t *__restrict__ mut_gam) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_items) return;
-    uint64_t item = first + t;
+__global__ void sample_mut_kernel(Stream st, MapDev m, const StepState *__restrict__ ss, int n_chr, int pop, uint32_t *__restrict__ count,
+                                  const uint64_t *__restrict__ mut_off, uint32_t *__restrict__ mut_bp, uint8_t *__restrict__ mut_gam) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n_items = ss->n_off * (uint64_t)n_chr;
+    const int gen = ss->gen;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t i = item / (uint64_t)n_chr;
     int c = (int)(item % (uint64_t)n_chr);
     uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
@@ -1075,13 +1040,14 @@ __global__ void sample_mut_kernel(Stream st, MapDev m, int n_chr, int pop, int g
         j = (uint32_t)k + 1;
     }
     if (!FILL) count[item] = n;
+    }
 }
-__global__ void sex_kernel(Stream st, int pop, int gen, uint64_t first, uint64_t n, uint8_t *__restrict__ sex) {
+__global__ void sex_kernel(Stream st, int pop, int gen, uint64_t n, uint8_t *__restrict__ sex) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t w[4];
-    draw(st, P_SEX, pop, gen, first + i, 0, 0, w);
-    sex[first + i] = (uint8_t)((w[0] & 1u) + 1);
+    draw(st, P_SEX, pop, gen, i, 0, 0, w);
+    sex[i] = (uint8_t)((w[0] & 1u) + 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1089,10 +1055,13 @@ __global__ void sex_kernel(Stream st, int pop, int gen, uint64_t first, uint64_t
 // parity, append this generation's hits, toggle a locus only on its first hit in the lineage (the reference
 // looks positions up with std::find, :1218-1222/:2770-2774, so repeated hits do not toggle back).
 // One thread per offspring slot; pass 0 counts, pass 1 fills + applies.
+// An entry is a position in bp; bit 31 (HM_BAKED) marks a toggle that a re-based founder panel already holds
+// (ge_rebase_founders): it still counts as "seen" for the first-hit rule but is not applied again at materialisation.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t HM_BAKED = 0x80000000u;
 struct MutArgs {
     int n_chr;
-    uint64_t off_first, n_off;
+    const StepState *ss;
     const uint32_t *father, *mother;
     const uint64_t *xo_off; const uint32_t *xo_bp; const uint8_t *start_hap;
     const uint64_t *par_hm_off; const uint32_t *par_hm_bp;   // parent lists, slot (par*n_chr + c)*2 + h; may be null (empty)
@@ -1107,9 +1076,9 @@ __device__ __forceinline__ int parity_at(const MutArgs &a, uint64_t slot, uint32
 template <bool FILL>
 __global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *__restrict__ count, const uint64_t *__restrict__ hm_off,
                                       uint32_t *__restrict__ hm_bp, uint32_t *__restrict__ off_rows, uint32_t *__restrict__ cv_bits) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_off * a.n_chr * 2) return;
-    uint64_t slot = a.off_first * a.n_chr * 2 + t;
+    if (a.ss->err & SE_FATAL) return;
+    const uint64_t n_slots = a.ss->n_off * (uint64_t)a.n_chr * 2;
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t i = (slot >> 1) / (uint64_t)a.n_chr;
     int c = (int)((slot >> 1) % (uint64_t)a.n_chr), gam = (int)(slot & 1);
     uint32_t parent = gam ? a.mother[i] : a.father[i];
@@ -1120,11 +1089,10 @@ __global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *_
             uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2 + h;
             for (uint64_t e = a.par_hm_off[ps]; e < a.par_hm_off[ps + 1]; e++) {
                 uint32_t m = a.par_hm_bp[e];
-                if (parity_at(a, slot, m) == h) { if (FILL) hm_bp[o + n] = m; n++; }
+                if (parity_at(a, slot, m & ~HM_BAKED) == h) { if (FILL) hm_bp[o + n] = m; n++; }
             }
         }
     }
-    uint32_t n_inherited = n;
     if (a.mut_off) {
         uint64_t item = i * a.n_chr + c;
         for (uint64_t e = a.mut_off[item]; e < a.mut_off[item + 1]; e++) {
@@ -1133,7 +1101,7 @@ __global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *_
             if (m < a.cov_lo[c] || m >= a.cov_hi[c]) continue;
             if (FILL) {
                 bool seen = false;
-                for (uint32_t q = 0; q < n; q++) if (hm_bp[o + q] == m) { seen = true; break; }
+                for (uint32_t q = 0; q < n; q++) if ((hm_bp[o + q] & ~HM_BAKED) == m) { seen = true; break; }
                 hm_bp[o + n] = m;
                 if (!seen) {
                     if (off_rows) {
@@ -1155,29 +1123,59 @@ __global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *_
             n++;
         }
     }
-    (void)n_inherited;
     if (!FILL) count[slot] = n;
+    }
 }
 
-// couples -> offspring (reproduce :2402-2406, :2432-2485): offsets by exclusive scan of the family sizes
-__global__ void family_size_kernel(uint64_t n_couples, const uint8_t *__restrict__ inbreed, const int32_t *__restrict__ noff, uint32_t *__restrict__ cnt) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n_couples) cnt[k] = inbreed[k] ? 0u : (uint32_t)max(noff[k], 0);
+// ------------------------------------------------------------------------------------------------
+// couples -> offspring (reproduce :2394-2493).  Offsets = exclusive scan of the family sizes of the couples that may
+// marry (:2402-2406); one thread per couple then writes, for each of its children in birth order, the parents'
+// positions, the sex draw (:2472), the pedigree (:2471-2479) and the sibling-common effect (one draw per couple and
+// phenotype, :2417-2429, :2481-2484).
+// ------------------------------------------------------------------------------------------------
+__global__ void family_size_kernel(const StepState *__restrict__ ss, const uint8_t *__restrict__ inbreed, const int32_t *__restrict__ noff, uint32_t *__restrict__ cnt) {
+    const uint64_t n_couples = ss->n_couples;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_couples; k += (uint64_t)gridDim.x * blockDim.x)
+        cnt[k] = inbreed[k] ? 0u : (uint32_t)max(noff[k], 0);
 }
-__global__ void expand_couples_kernel(uint64_t n_couples, const uint64_t *__restrict__ off, const uint32_t *__restrict__ male,
-                                      const uint32_t *__restrict__ female, uint32_t *__restrict__ father, uint32_t *__restrict__ mother,
-                                      uint32_t *__restrict__ couple_of) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_couples) return;
-    for (uint64_t i = off[k]; i < off[k + 1]; i++) { father[i] = male[k]; mother[i] = female[k]; couple_of[i] = (uint32_t)k; }
-}
-__global__ void common_from_couples_kernel(Stream st, int pop, int gen, int f, double sd, uint64_t first, uint64_t n_off,
-                                           const uint32_t *__restrict__ couple_of, double *__restrict__ Cc) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_off) return;
-    double z0, z1;
-    normal2(st, P_COMMON, pop, gen, couple_of[first + t], (uint32_t)f, z0, z1);
-    Cc[first + t] = z0 * sd;
+struct OffspringTotal {   // grand total of the family-size scan
+    StepState *ss;
+    __device__ __forceinline__ void operator()(uint64_t t) const {
+        ss->n_off = t;
+        if (t == 0) atomicOr(&ss->err, (uint32_t)SE_NO_OFFSPRING);
+        if (t > ss->cap) atomicOr(&ss->err, (uint32_t)SE_CAP_OFFSPRING);
+    }
+};
+struct CommonArgs { int n_phen; uint64_t stride; double sd[8]; };   // sd[f] = sqrt(vc) or 0
+__global__ void offspring_kernel(Stream st, const StepState *__restrict__ ss, int pop, const uint64_t *__restrict__ fam_off, const uint32_t *__restrict__ male,
+                                 const uint32_t *__restrict__ female, const uint64_t *__restrict__ par_ids, CommonArgs ca, uint32_t *__restrict__ father,
+                                 uint32_t *__restrict__ mother, uint32_t *__restrict__ couple_of, uint8_t *__restrict__ sex, uint64_t *__restrict__ ids,
+                                 double *__restrict__ Cc, uint64_t *__restrict__ n_new /* size of the offspring generation */) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_new = (ss->err & SE_FATAL) ? 0 : ss->n_off;
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n_couples = ss->n_couples;
+    const int gen = ss->gen;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_couples; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i0 = fam_off[k], i1 = fam_off[k + 1];
+        if (i0 == i1) continue;
+        const uint32_t pm = male[k], pf = female[k];
+        const uint64_t *fa = par_ids + (uint64_t)pm * 7, *mo = par_ids + (uint64_t)pf * 7;
+        const uint64_t a0 = fa[0], a1 = fa[1], a2 = fa[2], b0 = mo[0], b1 = mo[1], b2 = mo[2];
+        double cm[8];
+        for (int f = 0; f < ca.n_phen; f++) {
+            cm[f] = 0.0;
+            if (ca.sd[f] > 0) { double z0, z1; normal2(st, P_COMMON, pop, gen, k, (uint32_t)f, z0, z1); cm[f] = z0 * ca.sd[f]; }
+        }
+        for (uint64_t i = i0; i < i1; i++) {
+            father[i] = pm; mother[i] = pf; couple_of[i] = (uint32_t)k;
+            uint32_t w[4];
+            draw(st, P_SEX, pop, gen, i, 0, 0, w);
+            sex[i] = (uint8_t)((w[0] & 1u) + 1);
+            uint64_t *d = ids + i * 7;
+            d[0] = i; d[1] = a0; d[2] = b0; d[3] = a1; d[4] = a2; d[5] = b1; d[6] = b2;
+            for (int f = 0; f < ca.n_phen; f++) Cc[(uint64_t)f * ca.stride + i] = cm[f];
+        }
+    }
 }
 
 }  // namespace gek

@@ -5,13 +5,16 @@
 // (U_i < selection_value_func_i) followed by uniform index draws (random mating) or by pairing the males and
 // females, both sorted by mating value, through the ranks of a bivariate-normal template (assortative).
 // So the scans here are stream compaction and offspring-offset prefix sums.
-// Sorting (mating values, template values, trim keys; n <= N/2 elements, < 1 % of a generation) uses
-// cub::DeviceRadixSort, which is stable — that is what fixes the tie order the oracle also uses.
+//
+// Nothing in the chain comes back to the host: list lengths, the couple count, the number of inbred couples and the
+// Poisson mean live in StepState (ge_kernels.cuh), every kernel loops up to the device-side count on a grid sized from
+// the capacity, and which sex list gets trimmed is decided on the device.  Sorting (mating values, template values,
+// trim keys) is a stable tile sort + rank-by-search merges written here; their stability fixes the tie order the oracle
+// also uses.
 #pragma once
 #include "ge_context.cuh"
 
 #include <cub/block/block_radix_sort.cuh>
-#include <cub/device/device_radix_sort.cuh>
 
 namespace gek {
 
@@ -22,149 +25,207 @@ __device__ __forceinline__ uint64_t sortable(double x) {  // monotone map double
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
-// thinning (:2105-2117 / :2186-2216): number of list entries individual i contributes, split by sex
-__global__ void thin_count_kernel(Stream st, int pop, int gen, uint64_t n, const uint8_t *__restrict__ sex, const double *__restrict__ svf,
-                                  int with_mm, double mm, uint32_t *__restrict__ cnt_m, uint32_t *__restrict__ cnt_f) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t w[4];
-    draw(st, P_THIN, pop, gen, i, 0, 0, w);
-    double r = u01(w[0], w[1]), r2 = u01(w[2], w[3]);
-    uint32_t c = 0;
-    if (r < svf[i]) c = (with_mm && r2 < mm) ? 2u : 1u;
-    cnt_m[i] = sex[i] == 1 ? c : 0u;
-    cnt_f[i] = sex[i] == 2 ? c : 0u;
+// thinning (:2105-2117 / :2186-2216): number of list entries individual i contributes — males in the low, females in
+// the high 32 bits, so ONE scan gives the offsets into both lists
+__global__ void thin_count_kernel(Stream st, const StepState *__restrict__ ss, int pop, const uint64_t *__restrict__ n_ind, const uint8_t *__restrict__ sex,
+                                  const double *__restrict__ svf, int with_mm, double mm, uint64_t *__restrict__ cnt) {
+    const uint64_t n = *n_ind;
+    const int gen = ss->gen;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4];
+        draw(st, P_THIN, pop, gen, i, 0, 0, w);
+        double r = u01(w[0], w[1]), r2 = u01(w[2], w[3]);
+        uint64_t c = 0;
+        if (r < svf[i]) c = (with_mm && r2 < mm) ? 2u : 1u;
+        cnt[i] = sex[i] == 1 ? c : (sex[i] == 2 ? c << 32 : 0ull);
+    }
 }
-__global__ void thin_fill_kernel(uint64_t n, const uint64_t *__restrict__ off, uint32_t *__restrict__ list) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    for (uint64_t k = off[i]; k < off[i + 1]; k++) list[k] = (uint32_t)i;
+// grand total of the thinning scan: list lengths, the couple count and the errors of :2125-2129 / :2226-2230
+struct ThinTotal {
+    StepState *ss; int random_mating;
+    __device__ __forceinline__ void operator()(uint64_t t) const {
+        const uint64_t n_m = t & 0xFFFFFFFFull, n_f = t >> 32;
+        ss->n_m = n_m; ss->n_f = n_f;
+        ss->n2 = n_m < n_f ? n_m : n_f;
+        ss->trim_which = n_f > n_m ? 1u : 0u;
+        ss->n_trim = n_m > n_f ? n_m - n_f : n_f - n_m;
+        ss->n_trim_list = (random_mating || n_m == n_f) ? 0 : (n_m > n_f ? n_m : n_f);   // what the trim's sort and scan run over
+        if (random_mating) {
+            ss->n_couples = ss->pop_size;
+            if (n_m == 0 || n_f == 0) atomicOr(&ss->err, (uint32_t)SE_NO_MATES_RM);
+            if (ss->pop_size > ss->couples_cap) atomicOr(&ss->err, (uint32_t)SE_CAP_COUPLES);
+        } else {
+            ss->n_couples = ss->n2;
+            if (ss->n2 == 0) atomicOr(&ss->err, (uint32_t)SE_NO_COUPLES);
+        }
+    }
+};
+__global__ void thin_fill_kernel(const uint64_t *__restrict__ n_ind, const uint64_t *__restrict__ off, uint32_t *__restrict__ list_m, uint32_t *__restrict__ list_f) {
+    const uint64_t n = *n_ind;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = off[i], b = off[i + 1];
+        for (uint32_t k = (uint32_t)a; k < (uint32_t)b; k++) list_m[k] = (uint32_t)i;
+        for (uint32_t k = (uint32_t)(a >> 32); k < (uint32_t)(b >> 32); k++) list_f[k] = (uint32_t)i;
+    }
 }
-__global__ void rm_pair_kernel(Stream st, int pop, int gen, uint64_t n_couples, const uint32_t *__restrict__ list_m, uint64_t n_m,
-                               const uint32_t *__restrict__ list_f, uint64_t n_f, uint32_t *__restrict__ male, uint32_t *__restrict__ female,
-                               uint8_t *__restrict__ inbreed, int32_t *__restrict__ noff) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_couples) return;
-    uint32_t w[4];
-    draw(st, P_RM_PAIR, pop, gen, k, 0, 0, w);
-    male[k] = list_m[((uint64_t)w[0] * n_m) >> 32];
-    female[k] = list_f[((uint64_t)w[1] * n_f) >> 32];
-    inbreed[k] = 0; noff[k] = 1;
+__global__ void rm_pair_kernel(Stream st, const StepState *__restrict__ ss, int pop, const uint32_t *__restrict__ list_m, const uint32_t *__restrict__ list_f,
+                               uint32_t *__restrict__ male, uint32_t *__restrict__ female, uint8_t *__restrict__ inbreed, int32_t *__restrict__ noff) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n_couples = ss->n_couples, n_m = ss->n_m, n_f = ss->n_f;
+    const int gen = ss->gen;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_couples; k += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4];
+        draw(st, P_RM_PAIR, pop, gen, k, 0, 0, w);
+        male[k] = list_m[((uint64_t)w[0] * n_m) >> 32];
+        female[k] = list_f[((uint64_t)w[1] * n_f) >> 32];
+        inbreed[k] = 0; noff[k] = 1;
+    }
 }
-__global__ void philox_keys_kernel(Stream st, uint32_t purpose, int pop, int gen, uint32_t sub, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    uint32_t w[4];
-    draw(st, purpose, pop, gen, k, sub, 0, w);
-    keys[k] = key64(w); idx[k] = (uint32_t)k;
+// trim of the longer sex list (:2233-2246): the n_trim entries with the smallest (Philox key, position) leave, survivors keep
+// their order.  Keys of the longer list (nothing when the lists are equal) ...
+__global__ void trim_keys_kernel(Stream st, const StepState *__restrict__ ss, int pop, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    const uint64_t n = ss->n_trim_list;
+    const uint32_t sub = ss->trim_which;
+    const int gen = ss->gen;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4];
+        draw(st, P_TRIM, pop, gen, k, sub, 0, w);
+        keys[k] = key64(w); idx[k] = (uint32_t)k;
+    }
 }
-__global__ void mark_kernel(uint64_t n_mark, const uint32_t *__restrict__ sorted_idx, uint32_t *__restrict__ keep /* preset to 1 */) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n_mark) keep[sorted_idx[k]] = 0;
+// ... and, after the stable sort, who stays: flag[position] = 0 for the first n_trim of the sorted order
+__global__ void trim_flag_kernel(const StepState *__restrict__ ss, const uint32_t *__restrict__ sorted_idx, uint32_t *__restrict__ flag) {
+    const uint64_t n = ss->n_trim_list, n_trim = ss->n_trim;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) flag[sorted_idx[k]] = k >= n_trim;
 }
-__global__ void fill_u32_kernel(uint32_t *__restrict__ x, uint64_t n, uint32_t v) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) x[k] = v;
-}
-__global__ void compact_kernel(uint64_t n, const uint32_t *__restrict__ keep, const uint64_t *__restrict__ off, const uint32_t *__restrict__ in, uint32_t *__restrict__ out) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n && keep[k]) out[off[k]] = in[k];
-}
-__global__ void mv_keys_kernel(uint64_t n, const uint32_t *__restrict__ list, const double *__restrict__ mv, uint64_t *__restrict__ keys) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) keys[k] = sortable(mv[list[k]]);
+
+// sort keys of one sex list by mating value (:2251-2252); the trimmed list is compacted on the way (survivors keep their order)
+__global__ void mv_keys_kernel(const StepState *__restrict__ ss, uint32_t which, const uint32_t *__restrict__ list, const uint32_t *__restrict__ flag,
+                               const uint64_t *__restrict__ keep_off, const double *__restrict__ mv, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n = which ? ss->n_f : ss->n_m;
+    const bool trimmed = ss->n_trim != 0 && ss->trim_which == which;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t o = k;
+        if (trimmed) { if (!flag[k]) continue; o = keep_off[k]; }
+        const uint32_t ind = list[k];
+        keys[o] = sortable(mv[ind]); vals[o] = ind;
+    }
 }
 // bivariate-normal template (ras_mvnorm, src/RasRandomNumber.cpp:15-53, with U = [[1,rho],[0,sqrt(1-rho^2)]])
-__global__ void template_kernel(Stream st, int pop, int gen, uint64_t n, double rho, double u11, uint64_t *__restrict__ k1, uint64_t *__restrict__ k2, uint32_t *__restrict__ idx) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double z0, z1;
-    normal2(st, P_TEMPLATE, pop, gen, i, 0, z0, z1);
-    k1[i] = sortable(z0);
-    k2[i] = sortable(z0 * rho + z1 * u11);
-    idx[i] = (uint32_t)i;
+__global__ void template_kernel(Stream st, const StepState *__restrict__ ss, int pop, uint64_t *__restrict__ k1, uint64_t *__restrict__ k2, uint32_t *__restrict__ idx) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n = ss->n2;
+    const int gen = ss->gen;
+    const double rho = ss->mat_cor, u11 = ss->u11;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double z0, z1;
+        normal2(st, P_TEMPLATE, pop, gen, i, 0, z0, z1);
+        k1[i] = sortable(z0);
+        k2[i] = sortable(z0 * rho + z1 * u11);
+        idx[i] = (uint32_t)i;
+    }
 }
-__global__ void rank_scatter_kernel(uint64_t n, const uint32_t *__restrict__ sorted_idx, uint32_t *__restrict__ rank) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) rank[sorted_idx[k]] = (uint32_t)k;
+__global__ void rank_scatter_kernel(const StepState *__restrict__ ss, const uint32_t *__restrict__ sorted_idx, uint32_t *__restrict__ rank) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n = ss->n2;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) rank[sorted_idx[k]] = (uint32_t)k;
 }
 // couple i = (male at rank(t1_i), female at rank(t2_i)) and the sib/cousin exclusion (:2296-2320)
-__global__ void pair_kernel(uint64_t n, const uint32_t *__restrict__ males, const uint32_t *__restrict__ females, const uint32_t *__restrict__ r1,
+__global__ void pair_kernel(StepState *__restrict__ ss, const uint32_t *__restrict__ males, const uint32_t *__restrict__ females, const uint32_t *__restrict__ r1,
                             const uint32_t *__restrict__ r2, const uint64_t *__restrict__ ids, int avoid_inbreeding, uint32_t *__restrict__ male,
-                            uint32_t *__restrict__ female, uint8_t *__restrict__ inbreed, uint32_t *__restrict__ inbreed_cnt) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t pm = males[r1[i]], pf = females[r2[i]];
-    male[i] = pm; female[i] = pf;
-    uint8_t ib = 0;
-    if (avoid_inbreeding) {
-        const uint64_t *a = ids + (uint64_t)pm * 7, *b = ids + (uint64_t)pf * 7;
-        bool sib = a[1] == b[1];
-        bool cousin = (a[3] == b[3] || a[3] == b[5] || a[5] == b[3] || a[5] == b[5] || a[4] == b[4] || a[4] == b[6] || a[6] == b[4] || a[6] == b[6]);
-        ib = sib || cousin;
+                            uint32_t *__restrict__ female, uint8_t *__restrict__ inbreed) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n = ss->n2;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t pm = males[r1[i]], pf = females[r2[i]];
+        male[i] = pm; female[i] = pf;
+        uint8_t ib = 0;
+        if (avoid_inbreeding) {
+            const uint64_t *a = ids + (uint64_t)pm * 7, *b = ids + (uint64_t)pf * 7;
+            bool sib = a[1] == b[1];
+            bool cousin = (a[3] == b[3] || a[3] == b[5] || a[5] == b[3] || a[5] == b[5] || a[4] == b[4] || a[4] == b[6] || a[6] == b[4] || a[6] == b[6]);
+            ib = sib || cousin;
+            if (ib) atomicAdd((unsigned long long *)&ss->n_inbreed, 1ull);   // rare
+        }
+        inbreed[i] = ib;
     }
-    inbreed[i] = ib;
-    inbreed_cnt[i] = ib;
 }
-// exact Poisson(lam): sum of independent Poisson(<=32) chunks, each by sequential-search inversion (ras_rpois, src/RasRandomNumber.cpp:57-67)
-__global__ void poisson_kernel(Stream st, int pop, int gen, uint64_t n, double lam, int32_t *__restrict__ noff) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int total = 0; uint32_t blk = 0; double rem = lam;
-    while (rem > 0) {
-        double l = rem > 32.0 ? 32.0 : rem;
-        rem -= l;
+// family sizes.  Poisson (:2329-2337): exact Poisson(lam), lam = pop_size / marriageable couples, as a sum of independent
+// Poisson(<=32) chunks, each by sequential-search inversion (ras_rpois, src/RasRandomNumber.cpp:57-67).  Fixed (:2338-2355): floor.
+__global__ void family_kernel(Stream st, StepState *__restrict__ ss, int pop, int poisson, int32_t *__restrict__ noff) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n = ss->n2, n_ok = n - ss->n_inbreed;
+    if (n_ok == 0) {   // every couple is inbred
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ss->err, (uint32_t)SE_ALL_INBRED);
+        return;
+    }
+    const int gen = ss->gen;
+    const double lam = (double)ss->pop_size / (double)n_ok;
+    const int32_t nfix = (int32_t)floor((double)ss->pop_size / (double)n_ok);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (!poisson) { noff[i] = nfix; continue; }
+        int total = 0; uint32_t blk = 0; double rem = lam;
+        while (rem > 0) {
+            double l = rem > 32.0 ? 32.0 : rem;
+            rem -= l;
+            uint32_t w[4];
+            draw(st, P_POISSON, pop, gen, i, 0, blk++, w);
+            double u = u01(w[0], w[1]);
+            double pk = exp(-l), F = pk; int k = 0;
+            while (u >= F && k < 400) { k++; pk *= l / (double)k; F += pk; }
+            total += k;
+        }
+        noff[i] = total;
+    }
+}
+// fixed family size: the remainder goes to distinct random couples that may marry (the reference indexes an empty list here when
+// --avoid_inbreeding is on, :2314-2353; this is its evident intent): couples by Philox key, inbred ones last ...
+__global__ void remainder_keys_kernel(Stream st, const StepState *__restrict__ ss, int pop, const uint8_t *__restrict__ inbreed, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n = ss->n2;
+    const int gen = ss->gen;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t w[4];
-        draw(st, P_POISSON, pop, gen, i, 0, blk++, w);
-        double u = u01(w[0], w[1]);
-        double pk = exp(-l), F = pk; int k = 0;
-        while (u >= F && k < 400) { k++; pk *= l / (double)k; F += pk; }
-        total += k;
+        draw(st, P_REMAINDER, pop, gen, i, 0, 0, w);
+        keys[i] = inbreed[i] ? 0xFFFFFFFFFFFFFFFFull : key64(w);
+        idx[i] = (uint32_t)i;
     }
-    noff[i] = total;
 }
-__global__ void fixed_family_kernel(uint64_t n, int32_t nfix, int32_t *__restrict__ noff) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) noff[i] = nfix;
-}
-__global__ void remainder_keys_kernel(Stream st, int pop, int gen, uint64_t n, const uint8_t *__restrict__ inbreed, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t w[4];
-    draw(st, P_REMAINDER, pop, gen, i, 0, 0, w);
-    keys[i] = inbreed[i] ? 0xFFFFFFFFFFFFFFFFull : key64(w);
-    idx[i] = (uint32_t)i;
-}
-__global__ void remainder_add_kernel(uint64_t n_add, const uint32_t *__restrict__ sorted_idx, const uint8_t *__restrict__ inbreed, int32_t *__restrict__ noff) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n_add && !inbreed[sorted_idx[k]]) noff[sorted_idx[k]]++;
+// ... and the first `remainder` of the sorted order get one more child
+__global__ void remainder_add_kernel(const StepState *__restrict__ ss, const uint32_t *__restrict__ sorted_idx, const uint8_t *__restrict__ inbreed, int32_t *__restrict__ noff) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n_ok = ss->n2 - ss->n_inbreed;
+    if (n_ok == 0) return;
+    const uint64_t nfix = (uint64_t)floor((double)ss->pop_size / (double)n_ok);
+    const uint64_t remain = ss->pop_size - nfix * n_ok;
+    const uint64_t n_add = remain < n_ok ? remain : n_ok;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_add; k += (uint64_t)gridDim.x * blockDim.x)
+        if (!inbreed[sorted_idx[k]]) noff[sorted_idx[k]]++;
 }
 
 }  // namespace gek
 
-static void mate_release(MateScratch &m) {
-    for (Buf *b : {&m.fam_off, &m.keep, &m.keys_a, &m.keys_b, &m.idx_a, &m.idx_b, &m.list_m, &m.list_f, &m.t1, &m.t2, &m.rank1, &m.rank2,
-                   &m.tmp_sort, &m.counters, &m.mv_m, &m.mv_f})
-        if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Small stable sorts.  The mating chain sorts <= N/2 (key, value) pairs five times per generation and sits on the dependency
-// cycle mating -> draws -> CV planes -> genetic values -> phenotypes -> selection -> mating: at these sizes
-// cub::DeviceRadixSort is ten dependent launches (histogram, scan, eight onesweep passes) of a few microseconds each, i.e. pure
-// launch latency.  Up to SMALL_SORT_MAX pairs are sorted in ONE launch (a tile of 4096 fits one CTA: cub::BlockRadixSort in
-// shared memory) or TWO (tiles sorted by one CTA each, then every element finds its final rank by binary searches of the other
-// tiles: rank = position in its tile + #(<= key) in earlier tiles + #(< key) in later tiles, which keeps the sort stable).
+// Stable sorts of (uint64 key, uint32 value) pairs with the element count on the device.  The mating chain sorts <= N/2 pairs
+// five times per generation and sits on the dependency cycle mating -> draws -> CV planes -> genetic values -> phenotypes ->
+// selection -> mating: a library radix sort is ten dependent launches and wants its count on the host.
+// Here: tiles of 4096 pairs are sorted by one CTA each (cub::BlockRadixSort in shared memory), then merged by rank — every
+// element finds its final position by binary searches of the other runs of its group (up to 32 runs per level):
+// rank = position in its run + #(<= key) in earlier runs + #(< key) in later runs, which keeps the sort stable.
+// One launch up to 4096 pairs, two up to 131 072, three up to 4 194 304.
 // ------------------------------------------------------------------------------------------------
 namespace gek {
 constexpr int SS_THREADS = 512, SS_ITEMS = 8, SS_TILE = SS_THREADS * SS_ITEMS;
-constexpr uint64_t SMALL_SORT_MAX = 32ull * SS_TILE;   // 131 072 pairs: 31 searches of 12 steps per element at most
+constexpr uint32_t SS_GROUP = 32;
 
 __global__ void __launch_bounds__(SS_THREADS) small_sort_tile_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
-                                                                     uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t n) {
+                                                                     uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, DevN dn) {
     using Sort = cub::BlockRadixSort<uint64_t, SS_THREADS, SS_ITEMS, uint32_t>;
     __shared__ typename Sort::TempStorage tmp;
+    const uint32_t n = (uint32_t)dn.get();
     const uint32_t base = blockIdx.x * SS_TILE;
+    if (base >= n) return;
     uint64_t k[SS_ITEMS];
     uint32_t v[SS_ITEMS];
 #pragma unroll
@@ -181,188 +242,149 @@ __global__ void __launch_bounds__(SS_THREADS) small_sort_tile_kernel(const uint6
     }
 }
 
+// sorted runs of run_len pairs -> sorted runs of run_len * SS_GROUP pairs
 __global__ void small_sort_merge_kernel(const uint64_t *__restrict__ tk, const uint32_t *__restrict__ tv, uint64_t *__restrict__ kout,
-                                        uint32_t *__restrict__ vout, uint32_t n) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const uint64_t key = tk[e];
-    const uint32_t mine = e / SS_TILE, n_tiles = (n + SS_TILE - 1) / SS_TILE;
-    uint32_t rank = e - mine * SS_TILE;
-    for (uint32_t b = 0; b < n_tiles; b++) {
-        if (b == mine) continue;
-        const uint64_t *t = tk + (uint64_t)b * SS_TILE;
-        uint32_t lo = 0, hi = min((uint32_t)SS_TILE, n - b * SS_TILE);
-        if (b < mine) { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(t + mid) <= key) lo = mid + 1; else hi = mid; } }
-        else { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(t + mid) < key) lo = mid + 1; else hi = mid; } }
-        rank += lo;
+                                        uint32_t *__restrict__ vout, DevN dn, uint32_t run_len) {
+    const uint32_t n = (uint32_t)dn.get();
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint64_t key = tk[e];
+        const uint32_t mine = e / run_len, n_runs = (n + run_len - 1) / run_len;
+        const uint32_t g0 = mine / SS_GROUP * SS_GROUP, g1 = min(g0 + SS_GROUP, n_runs);
+        uint32_t rank = e - mine * run_len;
+        for (uint32_t b = g0; b < g1; b++) {
+            if (b == mine) continue;
+            const uint64_t *t = tk + (uint64_t)b * run_len;
+            uint32_t lo = 0, hi = min(run_len, n - b * run_len);
+            if (b < mine) { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(t + mid) <= key) lo = mid + 1; else hi = mid; } }
+            else { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(t + mid) < key) lo = mid + 1; else hi = mid; } }
+            rank += lo;
+        }
+        kout[(uint64_t)g0 * run_len + rank] = key;
+        vout[(uint64_t)g0 * run_len + rank] = tv[e];
     }
-    kout[rank] = key;
-    vout[rank] = tv[e];
 }
 }  // namespace gek
 
-// stable sort of (uint64 key, uint32 value) pairs: keys_in/vals_in -> keys_out/vals_out
-static int sort_pairs_on(ge_ctx *ctx, cudaStream_t st, Buf &tmp, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n) {
-    if (n == 0) return GE_OK;
-    if (n <= SMALL_SORT_MAX && !ctx->cub_sorts) {
-        const unsigned tiles = nblk(n, SS_TILE);
-        if (tiles == 1) {
-            small_sort_tile_kernel<<<1, SS_THREADS, 0, st>>>(kin, vin, kout, vout, (uint32_t)n);
-            return ctx->check_launch("small_sort_tile");
-        }
-        GE_TRY(ctx->ensure(tmp, n * 12 + 16));
-        uint64_t *tk = tmp.as<uint64_t>();
-        uint32_t *tv = reinterpret_cast<uint32_t *>(tk + n);
-        small_sort_tile_kernel<<<tiles, SS_THREADS, 0, st>>>(kin, vin, tk, tv, (uint32_t)n);
-        GE_TRY(ctx->check_launch("small_sort_tile"));
-        small_sort_merge_kernel<<<nblk(n, 256), 256, 0, st>>>(tk, tv, kout, vout, (uint32_t)n);
-        return ctx->check_launch("small_sort_merge");
+constexpr uint64_t SORT_MAX = (uint64_t)gek::SS_TILE * gek::SS_GROUP * gek::SS_GROUP;   // 4 194 304 pairs
+
+// keys_in/vals_in -> keys_out/vals_out; n on the device, n_bound (host) sizes the grids and the scratch
+static int sort_pairs_on(ge_ctx *ctx, cudaStream_t st, Buf &tmp, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, DevN n, uint64_t n_bound) {
+    if (n_bound == 0) return GE_OK;
+    if (n_bound > SORT_MAX) return fail(GE_ERR_UNSUPPORTED, "more than 4 194 304 list entries to sort (capacity above 8 388 608 individuals)");
+    const unsigned tiles = nblk(n_bound, SS_TILE);
+    if (tiles == 1) {
+        small_sort_tile_kernel<<<1, SS_THREADS, 0, st>>>(kin, vin, kout, vout, n);
+        return ctx->check_launch("small_sort_tile");
     }
-    size_t bytes = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 64, st));
-    GE_TRY(ctx->ensure(tmp, bytes));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, 64, st));
-    ctx->launches += 8;  // radix passes of the library sort (approximate, only for the launch counter)
+    GE_TRY(ctx->ensure(tmp, 2 * (n_bound * 12 + 16)));
+    uint64_t *ak = tmp.as<uint64_t>(), *bk = ak + n_bound;
+    uint32_t *av = reinterpret_cast<uint32_t *>(bk + n_bound), *bv = av + n_bound;
+    const bool two_levels = tiles > SS_GROUP;
+    small_sort_tile_kernel<<<tiles, SS_THREADS, 0, st>>>(kin, vin, ak, av, n);
+    GE_TRY(ctx->check_launch("small_sort_tile"));
+    const unsigned mgrid = (unsigned)std::min<uint64_t>(nblk(n_bound, 256), 65535);
+    small_sort_merge_kernel<<<mgrid, 256, 0, st>>>(ak, av, two_levels ? bk : kout, two_levels ? bv : vout, n, SS_TILE);
+    GE_TRY(ctx->check_launch("small_sort_merge"));
+    if (two_levels) {
+        small_sort_merge_kernel<<<mgrid, 256, 0, st>>>(bk, bv, kout, vout, n, SS_TILE * SS_GROUP);
+        GE_TRY(ctx->check_launch("small_sort_merge"));
+    }
     return GE_OK;
 }
-static int sort_pairs(ge_ctx *ctx, MateScratch &M, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n) {
-    return sort_pairs_on(ctx, ctx->stream, M.tmp_sort, kin, kout, vin, vout, n);
+
+static void mate_release(ge_ctx *ctx, MateScratch &m) {
+    for (Buf *b : {&m.fam_off, &m.keep, &m.keep_off, &m.keys_a, &m.keys_b, &m.idx_a, &m.idx_b, &m.list_m, &m.list_f, &m.t1, &m.t2, &m.rank1, &m.rank2, &m.tmp_sort})
+        ctx->release(*b);
 }
 
-// thinning + compaction of one sex list; returns list length on the host
-static int thin_lists(ge_ctx *ctx, int pop, int gen, bool with_mm, uint64_t *n_m, uint64_t *n_f) {
-    PopDev &P = ctx->pop[pop];
-    GenState &S = P.st[P.cur];
-    MateScratch &M = P.mate;
-    uint64_t n = S.n;
-    cudaStream_t st = ctx->stream;
-    GE_TRY(ctx->ensure(M.keep, (n + 1) * 4)); GE_TRY(ctx->ensure(M.rank1, (n + 1) * 4));  // cnt_m, cnt_f
-    GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8));  // offsets
-    thin_count_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->rng, pop, gen, n, S.sex.as<uint8_t>(), S.svf.as<double>(), with_mm, P.MM, M.keep.as<uint32_t>(), M.rank1.as<uint32_t>());
-    GE_TRY(ctx->check_launch("thin_count"));
-    GE_TRY(ctx->exclusive_scan(M.keep.as<uint32_t>(), n, M.keys_a.as<uint64_t>(), nullptr));
-    GE_TRY(ctx->exclusive_scan(M.rank1.as<uint32_t>(), n, M.keys_b.as<uint64_t>(), nullptr));
-    // both list lengths (the totals sit at out[n]) in one host read-back
-    CUDA_TRY(cudaMemcpyAsync(n_m, M.keys_a.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(n_f, M.keys_b.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    GE_TRY(ctx->ensure(M.list_m, std::max<uint64_t>(*n_m, 1) * 4)); GE_TRY(ctx->ensure(M.list_f, std::max<uint64_t>(*n_f, 1) * 4));
-    thin_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, M.keys_a.as<uint64_t>(), M.list_m.as<uint32_t>());
-    GE_TRY(ctx->check_launch("thin_fill"));
-    thin_fill_kernel<<<nblk(n, 256), 256, 0, st>>>(n, M.keys_b.as<uint64_t>(), M.list_f.as<uint32_t>());
-    return ctx->check_launch("thin_fill");
-}
-
+// ------------------------------------------------------------------------------------------------
+// the mating chain of one population, queued on the control stream (and the four sort lanes); see StepState for what it leaves
+// ------------------------------------------------------------------------------------------------
 static int ensure_couples(ge_ctx *ctx, PopDev &P, uint64_t n) {
-    GE_TRY(ctx->ensure(P.c_male, std::max<uint64_t>(n, 1) * 4)); GE_TRY(ctx->ensure(P.c_female, std::max<uint64_t>(n, 1) * 4));
-    GE_TRY(ctx->ensure(P.c_inbreed, std::max<uint64_t>(n, 1))); GE_TRY(ctx->ensure(P.c_noff, std::max<uint64_t>(n, 1) * 4));
-    return GE_OK;
+    if (n <= P.couples_cap) return GE_OK;
+    GE_TRY(ctx->ensure(P.c_male, n * 4)); GE_TRY(ctx->ensure(P.c_female, n * 4));
+    GE_TRY(ctx->ensure(P.c_inbreed, n)); GE_TRY(ctx->ensure(P.c_noff, n * 4));
+    GE_TRY(ctx->ensure(P.cnt32, (std::max<uint64_t>(n, ctx->cfg.capacity * ctx->cfg.n_chr * 2) + 1) * 4));
+    GE_TRY(ctx->ensure(P.mate.fam_off, (n + 1) * 8));
+    P.couples_cap = n;
+    P.hs.couples_cap = n;
+    ctx->graph_epoch++;
+    return ctx->push_state(P, offsetof(StepState, couples_cap), 8);
 }
 
-// remove the n_remove entries with the smallest (Philox key, position); survivors keep their order (:2233-2246)
-static int trim_list(ge_ctx *ctx, int pop, int gen, Buf &list, uint64_t n, uint64_t n_remove, uint32_t sub) {
-    PopDev &P = ctx->pop[pop];
-    MateScratch &M = P.mate;
-    cudaStream_t st = ctx->stream;
-    GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8));
-    GE_TRY(ctx->ensure(M.idx_a, n * 4)); GE_TRY(ctx->ensure(M.idx_b, n * 4)); GE_TRY(ctx->ensure(M.keep, (n + 1) * 4));
-    philox_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->rng, P_TRIM, pop, gen, sub, n, M.keys_a.as<uint64_t>(), M.idx_a.as<uint32_t>());
-    GE_TRY(ctx->check_launch("trim_keys"));
-    GE_TRY(sort_pairs(ctx, M, M.keys_a.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n));
-    fill_u32_kernel<<<nblk(n, 256), 256, 0, st>>>(M.keep.as<uint32_t>(), n, 1u);
-    GE_TRY(ctx->check_launch("fill"));
-    mark_kernel<<<nblk(n_remove, 256), 256, 0, st>>>(n_remove, M.idx_b.as<uint32_t>(), M.keep.as<uint32_t>());
-    GE_TRY(ctx->check_launch("mark"));
-    GE_TRY(ctx->exclusive_scan(M.keep.as<uint32_t>(), n, M.keys_a.as<uint64_t>(), nullptr));
-    compact_kernel<<<nblk(n, 256), 256, 0, st>>>(n, M.keep.as<uint32_t>(), M.keys_a.as<uint64_t>(), list.as<uint32_t>(), M.idx_a.as<uint32_t>());
-    GE_TRY(ctx->check_launch("compact"));
-    CUDA_TRY(cudaMemcpyAsync(list.p, M.idx_a.p, (n - n_remove) * 4, cudaMemcpyDeviceToDevice, st));
-    return GE_OK;
-}
-
-// sort a list of individuals by mating value, ascending, stable (:2251-2252), on one sort lane
-static int sort_by_mv(ge_ctx *ctx, int pop, Buf &list, uint64_t n, SortLane &L) {
-    PopDev &P = ctx->pop[pop];
-    GenState &S = P.st[P.cur];
-    GE_TRY(ctx->ensure(L.keys_in, (n + 1) * 8)); GE_TRY(ctx->ensure(L.keys_out, (n + 1) * 8)); GE_TRY(ctx->ensure(L.vals_out, (n + 1) * 4));
-    mv_keys_kernel<<<nblk(n, 256), 256, 0, L.s>>>(n, list.as<uint32_t>(), S.mv.as<double>(), L.keys_in.as<uint64_t>());
-    GE_TRY(ctx->check_launch("mv_keys"));
-    GE_TRY(sort_pairs_on(ctx, L.s, L.tmp, L.keys_in.as<uint64_t>(), L.keys_out.as<uint64_t>(), list.as<uint32_t>(), L.vals_out.as<uint32_t>(), n));
-    CUDA_TRY(cudaMemcpyAsync(list.p, L.vals_out.p, n * 4, cudaMemcpyDeviceToDevice, L.s));
-    return GE_OK;
-}
-// rank of every template value of one column: sort (key, index) and scatter the positions
-static int rank_column(ge_ctx *ctx, const uint64_t *keys, const uint32_t *idx, uint32_t *rank, uint64_t n, SortLane &L) {
-    GE_TRY(ctx->ensure(L.keys_out, (n + 1) * 8)); GE_TRY(ctx->ensure(L.vals_out, (n + 1) * 4));
-    GE_TRY(sort_pairs_on(ctx, L.s, L.tmp, keys, L.keys_out.as<uint64_t>(), idx, L.vals_out.as<uint32_t>(), n));
-    rank_scatter_kernel<<<nblk(n, 256), 256, 0, L.s>>>(n, L.vals_out.as<uint32_t>(), rank);
-    return ctx->check_launch("rank_scatter");
-}
-
-static int mate_philox(ge_ctx *ctx, int pop, int gen, const ge_gen_params &gp) {
+static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp) {
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     MateScratch &M = P.mate;
     cudaStream_t st = ctx->stream;
-    uint64_t n_m = 0, n_f = 0;
-    if (S.n == 0) return fail(GE_ERR_INVALID, "empty population");
-    GE_TRY(thin_lists(ctx, pop, gen, !P.RM, &n_m, &n_f));
+    StepState *ss = P.d_ss;
+    const uint64_t cap = ctx->cfg.capacity;
+    const bool with_mm = !P.RM;
+    const uint64_t lb = (with_mm && P.MM > 0 ? 2 : 1) * cap;        // list entries at most (a --MM duplicate is a second entry)
+    const unsigned g_ind = ctx->grid_for(cap, 256);
+    GE_TRY(ctx->ensure(M.keys_a, (cap + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (lb + 1) * 8));
+    GE_TRY(ctx->ensure(M.list_m, lb * 4)); GE_TRY(ctx->ensure(M.list_f, lb * 4));
+    // who may mate: thinning counts, one scan for both sexes, the two lists
+    thin_count_kernel<<<g_ind, 256, 0, st>>>(ctx->rng, ss, pop, S.d_n, S.sex.as<uint8_t>(), S.svf.as<double>(), with_mm, P.MM, M.keys_a.as<uint64_t>());
+    GE_TRY(ctx->check_launch("thin_count"));
+    GE_TRY(ctx->scan(st, M.keys_a.as<uint64_t>(), devn(S.d_n), cap, M.keys_b.as<uint64_t>(), ThinTotal{ss, P.RM ? 1 : 0}));
+    thin_fill_kernel<<<g_ind, 256, 0, st>>>(S.d_n, M.keys_b.as<uint64_t>(), M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>());
+    GE_TRY(ctx->check_launch("thin_fill"));
     if (P.RM) {  // random_mate :2090-2157
-        if (n_m == 0 || n_f == 0) return fail(GE_ERR_NO_MATES, "Error: No one can marry, num_males_mate=" + std::to_string(n_m) + ", num_females_mate=" + std::to_string(n_f));
-        uint64_t nc = gp.pop_size;
-        GE_TRY(ensure_couples(ctx, P, nc));
-        rm_pair_kernel<<<nblk(nc, 256), 256, 0, st>>>(ctx->rng, pop, gen, nc, M.list_m.as<uint32_t>(), n_m, M.list_f.as<uint32_t>(), n_f, P.c_male.as<uint32_t>(),
-                                                      P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
-        GE_TRY(ctx->check_launch("rm_pair"));
-        P.n_couples = nc;
-        return GE_OK;
+        GE_TRY(ensure_couples(ctx, P, std::max<uint64_t>(gp.pop_size, 1)));
+        rm_pair_kernel<<<ctx->grid_for(gp.pop_size, 256), 256, 0, st>>>(ctx->rng, ss, pop, M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>(), P.c_male.as<uint32_t>(),
+                                                                        P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
+        return ctx->check_launch("rm_pair");
     }
     // assort_mate :2167-2360
-    uint64_t n2 = std::min(n_m, n_f);
-    if (n2 == 0) return fail(GE_ERR_NO_MATES, "Error: couples=0, num_males_mate=" + std::to_string(n_m) + ", num_females_mate=" + std::to_string(n_f));
-    if (n_m > n_f) GE_TRY(trim_list(ctx, pop, gen, M.list_m, n_m, n_m - n_f, 0));
-    else if (n_f > n_m) GE_TRY(trim_list(ctx, pop, gen, M.list_f, n_f, n_f - n_m, 1));
-    // template values first, then the four independent sorts side by side on the sort lanes
-    GE_TRY(ctx->ensure(M.t1, n2 * 8)); GE_TRY(ctx->ensure(M.t2, n2 * 8)); GE_TRY(ctx->ensure(M.idx_a, n2 * 4)); GE_TRY(ctx->ensure(M.idx_b, n2 * 4));
-    GE_TRY(ctx->ensure(M.keys_b, (n2 + 1) * 8)); GE_TRY(ctx->ensure(M.rank1, (n2 + 1) * 4)); GE_TRY(ctx->ensure(M.rank2, (n2 + 1) * 4));
-    double rho = gp.mat_cor, u11 = std::sqrt(1.0 - rho * rho);
-    template_kernel<<<nblk(n2, 256), 256, 0, st>>>(ctx->rng, pop, gen, n2, rho, u11, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>());
+    const uint64_t cb = lb / 2 + 1;                                  // couples at most: min(n_m, n_f)
+    const unsigned g_list = ctx->grid_for(lb, 256), g_c = ctx->grid_for(cb, 256);
+    GE_TRY(ensure_couples(ctx, P, cb));
+    GE_TRY(ctx->ensure(M.t1, lb * 8)); GE_TRY(ctx->ensure(M.t2, lb * 8)); GE_TRY(ctx->ensure(M.idx_a, lb * 4)); GE_TRY(ctx->ensure(M.idx_b, lb * 4));
+    GE_TRY(ctx->ensure(M.keep, (lb + 1) * 4)); GE_TRY(ctx->ensure(M.keep_off, (lb + 1) * 8));
+    GE_TRY(ctx->ensure(M.rank1, cb * 4)); GE_TRY(ctx->ensure(M.rank2, cb * 4));
+    const uint64_t *d_trim_len = &ss->n_trim_list;
+    // trim the longer list: Philox keys, stable sort, flags, offsets (all of it idles when the lists are equal)
+    trim_keys_kernel<<<g_list, 256, 0, st>>>(ctx->rng, ss, pop, M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>());
+    GE_TRY(ctx->check_launch("trim_keys"));
+    GE_TRY(sort_pairs_on(ctx, st, M.tmp_sort, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), devn(d_trim_len), lb));
+    trim_flag_kernel<<<g_list, 256, 0, st>>>(ss, M.idx_b.as<uint32_t>(), M.keep.as<uint32_t>());
+    GE_TRY(ctx->check_launch("trim_flag"));
+    GE_TRY(ctx->scan(st, M.keep.as<uint32_t>(), devn(d_trim_len), lb, M.keep_off.as<uint64_t>(), NoTotal{}));
+    // template values, then the four independent sorts side by side on the sort lanes
+    template_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>());
     GE_TRY(ctx->check_launch("template"));
     GE_TRY(ctx->fork_lanes());
-    GE_TRY(sort_by_mv(ctx, pop, M.list_m, n2, ctx->lane[0]));
-    GE_TRY(sort_by_mv(ctx, pop, M.list_f, n2, ctx->lane[1]));
-    GE_TRY(rank_column(ctx, M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.rank1.as<uint32_t>(), n2, ctx->lane[2]));
-    GE_TRY(rank_column(ctx, M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.rank2.as<uint32_t>(), n2, ctx->lane[3]));
-    GE_TRY(ctx->join_lanes());
-    GE_TRY(ensure_couples(ctx, P, n2));
-    GE_TRY(ctx->ensure(M.keep, (n2 + 1) * 4)); GE_TRY(ctx->ensure(M.keys_a, (n2 + 1) * 8));
-    pair_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>(), M.rank1.as<uint32_t>(), M.rank2.as<uint32_t>(), S.ids.as<uint64_t>(),
-                                               P.avoid_inbreeding, P.c_male.as<uint32_t>(), P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), M.keep.as<uint32_t>());
-    GE_TRY(ctx->check_launch("pair"));
-    uint64_t n_inbreed = 0;
-    if (P.avoid_inbreeding) GE_TRY(ctx->exclusive_scan(M.keep.as<uint32_t>(), n2, M.keys_a.as<uint64_t>(), &n_inbreed));
-    if (n2 == n_inbreed) return fail(GE_ERR_NO_MATES, "every couple is inbred");
-    if (gp.offspring_dist == 'p' || gp.offspring_dist == 'P') {  // :2329-2337
-        double lam = (double)gp.pop_size / (double)(n2 - n_inbreed);
-        poisson_kernel<<<nblk(n2, 256), 256, 0, st>>>(ctx->rng, pop, gen, n2, lam, P.c_noff.as<int32_t>());
-        GE_TRY(ctx->check_launch("poisson"));
-    } else {  // :2338-2355
-        int nfix = (int)std::floor((double)gp.pop_size / (double)(n2 - n_inbreed));
-        uint64_t remain = gp.pop_size - (uint64_t)nfix * (n2 - n_inbreed);
-        fixed_family_kernel<<<nblk(n2, 256), 256, 0, st>>>(n2, nfix, P.c_noff.as<int32_t>());
-        GE_TRY(ctx->check_launch("fixed_family"));
-        if (remain) {
-            // the remainder goes to distinct random couples that may marry (the reference indexes an empty
-            // list here when --avoid_inbreeding is on, :2314-2353; this is its evident intent)
-            remainder_keys_kernel<<<nblk(n2, 256), 256, 0, st>>>(ctx->rng, pop, gen, n2, P.c_inbreed.as<uint8_t>(), M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>());
-            GE_TRY(ctx->check_launch("remainder_keys"));
-            GE_TRY(sort_pairs(ctx, M, M.t1.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2));
-            uint64_t n_add = std::min(remain, n2 - n_inbreed);
-            remainder_add_kernel<<<nblk(n_add, 256), 256, 0, st>>>(n_add, M.idx_b.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
-            GE_TRY(ctx->check_launch("remainder_add"));
-        }
+    const DevN n2 = devn(&ss->n2);
+    for (int w = 0; w < 2; w++) {   // males, females by mating value
+        SortLane &L = ctx->lane[w];
+        GE_TRY(ctx->ensure(L.keys_in, cb * 8)); GE_TRY(ctx->ensure(L.vals_in, cb * 4)); GE_TRY(ctx->ensure(L.keys_out, cb * 8)); GE_TRY(ctx->ensure(L.vals_out, cb * 4));
+        mv_keys_kernel<<<g_list, 256, 0, L.s>>>(ss, (uint32_t)w, (w ? M.list_f : M.list_m).as<uint32_t>(), M.keep.as<uint32_t>(), M.keep_off.as<uint64_t>(), S.mv.as<double>(),
+                                                L.keys_in.as<uint64_t>(), L.vals_in.as<uint32_t>());
+        GE_TRY(ctx->check_launch("mv_keys"));
+        GE_TRY(sort_pairs_on(ctx, L.s, L.tmp, L.keys_in.as<uint64_t>(), L.keys_out.as<uint64_t>(), L.vals_in.as<uint32_t>(), L.vals_out.as<uint32_t>(), n2, cb));
     }
-    P.n_couples = n2;
+    for (int w = 0; w < 2; w++) {   // ranks of the two template columns
+        SortLane &L = ctx->lane[2 + w];
+        GE_TRY(ctx->ensure(L.keys_out, cb * 8)); GE_TRY(ctx->ensure(L.vals_out, cb * 4));
+        GE_TRY(sort_pairs_on(ctx, L.s, L.tmp, (w ? M.t2 : M.t1).as<uint64_t>(), L.keys_out.as<uint64_t>(), M.idx_a.as<uint32_t>(), L.vals_out.as<uint32_t>(), n2, cb));
+        rank_scatter_kernel<<<g_c, 256, 0, L.s>>>(ss, L.vals_out.as<uint32_t>(), (w ? M.rank2 : M.rank1).as<uint32_t>());
+        GE_TRY(ctx->check_launch("rank_scatter"));
+    }
+    GE_TRY(ctx->join_lanes());
+    pair_kernel<<<g_c, 256, 0, st>>>(ss, ctx->lane[0].vals_out.as<uint32_t>(), ctx->lane[1].vals_out.as<uint32_t>(), M.rank1.as<uint32_t>(), M.rank2.as<uint32_t>(), S.ids.as<uint64_t>(),
+                                     P.avoid_inbreeding, P.c_male.as<uint32_t>(), P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>());
+    GE_TRY(ctx->check_launch("pair"));
+    const bool poisson = gp.offspring_dist == 'p' || gp.offspring_dist == 'P';
+    family_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, poisson ? 1 : 0, P.c_noff.as<int32_t>());
+    GE_TRY(ctx->check_launch("family"));
+    if (!poisson) {
+        remainder_keys_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, P.c_inbreed.as<uint8_t>(), M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>());
+        GE_TRY(ctx->check_launch("remainder_keys"));
+        GE_TRY(sort_pairs_on(ctx, st, M.tmp_sort, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2, cb));
+        remainder_add_kernel<<<g_c, 256, 0, st>>>(ss, M.idx_b.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
+        GE_TRY(ctx->check_launch("remainder_add"));
+    }
     return GE_OK;
 }
 
@@ -405,14 +427,14 @@ __global__ void gather_bytes_kernel(PopPtrs src, const uint8_t *__restrict__ gpo
     uint64_t k = t / bytes_per_ind; uint32_t b = (uint32_t)(t % bytes_per_ind);
     dst[t] = static_cast<const uint8_t *>(src.p[gpop[k]])[(uint64_t)gidx[k] * bytes_per_ind + b];
 }
-// fp64 columns are stored [f*n + i] with n the population's own size
-__global__ void gather_f64_kernel(PopPtrs src, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst, int n_col,
+// fp64 columns are stored [f*stride + i], stride = the capacity
+__global__ void gather_f64_kernel(PopPtrs src, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst, int n_col, uint64_t stride,
                                   double *__restrict__ dst) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_dst * n_col) return;
     uint64_t k = t % n_dst; int f = (int)(t / n_dst);
     int p = gpop[k];
-    dst[(uint64_t)f * n_dst + k] = static_cast<const double *>(src.p[p])[(uint64_t)f * src.n[p] + gidx[k]];
+    dst[(uint64_t)f * stride + k] = static_cast<const double *>(src.p[p])[(uint64_t)f * stride + gidx[k]];
 }
 // CSR gather: slots_per_ind lists per individual; element = ELEM bytes
 __global__ void gather_csr_count_kernel(PopPtrs src_off, const uint8_t *__restrict__ gpop, const uint32_t *__restrict__ gidx, uint64_t n_dst,
@@ -485,7 +507,7 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
             GE_TRY(ctx->ensure(M.keys_a, (n + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (n + 1) * 8)); GE_TRY(ctx->ensure(M.idx_a, n * 4)); GE_TRY(ctx->ensure(M.idx_b, n * 4));
             migrate_keys_kernel<<<nblk(n, 256), 256, 0, st>>>(ctx->rng, i, gen, n, M.keys_a.as<uint64_t>(), M.idx_a.as<uint32_t>());
             GE_TRY(ctx->check_launch("migrate_keys"));
-            GE_TRY(sort_pairs(ctx, M, M.keys_a.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n));
+            GE_TRY(sort_pairs_on(ctx, st, M.tmp_sort, M.keys_a.as<uint64_t>(), M.keys_b.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), hostn(n), n));
             std::vector<uint32_t> h(s);
             CUDA_TRY(cudaMemcpyAsync(h.data(), M.idx_b.p, s * 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -540,7 +562,7 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
             for (const Col &cc : cols) {
                 PopPtrs t{};
                 for (int p = 0; p < np; p++) { GenState &S = ctx->pop[p].st[ctx->pop[p].cur]; t.p[p] = (S.*(cc.m)).p; t.n[p] = S.n; }
-                gather_f64_kernel<<<nblk(n * cc.cols, 256), 256, 0, st>>>(t, g8, g32, n, cc.cols, (D.*(cc.m)).as<double>());
+                gather_f64_kernel<<<nblk(n * cc.cols, 256), 256, 0, st>>>(t, g8, g32, n, cc.cols, ctx->cfg.capacity, (D.*(cc.m)).as<double>());
                 GE_TRY(ctx->check_launch("gather_f64"));
             }
         }
@@ -559,7 +581,7 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
             GE_TRY(ctx->ensure(P.cnt32, (n * spi + 1) * 4)); GE_TRY(ctx->ensure(D.seg.off, (n * spi + 1) * 8));
             if (n) { gather_csr_count_kernel<<<nblk(n * spi, 256), 256, 0, st>>>(to, g8, g32, n, spi, P.cnt32.as<uint32_t>()); GE_TRY(ctx->check_launch("gather_csr_count")); }
             GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n * spi, D.seg.off.as<uint64_t>(), &D.seg.n_seg));
-            GE_TRY(ctx->ensure(D.seg.seg, std::max<uint64_t>(D.seg.n_seg, 1) * ctx->seg_esz()));
+            GE_TRY(ctx->ensure(D.seg.seg, std::max<uint64_t>(std::max<uint64_t>(D.seg.n_seg, ctx->cfg.seg_capacity), 1) * ctx->seg_esz()));
             if (n && ctx->seg_packed) { gather_csr_fill_kernel<uint2><<<nblk(n * spi, 256), 256, 0, st>>>(to, tv, g8, g32, n, spi, D.seg.off.as<uint64_t>(), D.seg.seg.as<uint2>()); GE_TRY(ctx->check_launch("gather_csr_fill")); }
             else if (n) { gather_csr_fill_kernel<uint4><<<nblk(n * spi, 256), 256, 0, st>>>(to, tv, g8, g32, n, spi, D.seg.off.as<uint64_t>(), D.seg.seg.as<uint4>()); GE_TRY(ctx->check_launch("gather_csr_fill")); }
             D.seg.valid = true;
@@ -616,7 +638,13 @@ static int migrate(ge_ctx *ctx, int gen, const double *row) {
         }
         for (int j = 0; j < np; j++) { PopDev &P = ctx->pop[j]; std::swap(P.st[P.cur].hap, P.st[P.cur ^ 1].hap); }   // the rows stay where they are
     }
-    for (int j = 0; j < np; j++) ctx->pop[j].cur ^= 1;
+    for (int j = 0; j < np; j++) {   // the host decided the new sizes: tell the device-resident step state
+        PopDev &P = ctx->pop[j];
+        P.cur ^= 1;
+        GenState &S = P.st[P.cur];
+        P.hs.n[P.cur] = S.n; P.hs.n_hm[P.cur] = S.n_hm; P.hs.n_seg[P.cur] = S.seg.n_seg;
+        GE_TRY(ctx->push_state(P, offsetof(StepState, n), offsetof(StepState, prev_n) - offsetof(StepState, n)));
+    }
     ctx->mig_sample.clear();
     return GE_OK;
 }

@@ -11,8 +11,8 @@
 // part that covers it" and "position is in the haplotype's list" are the same predicate.
 //
 // Kernels: seg_recombine_kernel (one thread per slot, the reference's loop verbatim: maps that can give unsorted lists,
-// and the cross-check of the GPU tests), seg_recombine_warp_kernel (one warp per slot, the older at-scale form, kept
-// for A/B runs), and the default seg_plan_kernel + seg_gather_kernel.
+// and the cross-check of the GPU tests) and the default seg_plan_kernel + seg_gather_kernel.  Sizes (offspring, crossovers,
+// intervals, parts) are read from StepState on the device; grids are sized from the capacity.
 #pragma once
 #include "ge_context.cuh"
 
@@ -43,7 +43,9 @@ __global__ void seg_init_kernel(uint64_t n, int n_chr, int pop, const uint32_t *
 
 struct SegArgs {
     int n_chr;
-    uint64_t off_first, n_off;
+    const StepState *ss;      // live error bits of the segment lists (set by the bulk stream itself, a generation earlier)
+    const DrawCounts *dc;     // sizes of the draw set being recombined (the bulk stream runs behind the control stream's counters)
+    __device__ __forceinline__ bool dead() const { return dc->fatal || (ss->err & (SE_CAP_SEG | SE_SEG_UNSORTED)); }
     const uint32_t *father, *mother;
     const uint64_t *xo_off; const uint32_t *xo_bp; const uint8_t *start_hap;
     const uint64_t *par_off; const void *par_seg;   // uint4 parts, or uint2 packed parts (plan + gather only)
@@ -58,10 +60,12 @@ struct SegArgs {
 // 100 a list holds ~160 parts.  A descending L (only possible with maps whose rows are closer than bp_dist_in_rmap)
 // resets the cursors, which restores the reference's rescan.
 template <bool FILL>
-__global__ void seg_recombine_kernel(SegArgs a, uint32_t *__restrict__ count, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg) {
-    const uint64_t n_total = a.n_off * a.n_chr * 2;
+__global__ void seg_recombine_kernel(SegArgs a, uint32_t *__restrict__ count, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg, uint64_t cap) {
+    if (a.dead()) return;
+    const uint64_t n_total = a.dc->n_off * a.n_chr * 2;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t slot = a.off_first * a.n_chr * 2 + t;
+        uint64_t slot = t;
+        if (FILL && off_off[slot + 1] > cap) continue;   // (a generation that outgrew the buffer: reported through StepState::err)
         uint64_t i = (slot >> 1) / (uint64_t)a.n_chr;
         int c = (int)((slot >> 1) % (uint64_t)a.n_chr), gam = (int)(slot & 1);
         uint32_t parent = gam ? a.mother[i] : a.father[i];
@@ -115,85 +119,6 @@ __global__ void seg_recombine_kernel(SegArgs a, uint32_t *__restrict__ count, co
     }
 }
 
-// The same function, one WARP per offspring haplotype slot — the kernel the segment path runs by default.
-// Parental lists are sorted and tile the chromosome, so whether part (x, y) of the current haplotype contributes to
-// interval [L, R) — and with which clip — is a local predicate that reproduces the four branches of :2922-2954:
-//   y <= L                      not reached (the `while` skip)
-//   x <  L, R <  y              (L, R)    interval inside one part   [clip both]
-//   x <  L, R >= y              (L, y)                               [clip start]
-//   x >= L, y <= R              (x, y)    whole part (zero-length parts included, as in the reference)
-//   x >= L, x < R < y           (x, R)                               [clip end]
-// The warp walks the intervals in order; for each it reads the parts of the current haplotype from that haplotype's
-// cursor in coalesced chunks of 32 (512 B), ballots the predicate and writes the pieces compacted with coalesced
-// 16-byte stores.  Pieces come out in (interval, part) order exactly as the reference appends them.  Lists that are
-// not sorted can only arise from genetic maps with rows closer than bp_dist_in_rmap; contexts with such a map use the
-// thread-per-slot kernel above, which is the reference's loop verbatim.
-// G lanes cooperate on one slot (G = 32: a warp; G = 8: four slots per warp while the lists are still short).
-template <bool FILL, int G>
-__global__ void seg_recombine_warp_kernel(SegArgs a, uint32_t *__restrict__ count, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg) {
-    const int lane = threadIdx.x & (G - 1);
-    const int shift = (threadIdx.x & 31) - lane;
-    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << shift;
-    const unsigned lt = (1u << lane) - 1u;
-    const uint64_t n_total = a.n_off * a.n_chr * 2;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) / G;
-    for (uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G; t < n_total; t += n_warps) {
-        const uint64_t slot = a.off_first * a.n_chr * 2 + t;
-        const uint64_t i = (slot >> 1) / (uint64_t)a.n_chr;
-        const int c = (int)((slot >> 1) % (uint64_t)a.n_chr), gam = (int)(slot & 1);
-        const uint32_t parent = gam ? a.mother[i] : a.father[i];
-        const uint64_t ps = ((uint64_t)parent * a.n_chr + c) * 2;
-        const uint64_t o0 = a.par_off[ps], o1 = a.par_off[ps + 1], o2 = a.par_off[ps + 2];
-        const uint4 *H0 = static_cast<const uint4 *>(a.par_seg) + o0, *H1 = static_cast<const uint4 *>(a.par_seg) + o1;
-        const uint32_t n0 = (uint32_t)(o1 - o0), n1 = (uint32_t)(o2 - o1);
-        const uint64_t e0 = a.xo_off[slot];
-        const uint32_t k = (uint32_t)(a.xo_off[slot + 1] - e0);
-        int hi = a.start_hap[slot] & 1;
-        uint4 *out = FILL ? off_seg + off_off[slot] : nullptr;
-        uint32_t n = 0;
-        if (k == 0) {  // the chosen parental haplotype unchanged (:2910)
-            const uint4 *H = hi ? H1 : H0;
-            n = hi ? n1 : n0;
-            if (FILL) for (uint32_t q = lane; q < n; q += G) out[q] = H[q];
-        } else {
-            uint32_t cur0 = 0, cur1 = 0, prevL = 0;
-            const uint32_t lo_c = a.cov_lo[c], hi_c = a.cov_hi[c];
-            for (uint32_t i1 = 0; i1 <= k; i1++) {
-                const uint32_t L = i1 == 0 ? lo_c : a.xo_bp[e0 + i1 - 1];
-                const uint32_t R = i1 == k ? hi_c : a.xo_bp[e0 + i1];
-                if (L < prevL) { cur0 = 0; cur1 = 0; }
-                prevL = L;
-                const uint4 *H = hi ? H1 : H0;
-                const uint32_t nH = hi ? n1 : n0, base = hi ? cur1 : cur0;
-                uint32_t adv = 0;
-                for (uint32_t b = base; b < nH; b += G) {
-                    const uint32_t p = b + lane;
-                    const bool valid = p < nH;
-                    uint4 q = make_uint4(0, 0, 0, 0);
-                    if (valid) q = H[p];
-                    const bool reached = valid && q.y > L;
-                    bool emit = false;
-                    uint4 o = q;
-                    if (reached) {
-                        if (q.x < L) { emit = true; o.x = L; if (R < q.y) o.y = R; }
-                        else if (q.y <= R) emit = true;
-                        else if (q.x < R) { emit = true; o.y = R; }
-                    }
-                    const unsigned em = __ballot_sync(gmask, emit) >> shift;
-                    const unsigned past = __ballot_sync(gmask, reached && q.y > R);
-                    adv += __popc(__ballot_sync(gmask, valid && q.y <= R));
-                    if (FILL && emit) out[n + __popc(em & lt)] = o;
-                    n += __popc(em);
-                    if (past) break;
-                }
-                if (hi) cur1 = base + adv; else cur0 = base + adv;
-                hi ^= 1;
-            }
-        }
-        if (!FILL && lane == 0) count[slot] = n;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Plan + gather: the form the segment path runs by default (every list length).  ncu on the walk kernels above
 // (1M individuals, generation 41) showed both passes ISSUE-bound (81 % / 65 % issue-active at 1.6 / 2.9 TB/s of DRAM
@@ -211,10 +136,9 @@ __global__ void seg_recombine_warp_kernel(SegArgs a, uint32_t *__restrict__ coun
 //                     that haplotype's previous end); writes a 16-byte copy descriptor and the part count of every interval.
 //  (scan of the interval counts -> absolute output offset of every interval; seg_slot_offsets_kernel -> the new CSR offsets)
 //  seg_gather_kernel  flat clipped copy over all intervals, load-balanced by output part, fully coalesced stores.
-// Two warp-per-slot forms were built and measured first (bit-identical, GPU tests green): balloting the prefix counts chunk by
-// chunk (450 warp instructions per slot, slower than the walk) and a per-slot gather (52 % of stalls on one DRAM round trip per
-// interval, then 314 instructions per slot once flattened inside the warp).  The per-slot prologue — a division, six dependent
-// loads — is what both paid; here only the thread-per-slot plan pays it.
+// Warp-per-slot forms were built and measured first in round 1 (a walk with ballots in both passes, balloted prefix counts, a
+// per-slot gather; DESIGN.md §3 has the numbers): the per-slot prologue — a division, six dependent loads — is what all of them
+// paid in both passes; here only the thread-per-slot plan pays it.
 // Slots whose positions do not ascend are done by one thread with the reference's loop verbatim (descriptor y = 0xFFFFFFFF).
 // ------------------------------------------------------------------------------------------------
 template <bool FILL>
@@ -251,8 +175,7 @@ __device__ __forceinline__ SegSlot seg_slot(const SegArgs &a, uint64_t t) {
     uint64_t i; uint32_t r;
     if (t <= 0xFFFFFFFFull) { const uint32_t t32 = (uint32_t)t, q = t32 / per; i = q; r = t32 - q * per; }   // 32-bit division: the 64-bit one is ~100 instructions
     else { i = t / per; r = (uint32_t)(t - i * per); }
-    i += a.off_first;
-    s.slot = a.off_first * per + t;
+    s.slot = t;
     s.c = r >> 1;
     const uint32_t parent = (r & 1u) ? a.mother[i] : a.father[i];
     const uint64_t ps = ((uint64_t)parent * a.n_chr + s.c) * 2;
@@ -298,10 +221,11 @@ __device__ __forceinline__ void seg_count_y_le2(const T *__restrict__ H, uint32_
 // part count; the scan of the counts gives every interval its absolute output offset, so the copy itself knows nothing of slots.
 template <class T>
 __global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__restrict__ iv_count, uint4 *__restrict__ desc, unsigned int *__restrict__ n_verbatim,
-                                                       uint64_t *__restrict__ verb_list, uint32_t verb_cap) {
+                                                       uint64_t *__restrict__ verb_list, uint32_t verb_cap, uint32_t *__restrict__ err) {
     constexpr bool PACKED = sizeof(T) == 8;
+    if (a.dead()) return;   // also: the parental lists outgrew their buffer
     const T *par = static_cast<const T *>(a.par_seg);
-    const uint64_t n_total = a.n_off * a.n_chr * 2;
+    const uint64_t n_total = a.dc->n_off * a.n_chr * 2;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
         const SegSlot s = seg_slot(a, t);
         const uint64_t g = s.e0 + s.slot;
@@ -329,7 +253,7 @@ __global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__re
         }
         if (!fast) {
             if constexpr (PACKED) {   // pieces that do not tile cannot be stored with an implied end: refuse (ge_last_error names the 16-byte format)
-                atomicAdd(n_verbatim + 1, 1u);
+                atomicOr(err, (uint32_t)SE_SEG_UNSORTED);
                 for (uint32_t j = 0; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
             } else {   // the reference's loop verbatim (seg_verbatim_fill_kernel writes the parts)
                 const uint32_t n = seg_recombine_verbatim<false>(H0, s.n0, H1, s.n1, xo, s.k, lo_c, hi_c, s.hi, nullptr);
@@ -361,10 +285,19 @@ __global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__re
 }
 
 // CSR offsets of the new generation: slot -> output offset of its first interval
-__global__ void seg_slot_offsets_kernel(uint64_t n_slots, uint64_t slot0, const uint64_t *__restrict__ xo_off, const uint64_t *__restrict__ iv_off, uint64_t *__restrict__ off) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t <= n_slots) off[t] = iv_off[xo_off[slot0 + t] + slot0 + t];
+__global__ void seg_slot_offsets_kernel(SegArgs a, const uint64_t *__restrict__ xo_off, const uint64_t *__restrict__ iv_off, uint64_t *__restrict__ off) {
+    if (a.dead()) return;
+    const uint64_t n_slots = a.dc->n_off * (uint64_t)a.n_chr * 2;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= n_slots; t += (uint64_t)gridDim.x * blockDim.x) off[t] = iv_off[xo_off[t] + t];
 }
+// grand total of a part-count scan: the size of the new generation's lists, and whether they fit
+struct SegTotal {
+    StepState *ss; int k; uint64_t cap;   // cap == 0: no limit (the host sizes the buffer from the total)
+    __device__ __forceinline__ void operator()(uint64_t t) const {
+        ss->n_seg[k] = t;
+        if (cap && t > cap) atomicOr(&ss->err, (uint32_t)SE_CAP_SEG);
+    }
+};
 
 // The copy: a CTA takes SEG_GATHER_IV consecutive intervals (descriptors and offsets staged in shared memory with coalesced
 // loads) and its threads walk the flat run of output parts those intervals own — every thread finds the interval of its output
@@ -381,8 +314,10 @@ __device__ __forceinline__ void part_clip(uint4 &q, uint32_t L, uint32_t R) { q.
 __device__ __forceinline__ void part_clip(uint2 &q, uint32_t L, uint32_t) { q.x = max(q.x, L); }   // the end is the next part's start
 
 template <class T, int DEPTH>
-__global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict__ desc, const uint64_t *__restrict__ iv_off, uint64_t n_iv,
+__global__ void __launch_bounds__(256) seg_gather_kernel(SegArgs a, const uint4 *__restrict__ desc, const uint64_t *__restrict__ iv_off,
                                                          const T *__restrict__ par_seg, T *__restrict__ off_seg, uint64_t cap) {
+    if (a.dead()) return;
+    const uint64_t n_iv = a.dc->n_iv;
     constexpr int TILE = 256 * 16;                 // outputs per owner tile: one uint4 of owner bytes per thread
     static_assert(SEG_GATHER_IV <= 256 && (16 % DEPTH) == 0, "interval ids are bytes; a tile is a whole number of load batches");
     __shared__ uint32_t s_rel[SEG_GATHER_IV + 1];
@@ -396,7 +331,7 @@ __global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict
         if (tid < m) s_desc[tid] = desc[g0 + tid];
         if (tid <= SEG_GATHER_IV) s_rel[tid] = (uint32_t)(iv_off[g0 + min(tid, m)] - o0);   // entries beyond m repeat the end
         __syncthreads();
-        // parts beyond the buffer are not written (asynchronous form: the host learns the total only afterwards and reports GE_ERR_CAPACITY)
+        // parts beyond the buffer are never written (the scan's total set SE_CAP_SEG; the host reports GE_ERR_CAPACITY at its next read-back)
         const uint64_t room = cap > o0 ? cap - o0 : 0;
         const uint32_t n = room < (uint64_t)s_rel[m] ? (uint32_t)room : s_rel[m];
         T *out = off_seg + o0;
@@ -467,9 +402,9 @@ __global__ void __launch_bounds__(256) seg_gather_kernel(const uint4 *__restrict
 __global__ void seg_verbatim_fill_kernel(SegArgs a, const uint4 *__restrict__ desc, const unsigned int *__restrict__ n_verbatim, const uint64_t *__restrict__ verb_list,
                                          uint32_t verb_cap, const uint64_t *__restrict__ off_off, uint4 *__restrict__ off_seg, uint64_t cap) {
     const unsigned int nv = *n_verbatim;
-    if (nv == 0) return;
+    if (nv == 0 || a.dead()) return;
     const bool listed = nv <= verb_cap;
-    const uint64_t n_total = listed ? nv : a.n_off * a.n_chr * 2;
+    const uint64_t n_total = listed ? nv : a.dc->n_off * a.n_chr * 2;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_total; w += (uint64_t)gridDim.x * blockDim.x) {
         const SegSlot s = seg_slot(a, listed ? verb_list[w] : w);
         if (s.k == 0 || desc[s.e0 + s.slot].y != SEG_PLAN_VERBATIM) continue;
@@ -646,191 +581,145 @@ static int seg_ibd(ge_ctx *ctx, int pop, int c, const uint64_t *ind_a, const uin
     return GE_OK;
 }
 
-static void seg_release(SegState &s) {
-    for (Buf *b : {&s.off, &s.seg}) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
-    if (s.ready) { cudaEventDestroy(s.ready); s.ready = nullptr; }
-    if (s.h_total) { cudaFreeHost(s.h_total); s.h_total = nullptr; }
-    s.valid = false; s.pending = false;
+static void seg_release(ge_ctx *ctx, SegState &s) {
+    ctx->release(s.off); ctx->release(s.seg);
+    s.valid = false;
 }
 
 static int seg_init_gen0(ge_ctx *ctx, int p, uint64_t n) {
     PopDev &P = ctx->pop[p];
     SegState &S = P.st[P.cur].seg;
     uint64_t n_slots = n * ctx->cfg.n_chr * 2;
-    // the part format is fixed here, once the maps are known: packed 8-byte parts wherever lists are sorted tilings and the walk
-    // kernels (which need en in memory) are not asked for
+    // the part format is fixed here, once the maps are known: packed 8-byte parts wherever lists are sorted tilings and the
+    // reference's verbatim loop (which needs en in memory) is not asked for
     if (p == 0) {
         bool same_range = true;
         for (int q = 1; q < ctx->cfg.n_pop; q++)
             for (int c = 0; c < ctx->cfg.n_chr; c++)
                 same_range &= ctx->pop[q].rmap_bp[c].front() == ctx->pop[0].rmap_bp[c].front() && ctx->pop[q].rmap_bp[c].back() == ctx->pop[0].rmap_bp[c].back();
         uint64_t max_haps = 0;
-        for (PopDev &Q : ctx->pop) max_haps = std::max<uint64_t>(max_haps, Q.cv[0][0].nhap);
-        ctx->seg_packed = !ctx->seg_per_thread && ctx->seg_group == 0 && !ctx->seg_walk && !ctx->seg_wide && same_range && max_haps < (1ull << SEG_ID_BITS) &&
-                          ctx->cfg.n_pop <= (1 << (32 - SEG_ID_BITS));
+        for (PopDev &Q : ctx->pop) max_haps = std::max<uint64_t>(max_haps, std::max<uint64_t>(Q.cv[0][0].nhap, 2 * ctx->cfg.capacity));   // (re-basing makes every haplotype of a generation a founder)
+        ctx->seg_packed = !ctx->seg_per_thread && !ctx->seg_wide && same_range && max_haps < (1ull << SEG_ID_BITS) && ctx->cfg.n_pop <= (1 << (32 - SEG_ID_BITS));
     }
     const size_t esz = ctx->seg_esz();
-    GE_TRY(ctx->ensure(S.off, (n_slots + 1) * 8)); GE_TRY(ctx->ensure(S.seg, std::max<uint64_t>(n_slots, 1) * esz));
+    const uint64_t slots_cap = ctx->cfg.capacity * ctx->cfg.n_chr * 2;
+    for (GenState &G : P.st) GE_TRY(ctx->ensure(G.seg.off, (slots_cap + 1) * 8));
+    GE_TRY(ctx->ensure(S.seg, std::max<uint64_t>(std::max<uint64_t>(n_slots, ctx->cfg.seg_capacity), 1) * esz));
     if (ctx->seg_packed) seg_init_kernel<uint2><<<nblk(n_slots + 1, 256), 256, 0, ctx->stream>>>(n, ctx->cfg.n_chr, p, P.d_cov_lo.as<uint32_t>(), P.d_cov_hi.as<uint32_t>(),
                                                                                               S.off.as<uint64_t>(), S.seg.as<uint2>());
     else seg_init_kernel<uint4><<<nblk(n_slots + 1, 256), 256, 0, ctx->stream>>>(n, ctx->cfg.n_chr, p, P.d_cov_lo.as<uint32_t>(), P.d_cov_hi.as<uint32_t>(),
                                                                                 S.off.as<uint64_t>(), S.seg.as<uint4>());
     GE_TRY(ctx->check_launch("seg_init"));
     S.n_seg = n_slots; S.valid = true;
-    return GE_OK;
+    P.hs.n_seg[P.cur] = n_slots;
+    return ctx->push_state(P, offsetof(StepState, n_seg), 16);
 }
 
-// n_seg of a generation whose plan + gather was queued on the bulk stream: wait for the scan's total (not for the gather)
-static int seg_finish(ge_ctx *ctx, GenState &S) {
-    SegState &g = S.seg;
-    if (!g.pending) return GE_OK;
-    g.pending = false;
-    CUDA_TRY(cudaEventSynchronize(g.ready));
-    g.n_seg = g.h_total[0];
-    if ((uint32_t)g.h_total[1]) {
-        g.valid = false;
-        return fail(GE_ERR_UNSUPPORTED, std::to_string((uint32_t)g.h_total[1]) + " gametes had crossover positions that do not ascend: the packed segment format cannot hold "
-                    "the pieces the reference emits for them (set GE_SEG_FORMAT=16 to keep its 16-byte parts)");
-    }
-    if (g.ev[0]) {   // 16 (8 packed) B per part: every emitted piece comes from one parental part, read by both passes and written once
-        ctx->ev_pending.push_back(ge_ctx::EvPair{g.ev[0], g.ev[1], GE_KERNEL_RECOMBINE_SEGMENTS, ctx->seg_esz() * g.n_seg});
-        ctx->ev_pending.push_back(ge_ctx::EvPair{g.ev[2], g.ev[3], GE_KERNEL_RECOMBINE_SEGMENTS, 2 * ctx->seg_esz() * g.n_seg});
-        g.ev[0] = g.ev[1] = g.ev[2] = g.ev[3] = nullptr;
-    }
-    if (ctx->cfg.seg_capacity && g.n_seg > ctx->cfg.seg_capacity) {
-        g.valid = false;
-        return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity (" + std::to_string(g.n_seg) + " parts; reported by the first call after the generation that overflowed)");
-    }
-    return GE_OK;
-}
-// before anything on the control stream (or the host) reads segment lists
+// before anything on the control stream (or the host) reads segment lists: the bulk stream's plan + gather is complete and the host's
+// sizes (n_seg among them) are exact; a generation that outgrew seg_capacity or could not be stored in packed parts is reported here
 static int seg_finish_all(ge_ctx *ctx) {
     if (!ctx->segs()) return GE_OK;
-    int rc = GE_OK;
-    for (PopDev &P : ctx->pop) for (GenState &S : P.st) { int r = seg_finish(ctx, S); if (r != GE_OK) rc = r; }
     GE_TRY(ctx->join_bulk());
-    return rc;
+    return ctx->pull_state("founder segments");
 }
 
-static int seg_recombine(ge_ctx *ctx, int pop, uint64_t n_off) {
+static int seg_recombine(ge_ctx *ctx, int pop, uint64_t) {
     PopDev &P = ctx->pop[pop];
     GenState &par = P.st[P.cur], &off = P.st[P.cur ^ 1];
     if (!par.seg.valid) return fail(GE_ERR_INVALID, "parent generation has no segment lists");
-    GE_TRY(seg_finish(ctx, par));
-    GE_TRY(seg_finish(ctx, off));   // (a generation nobody looked at: its events and capacity check)
-    int C = ctx->cfg.n_chr;
-    uint64_t n_slots = n_off * C * 2;
+    const int C = ctx->cfg.n_chr, k_off = P.cur ^ 1;
+    const uint64_t slots_cap = ctx->cfg.capacity * C * 2;
+    StepState *ss = P.d_ss;
     SegArgs a;
     DrawSet &D = P.draws();
-    a.n_chr = C; a.off_first = 0; a.n_off = n_off; a.father = D.father.as<uint32_t>(); a.mother = D.mother.as<uint32_t>();
+    const DrawCounts *dc = &ss->dc[P.dcur];
+    a.n_chr = C; a.ss = ss; a.dc = dc; a.father = D.father.as<uint32_t>(); a.mother = D.mother.as<uint32_t>();
     a.xo_off = D.xo_off.as<uint64_t>(); a.xo_bp = D.xo_bp.as<uint32_t>(); a.start_hap = D.start_hap.as<uint8_t>();
     a.par_off = par.seg.off.as<uint64_t>(); a.par_seg = par.seg.seg.p; a.cov_lo = P.d_cov_lo.as<uint32_t>(); a.cov_hi = P.d_cov_hi.as<uint32_t>();
-    GE_TRY(ctx->ensure(off.seg.off, ((size_t)ctx->cfg.capacity * C * 2 + 1) * 8));
-    // the reference's loop verbatim in one thread per slot while the lists are short (or may be unsorted), plan + gather once a
-    // parental list averages 30 parts (GE_SEG_GROUP forces either; GE_SEG_WALK=1 selects the older warp-per-slot walk passes)
-    const double avg_parts = (double)par.seg.n_seg / (double)std::max<uint64_t>(1, par.n * C * 2);
-    int group = ctx->seg_per_thread ? 1 : (ctx->seg_group > 0 ? ctx->seg_group : (avg_parts < ctx->seg_plan_min_parts ? 1 : 32));
-    const bool plan = ctx->seg_packed || (group == 32 && !ctx->seg_walk);
     const size_t esz = ctx->seg_esz();
-    if (!plan) {   // ---- two walk passes on the control stream, host read-back of the total in between
-        cudaStream_t st = ctx->stream;
-        GE_TRY(ctx->ensure(P.cnt32, (n_slots + 1) * 4));
-        ge_ctx::EvPair ev1{nullptr, nullptr, GE_KERNEL_RECOMBINE_SEGMENTS, 0}, ev2 = ev1;
-        if (ctx->profiling) { ev1.a = ctx->get_event(); ev1.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev1.a, st)); }
-        const unsigned wgrid = (unsigned)std::min<uint64_t>(nblk(n_slots * (uint64_t)group, 256), (uint64_t)ctx->n_sm * 64);
-        if (group == 1) seg_recombine_kernel<false><<<ctx->ctrl_grid(n_slots, 128), 128, 0, st>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
-        else if (group == 8) seg_recombine_warp_kernel<false, 8><<<wgrid, 256, 0, st>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
-        else seg_recombine_warp_kernel<false, 32><<<wgrid, 256, 0, st>>>(a, P.cnt32.as<uint32_t>(), nullptr, nullptr);
-        GE_TRY(ctx->check_launch("seg_recombine<count>"));
-        if (ctx->profiling) CUDA_TRY(cudaEventRecord(ev1.b, st));
-        GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, off.seg.off.as<uint64_t>(), &off.seg.n_seg));
-        if (ctx->cfg.seg_capacity && off.seg.n_seg > ctx->cfg.seg_capacity) return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity");
-        // lists grow by ~36 parts per individual-haplotype-genome per generation: size the buffer once when the caller
-        // gave seg_capacity, otherwise grow geometrically (a reallocation of tens of GB costs more than a generation)
-        uint64_t want = std::max<uint64_t>(off.seg.n_seg, 1);
-        if (ctx->cfg.seg_capacity) want = ctx->cfg.seg_capacity; else if (want * 16 > off.seg.seg.cap) want += want / 2;
-        GE_TRY(ctx->ensure_exact(off.seg.seg, want * 16));
-        if (ctx->profiling) { ev2.a = ctx->get_event(); ev2.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(ev2.a, st)); }
-        if (group == 1) seg_recombine_kernel<true><<<ctx->ctrl_grid(n_slots, 128), 128, 0, st>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
-        else if (group == 8) seg_recombine_warp_kernel<true, 8><<<wgrid, 256, 0, st>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
-        else seg_recombine_warp_kernel<true, 32><<<wgrid, 256, 0, st>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>());
-        GE_TRY(ctx->check_launch("seg_recombine<fill>"));
-        if (ctx->profiling) {
-            CUDA_TRY(cudaEventRecord(ev2.b, st));
-            ev1.bytes = 16 * off.seg.n_seg; ev2.bytes = 32 * off.seg.n_seg;
-            ctx->ev_pending.push_back(ev1); ctx->ev_pending.push_back(ev2);
-        }
-        off.seg.valid = true;
-        return GE_OK;
-    }
-    // ---- plan + gather.  With seg_capacity the output buffer is sized once, so nothing between the passes needs the host:
-    // the whole chain is queued on the bulk stream behind the draws (like the bit-packed copy) and the control chain of the
-    // next generation overlaps it; n_seg arrives in pinned memory and is looked at by the next call that needs it.
-    const bool async = ctx->cfg.seg_capacity != 0 && !ctx->serial && !ctx->seg_sync_mode;
+    const bool plan = !ctx->seg_per_thread;
+    // With seg_capacity the output buffer is sized once, so nothing between the passes needs the host: the whole chain is queued on
+    // the bulk stream behind the draws (like the bit-packed copy) and the control chain of the next generation overlaps it.  Without
+    // it the host reads the total between the passes and grows the buffer.
+    const bool fixed = ctx->cfg.seg_capacity != 0;
+    const bool async = fixed && !ctx->serial;
     cudaStream_t st = async ? ctx->bulk : ctx->stream;
-    const uint64_t n_iv = P.n_xo + n_slots;            // intervals: one more than crossovers in every slot
-    constexpr uint32_t VERB_CAP = 1u << 18;
-    GE_TRY(ctx->ensure(ctx->seg_cnt, (n_iv + 1) * 4));
-    GE_TRY(ctx->ensure(ctx->seg_desc, (size_t)(n_iv + 1) * 16));
-    GE_TRY(ctx->ensure(ctx->seg_iv_off, (size_t)(n_iv + 1) * 8));
-    GE_TRY(ctx->ensure(ctx->seg_flags, 16));
-    GE_TRY(ctx->ensure(ctx->seg_verb, (size_t)VERB_CAP * 8));
-    if (!off.seg.ready) CUDA_TRY(cudaEventCreateWithFlags(&off.seg.ready, cudaEventDisableTiming));
-    if (!off.seg.h_total) CUDA_TRY(cudaMallocHost(&off.seg.h_total, 16));
     uint64_t cap = 0;
-    if (ctx->cfg.seg_capacity) { GE_TRY(ctx->ensure_exact(off.seg.seg, ctx->cfg.seg_capacity * esz)); cap = off.seg.seg.cap / esz; }
+    if (fixed) { GE_TRY(ctx->ensure_exact(off.seg.seg, ctx->cfg.seg_capacity * esz)); cap = ctx->cfg.seg_capacity; }
     if (async) {
         CUDA_TRY(cudaEventRecord(ctx->ev_ready, ctx->stream));   // the draws (and whatever the control stream did to the parental lists) are complete
         CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
     }
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (ctx->profiling) for (cudaEvent_t &e : ev) e = ctx->get_event();
-    if (ev[0]) CUDA_TRY(cudaEventRecord(ev[0], st));
-    CUDA_TRY(cudaMemsetAsync(ctx->seg_flags.p, 0, 16, st));
-    const unsigned pgrid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n_slots, 128)), 1u << 30);
-    if (ctx->seg_packed) seg_plan_kernel<uint2><<<pgrid, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP);
-    else seg_plan_kernel<uint4><<<pgrid, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP);
-    GE_TRY(ctx->check_launch("seg_plan"));
-    if (ev[1]) CUDA_TRY(cudaEventRecord(ev[1], st));
-    GE_TRY(ctx->exclusive_scan_on(st, ctx->seg_scan_blocks, ctx->seg_scan_total, ctx->seg_cnt.as<uint32_t>(), n_iv, ctx->seg_iv_off.as<uint64_t>()));
-    CUDA_TRY(cudaMemcpyAsync(off.seg.h_total, ctx->seg_scan_total.p, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(off.seg.h_total + 1, ctx->seg_flags.as<unsigned int>() + 1, 4, cudaMemcpyDeviceToHost, st));   // slots whose crossovers do not ascend (packed format)
-    CUDA_TRY(cudaEventRecord(off.seg.ready, st));
-    seg_slot_offsets_kernel<<<nblk(n_slots + 1, 256), 256, 0, st>>>(n_slots, 0, a.xo_off, ctx->seg_iv_off.as<uint64_t>(), off.seg.off.as<uint64_t>());
-    GE_TRY(ctx->check_launch("seg_slot_offsets"));
-    off.seg.pending = true;
-    off.seg.valid = true;
-    for (int k = 0; k < 4; k++) off.seg.ev[k] = ev[k];
-    if (!async) {
+    auto grow = [&]() -> int {   // seg_capacity == 0: the total comes to the host, the buffer grows geometrically (a reallocation of tens of GB costs more than a generation)
+        uint64_t n_seg = 0;
+        CUDA_TRY(cudaMemcpyAsync(&n_seg, &ss->n_seg[k_off], 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        const uint64_t n_seg = off.seg.h_total[0];
-        if (!ctx->cfg.seg_capacity) {   // grow geometrically (a reallocation of tens of GB costs more than a generation)
-            uint64_t want = std::max<uint64_t>(n_seg, 1);
-            if (want * esz > off.seg.seg.cap) want += want / 2;
-            GE_TRY(ctx->ensure_exact(off.seg.seg, want * esz));
-            cap = off.seg.seg.cap / esz;
-        } else if (n_seg > ctx->cfg.seg_capacity) { off.seg.pending = false; off.seg.valid = false; return fail(GE_ERR_CAPACITY, "segments exceed seg_capacity"); }
+        uint64_t want = std::max<uint64_t>(n_seg, 1);
+        if (want * esz > off.seg.seg.cap) want += want / 2;
+        GE_TRY(ctx->ensure_exact(off.seg.seg, want * esz));
+        cap = off.seg.seg.cap / esz;
+        return GE_OK;
+    };
+    if (ev[0]) CUDA_TRY(cudaEventRecord(ev[0], st));
+    if (!plan) {   // ---- the reference's loop, one thread per slot: count, scan, fill
+        const unsigned g = ctx->ctrl_grid(slots_cap, 128);
+        GE_TRY(ctx->ensure(ctx->seg_cnt, (slots_cap + 1) * 4));   // (its own scratch: this may run on the bulk stream beside the next generation's control chain)
+        seg_recombine_kernel<false><<<g, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), nullptr, nullptr, 0);
+        GE_TRY(ctx->check_launch("seg_recombine<count>"));
+        if (ev[1]) CUDA_TRY(cudaEventRecord(ev[1], st));
+        GE_TRY(ctx->scan(st, ctx->seg_cnt.as<uint32_t>(), devn(&dc->n_off, (uint64_t)C * 2), slots_cap, off.seg.off.as<uint64_t>(), SegTotal{ss, k_off, cap}));
+        if (!fixed) GE_TRY(grow());
+        if (ev[2]) CUDA_TRY(cudaEventRecord(ev[2], st));
+        seg_recombine_kernel<true><<<g, 128, 0, st>>>(a, nullptr, off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>(), cap);
+        GE_TRY(ctx->check_launch("seg_recombine<fill>"));
+    } else {       // ---- plan + gather
+        const uint64_t iv_cap = P.hs.xo_cap + slots_cap;          // intervals: one more than crossovers in every slot
+        constexpr uint32_t VERB_CAP = 1u << 18;
+        GE_TRY(ctx->ensure(ctx->seg_cnt, (iv_cap + 1) * 4));
+        GE_TRY(ctx->ensure(ctx->seg_desc, (size_t)(iv_cap + 1) * 16));
+        GE_TRY(ctx->ensure(ctx->seg_iv_off, (size_t)(iv_cap + 1) * 8));
+        GE_TRY(ctx->ensure(ctx->seg_flags, 16));
+        GE_TRY(ctx->ensure(ctx->seg_verb, (size_t)VERB_CAP * 8));
+        CUDA_TRY(cudaMemsetAsync(ctx->seg_flags.p, 0, 16, st));
+        const unsigned pgrid = ctx->grid_for(slots_cap, 128);
+        if (ctx->seg_packed) seg_plan_kernel<uint2><<<pgrid, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP, &ss->err);
+        else seg_plan_kernel<uint4><<<pgrid, 128, 0, st>>>(a, ctx->seg_cnt.as<uint32_t>(), ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP, &ss->err);
+        GE_TRY(ctx->check_launch("seg_plan"));
+        if (ev[1]) CUDA_TRY(cudaEventRecord(ev[1], st));
+        GE_TRY(ctx->scan(st, ctx->seg_cnt.as<uint32_t>(), devn(&dc->n_iv), iv_cap, ctx->seg_iv_off.as<uint64_t>(), SegTotal{ss, k_off, cap}));
+        seg_slot_offsets_kernel<<<ctx->grid_for(slots_cap + 1, 256), 256, 0, st>>>(a, a.xo_off, ctx->seg_iv_off.as<uint64_t>(), off.seg.off.as<uint64_t>());
+        GE_TRY(ctx->check_launch("seg_slot_offsets"));
+        if (!fixed) GE_TRY(grow());
+        if (ev[2]) CUDA_TRY(cudaEventRecord(ev[2], st));
+        const unsigned ggrid = ctx->grid_for(iv_cap, SEG_GATHER_IV);
+        if (ctx->seg_packed) {
+            seg_gather_kernel<uint2, 4><<<ggrid, 256, 0, st>>>(a, ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), par.seg.seg.as<uint2>(), off.seg.seg.as<uint2>(), cap);
+            GE_TRY(ctx->check_launch("seg_gather"));
+        } else {
+            seg_gather_kernel<uint4, 4><<<ggrid, 256, 0, st>>>(a, ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), par.seg.seg.as<uint4>(), off.seg.seg.as<uint4>(), cap);
+            GE_TRY(ctx->check_launch("seg_gather"));
+            seg_verbatim_fill_kernel<<<ctx->n_sm * 8, 128, 0, st>>>(a, ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP,
+                                                               off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>(), cap);
+            GE_TRY(ctx->check_launch("seg_verbatim_fill"));
+        }
     }
-    if (ev[2]) CUDA_TRY(cudaEventRecord(ev[2], st));
-    const unsigned ggrid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, nblk(n_iv, SEG_GATHER_IV)), 1u << 30);
-    if (ctx->seg_packed) {
-        if (ctx->seg_depth == 4) seg_gather_kernel<uint2, 4><<<ggrid, 256, 0, st>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, par.seg.seg.as<uint2>(), off.seg.seg.as<uint2>(), cap);
-        else seg_gather_kernel<uint2, 8><<<ggrid, 256, 0, st>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, par.seg.seg.as<uint2>(), off.seg.seg.as<uint2>(), cap);
-        GE_TRY(ctx->check_launch("seg_gather"));
-    } else {
-        seg_gather_kernel<uint4, 4><<<ggrid, 256, 0, st>>>(ctx->seg_desc.as<uint4>(), ctx->seg_iv_off.as<uint64_t>(), n_iv, par.seg.seg.as<uint4>(), off.seg.seg.as<uint4>(), cap);
-        GE_TRY(ctx->check_launch("seg_gather"));
-        seg_verbatim_fill_kernel<<<ctx->n_sm * 8, 128, 0, st>>>(a, ctx->seg_desc.as<uint4>(), ctx->seg_flags.as<unsigned int>(), ctx->seg_verb.as<uint64_t>(), VERB_CAP,
-                                                           off.seg.off.as<uint64_t>(), off.seg.seg.as<uint4>(), cap);
-        GE_TRY(ctx->check_launch("seg_verbatim_fill"));
+    if (ev[3]) {   // 16 (8 packed) B per part: every emitted piece comes from one parental part, read by both passes and written once; the part
+        CUDA_TRY(cudaEventRecord(ev[3], st));   // count of THIS generation follows the kernels into a pinned slot
+        uint64_t *slot = ctx->pinned_slot();
+        CUDA_TRY(cudaMemcpyAsync(slot, &ss->n_seg[k_off], 8, cudaMemcpyDeviceToHost, st));
+        ge_ctx::EvPair p1{ev[0], ev[1], GE_KERNEL_RECOMBINE_SEGMENTS, 0, 0, 0}, p2{ev[2], ev[3], GE_KERNEL_RECOMBINE_SEGMENTS, 0, 0, 0};
+        p1.count_src = slot; p1.count_scale = esz; p2.count_src = slot; p2.count_scale = 2 * esz;
+        ctx->ev_pending.push_back(p1); ctx->ev_pending.push_back(p2);
     }
-    if (ev[3]) CUDA_TRY(cudaEventRecord(ev[3], st));
+    off.seg.valid = true;
     if (async) {
         CUDA_TRY(cudaEventRecord(D.bulk_done, st));   // the draw set is read until here
         D.bulk_pending = true;
         // a long copy is in flight: the heavy control kernels of the next generation run on thin grids beside it (as for the bit-packed copy)
         if (!ctx->bits()) ctx->note_bulk((double)par.seg.n_seg * 2.0 * (double)esz);
-    } else GE_TRY(seg_finish(ctx, off));
+    }
     return GE_OK;
 }
 
@@ -887,6 +776,7 @@ static int seg_compact(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_aft
     GE_TRY(seg_finish_all(ctx));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur], &O = P.st[P.cur ^ 1];   // the other generation's buffers are free between generations
+    const bool fixed = ctx->cfg.seg_capacity != 0;
     if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists (GE_REP_SEGMENTS not enabled)");
     const uint64_t n_slots = S.n * ctx->cfg.n_chr * 2;
     if (n_before) *n_before = S.seg.n_seg;
@@ -900,7 +790,7 @@ static int seg_compact(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_aft
     GE_TRY(ctx->check_launch("seg_compact<count>"));
     uint64_t n_new = 0;
     GE_TRY(ctx->exclusive_scan(P.cnt32.as<uint32_t>(), n_slots, O.seg.off.as<uint64_t>(), &n_new));
-    GE_TRY(ctx->ensure(O.seg.seg, std::max<uint64_t>(n_new, 1) * ctx->seg_esz()));
+    GE_TRY(ctx->ensure(O.seg.seg, std::max<uint64_t>(fixed ? ctx->cfg.seg_capacity : n_new, 1) * ctx->seg_esz()));
     if (ctx->seg_packed) seg_compact_kernel<true, uint2><<<grid, 128, 0, ctx->stream>>>(n_slots, C, chi, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), nullptr, O.seg.off.as<uint64_t>(), O.seg.seg.as<uint2>());
     else seg_compact_kernel<true, uint4><<<grid, 128, 0, ctx->stream>>>(n_slots, C, chi, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), nullptr, O.seg.off.as<uint64_t>(), O.seg.seg.as<uint4>());
     GE_TRY(ctx->check_launch("seg_compact<fill>"));
@@ -908,7 +798,8 @@ static int seg_compact(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_aft
     S.seg.n_seg = n_new;
     O.seg.valid = false;
     if (n_after) *n_after = n_new;
-    return GE_OK;
+    P.hs.n_seg[P.cur] = n_new;
+    return ctx->push_state(P, offsetof(StepState, n_seg), 16);
 }
 
 // host-side slicing of one chromosome out of the slot-major CSR (output path, `.int` writer)

@@ -44,6 +44,15 @@ extern "C" {
 #define GE_SEL_STAB 3
 #define GE_SEL_THR 4
 
+/* ge_config.flags: measurement and verification aids.  None of them selects a different kernel for the same job: SERIAL changes
+ * which stream a kernel is queued on, the SEG flags choose the memory format of a part and the (reference-verbatim) kernel that maps
+ * with unsorted crossover lists always use, CV_FROM_SEGMENTS adds the reference's own rescan on top of the carried planes. */
+#define GE_FLAG_SERIAL 1            /* queue the bulk copy on the control stream: no overlap of generations (kernel-alone timings) */
+#define GE_FLAG_SEG_WIDE_PARTS 2    /* keep the reference's 16-byte parts {st, en, hap_index, root_population} instead of packed 8-byte parts */
+#define GE_FLAG_SEG_VERBATIM 4      /* recombine founder segments with the reference's loop verbatim, one thread per gamete (implies 16-byte parts) */
+#define GE_FLAG_CV_FROM_SEGMENTS 8  /* ge_compute_AD rebuilds the causal-variant planes from the segment lists like ras_find_cv, every generation */
+#define GE_FLAG_NO_GRAPH 16         /* never replay a generation's control chain as a captured CUDA graph */
+
 typedef struct ge_ctx ge_ctx;
 
 /* ge_create: replaces the allocation side of ras_init_parameters (:164-525). */
@@ -55,7 +64,7 @@ typedef struct ge_config {
     int32_t vt_type;         /* Parameters::_vt_type: 1 = parents' phenotype, 2 = parents' F (:3122-3131) */
     int32_t representation;  /* GE_REP_BITS | GE_REP_SEGMENTS (bit-or) */
     int32_t rng_mode;        /* GE_RNG_PHILOX or GE_RNG_REPLAY */
-    int32_t reserved0;
+    int32_t flags;           /* GE_FLAG_* (bit-or), 0 for production runs */
     uint64_t seed;           /* Parameters::_seed; Philox key */
     uint64_t capacity;       /* max individuals per population in any generation */
     uint64_t seg_capacity;   /* max segments per population per generation (GE_REP_SEGMENTS), 0 = auto (buffers grow, one host read-back

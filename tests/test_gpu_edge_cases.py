@@ -73,9 +73,9 @@ class Case:
                           start_hap=rng.integers(0, 2, n_off * C * 2).astype(np.uint8), e_raw=rng.normal(size=(1, n_off)))
 
 
-def run_pair(cuda_lib, case, gens, rep=capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, cap=64):
+def run_pair(cuda_lib, case, gens, rep=capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, cap=64, flags=0):
     """gens: list of (n_off, xo_lists).  Runs the library and the oracle on identical draws, compares everything."""
-    gpu = capi.Engine(cuda_lib, **case.kwargs(cap, representation=rep))
+    gpu = capi.Engine(cuda_lib, **case.kwargs(cap, representation=rep, flags=flags))
     cpu = OracleEngine(**case.kwargs(cap))
     d0 = case.draws0()
     for e in (gpu, cpu):
@@ -147,14 +147,11 @@ def test_hundreds_of_crossovers_per_gamete(cuda_lib):
     run_pair(cuda_lib, case, [(6, xo), (5, xo)], rep=capi.GE_REP_BITS)
 
 
-@pytest.mark.parametrize("walk", [False, True])
-def test_segment_warp_kernels_long_lists_and_many_crossovers(cuda_lib, monkeypatch, walk):
-    """The kernels the segment path runs at scale (GE_SEG_GROUP=32: seg_plan_kernel + seg_gather_kernel, or the two walk
-    passes with GE_SEG_WALK) against the oracle's verbatim `recombine`: lists that grow past several 32-part chunks, slots
-    without crossovers, crossovers on map rows / loci / duplicated, and slots with more than 30 crossovers (lane-0 fallback)."""
-    monkeypatch.setenv("GE_SEG_GROUP", "32")
-    if walk:
-        monkeypatch.setenv("GE_SEG_WALK", "1")
+@pytest.mark.parametrize("flags", [0, capi.GE_FLAG_SEG_WIDE_PARTS, capi.GE_FLAG_SEG_VERBATIM])
+def test_segment_kernels_long_lists_and_many_crossovers(cuda_lib, flags):
+    """The kernels of the segment path (seg_plan_kernel + seg_gather_kernel on packed and on 16-byte parts, and the reference's loop
+    verbatim) against the oracle's `recombine`: lists that grow past several 32-part chunks, slots without crossovers, crossovers on
+    map rows / loci / duplicated, beyond the covered end, and slots with more than 30 crossovers."""
     case = Case(31, [900, 60, 7], map_rows=50, step=128)
 
     def xo(slot, c):
@@ -172,7 +169,7 @@ def test_segment_warp_kernels_long_lists_and_many_crossovers(cuda_lib, monkeypat
             return np.sort(r.integers(int(bp[0]), int(bp[-1]) + step, size=45))      # > 30 crossovers: verbatim fallback
         return np.sort(r.integers(int(bp[0]), int(bp[-1]) + step, size=int(r.integers(1, 14))))
 
-    run_pair(cuda_lib, case, [(20, xo)] * 9, cap=64)
+    run_pair(cuda_lib, case, [(20, xo)] * 9, cap=64, flags=flags)
 
 
 def ibd_numpy(seg, off, i, j, min_bp):
@@ -197,11 +194,9 @@ def ibd_numpy(seg, off, i, j, min_bp):
 
 
 @pytest.mark.parametrize("fmt", ["packed", "16"])
-def test_ibd_sharing_matches_a_position_by_position_count(cuda_lib, monkeypatch, fmt):
-    if fmt == "16":
-        monkeypatch.setenv("GE_SEG_FORMAT", "16")
+def test_ibd_sharing_matches_a_position_by_position_count(cuda_lib, fmt):
     case = Case(77, [120, 30], n_founders=10, map_rows=12, step=40)
-    gpu = capi.Engine(cuda_lib, **case.kwargs(64, representation=capi.GE_REP_SEGMENTS))
+    gpu = capi.Engine(cuda_lib, **case.kwargs(64, representation=capi.GE_REP_SEGMENTS, flags=capi.GE_FLAG_SEG_WIDE_PARTS if fmt == "16" else 0))
     case.configure(gpu)
     gpu.init_generation0([case.draws0()])
     assert gpu.segment_format() == (8 if fmt == "packed" else 16)
@@ -226,13 +221,12 @@ def test_ibd_sharing_matches_a_position_by_position_count(cuda_lib, monkeypatch,
         assert tot[:40].max() > 0   # unrelated pairs share something, too, after four generations of ten founders
 
 
-def test_segment_capacity_is_enforced_on_both_paths(cuda_lib, monkeypatch):
-    """seg_capacity smaller than the lists: GE_ERR_CAPACITY from the generation itself (host read-back between the passes) or,
-    when the chain is queued on the bulk stream, from the first call after it — never a write beyond the buffer."""
-    for group, cap_parts in (("1", 40), ("32", 40)):
-        monkeypatch.setenv("GE_SEG_GROUP", group)
+def test_segment_capacity_is_enforced_on_both_paths(cuda_lib):
+    """seg_capacity smaller than the lists: GE_ERR_CAPACITY from the generation itself or, when the chain is queued on the bulk
+    stream and finishes after the generation's read-back, from the first call after it — never a write beyond the buffer."""
+    for flags, cap_parts in ((capi.GE_FLAG_SEG_VERBATIM, 40), (0, 40), (capi.GE_FLAG_SERIAL, 40)):
         case = Case(5, [200, 50])
-        gpu = capi.Engine(cuda_lib, **case.kwargs(64, representation=capi.GE_REP_SEGMENTS, seg_capacity=cap_parts))
+        gpu = capi.Engine(cuda_lib, **case.kwargs(64, representation=capi.GE_REP_SEGMENTS, seg_capacity=cap_parts, flags=flags))
         case.configure(gpu)
         gpu.init_generation0([case.draws0()])
 

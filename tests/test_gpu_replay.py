@@ -32,18 +32,18 @@ def compare_to_golden(G, eng, gen, pops=None):
 
 
 @pytest.mark.parametrize("name", SCENARIOS)
-@pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS, "segments-thread-walk",
-                                 "segments-warp-walk", "segments-bulk-stream", "both-bulk-stream"])
-def test_replay_matches_reference(cuda_lib, name, rep, monkeypatch):
-    extra, fmt = {}, 8   # sorted genetic maps: packed 8-byte parts, unless a walk kernel (which needs `en` in memory) is forced
+@pytest.mark.parametrize("rep", [capi.GE_REP_BITS, capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, capi.GE_REP_SEGMENTS, "segments-verbatim-walk",
+                                 "segments-wide-parts", "segments-bulk-stream", "both-bulk-stream"])
+def test_replay_matches_reference(cuda_lib, name, rep):
+    extra, fmt = {}, 8   # sorted genetic maps: packed 8-byte parts, unless the verbatim walk (which needs `en` in memory) or wide parts are asked for
     if isinstance(rep, str):
-        # the segment path's default is plan + gather (seg_plan_kernel, seg_gather_kernel); the walk kernels stay selectable
-        if rep == "segments-thread-walk":
-            monkeypatch.setenv("GE_SEG_GROUP", "1")
+        # the segment path's default is plan + gather (seg_plan_kernel, seg_gather_kernel); the reference's loop verbatim (one thread per
+        # gamete, what maps with unsorted crossover lists use) and plan + gather on the reference's 16-byte parts are checked the same way
+        if rep == "segments-verbatim-walk":
+            extra["flags"] = capi.GE_FLAG_SEG_VERBATIM
             fmt = 16
-        if rep == "segments-warp-walk":
-            monkeypatch.setenv("GE_SEG_GROUP", "32")
-            monkeypatch.setenv("GE_SEG_WALK", "1")
+        if rep == "segments-wide-parts":
+            extra["flags"] = capi.GE_FLAG_SEG_WIDE_PARTS
             fmt = 16
         if rep.endswith("bulk-stream"):   # with seg_capacity the whole chain is queued on the bulk stream, n_seg is read back later
             extra["seg_capacity"] = 400000
