@@ -170,25 +170,42 @@ def cpu_baseline_single(args, M):
 
 
 # ------------------------------------------------------------------------------------------------
-def ours(args):
+def state_hash(eng, n_pop):
+    """Integer fingerprint of the simulated state: pedigree, sex and couples of every population (crc32).  The fp64 columns are
+    left out on purpose — sharded runs add the chromosomes' partial genetic values in another order (1e-16) — but couples, family
+    sizes and pedigree depend on every phenotype through selection and the mating-value sorts, so equal hashes across --gpus N mean
+    the sharded runs simulated the same populations."""
+    import zlib
+    h = 0
+    for p in range(n_pop):
+        ind = eng.individuals(p)
+        c = eng.get_couples(p)
+        for a in (ind["ids"], ind["sex"], c["pos_male"], c["pos_female"], c["num_offspring"]):
+            h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
+    return h
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measure_workload(name, local, steps, warmup, n=None, loci=None, e2e=True, phases_steps=5):
+    """One single-GPU workload through the C-ABI: device-resident arm, end-to-end arm, dominant-kernel roofline (CUDA events on the
+    kernel's own stream inside the timed region) and, in a short extra pass, the phases of the control chain."""
     import torch
-    import torch.distributed as dist
     from geneevolve_b200 import capi, workloads
-    rank, world, local = rank_world()
-    if world > 1:
-        from geneevolve_b200 import dist as gdist
-        return gdist.bench_sharded(args, METRIC, UNIT)
-    torch.cuda.set_device(local)
-    cfg = workloads.make_workload(args.workload, n_override=args.n, loci_override=args.loci)
-    if "pops" in cfg:
-        raise SystemExit("multi-population workloads run chromosome-sharded: launch with torchrun (config 4 needs >= 4 GPUs at full size)")
+    cfg = workloads.make_workload(name, n_override=n, loci_override=loci)
     M, N = sum(cfg["n_loci"]), cfg["n"]
     cap = int(max(N, cfg["founders"]) * 1.03) + 1024
     segs = bool(cfg.get("segments"))
+    total_steps = warmup + steps * (2 if e2e else 1) + phases_steps
     seg_cap = 0
-    if segs:  # parts per haplotype-genome after g generations ~ n_chr + g * (map length in Morgans); both arms run back to back
+    if segs:  # parts per haplotype-genome after g generations ~ n_chr + g * (map length in Morgans)
         morgans = sum(float(p.sum()) for _, _, p in cfg["maps"])
-        seg_cap = int(2 * cap * (len(cfg["chrs"]) + (args.warmup + 2 * args.steps + 1) * morgans) * 1.05)
+        seg_cap = int(2 * cap * (len(cfg["chrs"]) + (total_steps + 1) * morgans) * 1.05)
     eng = capi.Engine(seg_capacity=seg_cap, n_pop=1, n_chr=len(cfg["chrs"]), n_phen=1, device=local, representation=capi.GE_REP_SEGMENTS if segs else capi.GE_REP_BITS,
                       rng_mode=capi.GE_RNG_PHILOX, seed=12345, capacity=cap)
     kid = capi.GE_KERNEL_RECOMBINE_SEGMENTS if segs else capi.GE_KERNEL_PROPAGATE_BITS
@@ -197,84 +214,136 @@ def ours(args):
     eng.init_generation0()
     gp = [capi.gen_params(N, cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
     gen = 0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         gen += 1
         eng.step_generation(gen, gp)
-    # pinned host buffers for the `.info` columns
-    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
-    out = {"ids": pin((cap, 7), torch.int64).view(np.uint64), "sex": pin((cap,), torch.uint8)}
-    for k in "ADGCEFP":
-        out[k] = pin((1, cap), torch.float64)
-    for k in ("mv", "sv", "svf"):
-        out[k] = pin((cap,), torch.float64)
-
     # ---- device-resident arm
-    eng.set_profiling(True)
+    eng.set_profiling(1)
     eng.reset_kernel_times()
     eng.synchronize()
     work = 0
     with ClockSampler(local) as clocks:
         eng.timer_start()
-        for _ in range(args.steps):
+        for _ in range(steps):
             gen += 1
             eng.step_generation(gen, gp)
             work += eng.population_size(0) * M
         ms_dev = eng.timer_stop()
     launches = eng.launch_count()
     k_ms, k_n, k_bytes = eng.kernel_time(kid)
-    phases = {name: eng.kernel_time(pid)[0] / args.steps for name, pid in capi.GE_PHASES.items()}   # ms per step, control stream, overlapped by the copy
-    eng.set_profiling(False)
-    value = work / (ms_dev * 1e-3)
-
+    eng.set_profiling(0)
+    res = {"cfg": cfg, "M": M, "N": N, "cap": cap, "segs": segs, "kname": kname, "ms_dev": ms_dev, "work": work, "launches": launches,
+           "k_ms": k_ms, "k_n": k_n, "k_bytes": k_bytes, "clocks": clocks.summary(), "first_timed_gen": warmup + 1}
     # ---- end-to-end arm: host parameters in, `.info` columns out to pinned host memory, every step
-    eng.synchronize()
-    work2, d2h = 0, 0
-    eng.timer_start()
-    for _ in range(args.steps):
+    if e2e:
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
+        out = {"ids": pin((cap, 7), torch.int64).view(np.uint64), "sex": pin((cap,), torch.uint8)}
+        for k in "ADGCEFP":
+            out[k] = pin((1, cap), torch.float64)
+        for k in ("mv", "sv", "svf"):
+            out[k] = pin((cap,), torch.float64)
+        eng.synchronize()
+        work2, d2h = 0, 0
+        eng.timer_start()
+        for _ in range(steps):
+            gen += 1
+            eng.step_generation(gen, gp)
+            nn = eng.population_size(0)
+            eng.individuals(0, out=out)
+            work2 += nn * M
+            d2h += capi.Engine.individual_bytes(nn, 1)
+        res.update(ms_e2e=eng.timer_stop(), work2=work2, d2h=d2h // steps, checksum=float(out["P"].reshape(-1)[:16].sum()), state_hash=state_hash(eng, 1))
+    # ---- the control chain's phases (CUDA events between its kernels: queued kernel by kernel, hence outside the timed regions)
+    eng.set_profiling(2)
+    eng.reset_kernel_times()
+    for _ in range(phases_steps):
         gen += 1
         eng.step_generation(gen, gp)
-        n = eng.population_size(0)
-        eng.individuals(0, out=out)
-        work2 += n * M
-        d2h += capi.Engine.individual_bytes(n, 1)
-    ms_e2e = eng.timer_stop()
-    checksum = float(out["P"].reshape(-1)[:16].sum())
+    res["phases"] = {nm: eng.kernel_time(pid)[0] / phases_steps for nm, pid in capi.GE_PHASES.items()}
+    eng.set_profiling(0)
+    res["device_memory_gb"] = eng.device_memory_bytes() / 1e9
+    eng.close()
+    return res
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
-    traffic = None
+
+def roofline_of(r, traffic=None, traffic_source=None):
+    peak, peak_src = hbm_peak()
+    achieved = r["k_bytes"] / (r["k_ms"] * 1e-3) / 1e9 if r["k_ms"] > 0 else None
+    return {"bound": "hbm", "kernel": r["kname"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+            "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src, "kernel_ms_per_launch": r["k_ms"] / max(r["k_n"], 1),
+            "kernel_share_of_step": r["k_ms"] / r["ms_dev"], "algorithmic_bytes_per_launch": r["k_bytes"] // max(r["k_n"], 1)}
+
+
+def other_workloads(local, budget_s=60.0):
+    """The other BASELINE configurations a single GPU can hold, each as a short record next to the headline (config 2 whole; config 5
+    as a founder-segment sample: 250 000 individuals, generations 41-45)."""
+    out = []
+    t0 = time.perf_counter()
+    for name, kw in (("config2_chr22_10k", dict(steps=40, warmup=5)),
+                     ("config1_bundled_1chr", dict(steps=100, warmup=5)),
+                     ("config5_1M_x_10M_segments", dict(steps=5, warmup=40, n=250000))):
+        if time.perf_counter() - t0 > budget_s:
+            out.append({"workload": name, "skipped": "time budget"})
+            continue
+        try:
+            r = measure_workload(name, local, e2e=False, phases_steps=3, **kw)
+            rec = {"workload": name, "individuals": r["N"], "loci": r["M"], "steps": kw["steps"], "warmup": kw["warmup"], "ms_per_step": r["ms_dev"] / kw["steps"],
+                   "value": r["work"] / (r["ms_dev"] * 1e-3), "unit": UNIT, "gpu_launches_per_step": r["launches"] / kw["steps"],
+                   "roofline": roofline_of(r), "control_chain_ms_per_step": r["phases"], "device_memory_gb": r["device_memory_gb"]}
+            if r["segs"]:
+                rec["note"] = "founder segments: loci nominal, cost grows with the generation (timed steps are generations %d..%d); algorithmic bytes = 8 B per " \
+                              "part read by the plan, read by the gather and written" % (r["first_timed_gen"], r["first_timed_gen"] + kw["steps"] - 1)
+            out.append(rec)
+        except Exception as e:  # never take the headline down
+            out.append({"workload": name, "failed": repr(e)})
+    return out
+
+
+def ours(args):
+    import torch
+    from geneevolve_b200 import capi, workloads
+    rank, world, local = rank_world()
+    if world > 1:
+        from geneevolve_b200 import dist as gdist
+        return gdist.bench_sharded(args, METRIC, UNIT)
+    torch.cuda.set_device(local)
+    if "pops" in workloads.CONFIGS[args.workload]:
+        raise SystemExit("multi-population workloads run sharded: launch with torchrun (config 4 needs >= 4 GPUs at full size)")
+    r = measure_workload(args.workload, local, args.steps, args.warmup, n=args.n, loci=args.loci)
+    cfg, M, N, segs = r["cfg"], r["M"], r["N"], r["segs"]
+    traffic = traffic_source = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and not segs and args.workload == "config3_100k_x_1M" and not args.n and not args.loci:
         traffic = json.load(open(tpath)).get("propagate_bits_dram_bytes_per_launch")
+        traffic_source = "profiles/traffic.json (static: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload, not measured in this run)"
+    value = r["work"] / (r["ms_dev"] * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-packed + f64",
+        "ms_per_step": r["ms_dev"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-packed + f64",
         "data": "synthetic",
         "config": {"workload": args.workload, "individuals": N, "loci": M, "chromosomes": len(cfg["chrs"]), "founders": cfg["founders"],
                    "causal_variants": sum(len(c["bp"]) for c in cfg["cvs"]), "mating": "random" if cfg["rm"] else "assortative rho=%.1f" % cfg["mat_cor"],
                    "selection": "logit(0,1)", "h2": 0.5, "rng": "philox4x32-10 on device",
                    "l2": ("inputs larger than L2 (%.1f GB of parental rows per step vs 126 MB)" % (N * M / 4 / 1e9)) if not segs else
-                         "inputs larger than L2 (founder-segment lists, %.1f GB written per step)" % (k_bytes / max(k_n, 1) / 2e9),
+                         "inputs larger than L2 (founder-segment lists, %.1f GB written per step)" % (r["k_bytes"] / max(r["k_n"], 1) / 2e9),
                    "representation": "founder segments (loci nominal; cost grows with the generation: steps are generations %d..%d)" % (args.warmup + 1, args.warmup + args.steps)
                    if segs else "bit-packed haplotypes",
-                   "device_memory_gb": eng.device_memory_bytes() / 1e9, "individual_generations_per_s": value / M},
-        "e2e": {"value": work2 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40, "d2h_bytes_per_step": d2h // args.steps,
-                "ms_per_step": ms_e2e / args.steps, "checksum": checksum,
+                   "device_memory_gb": r["device_memory_gb"], "individual_generations_per_s": value / M,
+                   "scaling_note": "the workload is fixed; --gpus N splits its loci over N ranks"},
+        "e2e": {"value": r["work2"] / (r["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40, "d2h_bytes_per_step": r["d2h"],
+                "ms_per_step": r["ms_e2e"] / args.steps, "checksum": r["checksum"], "state_hash": r["state_hash"],
+                "generations_simulated": args.warmup + 2 * args.steps,
                 "note": "generation state stays in HBM between steps by design (as it stays in process memory in the reference); per step the host sends the "
-                        "generation-table row and receives every individual's .info columns in pinned memory"},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                     "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms_dev,
-                     "algorithmic_bytes_per_launch": k_bytes // max(k_n, 1)},
-        "control_chain_ms_per_step": phases,
-        "clocks": clocks.summary(),
+                        "generation-table row and receives every individual's .info columns in pinned memory; state_hash = crc32 of pedigree, sex and couples "
+                        "after generations_simulated generations (equal across --gpus N when the sharded runs simulated the same populations)"},
+        "gpu_launches": r["launches"],
+        "roofline": roofline_of(r, traffic, traffic_source),
+        "control_chain_ms_per_step": r["phases"],
+        "clocks": r["clocks"],
     }
     line["cpu_baseline"] = cpu_baseline_single(args, M) if not args.no_cpu_baseline else None
+    if not args.no_other_workloads and args.workload == "config3_100k_x_1M" and not args.n and not args.loci:
+        line["other_workloads"] = other_workloads(local)
     print(json.dumps(line))
 
 
@@ -289,6 +358,7 @@ def main():
     ap.add_argument("--loci", type=int, default=None, help="override loci (debug)")
     ap.add_argument("--ref-sample", type=int, default=1500, help="individuals in the bounded reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the short records of the other BASELINE configurations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -545,7 +545,7 @@ static int enqueue_GEF(ge_ctx *ctx, int pop, int f, bool gen0, const double *e_h
         GE_TRY(ctx->check_launch("enoise_mean"));
     } else return fail(GE_ERR_INVALID, "replay mode needs e_raw");
     P.have_e_raw = true;
-    moment_kernel<<<mg, 256, 0, ctx->stream>>>(e, devn(S.d_n), mean_e, 1, 1, ctx->partial.as<double>(), var_e);
+    moment_kernel<<<mg, 256, 0, ctx->stream>>>(e, limited(devn(S.d_n), cap), mean_e, 1, 1, ctx->partial.as<double>(), var_e);
     GE_TRY(ctx->check_launch("moment<var>"));
     double *f0 = nullptr;
     if (gen0 && sc.vf > 0) {
@@ -911,7 +911,11 @@ static StepRow step_row(int gen, const ge_gen_params &gp) {
 }
 static int enqueue_step_begin(ge_ctx *ctx, int pop, int gen, const ge_gen_params &gp) {
     PopDev &P = ctx->pop[pop];
-    step_begin_kernel<<<1, 1, 0, ctx->stream>>>(P.d_ss, step_row(gen, gp));
+    const StepRow r = step_row(gen, gp);
+    // the host's copy follows (replayed draws push the whole struct later in the step)
+    P.hs.gen = r.gen; P.hs.sel_func = r.sel_func; P.hs.offspring_dist = r.offspring_dist; P.hs.pop_size = r.pop_size; P.hs.mat_cor = r.mat_cor;
+    P.hs.u11 = std::sqrt(1.0 - r.mat_cor * r.mat_cor); P.hs.sel_par1 = r.sel_par1; P.hs.sel_par2 = r.sel_par2; P.hs.n_inbreed = 0;
+    step_begin_kernel<<<1, 1, 0, ctx->stream>>>(P.d_ss, r);
     return ctx->check_launch("step_begin");
 }
 
@@ -1008,6 +1012,7 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
         // the host decided every size of this step
         P.hs.n_off = n_off; P.hs.n_xo = P.n_xo; P.hs.n_mut = P.n_mut; P.hs.n_iv = P.n_xo + n_slots; P.hs.n[P.cur ^ 1] = n_off;
         P.hs.dc[P.dcur] = DrawCounts{n_off, P.n_xo, P.n_xo + n_slots, 0u, 0u};
+        off.n = n_off; P.n_off = n_off;   // (host mirrors: the replayed environment draws are copied by this count before the step's read-back)
         GE_TRY(ctx->push_state(P));
         pedigree_kernel<<<nblk(n_off, 256), 256, 0, st>>>(n_off, D.father.as<uint32_t>(), D.mother.as<uint32_t>(), par.ids.as<uint64_t>(), off.ids.as<uint64_t>());
         GE_TRY(ctx->check_launch("pedigree"));
@@ -1380,7 +1385,7 @@ int ge_download_draws(ge_ctx *ctx, int pop, uint64_t *fa, uint64_t *mo, uint8_t 
 }
 
 // ---------------- measurement hooks ----------------
-int ge_set_profiling(ge_ctx *ctx, int enabled) { CHECK_CTX(ctx); ctx->profiling = enabled != 0; return GE_OK; }
+int ge_set_profiling(ge_ctx *ctx, int level) { CHECK_CTX(ctx); ctx->profiling = level != 0; ctx->phase_timing = level >= 2; return GE_OK; }
 int ge_get_kernel_time(ge_ctx *ctx, int k, double *ms, uint64_t *launches, uint64_t *bytes) {
     CHECK_CTX(ctx);
     if (k < 0 || k >= GE_KERNEL_COUNT) return fail(GE_ERR_INVALID, "bad kernel id");

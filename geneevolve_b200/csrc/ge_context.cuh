@@ -204,7 +204,8 @@ struct ge_ctx {
     uint64_t graph_epoch = 0;                   // bumped whenever a device buffer is (re)allocated: captured graphs hold raw pointers
     int n_sm = 148;
     // stats
-    bool profiling = false;
+    bool profiling = false;        // CUDA events around the dominant kernel (propagate_bits / the segment passes) on its own stream
+    bool phase_timing = false;     // ... and around the phases of the control chain (ge_set_profiling level 2; disables graph replay)
     KernelStat kstat[GE_KERNEL_COUNT];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // ge_timer_start / ge_timer_stop
     // bytes_per_offspring != 0: the launch's size was only known on the device; pull_state multiplies by the offspring count it reads back
@@ -237,7 +238,7 @@ struct ge_ctx {
     struct PhaseTimer {
         ge_ctx *c; EvPair p;
         PhaseTimer(ge_ctx *ctx, int id) : c(ctx), p{nullptr, nullptr, id, 0, 0, 0} {
-            if (c->profiling) { p.a = c->get_event(); p.b = c->get_event(); cudaEventRecord(p.a, c->stream); }
+            if (c->phase_timing) { p.a = c->get_event(); p.b = c->get_event(); cudaEventRecord(p.a, c->stream); }
         }
         ~PhaseTimer() { if (p.a) { cudaEventRecord(p.b, c->stream); c->ev_pending.push_back(p); } }
     };
@@ -326,6 +327,7 @@ struct ge_ctx {
     // grid; on_total runs in the thread that stores out[n].  One launch for small arrays, three otherwise.
     template <class TIn, class OnTotal>
     int scan_with(cudaStream_t st, Buf &blocks, const TIn *in, DevN n, uint64_t n_bound, uint64_t *out, OnTotal on_total) {
+        n = limited(n, n_bound);
         if (n_bound <= 2 * SCAN1_CHUNK) {
             scan_one_cta_kernel<TIn, OnTotal><<<1, SCAN1_THREADS, 0, st>>>(in, n, out, on_total);
             return check_launch("scan_one_cta");
@@ -362,12 +364,13 @@ struct ge_ctx {
     }
     int d_mean(const double *x, DevN n, uint64_t n_bound, double *out) {
         GE_TRY(ensure_partial());
+        n = limited(n, n_bound);
         moment_kernel<<<moment_grid(n_bound), 256, 0, stream>>>(x, n, nullptr, 0, 0, partial.as<double>(), out);
         return check_launch("moment<mean>");
     }
     int d_var(const double *x, DevN n, uint64_t n_bound, double *out /* device */, double *mean_scratch /* device */) {
         GE_TRY(d_mean(x, n, n_bound, mean_scratch));
-        moment_kernel<<<moment_grid(n_bound), 256, 0, stream>>>(x, n, mean_scratch, 1, 1, partial.as<double>(), out);
+        moment_kernel<<<moment_grid(n_bound), 256, 0, stream>>>(x, limited(n, n_bound), mean_scratch, 1, 1, partial.as<double>(), out);
         return check_launch("moment<var>");
     }
     int h_var(const double *x, uint64_t n, double *host_out, double *host_mean = nullptr) {

@@ -620,12 +620,14 @@ __global__ void cv_unpack_block_kernel(const uint32_t *__restrict__ bits, uint32
 }
 
 // a count that lives on the device: (*p) * mul + add (p == nullptr: add alone, a host-known count)
+// lim: the host-known bound the buffers were sized for — a count a failed step left behind never indexes beyond them
 struct DevN {
-    const uint64_t *p; uint64_t mul, add;
-    __device__ __forceinline__ uint64_t get() const { return (p ? *p : 0ull) * mul + add; }
+    const uint64_t *p; uint64_t mul, add, lim;
+    __device__ __forceinline__ uint64_t get() const { const uint64_t v = (p ? *p : 0ull) * mul + add; return v < lim ? v : lim; }
 };
-static inline DevN devn(const uint64_t *p, uint64_t mul = 1, uint64_t add = 0) { return DevN{p, mul, add}; }
-static inline DevN hostn(uint64_t n) { return DevN{nullptr, 0, n}; }
+static inline DevN devn(const uint64_t *p, uint64_t mul = 1, uint64_t add = 0) { return DevN{p, mul, add, ~0ull}; }
+static inline DevN hostn(uint64_t n) { return DevN{nullptr, 0, n, ~0ull}; }
+static inline DevN limited(DevN n, uint64_t lim) { n.lim = lim < n.lim ? lim : n.lim; return n; }
 
 // ------------------------------------------------------------------------------------------------
 // fp64 population moments: sum, then centred sum of squares (two-pass like CommFunc::var, src/CommFunc.cpp:57-68).
@@ -1134,7 +1136,7 @@ __global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *_
 // phenotype, :2417-2429, :2481-2484).
 // ------------------------------------------------------------------------------------------------
 __global__ void family_size_kernel(const StepState *__restrict__ ss, const uint8_t *__restrict__ inbreed, const int32_t *__restrict__ noff, uint32_t *__restrict__ cnt) {
-    const uint64_t n_couples = ss->n_couples;
+    const uint64_t n_couples = (ss->err & SE_FATAL) ? 0 : ss->n_couples;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_couples; k += (uint64_t)gridDim.x * blockDim.x)
         cnt[k] = inbreed[k] ? 0u : (uint32_t)max(noff[k], 0);
 }

@@ -271,6 +271,7 @@ constexpr uint64_t SORT_MAX = (uint64_t)gek::SS_TILE * gek::SS_GROUP * gek::SS_G
 static int sort_pairs_on(ge_ctx *ctx, cudaStream_t st, Buf &tmp, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, DevN n, uint64_t n_bound) {
     if (n_bound == 0) return GE_OK;
     if (n_bound > SORT_MAX) return fail(GE_ERR_UNSUPPORTED, "more than 4 194 304 list entries to sort (capacity above 8 388 608 individuals)");
+    n = limited(n, n_bound);
     const unsigned tiles = nblk(n_bound, SS_TILE);
     if (tiles == 1) {
         small_sort_tile_kernel<<<1, SS_THREADS, 0, st>>>(kin, vin, kout, vout, n);
@@ -322,6 +323,8 @@ static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp) {
     const bool with_mm = !P.RM;
     const uint64_t lb = (with_mm && P.MM > 0 ? 2 : 1) * cap;        // list entries at most (a --MM duplicate is a second entry)
     const unsigned g_ind = ctx->grid_for(cap, 256);
+    const uint64_t cb = lb / 2 + 1;                                  // couples of assortative mating at most: min(n_m, n_f)
+    GE_TRY(ensure_couples(ctx, P, P.RM ? std::max<uint64_t>(gp.pop_size, 1) : cb));   // (before the kernels below read couples_cap)
     GE_TRY(ctx->ensure(M.keys_a, (cap + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (lb + 1) * 8));
     GE_TRY(ctx->ensure(M.list_m, lb * 4)); GE_TRY(ctx->ensure(M.list_f, lb * 4));
     // who may mate: thinning counts, one scan for both sexes, the two lists
@@ -331,15 +334,12 @@ static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp) {
     thin_fill_kernel<<<g_ind, 256, 0, st>>>(S.d_n, M.keys_b.as<uint64_t>(), M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>());
     GE_TRY(ctx->check_launch("thin_fill"));
     if (P.RM) {  // random_mate :2090-2157
-        GE_TRY(ensure_couples(ctx, P, std::max<uint64_t>(gp.pop_size, 1)));
         rm_pair_kernel<<<ctx->grid_for(gp.pop_size, 256), 256, 0, st>>>(ctx->rng, ss, pop, M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>(), P.c_male.as<uint32_t>(),
                                                                         P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
         return ctx->check_launch("rm_pair");
     }
     // assort_mate :2167-2360
-    const uint64_t cb = lb / 2 + 1;                                  // couples at most: min(n_m, n_f)
     const unsigned g_list = ctx->grid_for(lb, 256), g_c = ctx->grid_for(cb, 256);
-    GE_TRY(ensure_couples(ctx, P, cb));
     GE_TRY(ctx->ensure(M.t1, lb * 8)); GE_TRY(ctx->ensure(M.t2, lb * 8)); GE_TRY(ctx->ensure(M.idx_a, lb * 4)); GE_TRY(ctx->ensure(M.idx_b, lb * 4));
     GE_TRY(ctx->ensure(M.keep, (lb + 1) * 4)); GE_TRY(ctx->ensure(M.keep_off, (lb + 1) * 8));
     GE_TRY(ctx->ensure(M.rank1, cb * 4)); GE_TRY(ctx->ensure(M.rank2, cb * 4));

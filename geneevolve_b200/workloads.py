@@ -130,45 +130,66 @@ def founder_words_multi(cfg, c, pop, rng):
     return w
 
 
-def configure_engine_multipop(eng, cfg, chrs_local=None, panel_seed=7):
+def shard_pieces(cfg, chrs_local=None, pieces=None):
+    """The (chromosome index, first locus, end locus) pieces a context owns: whole chromosomes (chrs_local, or everything) or
+    locus ranges from dist.assign_locus_ranges (a chromosome then appears on several ranks, each holding a slice of its loci,
+    all of them with the whole genetic map — crossovers are drawn per chromosome from Philox counters keyed by its global id)."""
+    if pieces is not None:
+        return [tuple(int(x) for x in pc) for pc in pieces]
+    chrs_local = list(range(len(cfg["chrs"]))) if chrs_local is None else list(chrs_local)
+    return [(c, 0, cfg["n_loci"][c]) for c in chrs_local]
+
+
+def _cv_slice(cv, s0, s1, val):
+    keep = (cv["idx"] >= s0) & (cv["idx"] < s1)
+    return cv["bp"][keep], cv["a"][keep], cv["d"][keep], np.ascontiguousarray(val[:, keep])
+
+
+def configure_engine_multipop(eng, cfg, chrs_local=None, panel_seed=7, pieces=None):
     """Multi-population workloads (config 4): every population its own founders, sizes and (here identical) effect sizes;
     phenotype f has omega = 1 / (1 + f), lambda = 1 for the first phenotype only."""
-    chrs_local = list(range(len(cfg["chrs"]))) if chrs_local is None else list(chrs_local)
-    if chrs_local != list(range(len(cfg["chrs"]))):
-        eng.set_chromosome_ids(chrs_local)
-    for k, c in enumerate(chrs_local):
-        eng.set_loci(k, cfg["loci"][c])
+    pcs = shard_pieces(cfg, chrs_local, pieces)
+    if pcs != [(c, 0, cfg["n_loci"][c]) for c in range(len(cfg["chrs"]))]:
+        eng.set_chromosome_ids([c for c, _, _ in pcs])
+    for k, (c, s0, s1) in enumerate(pcs):
+        eng.set_loci(k, cfg["loci"][c][s0:s1])
     for p in range(len(cfg["pops"])):
         eng.set_population(p, avoid_inbreeding=False, random_mating=cfg["rm"], mm_percent=0.0)
-        for k, c in enumerate(chrs_local):
+        for k, (c, s0, s1) in enumerate(pcs):
             bp, cm, pr = cfg["maps"][c]
             eng.set_genetic_map(p, k, bp, pr, int(bp[1] - bp[0]))
-            eng.set_founder_panel_packed(p, k, founder_words_multi(cfg, c, p, np.random.default_rng([panel_seed, c, p])))
+            w = founder_words_multi(cfg, c, p, np.random.default_rng([panel_seed, c, p]))
+            eng.set_founder_panel_packed(p, k, w[:, s0 // 32:(s1 + 31) // 32])
             for f in range(cfg["n_phen"]):
                 cv = cfg["cvs_multi"][f][c]
-                eng.set_cv(p, f, k, cv["bp"], cv["a"], cv["d"], cv["val"][p])
+                eng.set_cv(p, f, k, *_cv_slice(cv, s0, s1, cv["val"][p]))
         for f in range(cfg["n_phen"]):
             eng.set_pheno_scheme(p, f, va=0.5, vd=0.0, ve=0.5, vc=0.0, vf=0.0, omega=1.0 / (1 + f), beta=0.0, lam=1.0 if f == 0 else 0.0)
 
 
-def configure_engine(eng, cfg, va=0.5, vd=0.0, ve=0.5, panel_seed=7, chrs_local=None):
-    """Feeds the workload to an engine.  chrs_local: indices (into cfg['chrs']) of the chromosomes this context
-    owns (multi-GPU chromosome sharding); the founder panel of a chromosome does not depend on the sharding."""
-    chrs_local = list(range(len(cfg["chrs"]))) if chrs_local is None else list(chrs_local)
-    if len(chrs_local) != len(cfg["chrs"]) or chrs_local != list(range(len(chrs_local))):
-        eng.set_chromosome_ids(chrs_local)
+def configure_engine(eng, cfg, va=0.5, vd=0.0, ve=0.5, panel_seed=7, chrs_local=None, pieces=None):
+    """Feeds the workload to an engine.  chrs_local: indices (into cfg['chrs']) of the chromosomes this context owns
+    (chromosome sharding, what the segment representation uses); pieces: locus ranges (dist.assign_locus_ranges, bit-packed
+    rows).  The founder panel of a chromosome does not depend on the sharding."""
+    pcs = shard_pieces(cfg, chrs_local, pieces)
+    if pcs != [(c, 0, cfg["n_loci"][c]) for c in range(len(cfg["chrs"]))]:
+        eng.set_chromosome_ids([c for c, _, _ in pcs])
     segments_only = bool(cfg.get("segments"))
-    for k, c in enumerate(chrs_local):
+    for k, (c, s0, s1) in enumerate(pcs):
         if not segments_only:
-            eng.set_loci(k, cfg["loci"][c])
+            eng.set_loci(k, cfg["loci"][c][s0:s1])
     eng.set_population(0, avoid_inbreeding=False, random_mating=cfg["rm"], mm_percent=0.0)
-    for k, c in enumerate(chrs_local):
+    for k, (c, s0, s1) in enumerate(pcs):
         bp, cm, p = cfg["maps"][c]
         eng.set_genetic_map(0, k, bp, p, int(bp[1] - bp[0]))
         if not segments_only:
-            eng.set_founder_panel_packed(0, k, founder_words(cfg, c, np.random.default_rng([panel_seed, c])))
+            w = founder_words(cfg, c, np.random.default_rng([panel_seed, c]))
+            eng.set_founder_panel_packed(0, k, w[:, s0 // 32:(s1 + 31) // 32])
         cv = cfg["cvs"][c]
-        eng.set_cv(0, 0, k, cv["bp"], cv["a"], cv["d"], cv["val"])
+        if segments_only:
+            eng.set_cv(0, 0, k, cv["bp"], cv["a"], cv["d"], cv["val"])
+        else:
+            eng.set_cv(0, 0, k, *_cv_slice(cv, s0, s1, cv["val"]))
     eng.set_pheno_scheme(0, 0, va=va, vd=vd, ve=ve, vc=0.0, vf=0.0, omega=1.0, beta=0.0, lam=1.0)
 
 

@@ -260,7 +260,9 @@ int ge_download_draws(ge_ctx *ctx, int pop, uint64_t *father, uint64_t *mother, 
 #define GE_PHASE_CV_AD 4                /* causal-variant planes, allele counts, genetic values */
 #define GE_PHASE_PHENOTYPE 5            /* noise, scaling, phenotypes, mating and selection values */
 #define GE_KERNEL_COUNT 8
-int ge_set_profiling(ge_ctx *ctx, int enabled);
+/* level 0: off; 1: CUDA events around the dominant kernel on its own stream (what `roofline.achieved` is computed from; the control
+ * chain may still replay as a graph); 2: also around the phases of the control chain (GE_PHASE_*; the chain is then queued kernel by kernel) */
+int ge_set_profiling(ge_ctx *ctx, int level);
 int ge_get_kernel_time(ge_ctx *ctx, int kernel, double *total_ms, uint64_t *launches, uint64_t *algorithmic_bytes);
 int ge_reset_kernel_times(ge_ctx *ctx);
 int ge_get_launch_count(ge_ctx *ctx, uint64_t *launches);   /* every kernel this context launched */

@@ -10,7 +10,7 @@ import torch
 
 from geneevolve_b200 import capi, dist as gdist
 from golden_util import Golden
-from test_sharding_gloo import configure_subset, run_generations
+from test_sharding_gloo import configure_pieces, run_generations, shard_of
 
 pytestmark = pytest.mark.gpu
 
@@ -19,9 +19,12 @@ REPS = {"bits": (capi.GE_REP_BITS, 0), "segments": (capi.GE_REP_SEGMENTS, 0), "s
         "bits+segments": (capi.GE_REP_BITS | capi.GE_REP_SEGMENTS, 0)}
 
 
+@pytest.mark.parametrize("split", ["chromosomes", "locus-tiles"])
 @pytest.mark.parametrize("rep", sorted(REPS))
 @pytest.mark.parametrize("name", ["B_rm_mut", "A_am_pois", "D_two_pops"])
-def test_two_sharded_contexts_match_one(cuda_lib, name, rep):
+def test_two_sharded_contexts_match_one(cuda_lib, name, rep, split):
+    if split == "locus-tiles" and rep != "bits":
+        pytest.skip("founder segments are sharded by whole chromosomes (a part has no loci)")
     G = Golden(name)
     n_gen = min(G.G, 3)
     representation, seg_capacity = REPS[rep]
@@ -31,8 +34,7 @@ def test_two_sharded_contexts_match_one(cuda_lib, name, rep):
     ref = run_generations(G, single, n_gen, segments=segs)
 
     world = 2
-    weights = [len(G[f"in.p0.c{c}.panel_pos"]) for c in range(G.n_chr)]
-    parts = gdist.assign_chromosomes(weights, world)
+    parts = shard_of(G, split, world)
     barrier = threading.Barrier(world)
     slots = [None] * world
     results, errors = [None] * world, []
@@ -54,7 +56,7 @@ def test_two_sharded_contexts_match_one(cuda_lib, name, rep):
             kw = G.engine_kwargs(rng_mode=capi.GE_RNG_PHILOX, representation=representation, seg_capacity=seg_capacity, capacity=G.philox_capacity())
             kw.update(n_chr=len(parts[rank]), rank=rank, world_size=world)
             eng = capi.Engine(cuda_lib, **kw)
-            configure_subset(G, eng, parts[rank])
+            configure_pieces(G, eng, parts[rank])
             eng.set_allreduce(make_hook(rank))
             results[rank] = run_generations(G, eng, n_gen, segments=segs)
         except Exception as e:  # pragma: no cover
@@ -72,8 +74,8 @@ def test_two_sharded_contexts_match_one(cuda_lib, name, rep):
         assert np.array_equal(out["ind"]["ids"], ref["ind"]["ids"]) and np.array_equal(out["ind"]["sex"], ref["ind"]["sex"])
         for k in "ADGCEFP":
             np.testing.assert_allclose(out["ind"][k], ref["ind"][k], rtol=1e-10, atol=1e-12)
-        for k, c in enumerate(parts[rank]):
-            assert np.array_equal(out["hap"][k], ref["hap"][c])
+        for k, (c, s0, s1) in enumerate(parts[rank]):
+            assert np.array_equal(out["hap"][k], ref["hap"][c][:, s0:s1])
             if segs:
                 for key in ("seg_off", "seg", "mut_off", "mut_bp"):
                     assert np.array_equal(out["seg"][k][key], ref["seg"][c][key]), f"rank {rank} chromosome {c}: {key}"
