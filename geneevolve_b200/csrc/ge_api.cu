@@ -33,7 +33,13 @@ static int alloc_gen_state(ge_ctx *ctx, GenState &s) {
 // expected draws of one generation at full capacity (+ ten standard deviations): what the draw buffers are sized for once
 static uint64_t draw_bound(double mean) { return (uint64_t)(mean + 10.0 * std::sqrt(mean + 1.0)) + 4096; }
 
-void ge_ctx::drop_graphs() {}
+void ge_ctx::drop_graphs() {
+    for (auto &kv : graphs) {
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    graphs.clear();
+}
 
 // ge_ctx::pull_state — see ge_context.cuh
 int ge_ctx::pull_state(const char *where) {
@@ -310,6 +316,7 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
         CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         for (PopDev &P : c->pop) for (DrawSet &D : P.ds) CUDA_TRY(cudaEventCreateWithFlags(&D.bulk_done, cudaEventDisableTiming));
+        for (PopDev &P : c->pop) CUDA_TRY(cudaEventCreateWithFlags(&P.ev_ready, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         for (SortLane &l : c->lane) { CUDA_TRY(cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, prio_hi)); CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming)); }
         CUDA_TRY(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -355,6 +362,7 @@ int ge_destroy(ge_ctx *ctx) {
             seg_release(ctx, s.seg);
         }
         mate_release(ctx, P.mate);
+        if (P.ev_ready) cudaEventDestroy(P.ev_ready);
     }
     for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_bkt_off, &ctx->d_bkt_shift, &ctx->d_bkt, &ctx->d_LA, &ctx->d_cv_bitpos, &ctx->xo_stash, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
                    &ctx->d_cv_block_off, &ctx->d_cv_word_off, &ctx->d_cv_word_blk, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks, &ctx->bulk_scan_blocks,
@@ -909,12 +917,15 @@ static StepRow step_row(int gen, const ge_gen_params &gp) {
     r.mat_cor = gp.mat_cor; r.sel_par1 = gp.selection_par1; r.sel_par2 = gp.selection_par2;
     return r;
 }
+// the host's copy of the row follows the device's (replayed draws push the whole struct later in the step)
+static void host_row(PopDev &P, const StepRow &r) {
+    P.hs.gen = r.gen; P.hs.sel_func = r.sel_func; P.hs.offspring_dist = r.offspring_dist; P.hs.pop_size = r.pop_size; P.hs.mat_cor = r.mat_cor;
+    P.hs.u11 = std::sqrt(1.0 - r.mat_cor * r.mat_cor); P.hs.sel_par1 = r.sel_par1; P.hs.sel_par2 = r.sel_par2; P.hs.n_inbreed = 0;
+}
 static int enqueue_step_begin(ge_ctx *ctx, int pop, int gen, const ge_gen_params &gp) {
     PopDev &P = ctx->pop[pop];
     const StepRow r = step_row(gen, gp);
-    // the host's copy follows (replayed draws push the whole struct later in the step)
-    P.hs.gen = r.gen; P.hs.sel_func = r.sel_func; P.hs.offspring_dist = r.offspring_dist; P.hs.pop_size = r.pop_size; P.hs.mat_cor = r.mat_cor;
-    P.hs.u11 = std::sqrt(1.0 - r.mat_cor * r.mat_cor); P.hs.sel_par1 = r.sel_par1; P.hs.sel_par2 = r.sel_par2; P.hs.n_inbreed = 0;
+    host_row(P, r);
     step_begin_kernel<<<1, 1, 0, ctx->stream>>>(P.d_ss, r);
     return ctx->check_launch("step_begin");
 }
@@ -984,7 +995,7 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
     // the other draw set; the bulk stream may still read it for the generation before last
     P.dcur ^= 1;
     DrawSet &D = P.draws();
-    if (D.bulk_pending) { CUDA_TRY(cudaStreamWaitEvent(st, D.bulk_done, 0)); D.bulk_pending = false; }
+    GE_TRY(ctx->wait_bulk_done(D));
     if (dr) {
         const uint64_t n_off = dr->n_offspring, n_slots = n_off * C * 2;
         GE_TRY(upload_u64_as_u32(ctx, D.father, dr->father, n_off, tmp, "father"));
@@ -1058,26 +1069,36 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
             xo_to_flips_kernel<<<nblk(n_slots, 128), 128, 0, st>>>(ctx->genome(), n_slots, D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.flips.as<uint32_t>());
             GE_TRY(ctx->check_launch("xo_to_flips"));
         }
-        cudaStream_t bulk = ctx->serial ? st : ctx->bulk;
-        CUDA_TRY(cudaEventRecord(ctx->ev_ready, st));
-        CUDA_TRY(cudaStreamWaitEvent(bulk, ctx->ev_ready, 0));
-        ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0, 0, 0};
-        if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, bulk)); }
         // one short-lived CTA per offspring (control-stream kernels get SM slots quickly); CTAs beyond the device-side count exit at once
-        unsigned grid = (unsigned)std::min<uint64_t>(dr ? dr->n_offspring : cap, 1u << 20);
-        propagate_bits_kernel<<<grid, PROP_THREADS, prop_smem_bytes(C), bulk>>>(ctx->genome(), ctx->tiles(), &ss->dc[P.dcur], par.hap.as<uint32_t>(), par.rowmap, off.hap.as<uint32_t>(), D.father.as<uint32_t>(),
-                                                                                D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.flips.as<uint32_t>(), D.start_hap.as<uint8_t>());
-        GE_TRY(ctx->check_launch("propagate_bits"));
-        if (ctx->profiling) {
-            CUDA_TRY(cudaEventRecord(evp.b, bulk));
-            evp.bytes_per_offspring = ctx->n_loci_total / 2;  // 0.5 byte per individual-locus; the offspring count is taken from the step's read-back
-            evp.pop = pop;
-            ctx->ev_pending.push_back(evp);
-        }
-        CUDA_TRY(cudaEventRecord(D.bulk_done, bulk));
-        D.bulk_pending = true;
-        // thin control kernels only pay off while the bulk copy is longer than the control chain (~0.75 ms at 100k individuals)
-        ctx->note_bulk((double)cap * ctx->W * 16.0);
+        const unsigned grid = (unsigned)std::min<uint64_t>(dr ? dr->n_offspring : cap, 1u << 20);
+        const Genome gnm = ctx->genome();
+        const TileTable tiles = ctx->tiles();
+        const DrawCounts *dc = &ss->dc[P.dcur];
+        const uint32_t *par_rows = par.hap.as<uint32_t>(), *rowmap = par.rowmap, *fa = D.father.as<uint32_t>(), *mo = D.mother.as<uint32_t>(), *fl = D.flips.as<uint32_t>();
+        uint32_t *off_rows = off.hap.as<uint32_t>();
+        const uint64_t *xo_off = D.xo_off.as<uint64_t>();
+        const uint8_t *start = D.start_hap.as<uint8_t>();
+        const size_t smem = prop_smem_bytes(C);
+        DrawSet *Dp = &D;
+        const double bulk_bytes = (double)cap * ctx->W * 16.0;
+        GE_TRY(ctx->to_bulk(P.ev_ready, [=]() -> int {
+            cudaStream_t bulk = ctx->serial ? ctx->stream : ctx->bulk;
+            ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0, 0, 0};
+            if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, bulk)); }
+            propagate_bits_kernel<<<grid, PROP_THREADS, smem, bulk>>>(gnm, tiles, dc, par_rows, rowmap, off_rows, fa, mo, xo_off, fl, start);
+            GE_TRY(ctx->check_launch("propagate_bits"));
+            if (ctx->profiling) {
+                CUDA_TRY(cudaEventRecord(evp.b, bulk));
+                evp.bytes_per_offspring = ctx->n_loci_total / 2;  // 0.5 byte per individual-locus; the offspring count comes with the step's read-back
+                evp.pop = pop;
+                ctx->ev_pending.push_back(evp);
+            }
+            CUDA_TRY(cudaEventRecord(Dp->bulk_done, bulk));
+            Dp->bulk_pending = true;
+            // thin control kernels only pay off while the bulk copy is longer than the control chain (~0.75 ms at 100k individuals)
+            ctx->note_bulk(bulk_bytes);
+            return GE_OK;
+        }));
         bulk_launched = true;
     }
     // ---- causal-variant planes
@@ -1159,41 +1180,151 @@ int ge_do_migration(ge_ctx *ctx, int gen, const double *row) {  // ras_do_migrat
     return migrate(ctx, gen, row);
 }
 
+// everything of one generation except the final read-back (sim_next_generation :1890-2082, the reference's order)
+static int enqueue_generation(ge_ctx *ctx, int gen, const ge_gen_params *gp, const double *mig, const ge_draws *dr, int &reproduced, bool &migrated) {
+    const int nf = ctx->cfg.n_phen, np = ctx->cfg.n_pop;
+    for (int p = 0; p < np; p++) {
+        GE_TRY(enqueue_step_begin(ctx, p, gen, gp[p]));
+        if (!dr) { ge_ctx::PhaseTimer timer(ctx, GE_PHASE_MATE); GE_TRY(enqueue_mate(ctx, p, gp[p])); }
+        GE_TRY(enqueue_reproduce(ctx, p, dr ? &dr[p] : nullptr));
+        reproduced = p + 1;
+        GE_TRY(enqueue_AD(ctx, p));
+        {
+            ge_ctx::PhaseTimer timer(ctx, GE_PHASE_PHENOTYPE);
+            const uint64_t n = dr ? dr[p].n_offspring : 0;
+            for (int f = 0; f < nf; f++) GE_TRY(enqueue_GEF(ctx, p, f, false, (dr && dr[p].e_raw) ? dr[p].e_raw + (uint64_t)f * n : nullptr, nullptr));
+        }
+    }
+    for (int f = 0; f < nf; f++) GE_TRY(ge_environmental_effects_specific_to_each_population(ctx, f));
+    for (int p = 0; p < np; p++) GE_TRY(enqueue_mv_sv(ctx, p));
+    if (np > 1 && mig) {
+        GE_TRY(ctx->pull_state("generation"));   // migration builds its gather lists on the host
+        GE_TRY(seg_finish_all(ctx));
+        GE_TRY(migrate(ctx, gen, mig));
+        migrated = true;
+    }
+    for (int p = 0; p < np; p++) if (ctx->needs_prev) GE_TRY(enqueue_save_prev(ctx, p));
+    return GE_OK;
+}
+
+// ---- the control chain of a generation as a CUDA graph ----
+// With every size on the device, no kernel argument of the chain changes from one generation to the next except the generation-table
+// row (step_begin_kernel's argument) and which of the two buffer sets is read or written (two graphs, by parity).  The launch-bound
+// configurations (1 000 - 10 000 individuals: forty kernels of a few microseconds) then cost one graph launch, one node-parameter
+// update and one read-back per generation.  The bulk-stream work (bit-packed copy, segment plan + gather) stays outside the graph —
+// it overlaps the NEXT generation's chain, which a graph launched behind it could not — tied in by external event nodes.
+static bool graphable(ge_ctx *ctx, const double *mig, const ge_draws *dr) {
+    if (!ctx->use_graph || dr || mig || ctx->cfg.rng_mode != GE_RNG_PHILOX || ctx->phase_timing || ctx->allreduce || ctx->serial || ctx->cfg.n_pop != 1) return false;
+    for (double g : ctx->gamma) if (g != 0) return false;
+    if (ctx->segs() && (ctx->cfg.seg_capacity == 0 || ctx->cv_from_segments)) return false;   // the host sizes the segment buffer between the passes
+    for (PopDev &P : ctx->pop) if (P.has_mut || P.st[P.cur].has_hm || P.st[P.cur].rowmap) return false;   // the mutation pass waits for the bulk copy mid-chain
+    return true;
+}
+static void replay_host_state(ge_ctx *ctx, int p, int gen, const ge_gen_params &gp) {   // what enqueue_* change on the host
+    PopDev &P = ctx->pop[p];
+    host_row(P, step_row(gen, gp));
+    P.dcur ^= 1;
+    P.have_couple_of = true; P.have_e_raw = true;
+    GenState &off = P.st[P.cur ^ 1];
+    off.has_hm = false; off.rowmap = nullptr;
+    if (ctx->segs()) off.seg.valid = true;
+    P.cur ^= 1;
+}
+static int step_with_graph(ge_ctx *ctx, int gen, const ge_gen_params *gp, int &reproduced) {
+    const int np = ctx->cfg.n_pop;
+    std::string key;
+    for (int p = 0; p < np; p++) {
+        PopDev &P = ctx->pop[p];
+        key += (char)('0' + P.cur + 2 * P.dcur + 4 * (P.RM ? 1 : 0) + 8 * ((gp[p].offspring_dist == 'p' || gp[p].offspring_dist == 'P') ? 1 : 0));
+    }
+    key += ctx->bulk_busy ? 'b' : 'i';
+    key += (char)('A' + ctx->thin_now);
+    ge_ctx::StepGraph &G = ctx->graphs[key];
+    if (G.epoch != ctx->graph_epoch) {   // a buffer moved since this graph was recorded (or warmed): its nodes hold stale pointers
+        if (G.exec) cudaGraphExecDestroy(G.exec);
+        if (G.graph) cudaGraphDestroy(G.graph);
+        G = ge_ctx::StepGraph();
+        G.epoch = ctx->graph_epoch;
+    }
+    bool dummy = false;
+    if (!G.exec && G.warm < 1) {   // first pass with this key: queued kernel by kernel (it may still allocate)
+        int rc = enqueue_generation(ctx, gen, gp, nullptr, nullptr, reproduced, dummy);
+        if (rc == GE_OK && G.warm >= 0 && ctx->graph_epoch == G.epoch) G.warm++;
+        return rc;
+    }
+    if (!G.exec) {   // record
+        const uint64_t launches0 = ctx->launches;
+        struct Saved { int cur, dcur; } saved[16];
+        for (int p = 0; p < np; p++) saved[p] = {ctx->pop[p].cur, ctx->pop[p].dcur};
+        ctx->deferred.clear();
+        ctx->capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = e == cudaSuccess ? enqueue_generation(ctx, gen, gp, nullptr, nullptr, reproduced, dummy) : GE_ERR_CUDA;
+        cudaGraph_t g = nullptr;
+        if (e == cudaSuccess) e = cudaStreamEndCapture(ctx->stream, &g);
+        ctx->capturing = false;
+        if (rc == GE_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&G.exec, g, 0);
+        if (rc != GE_OK || e != cudaSuccess || !G.exec) {   // not capturable after all: back to plain launches, for good
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            G.exec = nullptr; G.warm = -1000000;
+            ctx->deferred.clear();
+            ctx->launches = launches0;
+            for (int p = 0; p < np; p++) { ctx->pop[p].cur = saved[p].cur; ctx->pop[p].dcur = saved[p].dcur; }
+            reproduced = 0;
+            return enqueue_generation(ctx, gen, gp, nullptr, nullptr, reproduced, dummy);
+        }
+        G.graph = g;
+        G.bulk = std::move(ctx->deferred);
+        ctx->deferred.clear();
+        G.launches = ctx->launches - launches0;
+        size_t n_nodes = 0;
+        CUDA_TRY(cudaGraphGetNodes(g, nullptr, &n_nodes));
+        std::vector<cudaGraphNode_t> nodes(n_nodes);
+        CUDA_TRY(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
+        G.begin_nodes.assign(np, nullptr);
+        for (cudaGraphNode_t nd : nodes) {
+            cudaGraphNodeType ty;
+            CUDA_TRY(cudaGraphNodeGetType(nd, &ty));
+            if (ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp{};
+            CUDA_TRY(cudaGraphKernelNodeGetParams(nd, &kp));
+            if (kp.func != (void *)step_begin_kernel) continue;
+            StepState *target = *static_cast<StepState **>(kp.kernelParams[0]);
+            for (int p = 0; p < np; p++) if (ctx->pop[p].d_ss == target) G.begin_nodes[p] = nd;
+        }
+        for (int p = 0; p < np; p++) if (!G.begin_nodes[p]) return fail(GE_ERR_CUDA, "captured generation graph has no step_begin node");
+        // the host state advanced while recording; the graph itself has not run yet
+    } else {         // replay: the one argument that changes, then the host-side bookkeeping enqueue_* would have done
+        for (int p = 0; p < np; p++) {
+            StepState *d = ctx->pop[p].d_ss;
+            StepRow r = step_row(gen, gp[p]);
+            void *args[2] = {&d, &r};
+            cudaKernelNodeParams kp{};
+            kp.func = (void *)step_begin_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+            CUDA_TRY(cudaGraphExecKernelNodeSetParams(G.exec, G.begin_nodes[p], &kp));
+            replay_host_state(ctx, p, gen, gp[p]);
+            reproduced = p + 1;
+        }
+        ctx->launches += G.launches;
+    }
+    CUDA_TRY(cudaGraphLaunch(G.exec, ctx->stream));
+    for (auto &fn : G.bulk) GE_TRY(fn());
+    return GE_OK;
+}
+
 int ge_step_generation(ge_ctx *ctx, int gen, const ge_gen_params *gp, const double *mig, const ge_draws *dr) {  // sim_next_generation :1890-2082
     CHECK_CTX(ctx);
     if (!gp) return fail(GE_ERR_INVALID, "null params");
     if (!ctx->gen0_done) return fail(GE_ERR_INVALID, "ge_step_generation before ge_init_generation0");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
-    int nf = ctx->cfg.n_phen, np = ctx->cfg.n_pop;
+    const int np = ctx->cfg.n_pop;
     if (dr) for (int p = 0; p < np; p++) GE_TRY(validate_draws(ctx, ctx->pop[p], &dr[p], ctx->pop[p].st[ctx->pop[p].cur].n));
     else if (ctx->cfg.rng_mode != GE_RNG_PHILOX) return fail(GE_ERR_INVALID, "replay mode needs draws");
     int reproduced = 0;
     bool migrated = false;
-    auto body = [&]() -> int {
-        for (int p = 0; p < np; p++) {
-            GE_TRY(enqueue_step_begin(ctx, p, gen, gp[p]));
-            if (!dr) { ge_ctx::PhaseTimer timer(ctx, GE_PHASE_MATE); GE_TRY(enqueue_mate(ctx, p, gp[p])); }
-            GE_TRY(enqueue_reproduce(ctx, p, dr ? &dr[p] : nullptr));
-            reproduced = p + 1;
-            GE_TRY(enqueue_AD(ctx, p));
-            {
-                ge_ctx::PhaseTimer timer(ctx, GE_PHASE_PHENOTYPE);
-                const uint64_t n = dr ? dr[p].n_offspring : 0;
-                for (int f = 0; f < nf; f++) GE_TRY(enqueue_GEF(ctx, p, f, false, (dr && dr[p].e_raw) ? dr[p].e_raw + (uint64_t)f * n : nullptr, nullptr));
-            }
-        }
-        for (int f = 0; f < nf; f++) GE_TRY(ge_environmental_effects_specific_to_each_population(ctx, f));
-        for (int p = 0; p < np; p++) GE_TRY(enqueue_mv_sv(ctx, p));
-        if (np > 1 && mig) {
-            GE_TRY(ctx->pull_state("generation"));   // migration builds its gather lists on the host
-            GE_TRY(seg_finish_all(ctx));
-            GE_TRY(migrate(ctx, gen, mig));
-            migrated = true;
-        }
-        for (int p = 0; p < np; p++) if (ctx->needs_prev) GE_TRY(enqueue_save_prev(ctx, p));
-        return ctx->pull_state("generation");   // THE host synchronisation of the generation: sizes for the host's bookkeeping, errors
-    };
-    int rc = body();
+    int rc = graphable(ctx, mig, dr) ? step_with_graph(ctx, gen, gp, reproduced) : enqueue_generation(ctx, gen, gp, mig, dr, reproduced, migrated);
+    if (rc == GE_OK) rc = ctx->pull_state("generation");   // THE host synchronisation of the generation: sizes for the host's bookkeeping, errors
     if (rc != GE_OK && !migrated) for (int p = 0; p < reproduced; p++) rollback_reproduce(ctx, p);
     return rc;
 }

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
+#include <map>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -102,6 +104,7 @@ struct PopDev {
     Buf mig_pop[1], mig_idx[1];                 // gather lists of a migration (control stream only)
     Buf rowmap_buf[2];                          // row maps of the last two migrations (by generation parity; the bulk stream reads them late)
     uint64_t prev_n = 0;
+    cudaEvent_t ev_ready = nullptr;   // control stream -> bulk stream: this population's draws are complete
     // device-resident sizes of the generation step (ge_kernels.cuh) and the host's copy of them
     StepState *d_ss = nullptr;
     StepState hs{};
@@ -217,7 +220,39 @@ struct ge_ctx {
         if (pinned_chunks.empty() || pinned_used == 512) { uint64_t *c = nullptr; if (cudaMallocHost(&c, 512 * 8) != cudaSuccess) return nullptr; pinned_chunks.push_back(c); pinned_used = 0; }
         return pinned_chunks.back() + pinned_used++;
     }
+    // ---- a generation's control chain as a CUDA graph (ge_api.cu: ge_step_generation) ----
+    struct StepGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        std::vector<cudaGraphNode_t> begin_nodes;      // the step_begin_kernel node of every population: the one parameter update per replay
+        std::vector<std::function<int()>> bulk;        // what follows every launch on the bulk stream (it runs a generation behind)
+        uint64_t launches = 0, epoch = 0;
+        int warm = 0;                                  // eager runs of this key since the buffers last moved
+    };
+    std::map<std::string, StepGraph> graphs;
+    bool capturing = false;
+    std::vector<std::function<int()>> deferred;
     void drop_graphs();
+    // Hand-off control stream -> bulk stream: fn (launches on the bulk stream) runs behind everything queued on the control stream so
+    // far.  Queued directly: event record, wait, fn.  While a generation is being captured: an external event-record node goes into
+    // the graph, fn is kept and run (wait + launches) after every launch of that graph.
+    int to_bulk(cudaEvent_t ev, std::function<int()> fn) {
+        cudaStream_t b = serial ? stream : bulk;
+        if (!capturing) {
+            CUDA_TRY(cudaEventRecord(ev, stream));
+            CUDA_TRY(cudaStreamWaitEvent(b, ev, 0));
+            return fn();
+        }
+        CUDA_TRY(cudaEventRecordWithFlags(ev, stream, cudaEventRecordExternal));
+        deferred.push_back([=]() -> int { CUDA_TRY(cudaStreamWaitEvent(b, ev, 0)); return fn(); });
+        return GE_OK;
+    }
+    // the control stream must not overwrite a draw set the bulk stream still reads
+    int wait_bulk_done(DrawSet &D) {
+        if (capturing) { CUDA_TRY(cudaStreamWaitEvent(stream, D.bulk_done, cudaEventWaitExternal)); return GE_OK; }
+        if (D.bulk_pending) { CUDA_TRY(cudaStreamWaitEvent(stream, D.bulk_done, 0)); D.bulk_pending = false; }
+        return GE_OK;
+    }
     std::vector<EvPair> ev_pending;            // per-launch events of profiled kernels, resolved lazily (no sync in the loop)
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t get_event() {

@@ -646,10 +646,9 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t) {
     cudaStream_t st = async ? ctx->bulk : ctx->stream;
     uint64_t cap = 0;
     if (fixed) { GE_TRY(ctx->ensure_exact(off.seg.seg, ctx->cfg.seg_capacity * esz)); cap = ctx->cfg.seg_capacity; }
-    if (async) {
-        CUDA_TRY(cudaEventRecord(ctx->ev_ready, ctx->stream));   // the draws (and whatever the control stream did to the parental lists) are complete
-        CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_ready, 0));
-    }
+    PopDev *Pp = &P; GenState *parp = &par, *offp = &off; DrawSet *Dp = &D;
+    auto chain = [=]() mutable -> int {
+    PopDev &P = *Pp; GenState &par = *parp, &off = *offp; DrawSet &D = *Dp;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (ctx->profiling) for (cudaEvent_t &e : ev) e = ctx->get_event();
     auto grow = [&]() -> int {   // seg_capacity == 0: the total comes to the host, the buffer grows geometrically (a reallocation of tens of GB costs more than a generation)
@@ -713,13 +712,17 @@ static int seg_recombine(ge_ctx *ctx, int pop, uint64_t) {
         p1.count_src = slot; p1.count_scale = esz; p2.count_src = slot; p2.count_scale = 2 * esz;
         ctx->ev_pending.push_back(p1); ctx->ev_pending.push_back(p2);
     }
-    off.seg.valid = true;
     if (async) {
         CUDA_TRY(cudaEventRecord(D.bulk_done, st));   // the draw set is read until here
         D.bulk_pending = true;
         // a long copy is in flight: the heavy control kernels of the next generation run on thin grids beside it (as for the bit-packed copy)
         if (!ctx->bits()) ctx->note_bulk((double)par.seg.n_seg * 2.0 * (double)esz);
     }
+    return GE_OK;
+    };
+    // the draws (and whatever the control stream did to the parental lists) are complete: the chain goes to the bulk stream, or runs in place
+    if (async) GE_TRY(ctx->to_bulk(P.ev_ready, chain)); else GE_TRY(chain());
+    off.seg.valid = true;
     return GE_OK;
 }
 
