@@ -323,6 +323,12 @@ class Engine:
         self._call("download_haplotypes", self.ctx, pop, chr_, _ptr(out, _u8p))
         return out
 
+    def haplotypes_from_segments(self, pop, chr_):
+        n = self.population_size(pop)
+        out = np.zeros((2 * n, self.n_loci[chr_]), np.uint8)
+        self._call("download_haplotypes_from_segments", self.ctx, pop, chr_, _ptr(out, _u8p))
+        return out
+
     def haplotypes_packed(self, pop, chr_):
         n = self.population_size(pop)
         out = np.zeros((2 * n, (self.n_loci[chr_] + 31) // 32), np.uint32)
@@ -349,6 +355,19 @@ class Engine:
         a, b = C.c_uint64(), C.c_uint64()
         self._call("compact_segments", self.ctx, pop, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def rebase_founders(self, keep_history=True):
+        """The current generation becomes the founder panel; every list restarts as one part (ge_rebase_founders)."""
+        self._call("rebase_founders", self.ctx, int(bool(keep_history)))
+
+    def segments_gen0(self, pop, chr_):
+        """The lists of one chromosome against the generation-0 founders, composed through the re-basing history."""
+        n = self.population_size(pop)
+        ns = C.c_uint64()
+        self._call("get_segment_count_gen0", self.ctx, pop, chr_, C.byref(ns))
+        off, seg = np.zeros(2 * n + 1, np.uint64), np.zeros((ns.value, 4), np.uint64)
+        self._call("download_segments_gen0", self.ctx, pop, chr_, _ptr(off, _u64p), _ptr(seg, _u64p))
+        return dict(seg_off=off, seg=seg)
 
     def segment_format(self):
         """Bytes per part in device memory: 16 (the reference's part) or 8 (packed, end implied)."""

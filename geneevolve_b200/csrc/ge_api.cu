@@ -352,7 +352,8 @@ int ge_destroy(ge_ctx *ctx) {
         for (Buf *b : {&P.d_row_off, &P.d_bp, &P.d_T, &P.d_bp_dist, &P.d_mrow_off, &P.d_mbp, &P.d_mT, &P.d_vb, &P.d_vb_off, &P.d_vb_scale, &P.d_mvb, &P.d_mvb_off, &P.d_mvb_scale, &P.d_cov_lo, &P.d_cov_hi, &P.d_omega,
                        &P.d_lambda, &P.d_vd_zero, &P.prev_P, &P.prev_F, &P.c_male, &P.c_female, &P.c_inbreed, &P.c_noff, &P.mut_off, &P.mut_bp, &P.mut_gam, &P.e_raw, &P.cnt32, &P.d_sv0, &P.founder_rows, &P.founder_cv})
             freeb(*b);
-        freeb(P.mig_pop[0]); freeb(P.mig_idx[0]); freeb(P.rowmap_buf[0]); freeb(P.rowmap_buf[1]);
+        freeb(P.mig_pop[0]); freeb(P.mig_idx[0]); freeb(P.rowmap_buf[0]); freeb(P.rowmap_buf[1]); freeb(P.founder_root);
+        for (PopDev::SegSnapshot &H : P.history) { freeb(H.off); freeb(H.seg); }
         for (DrawSet &D : P.ds) {
             for (Buf *b : {&D.father, &D.mother, &D.couple_of, &D.xo_off, &D.xo_bp, &D.flips, &D.start_hap}) freeb(*b);
             if (D.bulk_done) cudaEventDestroy(D.bulk_done);
@@ -1401,9 +1402,25 @@ int ge_download_haplotypes(ge_ctx *ctx, int pop, int c, uint8_t *al) {
     ctx->release(tmp);
     return GE_OK;
 }
+int ge_download_haplotypes_from_segments(ge_ctx *ctx, int pop, int c, uint8_t *al) {   // ras_convert_interval_to_hap_matrix :1186-1230, whatever else the context carries
+    CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_download_haplotypes_from_segments needs GE_REP_SEGMENTS");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(seg_finish_all(ctx));
+    GenState &S = ctx->pop[pop].st[ctx->pop[pop].cur];
+    uint64_t tot = (uint64_t)2 * S.n * ctx->chr_nloci[c];
+    if (tot == 0) return GE_OK;
+    Buf tmp;
+    GE_TRY(ctx->ensure_exact(tmp, tot));
+    GE_TRY(seg_materialise(ctx, pop, c, tmp.as<uint8_t>()));
+    CUDA_TRY(cudaMemcpyAsync(al, tmp.p, tot, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->release(tmp);
+    return GE_OK;
+}
 int ge_download_haplotypes_packed(ge_ctx *ctx, int pop, int c, uint32_t *words) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
-    if (!ctx->bits()) return fail(GE_ERR_UNSUPPORTED, "packed download needs GE_REP_BITS");
+    if (!ctx->bits() && ctx->seg_per_thread) return fail(GE_ERR_UNSUPPORTED, "packed download from segment lists that need not be sorted: use ge_download_haplotypes");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     GenState &S = ctx->pop[pop].st[ctx->pop[pop].cur];
     uint32_t nw = (ctx->chr_nloci[c] + 31) / 32;
@@ -1411,10 +1428,12 @@ int ge_download_haplotypes_packed(ge_ctx *ctx, int pop, int c, uint32_t *words) 
     if (tot == 0) return GE_OK;
     Buf tmp;
     GE_TRY(ctx->ensure_exact(tmp, tot * 4));
-    GE_TRY(ctx->join_bulk());
-    gather_packed_chr_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), S.rowmap, ctx->W, ctx->chr_word_off[c], (uint32_t)(2 * S.n), nw,
-                                                                      tmp.as<uint32_t>());
-    GE_TRY(ctx->check_launch("gather_packed"));
+    if (ctx->bits()) {
+        GE_TRY(ctx->join_bulk());
+        gather_packed_chr_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), S.rowmap, ctx->W, ctx->chr_word_off[c], (uint32_t)(2 * S.n), nw,
+                                                                          tmp.as<uint32_t>());
+        GE_TRY(ctx->check_launch("gather_packed"));
+    } else GE_TRY(seg_materialise_packed(ctx, pop, c, tmp.as<uint32_t>()));
     CUDA_TRY(cudaMemcpyAsync(words, tmp.p, tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->release(tmp);
@@ -1454,6 +1473,34 @@ int ge_compact_segments(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_af
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_compact_segments needs GE_REP_SEGMENTS");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     return seg_compact(ctx, pop, n_before, n_after);
+}
+
+int ge_rebase_founders(ge_ctx *ctx, int keep_history) {
+    CHECK_CTX(ctx);
+    if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_rebase_founders needs GE_REP_SEGMENTS");
+    if (!ctx->gen0_done) return fail(GE_ERR_INVALID, "ge_rebase_founders before ge_init_generation0");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    return seg_rebase(ctx, keep_history);
+}
+int ge_get_segment_count_gen0(ge_ctx *ctx, int pop, int c, uint64_t *ns) {
+    CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_get_segment_count_gen0 needs GE_REP_SEGMENTS");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(seg_download_gen0(ctx, pop, c, ctx->gen0_off, ctx->gen0_seg));
+    ctx->gen0_pop = pop; ctx->gen0_chr = c;
+    *ns = ctx->gen0_seg.size() / 4;
+    return GE_OK;
+}
+int ge_download_segments_gen0(ge_ctx *ctx, int pop, int c, uint64_t *off, uint64_t *seg) {
+    CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_download_segments_gen0 needs GE_REP_SEGMENTS");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    if (ctx->gen0_pop != pop || ctx->gen0_chr != c) GE_TRY(seg_download_gen0(ctx, pop, c, ctx->gen0_off, ctx->gen0_seg));   // (ge_get_segment_count_gen0 leaves the composed lists here)
+    std::memcpy(off, ctx->gen0_off.data(), ctx->gen0_off.size() * 8);
+    if (!ctx->gen0_seg.empty()) std::memcpy(seg, ctx->gen0_seg.data(), ctx->gen0_seg.size() * 8);
+    ctx->gen0_pop = ctx->gen0_chr = -1;
+    std::vector<uint64_t>().swap(ctx->gen0_off); std::vector<uint64_t>().swap(ctx->gen0_seg);
+    return GE_OK;
 }
 
 int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop) {  // ras_find_cv :2752-2815 literally: scan the parts of every haplotype

@@ -94,6 +94,10 @@ struct PopDev {
     std::vector<std::vector<uint32_t>> panel_packed;  // alternative: bit-packed by the host
     uint64_t n_founder_haps = 0;
     Buf founder_rows, founder_cv;  // kept on the device for segment materialisation / ras_find_cv (GE_REP_SEGMENTS)
+    Buf founder_root;              // after a re-base: generation-0 root population of every (founder haplotype, CV) — populations with different effect tables only
+    // re-basing history (ge_rebase_founders with keep_history): the lists of the generation that became the founder panel, oldest first
+    struct SegSnapshot { Buf off, seg; uint64_t n = 0, n_seg = 0; };
+    std::vector<SegSnapshot> history;
     // device maps
     Buf d_row_off, d_bp, d_T, d_bp_dist, d_mrow_off, d_mbp, d_mT, d_cov_lo, d_cov_hi;
     Buf d_vb, d_vb_off, d_vb_scale, d_mvb, d_mvb_off, d_mvb_scale;   // value indexes of the survival tables
@@ -147,6 +151,9 @@ struct ge_ctx {
     bool needs_prev = false;        // some phenotype has vertical transmission (vf > 0): keep the previous generation's P and F
     bool use_graph = true;          // replay the control chain of a generation as a CUDA graph where possible (GE_FLAG_NO_GRAPH)
     uint64_t n_loci_total = 0;      // loci of this context over all its chromosomes
+    int n_rebase = 0;               // ge_rebase_founders calls so far
+    std::vector<uint64_t> gen0_off, gen0_seg;   // lists composed by ge_get_segment_count_gen0, handed out by ge_download_segments_gen0
+    int gen0_pop = -1, gen0_chr = -1;
     int thin = 8;   // CTAs per SM the heavy control-stream kernels may take while a bulk copy is in flight (0 = no limit)
     bool bulk_busy = false;
     Buf seg_desc, seg_iv_off;       // copy descriptor and output offset of every interval (seg_plan_kernel -> seg_gather_kernel)

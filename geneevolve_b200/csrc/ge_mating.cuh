@@ -27,14 +27,20 @@ __device__ __forceinline__ uint64_t sortable(double x) {  // monotone map double
 
 // thinning (:2105-2117 / :2186-2216): number of list entries individual i contributes — males in the low, females in
 // the high 32 bits, so ONE scan gives the offsets into both lists
+// replayed draws (ge_mate_replay): thin_u / mm_u are the reference's own uniforms instead of the Philox ones
 __global__ void thin_count_kernel(Stream st, const StepState *__restrict__ ss, int pop, const uint64_t *__restrict__ n_ind, const uint8_t *__restrict__ sex,
-                                  const double *__restrict__ svf, int with_mm, double mm, uint64_t *__restrict__ cnt) {
+                                  const double *__restrict__ svf, int with_mm, double mm, const double *__restrict__ thin_u, const double *__restrict__ mm_u,
+                                  uint64_t *__restrict__ cnt) {
     const uint64_t n = *n_ind;
     const int gen = ss->gen;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t w[4];
-        draw(st, P_THIN, pop, gen, i, 0, 0, w);
-        double r = u01(w[0], w[1]), r2 = u01(w[2], w[3]);
+        double r, r2;
+        if (thin_u) { r = thin_u[i]; r2 = mm_u[i]; }
+        else {
+            uint32_t w[4];
+            draw(st, P_THIN, pop, gen, i, 0, 0, w);
+            r = u01(w[0], w[1]); r2 = u01(w[2], w[3]);
+        }
         uint64_t c = 0;
         if (r < svf[i]) c = (with_mm && r2 < mm) ? 2u : 1u;
         cnt[i] = sex[i] == 1 ? c : (sex[i] == 2 ? c << 32 : 0ull);
@@ -69,15 +75,21 @@ __global__ void thin_fill_kernel(const uint64_t *__restrict__ n_ind, const uint6
     }
 }
 __global__ void rm_pair_kernel(Stream st, const StepState *__restrict__ ss, int pop, const uint32_t *__restrict__ list_m, const uint32_t *__restrict__ list_f,
+                               const uint32_t *__restrict__ idx_m /* replayed index draws, or null */, const uint32_t *__restrict__ idx_f,
                                uint32_t *__restrict__ male, uint32_t *__restrict__ female, uint8_t *__restrict__ inbreed, int32_t *__restrict__ noff) {
     if (ss->err & SE_FATAL) return;
     const uint64_t n_couples = ss->n_couples, n_m = ss->n_m, n_f = ss->n_f;
     const int gen = ss->gen;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_couples; k += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t w[4];
-        draw(st, P_RM_PAIR, pop, gen, k, 0, 0, w);
-        male[k] = list_m[((uint64_t)w[0] * n_m) >> 32];
-        female[k] = list_f[((uint64_t)w[1] * n_f) >> 32];
+        uint64_t im, jf;
+        if (idx_m) { im = min((uint64_t)idx_m[k], n_m - 1); jf = min((uint64_t)idx_f[k], n_f - 1); }
+        else {
+            uint32_t w[4];
+            draw(st, P_RM_PAIR, pop, gen, k, 0, 0, w);
+            im = ((uint64_t)w[0] * n_m) >> 32; jf = ((uint64_t)w[1] * n_f) >> 32;
+        }
+        male[k] = list_m[im];
+        female[k] = list_f[jf];
         inbreed[k] = 0; noff[k] = 1;
     }
 }
@@ -126,6 +138,15 @@ __global__ void template_kernel(Stream st, const StepState *__restrict__ ss, int
         idx[i] = (uint32_t)i;
     }
 }
+// the same from replayed template values (ras_mvnorm's two columns as the reference drew them)
+__global__ void template_from_kernel(const StepState *__restrict__ ss, const double *__restrict__ t1, const double *__restrict__ t2, uint64_t *__restrict__ k1,
+                                     uint64_t *__restrict__ k2, uint32_t *__restrict__ idx) {
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n = ss->n2;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        k1[i] = sortable(t1[i]); k2[i] = sortable(t2[i]); idx[i] = (uint32_t)i;
+    }
+}
 __global__ void rank_scatter_kernel(const StepState *__restrict__ ss, const uint32_t *__restrict__ sorted_idx, uint32_t *__restrict__ rank) {
     if (ss->err & SE_FATAL) return;
     const uint64_t n = ss->n2;
@@ -153,6 +174,7 @@ __global__ void pair_kernel(StepState *__restrict__ ss, const uint32_t *__restri
 }
 // family sizes.  Poisson (:2329-2337): exact Poisson(lam), lam = pop_size / marriageable couples, as a sum of independent
 // Poisson(<=32) chunks, each by sequential-search inversion (ras_rpois, src/RasRandomNumber.cpp:57-67).  Fixed (:2338-2355): floor.
+// poisson: 1 = draw, 0 = fixed size, 2 = the sizes are already in noff (replayed draws): only the all-inbred check
 __global__ void family_kernel(Stream st, StepState *__restrict__ ss, int pop, int poisson, int32_t *__restrict__ noff) {
     if (ss->err & SE_FATAL) return;
     const uint64_t n = ss->n2, n_ok = n - ss->n_inbreed;
@@ -160,6 +182,7 @@ __global__ void family_kernel(Stream st, StepState *__restrict__ ss, int pop, in
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ss->err, (uint32_t)SE_ALL_INBRED);
         return;
     }
+    if (poisson == 2) return;
     const int gen = ss->gen;
     const double lam = (double)ss->pop_size / (double)n_ok;
     const int32_t nfix = (int32_t)floor((double)ss->pop_size / (double)n_ok);
@@ -313,7 +336,28 @@ static int ensure_couples(ge_ctx *ctx, PopDev &P, uint64_t n) {
     return ctx->push_state(P, offsetof(StepState, couples_cap), 8);
 }
 
-static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp) {
+// replayed mating draws -> device buffers (zero-padded to the buffers' bounds, values checked against them)
+static int upload_f64(ge_ctx *ctx, Buf &b, const double *src, uint64_t n, uint64_t bound) {
+    GE_TRY(ctx->ensure(b, std::max<uint64_t>(bound, 1) * 8));
+    CUDA_TRY(cudaMemsetAsync(b.p, 0, bound * 8, ctx->stream));
+    if (src && n) CUDA_TRY(cudaMemcpyAsync(b.p, src, std::min(n, bound) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return GE_OK;
+}
+static int upload_idx(ge_ctx *ctx, Buf &b, const uint64_t *src, uint64_t n, uint64_t bound, uint64_t limit, std::vector<uint32_t> &tmp, const char *what) {
+    GE_TRY(ctx->ensure(b, std::max<uint64_t>(bound, 1) * 4));
+    CUDA_TRY(cudaMemsetAsync(b.p, 0, bound * 4, ctx->stream));
+    if (n > bound) return fail(GE_ERR_INVALID, std::string("ge_mate_replay: ") + what + " is longer than the population allows");
+    tmp.resize(n);
+    for (uint64_t k = 0; k < n; k++) {
+        if (src[k] >= limit) return fail(GE_ERR_INVALID, std::string("ge_mate_replay: ") + what + " holds an index out of range");
+        tmp[k] = (uint32_t)src[k];
+    }
+    if (n) CUDA_TRY(cudaMemcpyAsync(b.p, tmp.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // tmp is reused by the caller
+    return GE_OK;
+}
+
+static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp, const ge_mate_draws *md = nullptr) {
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     MateScratch &M = P.mate;
@@ -328,13 +372,28 @@ static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp) {
     GE_TRY(ctx->ensure(M.keys_a, (cap + 1) * 8)); GE_TRY(ctx->ensure(M.keys_b, (lb + 1) * 8));
     GE_TRY(ctx->ensure(M.list_m, lb * 4)); GE_TRY(ctx->ensure(M.list_f, lb * 4));
     // who may mate: thinning counts, one scan for both sexes, the two lists
-    thin_count_kernel<<<g_ind, 256, 0, st>>>(ctx->rng, ss, pop, S.d_n, S.sex.as<uint8_t>(), S.svf.as<double>(), with_mm, P.MM, M.keys_a.as<uint64_t>());
+    std::vector<uint32_t> tmp;
+    const double *d_thin = nullptr, *d_mm = nullptr;
+    if (md) {   // the reference's own uniforms
+        if (!md->thin_u || (with_mm && !md->mm_u)) return fail(GE_ERR_INVALID, "ge_mate_replay: thin_u / mm_u missing");
+        GE_TRY(upload_f64(ctx, M.t1, md->thin_u, S.n, cap));
+        GE_TRY(upload_f64(ctx, M.t2, with_mm ? md->mm_u : nullptr, S.n, cap));
+        d_thin = M.t1.as<double>(); d_mm = M.t2.as<double>();
+    }
+    thin_count_kernel<<<g_ind, 256, 0, st>>>(ctx->rng, ss, pop, S.d_n, S.sex.as<uint8_t>(), S.svf.as<double>(), with_mm, P.MM, d_thin, d_mm, M.keys_a.as<uint64_t>());
     GE_TRY(ctx->check_launch("thin_count"));
     GE_TRY(ctx->scan(st, M.keys_a.as<uint64_t>(), devn(S.d_n), cap, M.keys_b.as<uint64_t>(), ThinTotal{ss, P.RM ? 1 : 0}));
     thin_fill_kernel<<<g_ind, 256, 0, st>>>(S.d_n, M.keys_b.as<uint64_t>(), M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>());
     GE_TRY(ctx->check_launch("thin_fill"));
     if (P.RM) {  // random_mate :2090-2157
-        rm_pair_kernel<<<ctx->grid_for(gp.pop_size, 256), 256, 0, st>>>(ctx->rng, ss, pop, M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>(), P.c_male.as<uint32_t>(),
+        const uint32_t *im = nullptr, *jf = nullptr;
+        if (md) {
+            if (!md->rm_father_idx || !md->rm_mother_idx || md->n_rm != gp.pop_size) return fail(GE_ERR_INVALID, "ge_mate_replay: random mating needs pop_size index draws for either parent");
+            GE_TRY(upload_idx(ctx, M.idx_a, md->rm_father_idx, md->n_rm, std::max<uint64_t>(gp.pop_size, 1), lb, tmp, "rm_father_idx"));
+            GE_TRY(upload_idx(ctx, M.idx_b, md->rm_mother_idx, md->n_rm, std::max<uint64_t>(gp.pop_size, 1), lb, tmp, "rm_mother_idx"));
+            im = M.idx_a.as<uint32_t>(); jf = M.idx_b.as<uint32_t>();
+        }
+        rm_pair_kernel<<<ctx->grid_for(gp.pop_size, 256), 256, 0, st>>>(ctx->rng, ss, pop, M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>(), im, jf, P.c_male.as<uint32_t>(),
                                                                         P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
         return ctx->check_launch("rm_pair");
     }
@@ -345,15 +404,27 @@ static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp) {
     GE_TRY(ctx->ensure(M.rank1, cb * 4)); GE_TRY(ctx->ensure(M.rank2, cb * 4));
     const uint64_t *d_trim_len = &ss->n_trim_list;
     // trim the longer list: Philox keys, stable sort, flags, offsets (all of it idles when the lists are equal)
-    trim_keys_kernel<<<g_list, 256, 0, st>>>(ctx->rng, ss, pop, M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>());
-    GE_TRY(ctx->check_launch("trim_keys"));
-    GE_TRY(sort_pairs_on(ctx, st, M.tmp_sort, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), devn(d_trim_len), lb));
+    if (md) {   // std::random_shuffle's order of the longer list (:2235 / :2242): its first n_trim entries leave
+        GE_TRY(upload_idx(ctx, M.idx_b, md->trim_order, md->trim_order ? md->n_trim_order : 0, lb, std::max<uint64_t>(md->n_trim_order, 1), tmp, "trim_order"));
+    } else {
+        trim_keys_kernel<<<g_list, 256, 0, st>>>(ctx->rng, ss, pop, M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>());
+        GE_TRY(ctx->check_launch("trim_keys"));
+        GE_TRY(sort_pairs_on(ctx, st, M.tmp_sort, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), devn(d_trim_len), lb));
+    }
     trim_flag_kernel<<<g_list, 256, 0, st>>>(ss, M.idx_b.as<uint32_t>(), M.keep.as<uint32_t>());
     GE_TRY(ctx->check_launch("trim_flag"));
     GE_TRY(ctx->scan(st, M.keep.as<uint32_t>(), devn(d_trim_len), lb, M.keep_off.as<uint64_t>(), NoTotal{}));
     // template values, then the four independent sorts side by side on the sort lanes
-    template_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>());
-    GE_TRY(ctx->check_launch("template"));
+    if (md) {
+        if (!md->t1 || !md->t2) return fail(GE_ERR_INVALID, "ge_mate_replay: template values missing");
+        GE_TRY(upload_f64(ctx, M.keys_a, md->t1, md->n_couples, cb));   // (keys_a / keys_b: the thinning is done with them)
+        GE_TRY(upload_f64(ctx, M.keys_b, md->t2, md->n_couples, cb));
+        template_from_kernel<<<g_c, 256, 0, st>>>(ss, M.keys_a.as<double>(), M.keys_b.as<double>(), M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>());
+        GE_TRY(ctx->check_launch("template_from"));
+    } else {
+        template_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>());
+        GE_TRY(ctx->check_launch("template"));
+    }
     GE_TRY(ctx->fork_lanes());
     const DevN n2 = devn(&ss->n2);
     for (int w = 0; w < 2; w++) {   // males, females by mating value
@@ -376,12 +447,21 @@ static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp) {
                                      P.avoid_inbreeding, P.c_male.as<uint32_t>(), P.c_female.as<uint32_t>(), P.c_inbreed.as<uint8_t>());
     GE_TRY(ctx->check_launch("pair"));
     const bool poisson = gp.offspring_dist == 'p' || gp.offspring_dist == 'P';
-    family_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, poisson ? 1 : 0, P.c_noff.as<int32_t>());
+    if (md && poisson) {   // ras_rpois's family sizes as the reference drew them
+        if (!md->family) return fail(GE_ERR_INVALID, "ge_mate_replay: family sizes missing");
+        CUDA_TRY(cudaMemsetAsync(P.c_noff.p, 0, cb * 4, st));
+        CUDA_TRY(cudaMemcpyAsync(P.c_noff.p, md->family, std::min<uint64_t>(md->n_couples, cb) * 4, cudaMemcpyHostToDevice, st));
+    }
+    family_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, md && poisson ? 2 : (poisson ? 1 : 0), P.c_noff.as<int32_t>());
     GE_TRY(ctx->check_launch("family"));
     if (!poisson) {
-        remainder_keys_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, P.c_inbreed.as<uint8_t>(), M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>());
-        GE_TRY(ctx->check_launch("remainder_keys"));
-        GE_TRY(sort_pairs_on(ctx, st, M.tmp_sort, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2, cb));
+        if (md) {   // pos_couple_can_marry after std::random_shuffle (:2350): its first `remainder` couples get one more child
+            GE_TRY(upload_idx(ctx, M.idx_b, md->remainder_order, md->remainder_order ? md->n_remainder_order : 0, cb, std::max<uint64_t>(md->n_couples, 1), tmp, "remainder_order"));
+        } else {
+            remainder_keys_kernel<<<g_c, 256, 0, st>>>(ctx->rng, ss, pop, P.c_inbreed.as<uint8_t>(), M.t1.as<uint64_t>(), M.idx_a.as<uint32_t>());
+            GE_TRY(ctx->check_launch("remainder_keys"));
+            GE_TRY(sort_pairs_on(ctx, st, M.tmp_sort, M.t1.as<uint64_t>(), M.t2.as<uint64_t>(), M.idx_a.as<uint32_t>(), M.idx_b.as<uint32_t>(), n2, cb));
+        }
         remainder_add_kernel<<<g_c, 256, 0, st>>>(ss, M.idx_b.as<uint32_t>(), P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>());
         GE_TRY(ctx->check_launch("remainder_add"));
     }

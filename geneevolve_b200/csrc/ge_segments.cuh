@@ -415,12 +415,15 @@ __global__ void seg_verbatim_fill_kernel(SegArgs a, const uint4 *__restrict__ de
 }
 
 // ras_find_cv (:2752-2815) on the segment lists: allele bit plane / root byte plane.  One thread per (haplotype
-// row, word of the CV bit plane); every CV of the word scans the segment list of its chromosome (the LAST part that
-// covers the position wins, like the reference's loop over all parts).
-template <class T>
+// row, word of the CV bit plane).  The reference scans every part for every CV and lets the LAST covering part win; in a sorted
+// tiling (SORTED) that part is the last one that starts at or before the position, found by binary search; lists that need not be
+// sorted (maps with rows closer than bp_dist_in_rmap) keep the reference's scan.  founder_root: after a re-base the parts name
+// haplotypes of the re-base generation, whose generation-0 root population per CV is kept in this byte plane.
+template <class T, bool SORTED>
 __global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__restrict__ off, const T *__restrict__ seg, const uint32_t *__restrict__ cov_hi,
                                    const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp,
                                    const uint8_t *const *__restrict__ founder_cv /* [n_pop] -> [nh][n_cv_tot] */,
+                                   const uint8_t *const *__restrict__ founder_root /* null, or [n_pop] -> [nh][n_cv_tot] */,
                                    uint32_t *__restrict__ bits, uint8_t *__restrict__ rootp) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_rows * cs.Wcv) return;
@@ -437,9 +440,18 @@ __global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__
             uint32_t bp = cs.bp[k];
             uint8_t v = 0, r = 0;
             bool found = false;
-            for (uint64_t e = off[slot]; e < e_end; e++) {
-                uint4 q = part_get(seg, e, e_end, hi_c);
-                if (q.x <= bp && bp < q.y) { v = founder_cv[q.w][(uint64_t)q.z * cs.n_cv_tot + k]; r = (uint8_t)q.w; found = true; }
+            if (SORTED) {
+                uint64_t lo = off[slot], hi = e_end;   // first part that starts beyond the position
+                while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (seg[mid].x <= bp) lo = mid + 1; else hi = mid; }
+                if (lo > off[slot]) {
+                    const uint4 q = part_get(seg, lo - 1, e_end, hi_c);
+                    if (bp < q.y) { const uint64_t o = (uint64_t)q.z * cs.n_cv_tot + k; v = founder_cv[q.w][o]; r = founder_root ? founder_root[q.w][o] : (uint8_t)q.w; found = true; }
+                }
+            } else {
+                for (uint64_t e = off[slot]; e < e_end; e++) {
+                    uint4 q = part_get(seg, e, e_end, hi_c);
+                    if (q.x <= bp && bp < q.y) { const uint64_t o = (uint64_t)q.z * cs.n_cv_tot + k; v = founder_cv[q.w][o]; r = founder_root ? founder_root[q.w][o] : (uint8_t)q.w; found = true; }
+                }
             }
             if (found && hm_off) {
                 for (uint64_t e = hm_off[slot]; e < hm_off[slot + 1]; e++) if (hm_bp[e] == bp) { v ^= 1; break; }
@@ -451,7 +463,115 @@ __global__ void seg_find_cv_kernel(CvSet cs, uint64_t n_rows, const uint64_t *__
     bits[t] = out;
 }
 
-// ras_convert_interval_to_hap_matrix (:1186-1230): alleles of one chromosome from segments + founder panels
+// ------------------------------------------------------------------------------------------------
+// One chromosome out of the slot-major lists (downloads, `.int`, materialisation): a compact CSR over the 2n haplotype rows of
+// chromosome c — count, scan, fill — built on the device, so a download moves one chromosome's parts once instead of the whole
+// population's lists twice (what seg_count + seg_download used to do per chromosome).
+// ------------------------------------------------------------------------------------------------
+__global__ void seg_slice_count_kernel(uint64_t n_rows, int n_chr, int c, const uint64_t *__restrict__ off, const uint64_t *__restrict__ hm_off, uint32_t *__restrict__ cnt,
+                                       uint32_t *__restrict__ hm_cnt) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t slot = ((row >> 1) * n_chr + c) * 2 + (row & 1);
+    cnt[row] = (uint32_t)(off[slot + 1] - off[slot]);
+    if (hm_cnt) hm_cnt[row] = hm_off ? (uint32_t)(hm_off[slot + 1] - hm_off[slot]) : 0u;
+}
+// parts of chromosome c as the four fields of `class part`, uint64 each (the layout ge_download_segments returns) ...
+template <class T>
+__global__ void seg_slice_fill_u64_kernel(uint64_t n_rows, int n_chr, int c, const uint64_t *__restrict__ off, const T *__restrict__ seg, uint32_t hi_c,
+                                          const uint64_t *__restrict__ row_off, uint64_t *__restrict__ out /* [n][4] */) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t slot = ((row >> 1) * n_chr + c) * 2 + (row & 1);
+    const uint64_t e0 = off[slot], e1 = off[slot + 1];
+    uint64_t o = row_off[row];
+    for (uint64_t e = e0; e < e1; e++, o++) {
+        const uint4 q = part_get(seg, e, e1, hi_c);
+        out[o * 4] = q.x; out[o * 4 + 1] = q.y; out[o * 4 + 2] = q.z; out[o * 4 + 3] = q.w;
+    }
+}
+__global__ void seg_slice_fill_hm_kernel(uint64_t n_rows, int n_chr, int c, const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp,
+                                         const uint64_t *__restrict__ row_off, uint64_t *__restrict__ out) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t slot = ((row >> 1) * n_chr + c) * 2 + (row & 1);
+    uint64_t o = row_off[row];
+    for (uint64_t e = hm_off[slot]; e < hm_off[slot + 1]; e++, o++) out[o] = hm_bp[e] & ~HM_BAKED;
+}
+// ... or, for the materialisation below, as {first locus index the part covers, founder id}: one thread per part
+struct PartLo { uint32_t lo, id; };   // id = hap_index | root_population << 27
+template <class T>
+__global__ void seg_slice_fill_lo_kernel(Genome g, uint64_t n_rows, int n_chr, int c, const uint64_t *__restrict__ off, const T *__restrict__ seg, uint32_t hi_c,
+                                         const uint64_t *__restrict__ row_off, PartLo *__restrict__ out) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t slot = ((row >> 1) * n_chr + c) * 2 + (row & 1);
+    const uint64_t e0 = off[slot], e1 = off[slot + 1];
+    uint64_t o = row_off[row];
+    for (uint64_t e = e0; e < e1; e++, o++) {
+        const uint4 q = part_get(seg, e, e1, hi_c);
+        out[o] = PartLo{locus_lower_bound(g, c, q.x), q.z | (q.w << SEG_ID_BITS)};
+    }
+}
+
+// ras_convert_interval_to_hap_matrix (:1186-1230) for sorted tilings: the bit-packed rows of chromosome c from the parts and the
+// founder panels.  The reference tests every part against every SNP (O(parts x loci) per haplotype); here ONE WARP walks a row: its
+// lanes take 32 consecutive words, each lane steps from the warp's cursor to the part that covers its first locus (parts and words
+// both ascend: a few steps per 1024 loci) and ORs together the founder words of the parts that intersect its 32 loci — one founder
+// word per output word almost always.  Output words are written coalesced; nothing is scanned twice.
+__global__ void __launch_bounds__(256) seg_materialise_rows_kernel(Genome g, int c, uint64_t n_rows, const uint64_t *__restrict__ row_off, const PartLo *__restrict__ parts,
+                                                                   uint32_t hi_locus /* first locus at or beyond the covered end */,
+                                                                   const uint32_t *const *__restrict__ founder_rows /* [n_pop] packed rows */, uint32_t nw,
+                                                                   uint32_t *__restrict__ out /* word w of row r at out[r * out_stride + w] */, uint64_t out_stride) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t woff = g.chr_word_off[c];
+    for (uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
+        const PartLo *P = parts + row_off[row];
+        const uint32_t n = (uint32_t)(row_off[row + 1] - row_off[row]);
+        uint32_t cur = 0;   // warp-uniform: last part whose first locus is at or before the chunk's first locus (0 if none)
+        for (uint32_t w0 = 0; w0 < nw; w0 += 32) {
+            const uint32_t w = w0 + lane, s0 = w << 5, s1 = s0 + 32;
+            uint32_t k = cur;
+            while (k + 1 < n && __ldg(&P[k + 1].lo) <= s0) k++;
+            uint32_t word = 0, q = k;
+            while (q < n) {
+                const uint32_t a = max(__ldg(&P[q].lo), s0);
+                if (a >= s1) break;
+                const uint32_t b = min(q + 1 < n ? __ldg(&P[q + 1].lo) : hi_locus, s1);
+                if (a < b) {
+                    const uint32_t id = __ldg(&P[q].id);
+                    const uint32_t fw = __ldg(founder_rows[id >> SEG_ID_BITS] + (uint64_t)(id & ((1u << SEG_ID_BITS) - 1u)) * g.W + woff + w);
+                    const uint32_t m = (b - s0 >= 32u ? 0xFFFFFFFFu : ((1u << (b - s0)) - 1u)) & ~((1u << (a - s0)) - 1u);
+                    word |= fw & m;
+                }
+                if (b >= s1) break;
+                q++;
+            }
+            if (w < nw) out[row * out_stride + w] = word;
+            cur = __shfl_sync(0xffffffffu, k, 31);   // the next chunk's first locus lies beyond lane 31's: its part is a valid place to resume
+        }
+    }
+}
+// toggles of the per-haplotype mutation lists that the (re-based) founder panel does not hold yet: one thread per row
+__global__ void seg_materialise_toggle_kernel(Genome g, int c, int n_chr, uint64_t n_rows, const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp, uint64_t out_stride,
+                                              uint32_t *__restrict__ out) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t slot = ((row >> 1) * n_chr + c) * 2 + (row & 1);
+    const uint32_t *pos = g.pos + g.locus_off[c];
+    const uint32_t nl = g.chr_nloci[c];
+    for (uint64_t e = hm_off[slot]; e < hm_off[slot + 1]; e++) {
+        const uint32_t m = hm_bp[e];
+        if (m & HM_BAKED) continue;
+        bool first = true;   // a position toggles once however often the lineage was hit there (the reference looks it up with std::find)
+        for (uint64_t e2 = hm_off[slot]; e2 < e; e2++) if ((hm_bp[e2] & ~HM_BAKED) == m) { first = false; break; }
+        if (!first) continue;
+        for (uint32_t s = lower_bound_u32(pos, nl, m); s < nl && pos[s] == m; s++) out[row * out_stride + (s >> 5)] ^= 1u << (s & 31);
+    }
+}
+// the verbatim form for lists that need not be sorted (maps with rows closer than bp_dist_in_rmap): every part against every locus, the
+// LAST covering part wins, exactly like the reference's loop
 template <class T>
 __global__ void seg_materialise_kernel(Genome g, int c, uint64_t n_rows, const uint64_t *__restrict__ off, const T *__restrict__ seg, const uint32_t *__restrict__ cov_hi,
                                        const uint64_t *__restrict__ hm_off, const uint32_t *__restrict__ hm_bp,
@@ -738,37 +858,109 @@ static int seg_find_cv(ge_ctx *ctx, int pop) {
     GenState &S = P.st[P.cur];
     if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists");
     if (ctx->n_cv_tot == 0) return GE_OK;
-    Buf tbl;
+    Buf tbl, tbl_root;
     GE_TRY(seg_device_tables(ctx, tbl, true));
+    const bool rebased_root = ctx->use_root && ctx->n_rebase > 0;
+    if (rebased_root) {
+        std::vector<const void *> ptrs(ctx->cfg.n_pop);
+        for (int p = 0; p < ctx->cfg.n_pop; p++) ptrs[p] = ctx->pop[p].founder_root.p;
+        GE_TRY(ctx->upload(tbl_root, ptrs));
+    }
+    const uint8_t *const *roots = rebased_root ? tbl_root.as<const uint8_t *>() : nullptr;
     uint64_t tot = 2 * S.n * ctx->Wcv;
+    const uint64_t *hm_off = S.has_hm ? S.hm_off.as<uint64_t>() : nullptr;
+    uint8_t *rootp = ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr;
     if (ctx->seg_packed)
-        seg_find_cv_kernel<uint2><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), P.d_cov_hi.as<uint32_t>(),
-                                                                       S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
-                                                                       tbl.as<const uint8_t *>(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr);
+        seg_find_cv_kernel<uint2, true><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), P.d_cov_hi.as<uint32_t>(), hm_off, S.hm_bp.as<uint32_t>(),
+                                                                             tbl.as<const uint8_t *>(), roots, S.cv_allele.as<uint32_t>(), rootp);
+    else if (!ctx->seg_per_thread)
+        seg_find_cv_kernel<uint4, true><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.d_cov_hi.as<uint32_t>(), hm_off, S.hm_bp.as<uint32_t>(),
+                                                                             tbl.as<const uint8_t *>(), roots, S.cv_allele.as<uint32_t>(), rootp);
     else
-        seg_find_cv_kernel<uint4><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.d_cov_hi.as<uint32_t>(),
-                                                                       S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(),
-                                                                       tbl.as<const uint8_t *>(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr);
+        seg_find_cv_kernel<uint4, false><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->cvset(), 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.d_cov_hi.as<uint32_t>(), hm_off, S.hm_bp.as<uint32_t>(),
+                                                                              tbl.as<const uint8_t *>(), roots, S.cv_allele.as<uint32_t>(), rootp);
     GE_TRY(ctx->check_launch("seg_find_cv"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    ctx->release(tbl);
+    ctx->release(tbl); ctx->release(tbl_root);
     return GE_OK;
 }
 
-static int seg_materialise(ge_ctx *ctx, int pop, int c, uint8_t *d_alleles) {
+// compact CSR of chromosome c over the 2n haplotype rows (scratch: P.cnt32, the caller's row_off buffers)
+static int seg_slice_offsets(ge_ctx *ctx, PopDev &P, GenState &S, int c, Buf &row_off, Buf *hm_row_off, uint64_t *n_seg, uint64_t *n_hm) {
+    const uint64_t n_rows = 2 * S.n;
+    GE_TRY(ctx->ensure(P.cnt32, (2 * n_rows + 2) * 4));
+    GE_TRY(ctx->ensure(row_off, (n_rows + 1) * 8));
+    if (hm_row_off) GE_TRY(ctx->ensure(*hm_row_off, (n_rows + 1) * 8));
+    uint32_t *cnt = P.cnt32.as<uint32_t>(), *hcnt = hm_row_off ? cnt + n_rows + 1 : nullptr;
+    seg_slice_count_kernel<<<nblk(n_rows, 256), 256, 0, ctx->stream>>>(n_rows, ctx->cfg.n_chr, c, S.seg.off.as<uint64_t>(), S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, cnt, hcnt);
+    GE_TRY(ctx->check_launch("seg_slice_count"));
+    GE_TRY(ctx->exclusive_scan(cnt, n_rows, row_off.as<uint64_t>(), n_seg));
+    if (hm_row_off) GE_TRY(ctx->exclusive_scan(hcnt, n_rows, hm_row_off->as<uint64_t>(), n_hm));
+    return GE_OK;
+}
+
+// packed rows of chromosome c from the segment lists: word w of haplotype row r goes to d_words[r * out_stride + w]
+// (out_stride = ceil(n_loci/32): a chromosome matrix for the downloads; = W with d_words advanced to the chromosome's first word:
+// whole rows, which is how a re-base builds the next founder panel)
+static int seg_materialise_packed(ge_ctx *ctx, int pop, int c, uint32_t *d_words, uint64_t out_stride = 0) {
     GE_TRY(seg_finish_all(ctx));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists");
+    for (PopDev &Q : ctx->pop) if (!Q.founder_rows.p) return fail(GE_ERR_INVALID, "haplotypes from segments need the founder panel (ge_set_founder_panel)");
+    const uint64_t n_rows = 2 * S.n;
+    const uint32_t nl = ctx->chr_nloci[c], nw = (nl + 31) / 32;
+    if (n_rows == 0 || nw == 0) return GE_OK;
+    if (out_stride == 0) out_stride = nw;
+    Buf tbl, row_off, parts;
+    GE_TRY(seg_device_tables(ctx, tbl, false));
+    uint64_t n_seg = 0;
+    GE_TRY(seg_slice_offsets(ctx, P, S, c, row_off, nullptr, &n_seg, nullptr));
+    GE_TRY(ctx->ensure_exact(parts, std::max<uint64_t>(n_seg, 1) * sizeof(PartLo)));
+    const uint32_t hi_c = (uint32_t)P.rmap_bp[c].back();
+    if (ctx->seg_packed) seg_slice_fill_lo_kernel<uint2><<<nblk(n_rows, 128), 128, 0, ctx->stream>>>(ctx->genome(), n_rows, ctx->cfg.n_chr, c, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), hi_c, row_off.as<uint64_t>(), parts.as<PartLo>());
+    else seg_slice_fill_lo_kernel<uint4><<<nblk(n_rows, 128), 128, 0, ctx->stream>>>(ctx->genome(), n_rows, ctx->cfg.n_chr, c, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), hi_c, row_off.as<uint64_t>(), parts.as<PartLo>());
+    GE_TRY(ctx->check_launch("seg_slice_fill_lo"));
+    const auto &L = ctx->loci[c];
+    const uint32_t hi_locus = (uint32_t)(std::lower_bound(L.begin(), L.end(), (uint64_t)hi_c) - L.begin());
+    const unsigned grid = (unsigned)std::min<uint64_t>(nblk(n_rows * 32, 256), (uint64_t)ctx->n_sm * 32);
+    seg_materialise_rows_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->genome(), c, n_rows, row_off.as<uint64_t>(), parts.as<PartLo>(), hi_locus, tbl.as<const uint32_t *>(), nw, d_words, out_stride);
+    GE_TRY(ctx->check_launch("seg_materialise_rows"));
+    if (S.has_hm) {
+        seg_materialise_toggle_kernel<<<nblk(n_rows, 128), 128, 0, ctx->stream>>>(ctx->genome(), c, ctx->cfg.n_chr, n_rows, S.hm_off.as<uint64_t>(), S.hm_bp.as<uint32_t>(), out_stride, d_words);
+        GE_TRY(ctx->check_launch("seg_materialise_toggle"));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (Buf *b : {&tbl, &row_off, &parts}) ctx->release(*b);
+    return GE_OK;
+}
+
+static int seg_materialise(ge_ctx *ctx, int pop, int c, uint8_t *d_alleles) {
+    PopDev &P = ctx->pop[pop];
+    GenState &S0 = P.st[P.cur];
+    if (!ctx->seg_per_thread) {   // sorted tilings: packed rows by the warp walk, then one bit -> one byte
+        const uint32_t nl = ctx->chr_nloci[c], nw = (nl + 31) / 32;
+        Buf words;
+        GE_TRY(ctx->ensure_exact(words, std::max<uint64_t>((uint64_t)2 * S0.n * nw, 1) * 4));
+        GE_TRY(seg_materialise_packed(ctx, pop, c, words.as<uint32_t>()));
+        const uint64_t tot = (uint64_t)2 * P.st[P.cur].n * nl;
+        if (tot) {
+            unpack_rows_kernel<<<nblk(tot, 256), 256, 0, ctx->stream>>>(words.as<uint32_t>(), nullptr, nw, 0, (uint32_t)(2 * P.st[P.cur].n), nl, d_alleles);
+            GE_TRY(ctx->check_launch("unpack_rows"));
+        }
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->release(words);
+        return GE_OK;
+    }
+    GE_TRY(seg_finish_all(ctx));
+    GenState &S = P.st[P.cur];
+    if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists");
+    for (PopDev &Q : ctx->pop) if (!Q.founder_rows.p) return fail(GE_ERR_INVALID, "haplotypes from segments need the founder panel (ge_set_founder_panel)");
     Buf tbl;
     GE_TRY(seg_device_tables(ctx, tbl, false));
     uint64_t tot = 2 * S.n * ctx->chr_nloci[c];
-    if (ctx->seg_packed)
-        seg_materialise_kernel<uint2><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->genome(), c, 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), P.d_cov_hi.as<uint32_t>(),
-                                                                           S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(), tbl.as<const uint32_t *>(), d_alleles);
-    else
-        seg_materialise_kernel<uint4><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->genome(), c, 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.d_cov_hi.as<uint32_t>(),
-                                                                           S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(), tbl.as<const uint32_t *>(), d_alleles);
+    seg_materialise_kernel<uint4><<<nblk(tot, 256), 256, 0, ctx->stream>>>(ctx->genome(), c, 2 * S.n, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), P.d_cov_hi.as<uint32_t>(),
+                                                                       S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, S.hm_bp.as<uint32_t>(), tbl.as<const uint32_t *>(), d_alleles);
     GE_TRY(ctx->check_launch("seg_materialise"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->release(tbl);
@@ -805,60 +997,195 @@ static int seg_compact(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_aft
     return ctx->push_state(P, offsetof(StepState, n_seg), 16);
 }
 
-// host-side slicing of one chromosome out of the slot-major CSR (output path, `.int` writer)
-static int seg_host_copy(ge_ctx *ctx, int pop, std::vector<uint64_t> &off, std::vector<uint4> &seg, std::vector<uint64_t> &hoff, std::vector<uint32_t> &hbp) {
+// one chromosome's lists for the host (`.int` writer, tests): sliced and converted to the four fields on the device, moved once
+static int seg_count(ge_ctx *ctx, int pop, int c, uint64_t *ns, uint64_t *nm) {
     GE_TRY(seg_finish_all(ctx));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists (GE_REP_SEGMENTS not enabled)");
-    uint64_t n_slots = S.n * ctx->cfg.n_chr * 2;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    off.resize(n_slots + 1); seg.resize(S.seg.n_seg);
-    CUDA_TRY(cudaMemcpy(off.data(), S.seg.off.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));
-    if (S.seg.n_seg && !ctx->seg_packed) CUDA_TRY(cudaMemcpy(seg.data(), S.seg.seg.p, S.seg.n_seg * 16, cudaMemcpyDeviceToHost));
-    if (S.seg.n_seg && ctx->seg_packed) {   // {st, id} -> {st, en, hap_index, root_population}: en is the next part's st, cov_hi at the end of a list
-        std::vector<uint2> pk(S.seg.n_seg);
-        CUDA_TRY(cudaMemcpy(pk.data(), S.seg.seg.p, S.seg.n_seg * 8, cudaMemcpyDeviceToHost));
-        const int C = ctx->cfg.n_chr;
-        for (uint64_t sl = 0; sl < n_slots; sl++) {
-            const uint32_t hi_c = (uint32_t)P.rmap_bp[(sl >> 1) % C].back();
-            for (uint64_t e = off[sl]; e < off[sl + 1]; e++)
-                seg[e] = make_uint4(pk[e].x, e + 1 < off[sl + 1] ? pk[e + 1].x : hi_c, pk[e].y & ((1u << SEG_ID_BITS) - 1u), pk[e].y >> SEG_ID_BITS);
-        }
-    }
-    hoff.assign(n_slots + 1, 0); hbp.clear();
-    if (S.has_hm) {
-        CUDA_TRY(cudaMemcpy(hoff.data(), S.hm_off.p, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));
-        hbp.resize(S.n_hm);
-        if (S.n_hm) CUDA_TRY(cudaMemcpy(hbp.data(), S.hm_bp.p, S.n_hm * 4, cudaMemcpyDeviceToHost));
-    }
-    return GE_OK;
-}
-
-static int seg_count(ge_ctx *ctx, int pop, int c, uint64_t *ns, uint64_t *nm) {
-    std::vector<uint64_t> off, hoff; std::vector<uint4> seg; std::vector<uint32_t> hbp;
-    GE_TRY(seg_host_copy(ctx, pop, off, seg, hoff, hbp));
-    uint64_t n = ctx->pop[pop].st[ctx->pop[pop].cur].n; int C = ctx->cfg.n_chr;
+    Buf row_off, hm_row_off;
     uint64_t a = 0, b = 0;
-    for (uint64_t i = 0; i < n; i++) for (int h = 0; h < 2; h++) { uint64_t s = (i * C + c) * 2 + h; a += off[s + 1] - off[s]; b += hoff[s + 1] - hoff[s]; }
+    GE_TRY(seg_slice_offsets(ctx, P, S, c, row_off, &hm_row_off, &a, &b));
     *ns = a; *nm = b;
+    ctx->release(row_off); ctx->release(hm_row_off);
     return GE_OK;
 }
 
 static int seg_download(ge_ctx *ctx, int pop, int c, uint64_t *o_off, uint64_t *o_seg, uint64_t *o_moff, uint64_t *o_mbp) {
-    std::vector<uint64_t> off, hoff; std::vector<uint4> seg; std::vector<uint32_t> hbp;
-    GE_TRY(seg_host_copy(ctx, pop, off, seg, hoff, hbp));
-    uint64_t n = ctx->pop[pop].st[ctx->pop[pop].cur].n; int C = ctx->cfg.n_chr;
-    uint64_t a = 0, b = 0;
-    for (uint64_t i = 0; i < n; i++)
-        for (int h = 0; h < 2; h++) {
-            uint64_t s = (i * C + c) * 2 + h;
-            o_off[i * 2 + h] = a;
-            if (o_moff) o_moff[i * 2 + h] = b;
-            for (uint64_t e = off[s]; e < off[s + 1]; e++, a++) { o_seg[a * 4] = seg[e].x; o_seg[a * 4 + 1] = seg[e].y; o_seg[a * 4 + 2] = seg[e].z; o_seg[a * 4 + 3] = seg[e].w; }
-            for (uint64_t e = hoff[s]; e < hoff[s + 1]; e++, b++) if (o_mbp) o_mbp[b] = hbp[e];
+    GE_TRY(seg_finish_all(ctx));
+    PopDev &P = ctx->pop[pop];
+    GenState &S = P.st[P.cur];
+    if (!S.seg.valid) return fail(GE_ERR_INVALID, "no segment lists (GE_REP_SEGMENTS not enabled)");
+    const uint64_t n_rows = 2 * S.n;
+    Buf row_off, hm_row_off, parts, hm;
+    uint64_t n_seg = 0, n_hm = 0;
+    GE_TRY(seg_slice_offsets(ctx, P, S, c, row_off, &hm_row_off, &n_seg, &n_hm));
+    GE_TRY(ctx->ensure_exact(parts, std::max<uint64_t>(n_seg, 1) * 32));
+    const uint32_t hi_c = (uint32_t)P.rmap_bp[c].back();
+    if (n_rows) {
+        if (ctx->seg_packed) seg_slice_fill_u64_kernel<uint2><<<nblk(n_rows, 128), 128, 0, ctx->stream>>>(n_rows, ctx->cfg.n_chr, c, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint2>(), hi_c, row_off.as<uint64_t>(), parts.as<uint64_t>());
+        else seg_slice_fill_u64_kernel<uint4><<<nblk(n_rows, 128), 128, 0, ctx->stream>>>(n_rows, ctx->cfg.n_chr, c, S.seg.off.as<uint64_t>(), S.seg.seg.as<uint4>(), hi_c, row_off.as<uint64_t>(), parts.as<uint64_t>());
+        GE_TRY(ctx->check_launch("seg_slice_fill"));
+    }
+    CUDA_TRY(cudaMemcpyAsync(o_off, row_off.p, (n_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_seg) CUDA_TRY(cudaMemcpyAsync(o_seg, parts.p, n_seg * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (o_moff) CUDA_TRY(cudaMemcpyAsync(o_moff, hm_row_off.p, (n_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (o_mbp && n_hm) {
+        GE_TRY(ctx->ensure_exact(hm, n_hm * 8));
+        seg_slice_fill_hm_kernel<<<nblk(n_rows, 128), 128, 0, ctx->stream>>>(n_rows, ctx->cfg.n_chr, c, S.hm_off.as<uint64_t>(), S.hm_bp.as<uint32_t>(), hm_row_off.as<uint64_t>(), hm.as<uint64_t>());
+        GE_TRY(ctx->check_launch("seg_slice_fill_hm"));
+        CUDA_TRY(cudaMemcpyAsync(o_mbp, hm.p, n_hm * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (Buf *b : {&row_off, &hm_row_off, &parts, &hm}) ctx->release(*b);
+    return GE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Re-basing the founder panel (GeneEvolveDocumentation.pdf p.52, limitation #2: the reference's lists only grow —
+// it appends clipped parts for ever, :2903-2958).  ge_rebase_founders makes the CURRENT generation the founder panel: every
+// haplotype's alleles are materialised once into a new bit-packed panel (from the bit-packed rows when the context carries them,
+// else from the lists and the old panel), its causal-variant alleles become the founder CV panel, and every list restarts as one
+// part naming the haplotype itself.  Cost and memory of the segment path then depend on the generations since the last re-base,
+// not since generation 0.  The lists that were replaced can be kept (keep_history): composing the current lists through them
+// gives back the reference's lists against the generation-0 founders (ge_download_segments_gen0).
+// ------------------------------------------------------------------------------------------------
+namespace gek {
+__global__ void rows_to_logical_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ rowmap, uint64_t n_rows, uint32_t W, uint32_t *__restrict__ out) {
+    for (uint64_t r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const uint64_t src = rowmap ? (uint64_t)rowmap[r >> 1] * 2 + (r & 1) : r;
+        const uint4 *s = reinterpret_cast<const uint4 *>(rows + src * W);
+        uint4 *d = reinterpret_cast<uint4 *>(out + r * W);
+        for (uint32_t q = threadIdx.x; q < W / 4; q += blockDim.x) st_stream(d + q, ld_stream(s + q));
+    }
+}
+__global__ void cv_planes_to_bytes_kernel(uint32_t n_cv, uint32_t Wcv, const uint32_t *__restrict__ bitpos, const uint32_t *__restrict__ bits, uint64_t n_rows, uint8_t *__restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * n_cv) return;
+    const uint32_t k = (uint32_t)(t % n_cv), bp = bitpos[k];
+    out[t] = (bits[(t / n_cv) * Wcv + (bp >> 5)] >> (bp & 31u)) & 1u;
+}
+__global__ void hm_bake_kernel(uint64_t n, uint32_t *__restrict__ hm_bp) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) hm_bp[e] |= HM_BAKED;
+}
+}  // namespace gek
+
+static int seg_rebase(ge_ctx *ctx, int keep_history) {
+    GE_TRY(seg_finish_all(ctx));
+    if (ctx->seg_per_thread) return fail(GE_ERR_UNSUPPORTED, "ge_rebase_founders needs sorted lists (a genetic map with rows closer than bp_dist_in_rmap was given)");
+    const int np = ctx->cfg.n_pop, C = ctx->cfg.n_chr;
+    const bool have_panel = ctx->pop[0].founder_rows.p != nullptr;
+    for (PopDev &P : ctx->pop) {
+        if (!P.st[P.cur].seg.valid || P.st[P.cur].n == 0) return fail(GE_ERR_INVALID, "ge_rebase_founders: no segment lists");
+        if (2 * P.st[P.cur].n >= (1ull << SEG_ID_BITS)) return fail(GE_ERR_UNSUPPORTED, "ge_rebase_founders: more haplotypes than a part can name");
+    }
+    // 1. the new panels, all of them from the OLD ones (a migrant's parts name another population's founders)
+    std::vector<Buf> new_rows(np), new_cv(np), new_root(np);
+    for (int p = 0; p < np; p++) {
+        PopDev &P = ctx->pop[p];
+        GenState &S = P.st[P.cur];
+        const uint64_t n_rows = 2 * S.n;
+        if (have_panel) {
+            GE_TRY(ctx->ensure_exact(new_rows[p], (size_t)n_rows * ctx->W * 4));
+            if (ctx->bits()) {
+                rows_to_logical_kernel<<<(unsigned)std::min<uint64_t>(n_rows, 1u << 16), 256, 0, ctx->stream>>>(S.hap.as<uint32_t>(), S.rowmap, n_rows, ctx->W, new_rows[p].as<uint32_t>());
+                GE_TRY(ctx->check_launch("rows_to_logical"));
+            } else {
+                CUDA_TRY(cudaMemsetAsync(new_rows[p].p, 0, (size_t)n_rows * ctx->W * 4, ctx->stream));
+                for (int c = 0; c < C; c++) GE_TRY(seg_materialise_packed(ctx, p, c, new_rows[p].as<uint32_t>() + ctx->chr_word_off[c], ctx->W));
+            }
         }
-    o_off[2 * n] = a;
-    if (o_moff) o_moff[2 * n] = b;
+        if (ctx->n_cv_tot) {
+            GE_TRY(ctx->ensure_exact(new_cv[p], (size_t)n_rows * ctx->n_cv_tot));
+            cv_planes_to_bytes_kernel<<<nblk(n_rows * ctx->n_cv_tot, 256), 256, 0, ctx->stream>>>(ctx->n_cv_tot, ctx->Wcv, ctx->d_cv_bitpos.as<uint32_t>(), S.cv_allele.as<uint32_t>(), n_rows, new_cv[p].as<uint8_t>());
+            GE_TRY(ctx->check_launch("cv_planes_to_bytes"));
+            if (ctx->use_root) {
+                GE_TRY(ctx->ensure_exact(new_root[p], (size_t)n_rows * ctx->n_cv_tot));
+                CUDA_TRY(cudaMemcpyAsync(new_root[p].p, S.cv_root.p, (size_t)n_rows * ctx->n_cv_tot, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    // 2. swap them in, retire the lists, restart every haplotype as one part
+    for (int p = 0; p < np; p++) {
+        PopDev &P = ctx->pop[p];
+        GenState &S = P.st[P.cur];
+        if (have_panel) { ctx->release(P.founder_rows); P.founder_rows = new_rows[p]; }
+        if (ctx->n_cv_tot) { ctx->release(P.founder_cv); P.founder_cv = new_cv[p]; }
+        if (ctx->use_root) { ctx->release(P.founder_root); P.founder_root = new_root[p]; }
+        P.n_founder_haps = 2 * S.n;
+        if (S.has_hm && S.n_hm) {   // toggles up to here are in the new panel: they stay in the lineage's memory, but are not applied again
+            hm_bake_kernel<<<nblk(S.n_hm, 256), 256, 0, ctx->stream>>>(S.n_hm, S.hm_bp.as<uint32_t>());
+            GE_TRY(ctx->check_launch("hm_bake"));
+        }
+        if (keep_history) {
+            PopDev::SegSnapshot snap;
+            snap.off = S.seg.off; snap.seg = S.seg.seg; snap.n = S.n; snap.n_seg = S.seg.n_seg;
+            S.seg.off = Buf(); S.seg.seg = Buf();
+            P.history.push_back(snap);
+        }
+        S.seg.valid = false;
+        GE_TRY(seg_init_gen0(ctx, p, S.n));   // (also pushes n_seg to the device-resident step state)
+    }
+    ctx->n_rebase++;
+    ctx->graph_epoch++;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GE_OK;
+}
+
+// The current lists of chromosome c expressed against the generation-0 founders: composed on the host through the kept re-basing
+// snapshots, newest first.  A current part (L, R, h, q) names haplotype h of population q at the last re-base; what the reference
+// would hold there are the parts of that haplotype's snapshot list that recombine's clip rule (:2922-2954) emits for [L, R):
+// y > L and (y <= R or x < R), clipped to (max(x, L), min(y, R)).
+static int seg_download_gen0(ge_ctx *ctx, int pop, int c, std::vector<uint64_t> &off, std::vector<uint64_t> &seg) {
+    PopDev &P = ctx->pop[pop];
+    for (PopDev &Q : ctx->pop) if ((int)Q.history.size() != ctx->n_rebase) return fail(GE_ERR_INVALID, "ge_download_segments_gen0: a re-base dropped its history (keep_history = 0)");
+    uint64_t ns = 0, nm = 0;
+    GE_TRY(seg_count(ctx, pop, c, &ns, &nm));
+    const uint64_t n_rows = 2 * P.st[P.cur].n;
+    off.assign(n_rows + 1, 0); seg.assign(ns * 4, 0);
+    GE_TRY(seg_download(ctx, pop, c, off.data(), seg.data(), nullptr, nullptr));
+    const int np = ctx->cfg.n_pop;
+    for (int level = ctx->n_rebase - 1; level >= 0; level--) {
+        // the snapshot lists of every population at this level (a part may name another population's haplotype)
+        std::vector<std::vector<uint64_t>> hoff(np), hseg(np);
+        for (int q = 0; q < np; q++) {
+            PopDev &Q = ctx->pop[q];
+            PopDev::SegSnapshot &H = Q.history[level];
+            // view the snapshot through a temporary generation state so that the slicing kernels can be reused
+            GenState tmp;
+            tmp.n = H.n; tmp.seg.off = H.off; tmp.seg.seg = H.seg; tmp.seg.n_seg = H.n_seg; tmp.seg.valid = true; tmp.has_hm = false;
+            Buf row_off, parts;
+            uint64_t n_seg = 0;
+            GE_TRY(seg_slice_offsets(ctx, Q, tmp, c, row_off, nullptr, &n_seg, nullptr));
+            GE_TRY(ctx->ensure_exact(parts, std::max<uint64_t>(n_seg, 1) * 32));
+            const uint32_t hi_c = (uint32_t)Q.rmap_bp[c].back();
+            const uint64_t hr = 2 * H.n;
+            if (ctx->seg_packed) seg_slice_fill_u64_kernel<uint2><<<nblk(hr, 128), 128, 0, ctx->stream>>>(hr, ctx->cfg.n_chr, c, H.off.as<uint64_t>(), H.seg.as<uint2>(), hi_c, row_off.as<uint64_t>(), parts.as<uint64_t>());
+            else seg_slice_fill_u64_kernel<uint4><<<nblk(hr, 128), 128, 0, ctx->stream>>>(hr, ctx->cfg.n_chr, c, H.off.as<uint64_t>(), H.seg.as<uint4>(), hi_c, row_off.as<uint64_t>(), parts.as<uint64_t>());
+            GE_TRY(ctx->check_launch("seg_slice_fill"));
+            hoff[q].resize(hr + 1); hseg[q].resize(n_seg * 4);
+            CUDA_TRY(cudaMemcpyAsync(hoff[q].data(), row_off.p, (hr + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (n_seg) CUDA_TRY(cudaMemcpyAsync(hseg[q].data(), parts.p, n_seg * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            ctx->release(row_off); ctx->release(parts);
+        }
+        std::vector<uint64_t> noff(n_rows + 1, 0), nseg;
+        nseg.reserve(seg.size() * 2);
+        for (uint64_t r = 0; r < n_rows; r++) {
+            noff[r] = nseg.size() / 4;
+            for (uint64_t e = off[r]; e < off[r + 1]; e++) {
+                const uint64_t L = seg[e * 4], R = seg[e * 4 + 1], h = seg[e * 4 + 2], q = seg[e * 4 + 3];
+                if (q >= (uint64_t)np || h + 1 >= hoff[q].size()) return fail(GE_ERR_INVALID, "ge_download_segments_gen0: a part names a haplotype outside the re-base snapshot");
+                for (uint64_t k = hoff[q][h]; k < hoff[q][h + 1]; k++) {
+                    const uint64_t x = hseg[q][k * 4], y = hseg[q][k * 4 + 1];
+                    if (y > L && (y <= R || x < R)) { nseg.push_back(std::max(x, L)); nseg.push_back(std::min(y, R)); nseg.push_back(hseg[q][k * 4 + 2]); nseg.push_back(hseg[q][k * 4 + 3]); }
+                }
+            }
+        }
+        noff[n_rows] = nseg.size() / 4;
+        off.swap(noff); seg.swap(nseg);
+    }
     return GE_OK;
 }

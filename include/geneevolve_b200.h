@@ -214,6 +214,9 @@ int ge_get_gen0_constants(ge_ctx *ctx, int pop, int phen, double *var_a0, double
 /* Haplotypes of one chromosome as the reference's Hap_SNP matrix (ras_convert_interval_to_hap_matrix
  * :1186-1230): alleles[(2*i+h)*n_loci + s] in {0,1}.  Works in both representations. */
 int ge_download_haplotypes(ge_ctx *ctx, int pop, int chr, uint8_t *alleles);
+/* Verification aid: the same matrix built from the founder-segment lists and the founder panel even when the context also carries the
+ * bit-packed rows (which ge_download_haplotypes prefers) — the two must agree.  GE_REP_SEGMENTS only. */
+int ge_download_haplotypes_from_segments(ge_ctx *ctx, int pop, int chr, uint8_t *alleles);
 /* Same, bit-packed: words_per_hap = ceil(n_loci/32) little-endian bit order (locus s -> word s/32, bit s%32). */
 int ge_download_haplotypes_packed(ge_ctx *ctx, int pop, int chr, uint32_t *words);
 /* Founder segments of one chromosome, the `.int` content (ras_write_hap_to_interval_format :1582-1639).
@@ -228,6 +231,21 @@ int ge_download_cv_alleles(ge_ctx *ctx, int pop, int phen, int chr, uint8_t *out
  * The materialised haplotypes, causal-variant alleles and all values are unchanged; ge_download_segments then returns
  * the merged lists, which are no longer the reference's `.int` content.  n_before / n_after may be NULL. */
 int ge_compact_segments(ge_ctx *ctx, int pop, uint64_t *n_before, uint64_t *n_after);
+/* Extension, the other half of SURVEY.md §8f-3: re-base the founder panel to the CURRENT generation (all populations).  Every
+ * haplotype's alleles are materialised once into a new bit-packed founder panel (from the bit-packed rows when the context carries
+ * them, else from the lists and the old panel; contexts without a panel — BASELINE config 5 — only relabel), its causal-variant
+ * alleles become the founder CV panel, and every list restarts as one part {cov_lo, cov_hi, 2*i + h, population}.  Haplotypes, CV
+ * alleles and every value are unchanged; cost and memory of the segment path then follow the generations since the last re-base
+ * instead of since generation 0 (the reference only ever appends, src/Simulation.cpp:2903-2958).  With keep_history the replaced
+ * lists stay on the device and ge_download_segments_gen0 composes the current lists through them back to the generation-0
+ * founders — the reference's `.int` content; without it that lineage is dropped and memory stays flat.  ge_ibd_sharing and
+ * ge_download_segments afterwards speak of the re-base generation's haplotypes.  Needs sorted lists (every map the bit-packed
+ * representation accepts). */
+int ge_rebase_founders(ge_ctx *ctx, int keep_history);
+/* The lists of one chromosome against the generation-0 founders, composed through every re-base (all of them must have kept
+ * their history): same layout as ge_get_segment_count / ge_download_segments. */
+int ge_get_segment_count_gen0(ge_ctx *ctx, int pop, int chr, uint64_t *n_seg);
+int ge_download_segments_gen0(ge_ctx *ctx, int pop, int chr, uint64_t *seg_off, uint64_t *seg);
 /* Verification aid (GE_REP_SEGMENTS): rebuild the causal-variant planes of the current generation by scanning every
  * haplotype's parts exactly like ras_find_cv (:2752-2815).  The hot path never does this — it carries the planes
  * forward by crossover parity — so the planes before and after this call must be identical. */

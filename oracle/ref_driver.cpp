@@ -239,6 +239,92 @@ static bool parts_equal(const std::vector<part> &a, const std::vector<part> &b) 
     return true;
 }
 
+// The draws random_mate (:2090-2157) / assort_mate (:2167-2360) consumed, captured by re-deriving their engines: the functions seed
+// everything from successive ras_glob_seed() calls, so with glob_generator rewound to its state before the call the same seeds come
+// out again, and the reference's OWN helpers (RasRandomNumber::ras_mvnorm, ras_rpois, std::random_shuffle over rand()) give the same
+// values.  Nothing of the pairing logic is restated here; the exported couples stay those of the untouched function.  Self-checks:
+// glob_generator must end in the state the real call left, and the Poisson family sizes must equal the couples' num_offspring.
+extern int myrandom(int i);   // src/Simulation.cpp:11-14
+static void export_mating_draws(Simulation &sim, int p, int gen, const std::default_random_engine &g_before) {
+    Population &P = sim.population[p];
+    const std::default_random_engine g_after = sim.glob_generator;
+    sim.glob_generator = g_before;
+    const uint64_t n_h = P.h.size();
+    const double nan = std::nan("");
+    std::vector<double> thin_u(n_h, nan), mm_u(n_h, nan);
+    if (P._RM) {
+        unsigned seed = sim.ras_glob_seed();
+        std::default_random_engine generator(seed);
+        std::uniform_real_distribution<double> distribution(0.0, 1.0);
+        uint64_t n_m = 0, n_f = 0;
+        for (uint64_t i = 0; i < n_h; i++) {
+            double r = distribution(generator);
+            thin_u[i] = r;
+            if (r < P.h[i].selection_value_func) { if (P.h[i].sex == 1) n_m++; else if (P.h[i].sex == 2) n_f++; }
+        }
+        std::default_random_engine g_uint_f(seed + 1), g_uint_m(seed + 2);
+        std::uniform_int_distribution<unsigned long int> d_uint_f(0, n_m - 1), d_uint_m(0, n_f - 1);
+        const uint64_t nc = P._pop_size[gen - 1];
+        std::vector<uint64_t> i_f(nc), i_m(nc);
+        for (uint64_t i = 0; i < nc; i++) { i_f[i] = d_uint_f(g_uint_f); i_m[i] = d_uint_m(g_uint_m); }
+        W.put(key(gen, p, "mate.rm_father_idx"), i_f);
+        W.put(key(gen, p, "mate.rm_mother_idx"), i_m);
+    } else {
+        unsigned seed = sim.ras_glob_seed();
+        std::srand(seed);
+        std::default_random_engine generator(sim.ras_glob_seed());
+        std::uniform_real_distribution<double> distribution(0.0, 1.0);
+        uint64_t n_m = 0, n_f = 0;
+        for (uint64_t i = 0; i < n_h; i++) {
+            double r = distribution(generator);
+            thin_u[i] = r;
+            if (r < P.h[i].selection_value_func && (P.h[i].sex == 1 || P.h[i].sex == 2)) {
+                double r2 = distribution(generator);
+                mm_u[i] = r2;
+                (P.h[i].sex == 1 ? n_m : n_f) += (r2 < P._MM_percent) ? 2 : 1;
+            }
+        }
+        std::vector<uint64_t> trim_order;
+        if (n_m != n_f) {   // the longer list after std::random_shuffle (:2235 / :2242): positions in the unshuffled list
+            trim_order.resize(std::max(n_m, n_f));
+            for (uint64_t k = 0; k < trim_order.size(); k++) trim_order[k] = k;
+            std::random_shuffle(trim_order.begin(), trim_order.end());
+        }
+        W.put(key(gen, p, "mate.trim_order"), trim_order);
+        const uint64_t n2 = std::min(n_m, n_f);
+        std::vector<double> mu(2, 0);
+        std::vector<std::vector<double> > corr(2, std::vector<double>(2, 0));
+        corr[0][0] = 1; corr[0][1] = P._mat_cor[gen - 1]; corr[1][0] = P._mat_cor[gen - 1]; corr[1][1] = 1;
+        std::vector<std::vector<double> > tpl = RasRandomNumber::ras_mvnorm(n2, mu, corr, sim.ras_glob_seed());
+        std::vector<double> t1(n2), t2(n2);
+        for (uint64_t i = 0; i < n2; i++) { t1[i] = tpl[i][0]; t2[i] = tpl[i][1]; }
+        W.put(key(gen, p, "mate.t1"), t1);
+        W.put(key(gen, p, "mate.t2"), t2);
+        if (P._couples_info.size() != n2) die("mating draws: couple count differs from the reference's");
+        uint64_t n_inbreed = 0;
+        for (auto &c : P._couples_info) n_inbreed += c.inbreed ? 1 : 0;
+        const std::string &od = P._offspring_dist[gen - 1];
+        std::vector<int32_t> family;
+        std::vector<uint64_t> remainder_order;
+        if (od == "p" || od == "P") {
+            double lam = (double)P._pop_size[gen - 1] / (n2 - n_inbreed);
+            std::vector<int> no = RasRandomNumber::ras_rpois(n2, lam, sim.ras_glob_seed());
+            family.assign(no.begin(), no.end());
+            for (uint64_t i = 0; i < n2; i++) if (family[i] != P._couples_info[i].num_offspring) die("mating draws: Poisson family sizes differ from the reference's couples");
+        } else if (!P._avoid_inbreeding) {   // pos_couple_can_marry is only filled without --avoid_inbreeding (:2322-2326)
+            remainder_order.resize(n2);
+            for (uint64_t k = 0; k < n2; k++) remainder_order[k] = k;
+            std::random_shuffle(remainder_order.begin(), remainder_order.end(), myrandom);
+        }
+        W.put(key(gen, p, "mate.family"), family);
+        W.put(key(gen, p, "mate.remainder_order"), remainder_order);
+    }
+    W.put(key(gen, p, "mate.thin_u"), thin_u);
+    W.put(key(gen, p, "mate.mm_u"), mm_u);
+    if (!(sim.glob_generator == g_after)) die("mating draws: glob_generator ended in a different state than the reference's call left");
+    sim.glob_generator = g_after;
+}
+
 // Runs the untouched reproduce(), then replays its loop body (:2433-2488) to capture the local draws.
 static std::vector<Human> reproduce_with_export(Simulation &sim, int p, int gen) {
     Population &P = sim.population[p];
@@ -425,8 +511,10 @@ int main(int argc, char **argv) {
     for (int gen = 1; gen <= sim._tot_gen; gen++) {
         for (int p = 0; p < sim._n_pop; p++) {
             Population &P = sim.population[p];
+            const std::default_random_engine g_before_mating = sim.glob_generator;
             bool ok = P._RM ? sim.random_mate(p, gen - 1) : sim.assort_mate(p, gen - 1);
             if (!ok) die("mating failed");
+            export_mating_draws(sim, p, gen, g_before_mating);
             P.h = reproduce_with_export(sim, p, gen);
             if (!sim.ras_compute_AD(p, gen)) die("ras_compute_AD failed");
             phenotypes_with_export(sim, gen, p);
