@@ -192,7 +192,7 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measure_workload(name, local, steps, warmup, n=None, loci=None, e2e=True, phases_steps=5):
+def measure_workload(name, local, steps, warmup, n=None, loci=None, e2e=True, phases_steps=5, flags=0):
     """One single-GPU workload through the C-ABI: device-resident arm, end-to-end arm, dominant-kernel roofline (CUDA events on the
     kernel's own stream inside the timed region) and, in a short extra pass, the phases of the control chain."""
     import torch
@@ -207,7 +207,7 @@ def measure_workload(name, local, steps, warmup, n=None, loci=None, e2e=True, ph
         morgans = sum(float(p.sum()) for _, _, p in cfg["maps"])
         seg_cap = int(2 * cap * (len(cfg["chrs"]) + (total_steps + 1) * morgans) * 1.05)
     eng = capi.Engine(seg_capacity=seg_cap, n_pop=1, n_chr=len(cfg["chrs"]), n_phen=1, device=local, representation=capi.GE_REP_SEGMENTS if segs else capi.GE_REP_BITS,
-                      rng_mode=capi.GE_RNG_PHILOX, seed=12345, capacity=cap)
+                      rng_mode=capi.GE_RNG_PHILOX, seed=12345, capacity=cap, flags=flags)
     kid = capi.GE_KERNEL_RECOMBINE_SEGMENTS if segs else capi.GE_KERNEL_PROPAGATE_BITS
     kname = "seg_plan_kernel + seg_gather_kernel" if segs else "propagate_bits_kernel"
     workloads.configure_engine(eng, cfg)
@@ -309,7 +309,9 @@ def ours(args):
     torch.cuda.set_device(local)
     if "pops" in workloads.CONFIGS[args.workload]:
         raise SystemExit("multi-population workloads run sharded: launch with torchrun (config 4 needs >= 4 GPUs at full size)")
-    r = measure_workload(args.workload, local, args.steps, args.warmup, n=args.n, loci=args.loci)
+    from geneevolve_b200 import capi as _capi
+    flags = (_capi.GE_FLAG_SERIAL if args.serial else 0) | _capi.GE_FLAG_CTRL_SMS(args.ctrl_sms)
+    r = measure_workload(args.workload, local, args.steps, args.warmup, n=args.n, loci=args.loci, flags=flags)
     cfg, M, N, segs = r["cfg"], r["M"], r["N"], r["segs"]
     traffic = traffic_source = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -358,6 +360,8 @@ def main():
     ap.add_argument("--loci", type=int, default=None, help="override loci (debug)")
     ap.add_argument("--ref-sample", type=int, default=1500, help="individuals in the bounded reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="measurement aid: no overlap of the bulk copy with the next generation's control chain")
+    ap.add_argument("--ctrl-sms", type=int, default=0, help="measurement aid: SM partition, SMs for the control chain (0 = library default)")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the short records of the other BASELINE configurations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

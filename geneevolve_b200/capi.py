@@ -14,6 +14,10 @@ import numpy as np
 GE_REP_BITS, GE_REP_SEGMENTS = 1, 2
 GE_RNG_PHILOX, GE_RNG_REPLAY = 0, 1
 GE_FLAG_SERIAL, GE_FLAG_SEG_WIDE_PARTS, GE_FLAG_SEG_VERBATIM, GE_FLAG_CV_FROM_SEGMENTS, GE_FLAG_NO_GRAPH = 1, 2, 4, 8, 16
+
+
+def GE_FLAG_CTRL_SMS(n):
+    return (int(n) & 0xFF) << 8
 GE_SEL = {"": 0, "logit": 1, "probit": 2, "stab": 3, "thr": 4}
 GE_KERNEL_PROPAGATE_BITS, GE_KERNEL_RECOMBINE_SEGMENTS = 0, 1
 GE_PHASES = {"mate": 2, "sample": 3, "cv_and_genetic_values": 4, "phenotype": 5}
@@ -38,6 +42,12 @@ class ge_draws(C.Structure):
     _fields_ = [("n_offspring", C.c_uint64), ("father", _u64p), ("mother", _u64p), ("sex", _u8p),
                 ("xo_off", _u64p), ("xo_bp", _u64p), ("start_hap", _u8p), ("mut_off", _u64p),
                 ("mut_bp", _u64p), ("mut_gam", _u8p), ("e_raw", _f64p), ("common", _f64p), ("parental0", _f64p)]
+
+
+class ge_mate_draws(C.Structure):
+    _fields_ = [("thin_u", _f64p), ("mm_u", _f64p), ("trim_order", _u64p), ("n_trim_order", C.c_uint64), ("t1", _f64p), ("t2", _f64p),
+                ("n_couples", C.c_uint64), ("family", _i32p), ("remainder_order", _u64p), ("n_remainder_order", C.c_uint64),
+                ("rm_father_idx", _u64p), ("rm_mother_idx", _u64p), ("n_rm", C.c_uint64)]
 
 
 class ge_indiv_soa(C.Structure):
@@ -221,6 +231,18 @@ class Engine:
 
     def mate(self, pop, gen, params):
         self._call("mate", self.ctx, pop, gen, C.byref(params))
+
+    def mate_replay(self, pop, gen, params, *, thin_u, mm_u=None, trim_order=None, t1=None, t2=None, family=None, remainder_order=None,
+                    rm_father_idx=None, rm_mother_idx=None):
+        """The device mating kernels under the reference's own draws (ge_mate_replay); arrays as exported into tests/golden."""
+        a = dict(thin_u=_arr(thin_u, np.float64), mm_u=_arr(mm_u, np.float64), trim_order=_arr(trim_order, np.uint64), t1=_arr(t1, np.float64),
+                 t2=_arr(t2, np.float64), family=_arr(family, np.int32), remainder_order=_arr(remainder_order, np.uint64),
+                 rm_father_idx=_arr(rm_father_idx, np.uint64), rm_mother_idx=_arr(rm_mother_idx, np.uint64))
+        n = lambda k: 0 if a[k] is None else len(a[k])  # noqa: E731
+        md = ge_mate_draws(_ptr(a["thin_u"], _f64p), _ptr(a["mm_u"], _f64p), _ptr(a["trim_order"], _u64p), n("trim_order"), _ptr(a["t1"], _f64p),
+                           _ptr(a["t2"], _f64p), n("t1"), _ptr(a["family"], _i32p), _ptr(a["remainder_order"], _u64p), n("remainder_order"),
+                           _ptr(a["rm_father_idx"], _u64p), _ptr(a["rm_mother_idx"], _u64p), n("rm_father_idx"))
+        self._call("mate_replay", self.ctx, pop, gen, C.byref(params), C.byref(md))
 
     def set_couples(self, pop, pos_male, pos_female, inbreed, num_offspring):
         m, f = _arr(pos_male, np.uint64), _arr(pos_female, np.uint64)

@@ -7,6 +7,8 @@
 // Reference lines cited as :N are src/Simulation.cpp:N.
 #include "ge_context.cuh"
 #include <cstdlib>
+#include <cuda.h>
+#include <dlfcn.h>
 #include "ge_segments.cuh"
 #include "ge_mating.cuh"
 
@@ -269,6 +271,45 @@ static int build_cvset(ge_ctx *ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// SM partition (green contexts): the control chain of generation g+1 runs beside the HBM-bound copy of generation g.  With stream
+// priorities alone its kernels displace copy CTAs on every SM (7.4 ms per generation against 6.4 ms for the copy alone on config 3);
+// with the SMs split, a small fixed slice runs the control chain and the copy keeps the rest to itself.  The driver API is taken
+// from libcuda at run time (no link dependency: the library must load on a box without a driver, e.g. to list its symbols).
+// ------------------------------------------------------------------------------------------------
+struct SmPartition {
+    CUgreenCtx ctrl = nullptr, bulk = nullptr;
+    int ctrl_sms = 0, bulk_sms = 0;
+};
+static bool make_sm_partition(int device, int want_ctrl_sms, SmPartition &out, cudaStream_t *ctrl_streams, int n_ctrl_streams, int prio_ctrl, cudaStream_t *bulk_stream, int prio_bulk) {
+    void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+#define GE_DRV(name) auto p_##name = reinterpret_cast<decltype(&name)>(dlsym(lib, #name)); if (!p_##name) return false
+    GE_DRV(cuDeviceGet); GE_DRV(cuDeviceGetDevResource); GE_DRV(cuDevSmResourceSplitByCount); GE_DRV(cuDevResourceGenerateDesc); GE_DRV(cuGreenCtxCreate);
+    GE_DRV(cuGreenCtxStreamCreate); GE_DRV(cuGreenCtxDestroy);
+#undef GE_DRV
+    CUdevice dev;
+    if (p_cuDeviceGet(&dev, device) != CUDA_SUCCESS) return false;
+    CUdevResource all, ctrl, rest;
+    if (p_cuDeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned int groups = 1;
+    if (p_cuDevSmResourceSplitByCount(&ctrl, &groups, &all, &rest, 0, (unsigned int)want_ctrl_sms) != CUDA_SUCCESS || groups != 1) return false;
+    CUdevResourceDesc d_ctrl, d_rest;
+    if (p_cuDevResourceGenerateDesc(&d_ctrl, &ctrl, 1) != CUDA_SUCCESS || p_cuDevResourceGenerateDesc(&d_rest, &rest, 1) != CUDA_SUCCESS) return false;
+    if (p_cuGreenCtxCreate(&out.ctrl, d_ctrl, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (p_cuGreenCtxCreate(&out.bulk, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { p_cuGreenCtxDestroy(out.ctrl); out.ctrl = nullptr; return false; }
+    out.ctrl_sms = (int)ctrl.sm.smCount; out.bulk_sms = (int)rest.sm.smCount;
+    for (int k = 0; k < n_ctrl_streams; k++) {
+        CUstream s;
+        if (p_cuGreenCtxStreamCreate(&s, out.ctrl, CU_STREAM_NON_BLOCKING, prio_ctrl) != CUDA_SUCCESS) return false;
+        ctrl_streams[k] = (cudaStream_t)s;
+    }
+    CUstream s;
+    if (p_cuGreenCtxStreamCreate(&s, out.bulk, CU_STREAM_NON_BLOCKING, prio_bulk) != CUDA_SUCCESS) return false;
+    *bulk_stream = (cudaStream_t)s;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -311,15 +352,28 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
     auto setup = [&]() -> int {
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
-        CUDA_TRY(cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo));
+        CUDA_TRY(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+        const int want = (cfg->flags >> 8) & 0xFF;   // GE_FLAG_CTRL_SMS(n)
+        if (want > 0 && !c->serial) {
+            CUDA_TRY(cudaFree(0));   // the primary context must exist before green contexts are carved out of it
+            cudaStream_t cs[1 + N_SORT_LANES] = {nullptr};
+            SmPartition part;
+            if (make_sm_partition(cfg->device, want, part, cs, 1 + N_SORT_LANES, prio_hi, &c->bulk, prio_lo)) {
+                c->stream = cs[0];
+                for (int k = 0; k < N_SORT_LANES; k++) c->lane[k].s = cs[1 + k];
+                c->ctrl_sms = part.ctrl_sms; c->bulk_sms = part.bulk_sms;
+                c->n_sm = part.ctrl_sms;   // what the control kernels' grids are sized for
+                c->thin = 0;               // no thin grids: the control chain owns its SMs
+            } else cudaGetLastError();
+        }
+        if (!c->stream) CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+        if (!c->bulk) CUDA_TRY(cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo));
         CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         for (PopDev &P : c->pop) for (DrawSet &D : P.ds) CUDA_TRY(cudaEventCreateWithFlags(&D.bulk_done, cudaEventDisableTiming));
         for (PopDev &P : c->pop) CUDA_TRY(cudaEventCreateWithFlags(&P.ev_ready, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        for (SortLane &l : c->lane) { CUDA_TRY(cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, prio_hi)); CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming)); }
-        CUDA_TRY(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+        for (SortLane &l : c->lane) { if (!l.s) CUDA_TRY(cudaStreamCreateWithPriority(&l.s, cudaStreamNonBlocking, prio_hi)); CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming)); }
         // the device-resident step state of every population, and its pinned read-back buffer
         GE_TRY(c->ensure(c->d_ss_all, sizeof(StepState) * cfg->n_pop));
         CUDA_TRY(cudaMemsetAsync(c->d_ss_all.p, 0, sizeof(StepState) * cfg->n_pop, c->stream));
@@ -943,6 +997,24 @@ int ge_mate(ge_ctx *ctx, int pop, int gen, const ge_gen_params *gp) {  // random
         GE_TRY(enqueue_mate(ctx, pop, *gp));
     }
     return ctx->pull_state("ge_mate");
+}
+
+int ge_mate_replay(ge_ctx *ctx, int pop, int gen, const ge_gen_params *gp, const ge_mate_draws *md) {
+    CHECK_POP(ctx, pop);
+    if (!gp || !md) return fail(GE_ERR_INVALID, "null params / draws");
+    PopDev &P = ctx->pop[pop];
+    if (P.st[P.cur].n == 0) return fail(GE_ERR_INVALID, "empty population");
+    CUDA_TRY(cudaSetDevice(ctx->cfg.device));
+    GE_TRY(enqueue_step_begin(ctx, pop, gen, *gp));
+    GE_TRY(enqueue_mate(ctx, pop, *gp, md));
+    GE_TRY(ctx->pull_state("ge_mate_replay"));   // (also: the caller's arrays were read asynchronously)
+    // the draws must be the ones of THIS population state: list lengths and couple count follow from the thinning uniforms
+    const StepState &h = P.hs;
+    if (!P.RM) {
+        if (h.n2 != md->n_couples) return fail(GE_ERR_INVALID, "ge_mate_replay: the thinning uniforms give " + std::to_string(h.n2) + " couples, the draws were made for " + std::to_string(md->n_couples));
+        if (h.n_trim_list != (md->trim_order ? md->n_trim_order : 0)) return fail(GE_ERR_INVALID, "ge_mate_replay: trim_order does not have the length of the longer sex list");
+    }
+    return GE_OK;
 }
 
 // ---------------- reproduce ----------------

@@ -52,6 +52,7 @@ extern "C" {
 #define GE_FLAG_SEG_VERBATIM 4      /* recombine founder segments with the reference's loop verbatim, one thread per gamete (implies 16-byte parts) */
 #define GE_FLAG_CV_FROM_SEGMENTS 8  /* ge_compute_AD rebuilds the causal-variant planes from the segment lists like ras_find_cv, every generation */
 #define GE_FLAG_NO_GRAPH 16         /* never replay a generation's control chain as a captured CUDA graph */
+#define GE_FLAG_CTRL_SMS(n) (((n) & 0xFF) << 8) /* SM partition (green contexts): the control chain gets n SMs to itself, the bulk copy the rest; 0 = none */
 
 typedef struct ge_ctx ge_ctx;
 
@@ -102,6 +103,23 @@ typedef struct ge_draws {
     const double *common;       /* [n_phen][n_offspring] sibling-common effect per offspring (:2481-2484), or NULL */
     const double *parental0;    /* [n_phen][n] generation-0 parental effect N(0,vf) (:3108-3114); read by ge_init_generation0 only */
 } ge_draws;
+
+/* The draws random_mate (:2090-2157) / assort_mate (:2167-2360) consume, for ge_mate_replay (fixed-draw parity of the mating kernels:
+ * with the reference's own draws the device must arrive at the reference's `_couples_info`).  Lengths are the reference's. */
+typedef struct ge_mate_draws {
+    const double *thin_u;            /* [n] the uniform compared with selection_value_func (:2110 / :2191), individual order */
+    const double *mm_u;              /* [n] the second uniform of a kept individual, compared with --MM (:2202, :2213); ignored elsewhere; NULL for random mating */
+    const uint64_t *trim_order;      /* [n_trim_order] the longer sex list after std::random_shuffle (:2235 / :2242), as positions in the unshuffled */
+    uint64_t n_trim_order;           /*   list: its first |n_m - n_f| entries leave.  NULL / 0 when the lists are equal */
+    const double *t1, *t2;           /* [n_couples] the two columns of ras_mvnorm's template (:2268) */
+    uint64_t n_couples;
+    const int32_t *family;           /* [n_couples] ras_rpois's family sizes (:2331), or NULL for the fixed distribution */
+    const uint64_t *remainder_order; /* [n_remainder_order] pos_couple_can_marry after std::random_shuffle (:2350): its first pop_size - nf * couples */
+    uint64_t n_remainder_order;      /*   entries get one more child.  Fixed distribution only */
+    const uint64_t *rm_father_idx;   /* [n_rm] random mating: index of the father in the thinned male list (:2145), mother likewise (:2146) */
+    const uint64_t *rm_mother_idx;
+    uint64_t n_rm;                   /* = pop_size */
+} ge_mate_draws;
 
 /* per-individual arrays, the columns of the `.info` file (Population::ras_save_human_info,
  * src/Population.cpp:510-568).  Caller allocates for ge_get_population_size() individuals. */
@@ -171,6 +189,12 @@ int ge_init_generation0(ge_ctx *ctx, const ge_draws *draws0 /* [n_pop] or NULL *
 /* bool random_mate(int ipop,int gen_ind) :2090-2157 / bool assort_mate(int ipop,int gen_ind) :2167-2360.
  * Chooses by the population's random_mating flag like sim_next_generation (:1907-1918). */
 int ge_mate(ge_ctx *ctx, int pop, int gen, const ge_gen_params *params);
+/* The same mating kernels under the reference's own draws (GE_RNG_REPLAY contexts): thinning, the trim of the longer sex list, the
+ * sorts by mating value, the ranks of the template, pairing, the inbreeding exclusion and the family sizes run on the device exactly
+ * as in ge_mate, with every random number taken from `draws` instead of the Philox streams.  The couples must then equal the
+ * reference's (ge_get_couples).  std::sort's order among DISTINCT individuals with equal mating values is the one thing not pinned
+ * (the device sorts stably). */
+int ge_mate_replay(ge_ctx *ctx, int pop, int gen, const ge_gen_params *params, const ge_mate_draws *draws);
 /* Population::_couples_info (src/Population.h:165-180): supply (replay) or read back the couples. */
 int ge_set_couples(ge_ctx *ctx, int pop, const uint64_t *pos_male, const uint64_t *pos_female,
                    const uint8_t *inbreed, const int32_t *num_offspring, uint64_t n_couples);

@@ -88,6 +88,20 @@ class Golden:
             kw.update(mut_off=g("mut_off"), mut_bp=g("mut_bp"), mut_gam=g("mut_gam"))
         return capi.Draws(n, **kw)
 
+    def mate_draws(self, gen, pop):
+        """Keyword arguments of Engine.mate_replay: the draws the reference's random_mate / assort_mate consumed in this generation."""
+        m = lambda k: self.g(gen, pop, "mate." + k)  # noqa: E731
+        if int(self.z[f"in.p{pop}.RM"]):
+            return dict(thin_u=m("thin_u"), rm_father_idx=m("rm_father_idx"), rm_mother_idx=m("rm_mother_idx"))
+        kw = dict(thin_u=m("thin_u"), mm_u=np.nan_to_num(m("mm_u"), nan=2.0), t1=m("t1"), t2=m("t2"))
+        if len(m("trim_order")):
+            kw["trim_order"] = m("trim_order")
+        if len(m("family")):
+            kw["family"] = m("family")
+        if len(m("remainder_order")):
+            kw["remainder_order"] = m("remainder_order")
+        return kw
+
     def birth_order(self, gen, pop, name):
         """Per-offspring [n_phen][n] array `name` in birth order.  Without migration that is the exported
         state; with migration the children are found again by (ID, father ID, mother ID)."""

@@ -63,6 +63,13 @@ def test_replay_matches_reference(cuda_lib, name, rep):
             for k in a:
                 assert a[k] == pytest.approx(b[k], rel=1e-12, abs=1e-14)
     for gen in range(1, G.G + 1):
+        # the device mating kernels under the reference's own mating draws must arrive at the reference's couples
+        # (src/Simulation.cpp:2090-2157 / :2167-2360); the generation itself then replays the reference's per-offspring draws
+        for p in range(G.n_pop):
+            gpu.mate_replay(p, gen, G.params(gen, p), **G.mate_draws(gen, p))
+            c = gpu.get_couples(p)
+            for k, key in (("pos_male", "couple_male"), ("pos_female", "couple_female"), ("inbreed", "couple_inbreed"), ("num_offspring", "couple_noff")):
+                assert np.array_equal(c[k].astype(np.int64), G.g(gen, p, key).astype(np.int64)), f"{G.name} gen {gen} pop {p}: {key} under the reference's mating draws"
         step_replay(G, gpu, gen)
         step_replay(G, cpu, gen)
         compare_to_golden(G, gpu, gen)
