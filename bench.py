@@ -310,7 +310,7 @@ def ours(args):
     if "pops" in workloads.CONFIGS[args.workload]:
         raise SystemExit("multi-population workloads run sharded: launch with torchrun (config 4 needs >= 4 GPUs at full size)")
     from geneevolve_b200 import capi as _capi
-    flags = (_capi.GE_FLAG_SERIAL if args.serial else 0) | _capi.GE_FLAG_CTRL_SMS(args.ctrl_sms)
+    flags = _capi.GE_FLAG_SERIAL if args.serial else 0
     r = measure_workload(args.workload, local, args.steps, args.warmup, n=args.n, loci=args.loci, flags=flags)
     cfg, M, N, segs = r["cfg"], r["M"], r["N"], r["segs"]
     traffic = traffic_source = None
@@ -361,7 +361,6 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1500, help="individuals in the bounded reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="measurement aid: no overlap of the bulk copy with the next generation's control chain")
-    ap.add_argument("--ctrl-sms", type=int, default=0, help="measurement aid: SM partition, SMs for the control chain (0 = library default)")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the short records of the other BASELINE configurations")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

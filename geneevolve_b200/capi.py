@@ -14,10 +14,6 @@ import numpy as np
 GE_REP_BITS, GE_REP_SEGMENTS = 1, 2
 GE_RNG_PHILOX, GE_RNG_REPLAY = 0, 1
 GE_FLAG_SERIAL, GE_FLAG_SEG_WIDE_PARTS, GE_FLAG_SEG_VERBATIM, GE_FLAG_CV_FROM_SEGMENTS, GE_FLAG_NO_GRAPH = 1, 2, 4, 8, 16
-
-
-def GE_FLAG_CTRL_SMS(n):
-    return (int(n) & 0xFF) << 8
 GE_SEL = {"": 0, "logit": 1, "probit": 2, "stab": 3, "thr": 4}
 GE_KERNEL_PROPAGATE_BITS, GE_KERNEL_RECOMBINE_SEGMENTS = 0, 1
 GE_PHASES = {"mate": 2, "sample": 3, "cv_and_genetic_values": 4, "phenotype": 5}

@@ -7,8 +7,6 @@
 // Reference lines cited as :N are src/Simulation.cpp:N.
 #include "ge_context.cuh"
 #include <cstdlib>
-#include <cuda.h>
-#include <dlfcn.h>
 #include "ge_segments.cuh"
 #include "ge_mating.cuh"
 
@@ -271,45 +269,6 @@ static int build_cvset(ge_ctx *ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// SM partition (green contexts): the control chain of generation g+1 runs beside the HBM-bound copy of generation g.  With stream
-// priorities alone its kernels displace copy CTAs on every SM (7.4 ms per generation against 6.4 ms for the copy alone on config 3);
-// with the SMs split, a small fixed slice runs the control chain and the copy keeps the rest to itself.  The driver API is taken
-// from libcuda at run time (no link dependency: the library must load on a box without a driver, e.g. to list its symbols).
-// ------------------------------------------------------------------------------------------------
-struct SmPartition {
-    CUgreenCtx ctrl = nullptr, bulk = nullptr;
-    int ctrl_sms = 0, bulk_sms = 0;
-};
-static bool make_sm_partition(int device, int want_ctrl_sms, SmPartition &out, cudaStream_t *ctrl_streams, int n_ctrl_streams, int prio_ctrl, cudaStream_t *bulk_stream, int prio_bulk) {
-    void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) return false;
-#define GE_DRV(name) auto p_##name = reinterpret_cast<decltype(&name)>(dlsym(lib, #name)); if (!p_##name) return false
-    GE_DRV(cuDeviceGet); GE_DRV(cuDeviceGetDevResource); GE_DRV(cuDevSmResourceSplitByCount); GE_DRV(cuDevResourceGenerateDesc); GE_DRV(cuGreenCtxCreate);
-    GE_DRV(cuGreenCtxStreamCreate); GE_DRV(cuGreenCtxDestroy);
-#undef GE_DRV
-    CUdevice dev;
-    if (p_cuDeviceGet(&dev, device) != CUDA_SUCCESS) return false;
-    CUdevResource all, ctrl, rest;
-    if (p_cuDeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
-    unsigned int groups = 1;
-    if (p_cuDevSmResourceSplitByCount(&ctrl, &groups, &all, &rest, 0, (unsigned int)want_ctrl_sms) != CUDA_SUCCESS || groups != 1) return false;
-    CUdevResourceDesc d_ctrl, d_rest;
-    if (p_cuDevResourceGenerateDesc(&d_ctrl, &ctrl, 1) != CUDA_SUCCESS || p_cuDevResourceGenerateDesc(&d_rest, &rest, 1) != CUDA_SUCCESS) return false;
-    if (p_cuGreenCtxCreate(&out.ctrl, d_ctrl, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
-    if (p_cuGreenCtxCreate(&out.bulk, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { p_cuGreenCtxDestroy(out.ctrl); out.ctrl = nullptr; return false; }
-    out.ctrl_sms = (int)ctrl.sm.smCount; out.bulk_sms = (int)rest.sm.smCount;
-    for (int k = 0; k < n_ctrl_streams; k++) {
-        CUstream s;
-        if (p_cuGreenCtxStreamCreate(&s, out.ctrl, CU_STREAM_NON_BLOCKING, prio_ctrl) != CUDA_SUCCESS) return false;
-        ctrl_streams[k] = (cudaStream_t)s;
-    }
-    CUstream s;
-    if (p_cuGreenCtxStreamCreate(&s, out.bulk, CU_STREAM_NON_BLOCKING, prio_bulk) != CUDA_SUCCESS) return false;
-    *bulk_stream = (cudaStream_t)s;
-    return true;
-}
-
-// ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -353,19 +312,6 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_TRY(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
-        const int want = (cfg->flags >> 8) & 0xFF;   // GE_FLAG_CTRL_SMS(n)
-        if (want > 0 && !c->serial) {
-            CUDA_TRY(cudaFree(0));   // the primary context must exist before green contexts are carved out of it
-            cudaStream_t cs[1 + N_SORT_LANES] = {nullptr};
-            SmPartition part;
-            if (make_sm_partition(cfg->device, want, part, cs, 1 + N_SORT_LANES, prio_hi, &c->bulk, prio_lo)) {
-                c->stream = cs[0];
-                for (int k = 0; k < N_SORT_LANES; k++) c->lane[k].s = cs[1 + k];
-                c->ctrl_sms = part.ctrl_sms; c->bulk_sms = part.bulk_sms;
-                c->n_sm = part.ctrl_sms;   // what the control kernels' grids are sized for
-                c->thin = 0;               // no thin grids: the control chain owns its SMs
-            } else cudaGetLastError();
-        }
         if (!c->stream) CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
         if (!c->bulk) CUDA_TRY(cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo));
         CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -1151,14 +1097,26 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
         uint32_t *off_rows = off.hap.as<uint32_t>();
         const uint64_t *xo_off = D.xo_off.as<uint64_t>();
         const uint8_t *start = D.start_hap.as<uint8_t>();
+#ifdef GE_EXP_RING
+        const size_t smem = prop_ring_smem_bytes(C);
+        if (!ctx->ring_attr_set) {   // six CTAs of 34 KB per SM: ask for the shared-memory end of the L1/shared split
+            CUDA_TRY(cudaFuncSetAttribute(propagate_bits_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            ctx->ring_attr_set = true;
+        }
+#else
         const size_t smem = prop_smem_bytes(C);
+#endif
         DrawSet *Dp = &D;
         const double bulk_bytes = (double)cap * ctx->W * 16.0;
         GE_TRY(ctx->to_bulk(P.ev_ready, [=]() -> int {
             cudaStream_t bulk = ctx->serial ? ctx->stream : ctx->bulk;
             ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0, 0, 0};
             if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, bulk)); }
+#ifdef GE_EXP_RING
+            propagate_bits_ring_kernel<<<grid, PROP_THREADS, smem, bulk>>>(gnm, tiles, dc, par_rows, rowmap, off_rows, fa, mo, xo_off, fl, start);
+#else
             propagate_bits_kernel<<<grid, PROP_THREADS, smem, bulk>>>(gnm, tiles, dc, par_rows, rowmap, off_rows, fa, mo, xo_off, fl, start);
+#endif
             GE_TRY(ctx->check_launch("propagate_bits"));
             if (ctx->profiling) {
                 CUDA_TRY(cudaEventRecord(evp.b, bulk));

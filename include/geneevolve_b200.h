@@ -52,7 +52,6 @@ extern "C" {
 #define GE_FLAG_SEG_VERBATIM 4      /* recombine founder segments with the reference's loop verbatim, one thread per gamete (implies 16-byte parts) */
 #define GE_FLAG_CV_FROM_SEGMENTS 8  /* ge_compute_AD rebuilds the causal-variant planes from the segment lists like ras_find_cv, every generation */
 #define GE_FLAG_NO_GRAPH 16         /* never replay a generation's control chain as a captured CUDA graph */
-#define GE_FLAG_CTRL_SMS(n) (((n) & 0xFF) << 8) /* SM partition (green contexts): the control chain gets n SMs to itself, the bulk copy the rest; 0 = none */
 
 typedef struct ge_ctx ge_ctx;
 
