@@ -1097,26 +1097,14 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
         uint32_t *off_rows = off.hap.as<uint32_t>();
         const uint64_t *xo_off = D.xo_off.as<uint64_t>();
         const uint8_t *start = D.start_hap.as<uint8_t>();
-#ifdef GE_EXP_RING
-        const size_t smem = prop_ring_smem_bytes(C);
-        if (!ctx->ring_attr_set) {   // six CTAs of 34 KB per SM: ask for the shared-memory end of the L1/shared split
-            CUDA_TRY(cudaFuncSetAttribute(propagate_bits_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            ctx->ring_attr_set = true;
-        }
-#else
         const size_t smem = prop_smem_bytes(C);
-#endif
         DrawSet *Dp = &D;
         const double bulk_bytes = (double)cap * ctx->W * 16.0;
         GE_TRY(ctx->to_bulk(P.ev_ready, [=]() -> int {
             cudaStream_t bulk = ctx->serial ? ctx->stream : ctx->bulk;
             ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0, 0, 0};
             if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, bulk)); }
-#ifdef GE_EXP_RING
-            propagate_bits_ring_kernel<<<grid, PROP_THREADS, smem, bulk>>>(gnm, tiles, dc, par_rows, rowmap, off_rows, fa, mo, xo_off, fl, start);
-#else
             propagate_bits_kernel<<<grid, PROP_THREADS, smem, bulk>>>(gnm, tiles, dc, par_rows, rowmap, off_rows, fa, mo, xo_off, fl, start);
-#endif
             GE_TRY(ctx->check_launch("propagate_bits"));
             if (ctx->profiling) {
                 CUDA_TRY(cudaEventRecord(evp.b, bulk));

@@ -213,7 +213,6 @@ struct ge_ctx {
     StepState *h_ss_all = nullptr;              // pinned read-back buffer of the same
     uint64_t graph_epoch = 0;                   // bumped whenever a device buffer is (re)allocated: captured graphs hold raw pointers
     int n_sm = 148;
-    bool ring_attr_set = false;
     // stats
     bool profiling = false;        // CUDA events around the dominant kernel (propagate_bits / the segment passes) on its own stream
     bool phase_timing = false;     // ... and around the phases of the control chain (ge_set_profiling level 2; disables graph replay)

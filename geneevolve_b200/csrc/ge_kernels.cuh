@@ -322,142 +322,6 @@ propagate_bits_kernel(Genome g, TileTable tt, const DrawCounts *__restrict__ dc,
 }
 
 // ------------------------------------------------------------------------------------------------
-// The same propagation with the runs staged through shared memory by cp.async (LDGSTS): the copy is bound by the bytes one SM keeps
-// in flight (its time follows the SM count, profiles/r2h_sm_partition.md), and with register-staged loads that is 4 x 16 B per lane
-// and 48 warps per SM because the data registers ARE the staging buffer.  Here every lane owns RING_STAGES 16-byte slots of a
-// per-warp ring in shared memory; a run is issued as asynchronous global->shared copies into one half of the ring while the
-// previous run's half is read back (LDS.128, the lane's own slots: no barrier) and stored — two runs (4 KB per warp) in flight
-// instead of one, at the same occupancy, with no data registers.  Runs longer than a half are split.  The crossover chunk is
-// unchanged (two register loads issued ahead, mask-merged by lane 0).
-// ------------------------------------------------------------------------------------------------
-constexpr int RING_STAGES = 8, RING_HALF = RING_STAGES / 2;
-static inline size_t prop_ring_smem_bytes(int n_chr) { return ((prop_smem_bytes(n_chr) + 15) & ~(size_t)15) + (size_t)(PROP_THREADS / 32) * RING_STAGES * 512; }
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g) {
-    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_addr));
-    return r;
-}
-struct RingPending { uint4 *dst; uint32_t q, qe, half; };   // a sub-run whose data is on its way into one half of the ring
-// chunks [q, qe) (at most RING_HALF * 32) of src -> ring half `half`; the lane's slot of stage s is at ring + s * 512
-__device__ __forceinline__ void ring_issue(uint32_t ring, uint32_t half, const uint4 *__restrict__ src, uint32_t q, uint32_t qe, int lane) {
-    uint32_t a = ring + half * (RING_HALF * 512);
-#pragma unroll
-    for (int u = 0; u < RING_HALF; u++) {
-        const uint32_t c = q + 32 * u + lane;
-        if (c < qe) cp_async16(a + u * 512, src + c);
-    }
-    cp_async_commit();
-}
-__device__ __forceinline__ void ring_drain(uint32_t ring, const RingPending &p, int lane) {
-    uint32_t a = ring + p.half * (RING_HALF * 512);
-#pragma unroll
-    for (int u = 0; u < RING_HALF; u += 2) {   // two slots at a time: eight data registers, not sixteen
-        const uint32_t c0 = p.q + 32 * u + lane, c1 = c0 + 32;
-        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-        if (c0 < p.qe) v0 = lds128(a + u * 512);
-        if (c1 < p.qe) v1 = lds128(a + (u + 1) * 512);
-        if (c0 < p.qe) st_stream(p.dst + c0, v0);
-        if (c1 < p.qe) st_stream(p.dst + c1, v1);
-    }
-}
-__global__ void __launch_bounds__(PROP_THREADS, 6)
-propagate_bits_ring_kernel(Genome g, TileTable tt, const DrawCounts *__restrict__ dc, const uint32_t *__restrict__ par_rows, const uint32_t *__restrict__ par_rowmap,
-                           uint32_t *__restrict__ off_rows, const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
-                           const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ flips, const uint8_t *__restrict__ start_hap) {
-    if (dc->fatal) return;
-    const uint32_t n_off = (uint32_t)dc->n_off;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_next;
-    const int n_ls = 2 * g.n_chr;
-    uint64_t *s_off = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *s_fl = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(n_ls + 1) * 8);
-    uint8_t *s_start = smem_raw + (size_t)(n_ls + 1) * 8 + PROP_SMEM_FLIPS * 4;
-    const size_t meta = ((size_t)(n_ls + 1) * 8 + PROP_SMEM_FLIPS * 4 + (size_t)((n_ls + 15) & ~15) + 15) & ~(size_t)15;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_raw + meta) + (uint32_t)warp * (RING_STAGES * 512) + (uint32_t)lane * 16;
-    for (uint32_t oi = blockIdx.x; oi < n_off; oi += gridDim.x) {
-        const uint64_t i = oi;
-        const uint64_t slot0 = i * (uint64_t)n_ls;
-        __syncthreads();
-        for (int t = threadIdx.x; t <= n_ls; t += PROP_THREADS) s_off[t] = xo_off[slot0 + t];
-        for (int t = threadIdx.x; t < n_ls; t += PROP_THREADS) s_start[t] = start_hap[slot0 + t];
-        if (threadIdx.x == 0) s_next = 0;
-        __syncthreads();
-        const uint64_t e_base = s_off[0];
-        const uint32_t n_fl = (uint32_t)(s_off[n_ls] - e_base);
-        const bool staged = n_fl <= PROP_SMEM_FLIPS;
-        if (staged) for (uint32_t t = threadIdx.x; t < n_fl; t += PROP_THREADS) s_fl[t] = flips[e_base + t];
-        const uint32_t pf = par_rowmap ? par_rowmap[father[i]] : father[i], pm = par_rowmap ? par_rowmap[mother[i]] : mother[i];
-        __syncthreads();
-        RingPending pend{nullptr, 0, 0, 0};
-        uint32_t half = 0;
-        for (;;) {
-            uint32_t item = 0;
-            if (lane == 0) item = atomicAdd(&s_next, 1u);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= 2 * tt.n_items) break;
-            const int gam = item >= tt.n_items;
-            const uint32_t it = gam ? item - tt.n_items : item;
-            const uint32_t c = tt.chr[it], q0 = tt.chunk0[it], q1 = q0 + tt.nchunk[it];
-            const int ls = (int)c * 2 + gam;
-            const uint64_t e0 = s_off[ls];
-            const uint32_t k = (uint32_t)(s_off[ls + 1] - e0);
-            const uint32_t *fl = staged ? s_fl + (e0 - e_base) : flips + e0;
-            const uint32_t woff = g.chr_word_off[c];
-            const uint32_t prow = gam ? pm : pf;
-            const uint4 *h0 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow) * g.W + woff);
-            const uint4 *h1 = reinterpret_cast<const uint4 *>(par_rows + (uint64_t)(2 * prow + 1) * g.W + woff);
-            uint4 *dst = reinterpret_cast<uint4 *>(off_rows + (uint64_t)(2 * i + gam) * g.W + woff);
-            uint32_t j = 0;
-            const uint32_t x0 = q0 << 7;
-            while (j < k && fl[j] <= x0) j++;
-            uint32_t cur = (s_start[ls] ^ j) & 1u;
-            uint32_t q = q0;
-            while (q < q1) {
-                const uint32_t f = j < k ? fl[j] : 0xFFFFFFFFu;
-                const uint32_t qb = min(f >> 7, q1);            // the run is [q, qb); a crossover chunk follows when qb < q1
-                const bool has_x = j < k && qb < q1;
-                uint4 a = make_uint4(0, 0, 0, 0), b = a;
-                if (has_x && lane == 0) { a = ld_stream(h0 + qb); b = ld_stream(h1 + qb); }
-                const uint4 *src = cur ? h1 : h0;
-                for (uint32_t s = q; s < qb; s += RING_HALF * 32) {   // sub-runs: issue this one, then retire the one before it
-                    const uint32_t e = min(s + RING_HALF * 32, qb);
-                    ring_issue(ring, half, src, s, e, lane);
-                    if (pend.dst) { cp_async_wait<1>(); ring_drain(ring, pend, lane); }
-                    pend = RingPending{dst, s, e, half};
-                    half ^= 1u;
-                }
-                if (!has_x) break;
-                if (lane == 0) {
-                    const uint32_t fill = cur ? 0xFFFFFFFFu : 0u;
-                    uint32_t m0 = fill, m1 = fill, m2 = fill, m3 = fill;
-                    const uint32_t base = qb << 7;
-                    for (uint32_t jj = j; jj < k && fl[jj] < base + 128u; jj++) {
-                        const uint32_t r = fl[jj] - base;
-                        m0 ^= r < 32u ? 0xFFFFFFFFu << r : 0u;
-                        m1 ^= r <= 32u ? 0xFFFFFFFFu : (r < 64u ? 0xFFFFFFFFu << (r - 32u) : 0u);
-                        m2 ^= r <= 64u ? 0xFFFFFFFFu : (r < 96u ? 0xFFFFFFFFu << (r - 64u) : 0u);
-                        m3 ^= r <= 96u ? 0xFFFFFFFFu : 0xFFFFFFFFu << (r - 96u);
-                    }
-                    uint4 o;
-                    o.x = (a.x & ~m0) | (b.x & m0); o.y = (a.y & ~m1) | (b.y & m1);
-                    o.z = (a.z & ~m2) | (b.z & m2); o.w = (a.w & ~m3) | (b.w & m3);
-                    st_stream(dst + qb, o);
-                }
-                while (j < k && fl[j] < ((qb + 1) << 7)) { j++; cur ^= 1u; }
-                q = qb + 1;
-            }
-        }
-        if (pend.dst) { cp_async_wait<0>(); ring_drain(ring, pend, lane); }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Founder panel (Hap_SNP bytes, hap-major) -> bit-packed generation-0 rows, masked to the covered range
 // [rmap.bp[0], rmap.bp[last]) (a locus outside it lies in no `part`, :3029-3034, and reads 0 at :1186-1230).
 // ------------------------------------------------------------------------------------------------
