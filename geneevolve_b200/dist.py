@@ -83,17 +83,13 @@ def host_allreduce_hook(group=None):
     return hook
 
 
-def bench_sharded(args, METRIC, UNIT):
-    """bench.py for WORLD_SIZE > 1: the same fixed workload, its loci spread over the ranks (strong scaling).  Bit-packed rows are
-    split by locus range (assign_locus_ranges: exact balance, a chromosome may span ranks), founder segments by whole chromosomes."""
+def measure_sharded(name, args, steps, warmup, rank, world, local, e2e=True, n=None, loci=None):
+    """One workload over all ranks of the process group; every rank returns the same dict (timings are max over ranks)."""
     import torch
     import torch.distributed as dist
     from . import capi, workloads
     import bench
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = workloads.make_workload(args.workload, n_override=args.n, loci_override=args.loci)
+    cfg = workloads.make_workload(name, n_override=n, loci_override=loci)
     segs = bool(cfg.get("segments"))
     if segs:
         if len(cfg["chrs"]) < world:
@@ -109,7 +105,7 @@ def bench_sharded(args, METRIC, UNIT):
     seg_cap = 0
     if segs:  # parts per haplotype after g generations ~ chromosomes + g * Morgans of this rank's chromosomes (both arms run back to back)
         morgans = sum(float(cfg["maps"][c][2].sum()) for c, _, _ in pieces)
-        seg_cap = int(2 * cap * (len(pieces) + (args.warmup + 2 * args.steps + 1) * morgans) * 1.05)
+        seg_cap = int(2 * cap * (len(pieces) + (warmup + 2 * steps + 1) * morgans) * 1.05)
     kid = capi.GE_KERNEL_RECOMBINE_SEGMENTS if segs else capi.GE_KERNEL_PROPAGATE_BITS
     eng = capi.Engine(n_pop=len(pops), n_chr=len(pieces), n_phen=n_phen, device=local, representation=capi.GE_REP_SEGMENTS if segs else capi.GE_REP_BITS,
                       rng_mode=capi.GE_RNG_PHILOX, seed=12345, capacity=cap, seg_capacity=seg_cap, rank=rank, world_size=world)
@@ -119,10 +115,10 @@ def bench_sharded(args, METRIC, UNIT):
         workloads.configure_engine(eng, cfg, pieces=pieces)
     eng.set_allreduce(cuda_allreduce_hook(local))
     eng.init_generation0()
-    gp = [capi.gen_params(n, cfg["mat_cor"], "p", "logit", 0.0, 1.0) for n in pops]
+    gp = [capi.gen_params(q, cfg["mat_cor"], "p", "logit", 0.0, 1.0) for q in pops]
     mig = cfg.get("migration")
     gen = 0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         gen += 1
         eng.step_generation(gen, gp, mig)
     pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
@@ -132,19 +128,19 @@ def bench_sharded(args, METRIC, UNIT):
     for k in ("mv", "sv", "svf"):
         out[k] = pin((cap,), torch.float64)
 
-    def timed(e2e):
+    def timed(with_download):
         nonlocal gen
         eng.synchronize()
         torch.cuda.synchronize()
         dist.barrier()
         work = 0
         eng.timer_start()
-        for _ in range(args.steps):
+        for _ in range(steps):
             gen += 1
             eng.step_generation(gen, gp, mig)
             for q in range(len(pops)):
                 work += eng.population_size(q) * M
-                if e2e and rank == 0:
+                if with_download and rank == 0:
                     eng.individuals(q, out=out)  # every rank holds identical columns; rank 0 feeds the host writers
         ms = eng.timer_stop()
         eng.synchronize()
@@ -159,45 +155,84 @@ def bench_sharded(args, METRIC, UNIT):
     launches = eng.launch_count()
     k_ms, k_n, k_bytes = eng.kernel_time(kid)
     eng.set_profiling(0)
-    work2, ms_e2e = timed(True)
-    checksum = float(out["P"].reshape(-1)[:16].sum()) if rank == 0 else 0.0
-    # every rank simulated the same populations: the integer fingerprint (pedigree, sex, couples) must agree on all of them,
-    # and with the unsharded run of the same number of generations (bench.py --gpus 1 prints the same field)
-    my_hash = bench.state_hash(eng, len(pops))
-    hs = torch.tensor([my_hash], dtype=torch.int64, device="cuda")
-    all_h = [torch.zeros_like(hs) for _ in range(world)]
-    dist.all_gather(all_h, hs)
-    hashes = [int(h.item()) for h in all_h]
+    r = dict(cfg=cfg, pieces=pieces, M=M, pops=pops, n_phen=n_phen, segs=segs, work=work, ms_dev=ms_dev, launches=launches, k_ms=k_ms, k_n=k_n, k_bytes=k_bytes,
+             clocks=clocks.summary(), steps=steps, warmup=warmup)
+    if e2e:
+        r["work2"], r["ms_e2e"] = timed(True)
+        r["checksum"] = float(out["P"].reshape(-1)[:16].sum()) if rank == 0 else 0.0
+        # every rank simulated the same populations: the integer fingerprint (pedigree, sex, couples) must agree on all of them,
+        # and with the unsharded run of the same number of generations (bench.py --gpus 1 prints the same field)
+        hs = torch.tensor([bench.state_hash(eng, len(pops))], dtype=torch.int64, device="cuda")
+        all_h = [torch.zeros_like(hs) for _ in range(world)]
+        dist.all_gather(all_h, hs)
+        r["hashes"] = [int(h.item()) for h in all_h]
     kb = torch.tensor([k_bytes / max(k_ms, 1e-9) / 1e6, k_ms / max(k_n, 1)], dtype=torch.float64, device="cuda")  # GB/s and ms per launch of this rank's kernel
     kmax = kb.clone()
     dist.all_reduce(kb, op=dist.ReduceOp.SUM)
     dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+    r["achieved"] = float(kb[0].item()) / world  # mean per-GPU achieved GB/s
+    r["k_ms_slowest"] = float(kmax[1].item())
+    r["device_memory_gb"] = eng.device_memory_bytes() / 1e9
+    eng.close()
+    return r
+
+
+def sharded_roofline(r):
+    import bench
+    peak, peak_src = bench.hbm_peak()
+    return {"bound": "hbm", "kernel": "seg_plan_kernel + seg_gather_kernel" if r["segs"] else "propagate_bits_kernel", "achieved": r["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": r["achieved"] / peak, "traffic": None, "traffic_source": "not captured for sharded runs (ncu is single-GPU; profiles/traffic.json holds the 1-GPU capture)",
+            "peak_source": peak_src, "kernel_ms_per_launch": r["k_ms"] / max(r["k_n"], 1), "kernel_ms_per_launch_slowest_rank": r["k_ms_slowest"],
+            "kernel_share_of_step": r["k_ms"] / r["ms_dev"], "algorithmic_bytes_per_launch_rank0": r["k_bytes"] // max(r["k_n"], 1), "note": "per-GPU mean"}
+
+
+def bench_sharded(args, METRIC, UNIT):
+    """bench.py for WORLD_SIZE > 1: the same fixed workload, its loci spread over the ranks (strong scaling).  Bit-packed rows are
+    split by locus range (assign_locus_ranges: exact balance, a chromosome may span ranks), founder segments by whole chromosomes.
+    From 4 ranks on, BASELINE config 4 (three populations, 150 GB of rows per generation: it needs them) is appended as a short record."""
+    import torch
+    import torch.distributed as dist
+    from . import capi
+    import bench
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    r = measure_sharded(args.workload, args, args.steps, args.warmup, rank, world, local, n=args.n, loci=args.loci)
+    cfg, M, pops, n_phen, segs = r["cfg"], r["M"], r["pops"], r["n_phen"], r["segs"]
+    others = []
+    if world >= 4 and args.workload == "config3_100k_x_1M" and not args.n and not args.loci and not args.no_other_workloads:
+        try:
+            o = measure_sharded("config4_3pop_300k_x_2M", args, 5, 3, rank, world, local, e2e=False)
+            others.append({"workload": "config4_3pop_300k_x_2M", "individuals": sum(o["pops"]), "populations": o["pops"], "phenotypes": o["n_phen"], "loci": o["M"],
+                           "steps": 5, "warmup": 3, "ms_per_step": o["ms_dev"] / 5, "value": o["work"] / (o["ms_dev"] * 1e-3), "unit": UNIT,
+                           "gpu_launches_per_step": o["launches"] / 5, "roofline": sharded_roofline(o), "device_memory_gb_rank0": o["device_memory_gb"],
+                           "note": "three populations 150k / 100k / 50k, ring migration 2 %, two phenotypes, 2M loci: 150 GB of bit-packed rows per generation over the ranks"})
+        except Exception as e:  # never take the headline down
+            others.append({"workload": "config4_3pop_300k_x_2M", "failed": repr(e)})
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu_base = bench.cpu_baseline_single(args, M)
     if rank == 0:
-        peak, peak_src = bench.hbm_peak()
-        achieved = float(kb[0].item()) / world  # mean per-GPU achieved GB/s
-        print(json.dumps({
-            "metric": METRIC, "value": work / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-packed + f64",
+        line = {
+            "metric": METRIC, "value": r["work"] / (r["ms_dev"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_dev"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-packed + f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "individuals": sum(pops), "populations": pops, "phenotypes": n_phen, "loci": M, "chromosomes": len(cfg["chrs"]),
                        "parallelism": ("chromosome-sharded x%d (founder segments)" if segs else "locus-range sharded x%d (every rank: all individuals, 1/N of the 16-byte chunks of the rows)") % world,
-                       "device_memory_gb_rank0": eng.device_memory_bytes() / 1e9,
+                       "device_memory_gb_rank0": r["device_memory_gb"],
                        "representation": "founder segments (loci nominal; steps are generations %d..%d)" % (args.warmup + 1, args.warmup + args.steps) if segs else "bit-packed haplotypes",
-                       "pieces_rank0": pieces, "collective": "all-reduce of 3 * n_phen * capacity doubles per population and generation (NCCL)",
+                       "pieces_rank0": r["pieces"], "collective": "all-reduce of 3 * n_phen * capacity doubles per population and generation (NCCL)",
                        "l2": ("inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (sum(pops) * M / 4 / 1e9 / world)) if not segs else
-                             "inputs larger than L2 (founder-segment lists, %.1f GB moved per step per GPU)" % (k_bytes / max(k_n, 1) * 2 / 1e9)},
-            "e2e": {"value": work2 / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,
-                    "d2h_bytes_per_step": sum(capi.Engine.individual_bytes(n, n_phen) for n in pops), "ms_per_step": ms_e2e / args.steps,
-                    "checksum": checksum, "state_hash": hashes[0], "state_hash_equal_on_all_ranks": len(set(hashes)) == 1,
+                             "inputs larger than L2 (founder-segment lists, %.1f GB moved per step per GPU)" % (r["k_bytes"] / max(r["k_n"], 1) * 2 / 1e9)},
+            "e2e": {"value": r["work2"] / (r["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,
+                    "d2h_bytes_per_step": sum(capi.Engine.individual_bytes(q, n_phen) for q in pops), "ms_per_step": r["ms_e2e"] / args.steps,
+                    "checksum": r["checksum"], "state_hash": r["hashes"][0], "state_hash_equal_on_all_ranks": len(set(r["hashes"])) == 1,
                     "generations_simulated": args.warmup + 2 * args.steps},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "seg_plan_kernel + seg_gather_kernel" if segs else "propagate_bits_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "traffic_source": "not captured for sharded runs (ncu is single-GPU; profiles/traffic.json holds the 1-GPU capture)", "peak_source": peak_src,
-                         "kernel_ms_per_launch": k_ms / max(k_n, 1), "kernel_ms_per_launch_slowest_rank": float(kmax[1].item()),
-                         "kernel_share_of_step": k_ms / ms_dev, "note": "per-GPU mean"},
-            "clocks": clocks.summary(), "cpu_baseline": cpu_base}))
+            "gpu_launches": r["launches"],
+            "roofline": sharded_roofline(r),
+            "clocks": r["clocks"], "cpu_baseline": cpu_base}
+        if others:
+            line["other_workloads"] = others
+        print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()
