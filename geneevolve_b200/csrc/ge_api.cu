@@ -138,6 +138,14 @@ static int build_genome(ge_ctx *ctx) {
     std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.nq > b.nq; });
     std::vector<uint32_t> tc, t0, tn;
     for (auto &it : items) { tc.push_back(it.c); t0.push_back(it.q0); tn.push_back(it.nq); }
+    // warps per offspring CTA: about one per 16 KB of the offspring's two rows.  A shard of a multi-GPU run has short rows: fewer, longer-lived
+    // warps per CTA and more offspring in flight per SM instead of eight warps that finish after one item.  Measured on one rank's share of
+    // config 3 (scripts/emulate_rank.py; 8 / 4 / 2 / 1 warps): 31 KB per offspring (8 ranks) 1.250 / 1.106 / 1.066 / 1.228 ms per generation,
+    // 62 KB (4 ranks) 2.129 / 1.985 / 2.034 / 2.330, 125 KB (2 ranks) 3.877 / 3.805 / 3.938, 250 KB (1 GPU) 7.32 / 7.50 / 7.94.
+    {
+        const uint64_t bytes_per_offspring = chunks_per_gamete * 16 * 2;
+        ctx->prop_threads = 32 * (unsigned)std::min<uint64_t>(8, std::max<uint64_t>(1, (bytes_per_offspring + 8192) / 16384));
+    }
     ctx->n_tiles = (uint32_t)items.size();
     ctx->n_loci_total = pos.size();
     GE_TRY(ctx->upload(ctx->d_tile_chr, tc));
@@ -535,7 +543,7 @@ int ge_compute_AD(ge_ctx *ctx, int pop, int gen) {
 }
 
 // e_host / f0_host: replayed draws (host arrays of the population's current size), else Philox
-static int enqueue_GEF(ge_ctx *ctx, int pop, int f, bool gen0, const double *e_host, const double *f0_host) {  // :3075-3206
+static int enqueue_GEF(ge_ctx *ctx, int pop, int f, bool gen0, const double *e_host, const double *f0_host, bool with_mv_sv = false) {  // :3075-3206
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
     const uint64_t cap = ctx->cfg.capacity;
@@ -569,6 +577,11 @@ static int enqueue_GEF(ge_ctx *ctx, int pop, int f, bool gen0, const double *e_h
     a.s_a = 1; if (sc.va > 0) a.s_a = std::sqrt(P.var_a0[f] / sc.va);
     a.s_d = 0; if (sc.vd > 0) a.s_d = std::sqrt(P.var_d0[f] / sc.vd); else if (sc.vd == -1) a.s_d = 1;
     a.ve = sc.ve; a.vf = sc.vf; a.beta = sc.beta; a.vt_type = ctx->cfg.vt_type;
+    a.omega = a.lambda = a.sv0 = nullptr; a.mv = a.sv = a.svf = nullptr;
+    if (with_mv_sv) {
+        a.omega = P.d_omega.as<double>(); a.lambda = P.d_lambda.as<double>(); a.sv0 = P.d_sv0.as<double>();
+        a.mv = S.mv.as<double>(); a.sv = S.sv.as<double>(); a.svf = S.svf.as<double>();
+    }
     uint64_t o = (uint64_t)f * cap;
     phenotype_kernel<<<ctx->grid_for(cap, 256), 256, 0, ctx->stream>>>(
         a, P.d_ss, S.d_n, &P.d_ss->prev_n, e, var_e, S.A.as<double>() + o, S.D.as<double>() + o, S.G.as<double>() + o, S.C.as<double>() + o, S.E.as<double>() + o,
@@ -1051,9 +1064,7 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
         // offspring offsets = exclusive scan of the family sizes of the couples that may marry (:2402-2406); the couple threads then
         // write parents, sex, pedigree and the sibling-common effect of their children
         const uint64_t cb = P.couples_cap;
-        family_size_kernel<<<ctx->grid_for(cb, 256), 256, 0, st>>>(ss, P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>(), P.cnt32.as<uint32_t>());
-        GE_TRY(ctx->check_launch("family_size"));
-        GE_TRY(ctx->scan(st, P.cnt32.as<uint32_t>(), devn(&ss->n_couples), cb, P.mate.fam_off.as<uint64_t>(), OffspringTotal{ss}));
+        GE_TRY(ctx->scan_in(st, FamilyIn{ss, P.c_inbreed.as<uint8_t>(), P.c_noff.as<int32_t>()}, devn(&ss->n_couples), cb, P.mate.fam_off.as<uint64_t>(), OffspringTotal{ss}));
         CommonArgs ca;
         ca.n_phen = nf; ca.stride = cap;
         for (int f = 0; f < 8; f++) ca.sd[f] = (f < nf && P.scheme[f].vc > 0) ? std::sqrt(P.scheme[f].vc) : 0.0;
@@ -1098,13 +1109,14 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
         const uint64_t *xo_off = D.xo_off.as<uint64_t>();
         const uint8_t *start = D.start_hap.as<uint8_t>();
         const size_t smem = prop_smem_bytes(C);
+        const unsigned prop_threads = ctx->prop_threads;
         DrawSet *Dp = &D;
         const double bulk_bytes = (double)cap * ctx->W * 16.0;
         GE_TRY(ctx->to_bulk(P.ev_ready, [=]() -> int {
             cudaStream_t bulk = ctx->serial ? ctx->stream : ctx->bulk;
             ge_ctx::EvPair evp{nullptr, nullptr, GE_KERNEL_PROPAGATE_BITS, 0, 0, 0};
             if (ctx->profiling) { evp.a = ctx->get_event(); evp.b = ctx->get_event(); CUDA_TRY(cudaEventRecord(evp.a, bulk)); }
-            propagate_bits_kernel<<<grid, PROP_THREADS, smem, bulk>>>(gnm, tiles, dc, par_rows, rowmap, off_rows, fa, mo, xo_off, fl, start);
+            propagate_bits_kernel<<<grid, prop_threads, smem, bulk>>>(gnm, tiles, dc, par_rows, rowmap, off_rows, fa, mo, xo_off, fl, start);
             GE_TRY(ctx->check_launch("propagate_bits"));
             if (ctx->profiling) {
                 CUDA_TRY(cudaEventRecord(evp.b, bulk));
@@ -1202,6 +1214,9 @@ int ge_do_migration(ge_ctx *ctx, int gen, const double *row) {  // ras_do_migrat
 // everything of one generation except the final read-back (sim_next_generation :1890-2082, the reference's order)
 static int enqueue_generation(ge_ctx *ctx, int gen, const ge_gen_params *gp, const double *mig, const ge_draws *dr, int &reproduced, bool &migrated) {
     const int nf = ctx->cfg.n_phen, np = ctx->cfg.n_pop;
+    // one phenotype, one population, no --gamma shift between the two: mating and selection values come out of the phenotype pass
+    bool fused_mv_sv = nf == 1 && np == 1;
+    for (double g : ctx->gamma) if (g != 0) fused_mv_sv = false;
     for (int p = 0; p < np; p++) {
         GE_TRY(enqueue_step_begin(ctx, p, gen, gp[p]));
         if (!dr) { ge_ctx::PhaseTimer timer(ctx, GE_PHASE_MATE); GE_TRY(enqueue_mate(ctx, p, gp[p])); }
@@ -1211,11 +1226,11 @@ static int enqueue_generation(ge_ctx *ctx, int gen, const ge_gen_params *gp, con
         {
             ge_ctx::PhaseTimer timer(ctx, GE_PHASE_PHENOTYPE);
             const uint64_t n = dr ? dr[p].n_offspring : 0;
-            for (int f = 0; f < nf; f++) GE_TRY(enqueue_GEF(ctx, p, f, false, (dr && dr[p].e_raw) ? dr[p].e_raw + (uint64_t)f * n : nullptr, nullptr));
+            for (int f = 0; f < nf; f++) GE_TRY(enqueue_GEF(ctx, p, f, false, (dr && dr[p].e_raw) ? dr[p].e_raw + (uint64_t)f * n : nullptr, nullptr, fused_mv_sv));
         }
     }
     for (int f = 0; f < nf; f++) GE_TRY(ge_environmental_effects_specific_to_each_population(ctx, f));
-    for (int p = 0; p < np; p++) GE_TRY(enqueue_mv_sv(ctx, p));
+    if (!fused_mv_sv) for (int p = 0; p < np; p++) GE_TRY(enqueue_mv_sv(ctx, p));
     if (np > 1 && mig) {
         GE_TRY(ctx->pull_state("generation"));   // migration builds its gather lists on the host
         GE_TRY(seg_finish_all(ctx));

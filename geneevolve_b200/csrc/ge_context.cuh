@@ -213,6 +213,7 @@ struct ge_ctx {
     StepState *h_ss_all = nullptr;              // pinned read-back buffer of the same
     uint64_t graph_epoch = 0;                   // bumped whenever a device buffer is (re)allocated: captured graphs hold raw pointers
     int n_sm = 148;
+    unsigned prop_threads = 256;   // threads of a propagate_bits_kernel CTA (one offspring): by row length, build_genome
     // stats
     bool profiling = false;        // CUDA events around the dominant kernel (propagate_bits / the segment passes) on its own stream
     bool phase_timing = false;     // ... and around the phases of the control chain (ge_set_profiling level 2; disables graph replay)
@@ -367,25 +368,26 @@ struct ge_ctx {
     unsigned grid_for(uint64_t bound, unsigned block) const { return (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (bound + block - 1) / block), 1u << 20); }
     // device exclusive scan: out[0..n] (n + 1 entries, out[n] = grand total); n lives on the device, n_bound (host) sizes the
     // grid; on_total runs in the thread that stores out[n].  One launch for small arrays, three otherwise.
-    template <class TIn, class OnTotal>
-    int scan_with(cudaStream_t st, Buf &blocks, const TIn *in, DevN n, uint64_t n_bound, uint64_t *out, OnTotal on_total) {
+    template <class In, class OnTotal>
+    int scan_in(cudaStream_t st, In in, DevN n, uint64_t n_bound, uint64_t *out, OnTotal on_total) {
+        Buf &blocks = st == bulk ? bulk_scan_blocks : scan_blocks;
         n = limited(n, n_bound);
         if (n_bound <= 2 * SCAN1_CHUNK) {
-            scan_one_cta_kernel<TIn, OnTotal><<<1, SCAN1_THREADS, 0, st>>>(in, n, out, on_total);
+            scan_one_cta_kernel<In, OnTotal><<<1, SCAN1_THREADS, 0, st>>>(in, n, out, on_total);
             return check_launch("scan_one_cta");
         }
         uint32_t nb = (uint32_t)(n_bound / SCAN_TILE) + 1;
         GE_TRY(ensure(blocks, (size_t)nb * 8));
-        scan_block_sums_kernel<TIn><<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>());
+        scan_block_sums_kernel<In><<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>());
         GE_TRY(check_launch("scan_block_sums"));
         scan_single_block_kernel<<<1, SCAN_THREADS, 0, st>>>(blocks.as<uint64_t>(), n);
         GE_TRY(check_launch("scan_single_block"));
-        scan_final_kernel<TIn, OnTotal><<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>(), out, on_total);
+        scan_final_kernel<In, OnTotal><<<nb, SCAN_THREADS, 0, st>>>(in, n, blocks.as<uint64_t>(), out, on_total);
         return check_launch("scan_final");
     }
-    template <class TIn, class OnTotal>
-    int scan(cudaStream_t st, const TIn *in, DevN n, uint64_t n_bound, uint64_t *out, OnTotal on_total) {
-        return scan_with(st, st == bulk ? bulk_scan_blocks : scan_blocks, in, n, n_bound, out, on_total);
+    template <class T, class OnTotal>
+    int scan(cudaStream_t st, const T *in, DevN n, uint64_t n_bound, uint64_t *out, OnTotal on_total) {
+        return scan_in(st, PtrIn<T>{in}, n, n_bound, out, on_total);
     }
     // host-known n (setup, migration, downloads); the total is also returned to the host when asked (one sync)
     int exclusive_scan(const uint32_t *in, uint64_t n, uint64_t *out, uint64_t *host_total) {

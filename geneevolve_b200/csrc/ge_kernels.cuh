@@ -254,14 +254,14 @@ propagate_bits_kernel(Genome g, TileTable tt, const DrawCounts *__restrict__ dc,
         __syncthreads();
         // stage this offspring's crossover metadata once, coalesced: the work items below never wait on a
         // dependent global load before their first copy
-        for (int t = threadIdx.x; t <= n_ls; t += PROP_THREADS) s_off[t] = xo_off[slot0 + t];
-        for (int t = threadIdx.x; t < n_ls; t += PROP_THREADS) s_start[t] = start_hap[slot0 + t];
+        for (int t = threadIdx.x; t <= n_ls; t += blockDim.x) s_off[t] = xo_off[slot0 + t];
+        for (int t = threadIdx.x; t < n_ls; t += blockDim.x) s_start[t] = start_hap[slot0 + t];
         if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
         const uint64_t e_base = s_off[0];
         const uint32_t n_fl = (uint32_t)(s_off[n_ls] - e_base);
         const bool staged = n_fl <= PROP_SMEM_FLIPS;
-        if (staged) for (uint32_t t = threadIdx.x; t < n_fl; t += PROP_THREADS) s_fl[t] = flips[e_base + t];
+        if (staged) for (uint32_t t = threadIdx.x; t < n_fl; t += blockDim.x) s_fl[t] = flips[e_base + t];
         // after a migration the parents' rows are not in logical order: par_rowmap gives the physical row pair
         const uint32_t pf = par_rowmap ? par_rowmap[father[i]] : father[i], pm = par_rowmap ? par_rowmap[mother[i]] : mother[i];
         __syncthreads();
@@ -711,7 +711,22 @@ __global__ void normal_scaled_kernel(Stream st, uint32_t purpose, int pop, int g
 struct PhenoArgs {
     double s_a, s_d, ve, vf, beta;
     int vt_type;
+    // one phenotype, one population: mating and selection values (mv_sv_selection_kernel) in the same pass; mv == nullptr otherwise
+    const double *omega, *lambda, *sv0;
+    double *mv, *sv, *svf;
 };
+// ras_selection_func :3386-3428
+__device__ __forceinline__ double selection_func(int gen, int func, double par1, double par2, double z) {
+    double r = 1.0;
+    if (gen != 0) {
+        if (func == 0) { double y = exp(0.0 + 1.0 * z); r = y / (1 + y); }
+        else if (func == 1) { double y = exp(par1 + par2 * z); r = y / (1 + y); }
+        else if (func == 2) r = .5 * (1 + erf((z - par1) / (sqrt(2.0) * par2)));
+        else if (func == 3) { const double pi = 3.1415926; double u = (z - par1) / par2; r = 1 / (sqrt(2.0 * pi) * par2) * exp(-0.5 * (u * u)); }
+        else if (func == 4) r = z <= par2 ? par1 : 1.0;
+    }
+    return r;
+}
 __global__ void phenotype_kernel(PhenoArgs a, const StepState *__restrict__ ss, const uint64_t *__restrict__ n_ind, const uint64_t *__restrict__ prev_n_ptr,
                                  const double *__restrict__ e_raw, const double *__restrict__ var_e,
                                  double *__restrict__ A, double *__restrict__ D, double *__restrict__ G, const double *__restrict__ Cc,
@@ -739,7 +754,16 @@ __global__ void phenotype_kernel(PhenoArgs a, const StepState *__restrict__ ss, 
             }
         }
         E[i] = e; A[i] = av; D[i] = dv; G[i] = av + dv; F[i] = fv;
-        P[i] = av + dv + Cc[i] + e + fv;
+        const double p = av + dv + Cc[i] + e + fv;
+        P[i] = p;
+        if (a.mv) {   // :3300-3342 for the one phenotype
+            a.mv[i] = a.omega[0] * p;
+            const double s = a.lambda[0] * p, mean0 = a.sv0[0], var0 = a.sv0[1];
+            double z = s - mean0;
+            if (var0 > 0) z = (s - mean0) / sqrt(var0);
+            a.sv[i] = z;
+            a.svf[i] = selection_func(gen, ss->sel_func, ss->sel_par1, ss->sel_par2, z);
+        }
     }
 }
 
@@ -760,15 +784,7 @@ __global__ void mv_sv_selection_kernel(const StepState *__restrict__ ss, const u
         double z = s - mean0;
         if (var0 > 0) z = (s - mean0) / sqrt(var0);
         sv[i] = z;
-        double r = 1.0;
-        if (gen != 0) {  // ras_selection_func :3386-3428
-            if (func == 0) { double y = exp(0.0 + 1.0 * z); r = y / (1 + y); }
-            else if (func == 1) { double y = exp(par1 + par2 * z); r = y / (1 + y); }
-            else if (func == 2) r = .5 * (1 + erf((z - par1) / (sqrt(2.0) * par2)));
-            else if (func == 3) { const double pi = 3.1415926; double u = (z - par1) / par2; r = 1 / (sqrt(2.0 * pi) * par2) * exp(-0.5 * (u * u)); }
-            else if (func == 4) r = z <= par2 ? par1 : 1.0;
-        }
-        svf[i] = r;
+        svf[i] = selection_func(gen, func, par1, par2, z);
     }
 }
 __global__ void add_scalar_kernel(double *__restrict__ x, uint64_t n, double v) {
@@ -829,14 +845,17 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t &t
     total = wsum[THREADS / 32 - 1];
     return base + x - v;
 }
+// What is scanned: an array (PtrIn), or values computed on the fly by a functor `uint64_t operator()(uint64_t i) const` — the thinning
+// counts and the family sizes are scanned as they are produced, without a kernel and an array in between.
+template <class T> struct PtrIn { const T *p; __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return p[i]; } };
 // three launches, any size: block sums, scan of the block sums (one CTA), final pass.  Blocks beyond the device-side n idle.
-template <class TIn>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const TIn *__restrict__ in, DevN dn, uint64_t *__restrict__ block_sums) {
+template <class In>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(In in, DevN dn, uint64_t *__restrict__ block_sums) {
     const uint64_t n = dn.get();
     uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
     if (base > n) return;
     uint64_t s = 0;
-    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; if (i < n) s += in[i]; }
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; if (i < n) s += in(i); }
     uint64_t total; block_exclusive_scan<SCAN_THREADS>(s, total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
@@ -857,13 +876,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_single_block_kernel(uint64_
         __syncthreads();
     }
 }
-template <class TIn, class OnTotal>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const TIn *__restrict__ in, DevN dn, const uint64_t *__restrict__ block_sums, uint64_t *__restrict__ out, OnTotal on_total) {
+template <class In, class OnTotal>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(In in, DevN dn, const uint64_t *__restrict__ block_sums, uint64_t *__restrict__ out, OnTotal on_total) {
     const uint64_t n = dn.get();
     uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
     if (base > n) return;
     uint64_t v[SCAN_ITEMS], s = 0;
-    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; v[k] = i < n ? in[i] : 0; s += v[k]; }
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; v[k] = i < n ? in(i) : 0; s += v[k]; }
     uint64_t total, ex = block_exclusive_scan<SCAN_THREADS>(s, total);
     uint64_t run = block_sums[blockIdx.x] + ex;
     for (int k = 0; k < SCAN_ITEMS; k++) {
@@ -876,15 +895,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const TIn *__r
 // one launch, small arrays (the launch-bound configurations): ONE CTA walks the array in chunks with a running carry
 constexpr int SCAN1_THREADS = 1024;
 constexpr int SCAN1_CHUNK = SCAN1_THREADS * SCAN_ITEMS;
-template <class TIn, class OnTotal>
-__global__ void __launch_bounds__(SCAN1_THREADS) scan_one_cta_kernel(const TIn *__restrict__ in, DevN dn, uint64_t *__restrict__ out, OnTotal on_total) {
+template <class In, class OnTotal>
+__global__ void __launch_bounds__(SCAN1_THREADS) scan_one_cta_kernel(In in, DevN dn, uint64_t *__restrict__ out, OnTotal on_total) {
     const uint64_t n = dn.get();
     __shared__ uint64_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (uint64_t base = 0; base <= n; base += SCAN1_CHUNK) {
         uint64_t v[SCAN_ITEMS], s = 0;
-        for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; v[k] = i < n ? in[i] : 0; s += v[k]; }
+        for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)threadIdx.x * SCAN_ITEMS + k; v[k] = i < n ? in(i) : 0; s += v[k]; }
         uint64_t total, ex = block_exclusive_scan<SCAN1_THREADS>(s, total);
         const uint64_t c = carry;
         uint64_t run = c + ex;
@@ -1137,11 +1156,10 @@ __global__ void mutation_lists_kernel(MutArgs a, Genome g, CvSet cs, uint32_t *_
 // positions, the sex draw (:2472), the pedigree (:2471-2479) and the sibling-common effect (one draw per couple and
 // phenotype, :2417-2429, :2481-2484).
 // ------------------------------------------------------------------------------------------------
-__global__ void family_size_kernel(const StepState *__restrict__ ss, const uint8_t *__restrict__ inbreed, const int32_t *__restrict__ noff, uint32_t *__restrict__ cnt) {
-    const uint64_t n_couples = (ss->err & SE_FATAL) ? 0 : ss->n_couples;
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_couples; k += (uint64_t)gridDim.x * blockDim.x)
-        cnt[k] = inbreed[k] ? 0u : (uint32_t)max(noff[k], 0);
-}
+struct FamilyIn {   // family size of couple k as the offspring scan sees it: couples that may not marry have none (:2402-2406)
+    const StepState *ss; const uint8_t *inbreed; const int32_t *noff;
+    __device__ __forceinline__ uint64_t operator()(uint64_t k) const { return ((ss->err & SE_FATAL) || inbreed[k]) ? 0u : (uint64_t)max(noff[k], 0); }
+};
 struct OffspringTotal {   // grand total of the family-size scan
     StepState *ss;
     __device__ __forceinline__ void operator()(uint64_t t) const {

@@ -27,25 +27,21 @@ __device__ __forceinline__ uint64_t sortable(double x) {  // monotone map double
 
 // thinning (:2105-2117 / :2186-2216): number of list entries individual i contributes — males in the low, females in
 // the high 32 bits, so ONE scan gives the offsets into both lists
-// replayed draws (ge_mate_replay): thin_u / mm_u are the reference's own uniforms instead of the Philox ones
-__global__ void thin_count_kernel(Stream st, const StepState *__restrict__ ss, int pop, const uint64_t *__restrict__ n_ind, const uint8_t *__restrict__ sex,
-                                  const double *__restrict__ svf, int with_mm, double mm, const double *__restrict__ thin_u, const double *__restrict__ mm_u,
-                                  uint64_t *__restrict__ cnt) {
-    const uint64_t n = *n_ind;
-    const int gen = ss->gen;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+struct ThinIn {   // scanned as it is drawn; replayed draws (ge_mate_replay): thin_u / mm_u are the reference's own uniforms instead of the Philox ones
+    Stream st; const StepState *ss; int pop; const uint8_t *sex; const double *svf; int with_mm; double mm; const double *thin_u, *mm_u;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
         double r, r2;
         if (thin_u) { r = thin_u[i]; r2 = mm_u[i]; }
         else {
             uint32_t w[4];
-            draw(st, P_THIN, pop, gen, i, 0, 0, w);
+            draw(st, P_THIN, pop, ss->gen, i, 0, 0, w);
             r = u01(w[0], w[1]); r2 = u01(w[2], w[3]);
         }
         uint64_t c = 0;
         if (r < svf[i]) c = (with_mm && r2 < mm) ? 2u : 1u;
-        cnt[i] = sex[i] == 1 ? c : (sex[i] == 2 ? c << 32 : 0ull);
+        return sex[i] == 1 ? c : (sex[i] == 2 ? c << 32 : 0ull);
     }
-}
+};
 // grand total of the thinning scan: list lengths, the couple count and the errors of :2125-2129 / :2226-2230
 struct ThinTotal {
     StepState *ss; int random_mating;
@@ -380,9 +376,8 @@ static int enqueue_mate(ge_ctx *ctx, int pop, const ge_gen_params &gp, const ge_
         GE_TRY(upload_f64(ctx, M.t2, with_mm ? md->mm_u : nullptr, S.n, cap));
         d_thin = M.t1.as<double>(); d_mm = M.t2.as<double>();
     }
-    thin_count_kernel<<<g_ind, 256, 0, st>>>(ctx->rng, ss, pop, S.d_n, S.sex.as<uint8_t>(), S.svf.as<double>(), with_mm, P.MM, d_thin, d_mm, M.keys_a.as<uint64_t>());
-    GE_TRY(ctx->check_launch("thin_count"));
-    GE_TRY(ctx->scan(st, M.keys_a.as<uint64_t>(), devn(S.d_n), cap, M.keys_b.as<uint64_t>(), ThinTotal{ss, P.RM ? 1 : 0}));
+    GE_TRY(ctx->scan_in(st, ThinIn{ctx->rng, ss, pop, S.sex.as<uint8_t>(), S.svf.as<double>(), with_mm ? 1 : 0, P.MM, d_thin, d_mm}, devn(S.d_n), cap, M.keys_b.as<uint64_t>(),
+                        ThinTotal{ss, P.RM ? 1 : 0}));
     thin_fill_kernel<<<g_ind, 256, 0, st>>>(S.d_n, M.keys_b.as<uint64_t>(), M.list_m.as<uint32_t>(), M.list_f.as<uint32_t>());
     GE_TRY(ctx->check_launch("thin_fill"));
     if (P.RM) {  // random_mate :2090-2157

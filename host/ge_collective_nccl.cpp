@@ -3,6 +3,7 @@
 #include <nccl.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,20 +29,32 @@ public:
         return true;
     }
     int allreduce_sum(int rank, double *buf, uint64_t count, void *stream) override {
-        if (aborted) return 1;
+        ncclComm_t c;
+        {   // the communicator handle is read under the lock abort() clears it under: a rank that arrives after an abort sees null
+            std::lock_guard<std::mutex> g(mu);
+            if (aborted || !comms[rank]) return 1;
+            c = comms[rank];
+        }
         cudaSetDevice(first + rank);
-        return ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, comms[rank], static_cast<cudaStream_t>(stream)) == ncclSuccess ? 0 : 1;
+        return ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, c, static_cast<cudaStream_t>(stream)) == ncclSuccess ? 0 : 1;
     }
-    void abort() override {
-        aborted = true;
-        for (ncclComm_t c : comms) if (c) ncclCommAbort(c);
-        comms.assign(comms.size(), nullptr);
+    void abort() override {   // ncclCommAbort is the documented way out for ranks already inside a collective on these communicators
+        std::vector<ncclComm_t> doomed;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (aborted) return;
+            aborted = true;
+            doomed.swap(comms);
+            comms.assign(doomed.size(), nullptr);
+        }
+        for (ncclComm_t c : doomed) if (c) ncclCommAbort(c);
     }
 
 private:
     std::vector<ncclComm_t> comms;
     int first = 0;
-    std::atomic<bool> aborted{false};
+    std::mutex mu;
+    bool aborted = false;
 };
 
 Collective *make_collective() { return new NcclCollective(); }

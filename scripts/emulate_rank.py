@@ -1,4 +1,4 @@
-"""Timing aid: runs ONE rank's share of a chromosome-sharded config-3 job on a single GPU (the all-reduce hook is a
+"""Timing aid: runs ONE rank's share of a locus-range-sharded config-3 job on a single GPU (the all-reduce hook is a
 no-op, so values are wrong but the kernel work, launches and host read-backs are those of that rank)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,21 +6,24 @@ from geneevolve_b200 import capi, workloads, dist as gdist
 
 world, steps = int(sys.argv[1]), int(sys.argv[2])
 cfg = workloads.make_workload("config3_100k_x_1M")
-mine = gdist.assign_chromosomes(cfg["n_loci"], world)[0]
+mine = gdist.assign_locus_ranges(cfg["n_loci"], world)[world // 2]
 N = cfg["n"]
 eng = capi.Engine(n_pop=1, n_chr=len(mine), n_phen=1, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX, seed=12345,
                   capacity=int(N * 1.03) + 1024, rank=0, world_size=world)
-workloads.configure_engine(eng, cfg, chrs_local=mine)
+workloads.configure_engine(eng, cfg, pieces=mine)
 eng.set_allreduce(lambda ptr, count, stream: None)
 eng.init_generation0()
 gp = [capi.gen_params(N, cfg["mat_cor"], "p", "logit", 0.0, 1.0)]
-for g in range(1, 4):
+for g in range(1, 6):
     eng.step_generation(g, gp)
-eng.set_profiling(True); eng.reset_kernel_times(); eng.synchronize()
+eng.set_profiling(1); eng.reset_kernel_times(); eng.synchronize()
 t0 = time.perf_counter(); eng.timer_start()
-for g in range(4, 4 + steps):
+for g in range(6, 6 + steps):
     eng.step_generation(g, gp)
 ms = eng.timer_stop(); wall = (time.perf_counter() - t0) * 1e3
 k_ms, k_n, _ = eng.kernel_time(capi.GE_KERNEL_PROPAGATE_BITS)
-phases = {name: round(eng.kernel_time(pid)[0] / steps, 3) for name, pid in capi.GE_PHASES.items()}
-print(f"world {world}: chromosomes {mine}: {ms / steps:.3f} ms/step (host wall {wall / steps:.3f}), propagate {k_ms / max(k_n, 1):.3f} ms, launches/step {eng.launch_count() / steps:.0f}, control chain {phases}")
+eng.set_profiling(2); eng.reset_kernel_times()
+for g in range(6 + steps, 11 + steps):
+    eng.step_generation(g, gp)
+phases = {name: round(eng.kernel_time(pid)[0] / 5, 3) for name, pid in capi.GE_PHASES.items()}
+print(f"world {world}: pieces {mine}: {ms / steps:.3f} ms/step (host wall {wall / steps:.3f}), propagate {k_ms / max(k_n, 1):.3f} ms, launches/step {eng.launch_count() / steps:.0f}, control chain {phases}")
