@@ -1416,6 +1416,7 @@ int ge_get_gen0_constants(ge_ctx *ctx, int pop, int f, double *va0, double *vd0,
 
 int ge_download_haplotypes(ge_ctx *ctx, int pop, int c, uint8_t *al) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    ge_ctx::TmpScope scratch_only(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     PopDev &P = ctx->pop[pop];
     GenState &S = P.st[P.cur];
@@ -1437,6 +1438,7 @@ int ge_download_haplotypes(ge_ctx *ctx, int pop, int c, uint8_t *al) {
 }
 int ge_download_haplotypes_from_segments(ge_ctx *ctx, int pop, int c, uint8_t *al) {   // ras_convert_interval_to_hap_matrix :1186-1230, whatever else the context carries
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    ge_ctx::TmpScope scratch_only(ctx);
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_download_haplotypes_from_segments needs GE_REP_SEGMENTS");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     GE_TRY(seg_finish_all(ctx));
@@ -1453,6 +1455,7 @@ int ge_download_haplotypes_from_segments(ge_ctx *ctx, int pop, int c, uint8_t *a
 }
 int ge_download_haplotypes_packed(ge_ctx *ctx, int pop, int c, uint32_t *words) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    ge_ctx::TmpScope scratch_only(ctx);
     if (!ctx->bits() && ctx->seg_per_thread) return fail(GE_ERR_UNSUPPORTED, "packed download from segment lists that need not be sorted: use ge_download_haplotypes");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     GenState &S = ctx->pop[pop].st[ctx->pop[pop].cur];
@@ -1475,17 +1478,20 @@ int ge_download_haplotypes_packed(ge_ctx *ctx, int pop, int c, uint32_t *words) 
 
 int ge_get_segment_count(ge_ctx *ctx, int pop, int c, uint64_t *ns, uint64_t *nm) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    ge_ctx::TmpScope scratch_only(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     return seg_count(ctx, pop, c, ns, nm);
 }
 int ge_download_segments(ge_ctx *ctx, int pop, int c, uint64_t *off, uint64_t *seg, uint64_t *moff, uint64_t *mbp) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    ge_ctx::TmpScope scratch_only(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     return seg_download(ctx, pop, c, off, seg, moff, mbp);
 }
 
 int ge_download_cv_alleles(ge_ctx *ctx, int pop, int f, int c, uint8_t *out) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c); CHECK_PHEN(ctx, f);
+    ge_ctx::TmpScope scratch_only(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     GenState &S = ctx->pop[pop].st[ctx->pop[pop].cur];
     uint32_t b0 = ctx->cv_block_off[(size_t)f * ctx->cfg.n_chr + c], b1 = ctx->cv_block_off[(size_t)f * ctx->cfg.n_chr + c + 1];
@@ -1517,6 +1523,7 @@ int ge_rebase_founders(ge_ctx *ctx, int keep_history) {
 }
 int ge_get_segment_count_gen0(ge_ctx *ctx, int pop, int c, uint64_t *ns) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    ge_ctx::TmpScope scratch_only(ctx);
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_get_segment_count_gen0 needs GE_REP_SEGMENTS");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     GE_TRY(seg_download_gen0(ctx, pop, c, ctx->gen0_off, ctx->gen0_seg));
@@ -1526,6 +1533,7 @@ int ge_get_segment_count_gen0(ge_ctx *ctx, int pop, int c, uint64_t *ns) {
 }
 int ge_download_segments_gen0(ge_ctx *ctx, int pop, int c, uint64_t *off, uint64_t *seg) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, c);
+    ge_ctx::TmpScope scratch_only(ctx);
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_download_segments_gen0 needs GE_REP_SEGMENTS");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     if (ctx->gen0_pop != pop || ctx->gen0_chr != c) GE_TRY(seg_download_gen0(ctx, pop, c, ctx->gen0_off, ctx->gen0_seg));   // (ge_get_segment_count_gen0 leaves the composed lists here)
@@ -1538,6 +1546,7 @@ int ge_download_segments_gen0(ge_ctx *ctx, int pop, int c, uint64_t *off, uint64
 
 int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop) {  // ras_find_cv :2752-2815 literally: scan the parts of every haplotype
     CHECK_POP(ctx, pop);
+    ge_ctx::TmpScope scratch_only(ctx);
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_recompute_cv_from_segments needs GE_REP_SEGMENTS");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     return seg_find_cv(ctx, pop);
@@ -1545,6 +1554,7 @@ int ge_recompute_cv_from_segments(ge_ctx *ctx, int pop) {  // ras_find_cv :2752-
 
 int ge_ibd_sharing(ge_ctx *ctx, int pop, int chr, const uint64_t *ind_a, const uint64_t *ind_b, uint64_t n_pairs, uint64_t min_bp, uint64_t *shared_bp, uint32_t *n_runs) {
     CHECK_POP(ctx, pop); CHECK_CHR(ctx, chr);
+    ge_ctx::TmpScope scratch_only(ctx);
     if (!ctx->segs()) return fail(GE_ERR_UNSUPPORTED, "ge_ibd_sharing needs GE_REP_SEGMENTS");
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));
     return seg_ibd(ctx, pop, chr, ind_a, ind_b, n_pairs, min_bp, shared_bp, n_runs);

@@ -212,6 +212,9 @@ struct ge_ctx {
     Buf d_ss_all;                               // StepState [n_pop]
     StepState *h_ss_all = nullptr;              // pinned read-back buffer of the same
     uint64_t graph_epoch = 0;                   // bumped whenever a device buffer is (re)allocated: captured graphs hold raw pointers
+    int tmp_depth = 0;                          // > 0 inside a download: its scratch buffers come and go without touching any graph
+    struct TmpScope { ge_ctx *c; explicit TmpScope(ge_ctx *ctx) : c(ctx) { c->tmp_depth++; } ~TmpScope() { c->tmp_depth--; } };
+    void buffers_moved() { if (tmp_depth == 0) graph_epoch++; }
     int n_sm = 148;
     unsigned prop_threads = 256;   // threads of a propagate_bits_kernel CTA (one offspring): by row length, build_genome
     // stats
@@ -300,7 +303,7 @@ struct ge_ctx {
         if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&b.p, want); }
         if (e != cudaSuccess) return fail(GE_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
         b.cap = want; mem_now += want; mem_peak = std::max(mem_peak, mem_now);
-        graph_epoch++;
+        buffers_moved();
         return GE_OK;
     }
     int ensure_exact(Buf &b, size_t bytes) {
@@ -310,10 +313,10 @@ struct ge_ctx {
         cudaError_t e = cudaMalloc(&b.p, bytes);
         if (e != cudaSuccess) return fail(GE_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
         b.cap = bytes; mem_now += bytes; mem_peak = std::max(mem_peak, mem_now);
-        graph_epoch++;
+        buffers_moved();
         return GE_OK;
     }
-    void release(Buf &b) { if (b.p) { cudaFree(b.p); mem_now -= b.cap; graph_epoch++; } b.p = nullptr; b.cap = 0; }
+    void release(Buf &b) { if (b.p) { cudaFree(b.p); mem_now -= b.cap; buffers_moved(); } b.p = nullptr; b.cap = 0; }
     template <class T> int upload(Buf &b, const std::vector<T> &v) {
         GE_TRY(ensure(b, v.size() * sizeof(T)));
         if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));

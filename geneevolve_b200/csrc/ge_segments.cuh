@@ -886,17 +886,22 @@ static int seg_find_cv(ge_ctx *ctx, int pop) {
     return GE_OK;
 }
 
-// compact CSR of chromosome c over the 2n haplotype rows (scratch: P.cnt32, the caller's row_off buffers)
+// compact CSR of chromosome c over the 2n haplotype rows (all scratch is the caller's or local: downloads never touch a buffer a
+// captured graph points at)
 static int seg_slice_offsets(ge_ctx *ctx, PopDev &P, GenState &S, int c, Buf &row_off, Buf *hm_row_off, uint64_t *n_seg, uint64_t *n_hm) {
+    (void)P;
     const uint64_t n_rows = 2 * S.n;
-    GE_TRY(ctx->ensure(P.cnt32, (2 * n_rows + 2) * 4));
+    Buf cnt_buf;
+    GE_TRY(ctx->ensure_exact(cnt_buf, (2 * n_rows + 2) * 4));
     GE_TRY(ctx->ensure(row_off, (n_rows + 1) * 8));
     if (hm_row_off) GE_TRY(ctx->ensure(*hm_row_off, (n_rows + 1) * 8));
-    uint32_t *cnt = P.cnt32.as<uint32_t>(), *hcnt = hm_row_off ? cnt + n_rows + 1 : nullptr;
+    uint32_t *cnt = cnt_buf.as<uint32_t>(), *hcnt = hm_row_off ? cnt + n_rows + 1 : nullptr;
     seg_slice_count_kernel<<<nblk(n_rows, 256), 256, 0, ctx->stream>>>(n_rows, ctx->cfg.n_chr, c, S.seg.off.as<uint64_t>(), S.has_hm ? S.hm_off.as<uint64_t>() : nullptr, cnt, hcnt);
     GE_TRY(ctx->check_launch("seg_slice_count"));
     GE_TRY(ctx->exclusive_scan(cnt, n_rows, row_off.as<uint64_t>(), n_seg));
     if (hm_row_off) GE_TRY(ctx->exclusive_scan(hcnt, n_rows, hm_row_off->as<uint64_t>(), n_hm));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->release(cnt_buf);
     return GE_OK;
 }
 

@@ -466,3 +466,48 @@ def test_segment_compaction_preserves_haplotypes(cuda_lib):
         for k in "ADGEP":
             assert np.array_equal(a[k], b[k])
     assert shrunk > 0
+
+
+def test_caller_arrays_are_validated_before_any_kernel_reads_them(cuda_lib):
+    """The C-ABI refuses bad caller input with GE_ERR_INVALID before any state changes (no device read through a bad index): couple
+    positions outside the generation, negative family sizes, CSR offsets that do not start at 0 or decrease, crossover positions
+    that do not ascend (bit-packed rows need them monotone), mutation hits without a mutation map, maps changed after generation 0
+    and map rows with probability >= 1 (GE_ERR_UNSUPPORTED)."""
+    case = Case(9, [70, 33])
+    e = capi.Engine(cuda_lib, **case.kwargs(32, representation=capi.GE_REP_BITS))
+    case.configure(e)
+    e.init_generation0([case.draws0()])
+    n = case.nf
+    ok = dict(pos_male=[0, 1], pos_female=[1, 0], inbreed=[0, 0], num_offspring=[1, 2])
+    for bad in (dict(pos_male=[0, n]), dict(pos_female=[n + 5, 0]), dict(num_offspring=[1, -1])):
+        with pytest.raises(capi.GeneEvolveError) as ei:
+            e.set_couples(0, **{**ok, **bad})
+        assert ei.value.code == -1
+    e.set_couples(0, **ok)
+    none = lambda s, c: []  # noqa: E731
+    gp = [capi.gen_params(10)]
+
+    def broken(mutate):
+        d = case.draws(n, 6, lambda s, c: [int(case.maps[c][0][1]) + 3, int(case.maps[c][0][2]) + 5])
+        mutate(d.arrays)
+        with pytest.raises(capi.GeneEvolveError) as ei:
+            e.step_generation(1, gp, None, [d])
+        assert ei.value.code == -1, str(ei.value)
+        assert e.population_size(0) == n        # nothing happened
+
+    broken(lambda a: a["xo_off"].__setitem__(0, 1))                                   # offsets must start at 0
+    broken(lambda a: a["xo_off"].__setitem__(3, int(a["xo_off"][2]) - 1))             # ... and never decrease
+    broken(lambda a: a["xo_bp"].__setitem__(slice(0, 2), a["xo_bp"][:2][::-1].copy()))  # positions of a gamete must ascend
+    broken(lambda a: a.__setitem__("mut_off", np.zeros(6 * case.n_chr + 1, np.uint64)))   # hits without a mutation map
+    e.step_generation(1, gp, None, [case.draws(n, 6, none)])                          # the context is still usable
+    assert e.population_size(0) == 6
+    bp, pr, step = case.maps[0]
+    with pytest.raises(capi.GeneEvolveError) as ei:                                    # maps are frozen at generation 0
+        e.set_genetic_map(0, 0, bp, pr, step)
+    assert ei.value.code == -1
+    f = capi.Engine(cuda_lib, **case.kwargs(32, representation=capi.GE_REP_BITS))
+    p1 = np.array(pr, float)
+    p1[2] = 1.0
+    with pytest.raises(capi.GeneEvolveError) as ei:                                    # a 100 cM jump between two rows
+        f.set_genetic_map(0, 0, bp, p1, step)
+    assert ei.value.code == -7
