@@ -1074,7 +1074,8 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
         GE_TRY(ctx->check_launch("offspring"));
         P.have_couple_of = true;
         // crossovers: count + stash, scan, place
-        sample_xo_kernel<<<ctx->ctrl_grid(slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ss, C, pop, P.cnt32.as<uint32_t>(), D.start_hap.as<uint8_t>(), ctx->xo_stash.as<uint32_t>());
+        // (its warps refill their lanes from a chunk of slots: about one resident wave, so that the chunks are long)
+        sample_xo_kernel<<<std::min<unsigned>(ctx->ctrl_grid(slots, 128), (unsigned)ctx->n_sm * 12u), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ss, C, pop, P.cnt32.as<uint32_t>(), D.start_hap.as<uint8_t>(), ctx->xo_stash.as<uint32_t>());
         GE_TRY(ctx->check_launch("sample_xo"));
         GE_TRY(ctx->scan(st, P.cnt32.as<uint32_t>(), devn(&ss->n_off, (uint64_t)C * 2), slots, D.xo_off.as<uint64_t>(), XoTotal{ss, (uint64_t)C * 2, P.dcur}));
         xo_place_kernel<<<ctx->ctrl_grid(slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ctx->genome(), ss, C, pop, D.xo_off.as<uint64_t>(), ctx->xo_stash.as<uint32_t>(),
@@ -1135,8 +1136,13 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
     // ---- causal-variant planes
     if (ctx->n_cv_tot) {  // in every representation: crossover parity at the CV positions, never a rescan of the segment lists
         uint64_t tot = cap * 2 * ctx->Wcv;
-        cv_propagate_bits_kernel<<<ctx->ctrl_grid(tot, 256), 256, 0, st>>>(ctx->cvset(), ss, par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
-                                                                 D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>());
+        const CvSet cvs = ctx->cvset();
+        if (cvs.sorted && (size_t)ctx->Wcv * 4 * 10 <= 48 * 1024)   // a warp per gamete row, toggle words in shared memory (about one resident wave: the CTAs keep their tables)
+            cv_propagate_rows_kernel<<<std::min<unsigned>(ctx->ctrl_grid(cap * 2 * 32, 256), (unsigned)ctx->n_sm * 8u), 256, (size_t)ctx->Wcv * 4 * 10, st>>>(cvs, ss, par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
+                                                                                                         D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>());
+        else   // unsorted cv.info rows, or more CV words per row than eight warps can hold in shared memory
+            cv_propagate_bits_kernel<<<ctx->ctrl_grid(tot, 256), 256, 0, st>>>(cvs, ss, par.cv_allele.as<uint32_t>(), off.cv_allele.as<uint32_t>(), D.father.as<uint32_t>(),
+                                                                     D.mother.as<uint32_t>(), D.xo_off.as<uint64_t>(), D.xo_bp.as<uint32_t>(), D.start_hap.as<uint8_t>());
         GE_TRY(ctx->check_launch("cv_propagate_bits"));
         if (ctx->use_root) {
             uint64_t tr = cap * 2 * ctx->n_cv_tot;

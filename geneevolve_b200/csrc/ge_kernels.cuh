@@ -461,6 +461,87 @@ __global__ void cv_propagate_bits_kernel(CvSet cs, const StepState *__restrict__
     }
 }
 
+// The same planes, one WARP per offspring gamete row (sorted CV blocks, toggle words in shared memory).  The thread-per-word kernel
+// above re-walks the slot's crossovers for every word of the chromosome and ran with 15 of 32 lanes active (ncu, round 2); here the
+// ~35 crossovers of the whole gamete are one flat list dealt out to the lanes, each crossover marks "the haplotype flips from CV idx
+// on" as ONE toggle bit per phenotype block (idx = lower_bound over the block's positions), and the copy mask of a word is the
+// running XOR of the toggle bits before it in its block: a prefix-XOR inside the word (five shifts) and the parity of the block's
+// earlier words.
+__global__ void __launch_bounds__(256) cv_propagate_rows_kernel(CvSet cs, const StepState *__restrict__ ss, const uint32_t *__restrict__ par_bits, uint32_t *__restrict__ off_bits,
+                                                                const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
+                                                                const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
+                                                                const uint8_t *__restrict__ start_hap) {
+    extern __shared__ uint32_t s_toggle[];   // [warps per CTA][Wcv] toggle words, then [Wcv] chromosome and [Wcv] first block word of every word
+    if (ss->err & SE_FATAL) return;
+    const uint64_t n_rows = ss->n_off * 2;
+    const int lane = threadIdx.x & 31;
+    const uint32_t C = (uint32_t)cs.n_chr, Wcv = cs.Wcv;
+    uint32_t *T = s_toggle + (threadIdx.x >> 5) * Wcv;
+    uint32_t *s_chr = s_toggle + (blockDim.x >> 5) * Wcv, *s_first = s_chr + Wcv;
+    for (uint32_t w = threadIdx.x; w < Wcv; w += blockDim.x) {   // (the same for every row this CTA will take)
+        const uint32_t b = cs.word_blk[w];
+        s_chr[w] = b == 0xFFFFFFFFu ? b : b % C;
+        s_first[w] = b == 0xFFFFFFFFu ? 0u : cs.word_off[b];
+    }
+    __syncthreads();
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
+        const uint64_t i = row >> 1;
+        const uint32_t gam = (uint32_t)(row & 1);
+        for (uint32_t w = lane; w < Wcv; w += 32) T[w] = 0u;
+        __syncwarp();
+        for (uint32_t c0 = 0; c0 < C; c0 += 32) {   // the crossovers of up to 32 chromosomes of this gamete, as one flat list
+            const uint32_t c = c0 + lane;
+            uint64_t e0 = 0;
+            uint32_t cnt = 0;
+            if (c < C) { const uint64_t slot = (i * C + c) * 2 + gam; e0 = xo_off[slot]; cnt = (uint32_t)(xo_off[slot + 1] - e0); }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+                const bool act = r0 + lane < total;
+                const uint32_t r = min(r0 + lane, total - 1);
+                int lo = 0, hi = 31;   // owner: the first lane whose inclusive prefix exceeds r
+#pragma unroll
+                for (int step = 0; step < 5; step++) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint32_t v = __shfl_sync(0xffffffffu, incl, mid);
+                    if (v > r) hi = mid; else lo = mid + 1;
+                }
+                const uint32_t q = r - (__shfl_sync(0xffffffffu, incl, lo) - __shfl_sync(0xffffffffu, cnt, lo));
+                const uint64_t e = __shfl_sync(0xffffffffu, e0, lo) + q;
+                if (act) {
+                    const uint32_t x = xo_bp[e];
+                    for (int f = 0; f < cs.n_phen; f++) {
+                        const uint32_t b = (uint32_t)f * C + c0 + (uint32_t)lo;
+                        const uint32_t k0 = cs.block_off[b], nk = cs.block_off[b + 1] - k0;
+                        const uint32_t idx = lower_bound_u32(cs.bp + k0, nk, x);   // CVs at or above the crossover flip
+                        if (idx < nk) atomicXor(&T[cs.word_off[b] + (idx >> 5)], 1u << (idx & 31u));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        const uint32_t parent = gam ? mother[i] : father[i];
+        const uint32_t *pr = par_bits + (uint64_t)parent * 2 * Wcv;
+        for (uint32_t w = lane; w < Wcv; w += 32) {
+            const uint32_t c = s_chr[w];
+            uint32_t v = 0;
+            if (c != 0xFFFFFFFFu) {
+                uint32_t m = T[w];
+                m ^= m << 1; m ^= m << 2; m ^= m << 4; m ^= m << 8; m ^= m << 16;
+                uint32_t par = start_hap[(i * C + c) * 2 + gam] & 1u;
+                for (uint32_t w2 = s_first[w]; w2 < w; w2++) par ^= (uint32_t)__popc(T[w2]) & 1u;
+                if (par) m = ~m;
+                v = (pr[w] & ~m) | (pr[Wcv + w] & m);
+            }
+            off_bits[row * Wcv + w] = v;
+        }
+        __syncwarp();   // the toggle words are cleared for the next row
+    }
+}
+
 // root-population plane (only with more than one population): one thread per (offspring gamete row, CV)
 __global__ void cv_root_propagate_kernel(CvSet cs, const StepState *__restrict__ ss, const uint8_t *__restrict__ par_root, uint8_t *__restrict__ off_root,
                                          const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
@@ -948,78 +1029,126 @@ __device__ __forceinline__ long long next_success(const MapDev &m, int c, const 
     if (lo < j) lo = j;
     return (long long)lo;
 }
-// One thread per slot: counts the crossovers of the slot, writes start_hap and stashes the first XO_STASH positions at a
-// fixed stride; after the scan, xo_place_kernel moves the stash into the CSR (re-drawing only the rare longer lists)
-// and converts positions to locus indices in the same sweep.
-constexpr int XO_STASH = 4;
+// Counts the crossovers of every slot, writes start_hap and stashes the first XO_STASH positions at a fixed stride; after
+// the scan, xo_place_kernel moves the stash into the CSR (re-drawing only the rare longer lists) and converts positions to
+// locus indices in the same sweep.
+// A slot takes 1 + (its crossovers) draws — 1 for most of chromosome 22, up to a dozen for chromosome 1 — so one thread per slot
+// kept 12 of 32 lanes busy (ncu, round 2).  Here a warp owns a chunk of consecutive slots and its lanes take them one at a time: a
+// lane whose slot is finished picks the next free slot of the chunk at the end of the round (ballot + rank), so every lane draws in
+// every round until the chunk runs dry.  The draws are keyed by (individual, chromosome, gamete, block): the schedule cannot change them.
+constexpr int XO_STASH = 8;
 __global__ void sample_xo_kernel(Stream st, MapDev m, const StepState *__restrict__ ss, int n_chr, int pop, uint32_t *__restrict__ count,
                                  uint8_t *__restrict__ start_hap, uint32_t *__restrict__ stash) {
     if (ss->err & SE_FATAL) return;
     const uint64_t n_slots = ss->n_off * (uint64_t)n_chr * 2;
     const int gen = ss->gen;
-    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t i;
-    uint32_t cc;
-    divmod_idx(slot >> 1, (uint32_t)n_chr, i, cc);
-    const int c = (int)cc, gam = (int)(slot & 1);
-    uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
-    const double *T = m.T + r0 + c;
-    uint32_t j = 0, blk = 0, n = 0;
-    for (;;) {
-        uint32_t w[4];
-        draw(st, P_XO, pop, gen, i, m.chr_id[c] * 2u + (uint32_t)gam, blk, w);
-        if (blk == 0) start_hap[slot] = (uint8_t)(w[3] & 1u);
-        blk++;
-        if (j >= R) break;
-        double v = (1.0 - u01(w[0], w[1])) * T[j];
-        long long k = next_success(m, c, T, R, j, v);
-        if (k < 0) break;
-        if (n < XO_STASH) stash[slot * XO_STASH + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
-        n++;
-        j = (uint32_t)k + 1;
-    }
-    count[slot] = n;
+    const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5, warp_id = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // chunk: long enough to keep the lanes fed (the tail of a chunk idles), short enough that a small population still covers the grid,
+    // and the same number of chunks for every warp (1.5 chunks per warp would leave half the warps waiting for the other half)
+    const uint64_t per_warp = (n_slots + n_warps - 1) / n_warps, passes = (per_warp + 1023) / 1024;
+    const uint64_t chunk = max((uint64_t)32, ((per_warp + passes - 1) / max(passes, (uint64_t)1) + 31) & ~31ull);
+    for (uint64_t c0 = warp_id * chunk; c0 < n_slots; c0 += n_warps * chunk) {
+        const uint64_t end = min(c0 + chunk, n_slots);
+        uint64_t next = c0 + 32, slot = c0 + lane, i = 0;
+        bool have = slot < end, fresh = have;
+        uint32_t c = 0, r0 = 0, R = 0, j = 0, blk = 0, n = 0, key = 0;
+        const double *T = nullptr;
+        while (__any_sync(0xffffffffu, have)) {
+            if (have) {
+                if (fresh) {
+                    divmod_idx(slot >> 1, (uint32_t)n_chr, i, c);
+                    r0 = m.row_off[c]; R = m.row_off[c + 1] - r0;
+                    T = m.T + r0 + c;
+                    key = m.chr_id[c] * 2u + (uint32_t)(slot & 1);
+                    j = 0; blk = 0; n = 0; fresh = false;
+                }
+                uint32_t w[4];
+                draw(st, P_XO, pop, gen, i, key, blk, w);
+                if (blk == 0) start_hap[slot] = (uint8_t)(w[3] & 1u);
+                blk++;
+                bool done = j >= R;
+                if (!done) {
+                    const double v = (1.0 - u01(w[0], w[1])) * T[j];
+                    const long long k = next_success(m, (int)c, T, R, j, v);
+                    if (k < 0) done = true;
+                    else {
+                        if (n < XO_STASH) stash[slot * XO_STASH + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
+                        n++;
+                        j = (uint32_t)k + 1;
+                    }
+                }
+                if (done) { count[slot] = n; have = false; }
+            }
+            const unsigned idle = __ballot_sync(0xffffffffu, !have);
+            if (idle && next < end) {   // (warp-uniform) idle lanes take the next slots of the chunk, in lane order
+                if (!have) { slot = next + __popc(idle & lt_mask); have = slot < end; fresh = have; }
+                next += __popc(idle);
+            }
+        }
     }
 }
-// stash -> CSR (+ locus indices of the flips when the bit-packed rows are kept); slots longer than the stash re-draw
+// stash -> CSR (+ locus indices of the flips when the bit-packed rows are kept); slots longer than the stash re-draw.
+// One thread per slot ran at 4.6 of 32 lanes active (ncu, round 2: most slots hold no crossover, a few hold many).  A WARP now takes 32
+// consecutive slots and deals their crossovers — one flat list, prefix-summed over the lanes — out one per lane and round: every lane
+// moves one position (and looks one locus index up) per round, and the stores of a round are consecutive CSR entries.
 __global__ void xo_place_kernel(Stream st, MapDev m, Genome g, const StepState *__restrict__ ss, int n_chr, int pop, const uint64_t *__restrict__ xo_off,
                                 const uint32_t *__restrict__ stash, uint32_t *__restrict__ xo_bp, uint32_t *__restrict__ flips) {
     if (ss->err & SE_FATAL) return;   // (also: more crossovers than the draw buffers hold — nothing is written)
     const uint64_t n_slots = ss->n_off * (uint64_t)n_chr * 2;
     const int gen = ss->gen;
-    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t o = xo_off[slot];
-    const uint32_t cnt = (uint32_t)(xo_off[slot + 1] - o);
-    if (cnt == 0) continue;
-    uint64_t i;
-    uint32_t cc;
-    divmod_idx(slot >> 1, (uint32_t)n_chr, i, cc);
-    const int c = (int)cc;
-    if (cnt <= XO_STASH) {
-        for (uint32_t q = 0; q < cnt; q++) {
-            uint32_t x = stash[slot * XO_STASH + q];
-            xo_bp[o + q] = x;
-            if (flips) flips[o + q] = locus_lower_bound(g, c, x);
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t w0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < n_slots; w0 += n_warps * 32) {
+        const uint64_t slot = w0 + lane;
+        uint64_t o = 0;
+        uint32_t cnt = 0, cc = 0;
+        uint64_t i = 0;
+        if (slot < n_slots) {
+            o = xo_off[slot];
+            cnt = (uint32_t)(xo_off[slot + 1] - o);
+            divmod_idx(slot >> 1, (uint32_t)n_chr, i, cc);
         }
-        continue;
-    }
-    const int gam = (int)(slot & 1);
-    const uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
-    const double *T = m.T + r0 + c;
-    uint32_t j = 0, blk = 0, n = 0;
-    for (;;) {
-        uint32_t w[4];
-        draw(st, P_XO, pop, gen, i, m.chr_id[c] * 2u + (uint32_t)gam, blk++, w);
-        if (j >= R) break;
-        double v = (1.0 - u01(w[0], w[1])) * T[j];
-        long long k = next_success(m, c, T, R, j, v);
-        if (k < 0) break;
-        uint32_t x = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
-        xo_bp[o + n] = x;
-        if (flips) flips[o + n] = locus_lower_bound(g, c, x);
-        n++;
-        j = (uint32_t)k + 1;
-    }
+        const uint32_t coop = cnt <= XO_STASH ? cnt : 0u;   // what this lane's slot hands to the cooperative rounds
+        uint32_t incl = coop;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+            const uint32_t r = min(r0 + lane, total - 1);   // (lanes beyond the list redo its last entry)
+            int lo = 0, hi = 31;                            // owner: the first lane whose inclusive prefix exceeds r
+#pragma unroll
+            for (int step = 0; step < 5; step++) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, mid);
+                if (v > r) hi = mid; else lo = mid + 1;
+            }
+            const uint32_t q = r - (__shfl_sync(0xffffffffu, incl, lo) - __shfl_sync(0xffffffffu, coop, lo));
+            const uint64_t oo = __shfl_sync(0xffffffffu, o, lo);
+            const uint32_t oc = __shfl_sync(0xffffffffu, cc, lo);
+            const uint32_t x = stash[(w0 + lo) * XO_STASH + q];
+            xo_bp[oo + q] = x;
+            if (flips) flips[oo + q] = locus_lower_bound(g, (int)oc, x);
+        }
+        if (cnt > XO_STASH) {   // the rare long list: drawn again by its own lane
+            const int c = (int)cc, gam = (int)(slot & 1);
+            const uint32_t r0 = m.row_off[c], R = m.row_off[c + 1] - r0;
+            const double *T = m.T + r0 + c;
+            uint32_t j = 0, blk = 0, n = 0;
+            for (;;) {
+                uint32_t w[4];
+                draw(st, P_XO, pop, gen, i, m.chr_id[c] * 2u + (uint32_t)gam, blk++, w);
+                if (j >= R) break;
+                double v = (1.0 - u01(w[0], w[1])) * T[j];
+                long long k = next_success(m, c, T, R, j, v);
+                if (k < 0) break;
+                uint32_t x = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
+                xo_bp[o + n] = x;
+                if (flips) flips[o + n] = locus_lower_bound(g, c, x);
+                n++;
+                j = (uint32_t)k + 1;
+            }
+        }
     }
 }
 // the grand total of the crossover scan: n_xo, the interval count of the segment plan, and the capacity check

@@ -201,8 +201,8 @@ __device__ __forceinline__ uint32_t part_y(const uint2 *__restrict__ H, uint32_t
 // #(y <= X) among parts [lo, n) of a list with non-decreasing y, plus lo — two searches with independent loads in flight
 // (XA <= XB in every caller that matters, not required)
 template <class T>
-__device__ __forceinline__ void seg_count_y_le2(const T *__restrict__ H, uint32_t lo, uint32_t n, uint32_t hi_c, uint32_t XA, uint32_t XB, uint32_t &rA, uint32_t &rB) {
-    uint32_t loA = lo, hiA = n, loB = lo, hiB = n;
+__device__ __forceinline__ void seg_count_y_le2(const T *__restrict__ H, uint32_t n, uint32_t hi_c, uint32_t XA, uint32_t XB, uint32_t loA, uint32_t hiA, uint32_t loB, uint32_t hiB,
+                                                uint32_t &rA, uint32_t &rB) {   // [loA, hiA), [loB, hiB): windows known to hold the two answers
     while (loA < hiA || loB < hiB) {
         const bool actA = loA < hiA, actB = loB < hiB;
         const uint32_t mA = (loA + hiA) >> 1, mB = (loB + hiB) >> 1;
@@ -215,72 +215,107 @@ __device__ __forceinline__ void seg_count_y_le2(const T *__restrict__ H, uint32_
     rA = loA; rB = loB;
 }
 
-// One THREAD per slot: two binary searches per interval over the .y column (about 1 KB of sectors per slot instead of the
-// 2.7 KB of both lists, and ~10 warp instructions per slot instead of ~400 for a warp that ballots its way through them).
-// Interval g = xo_off[slot] + slot + j gets a copy descriptor {absolute index of its first parental part (64 bit), L, R} and its
-// part count; the scan of the counts gives every interval its absolute output offset, so the copy itself knows nothing of slots.
+// The plan.  Interval g = xo_off[slot] + slot + j gets a copy descriptor {absolute index of its first parental part (64 bit), L, R} and
+// its part count; the scan of the counts gives every interval its absolute output offset, so the copy itself knows nothing of slots.
+// Round 1 ran one THREAD per slot through its k + 1 intervals: with k = 0 for half the slots and up to a dozen for chromosome 1, ncu
+// (profiles/r2k_seg_plan_gather_ncu_full_raw.csv) found 11 of 32 lanes active in the search loop and the kernel issue-bound on that
+// waste (1.13 ms for 250k individuals at generation 41).  Now a WARP takes 32 consecutive slots: every lane reads its slot's header
+// and does the per-slot checks, the headers go to shared memory, and the intervals of all 32 slots — a flat list, prefix-summed —
+// are dealt out to the lanes one each per round, so every lane of every round does exactly one interval: two binary searches, side
+// by side, over the .y column of its haplotype.  Slots without a crossover (one unclipped interval) and slots whose positions do not
+// ascend (the reference's loop verbatim, or refused with packed parts) are finished by their own lane.
 template <class T>
 __global__ void __launch_bounds__(128) seg_plan_kernel(SegArgs a, uint32_t *__restrict__ iv_count, uint4 *__restrict__ desc, unsigned int *__restrict__ n_verbatim,
                                                        uint64_t *__restrict__ verb_list, uint32_t verb_cap, uint32_t *__restrict__ err) {
     constexpr bool PACKED = sizeof(T) == 8;
     if (a.dead()) return;   // also: the parental lists outgrew their buffer
+    __shared__ SegSlot s_slot[4][32];
     const T *par = static_cast<const T *>(a.par_seg);
     const uint64_t n_total = a.dc->n_off * a.n_chr * 2;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const SegSlot s = seg_slot(a, t);
-        const uint64_t g = s.e0 + s.slot;
-        if (s.k == 0) {   // the chosen parental haplotype unchanged (:2910): one unclipped interval
-            const uint64_t src = s.hi ? s.b1 : s.b0;
-            desc[g] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), 0u, 0xFFFFFFFFu);
-            iv_count[g] = s.hi ? s.n1 : s.n0;
-            continue;
-        }
-        const T *H0 = par + s.b0, *H1 = par + s.b1;
-        const uint32_t lo_c = a.cov_lo[s.c], hi_c = a.cov_hi[s.c];
-        const uint32_t *xo = a.xo_bp + s.e0;
-        bool fast = true;   // positions must ascend: X_1 <= ... <= X_k (positions below cov_lo only make the first interval empty)
-        {
-            uint32_t prev = 0;
-            for (uint32_t j = 0; j < s.k; j++) { const uint32_t x = __ldg(xo + j); fast &= x >= prev; prev = x; }
-            if (fast && prev > hi_c) {
-                // a crossover in the last map row lies beyond cov_hi, so the last interval has L > R.  The reference's loop first skips
-                // every part with y <= L: if that is the whole list (the normal case, lists end at cov_hi) the interval emits nothing,
-                // which is what the index range gives (i0 = n).  Anything else goes to the verbatim loop.
-                const int hl = s.hi ^ (int)(s.k & 1u);
-                const uint32_t nl = hl ? s.n1 : s.n0;
-                fast = nl == 0 || part_y(hl ? H1 : H0, nl - 1, nl, hi_c) <= prev;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SegSlot *mine = s_slot[warp];
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t w0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < n_total; w0 += n_warps * 32) {
+        const uint64_t t = w0 + lane;
+        uint32_t cnt = 0;   // intervals this lane's slot hands to the cooperative rounds
+        if (t < n_total) {
+            const SegSlot s = seg_slot(a, t);
+            const uint64_t g = s.e0 + s.slot;
+            if (s.k == 0) {   // the chosen parental haplotype unchanged (:2910): one unclipped interval
+                const uint64_t src = s.hi ? s.b1 : s.b0;
+                desc[g] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), 0u, 0xFFFFFFFFu);
+                iv_count[g] = s.hi ? s.n1 : s.n0;
+            } else {
+                const T *H0 = par + s.b0, *H1 = par + s.b1;
+                const uint32_t lo_c = a.cov_lo[s.c], hi_c = a.cov_hi[s.c];
+                const uint32_t *xo = a.xo_bp + s.e0;
+                bool fast = true;   // positions must ascend: X_1 <= ... <= X_k (positions below cov_lo only make the first interval empty)
+                uint32_t prev = 0;
+                for (uint32_t j = 0; j < s.k; j++) { const uint32_t x = __ldg(xo + j); fast &= x >= prev; prev = x; }
+                if (fast && prev > hi_c) {
+                    // a crossover in the last map row lies beyond cov_hi, so the last interval has L > R.  The reference's loop first skips
+                    // every part with y <= L: if that is the whole list (the normal case, lists end at cov_hi) the interval emits nothing,
+                    // which is what the index range gives (i0 = n).  Anything else goes to the verbatim loop.
+                    const int hl = s.hi ^ (int)(s.k & 1u);
+                    const uint32_t nl = hl ? s.n1 : s.n0;
+                    fast = nl == 0 || part_y(hl ? H1 : H0, nl - 1, nl, hi_c) <= prev;
+                }
+                if (fast) { cnt = s.k + 1; mine[lane] = s; }
+                else if constexpr (PACKED) {   // pieces that do not tile cannot be stored with an implied end: refuse (ge_last_error names the 16-byte format)
+                    atomicOr(err, (uint32_t)SE_SEG_UNSORTED);
+                    for (uint32_t j = 0; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
+                } else {   // the reference's loop verbatim (seg_verbatim_fill_kernel writes the parts)
+                    const uint32_t n = seg_recombine_verbatim<false>(H0, s.n0, H1, s.n1, xo, s.k, lo_c, hi_c, s.hi, nullptr);
+                    desc[g] = make_uint4(0u, SEG_PLAN_VERBATIM, 0u, 0u);
+                    iv_count[g] = n;
+                    for (uint32_t j = 1; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
+                    const unsigned int w = atomicAdd(n_verbatim, 1u);
+                    if (w < verb_cap) verb_list[w] = t;
+                }
             }
         }
-        if (!fast) {
-            if constexpr (PACKED) {   // pieces that do not tile cannot be stored with an implied end: refuse (ge_last_error names the 16-byte format)
-                atomicOr(err, (uint32_t)SE_SEG_UNSORTED);
-                for (uint32_t j = 0; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
-            } else {   // the reference's loop verbatim (seg_verbatim_fill_kernel writes the parts)
-                const uint32_t n = seg_recombine_verbatim<false>(H0, s.n0, H1, s.n1, xo, s.k, lo_c, hi_c, s.hi, nullptr);
-                desc[g] = make_uint4(0u, SEG_PLAN_VERBATIM, 0u, 0u);
-                iv_count[g] = n;
-                for (uint32_t j = 1; j <= s.k; j++) { desc[g + j] = make_uint4(0u, 0u, 0u, 0u); iv_count[g + j] = 0u; }
-                const unsigned int w = atomicAdd(n_verbatim, 1u);
-                if (w < verb_cap) verb_list[w] = t;
+        // the warp's intervals as one flat list: inclusive prefix of the per-lane counts
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+            const uint32_t r = min(r0 + lane, total - 1);   // (lanes beyond the list redo its last interval: no divergence, the same stores)
+            int lo = 0, hi = 31;                            // owner: the first lane whose inclusive prefix exceeds r
+#pragma unroll
+            for (int step = 0; step < 5; step++) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, mid);
+                if (v > r) hi = mid; else lo = mid + 1;
             }
-            continue;
-        }
-        uint32_t cur0 = 0, cur1 = 0, L = lo_c;
-        int h = s.hi;
-        for (uint32_t j = 0; j <= s.k; j++) {
-            const uint32_t R = j == s.k ? hi_c : __ldg(xo + j);
-            const T *H = h ? H1 : H0;
+            const uint32_t owner_incl = __shfl_sync(0xffffffffu, incl, lo), owner_cnt = __shfl_sync(0xffffffffu, cnt, lo);
+            const uint32_t j = r - (owner_incl - owner_cnt);
+            const SegSlot &s = mine[lo];
+            const uint32_t lo_c = a.cov_lo[s.c], hi_c = a.cov_hi[s.c];
+            const uint32_t *xo = a.xo_bp + s.e0;
+            const uint32_t L = j == 0 ? lo_c : __ldg(xo + j - 1), R = j == s.k ? hi_c : __ldg(xo + j);
+            const int h = s.hi ^ (int)(j & 1u);
+            const T *H = par + (h ? s.b1 : s.b0);
             const uint32_t nH = h ? s.n1 : s.n0;
-            uint32_t i0, c;                                                   // first part with y > L; #(y <= R) — searched side by side
-            seg_count_y_le2(H, h ? cur1 : cur0, nH, hi_c, L, R, i0, c);
-            if (h) cur1 = c; else cur0 = c;                                   // #(y <= R): the next interval on this haplotype starts at or after R
+            // first part with y > L; #(y <= R) — searched side by side.  The two ends of a chromosome need no search (one probe says so): the
+            // first interval starts at the first part, the last one ends with the last — which leaves two searches per CROSSOVER, not per
+            // interval, and the divergent probes of the searches are what the kernel waits for (552 M warp instructions in 1.14 ms).
+            uint32_t aHi = nH, bLo = 0;
+            if (nH) {
+                if (j == 0 && part_y(H, 0u, nH, hi_c) > L) aHi = 0;
+                if (j == s.k && (PACKED || part_y(H, nH - 1, nH, hi_c) <= R)) bLo = nH;
+            }
+            uint32_t i0, c;
+            seg_count_y_le2(H, nH, hi_c, L, R, 0u, aHi, bLo, nH, i0, c);
             uint32_t i1 = max(c, i0);                                         // max(#(y <= R), #(x < R)), x non-decreasing; L > R (first interval with a
             while (i1 < nH && __ldg(&H[i1].x) < R) i1++;                      // position below cov_lo, last one beyond cov_hi) gives an empty range
             const uint64_t src = (h ? s.b1 : s.b0) + i0;
-            desc[g + j] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), L, R);
-            iv_count[g + j] = i1 - i0;
-            L = R; h ^= 1;
+            const uint64_t g = s.e0 + s.slot + j;
+            desc[g] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), L, R);
+            iv_count[g] = i1 - i0;
         }
+        __syncwarp();   // the headers are overwritten in the next round of 32 slots
     }
 }
 
