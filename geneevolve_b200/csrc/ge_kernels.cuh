@@ -1047,7 +1047,8 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, const StepState *__restric
     // chunk: long enough to keep the lanes fed (the tail of a chunk idles), short enough that a small population still covers the grid,
     // and the same number of chunks for every warp (1.5 chunks per warp would leave half the warps waiting for the other half)
     const uint64_t per_warp = (n_slots + n_warps - 1) / n_warps, passes = (per_warp + 1023) / 1024;
-    const uint64_t chunk = max((uint64_t)32, ((per_warp + passes - 1) / max(passes, (uint64_t)1) + 31) & ~31ull);
+    const uint64_t even = passes ? ((per_warp + passes - 1) / passes + 31) & ~31ull : 32;
+    const uint64_t chunk = even < 32 ? 32 : even;
     for (uint64_t c0 = warp_id * chunk; c0 < n_slots; c0 += n_warps * chunk) {
         const uint64_t end = min(c0 + chunk, n_slots);
         uint64_t next = c0 + 32, slot = c0 + lane, i = 0;
