@@ -244,6 +244,7 @@ static int build_cvset(ge_ctx *ctx) {
     for (int b = 0; b < nf * C; b++)
         for (uint32_t k = ctx->cv_block_off[b] + 1; k < ctx->cv_block_off[b + 1]; k++) if (bp[k] < bp[k - 1]) ctx->cv_sorted = false;
     GE_TRY(ctx->ensure(ctx->d_LA, (size_t)std::max<uint32_t>(ctx->n_cv_tot, 1) * 48));
+    GE_TRY(ctx->ensure(ctx->d_LG, (size_t)ctx->Wcv * 8 * 256 * 16));
     std::vector<uint32_t> bitpos(ctx->n_cv_tot);
     for (int b = 0; b < nf * C; b++)
         for (uint32_t k = ctx->cv_block_off[b]; k < ctx->cv_block_off[b + 1]; k++) bitpos[k] = ctx->cv_word_off[b] * 32 + (k - ctx->cv_block_off[b]);
@@ -373,7 +374,7 @@ int ge_destroy(ge_ctx *ctx) {
         mate_release(ctx, P.mate);
         if (P.ev_ready) cudaEventDestroy(P.ev_ready);
     }
-    for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_bkt_off, &ctx->d_bkt_shift, &ctx->d_bkt, &ctx->d_LA, &ctx->d_cv_bitpos, &ctx->xo_stash, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
+    for (Buf *b : {&ctx->d_chr_word_off, &ctx->d_chr_nloci, &ctx->d_locus_off, &ctx->d_pos, &ctx->d_bkt_off, &ctx->d_bkt_shift, &ctx->d_bkt, &ctx->d_LA, &ctx->d_LG, &ctx->d_cv_bitpos, &ctx->xo_stash, &ctx->d_tile_chr, &ctx->d_tile_chunk0, &ctx->d_tile_nchunk,
                    &ctx->d_cv_block_off, &ctx->d_cv_word_off, &ctx->d_cv_word_blk, &ctx->d_cv_bp, &ctx->d_cv_chr, &ctx->d_a_eff, &ctx->d_d_eff, &ctx->d_cv_count, &ctx->scan_blocks, &ctx->bulk_scan_blocks,
                    &ctx->partial, &ctx->scalars, &ctx->d_ss_all, &ctx->d_chr_ids, &ctx->ar_scratch, &ctx->seg_desc, &ctx->seg_iv_off, &ctx->seg_cnt, &ctx->seg_flags, &ctx->seg_verb})
         freeb(*b);
@@ -498,8 +499,10 @@ static int enqueue_AD(ge_ctx *ctx, int pop) {  // ras_compute_AD :2624-2749
     uint32_t ncv = ctx->n_cv_tot;
     if (ncv) {
         CUDA_TRY(cudaMemsetAsync(ctx->d_cv_count.p, 0, (size_t)ncv * 8, ctx->stream));
-        dim3 grid(nblk(ctx->Wcv, 32), nblk(2 * cap, 512));
-        cv_count_bits_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), S.d_n, ctx->d_cv_count.as<unsigned long long>());
+        // rows per CTA: long enough to amortise the unpacking of the bit-sliced counters, short enough that a small population still spreads out
+        const uint32_t rows_per_cta = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(64, ((2 * cap / ((uint64_t)ctx->n_sm * 4)) + 7) & ~7ull));
+        dim3 grid(nblk(ctx->Wcv, 32), nblk(2 * cap, rows_per_cta));
+        cv_count_bits_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), S.d_n, rows_per_cta, ctx->d_cv_count.as<unsigned long long>());
         GE_TRY(ctx->check_launch("cv_count"));
     }
     const uint64_t nw = cap * ctx->cfg.n_phen;
@@ -507,9 +510,11 @@ static int enqueue_AD(ge_ctx *ctx, int pop) {  // ras_compute_AD :2624-2749
         cv_tables_kernel<<<nblk(ncv, 128), 128, 0, ctx->stream>>>(ctx->cvset(), ctx->d_cv_count.as<unsigned long long>(), S.d_n, ctx->d_a_eff.as<double>(),
                                                                   ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), ctx->d_LA.as<double2>());
         GE_TRY(ctx->check_launch("cv_tables"));
-        genetic_value_lut_kernel<<<ctx->ctrl_grid(nw * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_cv_bitpos.as<uint32_t>(), ctx->d_LA.as<double2>(), S.d_n, cap,
-                                                                              S.A.as<double>(), S.D.as<double>(), S.G.as<double>(), &P.d_ss->err);
-        GE_TRY(ctx->check_launch("genetic_value_lut"));
+        cv_group_tables_kernel<<<nblk((uint64_t)ctx->Wcv * 8 * 256, 256), 256, 0, ctx->stream>>>(ctx->cvset(), ctx->d_LA.as<double2>(), ctx->d_LG.as<double2>());
+        GE_TRY(ctx->check_launch("cv_group_tables"));
+        genetic_value_groups_kernel<<<ctx->ctrl_grid(cap * 32, 256), 256, 0, ctx->stream>>>(ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->d_LG.as<double2>(), S.d_n, cap, S.A.as<double>(),
+                                                                                      S.D.as<double>(), S.G.as<double>(), &P.d_ss->err);
+        GE_TRY(ctx->check_launch("genetic_value_groups"));
     } else {
         genetic_value_kernel<<<ctx->ctrl_grid(nw * 32, 256), 256, 0, ctx->stream>>>(
             ctx->cvset(), S.cv_allele.as<uint32_t>(), ctx->use_root ? S.cv_root.as<uint8_t>() : nullptr, ctx->d_cv_count.as<unsigned long long>(), S.d_n,

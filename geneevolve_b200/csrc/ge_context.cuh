@@ -169,7 +169,11 @@ struct ge_ctx {
     // control kernels, the 6-25 GB copies of a shard 4 (2-3 % faster than 8 or no limit), copies of ~1 GB (config 2) no limit.
     void note_bulk(double bytes) {
         bulk_busy = !serial && bytes > thin_min_bytes;
+#ifdef GE_EXP_THIN_FULL
+        thin_now = bytes >= 30e9 ? GE_EXP_THIN_FULL : GE_EXP_THIN_SHARD;
+#else
         thin_now = bytes >= 30e9 ? thin : std::max(1, thin / 2);
+#endif
     }
     // grid of a grid-stride control kernel: full width, or thin while it shares the GPU with the bulk copy,
     // so that the high-priority control stream displaces only a fraction of the bulk kernel's resident CTAs
@@ -204,7 +208,7 @@ struct ge_ctx {
     uint32_t n_cv_tot = 0, Wcv = 4;
     bool cv_sorted = true;
     bool use_root = false;   // populations with different effect tables: carry the root population of every CV allele
-    Buf d_LA /* double2 [n_cv][3] */, d_cv_bitpos, xo_stash;
+    Buf d_LA /* double2 [n_cv][3] */, d_LG /* double2 [Wcv*8][256]: sums per group of four CVs */, d_cv_bitpos, xo_stash;
     Buf d_cv_word_off, d_cv_word_blk, d_cv_block_off, d_cv_bp, d_cv_chr, d_a_eff, d_d_eff, d_cv_count;
     bool cv_ready = false;
     // scratch

@@ -563,28 +563,35 @@ __global__ void cv_root_propagate_kernel(CvSet cs, const StepState *__restrict__
     }
 }
 
-// allele count per CV over the population (frq numerator, :2647-2663).  A CTA takes 32 word columns x 512 rows:
-// a warp reads 32 consecutive words of one row (128 B), 8 warps stride the rows, every thread keeps the 32 bit
-// counters of its word in registers; shared-memory atomics fold the 8 warps, one 64-bit atomic per CV and CTA.
-__global__ void cv_count_bits_kernel(CvSet cs, const uint32_t *__restrict__ bits, const uint64_t *__restrict__ n_ind, unsigned long long *__restrict__ count) {
+// allele count per CV over the population (frq numerator, :2647-2663).  A CTA takes 32 word columns x rows_per_cta rows:
+// a warp reads 32 consecutive words of one row (128 B), 8 warps stride the rows.  Every thread counts the 32 bit columns of its
+// word in eight bit-sliced planes (plane l holds bit l of all 32 counters: adding a word is a ripple of AND/XOR pairs, 16
+// logic operations instead of 96 shift-mask-adds), unpacks them once at the end, shared-memory atomics fold the 8 warps and
+// one 64-bit atomic per CV and CTA goes to memory.  rows_per_cta <= 8 * 255.
+__global__ void cv_count_bits_kernel(CvSet cs, const uint32_t *__restrict__ bits, const uint64_t *__restrict__ n_ind, uint32_t rows_per_cta, unsigned long long *__restrict__ count) {
     __shared__ unsigned int sh[32][33];
     const uint32_t w = blockIdx.x * 32 + threadIdx.x;
     const uint64_t n_rows = 2 * *n_ind;
-    const uint64_t r0 = (uint64_t)blockIdx.y * 512, r1 = min(r0 + 512, n_rows);
+    const uint64_t r0 = (uint64_t)blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, n_rows);
     if (r0 >= n_rows) return;
     for (int q = threadIdx.y; q < 32; q += 8) sh[q][threadIdx.x] = 0;
     __syncthreads();
-    unsigned int cnt[32];
+    uint32_t plane[8];
 #pragma unroll
-    for (int b = 0; b < 32; b++) cnt[b] = 0;
+    for (int l = 0; l < 8; l++) plane[l] = 0;
     if (w < cs.Wcv)
         for (uint64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-            uint32_t v = bits[r * cs.Wcv + w];
+            uint32_t x = bits[r * cs.Wcv + w];
 #pragma unroll
-            for (int b = 0; b < 32; b++) cnt[b] += (v >> b) & 1u;
+            for (int l = 0; l < 8; l++) { const uint32_t carry = plane[l] & x; plane[l] ^= x; x = carry; }
         }
 #pragma unroll
-    for (int b = 0; b < 32; b++) if (cnt[b]) atomicAdd(&sh[threadIdx.x][b], cnt[b]);
+    for (int b = 0; b < 32; b++) {
+        unsigned int c = 0;
+#pragma unroll
+        for (int l = 0; l < 8; l++) c |= ((plane[l] >> b) & 1u) << l;
+        if (c) atomicAdd(&sh[threadIdx.x][b], c);
+    }
     __syncthreads();
     if (w < cs.Wcv) {
         uint32_t blk = cs.word_blk[w];
@@ -660,35 +667,50 @@ __global__ void cv_tables_kernel(CvSet cs, const unsigned long long *__restrict_
         LAD[k * 3 + t] = make_double2(((double)t - 2 * p) * alpha, ct * d);
     }
 }
-// Lanes stride the CVs of the phenotype as one flat list (bitpos[k] = position of CV k in the bit row, LAD[k][t] =
-// {LA, LD} in one 16-byte load), so there is no per-chromosome bookkeeping and every lane has the same trip count.
-__global__ void genetic_value_lut_kernel(CvSet cs, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ bitpos, const double2 *__restrict__ LAD,
-                                         const uint64_t *__restrict__ n_ind, uint64_t stride /* column stride = capacity */, double *__restrict__ A, double *__restrict__ D,
-                                         double *__restrict__ Gv, uint32_t *__restrict__ err) {
+// The per-individual sums take four CVs at a time: a nibble of the two allele words of an individual indexes LG[group][256], the sum of
+// the four {LA, LD} terms for that combination of genotypes (CVs a block does not have contribute nothing, their bits are 0 in every
+// row).  One 16-byte load and two additions per four CVs; the first version — one table load per CV, located through a bit-position
+// list — ran 298 M warp instructions per 250k individuals (ncu launch lists of round 2).
+__global__ void cv_group_tables_kernel(CvSet cs, const double2 *__restrict__ LAD, double2 *__restrict__ LG) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cs.Wcv * 8u * 256u) return;
+    const uint32_t idx = t & 255u, grp = t >> 8, w = grp >> 3, q = grp & 7u, b = cs.word_blk[w];
+    double2 s = make_double2(0.0, 0.0);
+    if (b != 0xFFFFFFFFu) {
+        const uint32_t k0 = cs.block_off[b] + (w - cs.word_off[b]) * 32u + q * 4u, k1 = cs.block_off[b + 1];
+        for (uint32_t j = 0; j < 4u && k0 + j < k1; j++) {
+            const uint32_t g = ((idx >> j) & 1u) + ((idx >> (4 + j)) & 1u);
+            const double2 v = LAD[(uint64_t)(k0 + j) * 3 + g];
+            s.x += v.x; s.y += v.y;
+        }
+    }
+    LG[t] = s;
+}
+// one warp per individual; lanes stride the nibbles of the phenotype's words (its blocks are consecutive words of the row)
+__global__ void __launch_bounds__(256) genetic_value_groups_kernel(CvSet cs, const uint32_t *__restrict__ bits, const double2 *__restrict__ LG, const uint64_t *__restrict__ n_ind,
+                                                                   uint64_t stride /* column stride = capacity */, double *__restrict__ A, double *__restrict__ D, double *__restrict__ Gv,
+                                                                   uint32_t *__restrict__ err) {
     const uint64_t n = *n_ind;
     if (n == 0) return;
     const int lane = threadIdx.x & 31;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < n * cs.n_phen; wid += n_warps) {
-        uint64_t fq;
-        uint32_t ir;
-        divmod_idx(wid, (uint32_t)n, fq, ir);   // individuals are indexed with 32 bits throughout (parent indices are uint32)
-        const uint64_t i = ir;
-        const int f = (int)fq;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
         const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
-        const uint32_t k1 = cs.block_off[(f + 1) * cs.n_chr];
-        double Ac = 0, Dc = 0;
-        for (uint32_t k = cs.block_off[f * cs.n_chr] + lane; k < k1; k += 32) {
-            const uint32_t bp = __ldg(bitpos + k), w = bp >> 5, b = bp & 31u;
-            const unsigned t = ((al0[w] >> b) & 1u) + ((al1[w] >> b) & 1u);
-            const double2 v = __ldg(LAD + k * 3 + t);
-            Ac += v.x;
-            Dc += v.y;
-        }
-        for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
-        if (lane == 0) {
-            A[(uint64_t)f * stride + i] = Ac; D[(uint64_t)f * stride + i] = Dc; Gv[(uint64_t)f * stride + i] = Ac + Dc;
-            if (isnan(Ac) || isnan(Dc)) atomicOr(err, (uint32_t)SE_NAN);
+        for (int f = 0; f < cs.n_phen; f++) {
+            const uint32_t g1 = 8 * cs.word_off[(f + 1) * cs.n_chr];
+            double Ac = 0, Dc = 0;
+            for (uint32_t g = 8 * cs.word_off[f * cs.n_chr] + lane; g < g1; g += 32) {
+                const uint32_t w = g >> 3, sh = (g & 7u) * 4u;
+                const uint32_t idx = ((al0[w] >> sh) & 15u) | (((al1[w] >> sh) & 15u) << 4);
+                const double2 v = __ldg(LG + (uint64_t)g * 256 + idx);
+                Ac += v.x;
+                Dc += v.y;
+            }
+            for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
+            if (lane == 0) {
+                A[(uint64_t)f * stride + i] = Ac; D[(uint64_t)f * stride + i] = Dc; Gv[(uint64_t)f * stride + i] = Ac + Dc;
+                if (isnan(Ac) || isnan(Dc)) atomicOr(err, (uint32_t)SE_NAN);
+            }
         }
     }
 }

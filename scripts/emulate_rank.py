@@ -5,11 +5,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from geneevolve_b200 import capi, workloads, dist as gdist
 
 world, steps = int(sys.argv[1]), int(sys.argv[2])
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # e.g. 1 = GE_FLAG_SERIAL: the copy alone, after the control chain
 cfg = workloads.make_workload("config3_100k_x_1M")
 mine = gdist.assign_locus_ranges(cfg["n_loci"], world)[world // 2]
 N = cfg["n"]
 eng = capi.Engine(n_pop=1, n_chr=len(mine), n_phen=1, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX, seed=12345,
-                  capacity=int(N * 1.03) + 1024, rank=0, world_size=world)
+                  capacity=int(N * 1.03) + 1024, rank=0, world_size=world, flags=flags)
 workloads.configure_engine(eng, cfg, pieces=mine)
 eng.set_allreduce(lambda ptr, count, stream: None)
 eng.init_generation0()
