@@ -356,7 +356,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3_100k_x_1M")
-    ap.add_argument("--n", type=int, default=None, help="override individuals per generation (debug)")
+    ap.add_argument("--n", "--individuals", dest="n", type=int, default=None,
+                    help="override individuals per generation (debug; torch.distributed.run reads a bare --n as one of its own options: use --individuals there)")
     ap.add_argument("--loci", type=int, default=None, help="override loci (debug)")
     ap.add_argument("--ref-sample", type=int, default=1500, help="individuals in the bounded reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -208,6 +208,11 @@ class Engine:
         self._allreduce_cb = ALLREDUCE_FN(thunk)  # keep alive
         self._call("set_allreduce", self.ctx, self._allreduce_cb, None)
 
+    def set_allreduce_nccl(self, comm, nccl_all_reduce):
+        """comm: ncclComm_t of this rank (integer address); nccl_all_reduce: address of ncclAllReduce in the NCCL library that
+        made it (dist.NcclComm provides both).  The library then issues the exchange itself and sharded generations replay as graphs."""
+        self._call("set_allreduce_nccl", self.ctx, C.c_void_p(comm), C.c_void_p(nccl_all_reduce))
+
     def set_gamma(self, gamma):
         g = _arr(gamma, np.float64)
         self._call("set_gamma", self.ctx, _ptr(g, _f64p))
@@ -432,6 +437,11 @@ class Engine:
     def launch_count(self):
         n = C.c_uint64()
         self._call("get_launch_count", self.ctx, C.byref(n))
+        return n.value
+
+    def graph_replays(self):
+        n = C.c_uint64()
+        self._call("get_graph_replays", self.ctx, C.byref(n))
         return n.value
 
     def timer_start(self):

@@ -482,7 +482,22 @@ int ge_set_chromosome_ids(ge_ctx *ctx, const int32_t *ids) {
     for (int k = 0; k < ctx->cfg.n_chr; k++) { if (ids[k] < 0 || ids[k] > 32767) return fail(GE_ERR_INVALID, "bad chromosome id"); ctx->chr_ids[k] = (uint32_t)ids[k]; }
     return GE_OK;
 }
-int ge_set_allreduce(ge_ctx *ctx, ge_allreduce_fn fn, void *user) { CHECK_CTX(ctx); ctx->allreduce = fn; ctx->allreduce_user = user; return GE_OK; }
+int ge_set_allreduce(ge_ctx *ctx, ge_allreduce_fn fn, void *user) {
+    CHECK_CTX(ctx);
+    ctx->allreduce = fn; ctx->allreduce_user = user;
+    ctx->nccl_all_reduce = nullptr; ctx->nccl_comm = nullptr;
+    ctx->graph_epoch++;
+    return GE_OK;
+}
+int ge_set_allreduce_nccl(ge_ctx *ctx, void *nccl_comm, void *nccl_all_reduce) {
+    CHECK_CTX(ctx);
+    if ((nccl_comm == nullptr) != (nccl_all_reduce == nullptr)) return fail(GE_ERR_INVALID, "ge_set_allreduce_nccl: communicator and entry point go together");
+    ctx->nccl_comm = nccl_comm;
+    ctx->nccl_all_reduce = reinterpret_cast<ge_ctx::nccl_all_reduce_fn>(nccl_all_reduce);
+    ctx->allreduce = nullptr; ctx->allreduce_user = nullptr;
+    ctx->graph_epoch++;
+    return GE_OK;
+}
 int ge_set_gamma(ge_ctx *ctx, const double *g) { CHECK_CTX(ctx); ctx->gamma.assign(g, g + ctx->cfg.n_phen); return GE_OK; }
 
 // ---------------- per-method entry points ----------------
@@ -521,7 +536,7 @@ static int enqueue_AD(ge_ctx *ctx, int pop) {  // ras_compute_AD :2624-2749
             ctx->d_a_eff.as<double>(), ctx->d_d_eff.as<double>(), P.d_vd_zero.as<uint8_t>(), cap, S.A.as<double>(), S.D.as<double>(), S.G.as<double>(), &P.d_ss->err);
         GE_TRY(ctx->check_launch("genetic_value"));
     }
-    if (ctx->allreduce) {
+    if (ctx->sharded()) {
         // sharded contexts hold partial sums over their own loci: sum A, D, G over the ranks.  The columns go whole (stride =
         // capacity; rows beyond the population hold stale finite values nobody reads), so the count does not depend on a device-side size.
         size_t nb = (size_t)cap * ctx->cfg.n_phen * 8;
@@ -530,8 +545,13 @@ static int enqueue_AD(ge_ctx *ctx, int pop) {  // ras_compute_AD :2624-2749
         CUDA_TRY(cudaMemcpyAsync(sc, S.A.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(sc + nb, S.D.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(sc + 2 * nb, S.G.p, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-        int rc = ctx->allreduce(ctx->allreduce_user, reinterpret_cast<double *>(sc), 3 * nb / 8, (void *)ctx->stream);
-        if (rc != 0) return fail(GE_ERR_INVALID, "allreduce hook failed");
+        if (ctx->nccl_all_reduce) {   // ncclDouble = 8, ncclSum = 0 (nccl.h); in place, stream-ordered, capturable
+            const int rc = ctx->nccl_all_reduce(sc, sc, 3 * nb / 8, 8, 0, ctx->nccl_comm, ctx->stream);
+            if (rc != 0) return fail(GE_ERR_INVALID, "ncclAllReduce failed with ncclResult_t " + std::to_string(rc));
+        } else {
+            const int rc = ctx->allreduce(ctx->allreduce_user, reinterpret_cast<double *>(sc), 3 * nb / 8, (void *)ctx->stream);
+            if (rc != 0) return fail(GE_ERR_INVALID, "allreduce hook failed");
+        }
         CUDA_TRY(cudaMemcpyAsync(S.A.p, sc, nb, cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(S.D.p, sc + nb, nb, cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(S.G.p, sc + 2 * nb, nb, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1259,7 +1279,7 @@ static int enqueue_generation(ge_ctx *ctx, int gen, const ge_gen_params *gp, con
 // update and one read-back per generation.  The bulk-stream work (bit-packed copy, segment plan + gather) stays outside the graph —
 // it overlaps the NEXT generation's chain, which a graph launched behind it could not — tied in by external event nodes.
 static bool graphable(ge_ctx *ctx, const double *mig, const ge_draws *dr) {
-    if (!ctx->use_graph || dr || mig || ctx->cfg.rng_mode != GE_RNG_PHILOX || ctx->phase_timing || ctx->allreduce || ctx->serial || ctx->cfg.n_pop != 1) return false;
+    if (!ctx->use_graph || dr || mig || ctx->cfg.rng_mode != GE_RNG_PHILOX || ctx->phase_timing || ctx->allreduce /* a host hook cannot be captured; ge_set_allreduce_nccl can */ || ctx->serial || ctx->cfg.n_pop != 1) return false;
     for (double g : ctx->gamma) if (g != 0) return false;
     if (ctx->segs() && (ctx->cfg.seg_capacity == 0 || ctx->cv_from_segments)) return false;   // the host sizes the segment buffer between the passes
     for (PopDev &P : ctx->pop) if (P.has_mut || P.st[P.cur].has_hm || P.st[P.cur].rowmap) return false;   // the mutation pass waits for the bulk copy mid-chain
@@ -1333,7 +1353,7 @@ static int step_with_graph(ge_ctx *ctx, int gen, const ge_gen_params *gp, int &r
             CUDA_TRY(cudaGraphNodeGetType(nd, &ty));
             if (ty != cudaGraphNodeTypeKernel) continue;
             cudaKernelNodeParams kp{};
-            CUDA_TRY(cudaGraphKernelNodeGetParams(nd, &kp));
+            if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) { cudaGetLastError(); continue; }   // another library's kernel (the NCCL collective): not ours to patch
             if (kp.func != (void *)step_begin_kernel) continue;
             StepState *target = *static_cast<StepState **>(kp.kernelParams[0]);
             for (int p = 0; p < np; p++) if (ctx->pop[p].d_ss == target) G.begin_nodes[p] = nd;
@@ -1352,6 +1372,7 @@ static int step_with_graph(ge_ctx *ctx, int gen, const ge_gen_params *gp, int &r
             reproduced = p + 1;
         }
         ctx->launches += G.launches;
+        ctx->graph_replays++;
     }
     CUDA_TRY(cudaGraphLaunch(G.exec, ctx->stream));
     for (auto &fn : G.bulk) GE_TRY(fn());
@@ -1628,6 +1649,7 @@ int ge_get_kernel_time(ge_ctx *ctx, int k, double *ms, uint64_t *launches, uint6
 }
 int ge_reset_kernel_times(ge_ctx *ctx) { CHECK_CTX(ctx); GE_TRY(seg_finish_all(ctx)); ctx->resolve_events(); for (auto &k : ctx->kstat) k = KernelStat(); ctx->launches = 0; return GE_OK; }
 int ge_get_launch_count(ge_ctx *ctx, uint64_t *n) { CHECK_CTX(ctx); *n = ctx->launches; return GE_OK; }
+int ge_get_graph_replays(ge_ctx *ctx, uint64_t *n) { CHECK_CTX(ctx); *n = ctx->graph_replays; return GE_OK; }
 int ge_synchronize(ge_ctx *ctx) {
     CHECK_CTX(ctx);
     CUDA_TRY(cudaSetDevice(ctx->cfg.device));

@@ -193,6 +193,11 @@ struct ge_ctx {
     bool mig_pending[2] = {false, false};
     ge_allreduce_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
+    // ge_set_allreduce_nccl: ncclAllReduce(sendbuff, recvbuff, count, ncclDataType_t, ncclRedOp_t, comm, stream) called directly
+    typedef int (*nccl_all_reduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    nccl_all_reduce_fn nccl_all_reduce = nullptr;
+    void *nccl_comm = nullptr;
+    bool sharded() const { return allreduce || nccl_all_reduce; }
     Stream rng;
     // genome layout
     std::vector<uint32_t> chr_word_off, chr_nloci, locus_off;
@@ -292,7 +297,7 @@ struct ge_ctx {
         }
         ~PhaseTimer() { if (p.a) { cudaEventRecord(p.b, c->stream); c->ev_pending.push_back(p); } }
     };
-    uint64_t launches = 0;
+    uint64_t launches = 0, graph_replays = 0;
     size_t mem_now = 0, mem_peak = 0;
 
     bool bits() const { return cfg.representation & GE_REP_BITS; }

@@ -467,7 +467,7 @@ __global__ void cv_propagate_bits_kernel(CvSet cs, const StepState *__restrict__
 // on" as ONE toggle bit per phenotype block (idx = lower_bound over the block's positions), and the copy mask of a word is the
 // running XOR of the toggle bits before it in its block: a prefix-XOR inside the word (five shifts) and the parity of the block's
 // earlier words.
-__global__ void __launch_bounds__(256) cv_propagate_rows_kernel(CvSet cs, const StepState *__restrict__ ss, const uint32_t *__restrict__ par_bits, uint32_t *__restrict__ off_bits,
+__global__ void __launch_bounds__(256, 6) cv_propagate_rows_kernel(CvSet cs, const StepState *__restrict__ ss, const uint32_t *__restrict__ par_bits, uint32_t *__restrict__ off_bits,
                                                                 const uint32_t *__restrict__ father, const uint32_t *__restrict__ mother,
                                                                 const uint64_t *__restrict__ xo_off, const uint32_t *__restrict__ xo_bp,
                                                                 const uint8_t *__restrict__ start_hap) {
@@ -483,18 +483,18 @@ __global__ void __launch_bounds__(256) cv_propagate_rows_kernel(CvSet cs, const 
         s_chr[w] = b == 0xFFFFFFFFu ? b : b % C;
         s_first[w] = b == 0xFFFFFFFFu ? 0u : cs.word_off[b];
     }
+    for (uint32_t w = lane; w < Wcv; w += 32) T[w] = 0u;
     __syncthreads();
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += n_warps) {
         const uint64_t i = row >> 1;
         const uint32_t gam = (uint32_t)(row & 1);
-        for (uint32_t w = lane; w < Wcv; w += 32) T[w] = 0u;
-        __syncwarp();
+        const uint64_t slot0 = i * C * 2 + gam;     // slot of chromosome c: slot0 + 2c
         for (uint32_t c0 = 0; c0 < C; c0 += 32) {   // the crossovers of up to 32 chromosomes of this gamete, as one flat list
             const uint32_t c = c0 + lane;
             uint64_t e0 = 0;
             uint32_t cnt = 0;
-            if (c < C) { const uint64_t slot = (i * C + c) * 2 + gam; e0 = xo_off[slot]; cnt = (uint32_t)(xo_off[slot + 1] - e0); }
+            if (c < C) { const uint64_t slot = slot0 + 2 * c; e0 = xo_off[slot]; cnt = (uint32_t)(xo_off[slot + 1] - e0); }
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
@@ -531,14 +531,16 @@ __global__ void __launch_bounds__(256) cv_propagate_rows_kernel(CvSet cs, const 
             if (c != 0xFFFFFFFFu) {
                 uint32_t m = T[w];
                 m ^= m << 1; m ^= m << 2; m ^= m << 4; m ^= m << 8; m ^= m << 16;
-                uint32_t par = start_hap[(i * C + c) * 2 + gam] & 1u;
+                uint32_t par = start_hap[slot0 + 2 * c] & 1u;
                 for (uint32_t w2 = s_first[w]; w2 < w; w2++) par ^= (uint32_t)__popc(T[w2]) & 1u;
                 if (par) m = ~m;
                 v = (pr[w] & ~m) | (pr[Wcv + w] & m);
             }
             off_bits[row * Wcv + w] = v;
         }
-        __syncwarp();   // the toggle words are cleared for the next row
+        __syncwarp();   // every lane has read what it needs of the toggle words: cleared for the next row
+        for (uint32_t w = lane; w < Wcv; w += 32) T[w] = 0u;
+        __syncwarp();
     }
 }
 
@@ -686,7 +688,8 @@ __global__ void cv_group_tables_kernel(CvSet cs, const double2 *__restrict__ LAD
     }
     LG[t] = s;
 }
-// one warp per individual; lanes stride the nibbles of the phenotype's words (its blocks are consecutive words of the row)
+// one warp per individual; lanes stride the half words of the phenotype (its blocks are consecutive words of the row): two allele loads
+// and four table loads per lane and round
 __global__ void __launch_bounds__(256) genetic_value_groups_kernel(CvSet cs, const uint32_t *__restrict__ bits, const double2 *__restrict__ LG, const uint64_t *__restrict__ n_ind,
                                                                    uint64_t stride /* column stride = capacity */, double *__restrict__ A, double *__restrict__ D, double *__restrict__ Gv,
                                                                    uint32_t *__restrict__ err) {
@@ -697,14 +700,18 @@ __global__ void __launch_bounds__(256) genetic_value_groups_kernel(CvSet cs, con
     for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
         const uint32_t *al0 = bits + (i * 2) * (uint64_t)cs.Wcv, *al1 = al0 + cs.Wcv;
         for (int f = 0; f < cs.n_phen; f++) {
-            const uint32_t g1 = 8 * cs.word_off[(f + 1) * cs.n_chr];
+            const uint32_t h1 = 2 * cs.word_off[(f + 1) * cs.n_chr];
             double Ac = 0, Dc = 0;
-            for (uint32_t g = 8 * cs.word_off[f * cs.n_chr] + lane; g < g1; g += 32) {
-                const uint32_t w = g >> 3, sh = (g & 7u) * 4u;
-                const uint32_t idx = ((al0[w] >> sh) & 15u) | (((al1[w] >> sh) & 15u) << 4);
-                const double2 v = __ldg(LG + (uint64_t)g * 256 + idx);
-                Ac += v.x;
-                Dc += v.y;
+            for (uint32_t h = 2 * cs.word_off[f * cs.n_chr] + lane; h < h1; h += 32) {
+                const uint32_t w = h >> 1, sh = (h & 1u) * 16u;
+                const uint32_t a0 = al0[w] >> sh, a1 = (al1[w] >> sh) << 4;
+                const double2 *G = LG + (uint64_t)h * 1024;   // four groups of 256 entries
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double2 v = __ldg(G + q * 256 + (((a0 >> (4 * q)) & 15u) | ((a1 >> (4 * q)) & 240u)));
+                    Ac += v.x;
+                    Dc += v.y;
+                }
             }
             for (int o = 16; o; o >>= 1) { Ac += __shfl_xor_sync(0xffffffffu, Ac, o); Dc += __shfl_xor_sync(0xffffffffu, Dc, o); }
             if (lane == 0) {

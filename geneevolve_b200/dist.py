@@ -71,6 +71,44 @@ def cuda_allreduce_hook(device, group=None):
     return hook
 
 
+class NcclComm:
+    """This rank's own NCCL communicator, made with the NCCL library torch already loaded (ncclGetUniqueId on rank 0, the id
+    broadcast through the torch.distributed group, ncclCommInitRank on every rank).  Engine.set_allreduce_nccl(comm.handle,
+    comm.all_reduce_address) hands it to the CUDA library, which then calls ncclAllReduce itself: no Python, no host code at all in
+    the generation loop, and the sharded control chain is captured into a CUDA graph with the collective inside."""
+
+    class _UniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_ubyte * 128)]
+
+    def __init__(self, rank, world, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.lib = ctypes.CDLL("libnccl.so.2")   # the soname torch's CUDA library is linked against: already in the process
+        self.lib.ncclGetErrorString.restype = ctypes.c_char_p
+        uid = self._UniqueId()
+        if rank == 0:
+            self._check(self.lib.ncclGetUniqueId(ctypes.byref(uid)), "ncclGetUniqueId")
+        box = [ctypes.string_at(ctypes.byref(uid), 128) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ctypes.memmove(ctypes.byref(uid), box[0], 128)
+        torch.cuda.set_device(device)
+        comm = ctypes.c_void_p()
+        self.lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, self._UniqueId, ctypes.c_int]
+        self._check(self.lib.ncclCommInitRank(ctypes.byref(comm), world, uid, rank), "ncclCommInitRank")
+        self.handle = comm.value
+        self.all_reduce_address = ctypes.cast(self.lib.ncclAllReduce, ctypes.c_void_p).value
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {self.lib.ncclGetErrorString(rc).decode()}")
+
+    def close(self):
+        if self.handle:
+            self.lib.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+            self.lib.ncclCommDestroy(ctypes.c_void_p(self.handle))
+            self.handle = None
+
+
 def host_allreduce_hook(group=None):
     """Same for a host buffer (gloo) — used by the CPU tests of the sharding logic."""
     import torch
@@ -113,7 +151,8 @@ def measure_sharded(name, args, steps, warmup, rank, world, local, e2e=True, n=N
         workloads.configure_engine_multipop(eng, cfg, pieces=pieces)
     else:
         workloads.configure_engine(eng, cfg, pieces=pieces)
-    eng.set_allreduce(cuda_allreduce_hook(local))
+    comm = NcclComm(rank, world, local)
+    eng.set_allreduce_nccl(comm.handle, comm.all_reduce_address)
     eng.init_generation0()
     gp = [capi.gen_params(q, cfg["mat_cor"], "p", "logit", 0.0, 1.0) for q in pops]
     mig = cfg.get("migration")
@@ -173,7 +212,9 @@ def measure_sharded(name, args, steps, warmup, rank, world, local, e2e=True, n=N
     r["achieved"] = float(kb[0].item()) / world  # mean per-GPU achieved GB/s
     r["k_ms_slowest"] = float(kmax[1].item())
     r["device_memory_gb"] = eng.device_memory_bytes() / 1e9
+    r["graph_replays"] = eng.graph_replays()
     eng.close()
+    comm.close()
     return r
 
 
@@ -221,7 +262,8 @@ def bench_sharded(args, METRIC, UNIT):
                        "parallelism": ("chromosome-sharded x%d (founder segments)" if segs else "locus-range sharded x%d (every rank: all individuals, 1/N of the 16-byte chunks of the rows)") % world,
                        "device_memory_gb_rank0": r["device_memory_gb"],
                        "representation": "founder segments (loci nominal; steps are generations %d..%d)" % (args.warmup + 1, args.warmup + args.steps) if segs else "bit-packed haplotypes",
-                       "pieces_rank0": r["pieces"], "collective": "all-reduce of 3 * n_phen * capacity doubles per population and generation (NCCL)",
+                       "pieces_rank0": r["pieces"], "collective": "all-reduce of 3 * n_phen * capacity doubles per population and generation (ncclAllReduce issued by the CUDA library on its control stream, inside the captured generation graph when the chain is graphable)",
+                       "graph_replays_rank0": r["graph_replays"],
                        "l2": ("inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (sum(pops) * M / 4 / 1e9 / world)) if not segs else
                              "inputs larger than L2 (founder-segment lists, %.1f GB moved per step per GPU)" % (r["k_bytes"] / max(r["k_n"], 1) * 2 / 1e9)},
             "e2e": {"value": r["work2"] / (r["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,

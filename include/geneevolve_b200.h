@@ -178,6 +178,11 @@ int ge_set_chromosome_ids(ge_ctx *ctx, const int32_t *global_ids /* [n_chr] */);
  * The Python host wires torch.distributed/NCCL (geneevolve_b200/dist.py); a C++ host can wire ncclAllReduce. */
 typedef int (*ge_allreduce_fn)(void *user, double *dev_buf, uint64_t count, void *cuda_stream);
 int ge_set_allreduce(ge_ctx *ctx, ge_allreduce_fn fn, void *user);
+/* The same exchange issued by the library itself: `nccl_comm` is this rank's ncclComm_t, `nccl_all_reduce` the address of
+ * ncclAllReduce in the NCCL library the communicator came from (the library does not link NCCL: the host that created the
+ * communicator hands the entry point over).  No host code runs per generation, so a sharded generation replays as a
+ * captured CUDA graph like an unsharded one — NCCL collectives are capturable.  Replaces a ge_set_allreduce hook. */
+int ge_set_allreduce_nccl(ge_ctx *ctx, void *nccl_comm, void *nccl_all_reduce);
 
 /* ---- generation 0: Simulation::ras_init_generation0 (:529-679) + ras_initial_human_gen0 (:3000-3072) ----
  * draws0[pop] (GE_RNG_REPLAY) carries sex, e_raw, common for the founders; NULL in GE_RNG_PHILOX mode. */
@@ -307,6 +312,7 @@ int ge_set_profiling(ge_ctx *ctx, int level);
 int ge_get_kernel_time(ge_ctx *ctx, int kernel, double *total_ms, uint64_t *launches, uint64_t *algorithmic_bytes);
 int ge_reset_kernel_times(ge_ctx *ctx);
 int ge_get_launch_count(ge_ctx *ctx, uint64_t *launches);   /* every kernel this context launched */
+int ge_get_graph_replays(ge_ctx *ctx, uint64_t *replays);   /* generations whose control chain was replayed from a captured CUDA graph */
 int ge_synchronize(ge_ctx *ctx);
 /* CUDA events on the library's stream around a caller-defined region (everything queued in between) */
 int ge_timer_start(ge_ctx *ctx);

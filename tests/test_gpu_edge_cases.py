@@ -147,6 +147,25 @@ def test_hundreds_of_crossovers_per_gamete(cuda_lib):
     run_pair(cuda_lib, case, [(6, xo), (5, xo)], rep=capi.GE_REP_BITS)
 
 
+@pytest.mark.parametrize("order", ["sorted", "reversed", "shuffled"])
+def test_causal_variant_blocks_of_several_words_in_any_row_order(cuda_lib, order):
+    """70 and 40 causal variants on two chromosomes (blocks of 3 and 2 words of the CV bit planes), listed in ascending
+    position (the warp-per-row kernel with its prefix-XOR masks), reversed and shuffled (cv.info rows need not be sorted:
+    the thread-per-word kernel without binary search), many crossovers per gamete so that words see several flips."""
+    case = Case(31, [300, 40], n_founders=10, map_rows=12, n_cv=70)
+    if order != "sorted":
+        for cv in case.cv:
+            k = len(cv["bp"])
+            perm = np.arange(k)[::-1] if order == "reversed" else np.random.default_rng(5).permutation(k)
+            cv["bp"], cv["a"], cv["d"], cv["val"] = cv["bp"][perm], cv["a"][perm], cv["d"][perm], cv["val"][:, perm]
+    lo, hi = 1000, 1000 + 64 * 11
+
+    def xo(slot, c):
+        r = np.random.default_rng([slot, c])
+        return np.sort(r.integers(lo - 5, hi + 5, size=int(r.integers(0, 9))))
+    run_pair(cuda_lib, case, [(14, xo), (9, xo), (11, xo)])
+
+
 @pytest.mark.parametrize("flags", [0, capi.GE_FLAG_SEG_WIDE_PARTS, capi.GE_FLAG_SEG_VERBATIM])
 def test_segment_kernels_long_lists_and_many_crossovers(cuda_lib, flags):
     """The kernels of the segment path (seg_plan_kernel + seg_gather_kernel on packed and on 16-byte parts, and the reference's loop
