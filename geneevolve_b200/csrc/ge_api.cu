@@ -321,6 +321,8 @@ int ge_create(const ge_config *cfg, ge_ctx **out) {
         int prio_lo = 0, prio_hi = 0;
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUDA_TRY(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->xo_ctas_per_sm, sample_xo_kernel, 128, 0));   // one resident wave of the lane-refilling sampler
+        c->xo_ctas_per_sm = std::max(1, c->xo_ctas_per_sm);
         if (!c->stream) CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
         if (!c->bulk) CUDA_TRY(cudaStreamCreateWithPriority(&c->bulk, cudaStreamNonBlocking, prio_lo));
         CUDA_TRY(cudaEventCreate(&c->ev0)); CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -1100,7 +1102,7 @@ static int enqueue_reproduce(ge_ctx *ctx, int pop, const ge_draws *dr) {  // rep
         P.have_couple_of = true;
         // crossovers: count + stash, scan, place
         // (its warps refill their lanes from a chunk of slots: about one resident wave, so that the chunks are long)
-        sample_xo_kernel<<<std::min<unsigned>(ctx->ctrl_grid(slots, 128), (unsigned)ctx->n_sm * 12u), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ss, C, pop, P.cnt32.as<uint32_t>(), D.start_hap.as<uint8_t>(), ctx->xo_stash.as<uint32_t>());
+        sample_xo_kernel<<<std::min<unsigned>(ctx->ctrl_grid(slots, 128), (unsigned)(ctx->n_sm * ctx->xo_ctas_per_sm)), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ss, C, pop, P.cnt32.as<uint32_t>(), D.start_hap.as<uint8_t>(), ctx->xo_stash.as<uint32_t>());
         GE_TRY(ctx->check_launch("sample_xo"));
         GE_TRY(ctx->scan(st, P.cnt32.as<uint32_t>(), devn(&ss->n_off, (uint64_t)C * 2), slots, D.xo_off.as<uint64_t>(), XoTotal{ss, (uint64_t)C * 2, P.dcur}));
         xo_place_kernel<<<ctx->ctrl_grid(slots, 128), 128, 0, st>>>(ctx->rng, ctx->rmap(P), ctx->genome(), ss, C, pop, D.xo_off.as<uint64_t>(), ctx->xo_stash.as<uint32_t>(),

@@ -225,6 +225,7 @@ struct ge_ctx {
     struct TmpScope { ge_ctx *c; explicit TmpScope(ge_ctx *ctx) : c(ctx) { c->tmp_depth++; } ~TmpScope() { c->tmp_depth--; } };
     void buffers_moved() { if (tmp_depth == 0) graph_epoch++; }
     int n_sm = 148;
+    int xo_ctas_per_sm = 10;   // resident CTAs of sample_xo_kernel per SM (occupancy query at creation)
     unsigned prop_threads = 256;   // threads of a propagate_bits_kernel CTA (one offspring): by row length, build_genome
     // stats
     bool profiling = false;        // CUDA events around the dominant kernel (propagate_bits / the segment passes) on its own stream

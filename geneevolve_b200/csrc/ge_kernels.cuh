@@ -1048,16 +1048,28 @@ struct MapDev {
 // first row k >= j with T[k+1] < v, or -1.  T is non-increasing, so {k : T[k+1] < v} is an up-set with minimum k_g(v) and the
 // answer is max(j, k_g).  k_g lies between the index entries of v's bucket; one bucket of slack on either side absorbs
 // the rounding of the bucket number, and the binary search over that range returns exactly what a search over [0, R) would.
-__device__ __forceinline__ long long next_success(const MapDev &m, int c, const double *T, uint32_t R, uint32_t j, double v) {
-    if (j >= R || !(T[R] < v)) return -1;
-    const uint32_t *vb = m.vb + m.vb_off[c];
-    const uint32_t B = m.vb_off[c + 1] - m.vb_off[c] - 1;
-    uint32_t b = (uint32_t)fmin((1.0 - v) * m.vb_scale[c], (double)(B - 1));
-    uint32_t lo = __ldg(vb + (b > 0 ? b - 1 : 0)), hi = __ldg(vb + min(b + 2, B));
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (T[mid + 1] < v) hi = mid; else lo = mid + 1; }
+// (the constants of the chromosome come in registers: the sampler is bound by its load instructions, profiles/README.md r2r)
+struct ChrTable { const double *T; const uint32_t *vb; double T_last, vb_scale; uint32_t R, B; };
+__device__ __forceinline__ ChrTable chr_table(const MapDev &m, uint32_t c) {
+    ChrTable t;
+    const uint32_t r0 = m.row_off[c], v0 = m.vb_off[c];
+    t.R = m.row_off[c + 1] - r0;
+    t.T = m.T + r0 + c;
+    t.T_last = t.T[t.R];
+    t.vb = m.vb + v0;
+    t.B = m.vb_off[c + 1] - v0 - 1;
+    t.vb_scale = m.vb_scale[c];
+    return t;
+}
+__device__ __forceinline__ long long next_success(const ChrTable &t, uint32_t j, double v) {
+    if (j >= t.R || !(t.T_last < v)) return -1;
+    const uint32_t b = (uint32_t)fmin((1.0 - v) * t.vb_scale, (double)(t.B - 1));
+    uint32_t lo = __ldg(t.vb + (b > 0 ? b - 1 : 0)), hi = __ldg(t.vb + min(b + 2, t.B));
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(t.T + mid + 1) < v) hi = mid; else lo = mid + 1; }
     if (lo < j) lo = j;
     return (long long)lo;
 }
+__device__ __forceinline__ long long next_success(const MapDev &m, int c, const double *, uint32_t, uint32_t j, double v) { return next_success(chr_table(m, (uint32_t)c), j, v); }
 // Counts the crossovers of every slot, writes start_hap and stashes the first XO_STASH positions at a fixed stride; after
 // the scan, xo_place_kernel moves the stash into the CSR (re-drawing only the rare longer lists) and converts positions to
 // locus indices in the same sweep.
@@ -1082,14 +1094,16 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, const StepState *__restric
         const uint64_t end = min(c0 + chunk, n_slots);
         uint64_t next = c0 + 32, slot = c0 + lane, i = 0;
         bool have = slot < end, fresh = have;
-        uint32_t c = 0, r0 = 0, R = 0, j = 0, blk = 0, n = 0, key = 0;
-        const double *T = nullptr;
+        uint32_t c = 0, j = 0, blk = 0, n = 0, key = 0, bp_dist = 0;
+        const uint32_t *bp = nullptr;
+        ChrTable tab{};
         while (__any_sync(0xffffffffu, have)) {
             if (have) {
                 if (fresh) {
                     divmod_idx(slot >> 1, (uint32_t)n_chr, i, c);
-                    r0 = m.row_off[c]; R = m.row_off[c + 1] - r0;
-                    T = m.T + r0 + c;
+                    tab = chr_table(m, c);
+                    bp = m.bp + m.row_off[c];
+                    bp_dist = m.bp_dist[c];
                     key = m.chr_id[c] * 2u + (uint32_t)(slot & 1);
                     j = 0; blk = 0; n = 0; fresh = false;
                 }
@@ -1097,13 +1111,13 @@ __global__ void sample_xo_kernel(Stream st, MapDev m, const StepState *__restric
                 draw(st, P_XO, pop, gen, i, key, blk, w);
                 if (blk == 0) start_hap[slot] = (uint8_t)(w[3] & 1u);
                 blk++;
-                bool done = j >= R;
+                bool done = j >= tab.R;
                 if (!done) {
-                    const double v = (1.0 - u01(w[0], w[1])) * T[j];
-                    const long long k = next_success(m, (int)c, T, R, j, v);
+                    const double v = (1.0 - u01(w[0], w[1])) * __ldg(tab.T + j);
+                    const long long k = next_success(tab, j, v);
                     if (k < 0) done = true;
                     else {
-                        if (n < XO_STASH) stash[slot * XO_STASH + n] = m.bp[r0 + (uint32_t)k] + (uint32_t)(((uint64_t)w[2] * m.bp_dist[c]) >> 32);
+                        if (n < XO_STASH) stash[slot * XO_STASH + n] = __ldg(bp + (uint32_t)k) + (uint32_t)(((uint64_t)w[2] * bp_dist) >> 32);
                         n++;
                         j = (uint32_t)k + 1;
                     }

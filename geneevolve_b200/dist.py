@@ -28,23 +28,57 @@ def assign_chromosomes(weights, world_size):
     return [sorted(m) for m in mine]
 
 
-def assign_locus_ranges(n_loci, world_size, align=128):
+PIECE_COST_CHUNKS = 38   # what one more (chromosome piece, offspring) costs a rank, in 16-byte chunks of row (measured, see assign_locus_ranges)
+
+
+def assign_locus_ranges(n_loci, world_size, align=128, piece_cost=PIECE_COST_CHUNKS):
     """Balanced split of the bit-packed rows: the genome's 16-byte chunks (128 loci) in chromosome order are cut into world_size
-    contiguous runs of equal length (to within one chunk), so a chromosome may span ranks — every rank that holds a slice of it
-    draws that chromosome's crossovers itself (Philox counters are keyed by the global chromosome id, so the lists agree) and no
-    parental row ever crosses a link.  Returns, per rank, a list of (chromosome index, first locus, end locus).  Unlike whole
-    chromosomes (22 of very different lengths) this balances exactly, works with one chromosome and has no rank limit."""
+    contiguous runs, so a chromosome may span ranks — every rank that holds a slice of it draws that chromosome's crossovers itself
+    (Philox counters are keyed by the global chromosome id, so the lists agree) and no parental row ever crosses a link.  Returns, per
+    rank, a list of (chromosome index, first locus, end locus).  Unlike whole chromosomes (22 of very different lengths) this balances,
+    works with one chromosome and has no rank limit.
+
+    What is balanced is the measured cost of a rank, chunks + piece_cost * pieces: every chromosome piece a rank holds costs its copy
+    kernel a fixed amount per offspring (crossover lists staged, short runs, a ragged last tile).  One rank's share of config 3 on a B200
+    (scripts/emulate_rank.py, 8 ranks of 125k loci each): 2 pieces 1.066 ms per generation, 3 pieces 1.09, 4 pieces 1.137, 5 pieces
+    1.170, 6 pieces 1.219 — 0.038 ms per piece against 0.99 ms for the 977 chunks, i.e. 38 chunks per piece; with equal chunk counts the
+    rank holding chromosomes 17-22 set the pace of all eight.  The cuts minimise the largest cost (piece_cost=0: equal chunk counts)."""
     chunks = [(int(n) + align - 1) // align for n in n_loci]
     total = sum(chunks)
-    cuts = [total * r // world_size for r in range(world_size + 1)]
-    out = [[] for _ in range(world_size)]
-    base = 0
-    for c, (nc, nl) in enumerate(zip(chunks, n_loci)):
-        for r in range(world_size):
-            lo, hi = max(cuts[r], base), min(cuts[r + 1], base + nc)
-            if lo < hi:
-                out[r].append((c, (lo - base) * align, min((hi - base) * align, int(nl))))
-        base += nc
+    min_piece = min(8, piece_cost)   # never open a piece for fewer chunks than this unless the chromosome is that short
+
+    def sweep(limit):
+        out = [[] for _ in range(world_size)]
+        r, used = 0, 0
+        for c, nc in enumerate(chunks):
+            pos = 0
+            while pos < nc:
+                if r == world_size - 1:
+                    take = nc - pos
+                else:
+                    room = limit - used - piece_cost
+                    if room < max(1, min(min_piece, nc - pos)):
+                        if used == 0:
+                            return None, None           # the limit does not even hold one piece
+                        r, used = r + 1, 0
+                        continue
+                    take = min(room, nc - pos)
+                out[r].append((c, pos * align, min((pos + take) * align, int(n_loci[c]))))
+                used += piece_cost + take
+                pos += take
+                if r < world_size - 1 and used >= limit:
+                    r, used = r + 1, 0
+        return out, (used if r == world_size - 1 else 0)
+
+    lo, hi = max(1, total // world_size), total + piece_cost * (len(chunks) + world_size)
+    while lo < hi:   # smallest limit under which the last rank is not the most expensive
+        mid = (lo + hi) // 2
+        out, last = sweep(mid)
+        if out is not None and last <= mid:
+            hi = mid
+        else:
+            lo = mid + 1
+    out, _ = sweep(lo)
     return out
 
 

@@ -7,7 +7,8 @@ from geneevolve_b200 import capi, workloads, dist as gdist
 world, steps = int(sys.argv[1]), int(sys.argv[2])
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # e.g. 1 = GE_FLAG_SERIAL: the copy alone, after the control chain
 cfg = workloads.make_workload("config3_100k_x_1M")
-mine = gdist.assign_locus_ranges(cfg["n_loci"], world)[world // 2]
+which = int(sys.argv[4]) if len(sys.argv) > 4 else world // 2          # which rank's share
+mine = gdist.assign_locus_ranges(cfg["n_loci"], world)[which]
 N = cfg["n"]
 eng = capi.Engine(n_pop=1, n_chr=len(mine), n_phen=1, representation=capi.GE_REP_BITS, rng_mode=capi.GE_RNG_PHILOX, seed=12345,
                   capacity=int(N * 1.03) + 1024, rank=0, world_size=world, flags=flags)
@@ -27,4 +28,7 @@ eng.set_profiling(2); eng.reset_kernel_times()
 for g in range(6 + steps, 11 + steps):
     eng.step_generation(g, gp)
 phases = {name: round(eng.kernel_time(pid)[0] / 5, 3) for name, pid in capi.GE_PHASES.items()}
-print(f"world {world}: pieces {mine}: {ms / steps:.3f} ms/step (host wall {wall / steps:.3f}), propagate {k_ms / max(k_n, 1):.3f} ms, launches/step {eng.launch_count() / steps:.0f}, control chain {phases}")
+morgans = 0.0
+for c, s0, s1 in mine:   # expected crossovers per gamete this rank samples: a chromosome it holds any part of is sampled whole
+    morgans += float(cfg["maps"][c][2].sum())
+print(f"world {world} rank {which}: {len(mine)} pieces, {sum(s1 - s0 for _, s0, s1 in mine)} loci, {morgans:.3f} Morgans: {ms / steps:.3f} ms/step (host wall {wall / steps:.3f}), propagate {k_ms / max(k_n, 1):.3f} ms, launches/step {eng.launch_count() / steps:.0f}, control chain {phases}")

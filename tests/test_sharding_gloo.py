@@ -117,19 +117,27 @@ def test_assign_chromosomes_balances():
 
 def test_assign_locus_ranges_balances_and_covers():
     n_loci = [86555, 84425, 68745, 66366, 62807, 59403, 55236, 50808, 49019, 47040, 46866, 46467, 39972, 37246, 35579, 31360, 28165, 27088, 20507, 21861, 16687, 17798]
+    total = sum((n + 127) // 128 for n in n_loci)
     for world in (1, 2, 3, 8, 22, 40):
-        parts = gdist.assign_locus_ranges(n_loci, world)
-        seen = [[] for _ in n_loci]
-        loads = []
-        for pieces in parts:
-            loads.append(sum((s1 - s0 + 127) // 128 for _, s0, s1 in pieces))
-            for c, s0, s1 in pieces:
-                assert s0 % 128 == 0 and s0 < s1 <= n_loci[c]
-                seen[c].append((s0, s1))
-        assert max(loads) - min(loads) <= 1                      # chunks of 16 bytes, to within one
-        for c, iv in enumerate(seen):                            # every locus on exactly one rank
-            iv.sort()
-            assert iv[0][0] == 0 and iv[-1][1] == n_loci[c] and all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
+        for piece_cost in (0, gdist.PIECE_COST_CHUNKS):
+            parts = gdist.assign_locus_ranges(n_loci, world, piece_cost=piece_cost)
+            seen = [[] for _ in n_loci]
+            loads, costs = [], []
+            for pieces in parts:
+                loads.append(sum((s1 - s0 + 127) // 128 for _, s0, s1 in pieces))
+                costs.append(loads[-1] + piece_cost * len(pieces))
+                for c, s0, s1 in pieces:
+                    assert s0 % 128 == 0 and s0 < s1 <= n_loci[c]
+                    seen[c].append((s0, s1))
+            if piece_cost == 0:
+                assert max(loads) == -(-total // world)              # chunks of 16 bytes: no rank above the even share
+            else:                                                    # the most expensive rank is within one piece of the even share
+                assert max(costs) <= (total + piece_cost * (len(n_loci) + world - 1)) / world + piece_cost
+            for c, iv in enumerate(seen):                            # every locus on exactly one rank
+                iv.sort()
+                assert iv[0][0] == 0 and iv[-1][1] == n_loci[c] and all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
+    eight = gdist.assign_locus_ranges(n_loci, 8)                     # the rank with the six short chromosomes holds fewer loci than the rank with two long ones
+    assert len(eight[0]) < len(eight[7]) and sum(s1 - s0 for _, s0, s1 in eight[0]) > sum(s1 - s0 for _, s0, s1 in eight[7])
     assert [len(p) for p in gdist.assign_locus_ranges([500000], 4)] == [1, 1, 1, 1]   # one chromosome spreads over every rank
 
 
