@@ -28,10 +28,15 @@ def assign_chromosomes(weights, world_size):
     return [sorted(m) for m in mine]
 
 
-PIECE_COST_CHUNKS = 38   # what one more (chromosome piece, offspring) costs a rank, in 16-byte chunks of row (measured, see assign_locus_ranges)
+def piece_cost_chunks(chunks_per_rank):
+    """What one more chromosome piece costs a rank's copy kernel, in 16-byte chunks of row (measured, see assign_locus_ranges): it falls
+    with the warps per offspring CTA (ge_api.cu build_genome: one warp per 16 KB of the offspring's two rows, 1..8) because the warps of a
+    CTA work on different pieces side by side — 38 chunks with 2 warps (8 ranks of config 3), 16 with 8 warps (2 ranks)."""
+    warps = min(8, max(1, (32 * int(chunks_per_rank) + 8192) // 16384))
+    return int(round(8.7 + 58.7 / warps))
 
 
-def assign_locus_ranges(n_loci, world_size, align=128, piece_cost=PIECE_COST_CHUNKS):
+def assign_locus_ranges(n_loci, world_size, align=128, piece_cost=None):
     """Balanced split of the bit-packed rows: the genome's 16-byte chunks (128 loci) in chromosome order are cut into world_size
     contiguous runs, so a chromosome may span ranks — every rank that holds a slice of it draws that chromosome's crossovers itself
     (Philox counters are keyed by the global chromosome id, so the lists agree) and no parental row ever crosses a link.  Returns, per
@@ -42,9 +47,13 @@ def assign_locus_ranges(n_loci, world_size, align=128, piece_cost=PIECE_COST_CHU
     kernel a fixed amount per offspring (crossover lists staged, short runs, a ragged last tile).  One rank's share of config 3 on a B200
     (scripts/emulate_rank.py, 8 ranks of 125k loci each): 2 pieces 1.066 ms per generation, 3 pieces 1.09, 4 pieces 1.137, 5 pieces
     1.170, 6 pieces 1.219 — 0.038 ms per piece against 0.99 ms for the 977 chunks, i.e. 38 chunks per piece; with equal chunk counts the
-    rank holding chromosomes 17-22 set the pace of all eight.  The cuts minimise the largest cost (piece_cost=0: equal chunk counts)."""
+    rank holding chromosomes 17-22 set the pace of all eight (8 GPUs: 1.232 ms per generation with equal chunks, 1.170 with equal cost).
+    With 2 ranks the same measurement gives 16 chunks per piece (piece_cost_chunks).  The cuts minimise the largest cost
+    (piece_cost=0: equal chunk counts)."""
     chunks = [(int(n) + align - 1) // align for n in n_loci]
     total = sum(chunks)
+    if piece_cost is None:
+        piece_cost = piece_cost_chunks(total / max(world_size, 1))
     min_piece = min(8, piece_cost)   # never open a piece for fewer chunks than this unless the chromosome is that short
 
     def sweep(limit):

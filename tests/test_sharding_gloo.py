@@ -119,7 +119,7 @@ def test_assign_locus_ranges_balances_and_covers():
     n_loci = [86555, 84425, 68745, 66366, 62807, 59403, 55236, 50808, 49019, 47040, 46866, 46467, 39972, 37246, 35579, 31360, 28165, 27088, 20507, 21861, 16687, 17798]
     total = sum((n + 127) // 128 for n in n_loci)
     for world in (1, 2, 3, 8, 22, 40):
-        for piece_cost in (0, gdist.PIECE_COST_CHUNKS):
+        for piece_cost in (0, gdist.piece_cost_chunks(total / world)):
             parts = gdist.assign_locus_ranges(n_loci, world, piece_cost=piece_cost)
             seen = [[] for _ in n_loci]
             loads, costs = [], []
