@@ -363,6 +363,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="measurement aid: no overlap of the bulk copy with the next generation's control chain")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the short records of the other BASELINE configurations")
+    ap.add_argument("--collective", default="native", choices=["native", "hook"],
+                    help="measurement aid (N > 1): 'hook' routes the all-reduce through a Python callback into torch.distributed instead of the library's own ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

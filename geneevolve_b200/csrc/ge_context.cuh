@@ -169,11 +169,7 @@ struct ge_ctx {
     // control kernels, the 6-25 GB copies of a shard 4 (2-3 % faster than 8 or no limit), copies of ~1 GB (config 2) no limit.
     void note_bulk(double bytes) {
         bulk_busy = !serial && bytes > thin_min_bytes;
-#ifdef GE_EXP_THIN_FULL
-        thin_now = bytes >= 30e9 ? GE_EXP_THIN_FULL : GE_EXP_THIN_SHARD;
-#else
-        thin_now = bytes >= 30e9 ? thin : std::max(1, thin / 2);
-#endif
+        thin_now = bytes >= 30e9 ? thin : std::max(1, thin / 2);   // (re-measured after the control kernels were rebuilt: profiles/r2u_thin_grid_sweep.txt)
     }
     // grid of a grid-stride control kernel: full width, or thin while it shares the GPU with the bulk copy,
     // so that the high-priority control stream displaces only a fraction of the bulk kernel's resident CTAs

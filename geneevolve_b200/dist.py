@@ -194,8 +194,12 @@ def measure_sharded(name, args, steps, warmup, rank, world, local, e2e=True, n=N
         workloads.configure_engine_multipop(eng, cfg, pieces=pieces)
     else:
         workloads.configure_engine(eng, cfg, pieces=pieces)
-    comm = NcclComm(rank, world, local)
-    eng.set_allreduce_nccl(comm.handle, comm.all_reduce_address)
+    comm = None
+    if getattr(args, "collective", "native") == "hook":   # measurement aid: the Python hook into torch.distributed instead
+        eng.set_allreduce(cuda_allreduce_hook(local))
+    else:
+        comm = NcclComm(rank, world, local)
+        eng.set_allreduce_nccl(comm.handle, comm.all_reduce_address)
     eng.init_generation0()
     gp = [capi.gen_params(q, cfg["mat_cor"], "p", "logit", 0.0, 1.0) for q in pops]
     mig = cfg.get("migration")
@@ -257,7 +261,8 @@ def measure_sharded(name, args, steps, warmup, rank, world, local, e2e=True, n=N
     r["device_memory_gb"] = eng.device_memory_bytes() / 1e9
     r["graph_replays"] = eng.graph_replays()
     eng.close()
-    comm.close()
+    if comm:
+        comm.close()
     return r
 
 
