@@ -124,11 +124,13 @@ static int build_genome(ge_ctx *ctx) {
     GE_TRY(ctx->upload(ctx->d_bkt_off, bkt_off)); GE_TRY(ctx->upload(ctx->d_bkt_shift, bkt_shift)); GE_TRY(ctx->upload(ctx->d_bkt, bkt));
     // tile table: (chromosome, first chunk, chunk count), longest first so the warps of a CTA balance
     // 16-byte chunks per work item; smaller when this context owns few chromosomes (a shard of a multi-GPU run), so that
-    // the 8 warps of a CTA still find a dozen items per offspring
+    // the warps of a CTA (1-8 by row length, below) still find a few items each per offspring
     uint64_t chunks_per_gamete = 0;
     for (int c = 0; c < C; c++) chunks_per_gamete += ((ctx->chr_nloci[c] + 31) / 32 + 3) / 4;
     uint32_t TILE = 1024;  // 16 KB; measured 0.7 % better than 8 KB on the whole genome, 4 KB and 2 KB are 2 % worse
-    while (TILE > 64 && chunks_per_gamete / TILE < 6) TILE >>= 1;
+    // (one rank's share of config 3, 8 / 4 ranks, at least 1 / 3 / 6 / 12 items per gamete: 1.111 / 1.107 / 1.117 / 1.367 and 1.929 / 1.929 / 1.972 / 2.036 ms
+    //  per generation — profiles/r2G_tile_rule.txt)
+    while (TILE > 64 && chunks_per_gamete / TILE < 3) TILE >>= 1;
     struct Item { uint32_t c, q0, nq; };
     std::vector<Item> items;
     for (int c = 0; c < C; c++) {
