@@ -1316,9 +1316,17 @@ static int step_with_graph(ge_ctx *ctx, int gen, const ge_gen_params *gp, int &r
         G.epoch = ctx->graph_epoch;
     }
     bool dummy = false;
-    if (!G.exec && G.warm < 1) {   // first pass with this key: queued kernel by kernel (it may still allocate)
+    // The first generation of a context is queued kernel by kernel (it may still allocate), and so is the first pass of a key if no
+    // such generation has completed since a buffer last moved; after that a key is recorded the first time it comes up, so that the
+    // two buffer parities are graphs from the third generation on (a bench with three warm-up steps times replays only).
+    const bool settled = ctx->plain_epoch == ctx->graph_epoch && ctx->plain_gens >= 1;
+    if (!G.exec && (G.warm < 0 || (G.warm < 1 && !settled))) {
         int rc = enqueue_generation(ctx, gen, gp, nullptr, nullptr, reproduced, dummy);
-        if (rc == GE_OK && G.warm >= 0 && ctx->graph_epoch == G.epoch) G.warm++;
+        if (rc == GE_OK && ctx->graph_epoch == G.epoch) {
+            G.warm++;
+            if (ctx->plain_epoch != ctx->graph_epoch) { ctx->plain_epoch = ctx->graph_epoch; ctx->plain_gens = 0; }
+            ctx->plain_gens++;
+        }
         return rc;
     }
     if (!G.exec) {   // record
@@ -1333,10 +1341,10 @@ static int step_with_graph(ge_ctx *ctx, int gen, const ge_gen_params *gp, int &r
         if (e == cudaSuccess) e = cudaStreamEndCapture(ctx->stream, &g);
         ctx->capturing = false;
         if (rc == GE_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&G.exec, g, 0);
-        if (rc != GE_OK || e != cudaSuccess || !G.exec) {   // not capturable after all: back to plain launches, for good
+        if (rc != GE_OK || e != cudaSuccess || !G.exec) {   // not capturable (yet): back to plain launches — two more plain passes, then for good
             cudaGetLastError();
             if (g) cudaGraphDestroy(g);
-            G.exec = nullptr; G.warm = -1000000;
+            G.exec = nullptr; G.warm = ++G.fails >= 3 ? -1000000 : -2;
             ctx->deferred.clear();
             ctx->launches = launches0;
             for (int p = 0; p < np; p++) { ctx->pop[p].cur = saved[p].cur; ctx->pop[p].dcur = saved[p].dcur; }

@@ -244,9 +244,12 @@ struct ge_ctx {
         std::vector<cudaGraphNode_t> begin_nodes;      // the step_begin_kernel node of every population: the one parameter update per replay
         std::vector<std::function<int()>> bulk;        // what follows every launch on the bulk stream (it runs a generation behind)
         uint64_t launches = 0, epoch = 0;
-        int warm = 0;                                  // eager runs of this key since the buffers last moved
+        int warm = 0;                                  // eager runs of this key since the buffers last moved (negative: after a failed recording)
+        int fails = 0;
     };
     std::map<std::string, StepGraph> graphs;
+    uint64_t plain_epoch = ~0ull;                      // graph_epoch at which plain_gens generations were queued kernel by kernel
+    int plain_gens = 0;
     bool capturing = false;
     std::vector<std::function<int()>> deferred;
     void drop_graphs();

@@ -14,7 +14,6 @@
 #pragma once
 #include "ge_context.cuh"
 
-#include <cub/block/block_radix_sort.cuh>
 
 namespace gek {
 
@@ -229,36 +228,49 @@ __global__ void remainder_add_kernel(const StepState *__restrict__ ss, const uin
 // Stable sorts of (uint64 key, uint32 value) pairs with the element count on the device.  The mating chain sorts <= N/2 pairs
 // five times per generation and sits on the dependency cycle mating -> draws -> CV planes -> genetic values -> phenotypes ->
 // selection -> mating: a library radix sort is ten dependent launches and wants its count on the host.
-// Here: tiles of 4096 pairs are sorted by one CTA each (cub::BlockRadixSort in shared memory), then merged by rank — every
-// element finds its final position by binary searches of the other runs of its group (up to 32 runs per level):
-// rank = position in its run + #(<= key) in earlier runs + #(< key) in later runs, which keeps the sort stable.
-// One launch up to 4096 pairs, two up to 131 072, three up to 4 194 304.
+// Here: tiles of 4096 pairs are sorted by one CTA each, then merged by rank — every element finds its final position by binary
+// searches of the other runs of its group (up to 32 runs per level): rank = position in its run + #(<= key) in earlier runs +
+// #(< key) in later runs, which keeps the sort stable.  One launch up to 4096 pairs, two up to 131 072, three up to 4 194 304, ...
+// The tile sort is a bitonic network on (key, position in the tile) in shared memory — the position makes the order total, so
+// the network's instability cannot show; values are gathered by position at the end.  It replaces cub::BlockRadixSort on tiles
+// of the same size (sixteen 4-bit passes over 64-bit keys): 78 compare-exchange steps, most of them warp-local.
 // ------------------------------------------------------------------------------------------------
 namespace gek {
-constexpr int SS_THREADS = 512, SS_ITEMS = 8, SS_TILE = SS_THREADS * SS_ITEMS;
 constexpr uint32_t SS_GROUP = 32;
 
+// (SS_THREADS, SS_TILE) = (1024, 4096), or (512, 2048) for lists of at most four such tiles: a 2048-network is done in 7 us instead of
+// 16 (config 2, 5 700 pairs per list: 0.408 against 0.443 ms per generation), but twice the runs cost the merge of a long list more
+// than that — its dependent probes go to L2 beside the bulk copy (config 3, 52 000 pairs: mating phase 0.48 against 0.44 ms)
+template <int SS_THREADS, int SS_TILE>
 __global__ void __launch_bounds__(SS_THREADS) small_sort_tile_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                                                      uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, DevN dn) {
-    using Sort = cub::BlockRadixSort<uint64_t, SS_THREADS, SS_ITEMS, uint32_t>;
-    __shared__ typename Sort::TempStorage tmp;
+    __shared__ uint64_t sk[SS_TILE];
+    __shared__ uint16_t sp[SS_TILE];
     const uint32_t n = (uint32_t)dn.get();
     const uint32_t base = blockIdx.x * SS_TILE;
     if (base >= n) return;
-    uint64_t k[SS_ITEMS];
-    uint32_t v[SS_ITEMS];
-#pragma unroll
-    for (int j = 0; j < SS_ITEMS; j++) {   // blocked arrangement; padding sorts last (and, the sort being stable, after real all-ones keys)
-        const uint32_t idx = base + threadIdx.x * SS_ITEMS + j;
-        k[j] = idx < n ? kin[idx] : ~0ull;
-        v[j] = idx < n ? vin[idx] : 0xFFFFFFFFu;
+    const uint32_t cnt = min((uint32_t)SS_TILE, n - base);
+    uint32_t m = 64;   // the network's size: the power of two that holds the tile's pairs (padding sorts last: all-ones key, later position)
+    while (m < cnt) m <<= 1;
+    for (uint32_t t = threadIdx.x; t < m; t += SS_THREADS) { sk[t] = t < cnt ? kin[base + t] : ~0ull; sp[t] = (uint16_t)t; }
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t p = threadIdx.x; p < (m >> 1); p += SS_THREADS) {
+                const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i | j;
+                const uint64_t a = sk[i], b = sk[l];
+                const uint16_t pa = sp[i], pb = sp[l];
+                const bool gt = a > b || (a == b && pa > pb);
+                if (gt == ((i & k) == 0)) { sk[i] = b; sk[l] = a; sp[i] = pb; sp[l] = pa; }
+            }
+            // pairs at distance j <= 32 stay inside the 64 elements one warp's 32 pair indices cover: a warp barrier orders them; the
+            // step after this one decides (the first step of the next phase is at distance k)
+            const uint32_t next_j = j > 1 ? (j >> 1) : k;
+            if (j > 32 || next_j > 32) __syncthreads(); else __syncwarp();
+        }
     }
-    Sort(tmp).Sort(k, v);
-#pragma unroll
-    for (int j = 0; j < SS_ITEMS; j++) {
-        const uint32_t idx = base + threadIdx.x * SS_ITEMS + j;
-        if (idx < n) { kout[idx] = k[j]; vout[idx] = v[j]; }
-    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < cnt; t += SS_THREADS) { kout[base + t] = sk[t]; vout[base + t] = vin[base + sp[t]]; }
 }
 
 // sorted runs of run_len pairs -> sorted runs of run_len * SS_GROUP pairs
@@ -284,30 +296,35 @@ __global__ void small_sort_merge_kernel(const uint64_t *__restrict__ tk, const u
 }
 }  // namespace gek
 
-constexpr uint64_t SORT_MAX = (uint64_t)gek::SS_TILE * gek::SS_GROUP * gek::SS_GROUP;   // 4 194 304 pairs
+constexpr uint64_t SORT_MAX = 1ull << 31;   // element indices are 32 bits in the kernels above
 
 // keys_in/vals_in -> keys_out/vals_out; n on the device, n_bound (host) sizes the grids and the scratch
 static int sort_pairs_on(ge_ctx *ctx, cudaStream_t st, Buf &tmp, const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, DevN n, uint64_t n_bound) {
     if (n_bound == 0) return GE_OK;
-    if (n_bound > SORT_MAX) return fail(GE_ERR_UNSUPPORTED, "more than 4 194 304 list entries to sort (capacity above 8 388 608 individuals)");
+    if (n_bound > SORT_MAX) return fail(GE_ERR_UNSUPPORTED, "more than 2^31 list entries to sort");
     n = limited(n, n_bound);
+    const bool small = n_bound <= 4 * 2048;
+    const uint64_t SS_TILE = small ? 2048 : 4096;
     const unsigned tiles = nblk(n_bound, SS_TILE);
-    if (tiles == 1) {
-        small_sort_tile_kernel<<<1, SS_THREADS, 0, st>>>(kin, vin, kout, vout, n);
+    auto tile_sort = [&](uint64_t *ko, uint32_t *vo) {
+        if (small) small_sort_tile_kernel<512, 2048><<<tiles, 512, 0, st>>>(kin, vin, ko, vo, n);
+        else small_sort_tile_kernel<1024, 4096><<<tiles, 1024, 0, st>>>(kin, vin, ko, vo, n);
         return ctx->check_launch("small_sort_tile");
-    }
+    };
+    if (tiles == 1) return tile_sort(kout, vout);
+    int levels = 0;   // merge levels: runs of SS_TILE * 32^levels pairs cover the bound
+    for (uint64_t run = SS_TILE; run < n_bound; run *= SS_GROUP) levels++;
     GE_TRY(ctx->ensure(tmp, 2 * (n_bound * 12 + 16)));
     uint64_t *ak = tmp.as<uint64_t>(), *bk = ak + n_bound;
     uint32_t *av = reinterpret_cast<uint32_t *>(bk + n_bound), *bv = av + n_bound;
-    const bool two_levels = tiles > SS_GROUP;
-    small_sort_tile_kernel<<<tiles, SS_THREADS, 0, st>>>(kin, vin, ak, av, n);
-    GE_TRY(ctx->check_launch("small_sort_tile"));
+    GE_TRY(tile_sort(ak, av));
     const unsigned mgrid = (unsigned)std::min<uint64_t>(nblk(n_bound, 256), 65535);
-    small_sort_merge_kernel<<<mgrid, 256, 0, st>>>(ak, av, two_levels ? bk : kout, two_levels ? bv : vout, n, SS_TILE);
-    GE_TRY(ctx->check_launch("small_sort_merge"));
-    if (two_levels) {
-        small_sort_merge_kernel<<<mgrid, 256, 0, st>>>(bk, bv, kout, vout, n, SS_TILE * SS_GROUP);
+    uint64_t run = SS_TILE;
+    for (int lv = 0; lv < levels; lv++, run *= SS_GROUP) {   // a -> b -> a ...; the last level writes the caller's arrays
+        const bool last = lv == levels - 1;
+        small_sort_merge_kernel<<<mgrid, 256, 0, st>>>(ak, av, last ? kout : bk, last ? vout : bv, n, (uint32_t)std::min<uint64_t>(run, 1u << 31));
         GE_TRY(ctx->check_launch("small_sort_merge"));
+        std::swap(ak, bk); std::swap(av, bv);
     }
     return GE_OK;
 }
