@@ -192,6 +192,15 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+SETTLE = 6   # untimed generations before any timed region, at least: the library records its two generation graphs (with the NCCL
+             # collective inside on a sharded run: tens of milliseconds of capture and instantiation) once its buffers stop moving
+
+
+def untimed_generations(warmup):
+    """The W warm-up steps, or SETTLE of them when W is smaller (reported as config.untimed_generations_before_timing)."""
+    return max(int(warmup), SETTLE)
+
+
 def measure_workload(name, local, steps, warmup, n=None, loci=None, e2e=True, phases_steps=5, flags=0):
     """One single-GPU workload through the C-ABI: device-resident arm, end-to-end arm, dominant-kernel roofline (CUDA events on the
     kernel's own stream inside the timed region) and, in a short extra pass, the phases of the control chain."""
@@ -201,6 +210,7 @@ def measure_workload(name, local, steps, warmup, n=None, loci=None, e2e=True, ph
     M, N = sum(cfg["n_loci"]), cfg["n"]
     cap = int(max(N, cfg["founders"]) * 1.03) + 1024
     segs = bool(cfg.get("segments"))
+    warmup = untimed_generations(warmup)
     total_steps = warmup + steps * (2 if e2e else 1) + phases_steps
     seg_cap = 0
     if segs:  # parts per haplotype-genome after g generations ~ n_chr + g * (map length in Morgans)
@@ -328,13 +338,14 @@ def ours(args):
                    "selection": "logit(0,1)", "h2": 0.5, "rng": "philox4x32-10 on device",
                    "l2": ("inputs larger than L2 (%.1f GB of parental rows per step vs 126 MB)" % (N * M / 4 / 1e9)) if not segs else
                          "inputs larger than L2 (founder-segment lists, %.1f GB written per step)" % (r["k_bytes"] / max(r["k_n"], 1) / 2e9),
-                   "representation": "founder segments (loci nominal; cost grows with the generation: steps are generations %d..%d)" % (args.warmup + 1, args.warmup + args.steps)
+                   "representation": "founder segments (loci nominal; cost grows with the generation: steps are generations %d..%d)" % (untimed_generations(args.warmup) + 1, untimed_generations(args.warmup) + args.steps)
                    if segs else "bit-packed haplotypes",
+                   "untimed_generations_before_timing": untimed_generations(args.warmup),
                    "device_memory_gb": r["device_memory_gb"], "individual_generations_per_s": value / M,
                    "scaling_note": "the workload is fixed; --gpus N splits its loci over N ranks"},
         "e2e": {"value": r["work2"] / (r["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40, "d2h_bytes_per_step": r["d2h"],
                 "ms_per_step": r["ms_e2e"] / args.steps, "checksum": r["checksum"], "state_hash": r["state_hash"],
-                "generations_simulated": args.warmup + 2 * args.steps,
+                "generations_simulated": untimed_generations(args.warmup) + 2 * args.steps,
                 "note": "generation state stays in HBM between steps by design (as it stays in process memory in the reference); per step the host sends the "
                         "generation-table row and receives every individual's .info columns in pinned memory; state_hash = crc32 of pedigree, sex and couples "
                         "after generations_simulated generations (equal across --gpus N when the sharded runs simulated the same populations)"},

@@ -171,6 +171,7 @@ def measure_sharded(name, args, steps, warmup, rank, world, local, e2e=True, n=N
     from . import capi, workloads
     import bench
     cfg = workloads.make_workload(name, n_override=n, loci_override=loci)
+    warmup = bench.untimed_generations(warmup)
     segs = bool(cfg.get("segments"))
     if segs:
         if len(cfg["chrs"]) < world:
@@ -309,7 +310,8 @@ def bench_sharded(args, METRIC, UNIT):
             "config": {"workload": args.workload, "individuals": sum(pops), "populations": pops, "phenotypes": n_phen, "loci": M, "chromosomes": len(cfg["chrs"]),
                        "parallelism": ("chromosome-sharded x%d (founder segments)" if segs else "locus-range sharded x%d (every rank: all individuals, 1/N of the 16-byte chunks of the rows)") % world,
                        "device_memory_gb_rank0": r["device_memory_gb"],
-                       "representation": "founder segments (loci nominal; steps are generations %d..%d)" % (args.warmup + 1, args.warmup + args.steps) if segs else "bit-packed haplotypes",
+                       "representation": "founder segments (loci nominal; steps are generations %d..%d)" % (bench.untimed_generations(args.warmup) + 1, bench.untimed_generations(args.warmup) + args.steps) if segs else "bit-packed haplotypes",
+                       "untimed_generations_before_timing": bench.untimed_generations(args.warmup),
                        "pieces_rank0": r["pieces"], "collective": "all-reduce of 3 * n_phen * capacity doubles per population and generation (ncclAllReduce issued by the CUDA library on its control stream, inside the captured generation graph when the chain is graphable)",
                        "graph_replays_rank0": r["graph_replays"],
                        "l2": ("inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (sum(pops) * M / 4 / 1e9 / world)) if not segs else
@@ -317,7 +319,7 @@ def bench_sharded(args, METRIC, UNIT):
             "e2e": {"value": r["work2"] / (r["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,
                     "d2h_bytes_per_step": sum(capi.Engine.individual_bytes(q, n_phen) for q in pops), "ms_per_step": r["ms_e2e"] / args.steps,
                     "checksum": r["checksum"], "state_hash": r["hashes"][0], "state_hash_equal_on_all_ranks": len(set(r["hashes"])) == 1,
-                    "generations_simulated": args.warmup + 2 * args.steps},
+                    "generations_simulated": bench.untimed_generations(args.warmup) + 2 * args.steps},
             "gpu_launches": r["launches"],
             "roofline": sharded_roofline(r),
             "clocks": r["clocks"], "cpu_baseline": cpu_base}
