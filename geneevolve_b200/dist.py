@@ -195,12 +195,21 @@ def measure_sharded(name, args, steps, warmup, rank, world, local, e2e=True, n=N
         workloads.configure_engine_multipop(eng, cfg, pieces=pieces)
     else:
         workloads.configure_engine(eng, cfg, pieces=pieces)
-    comm = None
-    if getattr(args, "collective", "native") == "hook":   # measurement aid: the Python hook into torch.distributed instead
+    comm, collective = None, "hook"
+    if getattr(args, "collective", "native") != "hook":
+        # every rank must take the same path: a rank that cannot build its communicator (libnccl.so.2 not loadable by soname) says so first
+        try:
+            lib_ok = 1 if ctypes.CDLL("libnccl.so.2") else 0
+        except OSError:
+            lib_ok = 0
+        flag = torch.tensor([lib_ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            comm = NcclComm(rank, world, local)
+            eng.set_allreduce_nccl(comm.handle, comm.all_reduce_address)
+            collective = "native"
+    if comm is None:   # the Python hook into torch.distributed (also NCCL): measurement aid, or the NCCL library is not reachable from ctypes
         eng.set_allreduce(cuda_allreduce_hook(local))
-    else:
-        comm = NcclComm(rank, world, local)
-        eng.set_allreduce_nccl(comm.handle, comm.all_reduce_address)
     eng.init_generation0()
     gp = [capi.gen_params(q, cfg["mat_cor"], "p", "logit", 0.0, 1.0) for q in pops]
     mig = cfg.get("migration")
@@ -261,6 +270,7 @@ def measure_sharded(name, args, steps, warmup, rank, world, local, e2e=True, n=N
     r["k_ms_slowest"] = float(kmax[1].item())
     r["device_memory_gb"] = eng.device_memory_bytes() / 1e9
     r["graph_replays"] = eng.graph_replays()
+    r["collective"] = collective
     eng.close()
     if comm:
         comm.close()
@@ -313,7 +323,7 @@ def bench_sharded(args, METRIC, UNIT):
                        "representation": "founder segments (loci nominal; steps are generations %d..%d)" % (bench.untimed_generations(args.warmup) + 1, bench.untimed_generations(args.warmup) + args.steps) if segs else "bit-packed haplotypes",
                        "untimed_generations_before_timing": bench.untimed_generations(args.warmup),
                        "pieces_rank0": r["pieces"], "collective": "all-reduce of 3 * n_phen * capacity doubles per population and generation (ncclAllReduce issued by the CUDA library on its control stream, inside the captured generation graph when the chain is graphable)",
-                       "graph_replays_rank0": r["graph_replays"],
+                       "graph_replays_rank0": r["graph_replays"], "collective_path": r["collective"],
                        "l2": ("inputs larger than L2 (%.1f GB of parental rows per step per GPU)" % (sum(pops) * M / 4 / 1e9 / world)) if not segs else
                              "inputs larger than L2 (founder-segment lists, %.1f GB moved per step per GPU)" % (r["k_bytes"] / max(r["k_n"], 1) * 2 / 1e9)},
             "e2e": {"value": r["work2"] / (r["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 40 * world,
