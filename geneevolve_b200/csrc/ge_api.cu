@@ -168,29 +168,25 @@ static std::vector<double> survival_table(const std::vector<double> &p, size_t f
     return T;
 }
 
-// value index of one survival table for next_success (ge_kernels.cuh): first(b) = first row k with T[k+1] < 1 - b/scale; entry b holds
-// the search window {first(b - 1), first(b + 2)} of bucket b, clamped to the buckets 0 .. B
-static void value_index(const std::vector<double> &T, std::vector<uint2> &vb, double &scale) {
+// value index of one survival table for next_success (ge_kernels.cuh): entry b = first row k with T[k+1] < 1 - b/scale
+static void value_index(const std::vector<double> &T, std::vector<uint32_t> &vb, double &scale) {
     const size_t R = T.size() - 1;
     const size_t B = std::max<size_t>(16, 2 * R);
     const double span = 1.0 - T[R];
     scale = span > 0 ? (double)B / span : 0.0;
-    std::vector<uint32_t> first;
     size_t k = 0;
     for (size_t b = 0; b <= B; b++) {
         const double v_hi = scale > 0 ? 1.0 - (double)b / scale : 1.0;
         while (k < R && !(T[k + 1] < v_hi)) k++;
-        first.push_back((uint32_t)std::min(k, R > 0 ? R - 1 : 0));
+        vb.push_back((uint32_t)std::min(k, R > 0 ? R - 1 : 0));
     }
-    for (size_t b = 0; b <= B; b++) vb.push_back(make_uint2(first[b > 0 ? b - 1 : 0], first[std::min(b + 2, B)]));
 }
 
 static int build_maps(ge_ctx *ctx, PopDev &P) {
     int C = ctx->cfg.n_chr;
     std::vector<uint32_t> row_off(C + 1, 0), bp, dist, cov_lo(C), cov_hi(C);
     std::vector<double> T, vscale(C, 0.0);
-    std::vector<uint2> vb;
-    std::vector<uint32_t> vb_off(C + 1, 0);
+    std::vector<uint32_t> vb, vb_off(C + 1, 0);
     for (int c = 0; c < C; c++) {
         if (P.rmap_bp[c].size() < 2) return fail(GE_ERR_INVALID, "genetic map of a chromosome is missing (ge_set_genetic_map)");
         for (uint64_t v : P.rmap_bp[c]) { if (v > 0xFFFFFFFFull) return fail(GE_ERR_UNSUPPORTED, "map position does not fit 32 bits"); bp.push_back((uint32_t)v); }
@@ -206,8 +202,7 @@ static int build_maps(ge_ctx *ctx, PopDev &P) {
     GE_TRY(ctx->upload(P.d_vb, vb)); GE_TRY(ctx->upload(P.d_vb_off, vb_off)); GE_TRY(ctx->upload(P.d_vb_scale, vscale));
     GE_TRY(ctx->upload(P.d_bp_dist, dist)); GE_TRY(ctx->upload(P.d_cov_lo, cov_lo)); GE_TRY(ctx->upload(P.d_cov_hi, cov_hi));
     if (P.has_mut) {
-        std::vector<uint32_t> mro(C + 1, 0), mbp, mvb_off(C + 1, 0); std::vector<double> mT, mvscale(C, 0.0);
-        std::vector<uint2> mvb;
+        std::vector<uint32_t> mro(C + 1, 0), mbp, mvb, mvb_off(C + 1, 0); std::vector<double> mT, mvscale(C, 0.0);
         for (int c = 0; c < C; c++) {
             for (uint64_t v : P.mutmap_bp[c]) mbp.push_back((uint32_t)v);
             mro[c + 1] = (uint32_t)mbp.size();

@@ -354,13 +354,13 @@ struct ge_ctx {
     }
     MapDev rmap(const PopDev &P) const {
         MapDev m; m.row_off = P.d_row_off.as<uint32_t>(); m.bp = P.d_bp.as<uint32_t>(); m.T = P.d_T.as<double>(); m.bp_dist = P.d_bp_dist.as<uint32_t>();
-        m.vb = P.d_vb.as<uint2>(); m.vb_off = P.d_vb_off.as<uint32_t>(); m.vb_scale = P.d_vb_scale.as<double>();
+        m.vb = P.d_vb.as<uint32_t>(); m.vb_off = P.d_vb_off.as<uint32_t>(); m.vb_scale = P.d_vb_scale.as<double>();
         m.chr_id = d_chr_ids.as<uint32_t>();
         return m;
     }
     MapDev mmap(const PopDev &P) const {
         MapDev m; m.row_off = P.d_mrow_off.as<uint32_t>(); m.bp = P.d_mbp.as<uint32_t>(); m.T = P.d_mT.as<double>(); m.bp_dist = nullptr;
-        m.vb = P.d_mvb.as<uint2>(); m.vb_off = P.d_mvb_off.as<uint32_t>(); m.vb_scale = P.d_mvb_scale.as<double>();
+        m.vb = P.d_mvb.as<uint32_t>(); m.vb_off = P.d_mvb_off.as<uint32_t>(); m.vb_scale = P.d_mvb_scale.as<double>();
         m.chr_id = d_chr_ids.as<uint32_t>();
         return m;
     }

@@ -1037,11 +1037,10 @@ struct MapDev {
     const uint32_t *row_off;  // [n_chr+1] offsets into bp (rows per chromosome)
     const uint32_t *bp;       // concatenated map rows
     const double *T;          // concatenated survival tables, chromosome c starts at row_off[c] + c (R_c + 1 entries)
-    // value index of T (exact acceleration of the search below): with first(b) = first row k with T[k+1] < 1 - b / vb_scale[c],
-    // entry vb_off[c] + b holds the search window of bucket b, {first(b - 1), first(b + 2)} (one bucket of slack either side, clamped
-    // to 0 .. B_c), b = 0 .. B_c where B_c = vb_off[c+1] - vb_off[c] - 1: one 8-byte load per draw
+    // value index of T (exact acceleration of the search below): vb[vb_off[c] + b] = first row k with
+    // T[k+1] < 1 - b / vb_scale[c], b = 0 .. B_c where B_c = vb_off[c+1] - vb_off[c] - 1
     const uint32_t *vb_off;   // [n_chr+1]
-    const uint2 *vb;
+    const uint32_t *vb;
     const double *vb_scale;   // [n_chr]
     const uint32_t *bp_dist;  // [n_chr]
     const uint32_t *chr_id;   // [n_chr] index in the full genome (Philox counter; differs from c on a sharded context)
@@ -1050,7 +1049,7 @@ struct MapDev {
 // answer is max(j, k_g).  k_g lies between the index entries of v's bucket; one bucket of slack on either side absorbs
 // the rounding of the bucket number, and the binary search over that range returns exactly what a search over [0, R) would.
 // (the constants of the chromosome come in registers: the sampler is bound by its load instructions, profiles/README.md r2r)
-struct ChrTable { const double *T; const uint2 *vb; double T_last, vb_scale; uint32_t R, B; };
+struct ChrTable { const double *T; const uint32_t *vb; double T_last, vb_scale; uint32_t R, B; };
 __device__ __forceinline__ ChrTable chr_table(const MapDev &m, uint32_t c) {
     ChrTable t;
     const uint32_t r0 = m.row_off[c], v0 = m.vb_off[c];
@@ -1062,22 +1061,14 @@ __device__ __forceinline__ ChrTable chr_table(const MapDev &m, uint32_t c) {
     t.vb_scale = m.vb_scale[c];
     return t;
 }
-// T_next: T[k + 1] of the returned row k when the search happened to read it (what the next draw of the slot multiplies by), else < 0
-__device__ __forceinline__ long long next_success(const ChrTable &t, uint32_t j, double v, double &T_next) {
-    T_next = -1.0;
+__device__ __forceinline__ long long next_success(const ChrTable &t, uint32_t j, double v) {
     if (j >= t.R || !(t.T_last < v)) return -1;
     const uint32_t b = (uint32_t)fmin((1.0 - v) * t.vb_scale, (double)(t.B - 1));
-    const uint2 w = __ldg(t.vb + b);
-    uint32_t lo = w.x, hi = w.y;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const double Tm = __ldg(t.T + mid + 1);
-        if (Tm < v) { hi = mid; T_next = Tm; } else lo = mid + 1;
-    }
-    if (lo < j) { lo = j; T_next = -1.0; }
+    uint32_t lo = __ldg(t.vb + (b > 0 ? b - 1 : 0)), hi = __ldg(t.vb + min(b + 2, t.B));
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(t.T + mid + 1) < v) hi = mid; else lo = mid + 1; }
+    if (lo < j) lo = j;
     return (long long)lo;
 }
-__device__ __forceinline__ long long next_success(const ChrTable &t, uint32_t j, double v) { double unused; return next_success(t, j, v, unused); }
 __device__ __forceinline__ long long next_success(const MapDev &m, int c, const double *, uint32_t, uint32_t j, double v) { return next_success(chr_table(m, (uint32_t)c), j, v); }
 // Counts the crossovers of every slot, writes start_hap and stashes the first XO_STASH positions at a fixed stride; after
 // the scan, xo_place_kernel moves the stash into the CSR (re-drawing only the rare longer lists) and converts positions to
@@ -1087,7 +1078,7 @@ __device__ __forceinline__ long long next_success(const MapDev &m, int c, const 
 // lane whose slot is finished picks the next free slot of the chunk at the end of the round (ballot + rank), so every lane draws in
 // every round until the chunk runs dry.  The draws are keyed by (individual, chromosome, gamete, block): the schedule cannot change them.
 constexpr int XO_STASH = 8;
-__global__ void __launch_bounds__(128, 10) sample_xo_kernel(Stream st, MapDev m, const StepState *__restrict__ ss, int n_chr, int pop, uint32_t *__restrict__ count,
+__global__ void sample_xo_kernel(Stream st, MapDev m, const StepState *__restrict__ ss, int n_chr, int pop, uint32_t *__restrict__ count,
                                  uint8_t *__restrict__ start_hap, uint32_t *__restrict__ stash) {
     if (ss->err & SE_FATAL) return;
     const uint64_t n_slots = ss->n_off * (uint64_t)n_chr * 2;
@@ -1105,7 +1096,6 @@ __global__ void __launch_bounds__(128, 10) sample_xo_kernel(Stream st, MapDev m,
         bool have = slot < end, fresh = have;
         uint32_t c = 0, j = 0, blk = 0, n = 0, key = 0, bp_dist = 0;
         const uint32_t *bp = nullptr;
-        double Tj = -1.0;   // T[j] when the last search read it
         ChrTable tab{};
         while (__any_sync(0xffffffffu, have)) {
             if (have) {
@@ -1116,7 +1106,6 @@ __global__ void __launch_bounds__(128, 10) sample_xo_kernel(Stream st, MapDev m,
                     bp_dist = m.bp_dist[c];
                     key = m.chr_id[c] * 2u + (uint32_t)(slot & 1);
                     j = 0; blk = 0; n = 0; fresh = false;
-                    Tj = -1.0;
                 }
                 uint32_t w[4];
                 draw(st, P_XO, pop, gen, i, key, blk, w);
@@ -1124,8 +1113,8 @@ __global__ void __launch_bounds__(128, 10) sample_xo_kernel(Stream st, MapDev m,
                 blk++;
                 bool done = j >= tab.R;
                 if (!done) {
-                    const double v = (1.0 - u01(w[0], w[1])) * (Tj >= 0.0 ? Tj : __ldg(tab.T + j));
-                    const long long k = next_success(tab, j, v, Tj);
+                    const double v = (1.0 - u01(w[0], w[1])) * __ldg(tab.T + j);
+                    const long long k = next_success(tab, j, v);
                     if (k < 0) done = true;
                     else {
                         if (n < XO_STASH) stash[slot * XO_STASH + n] = __ldg(bp + (uint32_t)k) + (uint32_t)(((uint64_t)w[2] * bp_dist) >> 32);
